@@ -1,0 +1,1596 @@
+/*
+ * mskc_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Line-faithful plain-C restatement of the MulSKIPS KMC event loop.  Every
+ * function cites the reference file:line it follows ("src/" =
+ * /root/reference/mulskips-source).  Nothing under mulskips_b200/ or include/
+ * links, loads or calls this file; see oracle/mskc_oracle.h for who may.
+ *
+ * Build with -ffp-contract=off (no FMA contraction) so that the double
+ * arithmetic is the plain IEEE sequence gfortran -O emits for the reference.
+ */
+#include "mskc_oracle.h"
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ util */
+static void orc_fatal(Orc *o, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(o->errmsg, sizeof o->errmsg, fmt, ap); va_end(ap);
+  o->fatal = 1;
+  if (o->log) fprintf(o->log, " %s\n", o->errmsg);
+  fprintf(stderr, "oracle STOP: %s\n", o->errmsg);
+  if (o->jb_set) longjmp(o->jb, 1);
+  exit(3);
+}
+#define LOG(o, ...) do { if ((o)->log) fprintf((o)->log, __VA_ARGS__); } while (0)
+
+static inline int IBITS(int32_t w, int pos, int len) { return (int)(((uint32_t)w >> pos) & ((1u << len) - 1u)); }
+static inline void MVBITS(int from, int len, int32_t *to, int pos) {
+  uint32_t m = ((1u << len) - 1u);
+  *to = (int32_t)(((uint32_t)*to & ~(m << pos)) | (((uint32_t)from & m) << pos));
+}
+/* cell index with the bounds the Fortran arrays have (0:LenX-1,0:LenY-1,0:LenZ); out of
+ * range -> scratch cell + counter (the reference would read foreign memory there) */
+static inline size_t CI(Orc *o, int x, int y, int z) {
+  if ((unsigned)x >= (unsigned)o->LenX || (unsigned)y >= (unsigned)o->LenY || (unsigned)z > (unsigned)o->LenZ) {
+    o->q_oob++; o->LattCoo[o->scratch] = 0; o->LattInd[o->scratch] = 0; return o->scratch;
+  }
+  return (size_t)x + (size_t)o->LenX * ((size_t)y + (size_t)o->LenY * (size_t)z);
+}
+#define LC(o, s) ((o)->LattCoo[CI((o), (s)[0], (s)[1], (s)[2])])
+#define LI(o, s) ((o)->LattInd[CI((o), (s)[0], (s)[1], (s)[2])])
+static inline int eq3(const int32_t a[3], const int32_t b[3]) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+static inline void cp3(int32_t d[3], const int32_t s[3]) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+static inline void cpnn(int32_t d[4][3], const int32_t s[4][3]) { memcpy(d, s, 12 * sizeof(int32_t)); }
+static inline int recipr(const int32_t nn[4][3], const int32_t s[3]) {
+  int r = 0; for (int j = 0; j < 4; j++) if (eq3(nn[j], s)) r = 1; return r;
+}
+/* record fetches with the capacity guards the static Fortran arrays provide */
+static const int32_t ZERO_NN[4][3] = {{0}};
+static const int32_t (*mc_nn(Orc *o, int ind))[3] {
+  if (ind < 1 || ind > o->NumMcMax) { o->q_oob++; return ZERO_NN; }
+  return (const int32_t (*)[3])o->ListAdAtom[ind].nn;
+}
+static const int32_t (*bulk_nn(Orc *o, int ind))[3] {
+  if (ind < 1 || (size_t)ind >= o->capAtoms) return ZERO_NN;   /* zero-initialised static storage */
+  return (const int32_t (*)[3])o->ListAtom[ind].nn;
+}
+static const int32_t (*void_nn(Orc *o, int ind))[3] {
+  if (ind < 1 || ind > o->NumVdMax) { o->q_oob++; return ZERO_NN; }
+  return (const int32_t (*)[3])o->ListVoid[ind].nn;
+}
+
+/* src/modules/defsystem.f:104-105 (JumpDia, column j = bond j) */
+static const int JumpDia[8][3] = {{3, 3, 3}, {3, -3, -3}, {-3, -3, 3}, {-3, 3, -3},
+                                  {3, 3, -3}, {3, -3, 3}, {-3, -3, -3}, {-3, 3, 3}};
+
+/* Fortran column-major flattening of PTransE(3,0:3,0:3,0:3,0:3,0:3,0:3), defsystem.f:61-62 */
+static inline int IDXE(int sp, int i1, int i2, int i3, int i4, int i5, int i6) {
+  return (sp - 1) + 3 * (i1 + 4 * (i2 + 4 * (i3 + 4 * (i4 + 4 * (i5 + 4 * i6)))));
+}
+#define IDXD(sp, c) (((sp) - 1) + 3 * ((c) - 1))     /* PTransD(3,1:3)   defsystem.f:60 */
+#define IDXA(k, c) (((k) - 1) + 3 * (c))             /* PTransAbs/Des(3,0:3) defsystem.f:63-64 */
+
+/* ------------------------------------------------------------------ RNG */
+/* src/mcevent/random.f:22-69 (Knuth subtractive ran3; fac is a REAL(4) constant widened) */
+double orc_ran3(Orc *o) {
+  const int mbig = 1000000000, mseed = 161803398, mz = 0;
+  const double fac = (double)(1.0f / 1.0e9f);
+  int mj, mk, i, ii, k;
+  int *ma = o->r_ma;                       /* 1-based */
+  o->n_ran3++;
+  if (o->Idum < 0 || o->r_iff == 0) {
+    o->r_iff = 1;
+    mj = mseed - abs(o->Idum);
+    mj = mj % mbig;
+    ma[55] = mj;
+    mk = 1;
+    for (i = 1; i <= 54; i++) {
+      ii = (21 * i) % 55;
+      ma[ii] = mk;
+      mk = mj - mk;
+      if (mk < mz) mk += mbig;
+      mj = ma[ii];
+    }
+    for (k = 1; k <= 4; k++)
+      for (i = 1; i <= 55; i++) {
+        ma[i] = ma[i] - ma[1 + (i + 30) % 55];
+        if (ma[i] < mz) ma[i] += mbig;
+      }
+    o->r_inext = 0;
+    o->r_inextp = 31;
+    o->Idum = 1;
+  }
+  o->r_inext++;  if (o->r_inext == 56) o->r_inext = 1;
+  o->r_inextp++; if (o->r_inextp == 56) o->r_inextp = 1;
+  mj = ma[o->r_inext] - ma[o->r_inextp];
+  if (mj < mz) mj += mbig;
+  ma[o->r_inext] = mj;
+  return mj * fac;
+}
+
+/* src/mcevent/PickTreeEvent.f:72-1080: REAL(4) literals stored in REAL(8) */
+static const float NUMBERS[1000] = {
+#include "numberslist.inc"
+};
+double orc_numberslist(int64_t ind) { return (double)NUMBERS[(ind - 1) % 1000]; }
+
+/* ------------------------------------------------------------------ tree */
+/* src/mcevent/UpdateTree.f:25-66 */
+void orc_update_tree(Orc *o, int Index, double Patom) {
+  if (Patom == 0 && Index < o->NumAdAtom) orc_fatal(o, "error stabilizzato  da dentro Update! %d", Index);
+  else if (Index > o->NumAdAtom) orc_fatal(o, "Index > NumAdAtom %d %d", Index, o->NumAdAtom);
+  int Pos = Index + (1 << (o->Levels - 1)) - 1;
+  double *Tree = o->Tree;
+  Tree[Pos] = Patom;
+  for (int Parent = o->Levels - 1; Parent >= 1; Parent--) {
+    int NeighPos = (Pos & 1) ? Pos - 1 : Pos + 1;
+    int NewPos = Pos >> 1;
+    Tree[NewPos] = Tree[Pos] + Tree[NeighPos];
+    Pos = NewPos;
+  }
+}
+
+/* src/mcevent/PickTreeEvent.f:25-70 */
+static void pick_tree_event(Orc *o, int *Index, double *Patom) {
+  int idx = 1;
+  double *Tree = o->Tree, currrand, P = 0;
+  for (int Parent = 1; Parent <= o->Levels - 1; Parent++) {
+    if (o->RunType[0] == 'T') { o->counter++; currrand = orc_numberslist(o->counter); }
+    else currrand = orc_ran3(o);
+    P = currrand * Tree[idx];
+    idx <<= 1;
+    if (Tree[idx] < P) idx++;
+  }
+  P = Tree[idx];
+  if (idx - (1 << (o->Levels - 1)) + 1 > o->NumAdAtom)
+    orc_fatal(o, "write Index> NumAdAtom %d %d %.17g", idx - (1 << (o->Levels - 1)) + 1, o->NumAdAtom, Tree[1]);
+  *Index = idx - (1 << (o->Levels - 1)) + 1;
+  *Patom = P;
+}
+
+/* ------------------------------------------------------------------ lists */
+/* src/mcevent/Add.f:24-53 */
+static void AddMC(Orc *o, const int32_t Site[3], const int32_t NextN[4][3], int ev, double Prob) {
+  if (Prob == 0) orc_fatal(o, "provo ad aggiungere prob nulla");
+  o->NumAdAtom++;
+  if (o->NumAdAtom >= o->NumMcMax) orc_fatal(o, "troppe particelle cinetiche %d %d", o->NumAdAtom, o->NumMcMax);
+  LI(o, Site) = o->NumAdAtom;
+  OrcMC *r = &o->ListAdAtom[o->NumAdAtom];
+  cp3(r->xyz, Site); cpnn(r->nn, NextN); r->ev = ev; r->prob = Prob;
+  orc_update_tree(o, o->NumAdAtom, Prob);
+}
+/* src/mcevent/Add.f:58-76 */
+static void AddBulk(Orc *o, const int32_t Site[3], const int32_t NextN[4][3]) {
+  o->NumAtoms++;
+  if ((size_t)o->NumAtoms + 1 >= o->capAtoms) {
+    size_t nc = o->capAtoms * 2;
+    o->ListAtom = (OrcSite *)realloc(o->ListAtom, nc * sizeof(OrcSite));
+    memset(o->ListAtom + o->capAtoms, 0, (nc - o->capAtoms) * sizeof(OrcSite));
+    o->capAtoms = nc;
+  }
+  LI(o, Site) = o->NumAtoms;
+  cp3(o->ListAtom[o->NumAtoms].xyz, Site); cpnn(o->ListAtom[o->NumAtoms].nn, NextN);
+}
+/* src/mcevent/Add.f:82-100 */
+static void AddVoid(Orc *o, const int32_t Site[3], const int32_t NextN[4][3]) {
+  o->NumVoids++;
+  if (o->NumVoids >= o->NumVdMax) orc_fatal(o, "troppe vacanze %d", o->NumVoids);
+  LI(o, Site) = o->NumVoids;
+  cp3(o->ListVoid[o->NumVoids].xyz, Site); cpnn(o->ListVoid[o->NumVoids].nn, NextN);
+}
+/* src/mcevent/Erase.f:24-78 */
+static void EraseMC(Orc *o, const int32_t Site[3]) {
+  if (Site[2] == -1) orc_fatal(o, "accesso a latt fuori bond");
+  int IndNN = LI(o, Site);
+  if (IndNN > o->NumMcMax || IndNN == 0) orc_fatal(o, "err: EraseMC %d %d %d %d", IndNN, Site[0], Site[1], Site[2]);
+  if (IndNN >= o->NumAdAtom) {
+    memset(&o->ListAdAtom[IndNN], 0, sizeof(OrcMC));
+    LI(o, Site) = 0;
+    orc_update_tree(o, IndNN, 0.0);
+    o->NumAdAtom--;
+  } else {
+    o->ListAdAtom[IndNN] = o->ListAdAtom[o->NumAdAtom];
+    int ind = o->NumAdAtom + (1 << (o->Levels - 1)) - 1;
+    orc_update_tree(o, IndNN, o->Tree[ind]);
+    orc_update_tree(o, o->NumAdAtom, 0.0);
+    int32_t SiteTemp[3]; cp3(SiteTemp, o->ListAdAtom[o->NumAdAtom].xyz);
+    LI(o, SiteTemp) = IndNN;
+    memset(&o->ListAdAtom[o->NumAdAtom], 0, sizeof(OrcMC));
+    LI(o, Site) = 0;
+    o->NumAdAtom--;
+  }
+}
+/* src/mcevent/Erase.f:84-128 */
+static void EraseBulk(Orc *o, const int32_t Site[3]) {
+  if (Site[2] == -1) orc_fatal(o, "accesso a latt fuori bond");
+  int IndNN = LI(o, Site);
+  if (IndNN == 0 || IndNN > o->NumAtoms) orc_fatal(o, "err: EraseBulk %d %d %d %d", IndNN, Site[0], Site[1], Site[2]);
+  if (IndNN == o->NumAtoms) {
+    memset(&o->ListAtom[o->NumAtoms], 0, sizeof(OrcSite));
+    LI(o, Site) = 0;
+    o->NumAtoms--;
+  } else {
+    o->ListAtom[IndNN] = o->ListAtom[o->NumAtoms];
+    int32_t SiteTemp[3]; cp3(SiteTemp, o->ListAtom[o->NumAtoms].xyz);
+    LI(o, SiteTemp) = IndNN;
+    memset(&o->ListAtom[o->NumAtoms], 0, sizeof(OrcSite));
+    LI(o, Site) = 0;
+    o->NumAtoms--;
+  }
+}
+/* src/mcevent/Erase.f:135-179 */
+static void EraseVoid(Orc *o, const int32_t Site[3]) {
+  if (Site[2] == -1) orc_fatal(o, "accesso a latt fuori bond");
+  int IndNN = LI(o, Site);
+  if (IndNN > o->NumVdMax || IndNN == 0) orc_fatal(o, "err: EraseVoid %d %d %d %d", IndNN, Site[0], Site[1], Site[2]);
+  if (IndNN == o->NumVoids) {
+    memset(&o->ListVoid[o->NumVoids], 0, sizeof(OrcSite));
+    LI(o, Site) = 0;
+    o->NumVoids--;
+  } else {
+    o->ListVoid[IndNN] = o->ListVoid[o->NumVoids];
+    int32_t SiteTemp[3]; cp3(SiteTemp, o->ListVoid[o->NumVoids].xyz);
+    LI(o, SiteTemp) = IndNN;
+    memset(&o->ListVoid[o->NumVoids], 0, sizeof(OrcSite));
+    LI(o, Site) = 0;
+    o->NumVoids--;
+  }
+}
+
+/* ------------------------------------------------------------------ geometry */
+static inline int isign(int a, int b) { return b >= 0 ? abs(a) : -abs(a); }
+static inline int nint_d(double x) { return (int)(x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5)); }
+
+/* src/lattice/FIND_NN.f:25-77 */
+void orc_find_nn(const int Site1[3], const int Site2[3], const int SiteC[3], int NewSite[2][3], int LX, int LY) {
+  const double Pi = (double)3.14159265358979323f;   /* REAL(4) literal widened, FIND_NN.f:27 */
+  int Site11[3], Site22[3];
+  double ax[3], Rot[3][3] /* Rot[l][k] == Fortran Rot(l+1,k+1) */, snorm, Cth, Sth, R[3];
+  for (int k = 0; k < 3; k++) { Site11[k] = Site1[k]; Site22[k] = Site2[k]; }
+  if (abs(SiteC[0] - Site11[0]) > LX / 2) Site11[0] += isign(LX, SiteC[0] - Site11[0]);
+  if (abs(SiteC[1] - Site11[1]) > LY / 2) Site11[1] += isign(LY, SiteC[1] - Site11[1]);
+  if (abs(SiteC[0] - Site22[0]) > LX / 2) Site22[0] += isign(LX, SiteC[0] - Site22[0]);
+  if (abs(SiteC[1] - Site22[1]) > LY / 2) Site22[1] += isign(LY, SiteC[1] - Site22[1]);
+  for (int k = 0; k < 3; k++) ax[k] = (double)SiteC[k] - (double)Site11[k];
+  snorm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  for (int k = 0; k < 3; k++) ax[k] = ax[k] / snorm;
+  for (int irot = 1; irot <= 2; irot++) {
+    Cth = cos((double)(2 * irot) * Pi / 3.0);
+    Sth = sin((double)(2 * irot) * Pi / 3.0);
+    for (int i = 0; i < 3; i++) Rot[i][i] = ax[i] * ax[i] * (1 - Cth) + Cth;
+    Rot[1][0] = ax[0] * ax[1] * (1 - Cth) - ax[2] * Sth;   /* Rot(2,1) */
+    Rot[0][1] = ax[0] * ax[1] * (1 - Cth) + ax[2] * Sth;   /* Rot(1,2) */
+    Rot[2][0] = ax[0] * ax[2] * (1 - Cth) + ax[1] * Sth;   /* Rot(3,1) */
+    Rot[0][2] = ax[0] * ax[2] * (1 - Cth) - ax[1] * Sth;   /* Rot(1,3) */
+    Rot[2][1] = ax[1] * ax[2] * (1 - Cth) - ax[0] * Sth;   /* Rot(3,2) */
+    Rot[1][2] = ax[1] * ax[2] * (1 - Cth) + ax[0] * Sth;   /* Rot(2,3) */
+    for (int k = 0; k < 3; k++) {
+      R[k] = 0.0;
+      for (int l = 0; l < 3; l++) R[k] = R[k] + Rot[l][k] * ((double)Site22[l] - (double)SiteC[l]);
+    }
+    for (int k = 0; k < 3; k++) NewSite[irot - 1][k] = nint_d(R[k]) + SiteC[k];
+    if (NewSite[irot - 1][0] >= LX) NewSite[irot - 1][0] -= LX;
+    if (NewSite[irot - 1][0] < 0) NewSite[irot - 1][0] += LX;
+    if (NewSite[irot - 1][1] >= LY) NewSite[irot - 1][1] -= LY;
+    if (NewSite[irot - 1][1] < 0) NewSite[irot - 1][1] += LY;
+  }
+}
+
+/* src/lattice/FIND_SN.f:26-84 */
+void orc_find_sn(const int Site[3], const int SiteC_inp[3], const int SNSite_inp[3][3], int Zig[3][3], int Arm[3][3], int LX, int LY) {
+  int SNSite[3][3], SiteC[3];
+  double Cent[3], ax[3], snorm;
+  memcpy(SNSite, SNSite_inp, sizeof SNSite);
+  for (int k = 0; k < 3; k++) SiteC[k] = SiteC_inp[k];
+  if (abs(Site[0] - SiteC[0]) > LX / 2) SiteC[0] += isign(LX, Site[0] - SiteC[0]);
+  if (abs(Site[1] - SiteC[1]) > LY / 2) SiteC[1] += isign(LY, Site[1] - SiteC[1]);
+  for (int i = 0; i < 3; i++) {
+    if (abs(Site[0] - SNSite[i][0]) > LX / 2) SNSite[i][0] += isign(LX, Site[0] - SNSite[i][0]);
+    if (abs(Site[1] - SNSite[i][1]) > LY / 2) SNSite[i][1] += isign(LY, Site[1] - SNSite[i][1]);
+  }
+  for (int k = 0; k < 3; k++) Cent[k] = 0.5 * ((double)SiteC[k] + (double)(float)Site[k]);
+  for (int k = 0; k < 3; k++) ax[k] = (double)Site[k] - (double)SiteC[k];
+  snorm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  for (int k = 0; k < 3; k++) ax[k] = ax[k] / snorm;
+  const double ARM = (double)8.6602254037f;           /* REAL(4) literal, FIND_SN.f:67 */
+  for (int i = 0; i < 3; i++) {
+    for (int k = 0; k < 3; k++) {
+      double rz = 2 * Cent[k] - (double)SNSite[i][k];
+      double ra = (double)SNSite[i][k] + ARM * ax[k];
+      Zig[i][k] = nint_d(rz);
+      Arm[i][k] = nint_d(ra);
+    }
+    if (Zig[i][0] >= LX) Zig[i][0] -= LX;
+    if (Zig[i][0] < 0) Zig[i][0] += LX;
+    if (Zig[i][1] >= LY) Zig[i][1] -= LY;
+    if (Zig[i][1] < 0) Zig[i][1] += LY;
+    if (Arm[i][0] >= LX) Arm[i][0] -= LX;
+    if (Arm[i][0] < 0) Arm[i][0] += LX;
+    if (Arm[i][1] >= LY) Arm[i][1] -= LY;
+    if (Arm[i][1] < 0) Arm[i][1] += LY;
+  }
+}
+
+/* src/mcevent/IF_Arm_Choice.f:21-56 */
+static int IF_Arm_Choice(Orc *o, int NZig[3][3], int NArm[3][3]) {
+  int CoorArm = 0, CoorZig = 0;
+  for (int i = 0; i < 3; i++) {
+    CoorArm += IBITS(LC(o, NArm[i]), ORC_PosCoor, ORC_LenCoor);
+    CoorZig += IBITS(LC(o, NZig[i]), ORC_PosCoor, ORC_LenCoor);
+  }
+  if (CoorZig > CoorArm) return 0;
+  if (CoorZig == CoorArm) return (orc_ran3(o) <= o->PtransZig) ? 0 : 1;
+  return 1;
+}
+
+/* ------------------------------------------------------------------ rates */
+static const double KB = 0.00008617330350;        /* Get_Prob.f:70 */
+/* LA melting rate of one table entry, Get_Prob.f:143-144 */
+static inline double la_PE(Orc *o, int temperature, double e) {
+  return o->P0 * exp(-e / (KB * temperature)) * (e != 0.0 ? 1.0 : 0.0);
+}
+/* LA solidification rate, Get_Prob.f:146-148 */
+static inline double la_PD(Orc *o, int temperature, double d) {
+  return 0.5 * o->P0 * exp(-d / (KB * o->Tm)) * (1.0 + erf((temperature - o->Tflex) / o->sigma)) * (d != 0.0 ? 1.0 : 0.0);
+}
+static int site_temperature(Orc *o, const int32_t Site[3], const char *who) {
+  int t = IBITS(LC(o, Site), ORC_PosT, ORC_LenT);
+  if (t == 0) orc_fatal(o, "Temperature is zero in %s.", who);
+  return t;
+}
+/* the whole-table work the reference does on every call (Get_Prob.f:143-152); results unused */
+static void faithful_table_cost(Orc *o, int la, int temperature) {
+  if (!o->PEcopy) o->PEcopy = (double *)malloc((3 * 4096 + 9) * sizeof(double));
+  if (la) {
+    for (int i = 0; i < 3 * 4096; i++) o->PEcopy[i] = la_PE(o, temperature, o->PtransE[i]);
+    for (int i = 0; i < 9; i++) o->PEcopy[3 * 4096 + i] = la_PD(o, temperature, o->PtransD[i]);
+  } else {
+    memcpy(o->PEcopy, o->PtransE, 3 * 4096 * sizeof(double));
+    memcpy(o->PEcopy + 3 * 4096, o->PtransD, 9 * sizeof(double));
+  }
+  __asm__ volatile("" ::"r"(o->PEcopy) : "memory");
+}
+
+/* src/mcevent/Get_Prob.f:22-52 */
+static int IndexEvent_Abs(Orc *o, int Coor, double Ptmp, double PDepo) {
+  int res = 0;
+  if (o->NCov == 1) return 6;
+  if (o->NCov >= 2) {
+    for (int i = 1; i <= o->NCov; i++) {
+      double pmin, pmax, s;
+      if (i == 1) { pmin = PDepo; pmax = PDepo + o->PtransAbs[IDXA(1, Coor)]; }
+      else {
+        s = 0; for (int k = 1; k <= i - 1; k++) s += o->PtransAbs[IDXA(k, Coor)]; pmin = PDepo + s;
+        s = 0; for (int k = 1; k <= i; k++) s += o->PtransAbs[IDXA(k, Coor)]; pmax = PDepo + s;
+      }
+      if (Ptmp > pmin && Ptmp <= pmax) res = 5 + i;
+    }
+  }
+  if (res == 0) o->q_anom++;
+  return res;
+}
+
+/* deposition / absorption choice shared by Coor 1 and Coor 2,3; Get_Prob.f:160-179,186-204 */
+static void draw_dep_abs(Orc *o, int Coor, const double PD[4], int *ev, double *prob) {
+  double PDep = PD[1] + PD[2] + PD[3];
+  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += o->PtransAbs[IDXA(k, Coor)];
+  double Ptot = PDep + PAbs;
+  double Pcurr = orc_ran3(o) * Ptot;
+  if (Pcurr <= PDep) {
+    if (Pcurr <= PD[1]) *ev = 1;
+    else if (Pcurr > (PD[1] + PD[2])) *ev = 3;
+    else *ev = 2;
+  } else *ev = IndexEvent_Abs(o, Coor, Pcurr, PDep);
+  *prob = Ptot;
+}
+
+/* src/mcevent/Get_Prob.f:54-331 */
+static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int32_t Site[3], const int32_t NextN[4][3], int *Index_Event, double *Prob_Event) {
+  o->n_getprob++;
+  if (CovInd > 0 && CovInd < 113) {                       /* desorption, :93-123 */
+    if (Occ != 0) orc_fatal(o, "ERROR Covind!=0 with Occ!=0 in get_prob");
+    if (Coor <= 3) {
+      *Index_Event = 5;
+      int iCov = 0;
+      for (int j = 1; j <= o->NCov; j++) if (o->ListCov[j - 1] == CovInd) { iCov = j; break; }
+      if (iCov == 0) orc_fatal(o, "ERROR: could not find CovInd=%d inside ListCov", CovInd);
+      *Prob_Event = o->PtransDes[IDXA(iCov, Coor)];
+    } else {
+      *Index_Event = 0; *Prob_Event = 0.0;
+      if (Coor > 4) LOG(o, " anomalous coordination in desorption\n");
+    }
+  } else {
+    int la = (strcmp(o->InitSt, "LA") == 0), temperature = 0;
+    if (la) temperature = site_temperature(o, Site, "get_prob()");
+    if (o->faithful_cost) faithful_table_cost(o, la, temperature);
+    if (Occ == 0) {
+      double PD[4] = {0, 0, 0, 0};
+      if (Coor >= 1 && Coor <= 3)
+        for (int k = 1; k <= 3; k++) PD[k] = la ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)]) : o->PtransD[IDXD(k, Coor)];
+      if (Coor == 1) {
+        int CoorNN = IBITS(LC(o, NextN[0]), ORC_PosCoor, ORC_LenCoor);
+        if (CoorNN >= 2) draw_dep_abs(o, Coor, PD, Index_Event, Prob_Event);
+        else { *Index_Event = 1; *Prob_Event = (double)1.e-8f; }          /* :183 REAL(4) literal */
+      } else if (Coor == 2 || Coor == 3) {
+        draw_dep_abs(o, Coor, PD, Index_Event, Prob_Event);
+      } else if (Coor >= 4) {
+        *Index_Event = 0; *Prob_Event = 0.0;
+        if (Coor > 4) LOG(o, " anomalous coordination\n");
+      } else { LOG(o, " anomalous coordination %d\n", Coor); o->q_anom++; }
+    } else {                                                /* Occ=1: evaporation, :213-323 */
+      int N_Si = 0, N_C = 0, N_B = 0, N_wall = 0, covNN[3] = {0, 0, 0};
+      for (int i = 0; i < 4; i++) {
+        int32_t w = LC(o, NextN[i]);
+        int OccN = IBITS(w, ORC_PosOcc, ORC_LenOcc), CovIndN = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+        int CoorNN = IBITS(w, ORC_PosCoor, ORC_LenCoor);
+        if (OccN != 0) {
+          if (CovIndN != 113) {
+            int IndNN = LI(o, NextN[i]);
+            const int32_t (*NextNN)[3];
+            if (CoorNN >= 1 && CoorNN <= 3) NextNN = mc_nn(o, IndNN);
+            else { NextNN = bulk_nn(o, IndNN); if (CoorNN != 4) o->q_wrong_list++; }
+            if (recipr(NextNN, Site)) {
+              int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+              if (SiOrC == 1) N_Si++;
+              if (SiOrC == 2) N_C++;
+              if (SiOrC == 3) N_B++;
+            }
+          } else N_wall++;
+        } else if (CovIndN != 0) {
+          int IndNN = LI(o, NextN[i]);
+          if (CoorNN >= 4) o->q_wrong_list++;
+          const int32_t (*NextNN)[3] = mc_nn(o, IndNN);
+          if (recipr(NextNN, Site)) {
+            int iCov = 0;
+            for (int j = 1; j <= o->NCov; j++) if (o->ListCov[j - 1] == CovIndN) { iCov = j; break; }
+            if (iCov == 0) orc_fatal(o, "ERROR: could not find CovIndN=%d inside ListCov", CovIndN);
+            covNN[iCov - 1]++;
+          }
+        }
+      }
+      int ncry = N_Si + N_C + N_B + N_wall;
+      if (ncry != Coor)
+        orc_fatal(o, "%d %d %d %d %d Get Prob Error N_Si+N_C+N_B+N_wall.NE.Coor site %d %d %d", Coor, N_Si, N_C, N_B, N_wall, Site[0], Site[1], Site[2]);
+      if (ncry > 3) { *Index_Event = 0; *Prob_Event = 0.0; }
+      else if (ncry == 0) { *Index_Event = 4; *Prob_Event = (double)100000.f * o->Tree[1]; }
+      else {
+        *Index_Event = 4;
+        int c1 = 0, c2 = 0, c3 = 0;
+        if (o->NCov == 1) c1 = covNN[0];
+        else if (o->NCov == 2) { c1 = covNN[0]; c2 = covNN[1]; }
+        else if (o->NCov == 3) { c1 = covNN[0]; c2 = covNN[1]; c3 = covNN[2]; }
+        double e = o->PtransE[IDXE(NSiC, N_Si + N_wall, N_C, N_B, c1 & 3, c2 & 3, c3 & 3)];
+        if ((c1 | c2 | c3) > 3) o->q_oob++;
+        *Prob_Event = la ? la_PE(o, temperature, e) : e;
+      }
+    }
+  }
+  if (*Index_Event != 0 && *Prob_Event < (double)1e-12f)
+    LOG(o, " %d %.17g %d\n", *Index_Event, *Prob_Event, Coor);
+}
+
+/* src/mcevent/Get_Prob_Ini.f:23-161 */
+static void Get_Prob_Ini(Orc *o, int Occ, int NSiC, int Coor, const int32_t Site[3], const int32_t NextN[4][3], int *Index_Event, double *Prob_Event) {
+  int la = (strcmp(o->InitSt, "LA") == 0), temperature = 0;
+  o->n_getprob++;
+  if (la) temperature = site_temperature(o, Site, "get_prob_ini()");
+  if (o->faithful_cost) faithful_table_cost(o, la, temperature);
+  if (Occ == 0) {
+    double PD[4] = {0, 0, 0, 0};
+    if (Coor >= 1 && Coor <= 3)
+      for (int k = 1; k <= 3; k++) PD[k] = la ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)]) : o->PtransD[IDXD(k, Coor)];
+    int draw = 0;
+    if (Coor == 1) {
+      int CoorNN = IBITS(LC(o, NextN[0]), ORC_PosCoor, ORC_LenCoor);
+      if (CoorNN >= 2) draw = 1;
+      else { *Index_Event = 1; *Prob_Event = (double)1.e-6f; }
+    } else if (Coor == 2 || Coor == 3) draw = 1;
+    else if (Coor == 4) { *Index_Event = 0; *Prob_Event = 0.0; LOG(o, " %d Get Prob Vacancy Generation\n", Coor); }
+    if (draw) {
+      double Ptot = PD[1] + PD[2] + PD[3];
+      double Pcurr = orc_ran3(o) * Ptot;
+      if (Pcurr <= PD[1]) *Index_Event = 1;
+      else if (Pcurr > (PD[1] + PD[2])) *Index_Event = 3;
+      else *Index_Event = 2;
+      *Prob_Event = Ptot;
+    }
+  } else {
+    int N_Si = 0, N_C = 0, N_B = 0, N_cov = 0;
+    for (int i = 0; i < 4; i++) {
+      int32_t w = LC(o, NextN[i]);
+      int CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+      if (CovInd == 0) {
+        int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        if (SiOrC == 1) N_Si++;
+        if (SiOrC == 2) N_C++;
+        if (SiOrC == 3) N_B++;
+      } else N_cov++;
+    }
+    int n = N_Si + N_C + N_B + N_cov;
+    if (n != Coor) orc_fatal(o, "%d %d %d %d %d Get Prob Error N_Si+N_C++N_B+N_cov.NE.Coor", Coor, N_Si, N_C, N_B, N_cov);
+    if (n > 3) { *Index_Event = 0; *Prob_Event = 0.0; }
+    else if (n == 0) { *Index_Event = 4; *Prob_Event = (double)100000.f * o->Tree[1]; LOG(o, " %d Get Prob Isolated Atom\n", Coor); }
+    else {
+      *Index_Event = 4;
+      double e = o->PtransE[IDXE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)];
+      *Prob_Event = la ? la_PE(o, temperature, e) : e;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ events */
+static inline void set_rate(Orc *o, int Ind, int ev, double p) {
+  if (Ind < 1 || Ind > o->NumMcMax) { o->q_oob++; return; }
+  o->ListAdAtom[Ind].ev = ev; o->ListAdAtom[Ind].prob = p;
+}
+
+/* src/mcevent/deposition.f:24-251 */
+static void Deposition(Orc *o, int *IndVoid, int IAtom) {
+  int32_t Site[3], SiteC[3], NextN[4][3], NextNN[4][3];
+  int Index_Event = 0; double Prob = 0;
+  cp3(Site, o->ListAdAtom[*IndVoid].xyz);
+  int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor), CoorOld = Coor;
+  MVBITS(1, ORC_LenOcc, &LC(o, Site), ORC_PosOcc);
+  MVBITS(IAtom, ORC_LenSiC, &LC(o, Site), ORC_PosSiC);
+  if (Coor == 1) {                                         /* :49-74 */
+    cp3(SiteC, o->ListAdAtom[*IndVoid].nn[0]);
+    int IndNN = LI(o, SiteC);
+    if (IBITS(LC(o, SiteC), ORC_PosCoor, ORC_LenCoor) >= 4) o->q_wrong_list++;
+    const int32_t (*cnn)[3] = mc_nn(o, IndNN);
+    int SNSite[3][3] = {{0}}, NNZig[3][3], NNArm[3][3], j = 0;
+    for (int i = 0; i < 4; i++)
+      if (!eq3(cnn[i], Site)) { if (j < 3) cp3(SNSite[j], cnn[i]); else o->q_oob++; j++; }
+    orc_find_sn(Site, SiteC, (const int (*)[3])SNSite, NNZig, NNArm, o->LenX, o->LenY);
+    int IF_Arm = IF_Arm_Choice(o, NNZig, NNArm);
+    for (int i = 0; i < 3; i++) cp3(o->ListAdAtom[*IndVoid].nn[i + 1], IF_Arm ? NNArm[i] : NNZig[i]);
+  }
+  cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[*IndVoid].nn);
+  for (int i = 0; i < 4; i++) {
+    int32_t *wN = &LC(o, NextN[i]);
+    int Occ = IBITS(*wN, ORC_PosOcc, ORC_LenOcc);
+    int IndNN = LI(o, NextN[i]);
+    int CoorNN = IBITS(*wN, ORC_PosCoor, ORC_LenCoor);
+    int CovInd = IBITS(*wN, ORC_PosIndex, ORC_LenIndex);
+    memset(NextNN, 0, sizeof NextNN);
+    if (Occ == 0) {
+      if (CoorNN == 0) {                                   /* :88-99 new MC particle */
+        CoorNN = 1;
+        MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+        cp3(NextNN[0], Site);
+        Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+        if (Index_Event != 0) AddMC(o, NextN[i], (const int32_t (*)[3])NextNN, Index_Event, Prob);
+      } else if (CoorNN == 1) {                            /* :100-160 */
+        cpnn(NextNN, mc_nn(o, IndNN));
+        int Dx = abs(NextNN[0][0] - Site[0]); if (o->LenX - Dx < Dx) Dx = o->LenX - Dx;
+        int Dy = abs(NextNN[0][1] - Site[1]); if (o->LenY - Dy < Dy) Dy = o->LenY - Dy;
+        int DisNN2 = Dx * Dx + Dy * Dy + (NextNN[0][2] - Site[2]) * (NextNN[0][2] - Site[2]);
+        if (DisNN2 == 72) {
+          int NewSite[2][3];
+          CoorNN = 2;
+          cp3(NextNN[1], Site);
+          orc_find_nn(NextNN[0], NextNN[1], NextN[i], NewSite, o->LenX, o->LenY);
+          for (int j = 2; j < 4; j++) {
+            cp3(NextNN[j], NewSite[j - 2]);
+            int32_t w3 = LC(o, NextNN[j]);
+            if (IBITS(w3, ORC_PosOcc, ORC_LenOcc) != 0) {
+              int CoorNNN = IBITS(w3, ORC_PosCoor, ORC_LenCoor), CovIndNNN = IBITS(w3, ORC_PosIndex, ORC_LenIndex);
+              if (CoorNNN <= 3 && CovIndNNN != 113) {
+                int IndNNN = LI(o, NextNN[j]);
+                if (recipr(mc_nn(o, IndNNN), NextN[i])) CoorNN++;
+              }
+            }
+          }
+          MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+          cpnn(o->ListAdAtom[IndNN].nn, (const int32_t (*)[3])NextNN);
+          Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+          if (Index_Event == 0) { EraseMC(o, NextN[i]); AddVoid(o, NextN[i], (const int32_t (*)[3])NextNN); }
+          else { set_rate(o, IndNN, Index_Event, Prob); orc_update_tree(o, IndNN, Prob); }
+        }
+      } else if (CoorNN == 2 || CoorNN == 3) {             /* :161-190 */
+        cpnn(NextNN, mc_nn(o, IndNN));
+        if (recipr((const int32_t (*)[3])NextNN, Site)) {
+          CoorNN++;
+          MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+          Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+          if (Index_Event == 0) { EraseMC(o, NextN[i]); AddVoid(o, NextN[i], (const int32_t (*)[3])NextNN); }
+          else { set_rate(o, IndNN, Index_Event, Prob); orc_update_tree(o, IndNN, Prob); }
+        }
+      }
+    } else {                                               /* full site, :191-234 */
+      if (CovInd != 113) {
+        if (CovInd != 0) orc_fatal(o, "ERROR in deposition: Site can only have NN with CovInd=0 or 113 when its Occ=1");
+        if (CoorNN <= 3) {
+          cpnn(NextNN, mc_nn(o, IndNN));
+          if (recipr((const int32_t (*)[3])NextNN, Site)) {
+            CoorNN++;
+            MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+            if (Index_Event == 0) { EraseMC(o, NextN[i]); AddBulk(o, NextN[i], (const int32_t (*)[3])NextNN); }
+            else { set_rate(o, IndNN, Index_Event, Prob); orc_update_tree(o, IndNN, Prob); }
+            if (CoorOld == 1 && i >= 1) Coor++;
+          }
+        }
+      } else Coor++;
+    }
+  }
+  *IndVoid = LI(o, Site);
+  if (Coor != CoorOld) MVBITS(Coor, ORC_LenCoor, &LC(o, Site), ORC_PosCoor);
+  Get_Prob(o, 1, IAtom, 0, Coor, Site, (const int32_t (*)[3])NextN, &Index_Event, &Prob);
+  if (Index_Event == 0) { EraseMC(o, Site); AddBulk(o, Site, (const int32_t (*)[3])NextN); }
+  else { set_rate(o, *IndVoid, Index_Event, Prob); orc_update_tree(o, *IndVoid, Prob); }
+}
+
+/* the "keep only the occupied reciprocal neighbour" compaction, Evaporation.f:95-122 and :229-258.
+ * `rec` is the live list record, `old` the copy taken before, `me` the cell the record belongs to. */
+static void compact_to_single(Orc *o, int32_t rec[4][3], const int32_t old[4][3], const int32_t me[3]) {
+  int found = 0;
+  for (int j = 0; j < 4; j++) {
+    int32_t w = LC(o, old[j]);
+    if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 0) { rec[j][0] = rec[j][1] = rec[j][2] = 0; }
+    else {
+      int CoorNNN = IBITS(w, ORC_PosCoor, ORC_LenCoor), CovIndNN = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+      if (CoorNNN <= 3 && CovIndNN != 113) {
+        int IndNNN = LI(o, old[j]);
+        if (recipr(mc_nn(o, IndNNN), me)) { cp3(o->NBuff_evap, rec[j]); found = 1; }
+        rec[j][0] = rec[j][1] = rec[j][2] = 0;
+      } else { rec[j][0] = rec[j][1] = rec[j][2] = 0; }
+    }
+  }
+  if (!found) o->q_stale_nbuff++;
+  cp3(rec[0], o->NBuff_evap);
+}
+
+/* src/mcevent/Evaporation.f:25-262 */
+static void Evaporation(Orc *o, int *IndAtom) {
+  int32_t Site[3], NextN[4][3], NextNN[4][3];
+  int Index_Event = 0; double Prob = 0;
+  int keepT = (strcmp(o->InitSt, "LA") == 0 || strcmp(o->InitSt, "ST") == 0);
+  cp3(Site, o->ListAdAtom[*IndAtom].xyz);
+  int IAtom = IBITS(LC(o, Site), ORC_PosSiC, ORC_LenSiC);
+  if (IAtom >= 1 && IAtom <= 3) o->CountCrystal[IAtom - 1]--; else o->q_oob++;
+  int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor);
+  MVBITS(0, ORC_LenOcc, &LC(o, Site), ORC_PosOcc);
+  MVBITS(0, ORC_LenSiC, &LC(o, Site), ORC_PosSiC);
+  cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[*IndAtom].nn);
+  for (int i = 0; i < 4; i++) {
+    int32_t *wN = &LC(o, NextN[i]);
+    int Occ = IBITS(*wN, ORC_PosOcc, ORC_LenOcc);
+    int CoorNN = IBITS(*wN, ORC_PosCoor, ORC_LenCoor);
+    int IndNN = LI(o, NextN[i]);
+    int CovInd = IBITS(*wN, ORC_PosIndex, ORC_LenIndex);
+    memset(NextNN, 0, sizeof NextNN);
+    if (Occ == 0) {
+      if (CoorNN == 1) {                                   /* :62-79 */
+        cpnn(NextNN, mc_nn(o, IndNN));
+        if (recipr((const int32_t (*)[3])NextNN, Site)) {
+          EraseMC(o, NextN[i]);
+          if (keepT) { int t = IBITS(*wN, ORC_PosT, ORC_LenT); *wN = 0; MVBITS(t, ORC_LenT, wN, ORC_PosT); }
+          else *wN = 0;
+        }
+      } else if (CoorNN == 2) {                            /* :80-128 */
+        cpnn(NextNN, mc_nn(o, IndNN));
+        if (recipr((const int32_t (*)[3])NextNN, Site)) {
+          CoorNN = 1;
+          MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+          compact_to_single(o, o->ListAdAtom[IndNN].nn, (const int32_t (*)[3])NextNN, NextN[i]);
+          Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+          set_rate(o, IndNN, Index_Event, Prob);
+          orc_update_tree(o, IndNN, Prob);
+        }
+      } else if (CoorNN == 3) {                            /* :129-145 */
+        cpnn(NextNN, mc_nn(o, IndNN));
+        if (recipr((const int32_t (*)[3])NextNN, Site)) {
+          CoorNN = 2;
+          MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+          Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+          set_rate(o, IndNN, Index_Event, Prob);
+          orc_update_tree(o, IndNN, Prob);
+        }
+      } else if (CoorNN == 4) {                            /* :146-164 vacancy -> MC */
+        cpnn(NextNN, void_nn(o, IndNN));
+        if (recipr((const int32_t (*)[3])NextNN, Site)) {
+          CoorNN = 3;
+          MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+          Get_Prob(o, 0, 0, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+          EraseVoid(o, NextN[i]);
+          AddMC(o, NextN[i], (const int32_t (*)[3])NextNN, Index_Event, Prob);
+        }
+      }
+    } else {
+      if (CovInd != 113) {
+        if (CovInd != 0) orc_fatal(o, "ERROR in evaporation: Site can only have NN with CovInd=0 or 113 when its Occ=1");
+        if (CoorNN == 4) {                                 /* :173-190 bulk -> MC */
+          cpnn(NextNN, bulk_nn(o, IndNN));
+          if (recipr((const int32_t (*)[3])NextNN, Site)) {
+            CoorNN = 3;
+            MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+            EraseBulk(o, NextN[i]);
+            AddMC(o, NextN[i], (const int32_t (*)[3])NextNN, Index_Event, Prob);
+          }
+        } else {                                           /* :191-209 */
+          cpnn(NextNN, mc_nn(o, IndNN));
+          if (recipr((const int32_t (*)[3])NextNN, Site)) {
+            CoorNN--;
+            MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
+            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+            set_rate(o, IndNN, Index_Event, Prob);
+            orc_update_tree(o, IndNN, Prob);
+          }
+        }
+      } else Coor--;
+    }
+  }
+  *IndAtom = LI(o, Site);
+  MVBITS(Coor, ORC_LenCoor, &LC(o, Site), ORC_PosCoor);
+  if (Coor == 0) EraseMC(o, Site);
+  else {
+    Get_Prob(o, 0, 0, 0, Coor, Site, (const int32_t (*)[3])NextN, &Index_Event, &Prob);
+    set_rate(o, *IndAtom, Index_Event, Prob);
+    if (Coor == 1) {                                       /* :224-258 */
+      cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[*IndAtom].nn);
+      compact_to_single(o, o->ListAdAtom[*IndAtom].nn, (const int32_t (*)[3])NextN, Site);
+    }
+    orc_update_tree(o, *IndAtom, Prob);
+  }
+}
+
+/* re-rate an occupied reciprocal neighbour; shared by absorption.f:43-72 and desorption.f:54-111 */
+static void rerate_occ_nn(Orc *o, const int32_t Site[3], const int32_t N[3], int need_le3) {
+  int32_t w = LC(o, N);
+  int OccN = IBITS(w, ORC_PosOcc, ORC_LenOcc), IndNN = LI(o, N), CoorN = IBITS(w, ORC_PosCoor, ORC_LenCoor);
+  int Index_Event = 0; double Prob = 0;
+  if (OccN != 0) {
+    int CovIndN = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+    if (CovIndN != 113) {
+      if (need_le3 && CoorN > 3) return;
+      if (!need_le3 && CoorN > 3) o->q_wrong_list++;
+      int32_t NextNN[4][3]; cpnn(NextNN, mc_nn(o, IndNN));
+      if (recipr((const int32_t (*)[3])NextNN, Site)) {
+        int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        Get_Prob(o, 1, SiOrC, CovIndN, CoorN, N, (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
+        set_rate(o, IndNN, Index_Event, Prob);
+        orc_update_tree(o, IndNN, Prob);
+      }
+    }
+  }
+}
+
+/* src/mcevent/absorption.f:25-78 */
+static void Absorption(Orc *o, int IndVoid, int CovInd) {
+  int32_t Site[3], NextN[4][3];
+  int Index_Event = 0; double Prob = 0;
+  cp3(Site, o->ListAdAtom[IndVoid].xyz);
+  int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor);
+  MVBITS(CovInd, ORC_LenIndex, &LC(o, Site), ORC_PosIndex);
+  cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[IndVoid].nn);
+  for (int i = 0; i < 4; i++) rerate_occ_nn(o, Site, NextN[i], 1);
+  Get_Prob(o, 0, 0, CovInd, Coor, Site, (const int32_t (*)[3])NextN, &Index_Event, &Prob);
+  set_rate(o, IndVoid, Index_Event, Prob);
+  orc_update_tree(o, IndVoid, Prob);
+}
+
+/* src/mcevent/desorption.f:25-117 */
+static void Desorption(Orc *o, int IndAtom) {
+  int32_t Site[3], NextN[4][3];
+  int Index_Event = 0; double Prob = 0;
+  cp3(Site, o->ListAdAtom[IndAtom].xyz);
+  int CovInd = IBITS(LC(o, Site), ORC_PosIndex, ORC_LenIndex);
+  if (CovInd == o->ListCov[0]) o->CountCov[0]--;
+  else if (CovInd == o->ListCov[1]) o->CountCov[1]--;
+  else if (CovInd == o->ListCov[2]) o->CountCov[2]--;
+  int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor);
+  MVBITS(0, ORC_LenIndex, &LC(o, Site), ORC_PosIndex);
+  cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[IndAtom].nn);
+  if (Coor == 1) rerate_occ_nn(o, Site, NextN[0], 0);
+  else for (int i = 0; i < 4; i++) rerate_occ_nn(o, Site, NextN[i], 0);
+  Get_Prob(o, 0, 0, 0, Coor, Site, (const int32_t (*)[3])NextN, &Index_Event, &Prob);
+  set_rate(o, IndAtom, Index_Event, Prob);
+  orc_update_tree(o, IndAtom, Prob);
+}
+
+/* ------------------------------------------------------------------ create */
+Orc *orc_create(int lenx, int leny, int lenz, int nummcmax) {
+  Orc *o = (Orc *)calloc(1, sizeof(Orc));
+  o->LenX = lenx; o->LenY = leny; o->LenZ = lenz;
+  o->NumMcMax = nummcmax > 0 ? nummcmax : 500000;       /* defsystem.f:34 */
+  o->NumVdMax = 100000;                                  /* defsystem.f:35 */
+  o->ncell = (size_t)lenx * leny * ((size_t)lenz + 1);
+  o->scratch = o->ncell;
+  o->LattCoo = (int32_t *)calloc(o->ncell + 1, sizeof(int32_t));
+  o->LattInd = (int32_t *)calloc(o->ncell + 1, sizeof(int32_t));
+  o->ListAdAtom = (OrcMC *)calloc((size_t)o->NumMcMax + 2, sizeof(OrcMC));
+  o->capAtoms = 1 << 16;
+  o->ListAtom = (OrcSite *)calloc(o->capAtoms, sizeof(OrcSite));
+  o->ListVoid = (OrcSite *)calloc((size_t)o->NumVdMax + 2, sizeof(OrcSite));
+  /* src/mcevent/AllocateArrays.f:30-43 */
+  for (int ind = 0; ind <= 31; ind++) if ((o->NumMcMax >> ind) & 1) o->Levels = ind;
+  if (o->NumMcMax > (1 << o->Levels)) o->Levels += 2; else o->Levels += 1;
+  o->SizeTree = (1 << o->Levels) - 1;
+  o->Tree = (double *)calloc((size_t)o->SizeTree + 2, sizeof(double));
+  /* src/main.f:31-36 defaults */
+  o->Iter = 1; o->IterOut = 0; o->MaxIter = 2100000000; o->OutMolMol = 100000000;
+  o->MaxTime = 100000000.0; o->OutTime = 10000000.0; o->Time = 0.0;
+  o->Len1 = o->Len2 = o->Len3 = o->Len4 = 120;
+  strcpy(o->outdir, ".");
+  if (!o->LattCoo || !o->LattInd || !o->ListAdAtom || !o->Tree) { orc_destroy(o); return NULL; }
+  return o;
+}
+void orc_destroy(Orc *o) {
+  if (!o) return;
+  free(o->LattCoo); free(o->LattInd); free(o->ListAdAtom); free(o->ListAtom); free(o->ListVoid);
+  free(o->Tree); free(o->PEcopy); free(o->trace); free(o);
+}
+int orc_sizeof_mc(void) { return (int)sizeof(OrcMC); }
+
+/* FNV-1a over the lattice words, list sizes and the bits of Time: the parity fingerprint */
+uint64_t orc_state_hash(const Orc *o) {
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < o->ncell; i++) { h ^= (uint32_t)o->LattCoo[i]; h *= 1099511628211ull; }
+  uint64_t t; memcpy(&t, &o->Time, 8);
+  uint64_t extra[5] = {(uint64_t)o->NumAdAtom, (uint64_t)o->NumAtoms, (uint64_t)o->NumVoids, t, (uint64_t)o->Iter};
+  for (int i = 0; i < 5; i++) { h ^= extra[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+/* ------------------------------------------------------------------ start.dat */
+static char *next_line(FILE *f, char *buf, size_t n) {
+  if (!fgets(buf, (int)n, f)) return NULL;
+  size_t l = strlen(buf);
+  while (l && (buf[l - 1] == '\n' || buf[l - 1] == '\r')) buf[--l] = 0;
+  return buf;
+}
+static void trim_trailing(char *s) { size_t l = strlen(s); while (l && (s[l - 1] == ' ' || s[l - 1] == '\t')) s[--l] = 0; }
+/* list-directed read of one character token */
+static void tok_str(const char *line, char *out, size_t n) {
+  while (*line == ' ' || *line == '\t') line++;
+  size_t i = 0;
+  if (*line == '\'' || *line == '"') { char q = *line++; while (*line && *line != q && i + 1 < n) out[i++] = *line++; }
+  else while (*line && *line != ' ' && *line != '\t' && *line != ',' && *line != '/' && i + 1 < n) out[i++] = *line++;
+  out[i] = 0;
+}
+/* Fortran accepts 1.0d0 style exponents */
+static double fortran_strtod(const char *s, char **end) {
+  char tmp[128]; size_t i = 0;
+  while (*s == ' ' || *s == '\t' || *s == ',') s++;
+  const char *s0 = s;
+  while (*s && *s != ' ' && *s != '\t' && *s != ',' && *s != '!' && i + 1 < sizeof tmp) { char c = *s++; if (c == 'd' || c == 'D') c = 'e'; tmp[i++] = c; }
+  tmp[i] = 0;
+  char *e2; double v = strtod(tmp, &e2);
+  if (end) *end = (char *)(s0 + (e2 - tmp));
+  return v;
+}
+
+/* src/mcevent/SetProbability.f:21-143 */
+static int set_probability(Orc *o, FILE *f) {
+  char line[4096];
+  static const int tab[3][4] = {{3, 9, 19, 34}, {18, 50, 100, 172}, {57, 150, 288, 480}};
+  if (o->NCrystal < 1 || o->NCrystal > 3 || o->NCov < 0 || o->NCov > 3) orc_fatal(o, "ERROR NOT IMPLEMENTED: NCrystal and NCov");
+  int maxElines = tab[o->NCrystal - 1][o->NCov];
+  LOG(o, " maxElines %d\n", maxElines);
+  memset(o->PtransE, 0, sizeof o->PtransE);
+  for (int i = 1; i <= maxElines; i++) {
+    if (!next_line(f, line, sizeof line)) orc_fatal(o, "start.dat: EOF in evaporation block");
+    char *p = line; int indsp = (int)strtol(p, &p, 10); long elind = strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+    if (indsp > o->NCrystal) orc_fatal(o, "ERROR: 1st index in evap prob must be <= NCrystal");
+    int ind[6] = {0, 0, 0, 0, 0, 0};
+    int nd = o->NCrystal + o->NCov;
+    for (int j = 1; j <= o->NCrystal; j++) { long d = 1; for (int k = 0; k < nd - j; k++) d *= 10; ind[j - 1] = (int)((elind / d) % 10); }
+    for (int j = o->NCrystal + 1; j <= nd; j++) { long d = 1; for (int k = 0; k < nd - j; k++) d *= 10; ind[3 + j - o->NCrystal - 1] = (int)((elind / d) % 10); }
+    for (int k = 0; k < 6; k++) if (ind[k] > 3) orc_fatal(o, "evaporation index digit > 3");
+    o->PtransE[IDXE(indsp, ind[0], ind[1], ind[2], ind[3], ind[4], ind[5])] = v;
+  }
+  for (int j = 1; j <= o->NCrystal * 3; j++) {
+    if (!next_line(f, line, sizeof line)) orc_fatal(o, "start.dat: EOF in deposition block");
+    char *p = line; int indsp = (int)strtol(p, &p, 10); int el = (int)strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+    if (indsp > o->NCrystal || el < 1 || el > 3) orc_fatal(o, "ERROR: 1st index in depo prob block must be <= NCrystal");
+    o->PtransD[IDXD(indsp, el)] = v;
+  }
+  for (int pass = 0; pass < 2; pass++)
+    for (int j = 1; j <= o->NCov * 3; j++) {
+      if (!next_line(f, line, sizeof line)) orc_fatal(o, "start.dat: EOF in abs/des block");
+      char *p = line; int indsp = (int)strtol(p, &p, 10); int el = (int)strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+      if (indsp <= o->NCrystal || indsp > o->NCrystal + o->NCov || el < 0 || el > 3) orc_fatal(o, "ERROR: 1st index in abs/des prob block");
+      (pass == 0 ? o->PtransAbs : o->PtransDes)[IDXA(indsp - o->NCrystal, el)] = v;
+    }
+  return 0;
+}
+
+/* src/main.f:83-219 */
+int orc_read_start(Orc *o, const char *path) {
+  FILE *f = fopen(path, "r");
+  char line[4096], tok[64];
+  if (!f) { snprintf(o->errmsg, sizeof o->errmsg, "cannot open %s", path); return -1; }
+  o->jb_set = 1;
+  if (setjmp(o->jb)) { o->jb_set = 0; fclose(f); return -2; }
+#define NEXT() do { if (!next_line(f, line, sizeof line)) orc_fatal(o, "start.dat: unexpected EOF"); } while (0)
+  LOG(o, " KMC box size:  %d %d %d\n", o->LenX, o->LenY, o->LenZ);
+  NEXT(); { char *p = line; o->NCrystal = (int)strtol(p, &p, 10); o->NCov = (int)strtol(p, &p, 10); }
+  if (o->NCrystal > 3) orc_fatal(o, "ERR NOT IMPLEMENTED: NCrystal must be <= 3");
+  NEXT(); { char *p = line; for (int i = 0; i < o->NCrystal; i++) o->ListCrystal[i] = (int)strtol(p, &p, 10); }
+  if (o->NCov > 0 && o->NCov <= 3) {
+    LOG(o, "            ***** Simulating CVD *****\n");
+    NEXT(); { char *p = line; for (int i = 0; i < o->NCov; i++) o->ListCov[i] = (int)strtol(p, &p, 10); }
+  } else if (o->NCov == 0) LOG(o, "            ***** Simulating PVD or LA *****\n");
+  else orc_fatal(o, "ERR NOT IMPLEMENTED: NCov must be <= 3");
+  LOG(o, " Crystal species (NCrystal= %d ) --> Z:", o->NCrystal);
+  for (int i = 0; i < o->NCrystal; i++) LOG(o, " %d", o->ListCrystal[i]);
+  LOG(o, "\n");
+  if (o->NCov > 0) { LOG(o, " Coverage species (NCov= %d ) --> Z:", o->NCov); for (int i = 0; i < o->NCov; i++) LOG(o, " %d", o->ListCov[i]); LOG(o, "\n"); }
+  NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->InitSt, tok, 2); o->InitSt[2] = 0;
+  if (!strcmp(o->InitSt, "FF")) { NEXT(); char *p = line; o->Len1 = (int)strtol(p, &p, 10); o->Len2 = (int)strtol(p, &p, 10); o->Len3 = (int)strtol(p, &p, 10); o->Len4 = (int)strtol(p, &p, 10); }
+  else if (!strcmp(o->InitSt, "ST")) orc_fatal(o, "oracle: InitSt ST not restated");
+  else if (!strcmp(o->InitSt, "IN") || !strcmp(o->InitSt, "SH")) { NEXT(); strncpy(o->cadfilename, line, sizeof o->cadfilename - 1); trim_trailing(o->cadfilename); }
+  else if (!strcmp(o->InitSt, "LA")) {
+    LOG(o, " ****** MulSKIPs run for laser annealing ******\n");
+    if (o->NCov > 0) orc_fatal(o, "ERR NOT IMPLEMENTED: NCov=0 for LA");
+    NEXT(); strncpy(o->cadfilename, line, sizeof o->cadfilename - 1); trim_trailing(o->cadfilename);
+    NEXT(); strncpy(o->tempfilename, line, sizeof o->tempfilename - 1); trim_trailing(o->tempfilename);
+    NEXT(); o->Tm = fortran_strtod(line, NULL);
+    NEXT(); o->P0 = fortran_strtod(line, NULL);
+    NEXT(); o->sigma = fortran_strtod(line, NULL);
+    NEXT(); o->Tflex = fortran_strtod(line, NULL);
+    LOG(o, " Melting temperature in Kelvin:  %.17g\n", o->Tm);
+    NEXT(); o->LenVac = fortran_strtod(line, NULL);
+    LOG(o, " Top air thickness (ang):  %.17g\n", o->LenVac);
+    NEXT(); o->LenNuc = fortran_strtod(line, NULL);
+    LOG(o, " Nucleus thickness (ang):  %.17g\n", o->LenNuc);
+    NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->Homogeneous, tok, 2);
+    LOG(o, " Model homogeneous nucleation: %s\n", o->Homogeneous);
+  } else { NEXT(); char *p = line; o->Len1 = (int)strtol(p, &p, 10); o->Len2 = (int)strtol(p, &p, 10); o->Len3 = (int)strtol(p, &p, 10); }
+  /* SiGe alloy fraction, main.f:142-149; trap 5 of SURVEY 8(c) */
+  if ((o->NCrystal == 2 && o->ListCrystal[0] == 14 && o->ListCrystal[1] == 32) ||
+      (o->NCrystal == 3 && o->ListCrystal[0] == 14 && o->ListCrystal[1] == 32 && o->ListCrystal[2] == 5)) {
+    NEXT(); o->alloyfraction = fortran_strtod(line, NULL);
+    LOG(o, " Ge fraction in substrate:  %.17g\n", o->alloyfraction);
+  } else o->alloyfraction = 0.0;
+  NEXT(); o->PtransZig = fortran_strtod(line, NULL);
+  NEXT(); o->sf = fortran_strtod(line, NULL);
+  LOG(o, " KMC Super-Lattice parameter (ang):  %.17g\n", o->sf);
+  NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->ExitStrategy, tok, 4); o->ExitStrategy[4] = 0;
+  LOG(o, " Exit strategy: %s\n", o->ExitStrategy);
+  if (!strcmp(o->ExitStrategy, "Iter")) {
+    NEXT(); o->MaxIter = strtoll(line, NULL, 10);
+    NEXT(); o->OutMolMol = strtoll(line, NULL, 10);
+    LOG(o, " MaxIter:  %lld\n OutMolMol:  %lld\n", (long long)o->MaxIter, (long long)o->OutMolMol);
+  } else if (!strcmp(o->ExitStrategy, "Time")) {
+    NEXT(); o->MaxTime = fortran_strtod(line, NULL);
+    NEXT(); o->OutTime = fortran_strtod(line, NULL);
+    LOG(o, " Total simulation time in seconds:  %.17g\n Output frequency in seconds:  %.17g\n", o->MaxTime, o->OutTime);
+  }
+  NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->RunType, tok, 2); o->RunType[2] = 0;
+  if (o->RunType[0] == 'T' && o->RunType[1] == 0)
+    LOG(o, " ATTENTION! You are running mulskips in test modality,  that is random numbers are not so random!!\n");
+  NEXT(); o->Idum = (int)strtol(line, NULL, 10);
+  LOG(o, " IDUM %d\n", o->Idum);
+  NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->SaveFinalState, tok, 2);
+  if (!strcmp(o->SaveFinalState, "T")) {
+    NEXT(); strncpy(o->restartfilename, line, sizeof o->restartfilename - 1); trim_trailing(o->restartfilename);
+    LOG(o, " ATTENTION! Storing checkpoint file %s\n This will occupy a lot of disk space...\n", o->restartfilename);
+  } else LOG(o, " SaveFinalState flag is not \"T\": checkpoint file will  not be written.\n");
+  NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->SaveCoo, tok, 2);
+  if (!strcmp(o->SaveCoo, "T")) {
+    NEXT(); strncpy(o->coofilename, line, sizeof o->coofilename - 1); trim_trailing(o->coofilename);
+    LOG(o, " ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", o->coofilename);
+  } else {
+    if (!strcmp(o->InitSt, "LA")) orc_fatal(o, "ERR: SaveCoo flag must be \"T\" for LA simulations!");
+    LOG(o, " SaveCoo flag is not \"T\": Coor file not stored\n");
+  }
+  set_probability(o, f);
+  LOG(o, " numParticelle= %d Levels = %d , SizeTree = %d\n", o->NumMcMax, o->Levels, o->SizeTree);
+#undef NEXT
+  o->jb_set = 0;
+  fclose(f);
+  return 0;
+}
+
+/* ------------------------------------------------------------------ initial geometries */
+static inline int is_cubic_site(int x, int y, int z, int *kind) {
+  /* the test used by every builder, e.g. SetSi.f:52-57: kind 0 -> JumpDia 1..4, kind 1 -> JumpDia 5..8 */
+  if (x % 3 || y % 3 || z % 3) return 0;
+  int x1 = x / 3, y1 = y / 3, z1 = z / 3;
+  if ((x1 % 2) != (y1 % 2) || (x1 % 2) != (z1 % 2)) return 0;
+  int m = (x1 + y1 + z1) % 4;
+  if (m == 0) { *kind = 0; return 1; }
+  if (m == 3) { *kind = 1; return 1; }
+  return 0;
+}
+static inline void dia_nn(Orc *o, int x, int y, int z, int kind, int32_t NextN[4][3]) {
+  for (int i = 0; i < 4; i++) {
+    NextN[i][0] = x + JumpDia[i + 4 * kind][0];
+    NextN[i][1] = y + JumpDia[i + 4 * kind][1];
+    NextN[i][2] = z + JumpDia[i + 4 * kind][2];
+    if (NextN[i][0] >= o->LenX) NextN[i][0] -= o->LenX;
+    if (NextN[i][0] < 0) NextN[i][0] += o->LenX;
+    if (NextN[i][1] >= o->LenY) NextN[i][1] -= o->LenY;
+    if (NextN[i][1] < 0) NextN[i][1] += o->LenY;
+  }
+}
+static void set_wall_planes(Orc *o, int z0, int z1, int x0, int x1) {
+  for (int z = z0; z <= z1; z++) for (int y = 0; y < o->LenY; y++) for (int x = x0; x <= x1; x++) {
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    *w |= (1 << ORC_PosOcc);
+    MVBITS(113, ORC_LenIndex, w, ORC_PosIndex);
+  }
+}
+
+/* Flat (001) builders: src/initial/SetSi.f:25-221 (walls=1, one species) and SetSiC3C.f:25-199 (walls=0, Si/C) */
+static void set_flat(Orc *o, int Len, int walls, int two_species) {
+  int32_t Site[3], NextN[4][3]; int kind, ev; double Prob;
+  if (walls) set_wall_planes(o, 0, 5, 0, o->LenX - 1);
+  for (int z = (walls ? 6 : 0); z <= Len - 4; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+      *w |= 1 << ((kind && two_species) ? ORC_PosC : ORC_PosSi);
+      *w |= 1 << ORC_PosOcc;
+      MVBITS(4, ORC_LenCoor, w, ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  for (int z = Len - 3; z <= Len - 1; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+      int sp = (kind && two_species) ? 2 : 1;
+      *w |= 1 << (sp == 2 ? ORC_PosC : ORC_PosSi);
+      *w |= 1 << ORC_PosOcc;
+      MVBITS(2, ORC_LenCoor, w, ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      Prob = o->PtransE[IDXE(sp, 2, 0, 0, 0, 0, 0)];
+      AddMC(o, Site, (const int32_t (*)[3])NextN, 4, Prob);
+    }
+  for (int z = Len; z <= Len; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+      MVBITS(2, ORC_LenCoor, w, ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      ev = 0; Prob = 0;
+      Get_Prob(o, 0, 0, 0, 2, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+      AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+    }
+  if (walls) set_wall_planes(o, o->LenZ - 6, o->LenZ - 1, 0, o->LenX - 1);
+}
+
+/* "Set the coordination" pass shared by SetNC.f:60-133, SetNCSp.f, SetInvPOff.f, SetSiFINFET.f:118-214,
+ * SetCAD.f:203-296.  wallaware selects the SetCAD/FINFET variant (skip wall cells, empty sites do not
+ * count wall neighbours). */
+static void pass_coordination(Orc *o, int z0, int z1, int y0, int y1, int x0, int x1, int wallaware) {
+  int32_t NextN[4][3]; int kind;
+  int la = !strcmp(o->InitSt, "LA");
+  for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+    if (wallaware && IBITS(o->LattCoo[CI(o, x, y, z)], ORC_PosIndex, ORC_LenIndex) == 113) continue;
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    int Occ = IBITS(*w, ORC_PosOcc, ORC_LenOcc), Coor = 0;
+    dia_nn(o, x, y, z, kind, NextN);
+    for (int i = 0; i < 4; i++) {
+      int32_t wn = LC(o, NextN[i]);
+      int OccN = IBITS(wn, ORC_PosOcc, ORC_LenOcc);
+      if (!wallaware || Occ > 0) { if (OccN > 0) Coor++; }
+      else if (OccN > 0 && IBITS(wn, ORC_PosIndex, ORC_LenIndex) != 113) Coor++;
+    }
+    if (Occ != 0 && Coor == 0) {
+      if (la) { int t = IBITS(*w, ORC_PosT, ORC_LenT); *w = 0; MVBITS(t, ORC_LenT, w, ORC_PosT); }
+      else *w = 0;
+      for (int i = 0; i < 4; i++) {
+        int32_t *wn = &LC(o, NextN[i]);
+        int c = IBITS(*wn, ORC_PosCoor, ORC_LenCoor) - 1; if (c < 0) c = 0;
+        MVBITS(c, ORC_LenCoor, wn, ORC_PosCoor);
+      }
+    } else MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+  }
+}
+/* "Set the probability" pass: SetNC.f:135-233, SetSiFINFET.f:216-309, SetCAD.f:301-418 */
+static void pass_probability(Orc *o, int z0, int z1, int y0, int y1, int x0, int x1, int wallaware, int cadvoid) {
+  int32_t Site[3], NextN[4][3], NBuff[3] = {0, 0, 0}; int kind, ev; double Prob;
+  for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+    if (wallaware && IBITS(o->LattCoo[CI(o, x, y, z)], ORC_PosIndex, ORC_LenIndex) == 113) continue;
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    int32_t w = o->LattCoo[CI(o, x, y, z)];
+    Site[0] = x; Site[1] = y; Site[2] = z;
+    dia_nn(o, x, y, z, kind, NextN);
+    int Occ = IBITS(w, ORC_PosOcc, ORC_LenOcc), Coor = IBITS(w, ORC_PosCoor, ORC_LenCoor);
+    if (Occ != 0 && Coor == 0) LOG(o, " error %d %d %d %d %d\n", x, y, z, Occ, Coor);
+    ev = 0; Prob = 0;
+    if (Occ == 0) {
+      if (Coor > 0) {
+        if (Coor == 1) {
+          for (int i = 0; i < 4; i++) {
+            int32_t wn = LC(o, NextN[i]);
+            int OccN = IBITS(wn, ORC_PosOcc, ORC_LenOcc), CovIndN = IBITS(wn, ORC_PosIndex, ORC_LenIndex);
+            if (OccN == 0 || (wallaware && CovIndN == 113)) { NextN[i][0] = NextN[i][1] = NextN[i][2] = 0; }
+            else { cp3(NBuff, NextN[i]); NextN[i][0] = NextN[i][1] = NextN[i][2] = 0; }
+          }
+          cp3(NextN[0], NBuff);
+        }
+        if (cadvoid && Coor == 4) { LOG(o, " Initializing a vacancy\n"); AddVoid(o, Site, (const int32_t (*)[3])NextN); }
+        else {
+          Get_Prob_Ini(o, 0, 0, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+          AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+        }
+      }
+    } else {
+      if (Coor <= 3) {
+        int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        Get_Prob_Ini(o, 1, IAt, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+        AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+      } else AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  }
+}
+static inline void occupy(Orc *o, int x, int y, int z, int kind, int two_species) {
+  int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+  *w |= 1 << ((kind && two_species) ? ORC_PosC : ORC_PosSi);
+  *w |= 1 << ORC_PosOcc;
+}
+
+/* src/initial/SetNC.f:25-235 (sphere=0) and SetNCSp.f (sphere=1) */
+static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere) {
+  int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
+  if (!sphere) { LOG(o, " %d %d\n", LZ / 2 - Len3 / 2, LZ / 2 + Len3 / 2 + 1); LOG(o, " %d %d\n", LX / 2 - Len1 / 2, LX / 2 + Len1 / 2 + 1); }
+  for (int z = LZ / 2 - Len3 / 2; z <= LZ / 2 + Len3 / 2 - 1; z++)
+    for (int y = LY / 2 - Len2 / 2; y <= LY / 2 + Len2 / 2 - 1; y++)
+      for (int x = LX / 2 - Len1 / 2; x <= LX / 2 + Len1 / 2 - 1; x++) {
+        if (sphere) {
+          int d2 = (x - LX / 2) * (x - LX / 2) + (y - LY / 2) * (y - LY / 2) + (z - LZ / 2) * (z - LZ / 2);
+          if (d2 > Len1 * Len1 / 4) continue;
+        }
+        if (is_cubic_site(x, y, z, &kind)) occupy(o, x, y, z, kind, 1);
+      }
+  pass_coordination(o, LZ / 2 - Len3 / 2 - 10, LZ / 2 + Len3 / 2 + 9, LY / 2 - Len2 / 2 - 10, LY / 2 + Len2 / 2 + 9,
+                    LX / 2 - Len1 / 2 - 10, LX / 2 + Len1 / 2 + 9, 0);
+  pass_probability(o, LZ / 2 - Len3 / 2 - 10, LZ / 2 + Len3 / 2 + 9, LY / 2 - Len2 / 2 - 10, LY / 2 + Len2 / 2 + 9,
+                   LX / 2 - Len1 / 2 - 10, LX / 2 + Len1 / 2 + 9, 0, 0);
+}
+
+/* src/initial/SetInvPOff.f:22-286 */
+static void set_invp_off(Orc *o, int Len, int Len3) {
+  int kind, LX = o->LenX, LY = o->LenY; int32_t Site[3], NextN[4][3];
+  int Lenh = LX / 2 - 1;
+  LOG(o, " %d %d %d\n", Lenh, Len, Len3);
+  for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      occupy(o, x, y, z, kind, 1);
+      MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (x % 3 || y % 3 || z % 3) continue;
+    int x1 = x / 3, y1 = y / 3, z1 = z / 3;
+    if ((x1 % 2) != (y1 % 2) || (x1 % 2) != (z1 % 2)) continue;
+    /* mixed INTEGER/REAL(4) expression of SetInvPOff.f:78-82: 1.10 is REAL(4) */
+    float zt = 1.10f * (float)(z - Len3);
+#define PYR(ax, ay) (((float)(abs(ax) + abs(ay)) - zt) <= (float)Len)
+    int inside = PYR(x - Lenh, y - Lenh) || PYR(x, y) || PYR(x - LX, y) || PYR(x, y - LY) || PYR(x - LX, y - LY);
+#undef PYR
+    if (!inside) {
+      int m = (x1 + y1 + z1) % 4;
+      if (m == 0) occupy(o, x, y, z, 0, 1);
+      else if (m == 3) occupy(o, x, y, z, 1, 1);
+    }
+  }
+  pass_coordination(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0);
+  pass_probability(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0, 0);
+}
+
+/* src/initial/SetSiFINFET.f:25-312 */
+static void set_finfet(Orc *o, int Len, int Lenww, int Lenwwtop, int Laperture) {
+  int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
+  set_wall_planes(o, 0, 5, 0, LX - 1);
+  set_wall_planes(o, Lenww, LZ - 7, 0, (int)(0.5f * (float)(LX - Laperture)) - 1);
+  set_wall_planes(o, Lenww, LZ - 7, (int)(0.5f * (float)(LX + Laperture)), LX - 1);
+  set_wall_planes(o, Lenwwtop, LZ - 7, 0, LX - 1);
+  set_wall_planes(o, LZ - 6, LZ - 1, 0, LX - 1);
+  for (int z = 6; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (IBITS(o->LattCoo[CI(o, x, y, z)], ORC_PosIndex, ORC_LenIndex) == 113) continue;
+    if (is_cubic_site(x, y, z, &kind)) occupy(o, x, y, z, kind, 0);
+  }
+  pass_coordination(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1);
+  pass_probability(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1, 0);
+}
+
+/* token reader for the one-plane-per-line integer/real files (LattGeo / TempStat) */
+static int read_plane(Orc *o, FILE *f, double *buf, size_t n) {
+  for (size_t i = 0; i < n; i++) if (fscanf(f, "%lf", &buf[i]) != 1) { orc_fatal(o, "short read in geometry/temperature file"); return -1; }
+  return 0;
+}
+/* src/initial/SetT.f:25-50 */
+static void set_T(Orc *o) {
+  LOG(o, " Reading input temperature file: %s\n", o->tempfilename);
+  FILE *f = fopen(o->tempfilename, "r");
+  if (!f) orc_fatal(o, "cannot open %s", o->tempfilename);
+  size_t n = (size_t)o->LenX * o->LenY; double *buf = (double *)malloc(n * sizeof(double));
+  for (int z = 0; z < o->LenZ; z++) {
+    read_plane(o, f, buf, n);
+    for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++) {
+      int t = (int)buf[x + (size_t)o->LenX * y];
+      if (t != 10) MVBITS(t, ORC_LenT, &o->LattCoo[CI(o, x, y, z)], ORC_PosT);
+    }
+  }
+  free(buf); fclose(f);
+  LOG(o, " Done reading input temperatures file\n");
+}
+/* src/initial/SetCAD.f:25-421 (RunType 'C' checkpoint branch :54-79 included) */
+static void set_cad(Orc *o) {
+  int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ, la = !strcmp(o->InitSt, "LA");
+  size_t n = (size_t)LX * LY; double *buf = (double *)malloc(n * sizeof(double));
+  double LenSiGe = 0.0;     /* un-initialised local in the reference (SetCAD.f:38); irrelevant while alloyfraction==0 */
+  if (o->alloyfraction > 0) LOG(o, " Setting up a SiGe layer with fraction = %.17g\n", o->alloyfraction);
+  else LOG(o, " Setting up Silicon\n");
+  if (o->RunType[0] == 'C') {
+    LOG(o, " Reading checkpoint file %s\n", o->cadfilename);
+    FILE *f = fopen(o->cadfilename, "r"); if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
+    for (int z = 0; z < LZ; z++) {
+      read_plane(o, f, buf, n);
+      for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+        if (la) { int t = IBITS(*w, ORC_PosT, ORC_LenT); *w = (int32_t)buf[x + (size_t)LX * y]; MVBITS(t, ORC_LenT, w, ORC_PosT); if (t > o->tmax) o->tmax = t; }
+        else *w = (int32_t)buf[x + (size_t)LX * y];
+      }
+    }
+    fclose(f);
+    LOG(o, " Done reading checkpoint file\n");
+  } else {
+    set_wall_planes(o, 0, 3, 0, LX - 1);
+    set_wall_planes(o, LZ - 4, LZ - 1, 0, LX - 1);
+    LOG(o, " Reading input geometry file: %s\n", o->cadfilename);
+    FILE *f = fopen(o->cadfilename, "r"); if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
+    for (int z = 0; z <= 3; z++) read_plane(o, f, buf, n);
+    for (int z = 4; z <= LZ - 5; z++) {
+      read_plane(o, f, buf, n);
+      for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        int Id = (int)buf[x + (size_t)LX * y];
+        int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+        if (Id == 10) { *w |= 1 << ORC_PosOcc; MVBITS(113, ORC_LenIndex, w, ORC_PosIndex); }
+        else if (Id == 1 && is_cubic_site(x, y, z, &kind)) {
+          int fill = 0;
+          if (la) {
+            if (!strcmp(o->Homogeneous, "T")) fill = (z <= (LZ - (int)((o->LenVac + o->LenNuc) / o->sf)));
+            else if (!strcmp(o->Homogeneous, "F")) {
+              int x0 = LX / 2, y0 = LY / 2, z0 = LZ - (int)(o->LenVac / o->sf);
+              fill = ((x - x0) * (x - x0) + (y - y0) * (y - y0) + (z - z0) * (z - z0)) > (int)((o->LenNuc / o->sf) * (o->LenNuc / o->sf));
+            } else LOG(o, " ERROR: Homogeneous needs to be either T or F\n");
+          } else fill = 1;
+          if (fill) {
+            *w |= 1 << ORC_PosOcc;
+            /* libgfortran RAND() is not restated (SURVEY 8c trap 6): alloy init is "parity unpinned";
+             * with alloyfraction==0 every draw selects Si, which is all the goldens exercise. */
+            double rr = 1.0;
+            if (o->alloyfraction > 0 && !(la && z <= (LZ - (int)((o->LenVac + LenSiGe) / o->sf)))) {
+              static uint64_t lcg = 88172645463325252ull; lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+              rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
+            }
+            *w |= 1 << (rr >= o->alloyfraction ? ORC_PosSi : ORC_PosC);
+          }
+        }
+      }
+    }
+    fclose(f);
+    LOG(o, " Done reading input geometry file\n");
+    pass_coordination(o, 0, LZ - 1, 0, LY - 1, 0, LX - 1, 1);
+  }
+  free(buf);
+  pass_probability(o, 0, LZ - 1, 0, LY - 1, 0, LX - 1, 1, 1);
+}
+
+/* src/main.f:225-300 */
+int orc_setup(Orc *o) {
+  o->jb_set = 1;
+  if (setjmp(o->jb)) { o->jb_set = 0; return -2; }
+  const char *s = o->InitSt;
+  if (!strcmp(s, "F")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 0, 1); }
+  else if (!strcmp(s, "FS")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 0); }
+  else if (!strcmp(s, "C")) set_nc(o, o->Len1, o->Len2, o->Len3, 0);
+  else if (!strcmp(s, "S")) set_nc(o, o->Len1, o->Len1, o->Len1, 1);
+  else if (!strcmp(s, "I")) set_invp_off(o, o->Len1, o->Len2);
+  else if (!strcmp(s, "FF")) {
+    o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;
+    set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
+  } else if (!strcmp(s, "IN")) set_cad(o);
+  else if (!strcmp(s, "LA")) { o->tmax = 0; set_T(o); set_cad(o); LOG(o, " Max temperature is:  %d K\n", o->tmax); }
+  else orc_fatal(o, "initialization not_implemented in oracle: %s", s);
+  LOG(o, " Atoms,Voids,AdAtoms %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
+  for (int i = 0; i < 3; i++) o->CountCrystalOld[i] = o->CountCrystal[i];
+  orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
+  o->jb_set = 0;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ main loop */
+/* src/main.f:304-371, one trip through the DO body */
+static int iterate_inner(Orc *o) {
+  int Ind; double Patom;
+  o->IterOut = o->Iter;
+  if (o->NumAdAtom <= 20) { LOG(o, " few MC particles: stop MC %lld %d\n", (long long)o->Iter, o->NumAdAtom); o->done = 2; return 1; }
+  pick_tree_event(o, &Ind, &Patom);
+  o->Time = o->Time + 1.0 / o->Tree[1];
+  int Itrans = o->ListAdAtom[Ind].ev;
+  cp3(o->last_site, o->ListAdAtom[Ind].xyz);
+  if (!strcmp(o->ExitStrategy, "Iter")) {
+    if (o->Iter % o->OutMolMol == 0) {
+      o->framecounter = o->IterOut / o->OutMolMol;
+      orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
+      const int32_t *S = o->ListAdAtom[Ind].xyz;
+      LOG(o, " Iter, Time, Site %lld %.17g %d %d %d\n", (long long)o->Iter, o->Time, S[0], S[1], S[2]);
+      LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
+    }
+  } else if (!strcmp(o->ExitStrategy, "Time")) {
+    if (o->Time >= ((double)(o->framecounter + 1) * o->OutTime)) {
+      orc_write_frame(o, o->Time, o->IterOut, o->framecounter + 1);
+      const int32_t *S = o->ListAdAtom[Ind].xyz;
+      LOG(o, " Iter, Time, Site %lld %.17g %d %d %d\n", (long long)o->Iter, o->Time, S[0], S[1], S[2]);
+      LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
+      o->framecounter++;
+    }
+  }
+  if (o->trace && o->trace_n < o->trace_cap) {
+    OrcTrace *t = &o->trace[o->trace_n++];
+    t->iter = o->Iter; t->ind = Ind; cp3(t->site, o->ListAdAtom[Ind].xyz); t->itrans = Itrans; t->pad = 0; t->tree1 = o->Tree[1]; t->time = o->Time;
+  }
+  if (Itrans >= 0 && Itrans < 8) o->n_events[Itrans]++; else o->n_events[7]++;
+  if (Itrans <= 3) {
+    Deposition(o, &Ind, Itrans);
+    if (Itrans >= 1) o->CountCrystal[Itrans - 1]++;
+  } else if (Itrans == 4) Evaporation(o, &Ind);
+  else if (Itrans == 5) Desorption(o, Ind);
+  else {
+    int k = Itrans - 5; if (k > 3) { o->q_oob++; k = 3; }
+    Absorption(o, Ind, o->ListCov[k - 1]);
+    o->CountCov[k - 1]++;
+  }
+  o->Iter++;
+  if (!strcmp(o->ExitStrategy, "Iter")) { if (o->Iter > o->MaxIter) { o->done = 1; return 1; } }
+  else if (!strcmp(o->ExitStrategy, "Time")) { if (o->Time > o->MaxTime) { o->done = 1; return 1; } }
+  return 0;
+}
+int orc_iterate(Orc *o) {
+  o->jb_set = 1;
+  if (setjmp(o->jb)) { o->jb_set = 0; return -2; }
+  int r = iterate_inner(o);
+  o->jb_set = 0;
+  return r;
+}
+int64_t orc_run(Orc *o, int64_t nmax) {
+  int64_t n = 0;
+  o->jb_set = 1;
+  if (setjmp(o->jb)) { o->jb_set = 0; return -2; }
+  while (n < nmax && !o->done) { int r = iterate_inner(o); if (o->done == 2) break; n++; if (r) break; }
+  o->jb_set = 0;
+  return n;
+}
+
+/* src/main.f:374-430 */
+int orc_finish(Orc *o) {
+  o->jb_set = 1;
+  if (setjmp(o->jb)) { o->jb_set = 0; return -2; }
+  if (!strcmp(o->ExitStrategy, "Iter")) orc_write_frame(o, o->Time, o->IterOut, o->IterOut / o->OutMolMol);
+  else if (!strcmp(o->ExitStrategy, "Time")) orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
+  char path[4096];
+  if (!strcmp(o->SaveFinalState, "T") && o->write_files) {
+    LOG(o, " Writing checkpoint file for a restart run %s\n", o->restartfilename);
+    snprintf(path, sizeof path, "%s%s%s", o->restartfilename[0] == '/' ? "" : o->outdir, o->restartfilename[0] == '/' ? "" : "/", o->restartfilename);
+    FILE *f = fopen(path, "w");
+    if (f) {
+      for (int z = 0; z < o->LenZ; z++) {
+        for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++) fprintf(f, " %11d", o->LattCoo[CI(o, x, y, z)]);
+        fputc('\n', f);
+      }
+      fclose(f);
+    }
+    LOG(o, " Done writing checkpoint file for a restart run %s\n", o->restartfilename);
+  }
+  if (!strcmp(o->SaveCoo, "T") && o->write_files) {
+    LOG(o, " Writing Coor (LA phases) file %s\n", o->coofilename);
+    snprintf(path, sizeof path, "%s%s%s", o->coofilename[0] == '/' ? "" : o->outdir, o->coofilename[0] == '/' ? "" : "/", o->coofilename);
+    FILE *f = fopen(path, "w");
+    if (f) {
+      for (int z = 0; z < o->LenZ; z++) {
+        for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++) {
+          int32_t w = o->LattCoo[CI(o, x, y, z)]; int v = 0;
+          if (IBITS(w, ORC_PosIndex, ORC_LenIndex) != 113) { if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1) v = IBITS(w, ORC_PosCoor, ORC_LenCoor); }
+          else v = 10;
+          fprintf(f, "%4d", v);
+        }
+        fputc('\n', f);
+      }
+      fclose(f);
+    }
+    LOG(o, " Done writing Coor (LA phases) file %s\n", o->coofilename);
+  }
+  o->jb_set = 0;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ writers */
+/* Fortran E15.8: 0.dddddddd E+xx */
+static void fmt_e15_8(double v, char out[32]) {
+  if (v == 0.0) { strcpy(out, " 0.00000000E+00"); return; }
+  char t[40]; snprintf(t, sizeof t, "%.7e", fabs(v));
+  /* t = d.ddddddde[+-]xx */
+  char dig[16]; dig[0] = t[0]; memcpy(dig + 1, t + 2, 7); dig[8] = 0;
+  int ex = atoi(strchr(t, 'e') + 1) + 1;
+  char body[32];
+  if (abs(ex) < 100) snprintf(body, sizeof body, "%s0.%sE%c%02d", v < 0 ? "-" : "", dig, ex < 0 ? '-' : '+', abs(ex));
+  else snprintf(body, sizeof body, "%s0.%s%c%03d", v < 0 ? "-" : "", dig, ex < 0 ? '-' : '+', abs(ex));
+  snprintf(out, 32, "%15s", body);
+}
+static void atom_line(FILE *f, const char *el, double sf, int x, int y, int z, const char *tail) {
+  fprintf(f, "%s%10.5f %10.5f %10.5f%s\n", el, sf * x, sf * y, sf * z, tail);
+}
+static int noepi_bulk(int x, int y, int z) { int k; return !is_cubic_site(x, y, z, &k); }
+static const char *el_of_Z(int Z) { return Z == 6 ? "C " : Z == 32 ? "Ge " : Z == 5 ? "B " : NULL; }
+
+/* src/inpout/WriteMolMolXYZFile.f:22-407 (+ the name logic of WriteMolMolSource.f:22-113 and
+ * GetOutputFileName.f:22-83, which reduces to I%08d of Iout) */
+int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
+  int LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
+  double sf = o->sf;
+  char e1[32], e2[32], e3[32], et[32], base[64], path[2048];
+  int sic = (o->NCrystal == 2 && (o->ListCrystal[0] == 6 || o->ListCrystal[1] == 6 || o->ListCrystal[2] == 6));
+  if (Iter != 0) {                                        /* WriteMolMolSource.f:42-56 */
+    int s = 0, so = 0; for (int i = 0; i < 3; i++) { s += o->CountCrystal[i]; so += o->CountCrystalOld[i]; }
+    LOG(o, " SUM(CountCrystal) %d\n CountCrystal %d %d %d\n CountCrystalOld %d %d %d\n", s, o->CountCrystal[0], o->CountCrystal[1], o->CountCrystal[2], o->CountCrystalOld[0], o->CountCrystalOld[1], o->CountCrystalOld[2]);
+    float d[3]; for (int i = 0; i < 3; i++) d[i] = (float)(o->CountCrystal[i] - o->CountCrystalOld[i]);
+    LOG(o, " diff %.9g %.9g %.9g\n", d[0], d[1], d[2]);
+    LOG(o, " xGesolid %.17g %.17g %.17g\n", (double)d[0] / (s - so), (double)d[1] / (s - so), (double)d[2] / (s - so));
+    for (int i = 0; i < 3; i++) o->CountCrystalOld[i] = o->CountCrystal[i];
+    if (o->NCov != 0) LOG(o, " CountCov %d %d %d\n", o->CountCov[0], o->CountCov[1], o->CountCov[2]);
+  }
+  if (Iout * 10 >= 1000000000) orc_fatal(o, "GetOutputFileName:: Iter can not be represented");
+  snprintf(base, sizeof base, "I%08lld", (long long)Iout);
+  LOG(o, " %s\n", base);
+
+  /* census 1, :77-92 */
+  int NumAtTotal = 0, NumCovTotal = 0, NoEpiBulk = 0;
+  for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t w = o->LattCoo[CI(o, x, y, z)];
+    int CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+    if (CovInd != 113) {
+      int IfOcc = IBITS(w, ORC_PosOcc, ORC_LenOcc), Coo = IBITS(w, ORC_PosCoor, ORC_LenCoor);
+      if (IfOcc == 1 && Coo <= 3) NumAtTotal++;
+      else if (IfOcc == 0 && CovInd != 0) NumCovTotal++;
+    }
+  }
+  /* census 2, :95-119 */
+  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t w = o->LattCoo[CI(o, x, y, z)];
+    if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4 && noepi_bulk(x, y, z)) NoEpiBulk++;
+  }
+  LOG(o, " %d\n", NoEpiBulk);
+  if (!o->write_files) {
+    /* the _w pass still mutates LattCoo for SiC (WriteMolMolXYZFile.f:267-398); fall through with no files */
+  }
+  FILE *fx = NULL, *fd = NULL, *fv = NULL, *fw = NULL;
+  if (o->write_files) {
+    snprintf(path, sizeof path, "%s/%s.xyz", o->outdir, base); fx = fopen(path, "w");
+    snprintf(path, sizeof path, "%s/%s_d.xyz", o->outdir, base); fd = fopen(path, "w");
+    snprintf(path, sizeof path, "%s/%s_v.xyz", o->outdir, base); fv = fopen(path, "w");
+    if (sic) { snprintf(path, sizeof path, "%s/%s_w.xyz", o->outdir, base); fw = fopen(path, "w"); }
+    if (!fx || !fd || !fv) orc_fatal(o, "cannot open output files in %s", o->outdir);
+  }
+  fmt_e15_8(sf * (double)LX, e1); fmt_e15_8(sf * (double)LY, e2); fmt_e15_8(sf * (double)LZ, e3); fmt_e15_8(Time, et);
+  if (fd) {                                               /* :125-159 */
+    fprintf(fd, " %8d angstroem KMC-time: %s Iter: %12lld\n", NoEpiBulk, et, (long long)Iter);
+    fprintf(fd, " periodic %s %s %s\n", e1, e2, e3);
+    for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      int32_t w = o->LattCoo[CI(o, x, y, z)];
+      if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4 && noepi_bulk(x, y, z)) {
+        int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        if (IAt == 1) atom_line(fd, "Ge ", sf, x, y, z, "  ");
+        if (IAt == 2) atom_line(fd, "B ", sf, x, y, z, "  ");
+        if (IAt == 3) atom_line(fd, "Cl ", sf, x, y, z, "  ");
+      }
+    }
+  }
+  if (fx) {                                               /* :163-221 */
+    fprintf(fx, " %8d angstroem KMC-time: %s Iter: %12lld\n", NumAtTotal + o->NumVoids + NumCovTotal, et, (long long)Iter);
+    fprintf(fx, " periodic %s %s %s\n", e1, e2, e3);
+    for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      int32_t w = o->LattCoo[CI(o, x, y, z)];
+      if (w == 0) continue;
+      int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC), Coo = IBITS(w, ORC_PosCoor, ORC_LenCoor), CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+      if (CovInd == 1) atom_line(fx, "H ", sf, x, y, z, "  ");
+      if (CovInd == 17) atom_line(fx, "Cl ", sf, x, y, z, "  ");
+      if (IAt == 1 && Coo <= 3) atom_line(fx, "Si ", sf, x, y, z, "  ");
+      if ((IAt == 2 || IAt == 3) && Coo <= 3) {
+        if (o->NCrystal < IAt) orc_fatal(o, "ERR: IAt=%d should not happen, NCrystal=%d", IAt, o->NCrystal);
+        const char *el = el_of_Z(o->ListCrystal[IAt - 1]);
+        if (!el) orc_fatal(o, "ERROR: 2nd crystal specie can only be C/Ge/B");
+        atom_line(fx, el, sf, x, y, z, "  ");
+      }
+    }
+    for (int i = 1; i <= o->NumVoids; i++) atom_line(fx, "O ", sf, o->ListVoid[i].xyz[0], o->ListVoid[i].xyz[1], o->ListVoid[i].xyz[2], "  ");
+  }
+  if (fv) {                                               /* :228-260 */
+    fprintf(fv, " %8d angstroem\n", o->NumVoids);
+    fprintf(fv, " periodic %s %s %s\n", e1, e2, e3);
+    for (int i = 1; i <= o->NumVoids; i++) {
+      int x = o->ListVoid[i].xyz[0], y = o->ListVoid[i].xyz[1], z = o->ListVoid[i].xyz[2];
+      if (o->NCov == 0 && o->NCrystal == 2 && o->ListCrystal[1] == 6) {
+        int IAt = 0;
+        for (int j = 0; j < 4; j++) IAt += IBITS(LC(o, o->ListVoid[i].nn[j]), ORC_PosSiC, ORC_LenSiC);
+        if (IAt == 4) atom_line(fv, "Mg ", sf, x, y, z, " # CV (C vacancy)");
+        else if (IAt == 8) atom_line(fv, "He ", sf, x, y, z, " # SV (Si vacancy)");
+        else if (IAt == 7) atom_line(fv, "Ne ", sf, x, y, z, " # SAV (Si antisite vac)");
+        else if (IAt == 5) atom_line(fv, "Be ", sf, x, y, z, " # CAV (C antisite vac)");
+        else if (IAt == 6) atom_line(fv, "Ar ", sf, x, y, z, " # XV (near 2C and 2Si)");
+        else orc_fatal(o, "ERROR: Weird Defect type was formed...ABORTING");
+      } else atom_line(fv, "O ", sf, x, y, z, "  ");
+    }
+  }
+  if (sic) {                                              /* :267-398, including the restore quirk at :386 */
+    int NumIsWrong = 0, NumAtWrong = 0, cap = 1024;
+    int32_t (*buf)[4] = (int32_t (*)[4])malloc((size_t)cap * sizeof *buf);
+#define NCORR(w, x, y, z, out) do { int ia_ = IBITS(w, ORC_PosSiC, ORC_LenSiC); const int32_t (*nn_)[3] = bulk_nn(o, o->LattInd[CI(o, x, y, z)]); out = 0; \
+      if (ia_ == 1) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), ORC_PosC, 1); \
+      else if (ia_ == 2) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), ORC_PosSi, 1); } while (0)
+    for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+      if (*w == 0 || IBITS(*w, ORC_PosIndex, ORC_LenIndex) == 113) continue;
+      if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(*w, ORC_PosCoor, ORC_LenCoor) == 4) {
+        int IAt = IBITS(*w, ORC_PosSiC, ORC_LenSiC), n; NCORR(*w, x, y, z, n);
+        if (n == 0) {
+          if (NumIsWrong == cap) { cap *= 2; buf = (int32_t (*)[4])realloc(buf, (size_t)cap * sizeof *buf); }
+          buf[NumIsWrong][0] = x; buf[NumIsWrong][1] = y; buf[NumIsWrong][2] = z;
+          if (IAt == 1) { *w &= ~(1 << ORC_PosSi); *w |= 1 << ORC_PosC; buf[NumIsWrong][3] = 1; }
+          else { *w &= ~(1 << ORC_PosC); *w |= 1 << ORC_PosSi; buf[NumIsWrong][3] = 2; }
+          NumIsWrong++;
+        }
+      }
+    }
+    for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      int32_t w = o->LattCoo[CI(o, x, y, z)];
+      if (w == 0) continue;
+      if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4) { int n; NCORR(w, x, y, z, n); if (n == 3) NumAtWrong++; }
+    }
+    LOG(o, " NumAtWrong:  %d\n", NumAtWrong);
+    if (fw) {
+      fprintf(fw, " %8d angstroem\n", NumAtWrong);
+      fprintf(fw, " periodic %s %s %s\n", e1, e2, e3);
+      for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        int32_t w = o->LattCoo[CI(o, x, y, z)];
+        if (w == 0) continue;
+        if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4) {
+          int n; NCORR(w, x, y, z, n);
+          if (n == 3) { int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC); if (IAt == 1) atom_line(fw, "Si ", sf, x, y, z, "  "); if (IAt == 2) atom_line(fw, "C ", sf, x, y, z, "  "); }
+        }
+      }
+    }
+    for (int i = 0; i < NumIsWrong; i++) {
+      int32_t *w = &o->LattCoo[CI(o, buf[i][0], buf[i][1], buf[i][2])];
+      int ty = buf[NumIsWrong - 1][3];                    /* :386 uses the LAST entry's type for all */
+      if (ty == 1) { *w &= ~(1 << ORC_PosC); *w |= 1 << ORC_PosSi; }
+      else { *w &= ~(1 << ORC_PosSi); *w |= 1 << ORC_PosC; }
+    }
+    free(buf);
+#undef NCORR
+  }
+  if (fx) fclose(fx);
+  if (fd) fclose(fd);
+  if (fv) fclose(fv);
+  if (fw) fclose(fw);
+  if (o->write_files) {                                   /* WriteMolMolSource.f:77-112, side files */
+    snprintf(path, sizeof path, "%s/fort.30", o->outdir); FILE *f = fopen(path, "a"); if (f) { fprintf(f, " %.17g\n", Time); fclose(f); }
+    snprintf(path, sizeof path, "%s/%s.src", o->outdir, base); f = fopen(path, "w");
+    if (f) {
+      fprintf(f, " load xyz %s.xyz\n color temperature\n set background white\n set boundbox true\n zoom 140\n rotate x 41\n rotate y 4\n spacefill 2\n color axes black\n wireframe 2\n color atom green\n wireframe 12\n color atom purple\n set bondmode and\n", base);
+      fclose(f);
+    }
+    snprintf(path, sizeof path, "%s/movie.mos", o->outdir); f = fopen(path, Iter == 0 ? "w" : "a");
+    if (f) { fprintf(f, " source    %s.src\n write gif %s.gif\n zap\n", base, base); fclose(f); }
+    snprintf(path, sizeof path, "%s/DefAtEnergy.dat", o->outdir); f = fopen(path, Iter == 0 ? "w" : "a");
+    if (f) { fprintf(f, " \n"); fclose(f); }
+  }
+  return 0;
+}
