@@ -432,7 +432,7 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
             int IndNN = LI(o, NextN[i]);
             const int32_t (*NextNN)[3];
             if (CoorNN >= 1 && CoorNN <= 3) NextNN = mc_nn(o, IndNN);
-            else { NextNN = bulk_nn(o, IndNN); if (CoorNN != 4) o->q_wrong_list++; }
+            else { NextNN = bulk_nn(o, IndNN); if (CoorNN != 4) o->q_wl_iso++; }
             if (recipr(NextNN, Site)) {
               int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
               if (SiOrC == 1) N_Si++;
@@ -442,7 +442,7 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
           } else N_wall++;
         } else if (CovIndN != 0) {
           int IndNN = LI(o, NextN[i]);
-          if (CoorNN >= 4) o->q_wrong_list++;
+          if (CoorNN >= 4) o->q_wl_cov++;
           const int32_t (*NextNN)[3] = mc_nn(o, IndNN);
           if (recipr(NextNN, Site)) {
             int iCov = 0;
@@ -539,7 +539,7 @@ static void Deposition(Orc *o, int *IndVoid, int IAtom) {
   if (Coor == 1) {                                         /* :49-74 */
     cp3(SiteC, o->ListAdAtom[*IndVoid].nn[0]);
     int IndNN = LI(o, SiteC);
-    if (IBITS(LC(o, SiteC), ORC_PosCoor, ORC_LenCoor) >= 4) o->q_wrong_list++;
+    if (IBITS(LC(o, SiteC), ORC_PosCoor, ORC_LenCoor) >= 4) o->q_wl_dep++;
     const int32_t (*cnn)[3] = mc_nn(o, IndNN);
     int SNSite[3][3] = {{0}}, NNZig[3][3], NNArm[3][3], j = 0;
     for (int i = 0; i < 4; i++)
@@ -751,7 +751,7 @@ static void rerate_occ_nn(Orc *o, const int32_t Site[3], const int32_t N[3], int
     int CovIndN = IBITS(w, ORC_PosIndex, ORC_LenIndex);
     if (CovIndN != 113) {
       if (need_le3 && CoorN > 3) return;
-      if (!need_le3 && CoorN > 3) o->q_wrong_list++;
+      if (!need_le3 && CoorN > 3) o->q_wl_des++;
       int32_t NextNN[4][3]; cpnn(NextNN, mc_nn(o, IndNN));
       if (recipr((const int32_t (*)[3])NextNN, Site)) {
         int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
@@ -1200,9 +1200,22 @@ static void set_finfet(Orc *o, int Len, int Lenww, int Lenwwtop, int Laperture) 
   pass_probability(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1, 0);
 }
 
-/* token reader for the one-plane-per-line integer/real files (LattGeo / TempStat) */
+/* list-directed READ of one plane (LattGeo / TempStat files): take n values starting on a fresh
+ * record, continue onto following records only if the record is short, and DISCARD whatever is left
+ * on the last record read -- the regression LattGeo file has a line with one value too many. */
 static int read_plane(Orc *o, FILE *f, double *buf, size_t n) {
-  for (size_t i = 0; i < n; i++) if (fscanf(f, "%lf", &buf[i]) != 1) { orc_fatal(o, "short read in geometry/temperature file"); return -1; }
+  static char *line = NULL; static size_t cap = 0;
+  size_t got = 0;
+  while (got < n) {
+    if (getline(&line, &cap, f) < 0) { orc_fatal(o, "short read in geometry/temperature file"); return -1; }
+    char *p = line, *e;
+    while (got < n) {
+      double v = strtod(p, &e);
+      if (e == p) break;
+      buf[got++] = v; p = e;
+      while (*p == ',') p++;
+    }
+  }
   return 0;
 }
 /* src/initial/SetT.f:25-50 */
@@ -1246,7 +1259,9 @@ static void set_cad(Orc *o) {
     set_wall_planes(o, LZ - 4, LZ - 1, 0, LX - 1);
     LOG(o, " Reading input geometry file: %s\n", o->cadfilename);
     FILE *f = fopen(o->cadfilename, "r"); if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
-    for (int z = 0; z <= 3; z++) read_plane(o, f, buf, n);
+    /* SetCAD.f:99-102.  ORC_CAD_NOSKIP=1 emulates the OLDER build that produced the CAD/LA goldens
+     * (it did not skip the four wall planes, so file line k lands on z=k+4); see DESIGN.md. */
+    if (!getenv("ORC_CAD_NOSKIP")) for (int z = 0; z <= 3; z++) read_plane(o, f, buf, n);
     for (int z = 4; z <= LZ - 5; z++) {
       read_plane(o, f, buf, n);
       for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {

@@ -64,7 +64,7 @@ typedef struct Orc {
   int32_t NBuff_evap[3];               /* Evaporation.f's un-initialised NBuff, kept across calls */
   /* bookkeeping added by the oracle */
   int64_t n_getprob, n_ran3, n_events[8];
-  int64_t q_stale_nbuff, q_wrong_list, q_oob, q_anom, q_far_bond;
+  int64_t q_stale_nbuff, q_wl_iso, q_wl_cov, q_wl_dep, q_wl_des, q_oob, q_anom, q_far_bond;   /* reference-quirk counters */
   int faithful_cost;                   /* 1: also perform the 96 KiB PE/PD table copy per Get_Prob call */
   double *PEcopy;                      /* target of that copy */
   FILE *log;                           /* reference stdout stream (NULL = silent) */

@@ -36,9 +36,9 @@ int main(int argc, char **argv) {
   double t1 = now();
   if (n < 0) return 3;
   orc_finish(o);
-  fprintf(stderr, "oracle: %lld events in %.3f s = %.4g events/s; Get_Prob calls %lld (%.4g site-updates/s); ran3 draws %lld; quirks: stale_nbuff=%lld wrong_list=%lld oob=%lld anom=%lld\n",
+  fprintf(stderr, "oracle: %lld events in %.3f s = %.4g events/s; Get_Prob calls %lld (%.4g site-updates/s); ran3 draws %lld; quirks: stale_nbuff=%lld wl_iso=%lld wl_cov=%lld wl_dep=%lld wl_des=%lld oob=%lld anom=%lld\n",
           (long long)n, t1 - t0, n / (t1 - t0), (long long)o->n_getprob, o->n_getprob / (t1 - t0), (long long)o->n_ran3,
-          (long long)o->q_stale_nbuff, (long long)o->q_wrong_list, (long long)o->q_oob, (long long)o->q_anom);
+          (long long)o->q_stale_nbuff, (long long)o->q_wl_iso, (long long)o->q_wl_cov, (long long)o->q_wl_dep, (long long)o->q_wl_des, (long long)o->q_oob, (long long)o->q_anom);
   orc_destroy(o);
   return 0;
 }
