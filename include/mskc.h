@@ -1,0 +1,177 @@
+/*
+ * mskc.h -- C ABI of the B200-native MulSKIPS KMC event-loop library (libmskc.so).
+ *
+ * The reference (MulSKIPS, /root/reference) has no FFI for this path: the loop
+ * body lives in the Fortran host (mulskips-source/main.f:304-371) and works on
+ * module globals (mulskips-source/modules/defsystem.f).  These entry points sit
+ * exactly where that loop and the Set* -> AddMC/AddBulk/AddVoid calls sit, so a
+ * Fortran host binds them with one ISO_C_BINDING interface block
+ * (fortran/mskc_bind.f90).
+ *
+ * Conventions: extern "C", plain pointers and sizes, caller owns host buffers,
+ * the library owns device memory behind an opaque handle, every call returns
+ * int (0 = ok, <0 = error; mskc_last_error() gives the text, which mirrors the
+ * reference's STOP messages where one exists).  One handle per GPU, one host
+ * thread per handle (the reference is single-threaded).  No CPU fallback: if
+ * no CUDA device is usable mskc_create fails.
+ */
+#ifndef MSKC_H
+#define MSKC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mskc_ctx mskc_ctx;
+
+/* event codes of the PVD/CVD tree (main.f:335-357): 1..3 deposit species k, 4 evaporate,
+ * 5 desorb, 5+k adsorb coverage species k */
+enum { MSKC_EV_DEP1 = 1, MSKC_EV_DEP2 = 2, MSKC_EV_DEP3 = 3, MSKC_EV_EVAP = 4, MSKC_EV_DES = 5, MSKC_EV_ABS1 = 6 };
+
+/* why mskc_run_* returned */
+enum {
+  MSKC_STOP_BUDGET = 0,   /* event_budget / n_sweeps exhausted; call again to continue            */
+  MSKC_STOP_MAXITER = 1,  /* Iter > MaxIter            (main.f:362-363)                           */
+  MSKC_STOP_MAXTIME = 2,  /* Time > MaxTime            (main.f:364-365)                           */
+  MSKC_STOP_FRAME = 3,    /* output boundary reached AFTER the pick/time update and BEFORE the
+                             event is applied (main.f:316-333): write the frame, call again       */
+  MSKC_STOP_FEWMC = 4,    /* "few MC particles: stop MC" (main.f:307-310)                         */
+  MSKC_STOP_ERROR = -1
+};
+
+/* Replaces: static allocation in modules/defsystem.f:27-68 and mcevent/AllocateArrays.f:24-46.
+ * nummcmax<=0 selects the reference's NumMcMax=500000 (defsystem.f:34) -> Levels=20. */
+int mskc_create(int lenx, int leny, int lenz, int ncrystal, int ncov,
+                const int32_t *listcrystal /*[ncrystal]*/, const int32_t *listcov /*[ncov]*/,
+                int device_id, int nummcmax, mskc_ctx **out);
+int mskc_destroy(mskc_ctx *h);
+/* text of the last error on this handle (h may be NULL: last mskc_create failure) */
+const char *mskc_last_error(const mskc_ctx *h);
+
+/* Replaces: the tables filled by mcevent/SetProbability.f:21-143.  Fortran column-major
+ * flattening, exactly the module arrays: PtransE(3,0:3,0:3,0:3,0:3,0:3,0:3) = 12288 doubles,
+ * PtransD(3,1:3) = 9, PtransAbs(3,0:3) = 12, PtransDes(3,0:3) = 12 (defsystem.f:60-65). */
+int mskc_set_rates(mskc_ctx *h, const double *PtransE, const double *PtransD,
+                   const double *PtransAbs, const double *PtransDes, double PtransZig);
+/* Replaces: the LA rate law of mcevent/Get_Prob.f:127-149 (InitSt='LA').  Per-temperature tables are
+ * built on the host with libm exp/erf (bit-identical to the CPU reference) for every integer kelvin
+ * in [tmin,tmax].  enable=0 switches back to plain tables. */
+int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double sigma, double Tflex, int tmin, int tmax);
+
+/* Replaces: what the Set* builders leave in module globals (LattCoo + the three particle lists, in
+ * REFERENCE LIST ORDER, built through mcevent/Add.f).  Coordinates are absolute, neighbours are
+ * [n][4][3] with (0,0,0) = "not fixed" (defdertype.f:32-37).  LattCoo is [(lenz+1)][leny][lenx]. */
+int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
+                      int n_mc, const int32_t *mc_xyz, const int32_t *mc_nn, const int32_t *mc_event, const double *mc_rate,
+                      int n_bulk, const int32_t *bulk_xyz, const int32_t *bulk_nn,
+                      int n_void, const int32_t *void_xyz, const int32_t *void_nn);
+/* Device-side flat (001) builder for lattices too large to stage through the host: same geometry as
+ * initial/SetSi.f (walls=1, one species) / initial/SetSiC3C.f (walls=0, Si/C), parallel mode only
+ * (list order is not the reference's). */
+int mskc_init_flat(mskc_ctx *h, int len1, int walls, int two_species);
+
+/* Replaces: IDUM / counter / the SAVEd state of mcevent/random.f:32-34.  runtype is 'R' or 'T'
+ * (PickTreeEvent.f:43-49); ran3_state = {iff, inext, inextp, ma[1..55]} (58 ints) or NULL for a
+ * fresh generator seeded by idum; counter0 = numberslist cursor (definitions.f:35). */
+int mskc_seed(mskc_ctx *h, int idum, int runtype, int64_t counter0, const int32_t *ran3_state);
+/* read the generator back (58 ints + counter) so a host can continue the stream */
+int mskc_get_rng(mskc_ctx *h, int32_t *ran3_state, int64_t *counter, int32_t *idum);
+/* Iter/Time/species counters of main.f:31,54,75-76 (for continuation) */
+int mskc_set_clock(mskc_ctx *h, int64_t iter, double time, const int32_t *CountCrystal, const int32_t *CountCov);
+
+typedef struct {
+  int64_t max_iter;      /* MaxIter                                        */
+  double  max_time;      /* MaxTime                                        */
+  int32_t exit_on_time;  /* ExitStrategy=='Time'                           */
+  int32_t pad;
+  int64_t out_every;     /* OutMolMol ('Iter' strategy), 0 = no frames     */
+  double  out_time;      /* OutTime ('Time' strategy), 0 = no frames       */
+  int64_t framecounter;  /* frames already written in 'Time' strategy      */
+  int64_t event_budget;  /* events to execute in this call at most, 0=inf  */
+} mskc_parity_args;
+
+typedef struct {
+  int64_t iter;          /* Iter (1-based index of the NEXT event; main.f:31,359) */
+  int64_t iter_out;      /* IterOut                                               */
+  double  time;          /* Time                                                  */
+  int32_t last_site[3];  /* site of the last picked event                         */
+  int32_t stop_reason;
+  int32_t num_atoms, num_voids, num_adatom;
+  int32_t pad;
+  int64_t events_done;   /* events executed by this call                          */
+  int64_t site_updates;  /* Get_Prob evaluations by this call                     */
+  double  tree_root;     /* Tree(1)                                               */
+  float   kernel_ms;     /* device time of this call (CUDA events on the library's stream) */
+  int32_t launches;      /* kernels launched by this call */
+} mskc_parity_result;
+
+/* Replaces: the DO loop body main.f:304-371, serial-parity mode (single GPU): replays the reference's
+ * n-fold-way selection, RNG streams, list order and tree updates; lattice words, event sequence and
+ * Time are bit-identical to the reference. */
+int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_parity_result *r);
+
+typedef struct {
+  int64_t n_sweeps;          /* sweeps (4 colour steps each) to run in this call                    */
+  double  events_per_tile;   /* target mean events per active tile per colour step (sets tau)       */
+  double  tau_fixed;         /* >0: use this time quantum instead of the adaptive one               */
+  uint64_t seed;             /* Philox key                                                          */
+  int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
+  int32_t  flags;            /* bit0: flush L2 between sweeps is the caller's job (unused here)     */
+} mskc_parallel_args;
+
+typedef struct {
+  int64_t events_done;       /* events executed by this call                                        */
+  int64_t site_updates;      /* rate re-evaluations by this call                                    */
+  int64_t sweeps_done;
+  double  time;              /* KMC time after the call                                             */
+  double  total_rate;        /* sum of all rates at the last sweep                                  */
+  int64_t n_active;          /* active (listed) sites at the last sweep                             */
+  int64_t count_dep[3], count_evap, count_abs, count_des;
+  float   kernel_ms;         /* device time of this call (CUDA events on the library's stream)      */
+  int32_t launches;          /* kernels launched by this call                                       */
+  float   sweep_kernel_ms;   /* part of kernel_ms spent in the colour-step kernels                  */
+  int32_t stop_reason;
+} mskc_parallel_result;
+
+/* Synchronous-sublattice sampler: x-y tiles coloured 2x2, every tile of one colour runs its own
+ * n-fold way for a time quantum tau with counter-based Philox RNG.  Statistically equivalent to the
+ * loop of main.f:304-371 (see DESIGN.md for the tolerances). */
+int mskc_run_parallel(mskc_ctx *h, const mskc_parallel_args *a, mskc_parallel_result *r);
+/* Dense re-rate pass ("rate kernel"): recompute (event class, rate) of every listed site from the
+ * packed lattice and rebuild the per-tile sums.  Needed after a temperature upload. */
+int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate, float *kernel_ms);
+
+/* Replaces: initial/SetT.f:25-50 -- integer kelvin per cell, [lenz][leny*lenx], value 10 = wall
+ * (left untouched).  Writes bits 9..21 of every lattice word on the device. */
+int mskc_set_temperature(mskc_ctx *h, const int32_t *T);
+
+/* Replaces: the module globals read by inpout/WriteMolMolXYZFile.f, the checkpoint writer
+ * (main.f:385-403) and the Coor dump (main.f:407-430). */
+int mskc_download_lattice(mskc_ctx *h, int32_t *LattCoo);
+/* patch lattice words changed by the host (the _w.xyz pass of WriteMolMolXYZFile.f:267-398 flips
+ * species bits in place): n (cell index, word) pairs */
+int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const int32_t *word);
+typedef struct {
+  int32_t num_atoms, num_voids, num_adatom, pad;
+  int32_t CountCrystal[3], CountCov[3];
+  int64_t iter; double time;
+} mskc_counters;
+int mskc_get_counters(mskc_ctx *h, mskc_counters *c);
+/* list download; pass NULL for what is not wanted.  Sizes from mskc_get_counters.
+ * MC and void lists come in reference list order (parity mode); bulk in z,y,x scan order. */
+int mskc_download_lists(mskc_ctx *h,
+                        int32_t *mc_xyz, int32_t *mc_nn, int32_t *mc_event, double *mc_rate,
+                        int32_t *void_xyz, int32_t *void_nn,
+                        int32_t *bulk_xyz, int32_t *bulk_nn, int64_t bulk_cap, int64_t *n_bulk_found);
+/* 64-bit FNV-1a over the lattice words + list sizes + bits of Time + Iter: same function as the
+ * oracle's orc_state_hash, computed on the device lattice */
+int mskc_state_hash(mskc_ctx *h, uint64_t *hash);
+/* device census for output/statistics: counts used by WriteMolMolXYZFile.f:77-119 */
+typedef struct { int64_t undercoordinated, coverage, noepi_bulk, bulk, occupied, walls; double mean_height, sq_height; } mskc_census;
+int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,551 @@
+// mskc_api.cu -- the C ABI of include/mskc.h: context, state upload/download, kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 (see __graft_entry__.build()).
+#include "../../include/mskc.h"
+#include "mskc_device.cuh"
+#include "mskc_parity.cuh"
+#include "mskc_parallel.cuh"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mskc;
+
+static thread_local std::string g_last_error;
+
+struct mskc_ctx {
+  DevCtx D{};                 // device pointers inside
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string err;
+  // tables
+  double *d_PE = nullptr, *d_PD = nullptr, *d_PAbs = nullptr, *d_PDes = nullptr;
+  std::vector<double> h_PE, h_PD, h_PAbs, h_PDes;
+  short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr;
+  int *d_err = nullptr;
+  // parity mode
+  int NumMcMax = 500000, NumVdMax = 100000, Levels = 20;
+  double *d_Tree = nullptr; uint32_t *d_lattind = nullptr, *d_mc_cell = nullptr, *d_void_cell = nullptr; int *d_mc_ev = nullptr;
+  ParityState *d_ps = nullptr;
+  ParityState h_ps{};
+  bool parity_ready = false;
+  // parallel mode
+  ParallelCtx PC{};
+  bool parallel_ready = false;
+  bool have_rates = false, have_state = false;
+  int idum = 0, runtype = 'R';
+};
+
+static int set_err(mskc_ctx *h, const char *fmt, ...) {
+  char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf;
+  g_last_error = buf;
+  return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(h, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); } while (0)
+
+static const char *dev_err_text(int code) {
+  switch (code) {
+    case E_OOB: return "lattice access outside 0..LenZ (the reference would read foreign memory)";
+    case E_FARBOND: return "bond vector outside the +-15 range of the packed bond code";
+    case E_TREE_ZERO: return "error stabilizzato  da dentro Update!";
+    case E_TREE_IDX: return "Index > NumAdAtom";
+    case E_PICK: return "write Index> NumAdAtom";
+    case E_ADD_ZERO: return "provo ad aggiungere prob nulla";
+    case E_MC_FULL: return "troppe particelle cinetiche";
+    case E_VOID_FULL: return "troppe vacanze";
+    case E_ERASE: return "err: EraseMC/EraseVoid";
+    case E_COVOCC: return "ERROR Covind!=0 with Occ!=0 in get_prob";
+    case E_COVLIST: return "ERROR: could not find CovInd inside ListCov";
+    case E_CENSUS: return "Get Prob Error N_Si+N_C+N_B+N_wall.NE.Coor";
+    case E_TEMP0: return "Temperature is zero in get_prob().";
+    case E_NNCOV: return "ERROR in deposition: Site can only have NN with CovInd=0 or 113 when its Occ=1";
+    case E_TILE_FULL: return "per-tile active list capacity exceeded";
+    case E_STALE_NBUFF: return "Evaporation: no reciprocal occupied neighbour left (reference uses an uninitialised buffer here)";
+    case E_TRANGE: return "site temperature outside the table range given to mskc_set_la";
+    case E_BADEV: return "invalid event code";
+  }
+  return "unknown device error";
+}
+static int check_dev_err(mskc_ctx *h) {
+  int e[8];
+  CK(cudaMemcpyAsync(e, h->d_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (e[0] != 0) return set_err(h, "%s [code %d; %d %d %d %d]", dev_err_text(e[0]), e[0], e[1], e[2], e[3], e[4]);
+  return 0;
+}
+
+extern "C" const char *mskc_last_error(const mskc_ctx *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int mskc_create(int lenx, int leny, int lenz, int ncrystal, int ncov, const int32_t *listcrystal, const int32_t *listcov,
+                           int device_id, int nummcmax, mskc_ctx **out) {
+  mskc_ctx *h = nullptr;
+  if (!out) return set_err(nullptr, "mskc_create: out is NULL");
+  *out = nullptr;
+  if (lenx < 12 || leny < 12 || lenz < 12) return set_err(nullptr, "mskc_create: box too small");
+  if (ncrystal < 1 || ncrystal > 3) return set_err(nullptr, "ERR NOT IMPLEMENTED: NCrystal must be <= 3");
+  if (ncov < 0 || ncov > 3) return set_err(nullptr, "ERR NOT IMPLEMENTED: NCov must be <= 3");
+  if ((long long)lenx * leny * ((long long)lenz + 1) >= 0xFFFFFFF0ll) return set_err(nullptr, "mskc_create: more than 2^32 cells per GPU");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return set_err(nullptr, "mskc_create: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= ndev) return set_err(nullptr, "mskc_create: device %d of %d", device_id, ndev);
+  h = new mskc_ctx();
+  h->device = device_id;
+  CK(cudaSetDevice(device_id));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1)); CK(cudaEventCreate(&h->ev2)); CK(cudaEventCreate(&h->ev3));
+  DevCtx &D = h->D;
+  D.LX = lenx; D.LY = leny; D.LZ = lenz; D.ncell = (long long)lenx * leny * ((long long)lenz + 1);
+  D.NCrystal = ncrystal; D.NCov = ncov;
+  for (int i = 0; i < 3; i++) { D.ListCrystal[i] = (i < ncrystal && listcrystal) ? listcrystal[i] : 0; D.ListCov[i] = (i < ncov && listcov) ? listcov[i] : 0; }
+  CK(cudaMalloc(&D.state, D.ncell * sizeof(uint32_t)));
+  CK(cudaMalloc(&D.bonds, D.ncell * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(D.state, 0, D.ncell * sizeof(uint32_t), h->stream));
+  CK(cudaMemsetAsync(D.bonds, 0, D.ncell * sizeof(unsigned long long), h->stream));
+  CK(cudaMalloc(&h->d_PE, 12288 * sizeof(double))); CK(cudaMalloc(&h->d_PD, 9 * sizeof(double)));
+  CK(cudaMalloc(&h->d_PAbs, 12 * sizeof(double))); CK(cudaMalloc(&h->d_PDes, 12 * sizeof(double)));
+  CK(cudaMalloc(&h->d_err, 8 * sizeof(int))); CK(cudaMemsetAsync(h->d_err, 0, 8 * sizeof(int), h->stream));
+  D.PE = h->d_PE; D.PD = h->d_PD; D.PAbs = h->d_PAbs; D.PDes = h->d_PDes; D.err = h->d_err;
+  // FIND_NN.f:27,51-52: Pi is a REAL(4) literal; cos/sin from the host libm, as in the CPU reference
+  const double Pi = (double)3.14159265358979323f;
+  for (int irot = 1; irot <= 2; irot++) { D.rot_c[irot - 1] = cos((double)(2 * irot) * Pi / 3.0); D.rot_s[irot - 1] = sin((double)(2 * irot) * Pi / 3.0); }
+  // AllocateArrays.f:30-43
+  h->NumMcMax = nummcmax > 0 ? nummcmax : 500000;
+  h->Levels = 0;
+  for (int ind = 0; ind <= 31; ind++) if ((h->NumMcMax >> ind) & 1) h->Levels = ind;
+  h->Levels += (h->NumMcMax > (1 << h->Levels)) ? 2 : 1;
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+extern "C" int mskc_destroy(mskc_ctx *h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->D.state); cudaFree(h->D.bonds);
+  cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
+  cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
+  parallel_free(h->PC);
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int mskc_set_rates(mskc_ctx *h, const double *PtransE, const double *PtransD, const double *PtransAbs, const double *PtransDes, double PtransZig) {
+  if (!h || !PtransE || !PtransD) return set_err(h, "mskc_set_rates: NULL argument");
+  CK(cudaSetDevice(h->device));
+  h->h_PE.assign(PtransE, PtransE + 12288); h->h_PD.assign(PtransD, PtransD + 9);
+  h->h_PAbs.assign(12, 0.0); h->h_PDes.assign(12, 0.0);
+  if (PtransAbs) h->h_PAbs.assign(PtransAbs, PtransAbs + 12);
+  if (PtransDes) h->h_PDes.assign(PtransDes, PtransDes + 12);
+  CK(cudaMemcpyAsync(h->d_PE, h->h_PE.data(), 12288 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_PD, h->h_PD.data(), 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_PAbs, h->h_PAbs.data(), 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_PDes, h->h_PDes.data(), 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->D.PZig = PtransZig;
+  h->have_rates = true;
+  return 0;
+}
+
+extern "C" int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double sigma, double Tflex, int tmin, int tmax) {
+  if (!h) return set_err(h, "mskc_set_la: NULL handle");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  if (!enable) { D.la = 0; D.keepT = 0; return 0; }
+  if (!h->have_rates) return set_err(h, "mskc_set_la: call mskc_set_rates first");
+  if (tmin < 1 || tmax > 8191 || tmax < tmin) return set_err(h, "mskc_set_la: temperature range must lie in 1..8191 K (13-bit field)");
+  const double kb = 0.00008617330350;               // Get_Prob.f:70
+  std::vector<short> slot(12288, -1);
+  int nnz = 0;
+  for (int i = 0; i < 12288; i++) if (h->h_PE[i] != 0.0) slot[i] = (short)nnz++;
+  if (nnz == 0) nnz = 1;
+  int nt = tmax - tmin + 1;
+  std::vector<double> E((size_t)nt * nnz, 0.0), Dt((size_t)nt * 9, 0.0);
+  for (int t = tmin; t <= tmax; t++) {
+    int temperature = t;
+    for (int i = 0; i < 12288; i++) if (slot[i] >= 0)   // Get_Prob.f:143-144
+      E[(size_t)(t - tmin) * nnz + slot[i]] = P0 * exp(-h->h_PE[i] / (kb * temperature)) * 1.0;
+    for (int i = 0; i < 9; i++) {                       // Get_Prob.f:146-148
+      double d = h->h_PD[i];
+      Dt[(size_t)(t - tmin) * 9 + i] = 0.5 * P0 * exp(-d / (kb * Tm)) * (1.0 + erf((temperature - Tflex) / sigma)) * (d != 0.0 ? 1.0 : 0.0);
+    }
+  }
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D);
+  CK(cudaMalloc(&h->d_la_slot, 12288 * sizeof(short)));
+  CK(cudaMalloc(&h->d_la_E, E.size() * sizeof(double)));
+  CK(cudaMalloc(&h->d_la_D, Dt.size() * sizeof(double)));
+  CK(cudaMemcpy(h->d_la_slot, slot.data(), 12288 * sizeof(short), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_E, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_D, Dt.data(), Dt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  D.la = 1; D.keepT = 1; D.la_tmin = tmin; D.la_tmax = tmax; D.la_nnz = nnz;
+  D.la_slot = h->d_la_slot; D.la_E = h->d_la_E; D.la_D = h->d_la_D;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state upload
+static inline uint64_t h_enc_bonds(const DevCtx &D, const int32_t s[3], const int32_t nn[12], bool *far) {
+  uint64_t r = 0;
+  for (int i = 0; i < 4; i++) {
+    const int32_t *n = nn + 3 * i;
+    unsigned raw = 0;
+    if (!(n[0] == 0 && n[1] == 0 && n[2] == 0)) {
+      int dx = n[0] - s[0], dy = n[1] - s[1], dz = n[2] - s[2];
+      if (dx > D.LX / 2) dx -= D.LX; else if (dx < -(D.LX / 2)) dx += D.LX;
+      if (dy > D.LY / 2) dy -= D.LY; else if (dy < -(D.LY / 2)) dy += D.LY;
+      if (dx < -15 || dx > 15 || dy < -15 || dy > 15 || dz < -15 || dz > 15) { *far = true; dx = dy = dz = 0; }
+      raw = (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
+    }
+    r |= (uint64_t)raw << (16 * i);
+  }
+  return r;
+}
+static inline void h_dec_bonds(const DevCtx &D, const int32_t s[3], uint64_t b, int32_t nn[12]) {
+  for (int i = 0; i < 4; i++) {
+    unsigned raw = (unsigned)((b >> (16 * i)) & 0xFFFFu);
+    int32_t *n = nn + 3 * i;
+    if (raw == 0) { n[0] = n[1] = n[2] = 0; continue; }
+    n[0] = s[0] + (int)(raw & 31u) - 16; n[1] = s[1] + (int)((raw >> 5) & 31u) - 16; n[2] = s[2] + (int)((raw >> 10) & 31u) - 16;
+    if (n[0] >= D.LX) n[0] -= D.LX; else if (n[0] < 0) n[0] += D.LX;
+    if (n[1] >= D.LY) n[1] -= D.LY; else if (n[1] < 0) n[1] += D.LY;
+  }
+}
+
+static int ensure_parity_buffers(mskc_ctx *h) {
+  if (h->d_Tree) return 0;
+  size_t tsz = (size_t)1 << h->Levels;
+  CK(cudaMalloc(&h->d_Tree, tsz * sizeof(double)));
+  CK(cudaMalloc(&h->d_lattind, h->D.ncell * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->d_mc_cell, ((size_t)h->NumMcMax + 2) * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->d_mc_ev, ((size_t)h->NumMcMax + 2) * sizeof(int)));
+  CK(cudaMalloc(&h->d_void_cell, ((size_t)h->NumVdMax + 2) * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->d_ps, sizeof(ParityState)));
+  return 0;
+}
+
+extern "C" int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
+                                 int n_mc, const int32_t *mc_xyz, const int32_t *mc_nn, const int32_t *mc_event, const double *mc_rate,
+                                 int n_bulk, const int32_t *bulk_xyz, const int32_t *bulk_nn,
+                                 int n_void, const int32_t *void_xyz, const int32_t *void_nn) {
+  if (!h || !LattCoo) return set_err(h, "mskc_upload_state: NULL argument");
+  if (n_mc >= h->NumMcMax) return set_err(h, "troppe particelle cinetiche (%d >= %d)", n_mc, h->NumMcMax);
+  if (n_void >= h->NumVdMax) return set_err(h, "troppe vacanze");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  if (ensure_parity_buffers(h)) return -1;
+  CK(cudaMemcpyAsync(D.state, LattCoo, D.ncell * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  // bonds + lattind are assembled on the host (sparse) and scattered on the device
+  size_t nrec = (size_t)n_mc + n_bulk + n_void;
+  std::vector<uint32_t> rc(nrec ? nrec : 1), rind(nrec ? nrec : 1); std::vector<uint64_t> rb(nrec ? nrec : 1);
+  bool far = false; size_t k = 0;
+  auto cell_of = [&](const int32_t *p) { return (uint32_t)((long long)p[0] + (long long)D.LX * ((long long)p[1] + (long long)D.LY * (long long)p[2])); };
+  for (int i = 0; i < n_bulk; i++, k++) { rc[k] = cell_of(bulk_xyz + 3 * i); rb[k] = h_enc_bonds(D, bulk_xyz + 3 * i, bulk_nn + 12 * i, &far); rind[k] = 0; }
+  for (int i = 0; i < n_void; i++, k++) { rc[k] = cell_of(void_xyz + 3 * i); rb[k] = h_enc_bonds(D, void_xyz + 3 * i, void_nn + 12 * i, &far); rind[k] = (uint32_t)(i + 1); }
+  for (int i = 0; i < n_mc; i++, k++) { rc[k] = cell_of(mc_xyz + 3 * i); rb[k] = h_enc_bonds(D, mc_xyz + 3 * i, mc_nn + 12 * i, &far); rind[k] = (uint32_t)(i + 1); }
+  if (far) return set_err(h, "mskc_upload_state: %s", dev_err_text(E_FARBOND));
+  uint32_t *d_rc = nullptr, *d_rind = nullptr; unsigned long long *d_rb = nullptr;
+  CK(cudaMalloc(&d_rc, rc.size() * 4)); CK(cudaMalloc(&d_rind, rind.size() * 4)); CK(cudaMalloc(&d_rb, rb.size() * 8));
+  CK(cudaMemcpyAsync(d_rc, rc.data(), rc.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_rind, rind.data(), rind.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_rb, rb.data(), rb.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(D.bonds, 0, D.ncell * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->d_lattind, 0, D.ncell * sizeof(uint32_t), h->stream));
+  if (nrec) scatter_records<<<(unsigned)((nrec + 255) / 256), 256, 0, h->stream>>>(D.bonds, h->d_lattind, d_rc, d_rb, d_rind, (long long)nrec);
+  // MC list, void list, rate tree
+  std::vector<uint32_t> mcc((size_t)h->NumMcMax + 2, 0xFFFFFFFFu), vdc((size_t)h->NumVdMax + 2, 0xFFFFFFFFu);
+  std::vector<int> mce((size_t)h->NumMcMax + 2, 0);
+  size_t tsz = (size_t)1 << h->Levels, leaf0 = tsz >> 1;
+  std::vector<double> tree(tsz, 0.0);
+  for (int i = 0; i < n_mc; i++) { mcc[i + 1] = cell_of(mc_xyz + 3 * i); mce[i + 1] = mc_event[i]; tree[leaf0 + i] = mc_rate[i]; }
+  for (int i = 0; i < n_void; i++) vdc[i + 1] = cell_of(void_xyz + 3 * i);
+  // The tree as n successive UpdateTree calls leave it: every inner node is left+right of its final
+  // children (each node is last written with both children final), so one bottom-up pass is identical.
+  for (size_t p = leaf0 - 1; p >= 1; p--) tree[p] = tree[2 * p] + tree[2 * p + 1];
+  CK(cudaMemcpyAsync(h->d_Tree, tree.data(), tsz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_mc_cell, mcc.data(), mcc.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_mc_ev, mce.data(), mce.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_void_cell, vdc.data(), vdc.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  ParityState &S = h->h_ps;
+  int idum = S.idum, runtype = S.runtype, iff = S.r_iff, inext = S.r_inext, inextp = S.r_inextp; long long counter = S.counter;
+  int ma[56]; memcpy(ma, S.r_ma, sizeof ma);
+  memset(&S, 0, sizeof S);
+  S.idum = idum; S.runtype = runtype ? runtype : 'R'; S.r_iff = iff; S.r_inext = inext; S.r_inextp = inextp; S.counter = counter; memcpy(S.r_ma, ma, sizeof ma);
+  S.Iter = 1; S.Time = 0.0; S.NumAdAtom = n_mc; S.NumAtoms = n_bulk; S.NumVoids = n_void;
+  CK(cudaMemcpyAsync(h->d_ps, &S, sizeof S, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->d_err, 0, 8 * sizeof(int), h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_rc); cudaFree(d_rind); cudaFree(d_rb);
+  h->parity_ready = true; h->have_state = true;
+  // the parallel sampler's tile lists are (re)built lazily from the uploaded MC list
+  if (parallel_build_from_lists(h->PC, D, h->stream, n_mc, mcc.data() + 1, mce.data() + 1, mc_rate, n_bulk, n_void, &h->err)) { g_last_error = h->err; return -1; }
+  h->parallel_ready = true;
+  return 0;
+}
+
+extern "C" int mskc_seed(mskc_ctx *h, int idum, int runtype, int64_t counter0, const int32_t *ran3_state) {
+  if (!h) return set_err(h, "mskc_seed: NULL handle");
+  CK(cudaSetDevice(h->device));
+  ParityState &S = h->h_ps;
+  if (h->parity_ready) { CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost)); }
+  S.idum = idum; S.runtype = runtype; S.counter = counter0;
+  if (ran3_state) { S.r_iff = ran3_state[0]; S.r_inext = ran3_state[1]; S.r_inextp = ran3_state[2]; for (int i = 1; i <= 55; i++) S.r_ma[i] = ran3_state[2 + i]; }
+  else { S.r_iff = 0; S.r_inext = 0; S.r_inextp = 0; memset(S.r_ma, 0, sizeof S.r_ma); }
+  if (h->parity_ready) { CK(cudaMemcpy(h->d_ps, &S, sizeof S, cudaMemcpyHostToDevice)); }
+  return 0;
+}
+extern "C" int mskc_get_rng(mskc_ctx *h, int32_t *ran3_state, int64_t *counter, int32_t *idum) {
+  if (!h || !h->parity_ready) return set_err(h, "mskc_get_rng: no state");
+  CK(cudaSetDevice(h->device));
+  ParityState &S = h->h_ps;
+  CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
+  if (ran3_state) { ran3_state[0] = S.r_iff; ran3_state[1] = S.r_inext; ran3_state[2] = S.r_inextp; for (int i = 1; i <= 55; i++) ran3_state[2 + i] = S.r_ma[i]; }
+  if (counter) *counter = S.counter;
+  if (idum) *idum = S.idum;
+  return 0;
+}
+extern "C" int mskc_set_clock(mskc_ctx *h, int64_t iter, double time, const int32_t *CountCrystal, const int32_t *CountCov) {
+  if (!h || !h->parity_ready) return set_err(h, "mskc_set_clock: upload a state first");
+  CK(cudaSetDevice(h->device));
+  ParityState &S = h->h_ps;
+  CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
+  S.Iter = iter; S.Time = time;
+  for (int i = 0; i < 3; i++) { if (CountCrystal) S.CountCrystal[i] = CountCrystal[i]; if (CountCov) S.CountCov[i] = CountCov[i]; }
+  CK(cudaMemcpy(h->d_ps, &S, sizeof S, cudaMemcpyHostToDevice));
+  h->PC.time = time;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_parity_result *r) {
+  if (!h || !a || !r) return set_err(h, "mskc_run_parity: NULL argument");
+  if (!h->parity_ready || !h->have_rates) return set_err(h, "mskc_run_parity: rates and state must be uploaded first");
+  CK(cudaSetDevice(h->device));
+  ParityPol P{};
+  P.Tree = h->d_Tree; P.Levels = h->Levels; P.NumMcMax = h->NumMcMax; P.NumVdMax = h->NumVdMax; P.leaf0 = 1 << (h->Levels - 1);
+  P.lattind = h->d_lattind; P.mc_cell = h->d_mc_cell; P.void_cell = h->d_void_cell; P.mc_ev = h->d_mc_ev; P.ps = h->d_ps;
+  ParityArgs A{};
+  A.max_iter = a->max_iter; A.out_every = a->out_every; A.framecounter = a->framecounter; A.max_time = a->max_time; A.out_time = a->out_time;
+  A.exit_on_time = a->exit_on_time;
+  // The kernel is launched in slices so that a single launch stays well below any watchdog.
+  const long long slice = 2000000;
+  long long remaining = a->event_budget > 0 ? a->event_budget : -1;
+  memset(r, 0, sizeof *r);
+  float total_ms = 0; int launches = 0;
+  while (true) {
+    A.event_budget = (remaining < 0 || remaining > slice) ? slice : remaining;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    parity_kernel<<<1, 32, 0, h->stream>>>(h->D, P, A);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h->h_ps, h->d_ps, sizeof(ParityState), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); total_ms += ms; launches++;
+    ParityState &S = h->h_ps;
+    r->events_done += S.events_done; r->site_updates += S.site_updates;
+    A.framecounter = S.framecounter;
+    if (remaining > 0) remaining -= S.events_done;
+    if (S.stop_reason != MSKC_STOP_BUDGET || remaining == 0) break;
+  }
+  ParityState &S = h->h_ps;
+  r->iter = S.Iter; r->iter_out = S.IterOut; r->time = S.Time;
+  for (int i = 0; i < 3; i++) r->last_site[i] = S.last_site[i];
+  r->stop_reason = S.stop_reason; r->num_atoms = S.NumAtoms; r->num_voids = S.NumVoids; r->num_adatom = S.NumAdAtom;
+  r->kernel_ms = total_ms; r->launches = launches;
+  CK(cudaMemcpy(&r->tree_root, h->d_Tree + 1, sizeof(double), cudaMemcpyDeviceToHost));
+  h->PC.lists_stale = true;
+  if (S.stop_reason == MSKC_STOP_ERROR) { check_dev_err(h); return -1; }
+  return check_dev_err(h);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int mskc_download_lattice(mskc_ctx *h, int32_t *LattCoo) {
+  if (!h || !LattCoo) return set_err(h, "mskc_download_lattice: NULL argument");
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpyAsync(LattCoo, h->D.state, h->D.ncell * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->PC.listed_flag_in_state) { for (long long i = 0; i < h->D.ncell; i++) LattCoo[i] &= ~(int32_t)(1u << 30); }
+  return 0;
+}
+extern "C" int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const int32_t *word) {
+  if (!h) return set_err(h, "mskc_patch_lattice: NULL handle");
+  CK(cudaSetDevice(h->device));
+  for (int i = 0; i < n; i++) {
+    if (cell[i] < 0 || cell[i] >= h->D.ncell) return set_err(h, "mskc_patch_lattice: cell out of range");
+    CK(cudaMemcpyAsync(h->D.state + cell[i], word + i, 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int mskc_get_counters(mskc_ctx *h, mskc_counters *c) {
+  if (!h || !c) return set_err(h, "mskc_get_counters: NULL argument");
+  if (!h->parity_ready) return set_err(h, "mskc_get_counters: no state");
+  CK(cudaSetDevice(h->device));
+  ParityState &S = h->h_ps;
+  CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
+  memset(c, 0, sizeof *c);
+  c->num_atoms = S.NumAtoms; c->num_voids = S.NumVoids; c->num_adatom = S.NumAdAtom;
+  for (int i = 0; i < 3; i++) { c->CountCrystal[i] = S.CountCrystal[i]; c->CountCov[i] = S.CountCov[i]; }
+  c->iter = S.Iter; c->time = S.Time;
+  if (h->PC.ran) parallel_fill_counters(h->PC, c);
+  return 0;
+}
+
+extern "C" int mskc_download_lists(mskc_ctx *h, int32_t *mc_xyz, int32_t *mc_nn, int32_t *mc_event, double *mc_rate,
+                                   int32_t *void_xyz, int32_t *void_nn, int32_t *bulk_xyz, int32_t *bulk_nn, int64_t bulk_cap, int64_t *n_bulk_found) {
+  if (!h || !h->parity_ready) return set_err(h, "mskc_download_lists: no state");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  ParityState &S = h->h_ps;
+  CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
+  long long plane = (long long)D.LX * D.LY;
+  auto xyz_of = [&](uint32_t c, int32_t *p) { p[2] = (int32_t)(c / plane); long long r = c - (long long)p[2] * plane; p[1] = (int32_t)(r / D.LX); p[0] = (int32_t)(r - (long long)p[1] * D.LX); };
+  auto fetch_bonds = [&](const std::vector<uint32_t> &cells, std::vector<uint64_t> &out) -> int {
+    out.assign(cells.size(), 0);
+    if (cells.empty()) return 0;
+    uint32_t *d_c = nullptr; unsigned long long *d_b = nullptr;
+    CK(cudaMalloc(&d_c, cells.size() * 4)); CK(cudaMalloc(&d_b, cells.size() * 8));
+    CK(cudaMemcpy(d_c, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
+    gather_bonds<<<(unsigned)((cells.size() + 255) / 256), 256, 0, h->stream>>>(D.bonds, d_c, d_b, (long long)cells.size());
+    CK(cudaMemcpyAsync(out.data(), d_b, cells.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_c); cudaFree(d_b);
+    return 0;
+  };
+  if (mc_xyz || mc_nn || mc_event || mc_rate) {
+    int n = S.NumAdAtom;
+    std::vector<uint32_t> cells(n); std::vector<int> evs(n); std::vector<double> rates(n);
+    if (n) {
+      CK(cudaMemcpy(cells.data(), h->d_mc_cell + 1, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(evs.data(), h->d_mc_ev + 1, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(rates.data(), h->d_Tree + ((size_t)1 << (h->Levels - 1)), (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint64_t> b; if (fetch_bonds(cells, b)) return -1;
+    for (int i = 0; i < n; i++) {
+      int32_t p[3]; xyz_of(cells[i], p);
+      if (mc_xyz) memcpy(mc_xyz + 3 * i, p, 12);
+      if (mc_nn) h_dec_bonds(D, p, b[i], mc_nn + 12 * i);
+      if (mc_event) mc_event[i] = evs[i];
+      if (mc_rate) mc_rate[i] = rates[i];
+    }
+  }
+  if (void_xyz || void_nn) {
+    int n = S.NumVoids;
+    std::vector<uint32_t> cells(n);
+    if (n) CK(cudaMemcpy(cells.data(), h->d_void_cell + 1, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint64_t> b; if (fetch_bonds(cells, b)) return -1;
+    for (int i = 0; i < n; i++) {
+      int32_t p[3]; xyz_of(cells[i], p);
+      if (void_xyz) memcpy(void_xyz + 3 * i, p, 12);
+      if (void_nn) h_dec_bonds(D, p, b[i], void_nn + 12 * i);
+    }
+  }
+  if (bulk_xyz || bulk_nn || n_bulk_found) {
+    // bulk atoms = occupied, non-wall, coordination 4 cells in z,y,x order (compacted on the device)
+    long long cap = bulk_cap > 0 ? bulk_cap : 1;
+    uint32_t *d_c = nullptr; unsigned long long *d_cnt = nullptr;
+    CK(cudaMalloc(&d_c, (size_t)cap * 4)); CK(cudaMalloc(&d_cnt, 8)); CK(cudaMemset(d_cnt, 0, 8));
+    collect_bulk<<<1184, 256, 0, h->stream>>>(D, d_c, cap, d_cnt);
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n_bulk_found) *n_bulk_found = (int64_t)cnt;
+    long long n = (long long)cnt < cap ? (long long)cnt : cap;
+    if ((bulk_xyz || bulk_nn) && n > 0) {
+      std::vector<uint32_t> cells((size_t)n);
+      CK(cudaMemcpy(cells.data(), d_c, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      std::sort(cells.begin(), cells.end());
+      std::vector<uint64_t> b; if (fetch_bonds(cells, b)) return -1;
+      for (long long i = 0; i < n; i++) {
+        int32_t p[3]; xyz_of(cells[i], p);
+        if (bulk_xyz) memcpy(bulk_xyz + 3 * i, p, 12);
+        if (bulk_nn) h_dec_bonds(D, p, b[i], bulk_nn + 12 * i);
+      }
+    }
+    cudaFree(d_c); cudaFree(d_cnt);
+  }
+  return 0;
+}
+
+extern "C" int mskc_state_hash(mskc_ctx *h, uint64_t *hash) {
+  if (!h || !hash || !h->parity_ready) return set_err(h, "mskc_state_hash: no state");
+  CK(cudaSetDevice(h->device));
+  // FNV-1a is sequential by definition: hash on the host from a downloaded copy (test/diagnostic path)
+  std::vector<int32_t> L((size_t)h->D.ncell);
+  if (mskc_download_lattice(h, L.data())) return -1;
+  ParityState &S = h->h_ps;
+  CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
+  uint64_t x = 1469598103934665603ull;
+  for (size_t i = 0; i < L.size(); i++) { x ^= (uint32_t)L[i]; x *= 1099511628211ull; }
+  uint64_t t; memcpy(&t, &S.Time, 8);
+  uint64_t extra[5] = {(uint64_t)S.NumAdAtom, (uint64_t)S.NumAtoms, (uint64_t)S.NumVoids, t, (uint64_t)S.Iter};
+  for (int i = 0; i < 5; i++) { x ^= extra[i]; x *= 1099511628211ull; }
+  *hash = x;
+  return 0;
+}
+
+extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
+  if (!h || !T) return set_err(h, "mskc_set_temperature: NULL argument");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  size_t n = (size_t)D.LX * D.LY * D.LZ;
+  int32_t *d_T = nullptr;
+  CK(cudaMalloc(&d_T, n * 4));
+  CK(cudaMemcpyAsync(d_T, T, n * 4, cudaMemcpyHostToDevice, h->stream));
+  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(D, d_T, (long long)n);
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_T);
+  return 0;
+}
+
+extern "C" int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms) {
+  if (!h || !c) return set_err(h, "mskc_census_lattice: NULL argument");
+  CK(cudaSetDevice(h->device));
+  unsigned long long *d_out = nullptr; double *d_h = nullptr;
+  CK(cudaMalloc(&d_out, 8 * 8)); CK(cudaMalloc(&d_h, 2 * 8));
+  CK(cudaMemsetAsync(d_out, 0, 64, h->stream)); CK(cudaMemsetAsync(d_h, 0, 16, h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  census_kernel<<<148 * 8, 256, 0, h->stream>>>(h->D, d_out, d_h);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  unsigned long long o[8]; double hh[2];
+  CK(cudaMemcpyAsync(o, d_out, 64, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(hh, d_h, 16, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, h->ev0, h->ev1));
+  c->undercoordinated = (int64_t)o[0]; c->coverage = (int64_t)o[1]; c->noepi_bulk = (int64_t)o[2]; c->bulk = (int64_t)o[3]; c->occupied = (int64_t)o[4]; c->walls = (int64_t)o[5];
+  c->mean_height = o[0] ? hh[0] / (double)o[0] : 0.0; c->sq_height = o[0] ? hh[1] / (double)o[0] : 0.0;
+  cudaFree(d_out); cudaFree(d_h);
+  return 0;
+}
+
+// ---- parallel sampler entry points (kernels in mskc_parallel.cuh) -----------------------------------
+extern "C" int mskc_init_flat(mskc_ctx *h, int len1, int walls, int two_species) {
+  if (!h) return set_err(h, "mskc_init_flat: NULL handle");
+  if (!h->have_rates) return set_err(h, "mskc_init_flat: call mskc_set_rates first");
+  CK(cudaSetDevice(h->device));
+  if (parallel_init_flat(h->PC, h->D, h->stream, len1, walls, two_species, &h->err)) { g_last_error = h->err; return -1; }
+  h->parallel_ready = true; h->have_state = true;
+  return check_dev_err(h);
+}
+extern "C" int mskc_run_parallel(mskc_ctx *h, const mskc_parallel_args *a, mskc_parallel_result *r) {
+  if (!h || !a || !r) return set_err(h, "mskc_run_parallel: NULL argument");
+  if (!h->parallel_ready || !h->have_rates) return set_err(h, "mskc_run_parallel: rates and state must be set first");
+  CK(cudaSetDevice(h->device));
+  if (h->PC.lists_stale) return set_err(h, "mskc_run_parallel: the state was advanced in parity mode; upload it again to rebuild the tile lists");
+  if (parallel_run(h->PC, h->D, h->stream, h->ev0, h->ev1, a, r, &h->err)) { g_last_error = h->err; return -1; }
+  return check_dev_err(h);
+}
+extern "C" int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate, float *kernel_ms) {
+  if (!h || !h->parallel_ready) return set_err(h, "mskc_rerate_all: no parallel state");
+  CK(cudaSetDevice(h->device));
+  if (parallel_rerate(h->PC, h->D, h->stream, h->ev0, h->ev1, n_sites, total_rate, kernel_ms, &h->err)) { g_last_error = h->err; return -1; }
+  return check_dev_err(h);
+}

@@ -1,0 +1,208 @@
+// mskc_parity.cuh -- serial-parity mode: the reference's n-fold-way loop replayed on the device.
+//
+// One persistent single-thread kernel walks main.f:304-371 event by event with the reference's own
+// selection structure (complete binary rate tree, AllocateArrays.f / PickTreeEvent.f / UpdateTree.f),
+// the reference's list order (Add.f / Erase.f swap-with-last) and its two random streams (ran3 and the
+// 1000-number 'T' table), so that the lattice words, the event sequence and Time come out bit-identical.
+// Only what the selection needs is kept of the three AoS lists: the MC list is (cell, event) per entry,
+// the void list is (cell); bonds live per cell (mskc_device.cuh) and the bulk list is just a counter.
+#pragma once
+#include "mskc_device.cuh"
+
+namespace mskc {
+
+__device__ const float NUMBERSLIST[1000] = {
+#include "numberslist.inc"
+};
+
+// loop state that survives between launches (main.f:31-54 locals + random.f SAVEd state)
+struct ParityState {
+  long long Iter, IterOut, framecounter, counter, events_done, site_updates;
+  double Time;
+  int NumAdAtom, NumAtoms, NumVoids;
+  int CountCrystal[3], CountCov[3];
+  int idum, runtype, r_iff, r_inext, r_inextp, r_ma[56];
+  int pending, pend_ind, pend_itrans;       // an event picked but not yet applied (frame boundary)
+  int last_site[3];
+  int stop_reason;
+};
+
+struct ParityArgs {
+  long long max_iter, out_every, framecounter, event_budget;
+  double max_time, out_time;
+  int exit_on_time;
+};
+
+struct ParityPol {
+  double *Tree; int Levels, NumMcMax, NumVdMax, leaf0;
+  uint32_t *lattind, *mc_cell, *void_cell; int *mc_ev;
+  ParityState *ps;
+  int NumAdAtom, NumAtoms, NumVoids;
+  int CountCrystal[3], CountCov[3];
+  long long n_getprob, n_ran3;
+
+  __device__ __forceinline__ bool predraw() const { return true; }
+  __device__ __forceinline__ double tree_root() const { return Tree[1]; }
+
+  // mcevent/random.f:22-69
+  __device__ double uniform() {
+    const int mbig = 1000000000, mseed = 161803398, mz = 0;
+    const double fac = (double)(1.0f / 1.0e9f);
+    ParityState &s = *ps;
+    int *ma = s.r_ma, mj, mk;
+    n_ran3++;
+    if (s.idum < 0 || s.r_iff == 0) {
+      s.r_iff = 1;
+      mj = mseed - abs(s.idum); mj = mj % mbig; ma[55] = mj; mk = 1;
+      for (int i = 1; i <= 54; i++) { int ii = (21 * i) % 55; ma[ii] = mk; mk = mj - mk; if (mk < mz) mk += mbig; mj = ma[ii]; }
+      for (int k = 1; k <= 4; k++) for (int i = 1; i <= 55; i++) { ma[i] = ma[i] - ma[1 + (i + 30) % 55]; if (ma[i] < mz) ma[i] += mbig; }
+      s.r_inext = 0; s.r_inextp = 31; s.idum = 1;
+    }
+    if (++s.r_inext == 56) s.r_inext = 1;
+    if (++s.r_inextp == 56) s.r_inextp = 1;
+    mj = ma[s.r_inext] - ma[s.r_inextp];
+    if (mj < mz) mj += mbig;
+    ma[s.r_inext] = mj;
+    return mj * fac;
+  }
+
+  // mcevent/UpdateTree.f:25-66.  The sibling loads are independent of the running sum, so they are
+  // issued together; the 19 adds are the only dependent chain.
+  __device__ void update_tree(const DevCtx &D, int Index, double P) {
+    if (P == 0 && Index < NumAdAtom) { fail(D, E_TREE_ZERO, Index); return; }
+    if (Index > NumAdAtom) { fail(D, E_TREE_IDX, Index, NumAdAtom); return; }
+    int Pos = Index + leaf0 - 1;
+    double sib[24];
+    int nlev = Levels - 1;
+#pragma unroll
+    for (int l = 0; l < 24; l++) if (l < nlev) sib[l] = Tree[(Pos >> l) ^ 1];
+    Tree[Pos] = P;
+    double v = P;
+#pragma unroll
+    for (int l = 0; l < 24; l++) if (l < nlev) { v = v + sib[l]; Tree[Pos >> (l + 1)] = v; }
+  }
+  __device__ __forceinline__ double leaf(int Index) const { return Tree[Index + leaf0 - 1]; }
+
+  // mcevent/Add.f:24-53
+  __device__ void add_mc(const DevCtx &D, P3 s, long long c, const P3 nn[4], int ev, double p) {
+    if (p == 0) { fail(D, E_ADD_ZERO, s.x, s.y, s.z); return; }
+    NumAdAtom++;
+    if (NumAdAtom >= NumMcMax) { fail(D, E_MC_FULL, NumAdAtom); NumAdAtom--; return; }
+    lattind[c] = (uint32_t)NumAdAtom;
+    mc_cell[NumAdAtom] = (uint32_t)c; mc_ev[NumAdAtom] = ev;
+    D.bonds[c] = enc_bonds(D, s, nn);
+    update_tree(D, NumAdAtom, p);
+  }
+  __device__ __forceinline__ void set_rate(const DevCtx &D, P3 s, long long c, int ev, double p) {
+    int ind = (int)lattind[c];
+    if (ind < 1 || ind > NumMcMax) { fail(D, E_ERASE, s.x, s.y, s.z, ind); return; }
+    mc_ev[ind] = ev;
+    update_tree(D, ind, p);
+  }
+  // mcevent/Erase.f:24-78
+  __device__ void erase_mc(const DevCtx &D, P3 s, long long c) {
+    int IndNN = (int)lattind[c];
+    if (IndNN > NumMcMax || IndNN == 0) { fail(D, E_ERASE, s.x, s.y, s.z, IndNN); return; }
+    if (IndNN >= NumAdAtom) {
+      mc_cell[IndNN] = 0xFFFFFFFFu; mc_ev[IndNN] = 0;
+      lattind[c] = 0; D.bonds[c] = 0ull;
+      update_tree(D, IndNN, 0.0);
+      NumAdAtom--;
+    } else {
+      uint32_t moved = mc_cell[NumAdAtom];
+      mc_cell[IndNN] = moved; mc_ev[IndNN] = mc_ev[NumAdAtom];
+      update_tree(D, IndNN, leaf(NumAdAtom));
+      update_tree(D, NumAdAtom, 0.0);
+      lattind[moved] = (uint32_t)IndNN;
+      mc_cell[NumAdAtom] = 0xFFFFFFFFu; mc_ev[NumAdAtom] = 0;
+      lattind[c] = 0; D.bonds[c] = 0ull;
+      NumAdAtom--;
+    }
+  }
+  // mcevent/Add.f:82-100, Erase.f:135-179
+  __device__ void add_void(const DevCtx &D, P3 s, long long c, const P3 nn[4]) {
+    NumVoids++;
+    if (NumVoids >= NumVdMax) { fail(D, E_VOID_FULL, NumVoids); NumVoids--; return; }
+    lattind[c] = (uint32_t)NumVoids; void_cell[NumVoids] = (uint32_t)c;
+    D.bonds[c] = enc_bonds(D, s, nn);
+  }
+  __device__ void erase_void(const DevCtx &D, P3 s, long long c) {
+    int IndNN = (int)lattind[c];
+    if (IndNN > NumVdMax || IndNN == 0) { fail(D, E_ERASE, s.x, s.y, s.z, -IndNN); return; }
+    if (IndNN != NumVoids) { uint32_t moved = void_cell[NumVoids]; void_cell[IndNN] = moved; lattind[moved] = (uint32_t)IndNN; }
+    void_cell[NumVoids] = 0xFFFFFFFFu;
+    lattind[c] = 0; D.bonds[c] = 0ull;
+    NumVoids--;
+  }
+  // mcevent/Add.f:58-76, Erase.f:84-128: the bulk list is never enumerated by the loop, a counter suffices
+  __device__ __forceinline__ void add_bulk(const DevCtx &D, P3 s, long long c, const P3 nn[4]) { NumAtoms++; lattind[c] = 0; D.bonds[c] = enc_bonds(D, s, nn); }
+  __device__ __forceinline__ void erase_bulk(const DevCtx &D, P3 s, long long c) { NumAtoms--; D.bonds[c] = 0ull; }
+
+  // Get_Prob.f:266-269 looks a coverage neighbour up in ListAdAtom even when it sits on a 4-coordinated
+  // empty site, i.e. in ListVoid: it reads the MC record that happens to have the vacancy's index.  The
+  // CVD goldens depend on it (26 967 times in CVD-Si-SiH2), so parity mode reproduces the lookup.
+  __device__ bool cov_void_recipr(const DevCtx &D, P3 n, long long cn, P3 me) {
+    int v = (int)lattind[cn];
+    if (v < 1 || v > NumAdAtom) return eq(zero3(), me);          // zeroed record: NextNXYZ = 0
+    uint32_t c2 = mc_cell[v];
+    if (c2 == 0xFFFFFFFFu) return eq(zero3(), me);
+    return recipr_b(D, cell_xyz(D, (long long)c2), D.bonds[c2], me);
+  }
+};
+
+// mcevent/PickTreeEvent.f:25-70 + main.f:304-371
+__global__ void __launch_bounds__(32, 1) parity_kernel(DevCtx D, ParityPol P0, ParityArgs A) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ParityPol pol = P0;
+  ParityState &S = *pol.ps;
+  pol.NumAdAtom = S.NumAdAtom; pol.NumAtoms = S.NumAtoms; pol.NumVoids = S.NumVoids;
+  for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = S.CountCrystal[i]; pol.CountCov[i] = S.CountCov[i]; }
+  pol.n_getprob = 0; pol.n_ran3 = 0;
+  long long Iter = S.Iter, done = 0;
+  double Time = S.Time;
+  long long framecounter = A.framecounter;
+  int stop = 0;
+  const int nlev = pol.Levels - 1;
+  while (true) {
+    int Ind, Itrans;
+    if (S.pending) { Ind = S.pend_ind; Itrans = S.pend_itrans; S.pending = 0; }
+    else {
+      if (A.event_budget > 0 && done >= A.event_budget) { stop = 0; break; }
+      S.IterOut = Iter;
+      if (pol.NumAdAtom <= 20) { stop = 4; break; }
+      int idx = 1;
+      for (int lev = 0; lev < nlev; lev++) {
+        double r;
+        if (S.runtype == 'T') { S.counter++; r = (double)NUMBERSLIST[(S.counter - 1) % 1000]; }
+        else r = pol.uniform();
+        double Patom = r * pol.Tree[idx];
+        idx <<= 1;
+        if (pol.Tree[idx] < Patom) idx++;
+      }
+      Ind = idx - pol.leaf0 + 1;
+      if (Ind > pol.NumAdAtom) { fail(D, E_PICK, Ind, pol.NumAdAtom); stop = -1; break; }
+      Time = Time + 1.0 / pol.Tree[1];
+      Itrans = pol.mc_ev[Ind];
+      P3 s = cell_xyz(D, (long long)pol.mc_cell[Ind]);
+      S.last_site[0] = s.x; S.last_site[1] = s.y; S.last_site[2] = s.z;
+      bool frame = false;
+      if (!A.exit_on_time) { if (A.out_every > 0 && (Iter % A.out_every) == 0) frame = true; }
+      else if (A.out_time > 0 && Time >= ((double)(framecounter + 1) * A.out_time)) { frame = true; framecounter++; }
+      if (frame) { S.pending = 1; S.pend_ind = Ind; S.pend_itrans = Itrans; stop = 3; break; }
+    }
+    P3 Site = cell_xyz(D, (long long)pol.mc_cell[Ind]);
+    apply_event(D, pol, Site, Itrans);
+    done++;
+    Iter++;
+    if (D.err[0] != 0) { stop = -1; break; }
+    if (!A.exit_on_time) { if (Iter > A.max_iter) { stop = 1; break; } }
+    else if (Time > A.max_time) { stop = 2; break; }
+  }
+  S.Iter = Iter; S.Time = Time; S.framecounter = framecounter;
+  S.NumAdAtom = pol.NumAdAtom; S.NumAtoms = pol.NumAtoms; S.NumVoids = pol.NumVoids;
+  for (int i = 0; i < 3; i++) { S.CountCrystal[i] = pol.CountCrystal[i]; S.CountCov[i] = pol.CountCov[i]; }
+  S.events_done = done; S.site_updates = pol.n_getprob;
+  S.stop_reason = stop;
+}
+
+}  // namespace mskc

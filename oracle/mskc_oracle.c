@@ -1609,3 +1609,63 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------ accessors for the test harness */
+int32_t *orc_lattcoo(Orc *o) { return o->LattCoo; }
+void orc_get_sizes(Orc *o, int64_t out[8]) {
+  out[0] = o->NumAdAtom; out[1] = o->NumAtoms; out[2] = o->NumVoids; out[3] = o->Iter; out[4] = o->IterOut; out[5] = (int64_t)o->ncell; out[6] = o->Levels; out[7] = o->done;
+}
+double orc_get_time(Orc *o) { return o->Time; }
+double orc_get_tree_root(Orc *o) { return o->Tree[1]; }
+void orc_get_last_site(Orc *o, int32_t s[3]) { s[0] = o->last_site[0]; s[1] = o->last_site[1]; s[2] = o->last_site[2]; }
+void orc_export_lists(Orc *o, int32_t *mc_xyz, int32_t *mc_nn, int32_t *mc_ev, double *mc_rate,
+                      int32_t *bulk_xyz, int32_t *bulk_nn, int32_t *void_xyz, int32_t *void_nn) {
+  for (int i = 1; i <= o->NumAdAtom; i++) {
+    if (mc_xyz) memcpy(mc_xyz + 3 * (i - 1), o->ListAdAtom[i].xyz, 12);
+    if (mc_nn) memcpy(mc_nn + 12 * (i - 1), o->ListAdAtom[i].nn, 48);
+    if (mc_ev) mc_ev[i - 1] = o->ListAdAtom[i].ev;
+    if (mc_rate) mc_rate[i - 1] = o->Tree[i + (1 << (o->Levels - 1)) - 1];
+  }
+  for (int i = 1; i <= o->NumAtoms; i++) {
+    if (bulk_xyz) memcpy(bulk_xyz + 3 * (i - 1), o->ListAtom[i].xyz, 12);
+    if (bulk_nn) memcpy(bulk_nn + 12 * (i - 1), o->ListAtom[i].nn, 48);
+  }
+  for (int i = 1; i <= o->NumVoids; i++) {
+    if (void_xyz) memcpy(void_xyz + 3 * (i - 1), o->ListVoid[i].xyz, 12);
+    if (void_nn) memcpy(void_nn + 12 * (i - 1), o->ListVoid[i].nn, 48);
+  }
+}
+void orc_get_tables(Orc *o, double *PE, double *PD, double *PAbs, double *PDes, double *scal /*[8]: PtransZig,sf,Tm,P0,sigma,Tflex,MaxTime,OutTime*/) {
+  memcpy(PE, o->PtransE, sizeof o->PtransE); memcpy(PD, o->PtransD, sizeof o->PtransD);
+  memcpy(PAbs, o->PtransAbs, sizeof o->PtransAbs); memcpy(PDes, o->PtransDes, sizeof o->PtransDes);
+  scal[0] = o->PtransZig; scal[1] = o->sf; scal[2] = o->Tm; scal[3] = o->P0; scal[4] = o->sigma; scal[5] = o->Tflex; scal[6] = o->MaxTime; scal[7] = o->OutTime;
+}
+void orc_get_species(Orc *o, int32_t out[8]) {
+  out[0] = o->NCrystal; out[1] = o->NCov; for (int i = 0; i < 3; i++) { out[2 + i] = o->ListCrystal[i]; out[5 + i] = o->ListCov[i]; }
+}
+void orc_get_run(Orc *o, int64_t out[4], char initst[4], char runtype[4], char exitstrategy[8]) {
+  out[0] = o->MaxIter; out[1] = o->OutMolMol; out[2] = o->Idum; out[3] = o->counter;
+  strcpy(initst, o->InitSt); strcpy(runtype, o->RunType); strcpy(exitstrategy, o->ExitStrategy);
+}
+void orc_get_rng(Orc *o, int32_t st[58], int64_t *counter, int32_t *idum) {
+  st[0] = o->r_iff; st[1] = o->r_inext; st[2] = o->r_inextp; for (int i = 1; i <= 55; i++) st[2 + i] = o->r_ma[i];
+  *counter = o->counter; *idum = o->Idum;
+}
+void orc_get_counts(Orc *o, int32_t cc[3], int32_t cv[3]) { for (int i = 0; i < 3; i++) { cc[i] = o->CountCrystal[i]; cv[i] = o->CountCov[i]; } }
+void orc_get_quirks(Orc *o, int64_t q[8]) { q[0] = o->q_stale_nbuff; q[1] = o->q_wl_iso; q[2] = o->q_wl_cov; q[3] = o->q_wl_dep; q[4] = o->q_wl_des; q[5] = o->q_oob; q[6] = o->q_anom; q[7] = o->n_getprob; }
+void orc_set_io(Orc *o, const char *outdir, const char *logpath, int write_files) {
+  if (outdir) { strncpy(o->outdir, outdir, sizeof o->outdir - 1); }
+  o->write_files = write_files;
+  if (o->log && o->log != stdout) fclose(o->log);
+  o->log = logpath ? fopen(logpath, "w") : NULL;
+}
+void orc_set_run(Orc *o, int64_t maxiter, int64_t outmolmol, int runtype_T, int idum, int faithful_cost) {
+  if (maxiter > 0) o->MaxIter = maxiter;
+  if (outmolmol > 0) o->OutMolMol = outmolmol;
+  if (runtype_T >= 0) { o->RunType[0] = runtype_T ? 'T' : 'R'; o->RunType[1] = 0; }
+  if (idum != 0) o->Idum = idum;
+  o->faithful_cost = faithful_cost;
+}
+void orc_set_trace(Orc *o, int64_t cap) { free(o->trace); o->trace = cap > 0 ? (OrcTrace *)calloc((size_t)cap, sizeof(OrcTrace)) : NULL; o->trace_cap = cap; o->trace_n = 0; }
+OrcTrace *orc_get_trace(Orc *o, int64_t *n) { *n = o->trace_n; return o->trace; }
+const char *orc_errmsg(Orc *o) { return o->errmsg; }

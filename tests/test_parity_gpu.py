@@ -1,0 +1,63 @@
+"""Serial-parity mode on the GPU against the CPU oracle: same seeded input, bit-exact lattice words,
+event sequence end state and KMC time (integer work bit-exact, Time compared as raw bits)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from cases import make_start
+from oracle_binding import Oracle, upload_oracle_state
+
+pytestmark = pytest.mark.gpu
+
+# (case, box, lens, events): reduced boxes of the reference regression cases
+SMALL = [
+    ("Si-SL", (96, 96, 240), (216, 0, 0), 50000),
+    ("surface", (96, 96, 240), (48, 0, 0), 300000),
+    ("cube", (144, 144, 144), (48, 48, 48), 300000),
+    ("cube-zigzag", (144, 144, 144), (48, 48, 48), 300000),
+    ("sphere", (144, 144, 144), (60, 0, 0), 300000),
+    ("CVD-Si-SiH2", (96, 96, 96), (48, 0, 0), 400000),
+]
+
+
+def bits(x):
+    return struct.unpack("<Q", struct.pack("<d", x))[0]
+
+
+@pytest.mark.parametrize("case,box,lens,nev", SMALL, ids=[c[0] for c in SMALL])
+def test_parity_small(tmp_path, case, box, lens, nev):
+    from mulskips_b200 import Mskc
+    start = make_start(case, str(tmp_path / "start.dat"), lens=lens, maxiter=10**9, outmolmol=10**9, maxtime=1e30, outtime=1e30)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    assert ctx.state_hash() == orc.hash()
+    done = 0
+    for chunk in (1, 7, 1000, nev - 1008):
+        r = ctx.run_parity(event_budget=chunk)
+        n = orc.run(chunk)
+        assert n == chunk and r.events_done == chunk
+        done += chunk
+        s = orc.sizes()
+        assert (r.num_adatom, r.num_atoms, r.num_voids) == (s["NumAdAtom"], s["NumAtoms"], s["NumVoids"]), f"after {done} events"
+        assert bits(r.time) == bits(orc.time), f"after {done} events"
+        assert tuple(r.last_site) == orc.last_site()
+        assert r.iter == s["Iter"]
+    L = ctx.download_lattice()
+    assert np.array_equal(L, orc.lattcoo())
+    assert ctx.state_hash() == orc.hash()
+    assert bits(r.tree_root) == bits(orc.tree_root)
+    # lists in reference order
+    d, g = orc.lists(), ctx.download_lists()
+    for k in ("mc_xyz", "mc_nn", "mc_event", "void_xyz", "void_nn"):
+        assert np.array_equal(d[k], g[k]), k
+    assert np.array_equal(d["mc_rate"].view(np.uint64), g["mc_rate"].view(np.uint64))
+    cc, cv = orc.counts()
+    c = ctx.counters()
+    assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
+    assert r.site_updates > 0
+    ctx.close(); orc.close()
