@@ -40,6 +40,7 @@ struct mskc_ctx {
   int idum = 0, runtype = 'R';
 };
 
+static int upload_consts(mskc_ctx *h);
 static int set_err(mskc_ctx *h, const char *fmt, ...) {
   char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
   if (h) h->err = buf;
@@ -47,6 +48,22 @@ static int set_err(mskc_ctx *h, const char *fmt, ...) {
   return -1;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return set_err(h, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); } while (0)
+
+// Make h the context the kernels see: DevCtx, tile lists and parity structures go to constant memory.
+// Every API call that launches kernels does this first; calls return only after their stream is idle, so
+// no kernel of another context is in flight when the constants change (one host thread per process).
+static int upload_consts(mskc_ctx *h) {
+  CK(cudaSetDevice(h->device));
+  TileView tv = tile_view(h->PC);
+  ParityView pv{};
+  pv.Tree = h->d_Tree; pv.Levels = h->Levels; pv.NumMcMax = h->NumMcMax; pv.NumVdMax = h->NumVdMax; pv.leaf0 = 1 << (h->Levels - 1);
+  pv.lattind = h->d_lattind; pv.mc_cell = h->d_mc_cell; pv.void_cell = h->d_void_cell; pv.mc_ev = h->d_mc_ev; pv.ps = h->d_ps;
+  CK(cudaMemcpyToSymbolAsync(mskc::D, &h->D, sizeof(DevCtx), 0, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyToSymbolAsync(mskc::V, &tv, sizeof(TileView), 0, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyToSymbolAsync(mskc::PV, &pv, sizeof(ParityView), 0, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
 
 static const char *dev_err_text(int code) {
   switch (code) {
@@ -329,9 +346,7 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   if (!h || !a || !r) return set_err(h, "mskc_run_parity: NULL argument");
   if (!h->parity_ready || !h->have_rates) return set_err(h, "mskc_run_parity: rates and state must be uploaded first");
   CK(cudaSetDevice(h->device));
-  ParityPol P{};
-  P.Tree = h->d_Tree; P.Levels = h->Levels; P.NumMcMax = h->NumMcMax; P.NumVdMax = h->NumVdMax; P.leaf0 = 1 << (h->Levels - 1);
-  P.lattind = h->d_lattind; P.mc_cell = h->d_mc_cell; P.void_cell = h->d_void_cell; P.mc_ev = h->d_mc_ev; P.ps = h->d_ps;
+  if (upload_consts(h)) return -1;
   ParityArgs A{};
   A.max_iter = a->max_iter; A.out_every = a->out_every; A.framecounter = a->framecounter; A.max_time = a->max_time; A.out_time = a->out_time;
   A.exit_on_time = a->exit_on_time;
@@ -343,7 +358,7 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   while (true) {
     A.event_budget = (remaining < 0 || remaining > slice) ? slice : remaining;
     CK(cudaEventRecord(h->ev0, h->stream));
-    parity_kernel<<<1, 32, 0, h->stream>>>(h->D, P, A);
+    parity_kernel<<<1, 32, 0, h->stream>>>(A);
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_ps, h->d_ps, sizeof(ParityState), cudaMemcpyDeviceToHost, h->stream));
@@ -453,7 +468,8 @@ extern "C" int mskc_download_lists(mskc_ctx *h, int32_t *mc_xyz, int32_t *mc_nn,
     long long cap = bulk_cap > 0 ? bulk_cap : 1;
     uint32_t *d_c = nullptr; unsigned long long *d_cnt = nullptr;
     CK(cudaMalloc(&d_c, (size_t)cap * 4)); CK(cudaMalloc(&d_cnt, 8)); CK(cudaMemset(d_cnt, 0, 8));
-    collect_bulk<<<1184, 256, 0, h->stream>>>(D, d_c, cap, d_cnt);
+    if (upload_consts(h)) return -1;
+    collect_bulk<<<1184, 256, 0, h->stream>>>(d_c, cap, d_cnt);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -500,7 +516,8 @@ extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
   int32_t *d_T = nullptr;
   CK(cudaMalloc(&d_T, n * 4));
   CK(cudaMemcpyAsync(d_T, T, n * 4, cudaMemcpyHostToDevice, h->stream));
-  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(D, d_T, (long long)n);
+  if (upload_consts(h)) return -1;
+  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(d_T, (long long)n);
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d_T);
   return 0;
@@ -509,11 +526,12 @@ extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
 extern "C" int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms) {
   if (!h || !c) return set_err(h, "mskc_census_lattice: NULL argument");
   CK(cudaSetDevice(h->device));
+  if (upload_consts(h)) return -1;
   unsigned long long *d_out = nullptr; double *d_h = nullptr;
   CK(cudaMalloc(&d_out, 8 * 8)); CK(cudaMalloc(&d_h, 2 * 8));
   CK(cudaMemsetAsync(d_out, 0, 64, h->stream)); CK(cudaMemsetAsync(d_h, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
-  census_kernel<<<148 * 8, 256, 0, h->stream>>>(h->D, d_out, d_h);
+  census_kernel<<<148 * 8, 256, 0, h->stream>>>(d_out, d_h);
   CK(cudaEventRecord(h->ev1, h->stream));
   unsigned long long o[8]; double hh[2];
   CK(cudaMemcpyAsync(o, d_out, 64, cudaMemcpyDeviceToHost, h->stream));
@@ -531,7 +549,7 @@ extern "C" int mskc_init_flat(mskc_ctx *h, int len1, int walls, int two_species)
   if (!h) return set_err(h, "mskc_init_flat: NULL handle");
   if (!h->have_rates) return set_err(h, "mskc_init_flat: call mskc_set_rates first");
   CK(cudaSetDevice(h->device));
-  if (parallel_init_flat(h->PC, h->D, h->stream, len1, walls, two_species, &h->err)) { g_last_error = h->err; return -1; }
+  if (parallel_init_flat(h->PC, h->D, h->stream, len1, walls, two_species, [h]() { return upload_consts(h); }, &h->err)) { g_last_error = h->err; return -1; }
   h->parallel_ready = true; h->have_state = true;
   return check_dev_err(h);
 }
@@ -540,12 +558,14 @@ extern "C" int mskc_run_parallel(mskc_ctx *h, const mskc_parallel_args *a, mskc_
   if (!h->parallel_ready || !h->have_rates) return set_err(h, "mskc_run_parallel: rates and state must be set first");
   CK(cudaSetDevice(h->device));
   if (h->PC.lists_stale) return set_err(h, "mskc_run_parallel: the state was advanced in parity mode; upload it again to rebuild the tile lists");
+  if (upload_consts(h)) return -1;
   if (parallel_run(h->PC, h->D, h->stream, h->ev0, h->ev1, a, r, &h->err)) { g_last_error = h->err; return -1; }
   return check_dev_err(h);
 }
 extern "C" int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate, float *kernel_ms) {
   if (!h || !h->parallel_ready) return set_err(h, "mskc_rerate_all: no parallel state");
   CK(cudaSetDevice(h->device));
+  if (upload_consts(h)) return -1;
   if (parallel_rerate(h->PC, h->D, h->stream, h->ev0, h->ev1, n_sites, total_rate, kernel_ms, &h->err)) { g_last_error = h->err; return -1; }
   return check_dev_err(h);
 }

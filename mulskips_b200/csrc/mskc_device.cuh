@@ -51,7 +51,13 @@ struct DevCtx {
   int *err;                         // [8]: code, x, y, z, aux...
 };
 
-__device__ __forceinline__ void fail(const DevCtx &D, int code, int a = 0, int b = 0, int c = 0, int d = 0) {
+// The context lives in constant memory: every D.field below is a constant-bank operand (no parameter
+// copies on the stack of the non-inlined transition functions).  mskc_api.cu uploads the handle's
+// DevCtx before launching (one context is "current" per device at a time).
+__constant__ DevCtx D;
+
+// cold path, kept out of line so the hot code stays small (the kernels are instruction-fetch sensitive)
+__device__ __noinline__ void fail(int code, int a = 0, int b = 0, int c = 0, int d = 0) {
   if (atomicCAS(&D.err[0], 0, code) == 0) { D.err[1] = a; D.err[2] = b; D.err[3] = c; D.err[4] = d; }
 }
 
@@ -66,27 +72,38 @@ __device__ __forceinline__ int w_sp(uint32_t w) { return (w >> PosSiC) & 7; }
 
 // cell index; out-of-range z (the reference would read foreign memory) raises E_OOB and is redirected
 // to cell 0 so the kernel can unwind.
-__device__ __forceinline__ long long cidx(const DevCtx &D, P3 p) {
+__device__ __forceinline__ long long cidx(P3 p) {
   if ((unsigned)p.x >= (unsigned)D.LX || (unsigned)p.y >= (unsigned)D.LY || (unsigned)p.z > (unsigned)D.LZ) {
-    fail(D, E_OOB, p.x, p.y, p.z); return 0;
+    fail(E_OOB, p.x, p.y, p.z); return 0;
   }
   return (long long)p.x + (long long)D.LX * ((long long)p.y + (long long)D.LY * (long long)p.z);
 }
-__device__ __forceinline__ P3 cell_xyz(const DevCtx &D, long long c) {
-  P3 p; long long plane = (long long)D.LX * D.LY;
-  p.z = (int)(c / plane); int r = (int)(c - (long long)p.z * plane); p.y = r / D.LX; p.x = r - p.y * D.LX; return p;
+__device__ __forceinline__ P3 cell_xyz(long long c) {     // ncell < 2^32 (mskc_create checks)
+  P3 p; unsigned plane = (unsigned)D.LX * (unsigned)D.LY, cc = (unsigned)c;
+  unsigned z = cc / plane, r = cc - z * plane, y = r / (unsigned)D.LX;
+  p.z = (int)z; p.y = (int)y; p.x = (int)(r - y * (unsigned)D.LX); return p;
+}
+// fire-and-forget loads that pull a cell's words into L1 (results unused; volatile asm is not eliminated)
+__device__ __forceinline__ void touch32(const void *p) { unsigned v; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); }
+__device__ __forceinline__ void touch64(const void *p) { unsigned long long v; asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); }
+__device__ __forceinline__ void touch16(const void *p) { unsigned short v; asm volatile("ld.global.ca.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); }
+__device__ __forceinline__ bool in_box(P3 p) {
+  return (unsigned)p.x < (unsigned)D.LX && (unsigned)p.y < (unsigned)D.LY && (unsigned)p.z <= (unsigned)D.LZ;
+}
+__device__ __forceinline__ long long cidx_nofail(P3 p) {
+  return (long long)p.x + (long long)D.LX * ((long long)p.y + (long long)D.LY * (long long)p.z);
 }
 
 // ---- bond codec ------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned enc_bond(const DevCtx &D, P3 s, P3 n) {
+__device__ __forceinline__ unsigned enc_bond(P3 s, P3 n) {
   if (n.x == 0 && n.y == 0 && n.z == 0) return 0u;      // "not fixed" == absolute origin, as in the reference
   int dx = n.x - s.x, dy = n.y - s.y, dz = n.z - s.z;
   if (dx > D.LX / 2) dx -= D.LX; else if (dx < -(D.LX / 2)) dx += D.LX;
   if (dy > D.LY / 2) dy -= D.LY; else if (dy < -(D.LY / 2)) dy += D.LY;
-  if (dx < -15 || dx > 15 || dy < -15 || dy > 15 || dz < -15 || dz > 15) { fail(D, E_FARBOND, s.x, s.y, s.z); return 0u; }
+  if (dx < -15 || dx > 15 || dy < -15 || dy > 15 || dz < -15 || dz > 15) { fail(E_FARBOND, s.x, s.y, s.z); return 0u; }
   return (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
 }
-__device__ __forceinline__ P3 dec_bond(const DevCtx &D, P3 s, unsigned raw) {
+__device__ __forceinline__ P3 dec_bond(P3 s, unsigned raw) {
   P3 n;
   if (raw == 0u) { n.x = n.y = n.z = 0; return n; }
   n.x = s.x + (int)(raw & 31u) - 16; n.y = s.y + (int)((raw >> 5) & 31u) - 16; n.z = s.z + (int)((raw >> 10) & 31u) - 16;
@@ -94,20 +111,27 @@ __device__ __forceinline__ P3 dec_bond(const DevCtx &D, P3 s, unsigned raw) {
   if (n.y >= D.LY) n.y -= D.LY; else if (n.y < 0) n.y += D.LY;
   return n;
 }
-__device__ __forceinline__ unsigned long long enc_bonds(const DevCtx &D, P3 s, const P3 nn[4]) {
-  return (unsigned long long)enc_bond(D, s, nn[0]) | ((unsigned long long)enc_bond(D, s, nn[1]) << 16) |
-         ((unsigned long long)enc_bond(D, s, nn[2]) << 32) | ((unsigned long long)enc_bond(D, s, nn[3]) << 48);
+__device__ __noinline__ unsigned long long enc_bonds(P3 s, const P3 nn[4]) {
+  return (unsigned long long)enc_bond(s, nn[0]) | ((unsigned long long)enc_bond(s, nn[1]) << 16) |
+         ((unsigned long long)enc_bond(s, nn[2]) << 32) | ((unsigned long long)enc_bond(s, nn[3]) << 48);
 }
-__device__ __forceinline__ void dec_bonds(const DevCtx &D, P3 s, unsigned long long b, P3 nn[4]) {
+__device__ __noinline__ void dec_bonds(P3 s, unsigned long long b, P3 nn[4]) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) nn[i] = dec_bond(D, s, (unsigned)((b >> (16 * i)) & 0xFFFFu));
+  for (int i = 0; i < 4; i++) nn[i] = dec_bond(s, (unsigned)((b >> (16 * i)) & 0xFFFFu));
 }
-// "is `me` one of the four neighbours recorded at cell n?"  (the reciprocity test, Get_Prob.f:236-239)
-__device__ __forceinline__ bool recipr_b(const DevCtx &D, P3 n, unsigned long long bn, P3 me) {
-  bool r = false;
-#pragma unroll
-  for (int j = 0; j < 4; j++) r |= eq(dec_bond(D, n, (unsigned)((bn >> (16 * j)) & 0xFFFFu)), me);
-  return r;
+// "is `me` one of the four neighbours recorded at cell n?"  (the reciprocity test, Get_Prob.f:236-239).
+// Done on the packed codes: the code `me` would have relative to n is compared with the four stored
+// 16-bit fields; a stored 0 ("not fixed") stands for the absolute origin, as in the reference.
+__device__ __forceinline__ bool recipr_b(P3 n, unsigned long long bn, P3 me) {
+  int dx = me.x - n.x, dy = me.y - n.y, dz = me.z - n.z;
+  if (dx > D.LX / 2) dx -= D.LX; else if (dx < -(D.LX / 2)) dx += D.LX;
+  if (dy > D.LY / 2) dy -= D.LY; else if (dy < -(D.LY / 2)) dy += D.LY;
+  unsigned code = 0x10000u;                                   // matches nothing
+  if (dx >= -15 && dx <= 15 && dy >= -15 && dy <= 15 && dz >= -15 && dz <= 15)
+    code = (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
+  unsigned zero_code = (me.x == 0 && me.y == 0 && me.z == 0) ? 0u : 0x10000u;
+  unsigned f0 = (unsigned)(bn & 0xFFFFu), f1 = (unsigned)((bn >> 16) & 0xFFFFu), f2 = (unsigned)((bn >> 32) & 0xFFFFu), f3 = (unsigned)(bn >> 48);
+  return (f0 == code) | (f1 == code) | (f2 == code) | (f3 == code) | (f0 == zero_code) | (f1 == zero_code) | (f2 == zero_code) | (f3 == zero_code);
 }
 __device__ __forceinline__ bool recipr_nn(const P3 nn[4], P3 me) {
   return eq(nn[0], me) | eq(nn[1], me) | eq(nn[2], me) | eq(nn[3], me);
@@ -117,14 +141,14 @@ __device__ __forceinline__ P3 zero3() { P3 p; p.x = p.y = p.z = 0; return p; }
 // ---- geometry (compiled with -fmad=false: same IEEE sequence as the CPU reference) -----------
 __device__ __forceinline__ int isign(int a, int b) { return b >= 0 ? abs(a) : -abs(a); }
 __device__ __forceinline__ int nint_d(double x) { return (int)(x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5)); }
-__device__ __forceinline__ void wrapxy(const DevCtx &D, P3 &p) {
+__device__ __forceinline__ void wrapxy(P3 &p) {
   if (p.x >= D.LX) p.x -= D.LX;
   if (p.x < 0) p.x += D.LX;
   if (p.y >= D.LY) p.y -= D.LY;
   if (p.y < 0) p.y += D.LY;
 }
 // lattice/FIND_NN.f:25-77: the two missing neighbours of SiteC given two known ones
-__device__ __noinline__ void find_nn(const DevCtx &D, P3 Site1, P3 Site2, P3 SiteC, P3 out[2]) {
+__device__ __noinline__ void find_nn(P3 Site1, P3 Site2, P3 SiteC, P3 out[2]) {
   int LX = D.LX, LY = D.LY;
   if (abs(SiteC.x - Site1.x) > LX / 2) Site1.x += isign(LX, SiteC.x - Site1.x);
   if (abs(SiteC.y - Site1.y) > LY / 2) Site1.y += isign(LY, SiteC.y - Site1.y);
@@ -145,12 +169,12 @@ __device__ __noinline__ void find_nn(const DevCtx &D, P3 Site1, P3 Site2, P3 Sit
     Rot[1][2] = ax[1] * ax[2] * (1 - Cth) + ax[0] * Sth;
     for (int k = 0; k < 3; k++) { R[k] = 0.0; for (int l = 0; l < 3; l++) R[k] = R[k] + Rot[l][k] * v[l]; }
     P3 p; p.x = nint_d(R[0]) + SiteC.x; p.y = nint_d(R[1]) + SiteC.y; p.z = nint_d(R[2]) + SiteC.z;
-    wrapxy(D, p);
+    wrapxy(p);
     out[irot] = p;
   }
 }
 // lattice/FIND_SN.f:26-84: zig-zag (cubic) and arm-chair (hexagonal) continuations
-__device__ __noinline__ void find_sn(const DevCtx &D, P3 Site, P3 SiteC, const P3 SNin[3], P3 Zig[3], P3 Arm[3]) {
+__device__ __noinline__ void find_sn(P3 Site, P3 SiteC, const P3 SNin[3], P3 Zig[3], P3 Arm[3]) {
   int LX = D.LX, LY = D.LY;
   if (abs(Site.x - SiteC.x) > LX / 2) SiteC.x += isign(LX, Site.x - SiteC.x);
   if (abs(Site.y - SiteC.y) > LY / 2) SiteC.y += isign(LY, Site.y - SiteC.y);
@@ -170,7 +194,7 @@ __device__ __noinline__ void find_sn(const DevCtx &D, P3 Site, P3 SiteC, const P
     a.x = nint_d((double)sn.x + ARM * ax[0]);
     a.y = nint_d((double)sn.y + ARM * ax[1]);
     a.z = nint_d((double)sn.z + ARM * ax[2]);
-    wrapxy(D, z); wrapxy(D, a);
+    wrapxy(z); wrapxy(a);
     Zig[i] = z; Arm[i] = a;
   }
 }
@@ -179,43 +203,43 @@ __device__ __noinline__ void find_sn(const DevCtx &D, P3 Site, P3 SiteC, const P
 __device__ __forceinline__ int IDXE(int sp, int i1, int i2, int i3, int i4, int i5, int i6) {
   return (sp - 1) + 3 * (i1 + 4 * (i2 + 4 * (i3 + 4 * (i4 + 4 * (i5 + 4 * i6)))));
 }
-__device__ __forceinline__ int site_T(const DevCtx &D, uint32_t w, P3 s) {
+__device__ __forceinline__ int site_T(uint32_t w, P3 s) {
   int t = IBITS(w, PosT, LenT);
-  if (t == 0) { fail(D, E_TEMP0, s.x, s.y, s.z); return D.la_tmin; }
-  if (t < D.la_tmin || t > D.la_tmax) { fail(D, E_TRANGE, s.x, s.y, s.z, t); return D.la_tmin; }
+  if (t == 0) { fail(E_TEMP0, s.x, s.y, s.z); return D.la_tmin; }
+  if (t < D.la_tmin || t > D.la_tmax) { fail(E_TRANGE, s.x, s.y, s.z, t); return D.la_tmin; }
   return t;
 }
-__device__ __forceinline__ double rate_E(const DevCtx &D, int idx, int T) {
+__device__ __forceinline__ double rate_E(int idx, int T) {
   if (!D.la) return __ldg(&D.PE[idx]);
   int slot = D.la_slot[idx];
   return slot < 0 ? 0.0 : __ldg(&D.la_E[(long long)(T - D.la_tmin) * D.la_nnz + slot]);
 }
-__device__ __forceinline__ double rate_D(const DevCtx &D, int sp, int coor, int T) {
+__device__ __forceinline__ double rate_D(int sp, int coor, int T) {
   int i = (sp - 1) + 3 * (coor - 1);
   return D.la ? __ldg(&D.la_D[(long long)(T - D.la_tmin) * 9 + i]) : __ldg(&D.PD[i]);
 }
-__device__ __forceinline__ double rate_Abs(const DevCtx &D, int k, int coor) { return __ldg(&D.PAbs[(k - 1) + 3 * coor]); }
+__device__ __forceinline__ double rate_Abs(int k, int coor) { return __ldg(&D.PAbs[(k - 1) + 3 * coor]); }
 
 // Get_Prob.f:22-52
-__device__ __forceinline__ int index_event_abs(const DevCtx &D, int Coor, double Ptmp, double PDepo) {
+__device__ __noinline__ int index_event_abs(int Coor, double Ptmp, double PDepo) {
   if (D.NCov == 1) return 6;
   int res = 0;
   for (int i = 1; i <= D.NCov; i++) {
     double pmin, pmax, s;
-    if (i == 1) { pmin = PDepo; pmax = PDepo + rate_Abs(D, 1, Coor); }
+    if (i == 1) { pmin = PDepo; pmax = PDepo + rate_Abs(1, Coor); }
     else {
-      s = 0; for (int k = 1; k <= i - 1; k++) s += rate_Abs(D, k, Coor); pmin = PDepo + s;
-      s = 0; for (int k = 1; k <= i; k++) s += rate_Abs(D, k, Coor); pmax = PDepo + s;
+      s = 0; for (int k = 1; k <= i - 1; k++) s += rate_Abs(k, Coor); pmin = PDepo + s;
+      s = 0; for (int k = 1; k <= i; k++) s += rate_Abs(k, Coor); pmax = PDepo + s;
     }
     if (Ptmp > pmin && Ptmp <= pmax) res = 5 + i;
   }
   return res;
 }
 // the species / adsorbate choice of Get_Prob.f:160-179 for a uniform u in [0,1)
-__device__ __forceinline__ int choose_dep_abs(const DevCtx &D, int Coor, int T, double u, double *ptot) {
-  double PD1 = rate_D(D, 1, Coor, T), PD2 = rate_D(D, 2, Coor, T), PD3 = rate_D(D, 3, Coor, T);
+__device__ __noinline__ int choose_dep_abs(int Coor, int T, double u, double *ptot) {
+  double PD1 = rate_D(1, Coor, T), PD2 = rate_D(2, Coor, T), PD3 = rate_D(3, Coor, T);
   double PDep = PD1 + PD2 + PD3;
-  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(D, k, Coor);
+  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor);
   double Ptot = PDep + PAbs;
   if (ptot) *ptot = Ptot;
   double Pcurr = u * Ptot;
@@ -224,41 +248,41 @@ __device__ __forceinline__ int choose_dep_abs(const DevCtx &D, int Coor, int T, 
     if (Pcurr > (PD1 + PD2)) return 3;
     return 2;
   }
-  return index_event_abs(D, Coor, Pcurr, PDep);
+  return index_event_abs(Coor, Pcurr, PDep);
 }
-__device__ __forceinline__ double total_dep_abs(const DevCtx &D, int Coor, int T) {
-  double PDep = rate_D(D, 1, Coor, T) + rate_D(D, 2, Coor, T) + rate_D(D, 3, Coor, T);
-  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(D, k, Coor);
+__device__ __noinline__ double total_dep_abs(int Coor, int T) {
+  double PDep = rate_D(1, Coor, T) + rate_D(2, Coor, T) + rate_D(3, Coor, T);
+  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor);
   return PDep + PAbs;
 }
 
 // mcevent/Get_Prob.f:54-331.  NextN are the absolute neighbour coordinates the CALLER holds (they can
 // differ from the stored bonds, exactly as in the reference, e.g. Evaporation.f:123).
 template <class Pol>
-__device__ __noinline__ void get_prob(const DevCtx &D, Pol &pol, int Occ, int NSiC, int CovInd, int Coor, P3 Site, const P3 NextN[4], int &ev, double &prob) {
+__device__ __noinline__ void get_prob(Pol &pol, int Occ, int NSiC, int CovInd, int Coor, P3 Site, const P3 NextN[4], int &ev, double &prob) {
   pol.n_getprob++;
   if (CovInd > 0 && CovInd < 113) {                     // desorption, :93-123
-    if (Occ != 0) { fail(D, E_COVOCC, Site.x, Site.y, Site.z); return; }
+    if (Occ != 0) { fail(E_COVOCC, Site.x, Site.y, Site.z); return; }
     if (Coor <= 3) {
       int iCov = 0;
       for (int j = 1; j <= D.NCov; j++) if (D.ListCov[j - 1] == CovInd) { iCov = j; break; }
-      if (iCov == 0) { fail(D, E_COVLIST, Site.x, Site.y, Site.z, CovInd); return; }
+      if (iCov == 0) { fail(E_COVLIST, Site.x, Site.y, Site.z, CovInd); return; }
       ev = 5; prob = __ldg(&D.PDes[(iCov - 1) + 3 * Coor]);
     } else { ev = 0; prob = 0.0; }
     return;
   }
   int T = 0;
-  if (D.la) T = site_T(D, D.state[cidx(D, Site)], Site);
+  if (D.la) T = site_T(D.state[cidx(Site)], Site);
   if (Occ == 0) {
     if (Coor == 1) {
-      int CoorNN = w_coor(D.state[cidx(D, NextN[0])]);
+      int CoorNN = w_coor(D.state[cidx(NextN[0])]);
       if (CoorNN >= 2) {
-        if (pol.predraw()) ev = choose_dep_abs(D, Coor, T, pol.uniform(), &prob);
-        else { ev = EV_DRAW; prob = total_dep_abs(D, Coor, T); }
+        if (pol.predraw()) ev = choose_dep_abs(Coor, T, pol.uniform(), &prob);
+        else { ev = EV_DRAW; prob = total_dep_abs(Coor, T); }
       } else { ev = 1; prob = (double)1.e-8f; }             // Get_Prob.f:183
     } else if (Coor == 2 || Coor == 3) {
-      if (pol.predraw()) ev = choose_dep_abs(D, Coor, T, pol.uniform(), &prob);
-      else { ev = EV_DRAW; prob = total_dep_abs(D, Coor, T); }
+      if (pol.predraw()) ev = choose_dep_abs(Coor, T, pol.uniform(), &prob);
+      else { ev = EV_DRAW; prob = total_dep_abs(Coor, T); }
     } else if (Coor >= 4) { ev = 0; prob = 0.0; }
     return;
   }
@@ -266,14 +290,14 @@ __device__ __noinline__ void get_prob(const DevCtx &D, Pol &pol, int Occ, int NS
   int N_Si = 0, N_C = 0, N_B = 0, N_wall = 0, cv0 = 0, cv1 = 0, cv2 = 0;
   uint32_t wn[4]; unsigned long long bn[4]; long long cn[4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) { cn[i] = cidx(D, NextN[i]); wn[i] = D.state[cn[i]]; bn[i] = D.bonds[cn[i]]; }
-#pragma unroll
+  for (int i = 0; i < 4; i++) { cn[i] = cidx(NextN[i]); wn[i] = D.state[cn[i]]; bn[i] = D.bonds[cn[i]]; }
+#pragma unroll 1
   for (int i = 0; i < 4; i++) {
     uint32_t w = wn[i];
     int CovIndN = w_cov(w);
     if (w_occ(w)) {
       if (CovIndN != 113) {
-        if (recipr_b(D, NextN[i], bn[i], Site)) {
+        if (recipr_b(NextN[i], bn[i], Site)) {
           int s = w_sp(w);
           if (s == 1) N_Si++;
           if (s == 2) N_C++;
@@ -282,18 +306,18 @@ __device__ __noinline__ void get_prob(const DevCtx &D, Pol &pol, int Occ, int NS
       } else N_wall++;
     } else if (CovIndN != 0) {
       bool rec;
-      if (w_coor(w) >= 4) rec = pol.cov_void_recipr(D, NextN[i], cn[i], Site);   // reference reads the wrong list here
-      else rec = recipr_b(D, NextN[i], bn[i], Site);
+      if (w_coor(w) >= 4) rec = pol.cov_void_recipr(NextN[i], cn[i], Site);   // reference reads the wrong list here
+      else rec = recipr_b(NextN[i], bn[i], Site);
       if (rec) {
         int iCov = 0;
         for (int j = 1; j <= D.NCov; j++) if (D.ListCov[j - 1] == CovIndN) { iCov = j; break; }
-        if (iCov == 0) { fail(D, E_COVLIST, Site.x, Site.y, Site.z, CovIndN); return; }
+        if (iCov == 0) { fail(E_COVLIST, Site.x, Site.y, Site.z, CovIndN); return; }
         if (iCov == 1) cv0++; else if (iCov == 2) cv1++; else cv2++;
       }
     }
   }
   int ncry = N_Si + N_C + N_B + N_wall;
-  if (ncry != Coor) { fail(D, E_CENSUS, Site.x, Site.y, Site.z, Coor * 16 + ncry); return; }
+  if (ncry != Coor) { fail(E_CENSUS, Site.x, Site.y, Site.z, Coor * 16 + ncry); return; }
   if (ncry > 3) { ev = 0; prob = 0.0; }
   else if (ncry == 0) { ev = 4; prob = (double)100000.f * pol.tree_root(); }
   else {
@@ -302,17 +326,17 @@ __device__ __noinline__ void get_prob(const DevCtx &D, Pol &pol, int Occ, int NS
     if (D.NCov >= 2) c2 = cv1;
     if (D.NCov >= 3) c3 = cv2;
     ev = 4;
-    prob = rate_E(D, IDXE(NSiC, N_Si + N_wall, N_C, N_B, c1 & 3, c2 & 3, c3 & 3), T);
+    prob = rate_E(IDXE(NSiC, N_Si + N_wall, N_C, N_B, c1 & 3, c2 & 3, c3 & 3), T);
   }
 }
 
 // mcevent/IF_Arm_Choice.f:21-56
 template <class Pol>
-__device__ __forceinline__ bool arm_choice(const DevCtx &D, Pol &pol, const P3 Zig[3], const P3 Arm[3]) {
+__device__ __noinline__ bool arm_choice(Pol &pol, const P3 Zig[3], const P3 Arm[3]) {
   int CoorArm = 0, CoorZig = 0;
   for (int i = 0; i < 3; i++) {
-    CoorArm += w_coor(D.state[cidx(D, Arm[i])]);
-    CoorZig += w_coor(D.state[cidx(D, Zig[i])]);
+    CoorArm += w_coor(D.state[cidx(Arm[i])]);
+    CoorZig += w_coor(D.state[cidx(Zig[i])]);
   }
   if (CoorZig > CoorArm) return false;
   if (CoorZig == CoorArm) return !(pol.uniform() <= D.PZig);
@@ -321,32 +345,33 @@ __device__ __forceinline__ bool arm_choice(const DevCtx &D, Pol &pol, const P3 Z
 
 // mcevent/deposition.f:24-251
 template <class Pol>
-__device__ __noinline__ void deposition(const DevCtx &D, Pol &pol, P3 Site, int IAtom) {
-  long long cS = cidx(D, Site);
+__device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
+  long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int Coor = w_coor(wS), CoorOld = Coor;
   wS = MVBITS(wS, 1, 1, PosOcc);
   wS = MVBITS(wS, IAtom, LenSiC, PosSiC);
   D.state[cS] = wS;
   P3 NextN[4];
-  dec_bonds(D, Site, D.bonds[cS], NextN);
+  dec_bonds(Site, D.bonds[cS], NextN);
   int ev = 0; double Prob = 0;
   if (Coor == 1) {                                       // :49-74 fix the other three bonds
     P3 SiteC = NextN[0];
-    long long cC = cidx(D, SiteC);
+    long long cC = cidx(SiteC);
     P3 cnn[4], SN[3], Zig[3], Arm[3];
-    dec_bonds(D, SiteC, D.bonds[cC], cnn);
+    dec_bonds(SiteC, D.bonds[cC], cnn);
     int j = 0;
     SN[0] = SN[1] = SN[2] = zero3();
     for (int i = 0; i < 4; i++) if (!eq(cnn[i], Site)) { if (j < 3) SN[j] = cnn[i]; j++; }
-    find_sn(D, Site, SiteC, SN, Zig, Arm);
-    bool IF_Arm = arm_choice(D, pol, Zig, Arm);
+    find_sn(Site, SiteC, SN, Zig, Arm);
+    bool IF_Arm = arm_choice(pol, Zig, Arm);
     for (int i = 0; i < 3; i++) NextN[i + 1] = IF_Arm ? Arm[i] : Zig[i];
-    D.bonds[cS] = enc_bonds(D, Site, NextN);
+    D.bonds[cS] = enc_bonds(Site, NextN);
   }
+#pragma unroll 1
   for (int i = 0; i < 4; i++) {
     P3 N = NextN[i];
-    long long cN = cidx(D, N);
+    long long cN = cidx(N);
     uint32_t wN = D.state[cN];
     int Occ = w_occ(wN), CoorNN = w_coor(wN), CovInd = w_cov(wN);
     P3 NextNN[4];
@@ -355,10 +380,10 @@ __device__ __noinline__ void deposition(const DevCtx &D, Pol &pol, P3 Site, int 
         CoorNN = 1;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
         NextNN[0] = Site; NextNN[1] = NextNN[2] = NextNN[3] = zero3();
-        get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        if (ev != 0) pol.add_mc(D, N, cN, NextNN, ev, Prob);
+        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
+        if (ev != 0) pol.add_mc(N, cN, NextNN, ev, Prob);
       } else if (CoorNN == 1) {                          // :100-160 second bond: complete the tetrahedron
-        dec_bonds(D, N, D.bonds[cN], NextNN);
+        dec_bonds(N, D.bonds[cN], NextNN);
         int Dx = abs(NextNN[0].x - Site.x); Dx = min(Dx, D.LX - Dx);
         int Dy = abs(NextNN[0].y - Site.y); Dy = min(Dy, D.LY - Dy);
         int dz = NextNN[0].z - Site.z;
@@ -366,43 +391,43 @@ __device__ __noinline__ void deposition(const DevCtx &D, Pol &pol, P3 Site, int 
           P3 NewSite[2];
           CoorNN = 2;
           NextNN[1] = Site;
-          find_nn(D, NextNN[0], NextNN[1], N, NewSite);
+          find_nn(NextNN[0], NextNN[1], N, NewSite);
           for (int j = 2; j < 4; j++) {
             NextNN[j] = NewSite[j - 2];
-            long long c3 = cidx(D, NextNN[j]);
+            long long c3 = cidx(NextNN[j]);
             uint32_t w3 = D.state[c3];
             if (w_occ(w3) && w_coor(w3) <= 3 && w_cov(w3) != 113)
-              if (recipr_b(D, NextNN[j], D.bonds[c3], N)) CoorNN++;
+              if (recipr_b(NextNN[j], D.bonds[c3], N)) CoorNN++;
           }
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          D.bonds[cN] = enc_bonds(D, N, NextNN);
-          get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-          if (ev == 0) { pol.erase_mc(D, N, cN); pol.add_void(D, N, cN, NextNN); }
-          else pol.set_rate(D, N, cN, ev, Prob);
+          D.bonds[cN] = enc_bonds(N, NextNN);
+          get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
+          if (ev == 0) { pol.erase_mc(N, cN); pol.add_void(N, cN, NextNN); }
+          else pol.set_rate(N, cN, ev, Prob);
         }
       } else if (CoorNN == 2 || CoorNN == 3) {           // :161-190
         unsigned long long bN = D.bonds[cN];
-        if (recipr_b(D, N, bN, Site)) {
-          dec_bonds(D, N, bN, NextNN);
+        if (recipr_b(N, bN, Site)) {
+          dec_bonds(N, bN, NextNN);
           CoorNN++;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-          if (ev == 0) { pol.erase_mc(D, N, cN); pol.add_void(D, N, cN, NextNN); }
-          else pol.set_rate(D, N, cN, ev, Prob);
+          get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
+          if (ev == 0) { pol.erase_mc(N, cN); pol.add_void(N, cN, NextNN); }
+          else pol.set_rate(N, cN, ev, Prob);
         }
       }
     } else {                                             // full neighbour, :191-234
       if (CovInd != 113) {
-        if (CovInd != 0) { fail(D, E_NNCOV, N.x, N.y, N.z); return; }
+        if (CovInd != 0) { fail(E_NNCOV, N.x, N.y, N.z); return; }
         if (CoorNN <= 3) {
           unsigned long long bN = D.bonds[cN];
-          if (recipr_b(D, N, bN, Site)) {
-            dec_bonds(D, N, bN, NextNN);
+          if (recipr_b(N, bN, Site)) {
+            dec_bonds(N, bN, NextNN);
             CoorNN++;
             D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-            get_prob(D, pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-            if (ev == 0) { pol.erase_mc(D, N, cN); pol.add_bulk(D, N, cN, NextNN); }
-            else pol.set_rate(D, N, cN, ev, Prob);
+            get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
+            if (ev == 0) { pol.erase_mc(N, cN); pol.add_bulk(N, cN, NextNN); }
+            else pol.set_rate(N, cN, ev, Prob);
             if (CoorOld == 1 && i >= 1) Coor++;
           }
         }
@@ -410,29 +435,29 @@ __device__ __noinline__ void deposition(const DevCtx &D, Pol &pol, P3 Site, int 
     }
   }
   if (Coor != CoorOld) { wS = MVBITS(wS, Coor, LenCoor, PosCoor); D.state[cS] = wS; }
-  get_prob(D, pol, 1, IAtom, 0, Coor, Site, NextN, ev, Prob);
-  if (ev == 0) { pol.erase_mc(D, Site, cS); pol.add_bulk(D, Site, cS, NextN); }
-  else pol.set_rate(D, Site, cS, ev, Prob);
+  get_prob(pol, 1, IAtom, 0, Coor, Site, NextN, ev, Prob);
+  if (ev == 0) { pol.erase_mc(Site, cS); pol.add_bulk(Site, cS, NextN); }
+  else pol.set_rate(Site, cS, ev, Prob);
 }
 
 // Evaporation.f:95-122 / :229-258: keep only the occupied, under-coordinated, reciprocal neighbour and
 // move it to slot 1.  (The reference leaves slot 1 to an uninitialised buffer when none qualifies; that
 // never happens in any regression case -- here it raises E_STALE_NBUFF.)
-__device__ __forceinline__ void compact_to_single(const DevCtx &D, P3 me, long long cme, const P3 old[4]) {
+__device__ __noinline__ void compact_to_single(P3 me, long long cme, const P3 old[4]) {
   P3 keep = zero3(); bool found = false;
   for (int j = 0; j < 4; j++) {
-    long long c = cidx(D, old[j]);
+    long long c = cidx(old[j]);
     uint32_t w = D.state[c];
-    if (w_occ(w) && w_coor(w) <= 3 && w_cov(w) != 113 && recipr_b(D, old[j], D.bonds[c], me)) { keep = old[j]; found = true; }
+    if (w_occ(w) && w_coor(w) <= 3 && w_cov(w) != 113 && recipr_b(old[j], D.bonds[c], me)) { keep = old[j]; found = true; }
   }
-  if (!found) fail(D, E_STALE_NBUFF, me.x, me.y, me.z);
-  D.bonds[cme] = (unsigned long long)enc_bond(D, me, keep);
+  if (!found) fail(E_STALE_NBUFF, me.x, me.y, me.z);
+  D.bonds[cme] = (unsigned long long)enc_bond(me, keep);
 }
 
 // mcevent/Evaporation.f:25-262
 template <class Pol>
-__device__ __noinline__ void evaporation(const DevCtx &D, Pol &pol, P3 Site) {
-  long long cS = cidx(D, Site);
+__device__ __noinline__ void evaporation(Pol &pol, P3 Site) {
+  long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int IAtom = w_sp(wS);
   if (IAtom >= 1 && IAtom <= 3) pol.CountCrystal[IAtom - 1]--;
@@ -441,74 +466,75 @@ __device__ __noinline__ void evaporation(const DevCtx &D, Pol &pol, P3 Site) {
   wS = MVBITS(wS, 0, LenSiC, PosSiC);
   D.state[cS] = wS;
   P3 NextN[4];
-  dec_bonds(D, Site, D.bonds[cS], NextN);
+  dec_bonds(Site, D.bonds[cS], NextN);
   int ev = 0; double Prob = 0;
+#pragma unroll 1
   for (int i = 0; i < 4; i++) {
     P3 N = NextN[i];
-    long long cN = cidx(D, N);
+    long long cN = cidx(N);
     uint32_t wN = D.state[cN];
     int Occ = w_occ(wN), CoorNN = w_coor(wN), CovInd = w_cov(wN);
     unsigned long long bN = D.bonds[cN];
     P3 NextNN[4];
     if (Occ == 0) {
       if (CoorNN < 1 || CoorNN > 4) continue;
-      if (!recipr_b(D, N, bN, Site)) continue;
-      dec_bonds(D, N, bN, NextNN);
+      if (!recipr_b(N, bN, Site)) continue;
+      dec_bonds(N, bN, NextNN);
       if (CoorNN == 1) {                                 // :62-79 orphaned empty site leaves the lattice
-        pol.erase_mc(D, N, cN);
+        pol.erase_mc(N, cN);
         D.state[cN] = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
       } else if (CoorNN == 2) {                          // :80-128
         CoorNN = 1;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-        compact_to_single(D, N, cN, NextNN);
-        get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);   // NB: the OLD neighbour list, as in :123
-        pol.set_rate(D, N, cN, ev, Prob);
+        compact_to_single(N, cN, NextNN);
+        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);   // NB: the OLD neighbour list, as in :123
+        pol.set_rate(N, cN, ev, Prob);
       } else if (CoorNN == 3) {                          // :129-145
         CoorNN = 2;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-        get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        pol.set_rate(D, N, cN, ev, Prob);
+        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
+        pol.set_rate(N, cN, ev, Prob);
       } else {                                           // :146-164 vacancy becomes active again
         CoorNN = 3;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-        get_prob(D, pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        pol.erase_void(D, N, cN);
-        pol.add_mc(D, N, cN, NextNN, ev, Prob);
+        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
+        pol.erase_void(N, cN);
+        pol.add_mc(N, cN, NextNN, ev, Prob);
       }
     } else {
       if (CovInd != 113) {
-        if (CovInd != 0) { fail(D, E_NNCOV, N.x, N.y, N.z); return; }
-        if (!recipr_b(D, N, bN, Site)) continue;
-        dec_bonds(D, N, bN, NextNN);
+        if (CovInd != 0) { fail(E_NNCOV, N.x, N.y, N.z); return; }
+        if (!recipr_b(N, bN, Site)) continue;
+        dec_bonds(N, bN, NextNN);
         if (CoorNN == 4) {                               // :173-190 bulk atom becomes active again
           CoorNN = 3;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(D, pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-          pol.erase_bulk(D, N, cN);
-          pol.add_mc(D, N, cN, NextNN, ev, Prob);
+          get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
+          pol.erase_bulk(N, cN);
+          pol.add_mc(N, cN, NextNN, ev, Prob);
         } else {                                         // :191-209
           CoorNN--;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(D, pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-          pol.set_rate(D, N, cN, ev, Prob);
+          get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
+          pol.set_rate(N, cN, ev, Prob);
         }
       } else Coor--;
     }
   }
   wS = MVBITS(wS, Coor, LenCoor, PosCoor);
   D.state[cS] = wS;
-  if (Coor == 0) pol.erase_mc(D, Site, cS);
+  if (Coor == 0) pol.erase_mc(Site, cS);
   else {
-    get_prob(D, pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
-    if (Coor == 1) compact_to_single(D, Site, cS, NextN);           // :224-258
-    pol.set_rate(D, Site, cS, ev, Prob);
+    get_prob(pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
+    if (Coor == 1) compact_to_single(Site, cS, NextN);           // :224-258
+    pol.set_rate(Site, cS, ev, Prob);
   }
 }
 
 // absorption.f:43-72 / desorption.f:54-111: re-rate an occupied reciprocal neighbour
 template <class Pol>
-__device__ __forceinline__ void rerate_occ_nn(const DevCtx &D, Pol &pol, P3 Site, P3 N, bool need_le3) {
-  long long cN = cidx(D, N);
+__device__ __noinline__ void rerate_occ_nn(Pol &pol, P3 Site, P3 N, bool need_le3) {
+  long long cN = cidx(N);
   uint32_t wN = D.state[cN];
   if (!w_occ(wN)) return;
   int CovIndN = w_cov(wN), CoorN = w_coor(wN);
@@ -516,31 +542,31 @@ __device__ __forceinline__ void rerate_occ_nn(const DevCtx &D, Pol &pol, P3 Site
   if (need_le3 && CoorN > 3) return;
   if (CoorN > 3) return;     // desorption.f reads the MC list for a bulk atom here (never hit in the goldens); treated as inert
   unsigned long long bN = D.bonds[cN];
-  if (!recipr_b(D, N, bN, Site)) return;
-  P3 NextNN[4]; dec_bonds(D, N, bN, NextNN);
+  if (!recipr_b(N, bN, Site)) return;
+  P3 NextNN[4]; dec_bonds(N, bN, NextNN);
   int ev = 0; double Prob = 0;
-  get_prob(D, pol, 1, w_sp(wN), CovIndN, CoorN, N, NextNN, ev, Prob);
-  pol.set_rate(D, N, cN, ev, Prob);
+  get_prob(pol, 1, w_sp(wN), CovIndN, CoorN, N, NextNN, ev, Prob);
+  pol.set_rate(N, cN, ev, Prob);
 }
 
 // mcevent/absorption.f:25-78
 template <class Pol>
-__device__ __noinline__ void absorption(const DevCtx &D, Pol &pol, P3 Site, int CovInd) {
-  long long cS = cidx(D, Site);
+__device__ __noinline__ void absorption(Pol &pol, P3 Site, int CovInd) {
+  long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int Coor = w_coor(wS);
   D.state[cS] = MVBITS(wS, CovInd, LenIndex, PosIndex);
-  P3 NextN[4]; dec_bonds(D, Site, D.bonds[cS], NextN);
-  for (int i = 0; i < 4; i++) rerate_occ_nn(D, pol, Site, NextN[i], true);
+  P3 NextN[4]; dec_bonds(Site, D.bonds[cS], NextN);
+  for (int i = 0; i < 4; i++) rerate_occ_nn(pol, Site, NextN[i], true);
   int ev = 0; double Prob = 0;
-  get_prob(D, pol, 0, 0, CovInd, Coor, Site, NextN, ev, Prob);
-  pol.set_rate(D, Site, cS, ev, Prob);
+  get_prob(pol, 0, 0, CovInd, Coor, Site, NextN, ev, Prob);
+  pol.set_rate(Site, cS, ev, Prob);
 }
 
 // mcevent/desorption.f:25-117
 template <class Pol>
-__device__ __noinline__ void desorption(const DevCtx &D, Pol &pol, P3 Site) {
-  long long cS = cidx(D, Site);
+__device__ __noinline__ void desorption(Pol &pol, P3 Site) {
+  long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int CovInd = w_cov(wS);
   if (CovInd == D.ListCov[0]) pol.CountCov[0]--;
@@ -548,24 +574,24 @@ __device__ __noinline__ void desorption(const DevCtx &D, Pol &pol, P3 Site) {
   else if (CovInd == D.ListCov[2]) pol.CountCov[2]--;
   int Coor = w_coor(wS);
   D.state[cS] = MVBITS(wS, 0, LenIndex, PosIndex);
-  P3 NextN[4]; dec_bonds(D, Site, D.bonds[cS], NextN);
-  if (Coor == 1) rerate_occ_nn(D, pol, Site, NextN[0], false);
-  else for (int i = 0; i < 4; i++) rerate_occ_nn(D, pol, Site, NextN[i], false);
+  P3 NextN[4]; dec_bonds(Site, D.bonds[cS], NextN);
+  if (Coor == 1) rerate_occ_nn(pol, Site, NextN[0], false);
+  else for (int i = 0; i < 4; i++) rerate_occ_nn(pol, Site, NextN[i], false);
   int ev = 0; double Prob = 0;
-  get_prob(D, pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
-  pol.set_rate(D, Site, cS, ev, Prob);
+  get_prob(pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
+  pol.set_rate(Site, cS, ev, Prob);
 }
 
 // dispatch of main.f:335-357
 template <class Pol>
-__device__ __forceinline__ void apply_event(const DevCtx &D, Pol &pol, P3 Site, int Itrans) {
-  if (Itrans <= 3) { deposition(D, pol, Site, Itrans); if (Itrans >= 1) pol.CountCrystal[Itrans - 1]++; }
-  else if (Itrans == 4) evaporation(D, pol, Site);
-  else if (Itrans == 5) desorption(D, pol, Site);
+__device__ __forceinline__ void apply_event(Pol &pol, P3 Site, int Itrans) {
+  if (Itrans <= 3) { deposition(pol, Site, Itrans); if (Itrans >= 1) pol.CountCrystal[Itrans - 1]++; }
+  else if (Itrans == 4) evaporation(pol, Site);
+  else if (Itrans == 5) desorption(pol, Site);
   else {
     int k = Itrans - 5;
-    if (k > 3) { fail(D, E_BADEV, Site.x, Site.y, Site.z, Itrans); return; }
-    absorption(D, pol, Site, D.ListCov[k - 1]);
+    if (k > 3) { fail(E_BADEV, Site.x, Site.y, Site.z, Itrans); return; }
+    absorption(pol, Site, D.ListCov[k - 1]);
     pol.CountCov[k - 1]++;
   }
 }

@@ -15,6 +15,7 @@
 #include "mskc_device.cuh"
 #include "../../include/mskc.h"
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -68,8 +69,9 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {       // uniform
   return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
 }
 
+__constant__ TileView V;      // the current context's tile lists (uploaded with the DevCtx)
+
 struct TilePol {
-  TileView V;
   uint2 key; uint32_t tile_id; uint32_t step_lo, step_hi; uint32_t draw;
   double root;
   long long n_getprob;
@@ -82,41 +84,41 @@ struct TilePol {
   __device__ __forceinline__ double uniform() { uint4 r = next4(); return u53(r.x, r.y); }
   __device__ __forceinline__ int tile_of(P3 s) const { return (s.y / V.tile) * V.ntx + (s.x / V.tile); }
 
-  __device__ void put(const DevCtx &D, P3 s, long long c, int ev, double p) {
+  __device__ __noinline__ void put(P3 s, long long c, int ev, double p) {
     int t = tile_of(s);
     int sl = V.slot[c];
     TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = (uint32_t)ev;
     if (sl == 0) {
       int k = atomicAdd(&V.cnt[t], 1);
-      if (k >= V.cap) { atomicSub(&V.cnt[t], 1); fail(D, E_TILE_FULL, s.x, s.y, s.z, t); return; }
+      if (k >= V.cap) { atomicSub(&V.cnt[t], 1); fail(E_TILE_FULL, s.x, s.y, s.z, t); return; }
       V.slot[c] = (uint16_t)(k + 1);
       sl = k + 1;
     }
     V.entries[(long long)t * V.cap + sl - 1] = e;
   }
-  __device__ __forceinline__ void add_mc(const DevCtx &D, P3 s, long long c, const P3 nn[4], int ev, double p) {
-    if (p == 0) { fail(D, E_ADD_ZERO, s.x, s.y, s.z); return; }
-    D.bonds[c] = enc_bonds(D, s, nn);
-    put(D, s, c, ev, p);
+  __device__ __forceinline__ void add_mc(P3 s, long long c, const P3 nn[4], int ev, double p) {
+    if (p == 0) { fail(E_ADD_ZERO, s.x, s.y, s.z); return; }
+    D.bonds[c] = enc_bonds(s, nn);
+    put(s, c, ev, p);
   }
-  __device__ __forceinline__ void set_rate(const DevCtx &D, P3 s, long long c, int ev, double p) { put(D, s, c, ev, p); }
-  __device__ __forceinline__ void erase_mc(const DevCtx &D, P3 s, long long c) {
+  __device__ __forceinline__ void set_rate(P3 s, long long c, int ev, double p) { put(s, c, ev, p); }
+  __device__ __forceinline__ void erase_mc(P3 s, long long c) {
     int sl = V.slot[c];
     if (sl) V.entries[(long long)tile_of(s) * V.cap + sl - 1].rate = 0.0;      // tombstone; the owner compacts
     D.bonds[c] = 0ull;
   }
-  __device__ __forceinline__ void add_void(const DevCtx &D, P3 s, long long c, const P3 nn[4]) { dVoids++; D.bonds[c] = enc_bonds(D, s, nn); }
-  __device__ __forceinline__ void erase_void(const DevCtx &D, P3 s, long long c) { dVoids--; D.bonds[c] = 0ull; }
-  __device__ __forceinline__ void add_bulk(const DevCtx &D, P3 s, long long c, const P3 nn[4]) { dAtoms++; D.bonds[c] = enc_bonds(D, s, nn); }
-  __device__ __forceinline__ void erase_bulk(const DevCtx &D, P3 s, long long c) { dAtoms--; D.bonds[c] = 0ull; }
+  __device__ __forceinline__ void add_void(P3 s, long long c, const P3 nn[4]) { dVoids++; D.bonds[c] = enc_bonds(s, nn); }
+  __device__ __forceinline__ void erase_void(P3 s, long long c) { dVoids--; D.bonds[c] = 0ull; }
+  __device__ __forceinline__ void add_bulk(P3 s, long long c, const P3 nn[4]) { dAtoms++; D.bonds[c] = enc_bonds(s, nn); }
+  __device__ __forceinline__ void erase_bulk(P3 s, long long c) { dAtoms--; D.bonds[c] = 0ull; }
   // Coverage on a 4-coordinated empty site: the reference's lookup lands on an unrelated record
   // (see ParityPol::cov_void_recipr), i.e. such a neighbour is effectively never counted.
-  __device__ __forceinline__ bool cov_void_recipr(const DevCtx &, P3, long long, P3) const { return false; }
+  __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
 };
 
 // One colour step: every tile of colour (cx,cy) advances by tau.  One warp per tile; the lanes share
 // the selection scan, lane 0 applies the event (the transition rules are a serial dependency chain).
-__global__ void __launch_bounds__(128) colour_step_kernel(DevCtx D, TileView V, int cx, int cy, uint2 key, int max_events_per_tile) {
+__global__ void __launch_bounds__(128) colour_step_kernel(int cx, int cy, uint2 key, int max_events_per_tile) {
   const int lane = threadIdx.x & 31;
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int hx = V.ntx >> 1, hy = V.nty >> 1;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(128) colour_step_kernel(DevCtx D, TileView V, 
   __syncwarp();
 
   TilePol pol;
-  pol.V = V; pol.key = key; pol.tile_id = (uint32_t)t; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
+  pol.key = key; pol.tile_id = (uint32_t)t; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
   pol.root = ss.tree_root; pol.n_getprob = 0; pol.dAtoms = 0; pol.dVoids = 0;
   for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = 0; pol.CountCov[i] = 0; }
   int nev = 0, ndep[3] = {0, 0, 0}, nevap = 0, nabs = 0, ndes = 0;
@@ -188,17 +190,41 @@ __global__ void __launch_bounds__(128) colour_step_kernel(DevCtx D, TileView V, 
     }
     pick = __shfl_sync(0xFFFFFFFFu, pick, sel_lane);
     if (pick < 0) break;
+    {
+      // Cooperative gather: the transition rules are one serial dependency chain (lane 0), but every
+      // address they will touch is known up front -- the site, its 4 neighbours and their 16 neighbours.
+      // Lanes 0-3 / 0-15 pull those words into this SM's L1 in two round trips so that lane 0 then runs
+      // on L1 hits instead of ~20 dependent L2/HBM round trips.
+      uint32_t cS = E[pick].cell;
+      unsigned long long bS = D.bonds[cS];
+      touch32(D.state + cS);
+      P3 S = cell_xyz((long long)cS);
+      unsigned long long bN = 0ull; P3 N = zero3(); bool okN = false;
+      if (lane < 4) {
+        N = dec_bond(S, (unsigned)((bS >> (16 * lane)) & 0xFFFFu));
+        okN = in_box(N);
+        if (okN) { long long cN = cidx_nofail(N); bN = D.bonds[cN]; touch32(D.state + cN); touch16(V.slot + cN); }
+      }
+      int src = lane >> 2;
+      unsigned long long bq = __shfl_sync(0xFFFFFFFFu, bN, src & 3);
+      P3 Nq; Nq.x = __shfl_sync(0xFFFFFFFFu, N.x, src & 3); Nq.y = __shfl_sync(0xFFFFFFFFu, N.y, src & 3); Nq.z = __shfl_sync(0xFFFFFFFFu, N.z, src & 3);
+      bool okq = __shfl_sync(0xFFFFFFFFu, (int)okN, src & 3) != 0;
+      if (lane < 16 && okq) {
+        P3 M = dec_bond(Nq, (unsigned)((bq >> (16 * (lane & 3))) & 0xFFFFu));
+        if (in_box(M)) { long long cM = cidx_nofail(M); touch32(D.state + cM); touch64(D.bonds + cM); }
+      }
+    }
     if (lane == 0) {
       TileEntry e = E[pick];
-      P3 Site = cell_xyz(D, (long long)e.cell);
+      P3 Site = cell_xyz((long long)e.cell);
       int Itrans = (int)e.ev;
       if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
         uint32_t w = D.state[e.cell];
-        int T = D.la ? site_T(D, w, Site) : 0;
-        Itrans = choose_dep_abs(D, w_coor(w), T, pol.uniform(), nullptr);
+        int T = D.la ? site_T(w, Site) : 0;
+        Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
       }
       if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-      apply_event(D, pol, Site, Itrans);
+      apply_event(pol, Site, Itrans);
       nev++;
     }
     __syncwarp();
@@ -213,7 +239,7 @@ __global__ void __launch_bounds__(128) colour_step_kernel(DevCtx D, TileView V, 
 }
 
 // Per-sweep bookkeeping ("per-class rate sums"): total rate, active-site count, next tau, clock.
-__global__ void __launch_bounds__(1024) sweep_stats_kernel(TileView V, int ntiles, double events_per_tile, double tau_fixed, int advance) {
+__global__ void __launch_bounds__(1024) sweep_stats_kernel(int ntiles, double events_per_tile, double tau_fixed, int advance) {
   __shared__ double sR[32]; __shared__ long long sN[32]; __shared__ int sM[32];
   double r = 0.0; long long n = 0; int mx = 0;
   for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { r += V.tile_rate[t]; int c = V.cnt[t]; n += c; mx = max(mx, c); }
@@ -231,7 +257,7 @@ __global__ void __launch_bounds__(1024) sweep_stats_kernel(TileView V, int ntile
 }
 __global__ void bump_step_kernel(SweepState *ss) { ss->step++; }
 
-__global__ void __launch_bounds__(256) tile_rate_kernel(TileView V, int ntiles) {
+__global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (t >= ntiles) return;
   const TileEntry *E = V.entries + (long long)t * V.cap;
@@ -268,9 +294,9 @@ struct RatePol {             // Get_Prob without any bookkeeping side effects
   __device__ __forceinline__ bool predraw() const { return false; }
   __device__ __forceinline__ double tree_root() const { return root; }
   __device__ __forceinline__ double uniform() { return 0.5; }
-  __device__ __forceinline__ bool cov_void_recipr(const DevCtx &, P3, long long, P3) const { return false; }
+  __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
 };
-__global__ void __launch_bounds__(256) rerate_kernel(DevCtx D, TileView V, int ntiles, unsigned long long *n_sites) {
+__global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long long *n_sites) {
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)ntiles * V.cap;
   RatePol pol; pol.root = V.ss->tree_root; pol.n_getprob = 0;
@@ -280,11 +306,11 @@ __global__ void __launch_bounds__(256) rerate_kernel(DevCtx D, TileView V, int n
     if (i >= V.cnt[t]) continue;
     TileEntry e = V.entries[k];
     if (!(e.rate > 0.0)) continue;
-    P3 s = cell_xyz(D, (long long)e.cell);
+    P3 s = cell_xyz((long long)e.cell);
     uint32_t w = D.state[e.cell];
-    P3 nn[4]; dec_bonds(D, s, D.bonds[e.cell], nn);
+    P3 nn[4]; dec_bonds(s, D.bonds[e.cell], nn);
     int ev = 0; double p = 0;
-    get_prob(D, pol, w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, nn, ev, p);
+    get_prob(pol, w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, nn, ev, p);
     if (ev != 0 && p > 0) { e.rate = p; e.ev = (uint32_t)ev; V.entries[k] = e; mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
@@ -300,14 +326,14 @@ __global__ void gather_bonds(const unsigned long long *bonds, const uint32_t *ce
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = cell[i] == 0xFFFFFFFFu ? 0ull : bonds[cell[i]];
 }
-__global__ void collect_bulk(DevCtx D, uint32_t *out, long long cap, unsigned long long *cnt) {
+__global__ void collect_bulk(uint32_t *out, long long cap, unsigned long long *cnt) {
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < D.ncell; c += (long long)gridDim.x * blockDim.x) {
     uint32_t w = D.state[c];
     if (w_occ(w) && w_coor(w) == 4 && w_cov(w) != 113) { unsigned long long k = atomicAdd(cnt, 1ull); if ((long long)k < cap) out[k] = (uint32_t)c; }
   }
 }
 // initial/SetT.f:36-46
-__global__ void set_temperature_kernel(DevCtx D, const int32_t *T, long long n) {
+__global__ void set_temperature_kernel(const int32_t *T, long long n) {
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
     int t = T[c];
     if (t != 10) D.state[c] = MVBITS(D.state[c], t, LenT, PosT);
@@ -324,7 +350,7 @@ __device__ __forceinline__ bool is_cubic_site(int x, int y, int z, int &kind) {
 }
 // Streaming census (the counting scans of inpout/WriteMolMolXYZFile.f:77-119 fused into one pass,
 // 128-bit loads, 4 B/cell of HBM traffic): under-coordinated atoms, coverage, non-epitaxial bulk, ...
-__global__ void __launch_bounds__(256) census_kernel(DevCtx D, unsigned long long *out, double *hsum) {
+__global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, double *hsum) {
   unsigned long long nUnder = 0, nCov = 0, nNoEpi = 0, nBulk = 0, nOcc = 0, nWall = 0; double hz = 0, hz2 = 0;
   const long long n4 = D.ncell >> 2;
   const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
@@ -362,7 +388,7 @@ __global__ void __launch_bounds__(256) census_kernel(DevCtx D, unsigned long lon
 
 // Device-side flat (001) builder: geometry of initial/SetSi.f:25-221 (walls, one species) and
 // initial/SetSiC3C.f:25-199 (no walls, Si/C).  One thread per (x,y) column of cubic sites.
-__global__ void __launch_bounds__(256) init_flat_kernel(DevCtx D, TileView V, int Len, int walls, int two_species, unsigned long long *counters) {
+__global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int two_species, unsigned long long *counters) {
   const long long plane = (long long)D.LX * D.LY;
   const int JD[8][3] = {{3, 3, 3}, {3, -3, -3}, {-3, -3, 3}, {-3, 3, -3}, {3, 3, -3}, {3, -3, 3}, {-3, -3, -3}, {-3, 3, 3}};
   for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < plane; col += (long long)gridDim.x * blockDim.x) {
@@ -377,29 +403,29 @@ __global__ void __launch_bounds__(256) init_flat_kernel(DevCtx D, TileView V, in
       if (!is_cubic_site(x, y, z, kind)) continue;
       P3 s; s.x = x; s.y = y; s.z = z;
       P3 nn[4];
-      for (int i = 0; i < 4; i++) { nn[i].x = x + JD[i + 4 * kind][0]; nn[i].y = y + JD[i + 4 * kind][1]; nn[i].z = z + JD[i + 4 * kind][2]; wrapxy(D, nn[i]); }
+      for (int i = 0; i < 4; i++) { nn[i].x = x + JD[i + 4 * kind][0]; nn[i].y = y + JD[i + 4 * kind][1]; nn[i].z = z + JD[i + 4 * kind][2]; wrapxy(nn[i]); }
       long long c = col + plane * z;
       int sp = (kind && two_species) ? 2 : 1;
       if (z <= Len - 4) {
         D.state[c] = (1u << (PosSiC + sp - 1)) | (1u << PosOcc) | (4u << PosCoor);
-        D.bonds[c] = enc_bonds(D, s, nn);
+        D.bonds[c] = enc_bonds(s, nn);
         atomicAdd(&counters[0], 1ull);
       } else if (z <= Len - 1) {
         D.state[c] = (1u << (PosSiC + sp - 1)) | (1u << PosOcc) | (2u << PosCoor);
-        D.bonds[c] = enc_bonds(D, s, nn);
+        D.bonds[c] = enc_bonds(s, nn);
         double p = D.PE[IDXE(sp, 2, 0, 0, 0, 0, 0)];
         int t = (y / V.tile) * V.ntx + (x / V.tile);
         int k = atomicAdd(&V.cnt[t], 1);
-        if (k >= V.cap) { fail(D, E_TILE_FULL, x, y, z, t); continue; }
+        if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
         TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = 4; V.entries[(long long)t * V.cap + k] = e; V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       } else {
         D.state[c] = (2u << PosCoor);
-        D.bonds[c] = enc_bonds(D, s, nn);
-        double p = total_dep_abs(D, 2, 0);
+        D.bonds[c] = enc_bonds(s, nn);
+        double p = total_dep_abs(2, 0);
         int t = (y / V.tile) * V.ntx + (x / V.tile);
         int k = atomicAdd(&V.cnt[t], 1);
-        if (k >= V.cap) { fail(D, E_TILE_FULL, x, y, z, t); continue; }
+        if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
         TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = EV_DRAW; V.entries[(long long)t * V.cap + k] = e; V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       }
@@ -418,29 +444,29 @@ static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.entries = P.entries; V.cnt = P.cnt; V.slot = P.slot;
   V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; return V;
 }
-static inline int parallel_alloc(ParallelCtx &P, const DevCtx &D, cudaStream_t st, int cap, std::string *err) {
+static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int cap, std::string *err) {
   int tile = 24;
-  if (D.LX % (2 * tile) || D.LY % (2 * tile)) { if (err) *err = "parallel sampler needs LenX and LenY to be multiples of 48 (24-unit tiles, 2x2 colouring)"; return -1; }
-  if (P.entries && P.cap == cap && P.ncell == D.ncell) {
+  if (H.LX % (2 * tile) || H.LY % (2 * tile)) { if (err) *err = "parallel sampler needs LenX and LenY to be multiples of 48 (24-unit tiles, 2x2 colouring)"; return -1; }
+  if (P.entries && P.cap == cap && P.ncell == H.ncell) {
     PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
-    PCK(cudaMemsetAsync(P.slot, 0, (size_t)D.ncell * sizeof(uint16_t), st));
+    PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
     PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
     PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
     return 0;
   }
   parallel_free(P);
-  P.tile = tile; P.ntx = D.LX / tile; P.nty = D.LY / tile; P.ntiles = P.ntx * P.nty; P.cap = cap; P.ncell = D.ncell;
+  P.tile = tile; P.ntx = H.LX / tile; P.nty = H.LY / tile; P.ntiles = P.ntx * P.nty; P.cap = cap; P.ncell = H.ncell;
   PCK(cudaMalloc(&P.entries, (size_t)P.ntiles * cap * sizeof(TileEntry)));
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
-  PCK(cudaMalloc(&P.slot, (size_t)D.ncell * sizeof(uint16_t)));
+  PCK(cudaMalloc(&P.slot, (size_t)H.ncell * sizeof(uint16_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
   PCK(cudaMalloc(&P.ss, sizeof(SweepState)));
   PCK(cudaMalloc(&P.tot, sizeof(TileStat)));
   PCK(cudaMemsetAsync(P.entries, 0, (size_t)P.ntiles * cap * sizeof(TileEntry), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
-  PCK(cudaMemsetAsync(P.slot, 0, (size_t)D.ncell * sizeof(uint16_t), st));
+  PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
@@ -449,16 +475,16 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &D, cudaStream_t s
 static const int TILE_CAP = 192;
 
 // tile lists from an uploaded MC list (reference order is irrelevant here)
-static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &D, cudaStream_t st, int n_mc, const uint32_t *mc_cell, const int *mc_ev,
+static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int n_mc, const uint32_t *mc_cell, const int *mc_ev,
                                             const double *mc_rate, int n_bulk, int n_void, std::string *err) {
-  if (D.LX % 48 || D.LY % 48) { P.lists_stale = true; return 0; }      // parity-only box
-  if (parallel_alloc(P, D, st, TILE_CAP, err)) return -1;
-  std::vector<TileEntry> E((size_t)P.ntiles * P.cap); std::vector<int> cnt(P.ntiles, 0); std::vector<uint16_t> slot((size_t)D.ncell, 0);
+  if (H.LX % 48 || H.LY % 48) { P.lists_stale = true; return 0; }      // parity-only box
+  if (parallel_alloc(P, H, st, TILE_CAP, err)) return -1;
+  std::vector<TileEntry> E((size_t)P.ntiles * P.cap); std::vector<int> cnt(P.ntiles, 0); std::vector<uint16_t> slot((size_t)H.ncell, 0);
   memset(E.data(), 0, E.size() * sizeof(TileEntry));
-  long long plane = (long long)D.LX * D.LY;
+  long long plane = (long long)H.LX * H.LY;
   for (int i = 0; i < n_mc; i++) {
     uint32_t c = mc_cell[i];
-    long long r = c % plane; int y = (int)(r / D.LX), x = (int)(r - (long long)y * D.LX);
+    long long r = c % plane; int y = (int)(r / H.LX), x = (int)(r - (long long)y * H.LX);
     int t = (y / P.tile) * P.ntx + (x / P.tile);
     if (cnt[t] >= P.cap) { if (err) *err = "per-tile active list capacity exceeded at upload"; return -1; }
     TileEntry e; e.rate = mc_rate[i]; e.cell = c;
@@ -479,16 +505,17 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &D, cud
   return 0;
 }
 
-static inline int parallel_init_flat(ParallelCtx &P, DevCtx &D, cudaStream_t st, int len1, int walls, int two_species, std::string *err) {
+static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st, int len1, int walls, int two_species, const std::function<int()> &sync_consts, std::string *err) {
   len1 -= len1 % 24;                                                  // main.f:226,240
-  if (len1 < 24 || len1 + 12 > D.LZ - (walls ? 6 : 0)) { if (err) *err = "mskc_init_flat: Len1 does not fit the box"; return -1; }
-  if (D.LX % 48 || D.LY % 48) { if (err) *err = "mskc_init_flat: LenX, LenY must be multiples of 48"; return -1; }
-  if (parallel_alloc(P, D, st, TILE_CAP, err)) return -1;
-  PCK(cudaMemsetAsync(D.state, 0, (size_t)D.ncell * sizeof(uint32_t), st));
-  PCK(cudaMemsetAsync(D.bonds, 0, (size_t)D.ncell * sizeof(unsigned long long), st));
+  if (len1 < 24 || len1 + 12 > H.LZ - (walls ? 6 : 0)) { if (err) *err = "mskc_init_flat: Len1 does not fit the box"; return -1; }
+  if (H.LX % 48 || H.LY % 48) { if (err) *err = "mskc_init_flat: LenX, LenY must be multiples of 48"; return -1; }
+  if (parallel_alloc(P, H, st, TILE_CAP, err)) return -1;
+  if (sync_consts()) { if (err) *err = "constant upload failed"; return -1; }
+  PCK(cudaMemsetAsync(H.state, 0, (size_t)H.ncell * sizeof(uint32_t), st));
+  PCK(cudaMemsetAsync(H.bonds, 0, (size_t)H.ncell * sizeof(unsigned long long), st));
   unsigned long long *d_cnt = nullptr, h_cnt[2];
   PCK(cudaMalloc(&d_cnt, 16)); PCK(cudaMemsetAsync(d_cnt, 0, 16, st));
-  init_flat_kernel<<<148 * 8, 256, 0, st>>>(D, tile_view(P), len1, walls, two_species, d_cnt);
+  init_flat_kernel<<<148 * 8, 256, 0, st>>>(len1, walls, two_species, d_cnt);
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
   PCK(cudaStreamSynchronize(st));
@@ -498,8 +525,7 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &D, cudaStream_t st,
   return 0;
 }
 
-static inline int parallel_run(ParallelCtx &P, DevCtx &D, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
-  TileView V = tile_view(P);
+static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
   const int wpb = 4, blocks = (ntc + wpb - 1) / wpb;
@@ -509,18 +535,18 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &D, cudaStream_t st, cudaE
   int launches = 0;
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
-    tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(V, P.ntiles);
-    sweep_stats_kernel<<<1, 1024, 0, st>>>(V, P.ntiles, ept, a->tau_fixed, 0);
+    tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.ntiles);
+    sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, ept, a->tau_fixed, 0);
     launches += 2;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
   for (long long s = 0; s < a->n_sweeps; s++) {
     for (int c = 0; c < 4; c++) {
-      colour_step_kernel<<<blocks, wpb * 32, 0, st>>>(D, V, order[c][0], order[c][1], key, 1 << 20);
+      colour_step_kernel<<<blocks, wpb * 32, 0, st>>>(order[c][0], order[c][1], key, 1 << 20);
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
     }
-    sweep_stats_kernel<<<1, 1024, 0, st>>>(V, P.ntiles, ept, a->tau_fixed, 1);
+    sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, ept, a->tau_fixed, 1);
     launches++;
   }
   reduce_tstat_kernel<<<1, 256, 0, st>>>(P.tstat, P.ntiles, P.tot);
@@ -541,14 +567,13 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &D, cudaStream_t st, cudaE
   return 0;
 }
 
-static inline int parallel_rerate(ParallelCtx &P, DevCtx &D, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int64_t *n_sites, double *total_rate, float *ms, std::string *err) {
-  TileView V = tile_view(P);
+static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, int64_t *n_sites, double *total_rate, float *ms, std::string *err) {
   unsigned long long *d_n = nullptr, h_n = 0;
   PCK(cudaMalloc(&d_n, 8)); PCK(cudaMemsetAsync(d_n, 0, 8, st));
   PCK(cudaEventRecord(e0, st));
-  rerate_kernel<<<148 * 8, 256, 0, st>>>(D, V, P.ntiles, d_n);
-  tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(V, P.ntiles);
-  sweep_stats_kernel<<<1, 1024, 0, st>>>(V, P.ntiles, 4.0, 0.0, 0);
+  rerate_kernel<<<148 * 8, 256, 0, st>>>(P.ntiles, d_n);
+  tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.ntiles);
+  sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, 4.0, 0.0, 0);
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(&h_n, d_n, 8, cudaMemcpyDeviceToHost, st));

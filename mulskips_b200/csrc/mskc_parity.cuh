@@ -33,22 +33,27 @@ struct ParityArgs {
   int exit_on_time;
 };
 
-struct ParityPol {
+// device pointers of the parity structures, in constant memory (uploaded with the context)
+struct ParityView {
   double *Tree; int Levels, NumMcMax, NumVdMax, leaf0;
   uint32_t *lattind, *mc_cell, *void_cell; int *mc_ev;
   ParityState *ps;
+};
+__constant__ ParityView PV;
+
+struct ParityPol {
   int NumAdAtom, NumAtoms, NumVoids;
   int CountCrystal[3], CountCov[3];
   long long n_getprob, n_ran3;
 
   __device__ __forceinline__ bool predraw() const { return true; }
-  __device__ __forceinline__ double tree_root() const { return Tree[1]; }
+  __device__ __forceinline__ double tree_root() const { return PV.Tree[1]; }
 
   // mcevent/random.f:22-69
-  __device__ double uniform() {
+  __device__ __noinline__ double uniform() {
     const int mbig = 1000000000, mseed = 161803398, mz = 0;
     const double fac = (double)(1.0f / 1.0e9f);
-    ParityState &s = *ps;
+    ParityState &s = *PV.ps;
     int *ma = s.r_ma, mj, mk;
     n_ran3++;
     if (s.idum < 0 || s.r_iff == 0) {
@@ -68,93 +73,93 @@ struct ParityPol {
 
   // mcevent/UpdateTree.f:25-66.  The sibling loads are independent of the running sum, so they are
   // issued together; the 19 adds are the only dependent chain.
-  __device__ void update_tree(const DevCtx &D, int Index, double P) {
-    if (P == 0 && Index < NumAdAtom) { fail(D, E_TREE_ZERO, Index); return; }
-    if (Index > NumAdAtom) { fail(D, E_TREE_IDX, Index, NumAdAtom); return; }
-    int Pos = Index + leaf0 - 1;
+  __device__ __noinline__ void update_tree(int Index, double P) {
+    if (P == 0 && Index < NumAdAtom) { fail(E_TREE_ZERO, Index); return; }
+    if (Index > NumAdAtom) { fail(E_TREE_IDX, Index, NumAdAtom); return; }
+    int Pos = Index + PV.leaf0 - 1;
     double sib[24];
-    int nlev = Levels - 1;
+    int nlev = PV.Levels - 1;
 #pragma unroll
-    for (int l = 0; l < 24; l++) if (l < nlev) sib[l] = Tree[(Pos >> l) ^ 1];
-    Tree[Pos] = P;
+    for (int l = 0; l < 24; l++) if (l < nlev) sib[l] = PV.Tree[(Pos >> l) ^ 1];
+    PV.Tree[Pos] = P;
     double v = P;
 #pragma unroll
-    for (int l = 0; l < 24; l++) if (l < nlev) { v = v + sib[l]; Tree[Pos >> (l + 1)] = v; }
+    for (int l = 0; l < 24; l++) if (l < nlev) { v = v + sib[l]; PV.Tree[Pos >> (l + 1)] = v; }
   }
-  __device__ __forceinline__ double leaf(int Index) const { return Tree[Index + leaf0 - 1]; }
+  __device__ __forceinline__ double leaf(int Index) const { return PV.Tree[Index + PV.leaf0 - 1]; }
 
   // mcevent/Add.f:24-53
-  __device__ void add_mc(const DevCtx &D, P3 s, long long c, const P3 nn[4], int ev, double p) {
-    if (p == 0) { fail(D, E_ADD_ZERO, s.x, s.y, s.z); return; }
+  __device__ __noinline__ void add_mc(P3 s, long long c, const P3 nn[4], int ev, double p) {
+    if (p == 0) { fail(E_ADD_ZERO, s.x, s.y, s.z); return; }
     NumAdAtom++;
-    if (NumAdAtom >= NumMcMax) { fail(D, E_MC_FULL, NumAdAtom); NumAdAtom--; return; }
-    lattind[c] = (uint32_t)NumAdAtom;
-    mc_cell[NumAdAtom] = (uint32_t)c; mc_ev[NumAdAtom] = ev;
-    D.bonds[c] = enc_bonds(D, s, nn);
-    update_tree(D, NumAdAtom, p);
+    if (NumAdAtom >= PV.NumMcMax) { fail(E_MC_FULL, NumAdAtom); NumAdAtom--; return; }
+    PV.lattind[c] = (uint32_t)NumAdAtom;
+    PV.mc_cell[NumAdAtom] = (uint32_t)c; PV.mc_ev[NumAdAtom] = ev;
+    D.bonds[c] = enc_bonds(s, nn);
+    update_tree(NumAdAtom, p);
   }
-  __device__ __forceinline__ void set_rate(const DevCtx &D, P3 s, long long c, int ev, double p) {
-    int ind = (int)lattind[c];
-    if (ind < 1 || ind > NumMcMax) { fail(D, E_ERASE, s.x, s.y, s.z, ind); return; }
-    mc_ev[ind] = ev;
-    update_tree(D, ind, p);
+  __device__ __forceinline__ void set_rate(P3 s, long long c, int ev, double p) {
+    int ind = (int)PV.lattind[c];
+    if (ind < 1 || ind > PV.NumMcMax) { fail(E_ERASE, s.x, s.y, s.z, ind); return; }
+    PV.mc_ev[ind] = ev;
+    update_tree(ind, p);
   }
   // mcevent/Erase.f:24-78
-  __device__ void erase_mc(const DevCtx &D, P3 s, long long c) {
-    int IndNN = (int)lattind[c];
-    if (IndNN > NumMcMax || IndNN == 0) { fail(D, E_ERASE, s.x, s.y, s.z, IndNN); return; }
+  __device__ __noinline__ void erase_mc(P3 s, long long c) {
+    int IndNN = (int)PV.lattind[c];
+    if (IndNN > PV.NumMcMax || IndNN == 0) { fail(E_ERASE, s.x, s.y, s.z, IndNN); return; }
     if (IndNN >= NumAdAtom) {
-      mc_cell[IndNN] = 0xFFFFFFFFu; mc_ev[IndNN] = 0;
-      lattind[c] = 0; D.bonds[c] = 0ull;
-      update_tree(D, IndNN, 0.0);
+      PV.mc_cell[IndNN] = 0xFFFFFFFFu; PV.mc_ev[IndNN] = 0;
+      PV.lattind[c] = 0; D.bonds[c] = 0ull;
+      update_tree(IndNN, 0.0);
       NumAdAtom--;
     } else {
-      uint32_t moved = mc_cell[NumAdAtom];
-      mc_cell[IndNN] = moved; mc_ev[IndNN] = mc_ev[NumAdAtom];
-      update_tree(D, IndNN, leaf(NumAdAtom));
-      update_tree(D, NumAdAtom, 0.0);
-      lattind[moved] = (uint32_t)IndNN;
-      mc_cell[NumAdAtom] = 0xFFFFFFFFu; mc_ev[NumAdAtom] = 0;
-      lattind[c] = 0; D.bonds[c] = 0ull;
+      uint32_t moved = PV.mc_cell[NumAdAtom];
+      PV.mc_cell[IndNN] = moved; PV.mc_ev[IndNN] = PV.mc_ev[NumAdAtom];
+      update_tree(IndNN, leaf(NumAdAtom));
+      update_tree(NumAdAtom, 0.0);
+      PV.lattind[moved] = (uint32_t)IndNN;
+      PV.mc_cell[NumAdAtom] = 0xFFFFFFFFu; PV.mc_ev[NumAdAtom] = 0;
+      PV.lattind[c] = 0; D.bonds[c] = 0ull;
       NumAdAtom--;
     }
   }
   // mcevent/Add.f:82-100, Erase.f:135-179
-  __device__ void add_void(const DevCtx &D, P3 s, long long c, const P3 nn[4]) {
+  __device__ __noinline__ void add_void(P3 s, long long c, const P3 nn[4]) {
     NumVoids++;
-    if (NumVoids >= NumVdMax) { fail(D, E_VOID_FULL, NumVoids); NumVoids--; return; }
-    lattind[c] = (uint32_t)NumVoids; void_cell[NumVoids] = (uint32_t)c;
-    D.bonds[c] = enc_bonds(D, s, nn);
+    if (NumVoids >= PV.NumVdMax) { fail(E_VOID_FULL, NumVoids); NumVoids--; return; }
+    PV.lattind[c] = (uint32_t)NumVoids; PV.void_cell[NumVoids] = (uint32_t)c;
+    D.bonds[c] = enc_bonds(s, nn);
   }
-  __device__ void erase_void(const DevCtx &D, P3 s, long long c) {
-    int IndNN = (int)lattind[c];
-    if (IndNN > NumVdMax || IndNN == 0) { fail(D, E_ERASE, s.x, s.y, s.z, -IndNN); return; }
-    if (IndNN != NumVoids) { uint32_t moved = void_cell[NumVoids]; void_cell[IndNN] = moved; lattind[moved] = (uint32_t)IndNN; }
-    void_cell[NumVoids] = 0xFFFFFFFFu;
-    lattind[c] = 0; D.bonds[c] = 0ull;
+  __device__ __noinline__ void erase_void(P3 s, long long c) {
+    int IndNN = (int)PV.lattind[c];
+    if (IndNN > PV.NumVdMax || IndNN == 0) { fail(E_ERASE, s.x, s.y, s.z, -IndNN); return; }
+    if (IndNN != NumVoids) { uint32_t moved = PV.void_cell[NumVoids]; PV.void_cell[IndNN] = moved; PV.lattind[moved] = (uint32_t)IndNN; }
+    PV.void_cell[NumVoids] = 0xFFFFFFFFu;
+    PV.lattind[c] = 0; D.bonds[c] = 0ull;
     NumVoids--;
   }
   // mcevent/Add.f:58-76, Erase.f:84-128: the bulk list is never enumerated by the loop, a counter suffices
-  __device__ __forceinline__ void add_bulk(const DevCtx &D, P3 s, long long c, const P3 nn[4]) { NumAtoms++; lattind[c] = 0; D.bonds[c] = enc_bonds(D, s, nn); }
-  __device__ __forceinline__ void erase_bulk(const DevCtx &D, P3 s, long long c) { NumAtoms--; D.bonds[c] = 0ull; }
+  __device__ __forceinline__ void add_bulk(P3 s, long long c, const P3 nn[4]) { NumAtoms++; PV.lattind[c] = 0; D.bonds[c] = enc_bonds(s, nn); }
+  __device__ __forceinline__ void erase_bulk(P3 s, long long c) { NumAtoms--; D.bonds[c] = 0ull; }
 
   // Get_Prob.f:266-269 looks a coverage neighbour up in ListAdAtom even when it sits on a 4-coordinated
   // empty site, i.e. in ListVoid: it reads the MC record that happens to have the vacancy's index.  The
   // CVD goldens depend on it (26 967 times in CVD-Si-SiH2), so parity mode reproduces the lookup.
-  __device__ bool cov_void_recipr(const DevCtx &D, P3 n, long long cn, P3 me) {
-    int v = (int)lattind[cn];
+  __device__ __noinline__ bool cov_void_recipr(P3 n, long long cn, P3 me) {
+    int v = (int)PV.lattind[cn];
     if (v < 1 || v > NumAdAtom) return eq(zero3(), me);          // zeroed record: NextNXYZ = 0
-    uint32_t c2 = mc_cell[v];
+    uint32_t c2 = PV.mc_cell[v];
     if (c2 == 0xFFFFFFFFu) return eq(zero3(), me);
-    return recipr_b(D, cell_xyz(D, (long long)c2), D.bonds[c2], me);
+    return recipr_b(cell_xyz((long long)c2), D.bonds[c2], me);
   }
 };
 
 // mcevent/PickTreeEvent.f:25-70 + main.f:304-371
-__global__ void __launch_bounds__(32, 1) parity_kernel(DevCtx D, ParityPol P0, ParityArgs A) {
+__global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ParityPol pol = P0;
-  ParityState &S = *pol.ps;
+  ParityPol pol;
+  ParityState &S = *PV.ps;
   pol.NumAdAtom = S.NumAdAtom; pol.NumAtoms = S.NumAtoms; pol.NumVoids = S.NumVoids;
   for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = S.CountCrystal[i]; pol.CountCov[i] = S.CountCov[i]; }
   pol.n_getprob = 0; pol.n_ran3 = 0;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(DevCtx D, ParityPol P0, P
   double Time = S.Time;
   long long framecounter = A.framecounter;
   int stop = 0;
-  const int nlev = pol.Levels - 1;
+  const int nlev = PV.Levels - 1;
   while (true) {
     int Ind, Itrans;
     if (S.pending) { Ind = S.pend_ind; Itrans = S.pend_itrans; S.pending = 0; }
@@ -175,23 +180,23 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(DevCtx D, ParityPol P0, P
         double r;
         if (S.runtype == 'T') { S.counter++; r = (double)NUMBERSLIST[(S.counter - 1) % 1000]; }
         else r = pol.uniform();
-        double Patom = r * pol.Tree[idx];
+        double Patom = r * PV.Tree[idx];
         idx <<= 1;
-        if (pol.Tree[idx] < Patom) idx++;
+        if (PV.Tree[idx] < Patom) idx++;
       }
-      Ind = idx - pol.leaf0 + 1;
-      if (Ind > pol.NumAdAtom) { fail(D, E_PICK, Ind, pol.NumAdAtom); stop = -1; break; }
-      Time = Time + 1.0 / pol.Tree[1];
-      Itrans = pol.mc_ev[Ind];
-      P3 s = cell_xyz(D, (long long)pol.mc_cell[Ind]);
+      Ind = idx - PV.leaf0 + 1;
+      if (Ind > pol.NumAdAtom) { fail(E_PICK, Ind, pol.NumAdAtom); stop = -1; break; }
+      Time = Time + 1.0 / PV.Tree[1];
+      Itrans = PV.mc_ev[Ind];
+      P3 s = cell_xyz((long long)PV.mc_cell[Ind]);
       S.last_site[0] = s.x; S.last_site[1] = s.y; S.last_site[2] = s.z;
       bool frame = false;
       if (!A.exit_on_time) { if (A.out_every > 0 && (Iter % A.out_every) == 0) frame = true; }
       else if (A.out_time > 0 && Time >= ((double)(framecounter + 1) * A.out_time)) { frame = true; framecounter++; }
       if (frame) { S.pending = 1; S.pend_ind = Ind; S.pend_itrans = Itrans; stop = 3; break; }
     }
-    P3 Site = cell_xyz(D, (long long)pol.mc_cell[Ind]);
-    apply_event(D, pol, Site, Itrans);
+    P3 Site = cell_xyz((long long)PV.mc_cell[Ind]);
+    apply_event(pol, Site, Itrans);
     done++;
     Iter++;
     if (D.err[0] != 0) { stop = -1; break; }
