@@ -1,0 +1,286 @@
+#!/usr/bin/env python3
+"""bench.py -- KMC events/s of the MulSKIPS event loop on B200 (and the CPU reference arm).
+
+One "step" = one pass of the hot path over one batch: `--sweeps` synchronous-sublattice sweeps of the
+whole slab (4 colour steps each).  Workload (config.workload): flat 3C-SiC(001) slab, the reference's
+own PVD rate table (regression-tests start-surface.dat) with PtransZig=0.8 (hexagonal/stacking-fault
+branch enabled, as in start-cube-zigzag.dat), 4608x4608x48 super-lattice cells (1.02e9 sites) PER GPU,
+built on the device with the geometry of initial/SetSiC3C.f.  N>1: one slab per rank (weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "kmc_events_per_s"
+UNIT = "events/s"
+B_PER_SITE_UPDATE = 96     # algorithmic bytes per (event,rate) re-evaluation
+B_PER_EVENT = 448          # algorithmic bytes per applied event
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    from mulskips_b200.workloads import rates_for
+    w = rates_for("surface")
+    w["PtransZig"] = 0.8
+    return w
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def oracle_sample(args, faithful_cost, events, box=(480, 480, 48)):
+    """The CPU path on a bounded sample of the same workload: same rate table, same flat F builder
+    (Len1=24), a 480x480x48 patch, `events` events of the serial n-fold-way loop with ran3 ('R')."""
+    from cases import make_start
+    from oracle_binding import Oracle
+    with tempfile.TemporaryDirectory() as td:
+        start = make_start("surface", os.path.join(td, "start.dat"), lens=(24, 0, 0), maxiter=10**9, outmolmol=10**9, runtype="R", ptranszig=0.8)
+        orc = Oracle(*box, start)
+        orc.set_run(faithful_cost=int(faithful_cost))
+        orc.setup()
+        t0 = time.perf_counter()
+        n = orc.run(events)
+        dt = time.perf_counter() - t0
+        su = orc.quirks()["n_getprob"]
+        orc.close()
+    return n, su, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle_binding import build_oracle
+    build_oracle()
+    ev_per_step = 1_000_000
+    for _ in range(args.warmup and 1):
+        oracle_sample(args, True, 200_000)
+    tot_n, tot_t, tot_su = 0, 0.0, 0
+    for _ in range(args.steps):
+        n, su, dt = oracle_sample(args, True, ev_per_step)
+        tot_n += n; tot_t += dt; tot_su += su
+    v = tot_n / tot_t
+    n2, su2, dt2 = oracle_sample(args, False, ev_per_step)
+    sample = f"C restatement of mulskips.e (oracle/, -O2, 1 thread, per-call rate-table copy as in Get_Prob.f:151-152), 480x480x48 patch of the same SiC slab, {ev_per_step} events per step, ran3"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+           "data": "synthetic", "config": config_dict(args, "cpu"),
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample, "site_updates_per_s": tot_su / tot_t,
+                            "value_without_table_copy": n2 / dt2, "host_cores_available": os.cpu_count(),
+                            "note": "the reference loop is strictly serial (no threads/MPI); gfortran is not in the image so oracle/_ref cannot be built"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def config_dict(args, where):
+    bx, by, bz = args.box
+    return {"workload": f"3C-SiC(001) flat slab PVD, start-surface.dat rate table, PtransZig=0.8, {bx}x{by}x{bz} super-lattice cells ({bx * by * bz / 1e9:.2f}e9 sites) per GPU, F builder Len1={args.len1}",
+            "box_per_gpu": [bx, by, bz], "sweeps_per_step": args.sweeps, "events_per_tile": args.ept, "mode": "synchronous-sublattice sampler (24-unit tiles, 2x2 colours, Philox4x32-10)",
+            "parallelism": f"{args.gpus} independent x-y periodic slab(s), one per GPU", "l2": "inputs (state+bonds+slot, 14 B/cell) >> 126 MB L2; no flush", "where": where}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the KMC event loop has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mulskips_b200 import Mskc
+    import ctypes as C
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = workload(args)
+    bx, by, bz = args.box
+    ctx = Mskc(bx, by, bz, w["listcrystal"], w["listcov"], device=local)
+    ctx.set_rates(w["PtransE"], w["PtransD"], w["PtransAbs"], w["PtransDes"], w["PtransZig"])
+
+    def fresh():
+        ctx.init_flat(args.len1, walls=False, two_species=True)
+
+    # ---- device-resident throughput ("value") -----------------------------------------------------
+    fresh()
+    seed = 1000 + rank
+    for i in range(args.warmup):
+        ctx.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + i)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    ev = su = launches = 0; kms = 0.0
+    for i in range(args.steps):
+        r = ctx.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 100 + i)
+        ev += r.events_done; su += r.site_updates; launches += r.launches; kms += r.kernel_ms
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    dt = t1 - t0
+    n_active = r.n_active
+
+    # ---- roofline of the dominant kernel: every colour-step launch timed with CUDA events ---------
+    rr = ctx.run_parallel(min(args.sweeps, 16), events_per_tile=args.ept, seed=seed + 999)
+    n_launch = 4 * rr.sweeps_done
+    alg_bytes = B_PER_SITE_UPDATE * rr.site_updates + B_PER_EVENT * rr.events_done
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (rr.sweep_kernel_ms * 1e-3) / 1e9 if rr.sweep_kernel_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "colour_step_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "colour_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1), "launch_ms": rr.sweep_kernel_ms / max(n_launch, 1),
+                "share_of_step": rr.sweep_kernel_ms / rr.kernel_ms if rr.kernel_ms else None,
+                "note": "latency/instruction-issue bound: the touched surface set is L2-resident, DRAM traffic << algorithmic bytes (see DESIGN.md)"}
+
+    # ---- end to end through the C ABI with HOST buffers ------------------------------------------
+    # Per step: H2D of the per-cell input field the reference receives each cycle (SetT.f / the LA socket's
+    # SENDFIELD: int32 [LenZ][LenY*LenX]) from pinned memory, the sweeps, and D2H of the whole lattice
+    # (what WriteMolMolXYZFile / GETPHASES read).
+    ncell_T = bx * by * bz
+    T_host = torch.full((ncell_T,), 1000, dtype=torch.int32).pin_memory()
+    L_host = torch.empty(((bz + 1) * by * bx,), dtype=torch.int32).pin_memory()
+    i32p = C.POINTER(C.c_int32)
+    Tp, Lp = C.cast(T_host.data_ptr(), i32p), C.cast(L_host.data_ptr(), i32p)
+    fresh()
+
+    def e2e_step(i):
+        ctx._ck(ctx.lib.mskc_set_temperature(ctx.h, Tp))
+        rr_ = ctx.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 5000 + i)
+        ctx._ck(ctx.lib.mskc_download_lattice(ctx.h, Lp))
+        return rr_.events_done
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    barrier()
+    t2 = time.perf_counter()
+    ev2 = 0
+    for i in range(args.steps):
+        ev2 += e2e_step(10 + i)
+    barrier()
+    t3 = time.perf_counter()
+    occ = int(((L_host[:: 4097] >> 23) & 1).sum())       # touch the result
+
+    # ---- aggregate over ranks -----------------------------------------------------------------------
+    vals = torch.tensor([dt, t3 - t2, float(ev), float(ev2), float(su)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt_max, dt2_max, ev_sum, ev2_sum, su_sum = mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item(), sm[4].item()
+    else:
+        dt_max, dt2_max, ev_sum, ev2_sum, su_sum = dt, t3 - t2, float(ev), float(ev2), float(su)
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle_binding import build_oracle
+            build_oracle()
+            n, s_u, cdt = oracle_sample(args, True, 3_000_000)
+            n2, s_u2, cdt2 = oracle_sample(args, False, 3_000_000)
+            cpu = {"value": n / cdt, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "C restatement of mulskips.e (oracle/, 1 thread, per-call 96 KiB rate-table copy as in Get_Prob.f:151-152), 480x480x48 patch of the same slab, 3e6 events, ran3",
+                   "site_updates_per_s": s_u / cdt, "value_without_table_copy": n2 / cdt2, "host_cores_available": os.cpu_count()}
+        out = {"metric": METRIC, "value": ev_sum / dt_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
+               "data": "synthetic", "config": config_dict(args, "gpu"),
+               "site_updates_per_s": su_sum / dt_max, "events_per_step": ev_sum / args.steps, "active_sites_per_gpu": int(n_active),
+               "device_ms_per_step": kms / args.steps, "gpu_launches": int(launches),
+               "e2e": {"value": ev2_sum / dt2_max, "unit": UNIT, "h2d_bytes_per_step": 4 * ncell_T, "d2h_bytes_per_step": 4 * (bz + 1) * by * bx,
+                       "ms_per_step": 1e3 * dt2_max / args.steps, "what": "mskc_set_temperature(pinned int32 field) + mskc_run_parallel + mskc_download_lattice(pinned) per step", "checksum": occ},
+               "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--box", type=int, nargs=3, default=[4608, 4608, 48])
+    ap.add_argument("--len1", type=int, default=24)
+    ap.add_argument("--sweeps", type=int, default=16)
+    ap.add_argument("--ept", type=float, default=8.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@ struct mskc_ctx {
   std::vector<double> h_PE, h_PD, h_PAbs, h_PDes;
   short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr;
   int *d_err = nullptr;
+  int32_t *d_stage = nullptr;
   // parity mode
   int NumMcMax = 500000, NumVdMax = 100000, Levels = 20;
   double *d_Tree = nullptr; uint32_t *d_lattind = nullptr, *d_mc_cell = nullptr, *d_void_cell = nullptr; int *d_mc_ev = nullptr;
@@ -147,6 +148,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
+  cudaFree(h->d_stage);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   parallel_free(h->PC);
@@ -402,11 +404,12 @@ extern "C" int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const
 }
 extern "C" int mskc_get_counters(mskc_ctx *h, mskc_counters *c) {
   if (!h || !c) return set_err(h, "mskc_get_counters: NULL argument");
-  if (!h->parity_ready) return set_err(h, "mskc_get_counters: no state");
+  if (!h->parity_ready && !h->parallel_ready) return set_err(h, "mskc_get_counters: no state");
   CK(cudaSetDevice(h->device));
+  memset(c, 0, sizeof *c);
+  if (!h->parity_ready) { parallel_fill_counters(h->PC, c); return 0; }
   ParityState &S = h->h_ps;
   CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
-  memset(c, 0, sizeof *c);
   c->num_atoms = S.NumAtoms; c->num_voids = S.NumVoids; c->num_adatom = S.NumAdAtom;
   for (int i = 0; i < 3; i++) { c->CountCrystal[i] = S.CountCrystal[i]; c->CountCov[i] = S.CountCov[i]; }
   c->iter = S.Iter; c->time = S.Time;
@@ -513,13 +516,11 @@ extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
   CK(cudaSetDevice(h->device));
   DevCtx &D = h->D;
   size_t n = (size_t)D.LX * D.LY * D.LZ;
-  int32_t *d_T = nullptr;
-  CK(cudaMalloc(&d_T, n * 4));
-  CK(cudaMemcpyAsync(d_T, T, n * 4, cudaMemcpyHostToDevice, h->stream));
+  if (!h->d_stage) CK(cudaMalloc(&h->d_stage, n * 4));        // staging plane stack, kept for the next upload
   if (upload_consts(h)) return -1;
-  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(d_T, (long long)n);
+  CK(cudaMemcpyAsync(h->d_stage, T, n * 4, cudaMemcpyHostToDevice, h->stream));
+  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(h->d_stage, (long long)n);
   CK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_T);
   return 0;
 }
 

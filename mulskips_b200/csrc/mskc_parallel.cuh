@@ -540,9 +540,17 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     launches += 2;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
+  // short calls time every colour-step kernel on its own (CUDA events on the launching stream): this is
+  // the per-launch duration the roofline in bench.py is computed from
+  const bool timed = a->n_sweeps > 0 && a->n_sweeps <= 64;
+  std::vector<cudaEvent_t> evs;
+  if (timed) { evs.resize((size_t)a->n_sweeps * 8); for (auto &e : evs) PCK(cudaEventCreate(&e)); }
+  size_t ke = 0;
   for (long long s = 0; s < a->n_sweeps; s++) {
     for (int c = 0; c < 4; c++) {
+      if (timed) PCK(cudaEventRecord(evs[ke++], st));
       colour_step_kernel<<<blocks, wpb * 32, 0, st>>>(order[c][0], order[c][1], key, 1 << 20);
+      if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
     }
@@ -557,12 +565,19 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   PCK(cudaMemcpyAsync(&P.h_ss, P.ss, sizeof(SweepState), cudaMemcpyDeviceToHost, st));
   PCK(cudaStreamSynchronize(st));
   PCK(cudaEventElapsedTime(&r->kernel_ms, e0, e1));
+  if (timed) {
+    float tot = 0;
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) { float ms = 0; PCK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); tot += ms; }
+    r->sweep_kernel_ms = tot;
+    for (auto &e : evs) cudaEventDestroy(e);
+  }
   P.ran = true;
   r->events_done = P.h_tot.events - before.events; r->site_updates = P.h_tot.site_updates - before.site_updates;
   r->sweeps_done = a->n_sweeps; r->time = P.h_ss.time; r->total_rate = P.h_ss.total_rate; r->n_active = P.h_ss.n_active;
   for (int i = 0; i < 3; i++) r->count_dep[i] = P.h_tot.dep[i] - before.dep[i];
   r->count_evap = P.h_tot.evap - before.evap; r->count_abs = P.h_tot.abs_ - before.abs_; r->count_des = P.h_tot.des - before.des;
   r->launches = launches; r->stop_reason = MSKC_STOP_BUDGET;
+  (void)ke;
   P.time = P.h_ss.time;
   return 0;
 }

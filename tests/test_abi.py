@@ -1,0 +1,68 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/mskc.h declares;
+the product path fails loudly (no CPU fallback) when no CUDA device is present."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mulskips_b200 import capi
+    if not os.path.exists(capi.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    return capi.load_library()
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "mskc.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mskc_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_header_matches_binding(lib):
+    from mulskips_b200 import capi
+    assert header_symbols() == sorted(capi.SYMBOLS)
+
+
+def test_exports(lib):
+    for s in header_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_struct_sizes(tmp_path):
+    """ctypes mirrors have the layout the C compiler gives include/mskc.h (compiled here with gcc)."""
+    import subprocess
+    from mulskips_b200 import capi
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "mskc.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mskc_parity_args), sizeof(mskc_parity_result), '
+                   'sizeof(mskc_parallel_args), sizeof(mskc_parallel_result), sizeof(mskc_counters), sizeof(mskc_census));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    mirrors = [capi._ParityArgs, capi.ParityResult, capi._ParallelArgs, capi.ParallelResult, capi.Counters, capi.Census]
+    assert sizes == [C.sizeof(m) for m in mirrors]
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mulskips_b200 import Mskc, MskcError
+    with pytest.raises(MskcError) as e:
+        Mskc(96, 96, 96, [14])
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under mulskips_b200/ or include/ may reference oracle/ (the oracle is test infrastructure)."""
+    for base in ("mulskips_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", "Makefile")):
+                    t = open(os.path.join(dp, f), errors="ignore").read()
+                    assert "oracle_binding" not in t and "mskc_oracle" not in t and "libmskc_oracle" not in t, os.path.join(dp, f)
