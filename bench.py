@@ -4,7 +4,7 @@
 One "step" = one pass of the hot path over one batch: `--sweeps` synchronous-sublattice sweeps of the
 whole slab (4 colour steps each).  Workload (config.workload): flat 3C-SiC(001) slab, the reference's
 own PVD rate table (regression-tests start-surface.dat) with PtransZig=0.8 (hexagonal/stacking-fault
-branch enabled, as in start-cube-zigzag.dat), 4608x4608x48 super-lattice cells (1.02e9 sites) PER GPU,
+branch enabled, as in start-cube-zigzag.dat), 4608x4608x96 super-lattice cells (2.0e9 sites; the 4608x4608 surface of the 10^9-site C5 slab with head-room for roughness) PER GPU,
 built on the device with the geometry of initial/SetSiC3C.f.  N>1: one slab per rank (weak scaling).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -90,9 +90,9 @@ def workload(args):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
-def oracle_sample(args, faithful_cost, events, box=(480, 480, 48)):
+def oracle_sample(args, faithful_cost, events, box=(480, 480, 96)):
     """The CPU path on a bounded sample of the same workload: same rate table, same flat F builder
-    (Len1=24), a 480x480x48 patch, `events` events of the serial n-fold-way loop with ran3 ('R')."""
+    (Len1=24), a 480x480x96 patch, `events` events of the serial n-fold-way loop with ran3 ('R')."""
     from cases import make_start
     from oracle_binding import Oracle
     with tempfile.TemporaryDirectory() as td:
@@ -123,7 +123,7 @@ def run_reference(args):
         tot_n += n; tot_t += dt; tot_su += su
     v = tot_n / tot_t
     n2, su2, dt2 = oracle_sample(args, False, ev_per_step)
-    sample = f"C restatement of mulskips.e (oracle/, -O2, 1 thread, per-call rate-table copy as in Get_Prob.f:151-152), 480x480x48 patch of the same SiC slab, {ev_per_step} events per step, ran3"
+    sample = f"C restatement of mulskips.e (oracle/, -O2, 1 thread, per-call rate-table copy as in Get_Prob.f:151-152), 480x480x96 patch of the same SiC slab, {ev_per_step} events per step, ran3"
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
            "data": "synthetic", "config": config_dict(args, "cpu"),
@@ -248,7 +248,7 @@ def run_ours(args):
             n, s_u, cdt = oracle_sample(args, True, 3_000_000)
             n2, s_u2, cdt2 = oracle_sample(args, False, 3_000_000)
             cpu = {"value": n / cdt, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "C restatement of mulskips.e (oracle/, 1 thread, per-call 96 KiB rate-table copy as in Get_Prob.f:151-152), 480x480x48 patch of the same slab, 3e6 events, ran3",
+                   "sample": "C restatement of mulskips.e (oracle/, 1 thread, per-call 96 KiB rate-table copy as in Get_Prob.f:151-152), 480x480x96 patch of the same slab, 3e6 events, ran3",
                    "site_updates_per_s": s_u / cdt, "value_without_table_copy": n2 / cdt2, "host_cores_available": os.cpu_count()}
         out = {"metric": METRIC, "value": ev_sum / dt_max, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64",
@@ -270,7 +270,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--box", type=int, nargs=3, default=[4608, 4608, 48])
+    ap.add_argument("--box", type=int, nargs=3, default=[4608, 4608, 96])
     ap.add_argument("--len1", type=int, default=24)
     ap.add_argument("--sweeps", type=int, default=16)
     ap.add_argument("--ept", type=float, default=8.0)
