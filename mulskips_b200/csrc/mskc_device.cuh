@@ -343,9 +343,45 @@ __device__ __noinline__ bool arm_choice(Pol &pol, const P3 Zig[3], const P3 Arm[
   return true;
 }
 
+// ---- deferred re-rating -------------------------------------------------------------------------
+// The reference re-rates a site (Get_Prob + UpdateTree / list migration) right where it touches it.
+// Here every such request is queued by the transition function and executed afterwards, in the SAME
+// order, by rq_flush: one Get_Prob call site for all events, so that SIMT lanes working on different
+// tiles converge again for the expensive part, and the hot code stays small.  The order of list / tree
+// operations (hence parity mode's bit-exactness) is unchanged; Get_Prob of a neighbour never reads
+// what a later neighbour's update writes (neighbours of one site are not bonded to each other).
+enum { A_NEW = 0, A_SETVOID, A_SETBULK, A_SET, A_VOID2MC, A_BULK2MC, A_ERASE };
+struct RQItem { P3 N; long long c; P3 nn[4]; int Occ, NSiC, Cov, Coor, act, pre; uint32_t pre_w; };
+struct RQ { int n; RQItem it[6]; };
+__device__ __forceinline__ void rq_push(RQ &q, int act, P3 N, long long c, int Occ, int NSiC, int Cov, int Coor, const P3 nn[4], int pre = 0, uint32_t pre_w = 0) {
+  RQItem &it = q.it[q.n++];
+  it.N = N; it.c = c; it.Occ = Occ; it.NSiC = NSiC; it.Cov = Cov; it.Coor = Coor; it.act = act; it.pre = pre; it.pre_w = pre_w;
+  it.nn[0] = nn[0]; it.nn[1] = nn[1]; it.nn[2] = nn[2]; it.nn[3] = nn[3];
+}
+template <class Pol>
+__device__ __noinline__ void rq_flush(Pol &pol, RQ &q) {
+#pragma unroll 1
+  for (int k = 0; k < q.n; k++) {
+    RQItem &it = q.it[k];
+    if (it.pre) D.state[it.c] = it.pre_w;          // the site's own coordination is written after its neighbours were rated
+    int ev = 0; double p = 0.0;
+    if (it.act != A_ERASE) get_prob(pol, it.Occ, it.NSiC, it.Cov, it.Coor, it.N, it.nn, ev, p);
+    switch (it.act) {
+      case A_NEW: if (ev != 0) pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+      case A_SETVOID: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_void(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
+      case A_SETBULK: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
+      case A_SET: pol.set_rate(it.N, it.c, ev, p); break;
+      case A_VOID2MC: pol.erase_void(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+      case A_BULK2MC: pol.erase_bulk(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+      default: pol.erase_mc(it.N, it.c); break;
+    }
+  }
+  q.n = 0;
+}
+
 // mcevent/deposition.f:24-251
 template <class Pol>
-__device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
+__device__ __noinline__ void deposition(Pol &pol, RQ &q, P3 Site, int IAtom) {
   long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int Coor = w_coor(wS), CoorOld = Coor;
@@ -354,7 +390,6 @@ __device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
   D.state[cS] = wS;
   P3 NextN[4];
   dec_bonds(Site, D.bonds[cS], NextN);
-  int ev = 0; double Prob = 0;
   if (Coor == 1) {                                       // :49-74 fix the other three bonds
     P3 SiteC = NextN[0];
     long long cC = cidx(SiteC);
@@ -368,11 +403,16 @@ __device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
     for (int i = 0; i < 3; i++) NextN[i + 1] = IF_Arm ? Arm[i] : Zig[i];
     D.bonds[cS] = enc_bonds(Site, NextN);
   }
+  // the four neighbour words / bond codes are independent loads: issue them together
+  long long cNs[4]; uint32_t wNs[4]; unsigned long long bNs[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { cNs[i] = cidx(NextN[i]); wNs[i] = D.state[cNs[i]]; bNs[i] = D.bonds[cNs[i]]; }
 #pragma unroll 1
   for (int i = 0; i < 4; i++) {
     P3 N = NextN[i];
-    long long cN = cidx(N);
-    uint32_t wN = D.state[cN];
+    long long cN = cNs[i];
+    uint32_t wN = wNs[i];
+    unsigned long long bN = bNs[i];
     int Occ = w_occ(wN), CoorNN = w_coor(wN), CovInd = w_cov(wN);
     P3 NextNN[4];
     if (Occ == 0) {
@@ -380,10 +420,9 @@ __device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
         CoorNN = 1;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
         NextNN[0] = Site; NextNN[1] = NextNN[2] = NextNN[3] = zero3();
-        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        if (ev != 0) pol.add_mc(N, cN, NextNN, ev, Prob);
+        rq_push(q, A_NEW, N, cN, 0, 0, CovInd, CoorNN, NextNN);
       } else if (CoorNN == 1) {                          // :100-160 second bond: complete the tetrahedron
-        dec_bonds(N, D.bonds[cN], NextNN);
+        dec_bonds(N, bN, NextNN);
         int Dx = abs(NextNN[0].x - Site.x); Dx = min(Dx, D.LX - Dx);
         int Dy = abs(NextNN[0].y - Site.y); Dy = min(Dy, D.LY - Dy);
         int dz = NextNN[0].z - Site.z;
@@ -401,43 +440,33 @@ __device__ __noinline__ void deposition(Pol &pol, P3 Site, int IAtom) {
           }
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
           D.bonds[cN] = enc_bonds(N, NextNN);
-          get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-          if (ev == 0) { pol.erase_mc(N, cN); pol.add_void(N, cN, NextNN); }
-          else pol.set_rate(N, cN, ev, Prob);
+          rq_push(q, A_SETVOID, N, cN, 0, 0, CovInd, CoorNN, NextNN);
         }
       } else if (CoorNN == 2 || CoorNN == 3) {           // :161-190
-        unsigned long long bN = D.bonds[cN];
         if (recipr_b(N, bN, Site)) {
           dec_bonds(N, bN, NextNN);
           CoorNN++;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-          if (ev == 0) { pol.erase_mc(N, cN); pol.add_void(N, cN, NextNN); }
-          else pol.set_rate(N, cN, ev, Prob);
+          rq_push(q, A_SETVOID, N, cN, 0, 0, CovInd, CoorNN, NextNN);
         }
       }
     } else {                                             // full neighbour, :191-234
       if (CovInd != 113) {
         if (CovInd != 0) { fail(E_NNCOV, N.x, N.y, N.z); return; }
         if (CoorNN <= 3) {
-          unsigned long long bN = D.bonds[cN];
           if (recipr_b(N, bN, Site)) {
             dec_bonds(N, bN, NextNN);
             CoorNN++;
             D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-            get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-            if (ev == 0) { pol.erase_mc(N, cN); pol.add_bulk(N, cN, NextNN); }
-            else pol.set_rate(N, cN, ev, Prob);
+            rq_push(q, A_SETBULK, N, cN, 1, w_sp(wN), CovInd, CoorNN, NextNN);
             if (CoorOld == 1 && i >= 1) Coor++;
           }
         }
       } else Coor++;
     }
   }
-  if (Coor != CoorOld) { wS = MVBITS(wS, Coor, LenCoor, PosCoor); D.state[cS] = wS; }
-  get_prob(pol, 1, IAtom, 0, Coor, Site, NextN, ev, Prob);
-  if (ev == 0) { pol.erase_mc(Site, cS); pol.add_bulk(Site, cS, NextN); }
-  else pol.set_rate(Site, cS, ev, Prob);
+  uint32_t wS2 = (Coor != CoorOld) ? MVBITS(wS, Coor, LenCoor, PosCoor) : wS;
+  rq_push(q, A_SETBULK, Site, cS, 1, IAtom, 0, Coor, NextN, 1, wS2);
 }
 
 // Evaporation.f:95-122 / :229-258: keep only the occupied, under-coordinated, reciprocal neighbour and
@@ -456,7 +485,7 @@ __device__ __noinline__ void compact_to_single(P3 me, long long cme, const P3 ol
 
 // mcevent/Evaporation.f:25-262
 template <class Pol>
-__device__ __noinline__ void evaporation(Pol &pol, P3 Site) {
+__device__ __noinline__ void evaporation(Pol &pol, RQ &q, P3 Site) {
   long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int IAtom = w_sp(wS);
@@ -467,39 +496,37 @@ __device__ __noinline__ void evaporation(Pol &pol, P3 Site) {
   D.state[cS] = wS;
   P3 NextN[4];
   dec_bonds(Site, D.bonds[cS], NextN);
-  int ev = 0; double Prob = 0;
+  long long cNs[4]; uint32_t wNs[4]; unsigned long long bNs[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) { cNs[i] = cidx(NextN[i]); wNs[i] = D.state[cNs[i]]; bNs[i] = D.bonds[cNs[i]]; }
 #pragma unroll 1
   for (int i = 0; i < 4; i++) {
     P3 N = NextN[i];
-    long long cN = cidx(N);
-    uint32_t wN = D.state[cN];
+    long long cN = cNs[i];
+    uint32_t wN = wNs[i];
     int Occ = w_occ(wN), CoorNN = w_coor(wN), CovInd = w_cov(wN);
-    unsigned long long bN = D.bonds[cN];
+    unsigned long long bN = bNs[i];
     P3 NextNN[4];
     if (Occ == 0) {
       if (CoorNN < 1 || CoorNN > 4) continue;
       if (!recipr_b(N, bN, Site)) continue;
       dec_bonds(N, bN, NextNN);
       if (CoorNN == 1) {                                 // :62-79 orphaned empty site leaves the lattice
-        pol.erase_mc(N, cN);
         D.state[cN] = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
+        rq_push(q, A_ERASE, N, cN, 0, 0, 0, 0, NextNN);
       } else if (CoorNN == 2) {                          // :80-128
         CoorNN = 1;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
         compact_to_single(N, cN, NextNN);
-        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);   // NB: the OLD neighbour list, as in :123
-        pol.set_rate(N, cN, ev, Prob);
+        rq_push(q, A_SET, N, cN, 0, 0, CovInd, CoorNN, NextNN);     // NB: rated with the OLD neighbour list, as in :123
       } else if (CoorNN == 3) {                          // :129-145
         CoorNN = 2;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        pol.set_rate(N, cN, ev, Prob);
+        rq_push(q, A_SET, N, cN, 0, 0, CovInd, CoorNN, NextNN);
       } else {                                           // :146-164 vacancy becomes active again
         CoorNN = 3;
         D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-        get_prob(pol, 0, 0, CovInd, CoorNN, N, NextNN, ev, Prob);
-        pol.erase_void(N, cN);
-        pol.add_mc(N, cN, NextNN, ev, Prob);
+        rq_push(q, A_VOID2MC, N, cN, 0, 0, CovInd, CoorNN, NextNN);
       }
     } else {
       if (CovInd != 113) {
@@ -509,63 +536,56 @@ __device__ __noinline__ void evaporation(Pol &pol, P3 Site) {
         if (CoorNN == 4) {                               // :173-190 bulk atom becomes active again
           CoorNN = 3;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-          pol.erase_bulk(N, cN);
-          pol.add_mc(N, cN, NextNN, ev, Prob);
+          rq_push(q, A_BULK2MC, N, cN, 1, w_sp(wN), CovInd, CoorNN, NextNN);
         } else {                                         // :191-209
           CoorNN--;
           D.state[cN] = MVBITS(wN, CoorNN, LenCoor, PosCoor);
-          get_prob(pol, 1, w_sp(wN), CovInd, CoorNN, N, NextNN, ev, Prob);
-          pol.set_rate(N, cN, ev, Prob);
+          rq_push(q, A_SET, N, cN, 1, w_sp(wN), CovInd, CoorNN, NextNN);
         }
       } else Coor--;
     }
   }
-  wS = MVBITS(wS, Coor, LenCoor, PosCoor);
-  D.state[cS] = wS;
-  if (Coor == 0) pol.erase_mc(Site, cS);
+  uint32_t wS2 = MVBITS(wS, Coor, LenCoor, PosCoor);
+  if (Coor == 0) rq_push(q, A_ERASE, Site, cS, 0, 0, 0, 0, NextN, 1, wS2);
   else {
-    get_prob(pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
-    if (Coor == 1) compact_to_single(Site, cS, NextN);           // :224-258
-    pol.set_rate(Site, cS, ev, Prob);
+    // the orphan case above zeroes a neighbour's word in the reference only AFTER EraseMC; nothing reads it in between
+    if (Coor == 1) {                                     // :224-258; needs the final coordination words of the neighbours
+      rq_push(q, A_SET, Site, cS, 0, 0, 0, Coor, NextN, 1, wS2);
+      compact_to_single(Site, cS, NextN);
+    } else rq_push(q, A_SET, Site, cS, 0, 0, 0, Coor, NextN, 1, wS2);
   }
 }
 
 // absorption.f:43-72 / desorption.f:54-111: re-rate an occupied reciprocal neighbour
-template <class Pol>
-__device__ __noinline__ void rerate_occ_nn(Pol &pol, P3 Site, P3 N, bool need_le3) {
+__device__ __noinline__ void rerate_occ_nn(RQ &q, P3 Site, P3 N, bool need_le3) {
   long long cN = cidx(N);
   uint32_t wN = D.state[cN];
   if (!w_occ(wN)) return;
   int CovIndN = w_cov(wN), CoorN = w_coor(wN);
   if (CovIndN == 113) return;
-  if (need_le3 && CoorN > 3) return;
   if (CoorN > 3) return;     // desorption.f reads the MC list for a bulk atom here (never hit in the goldens); treated as inert
+  (void)need_le3;
   unsigned long long bN = D.bonds[cN];
   if (!recipr_b(N, bN, Site)) return;
   P3 NextNN[4]; dec_bonds(N, bN, NextNN);
-  int ev = 0; double Prob = 0;
-  get_prob(pol, 1, w_sp(wN), CovIndN, CoorN, N, NextNN, ev, Prob);
-  pol.set_rate(N, cN, ev, Prob);
+  rq_push(q, A_SET, N, cN, 1, w_sp(wN), CovIndN, CoorN, NextNN);
 }
 
 // mcevent/absorption.f:25-78
 template <class Pol>
-__device__ __noinline__ void absorption(Pol &pol, P3 Site, int CovInd) {
+__device__ __noinline__ void absorption(Pol &pol, RQ &q, P3 Site, int CovInd) {
   long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int Coor = w_coor(wS);
   D.state[cS] = MVBITS(wS, CovInd, LenIndex, PosIndex);
   P3 NextN[4]; dec_bonds(Site, D.bonds[cS], NextN);
-  for (int i = 0; i < 4; i++) rerate_occ_nn(pol, Site, NextN[i], true);
-  int ev = 0; double Prob = 0;
-  get_prob(pol, 0, 0, CovInd, Coor, Site, NextN, ev, Prob);
-  pol.set_rate(Site, cS, ev, Prob);
+  for (int i = 0; i < 4; i++) rerate_occ_nn(q, Site, NextN[i], true);
+  rq_push(q, A_SET, Site, cS, 0, 0, CovInd, Coor, NextN);
 }
 
 // mcevent/desorption.f:25-117
 template <class Pol>
-__device__ __noinline__ void desorption(Pol &pol, P3 Site) {
+__device__ __noinline__ void desorption(Pol &pol, RQ &q, P3 Site) {
   long long cS = cidx(Site);
   uint32_t wS = D.state[cS];
   int CovInd = w_cov(wS);
@@ -575,25 +595,25 @@ __device__ __noinline__ void desorption(Pol &pol, P3 Site) {
   int Coor = w_coor(wS);
   D.state[cS] = MVBITS(wS, 0, LenIndex, PosIndex);
   P3 NextN[4]; dec_bonds(Site, D.bonds[cS], NextN);
-  if (Coor == 1) rerate_occ_nn(pol, Site, NextN[0], false);
-  else for (int i = 0; i < 4; i++) rerate_occ_nn(pol, Site, NextN[i], false);
-  int ev = 0; double Prob = 0;
-  get_prob(pol, 0, 0, 0, Coor, Site, NextN, ev, Prob);
-  pol.set_rate(Site, cS, ev, Prob);
+  if (Coor == 1) rerate_occ_nn(q, Site, NextN[0], false);
+  else for (int i = 0; i < 4; i++) rerate_occ_nn(q, Site, NextN[i], false);
+  rq_push(q, A_SET, Site, cS, 0, 0, 0, Coor, NextN);
 }
 
 // dispatch of main.f:335-357
 template <class Pol>
 __device__ __forceinline__ void apply_event(Pol &pol, P3 Site, int Itrans) {
-  if (Itrans <= 3) { deposition(pol, Site, Itrans); if (Itrans >= 1) pol.CountCrystal[Itrans - 1]++; }
-  else if (Itrans == 4) evaporation(pol, Site);
-  else if (Itrans == 5) desorption(pol, Site);
+  RQ q; q.n = 0;
+  if (Itrans <= 3) { deposition(pol, q, Site, Itrans); if (Itrans >= 1) pol.CountCrystal[Itrans - 1]++; }
+  else if (Itrans == 4) evaporation(pol, q, Site);
+  else if (Itrans == 5) desorption(pol, q, Site);
   else {
     int k = Itrans - 5;
     if (k > 3) { fail(E_BADEV, Site.x, Site.y, Site.z, Itrans); return; }
-    absorption(pol, Site, D.ListCov[k - 1]);
+    absorption(pol, q, Site, D.ListCov[k - 1]);
     pol.CountCov[k - 1]++;
   }
+  rq_flush(pol, q);
 }
 
 }  // namespace mskc

@@ -7,7 +7,7 @@
 // run concurrently, one warp per tile, each doing its own n-fold way for a time quantum tau.
 //
 // HBM layout added to state[]/bonds[] (mskc_device.cuh):
-//   entries[tile][cap]  16 B {f64 rate, u32 cell, u32 event}   the tile's active-site list
+//   rate[slot][list] f64, ce[slot][list] u64 {u32 cell, u32 event}: the per-tile active-site lists, slot-major
 //   cnt[tile]           i32  slots in use (tombstones with rate 0 included until the owner compacts)
 //   slot[cell]          u16  1-based slot of the cell in its tile's list, 0 = not listed
 //   tstat[tile]         per-tile counters (events, site updates, per-class counts), summed on demand
@@ -21,9 +21,7 @@
 
 namespace mskc {
 
-struct __align__(16) TileEntry { double rate; uint32_t cell; uint32_t ev; };
-
-struct TileStat {            // 64 B, written only by the tile's own warp
+struct TileStat {            // written only by the tile's own lane
   long long events, site_updates;
   int dep[3], evap, abs_, des;
   int dAtoms, dVoids;        // bulk / vacancy list size changes
@@ -36,9 +34,12 @@ struct SweepState {          // one per context, device resident
   long long max_cnt;
 };
 
+// Per-tile active lists, slot-major ("SoA over tiles"): entry k of list l lives at [k*NT + l], and the
+// lists of one colour are contiguous (l = colour*ntc + index), so the 32 lanes of a warp -- 32 tiles of
+// the running colour -- read 32 consecutive words when they scan slot k together.
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
-  TileEntry *entries = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
+  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr, *ntomb = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
   long long ncell = 0;
   long long base_atoms = 0, base_voids = 0;
@@ -48,9 +49,9 @@ struct ParallelCtx {
   bool ran = false, lists_stale = false, listed_flag_in_state = false;
 };
 
-struct TileView {            // what the kernels need, by value
-  int tile, ntx, nty, cap;
-  TileEntry *entries; int *cnt; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
+struct TileView {            // what the kernels need (constant memory)
+  int tile, ntx, nty, cap, NT, hx, ntc;
+  double *rate; unsigned long long *ce; int *cnt, *ntomb; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no per-tile generator state in memory ----
@@ -71,6 +72,11 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {       // uniform
 
 __constant__ TileView V;      // the current context's tile lists (uploaded with the DevCtx)
 
+__device__ __forceinline__ int list_of(P3 s) {          // list id of the tile that owns site s
+  int tx = s.x / V.tile, ty = s.y / V.tile;
+  return (((ty & 1) << 1) | (tx & 1)) * V.ntc + (ty >> 1) * V.hx + (tx >> 1);
+}
+
 struct TilePol {
   uint2 key; uint32_t tile_id; uint32_t step_lo, step_hi; uint32_t draw;
   double root;
@@ -82,19 +88,19 @@ struct TilePol {
   __device__ __forceinline__ double tree_root() const { return root; }
   __device__ __forceinline__ uint4 next4() { return philox4x32_10(make_uint4(tile_id, step_lo, step_hi, draw++), key); }
   __device__ __forceinline__ double uniform() { uint4 r = next4(); return u53(r.x, r.y); }
-  __device__ __forceinline__ int tile_of(P3 s) const { return (s.y / V.tile) * V.ntx + (s.x / V.tile); }
 
   __device__ __noinline__ void put(P3 s, long long c, int ev, double p) {
-    int t = tile_of(s);
+    int l = list_of(s);
     int sl = V.slot[c];
-    TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = (uint32_t)ev;
     if (sl == 0) {
-      int k = atomicAdd(&V.cnt[t], 1);
-      if (k >= V.cap) { atomicSub(&V.cnt[t], 1); fail(E_TILE_FULL, s.x, s.y, s.z, t); return; }
+      int k = atomicAdd(&V.cnt[l], 1);
+      if (k >= V.cap) { atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
       V.slot[c] = (uint16_t)(k + 1);
       sl = k + 1;
-    }
-    V.entries[(long long)t * V.cap + sl - 1] = e;
+    } else if (V.rate[(long long)(sl - 1) * V.NT + l] == 0.0) atomicSub(&V.ntomb[l], 1);       // a tombstone comes back to life
+    long long a = (long long)(sl - 1) * V.NT + l;
+    V.rate[a] = p;
+    V.ce[a] = (unsigned long long)(uint32_t)c | ((unsigned long long)(uint32_t)ev << 32);
   }
   __device__ __forceinline__ void add_mc(P3 s, long long c, const P3 nn[4], int ev, double p) {
     if (p == 0) { fail(E_ADD_ZERO, s.x, s.y, s.z); return; }
@@ -102,9 +108,13 @@ struct TilePol {
     put(s, c, ev, p);
   }
   __device__ __forceinline__ void set_rate(P3 s, long long c, int ev, double p) { put(s, c, ev, p); }
-  __device__ __forceinline__ void erase_mc(P3 s, long long c) {
+  __device__ __noinline__ void erase_mc(P3 s, long long c) {
     int sl = V.slot[c];
-    if (sl) V.entries[(long long)tile_of(s) * V.cap + sl - 1].rate = 0.0;      // tombstone; the owner compacts
+    if (sl) {
+      int l = list_of(s);
+      long long a = (long long)(sl - 1) * V.NT + l;
+      if (V.rate[a] != 0.0) { V.rate[a] = 0.0; atomicAdd(&V.ntomb[l], 1); }     // tombstone; the owner compacts
+    }
     D.bonds[c] = 0ull;
   }
   __device__ __forceinline__ void add_void(P3 s, long long c, const P3 nn[4]) { dVoids++; D.bonds[c] = enc_bonds(s, nn); }
@@ -116,126 +126,64 @@ struct TilePol {
   __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
 };
 
-// One colour step: every tile of colour (cx,cy) advances by tau.  One warp per tile; the lanes share
-// the selection scan, lane 0 applies the event (the transition rules are a serial dependency chain).
-__global__ void __launch_bounds__(128) colour_step_kernel(int cx, int cy, uint2 key, int max_events_per_tile) {
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int hx = V.ntx >> 1, hy = V.nty >> 1;
-  if (wid >= hx * hy) return;
-  const int tx = 2 * (wid % hx) + cx, ty = 2 * (wid / hx) + cy;
-  const int t = ty * V.ntx + tx;
-  TileEntry *E = V.entries + (long long)t * V.cap;
+// One colour step: every tile of colour `colour` advances by tau.  ONE LANE PER TILE: the 32 lanes of a
+// warp run 32 independent n-fold-way loops; the list scans are coalesced across lanes (slot-major lists),
+// the transition functions diverge by event type and re-converge in rq_flush / get_prob.
+__global__ void __launch_bounds__(32) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
+  const int wid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wid >= V.ntc) return;
+  const int l = colour * V.ntc + wid;
+  const long long NT = V.NT;
   const SweepState ss = *V.ss;
   const double tau = ss.tau;
-  int n = V.cnt[t];
-
-  // -- compaction: drop tombstones (rate 0), keep slot[] consistent
-  {
-    int w = 0;
-    for (int base = 0; base < n; base += 32) {
-      int i = base + lane;
-      TileEntry e; e.rate = 0; e.cell = 0; e.ev = 0;
-      bool live = false;
-      if (i < n) { e = E[i]; live = e.rate > 0.0; }
-      unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-      int pos = w + __popc(m & ((1u << lane) - 1u));
-      __syncwarp();
-      if (i < n) {
-        if (live) { if (pos != i) { E[pos] = e; V.slot[e.cell] = (uint16_t)(pos + 1); } }
-        else V.slot[e.cell] = 0;
-      }
-      w += __popc(m);
-      __syncwarp();
+  double *rate = V.rate + l; unsigned long long *ce = V.ce + l;
+  int n = V.cnt[l];
+  if (V.ntomb[l] > 0) {               // compaction: drop tombstones (swap with last), keep slot[] consistent
+    int i = 0;
+    while (i < n) {
+      if (rate[i * NT] == 0.0) {
+        V.slot[(uint32_t)ce[i * NT]] = 0;
+        n--;
+        if (i < n) { double r = rate[n * NT]; unsigned long long e = ce[n * NT]; rate[i * NT] = r; ce[i * NT] = e; if (r != 0.0) V.slot[(uint32_t)e] = (uint16_t)(i + 1); }
+      } else i++;
     }
-    if (w != n && lane == 0) V.cnt[t] = w;
-    n = w;
+    V.cnt[l] = n; V.ntomb[l] = 0;
   }
-  __syncwarp();
-
   TilePol pol;
-  pol.key = key; pol.tile_id = (uint32_t)t; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
+  pol.key = key; pol.tile_id = (uint32_t)l; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
   pol.root = ss.tree_root; pol.n_getprob = 0; pol.dAtoms = 0; pol.dVoids = 0;
   for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = 0; pol.CountCov[i] = 0; }
   int nev = 0, ndep[3] = {0, 0, 0}, nevap = 0, nabs = 0, ndes = 0;
-  double tloc = 0.0, Rlast = 0.0;
-
+  double tloc = 0.0, R = 0.0;
   while (true) {
-    n = V.cnt[t];                                   // own-tile appends happen through lane 0 of this warp
-    // per-lane partial sums over entries lane, lane+32, ...
-    double part = 0.0;
-    for (int i = lane; i < n; i += 32) part += E[i].rate;
-    double incl = part;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { double v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-    double R = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    Rlast = R;
+    n = V.cnt[l];
+    R = 0.0;
+    for (int i = 0; i < n; i++) R += rate[i * NT];
     if (!(R > 0.0) || nev >= max_events_per_tile || D.err[0] != 0) break;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (lane == 0) rnd = pol.next4();
-    rnd.x = __shfl_sync(0xFFFFFFFFu, rnd.x, 0); rnd.y = __shfl_sync(0xFFFFFFFFu, rnd.y, 0);
-    rnd.z = __shfl_sync(0xFFFFFFFFu, rnd.z, 0); rnd.w = __shfl_sync(0xFFFFFFFFu, rnd.w, 0);
+    uint4 rnd = pol.next4();
     tloc += -log(u53(rnd.x, rnd.y)) / R;
     if (tloc > tau) break;
-    double target = u53(rnd.z, rnd.w) * R;
-    // the lane whose inclusive prefix first exceeds target
-    unsigned m = __ballot_sync(0xFFFFFFFFu, incl > target);
-    int sel_lane = m ? (__ffs(m) - 1) : 31;
-    double before = __shfl_sync(0xFFFFFFFFu, incl - part, sel_lane);
-    int pick = -1;
-    if (lane == sel_lane) {
-      double acc = before; int last = -1;
-      for (int i = lane; i < n; i += 32) { double r = E[i].rate; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
-      if (pick < 0) pick = last;
+    double target = u53(rnd.z, rnd.w) * R, acc = 0.0;
+    int pick = -1, last = -1;
+    for (int i = 0; i < n; i++) { double r = rate[i * NT]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
+    if (pick < 0) pick = last;
+    unsigned long long e = ce[pick * NT];
+    uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
+    P3 Site = cell_xyz((long long)cell);
+    if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
+      uint32_t w = D.state[cell];
+      int T = D.la ? site_T(w, Site) : 0;
+      Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
     }
-    pick = __shfl_sync(0xFFFFFFFFu, pick, sel_lane);
-    if (pick < 0) break;
-    {
-      // Cooperative gather: the transition rules are one serial dependency chain (lane 0), but every
-      // address they will touch is known up front -- the site, its 4 neighbours and their 16 neighbours.
-      // Lanes 0-3 / 0-15 pull those words into this SM's L1 in two round trips so that lane 0 then runs
-      // on L1 hits instead of ~20 dependent L2/HBM round trips.
-      uint32_t cS = E[pick].cell;
-      unsigned long long bS = D.bonds[cS];
-      touch32(D.state + cS);
-      P3 S = cell_xyz((long long)cS);
-      unsigned long long bN = 0ull; P3 N = zero3(); bool okN = false;
-      if (lane < 4) {
-        N = dec_bond(S, (unsigned)((bS >> (16 * lane)) & 0xFFFFu));
-        okN = in_box(N);
-        if (okN) { long long cN = cidx_nofail(N); bN = D.bonds[cN]; touch32(D.state + cN); touch16(V.slot + cN); }
-      }
-      int src = lane >> 2;
-      unsigned long long bq = __shfl_sync(0xFFFFFFFFu, bN, src & 3);
-      P3 Nq; Nq.x = __shfl_sync(0xFFFFFFFFu, N.x, src & 3); Nq.y = __shfl_sync(0xFFFFFFFFu, N.y, src & 3); Nq.z = __shfl_sync(0xFFFFFFFFu, N.z, src & 3);
-      bool okq = __shfl_sync(0xFFFFFFFFu, (int)okN, src & 3) != 0;
-      if (lane < 16 && okq) {
-        P3 M = dec_bond(Nq, (unsigned)((bq >> (16 * (lane & 3))) & 0xFFFFu));
-        if (in_box(M)) { long long cM = cidx_nofail(M); touch32(D.state + cM); touch64(D.bonds + cM); }
-      }
-    }
-    if (lane == 0) {
-      TileEntry e = E[pick];
-      P3 Site = cell_xyz((long long)e.cell);
-      int Itrans = (int)e.ev;
-      if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
-        uint32_t w = D.state[e.cell];
-        int T = D.la ? site_T(w, Site) : 0;
-        Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
-      }
-      if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-      apply_event(pol, Site, Itrans);
-      nev++;
-    }
-    __syncwarp();
+    if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
+    apply_event(pol, Site, Itrans);
+    nev++;
   }
-  if (lane == 0) {
-    V.tile_rate[t] = Rlast;
-    TileStat &st = V.tstat[t];
-    st.events += nev; st.site_updates += pol.n_getprob;
-    for (int i = 0; i < 3; i++) { st.dep[i] += ndep[i]; st.dCrystal[i] += pol.CountCrystal[i]; st.dCov[i] += pol.CountCov[i]; }
-    st.evap += nevap; st.abs_ += nabs; st.des += ndes; st.dAtoms += pol.dAtoms; st.dVoids += pol.dVoids;
-  }
+  V.tile_rate[l] = R;
+  TileStat &st = V.tstat[l];
+  st.events += nev; st.site_updates += pol.n_getprob;
+  for (int i = 0; i < 3; i++) { st.dep[i] += ndep[i]; st.dCrystal[i] += pol.CountCrystal[i]; st.dCov[i] += pol.CountCov[i]; }
+  st.evap += nevap; st.abs_ += nabs; st.des += ndes; st.dAtoms += pol.dAtoms; st.dVoids += pol.dVoids;
 }
 
 // Per-sweep bookkeeping ("per-class rate sums"): total rate, active-site count, next tau, clock.
@@ -258,13 +206,11 @@ __global__ void __launch_bounds__(1024) sweep_stats_kernel(int ntiles, double ev
 __global__ void bump_step_kernel(SweepState *ss) { ss->step++; }
 
 __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
-  int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (t >= ntiles) return;
-  const TileEntry *E = V.entries + (long long)t * V.cap;
-  int n = V.cnt[t]; double part = 0;
-  for (int i = lane; i < n; i += 32) part += E[i].rate;
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xFFFFFFFFu, part, o);
-  if (lane == 0) V.tile_rate[t] = part;
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= ntiles) return;
+  int n = V.cnt[l]; double r = 0;
+  for (int i = 0; i < n; i++) r += V.rate[(long long)i * V.NT + l];
+  V.tile_rate[l] = r;
 }
 
 __global__ void __launch_bounds__(256) reduce_tstat_kernel(const TileStat *ts, int ntiles, TileStat *out) {
@@ -302,16 +248,17 @@ __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long l
   RatePol pol; pol.root = V.ss->tree_root; pol.n_getprob = 0;
   unsigned long long mine = 0;
   for (long long k = gid; k < total; k += (long long)gridDim.x * blockDim.x) {
-    int t = (int)(k / V.cap), i = (int)(k - (long long)t * V.cap);
-    if (i >= V.cnt[t]) continue;
-    TileEntry e = V.entries[k];
-    if (!(e.rate > 0.0)) continue;
-    P3 s = cell_xyz((long long)e.cell);
-    uint32_t w = D.state[e.cell];
-    P3 nn[4]; dec_bonds(s, D.bonds[e.cell], nn);
+    int i = (int)(k / ntiles), l = (int)(k - (long long)i * ntiles);
+    if (i >= V.cnt[l]) continue;
+    double r = V.rate[k];
+    if (!(r > 0.0)) continue;
+    uint32_t cell = (uint32_t)V.ce[k];
+    P3 s = cell_xyz((long long)cell);
+    uint32_t w = D.state[cell];
+    P3 nn[4]; dec_bonds(s, D.bonds[cell], nn);
     int ev = 0; double p = 0;
     get_prob(pol, w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, nn, ev, p);
-    if (ev != 0 && p > 0) { e.rate = p; e.ev = (uint32_t)ev; V.entries[k] = e; mine++; }
+    if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = (unsigned long long)cell | ((unsigned long long)(uint32_t)ev << 32); mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_sites, mine);
@@ -414,19 +361,19 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         D.state[c] = (1u << (PosSiC + sp - 1)) | (1u << PosOcc) | (2u << PosCoor);
         D.bonds[c] = enc_bonds(s, nn);
         double p = D.PE[IDXE(sp, 2, 0, 0, 0, 0, 0)];
-        int t = (y / V.tile) * V.ntx + (x / V.tile);
+        int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = 4; V.entries[(long long)t * V.cap + k] = e; V.slot[c] = (uint16_t)(k + 1);
+        V.rate[(long long)k * V.NT + t] = p; V.ce[(long long)k * V.NT + t] = (unsigned long long)(uint32_t)c | (4ull << 32); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       } else {
         D.state[c] = (2u << PosCoor);
         D.bonds[c] = enc_bonds(s, nn);
         double p = total_dep_abs(2, 0);
-        int t = (y / V.tile) * V.ntx + (x / V.tile);
+        int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        TileEntry e; e.rate = p; e.cell = (uint32_t)c; e.ev = EV_DRAW; V.entries[(long long)t * V.cap + k] = e; V.slot[c] = (uint16_t)(k + 1);
+        V.rate[(long long)k * V.NT + t] = p; V.ce[(long long)k * V.NT + t] = (unsigned long long)(uint32_t)c | ((unsigned long long)EV_DRAW << 32); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       }
     }
@@ -437,18 +384,21 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
 #define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (err) *err = std::string("CUDA error ") + cudaGetErrorString(e_) + " in " #call; return -1; } } while (0)
 
 static inline void parallel_free(ParallelCtx &P) {
-  cudaFree(P.entries); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
+  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.ntomb); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
 }
 static inline TileView tile_view(const ParallelCtx &P) {
-  TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.entries = P.entries; V.cnt = P.cnt; V.slot = P.slot;
+  TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
+  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.ntomb = P.ntomb; V.slot = P.slot;
   V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; return V;
 }
 static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int cap, std::string *err) {
   int tile = 24;
   if (H.LX % (2 * tile) || H.LY % (2 * tile)) { if (err) *err = "parallel sampler needs LenX and LenY to be multiples of 48 (24-unit tiles, 2x2 colouring)"; return -1; }
-  if (P.entries && P.cap == cap && P.ncell == H.ncell) {
+  if (P.rate && P.cap == cap && P.ncell == H.ncell) {
     PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
+    PCK(cudaMemsetAsync(P.ntomb, 0, (size_t)P.ntiles * sizeof(int), st));
+    PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
     PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
     PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
@@ -457,15 +407,19 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   }
   parallel_free(P);
   P.tile = tile; P.ntx = H.LX / tile; P.nty = H.LY / tile; P.ntiles = P.ntx * P.nty; P.cap = cap; P.ncell = H.ncell;
-  PCK(cudaMalloc(&P.entries, (size_t)P.ntiles * cap * sizeof(TileEntry)));
+  PCK(cudaMalloc(&P.rate, (size_t)P.ntiles * cap * sizeof(double)));
+  PCK(cudaMalloc(&P.ce, (size_t)P.ntiles * cap * sizeof(unsigned long long)));
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
+  PCK(cudaMalloc(&P.ntomb, (size_t)P.ntiles * sizeof(int)));
   PCK(cudaMalloc(&P.slot, (size_t)H.ncell * sizeof(uint16_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
   PCK(cudaMalloc(&P.ss, sizeof(SweepState)));
   PCK(cudaMalloc(&P.tot, sizeof(TileStat)));
-  PCK(cudaMemsetAsync(P.entries, 0, (size_t)P.ntiles * cap * sizeof(TileEntry), st));
+  PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
+  PCK(cudaMemsetAsync(P.ce, 0, (size_t)P.ntiles * cap * sizeof(unsigned long long), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
+  PCK(cudaMemsetAsync(P.ntomb, 0, (size_t)P.ntiles * sizeof(int), st));
   PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
@@ -479,23 +433,27 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
                                             const double *mc_rate, int n_bulk, int n_void, std::string *err) {
   if (H.LX % 48 || H.LY % 48) { P.lists_stale = true; return 0; }      // parity-only box
   if (parallel_alloc(P, H, st, TILE_CAP, err)) return -1;
-  std::vector<TileEntry> E((size_t)P.ntiles * P.cap); std::vector<int> cnt(P.ntiles, 0); std::vector<uint16_t> slot((size_t)H.ncell, 0);
-  memset(E.data(), 0, E.size() * sizeof(TileEntry));
+  std::vector<double> R((size_t)P.ntiles * P.cap, 0.0); std::vector<unsigned long long> CE((size_t)P.ntiles * P.cap, 0ull);
+  std::vector<int> cnt(P.ntiles, 0); std::vector<uint16_t> slot((size_t)H.ncell, 0);
   long long plane = (long long)H.LX * H.LY;
+  const int hx = P.ntx / 2, ntc = (P.ntx / 2) * (P.nty / 2);
   for (int i = 0; i < n_mc; i++) {
     uint32_t c = mc_cell[i];
     long long r = c % plane; int y = (int)(r / H.LX), x = (int)(r - (long long)y * H.LX);
-    int t = (y / P.tile) * P.ntx + (x / P.tile);
+    int tx = x / P.tile, ty = y / P.tile;
+    int t = (((ty & 1) << 1) | (tx & 1)) * ntc + (ty >> 1) * hx + (tx >> 1);
     if (cnt[t] >= P.cap) { if (err) *err = "per-tile active list capacity exceeded at upload"; return -1; }
-    TileEntry e; e.rate = mc_rate[i]; e.cell = c;
     // pre-drawn deposition/adsorption codes (1..3, >=6) of empty sites become "draw at fire time",
-    // except the forced code-1 entry of Get_Prob.f:182-183 (rate 1e-8)
+    // except the forced code-1 entry of Get_Prob.f:182-183 (rate 1e-8) / Get_Prob_Ini.f:104 (1e-6)
     int ev = mc_ev[i];
-    bool forced = (ev == 1 && mc_rate[i] == (double)1.e-8f) || (ev == 1 && mc_rate[i] == (double)1.e-6f);
-    e.ev = (ev == 4 || ev == 5 || forced) ? (uint32_t)ev : (uint32_t)EV_DRAW;
-    E[(size_t)t * P.cap + cnt[t]] = e; slot[c] = (uint16_t)(++cnt[t]);
+    bool forced = ev == 1 && (mc_rate[i] == (double)1.e-8f || mc_rate[i] == (double)1.e-6f);
+    uint32_t e = (ev == 4 || ev == 5 || forced) ? (uint32_t)ev : (uint32_t)EV_DRAW;
+    size_t a = (size_t)cnt[t] * P.ntiles + t;
+    R[a] = mc_rate[i]; CE[a] = (unsigned long long)c | ((unsigned long long)e << 32);
+    slot[c] = (uint16_t)(++cnt[t]);
   }
-  PCK(cudaMemcpyAsync(P.entries, E.data(), E.size() * sizeof(TileEntry), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(P.rate, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(P.ce, CE.data(), CE.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(P.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(P.slot, slot.data(), slot.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   PCK(cudaStreamSynchronize(st));
@@ -528,14 +486,14 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
 static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
-  const int wpb = 4, blocks = (ntc + wpb - 1) / wpb;
+  const int blocks = (ntc + 31) / 32;
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
   int launches = 0;
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
-    tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.ntiles);
+    tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
     sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, ept, a->tau_fixed, 0);
     launches += 2;
   }
@@ -549,7 +507,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   for (long long s = 0; s < a->n_sweeps; s++) {
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
-      colour_step_kernel<<<blocks, wpb * 32, 0, st>>>(order[c][0], order[c][1], key, 1 << 20);
+      colour_step_kernel<<<blocks, 32, 0, st>>>(order[c][1] * 2 + order[c][0], key, 1 << 20);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
@@ -587,7 +545,7 @@ static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cu
   PCK(cudaMalloc(&d_n, 8)); PCK(cudaMemsetAsync(d_n, 0, 8, st));
   PCK(cudaEventRecord(e0, st));
   rerate_kernel<<<148 * 8, 256, 0, st>>>(P.ntiles, d_n);
-  tile_rate_kernel<<<(P.ntiles * 32 + 255) / 256, 256, 0, st>>>(P.ntiles);
+  tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
   sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, 4.0, 0.0, 0);
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
