@@ -171,6 +171,9 @@ int mskc_state_hash(mskc_ctx *h, uint64_t *hash);
 typedef struct { int64_t undercoordinated, coverage, noepi_bulk, bulk, occupied, walls; double mean_height, sq_height; } mskc_census;
 int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms);
 
+/* diagnostics: raw per-tile counters of the sublattice sampler (80 B records, colour-major list order) */
+int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles);
+
 #ifdef __cplusplus
 }
 #endif

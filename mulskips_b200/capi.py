@@ -65,7 +65,7 @@ _LIB = None
 SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_upload_state",
            "mskc_init_flat", "mskc_seed", "mskc_get_rng", "mskc_set_clock", "mskc_run_parity", "mskc_run_parallel",
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
-           "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice"]
+           "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats"]
 
 
 def load_library():
@@ -100,6 +100,7 @@ def load_library():
     lib.mskc_download_lists.argtypes = [vp, i32p, i32p, i32p, f64p, i32p, i32p, i32p, i32p, C.c_int64, i64p]
     lib.mskc_state_hash.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.mskc_census_lattice.argtypes = [vp, C.POINTER(Census), C.POINTER(C.c_float)]
+    lib.mskc_debug_tile_stats.argtypes = [vp, C.c_void_p, C.c_int64, i64p]
     for s in SYMBOLS:
         if s != "mskc_last_error":
             getattr(lib, s).restype = C.c_int
@@ -248,6 +249,15 @@ class Mskc:
         v = C.c_uint64()
         self._ck(self.lib.mskc_state_hash(self.h, C.byref(v)))
         return v.value
+
+    def tile_stats(self):
+        n = C.c_int64()
+        self._ck(self.lib.mskc_debug_tile_stats(self.h, None, 0, C.byref(n)))
+        dt = np.dtype([("events", "<i8"), ("site_updates", "<i8"), ("dep", "<i4", 3), ("evap", "<i4"), ("abs", "<i4"), ("des", "<i4"), ("dAtoms", "<i4"),
+                       ("dVoids", "<i4"), ("dCrystal", "<i4", 3), ("dCov", "<i4", 3), ("maxev", "<i4"), ("pad", "<i4")])
+        a = np.zeros(n.value, dt)
+        self._ck(self.lib.mskc_debug_tile_stats(self.h, a.ctypes.data, n.value, C.byref(n)))
+        return a
 
     def census(self):
         c = Census(); ms = C.c_float()

@@ -570,3 +570,14 @@ extern "C" int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate
   if (parallel_rerate(h->PC, h->D, h->stream, h->ev0, h->ev1, n_sites, total_rate, kernel_ms, &h->err)) { g_last_error = h->err; return -1; }
   return check_dev_err(h);
 }
+
+// diagnostics: raw per-tile counters (TileStat, 80 B each: i64 events, i64 site_updates, i32 dep[3], evap, abs, des, dAtoms, dVoids,
+// dCrystal[3], dCov[3], maxev, pad), list id order (colour-major)
+extern "C" int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles) {
+  if (!h || !h->parallel_ready) return set_err(h, "mskc_debug_tile_stats: no parallel state");
+  CK(cudaSetDevice(h->device));
+  if (ntiles) *ntiles = h->PC.ntiles;
+  int64_t n = h->PC.ntiles < max_tiles ? h->PC.ntiles : max_tiles;
+  if (out && n > 0) CK(cudaMemcpy(out, h->PC.tstat, (size_t)n * sizeof(TileStat), cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -359,22 +359,28 @@ __device__ __forceinline__ void rq_push(RQ &q, int act, P3 N, long long c, int O
   it.nn[0] = nn[0]; it.nn[1] = nn[1]; it.nn[2] = nn[2]; it.nn[3] = nn[3];
 }
 template <class Pol>
+__device__ __forceinline__ void rq_commit(Pol &pol, RQItem &it, int ev, double p) {
+  if (it.pre) D.state[it.c] = it.pre_w;            // the site's own coordination is written after its neighbours were rated
+  switch (it.act) {
+    case A_NEW: if (ev != 0) pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+    case A_SETVOID: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_void(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
+    case A_SETBULK: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
+    case A_SET: pol.set_rate(it.N, it.c, ev, p); break;
+    case A_VOID2MC: pol.erase_void(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+    case A_BULK2MC: pol.erase_bulk(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+    default: pol.erase_mc(it.N, it.c); break;
+  }
+}
+// serial flush, in request order (parity mode: the order of tree/list operations is the reference's)
+template <class Pol>
 __device__ __noinline__ void rq_flush(Pol &pol, RQ &q) {
 #pragma unroll 1
   for (int k = 0; k < q.n; k++) {
     RQItem &it = q.it[k];
-    if (it.pre) D.state[it.c] = it.pre_w;          // the site's own coordination is written after its neighbours were rated
+    if (it.pre) { D.state[it.c] = it.pre_w; it.pre = 0; }
     int ev = 0; double p = 0.0;
     if (it.act != A_ERASE) get_prob(pol, it.Occ, it.NSiC, it.Cov, it.Coor, it.N, it.nn, ev, p);
-    switch (it.act) {
-      case A_NEW: if (ev != 0) pol.add_mc(it.N, it.c, it.nn, ev, p); break;
-      case A_SETVOID: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_void(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
-      case A_SETBULK: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
-      case A_SET: pol.set_rate(it.N, it.c, ev, p); break;
-      case A_VOID2MC: pol.erase_void(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
-      case A_BULK2MC: pol.erase_bulk(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
-      default: pol.erase_mc(it.N, it.c); break;
-    }
+    rq_commit(pol, it, ev, p);
   }
   q.n = 0;
 }
@@ -600,7 +606,20 @@ __device__ __noinline__ void desorption(Pol &pol, RQ &q, P3 Site) {
   rq_push(q, A_SET, Site, cS, 0, 0, 0, Coor, NextN);
 }
 
-// dispatch of main.f:335-357
+// dispatch of main.f:335-357; the re-rate requests are left in q
+template <class Pol>
+__device__ __forceinline__ void apply_event_q(Pol &pol, RQ &q, P3 Site, int Itrans) {
+  q.n = 0;
+  if (Itrans <= 3) { deposition(pol, q, Site, Itrans); if (Itrans >= 1) pol.CountCrystal[Itrans - 1]++; }
+  else if (Itrans == 4) evaporation(pol, q, Site);
+  else if (Itrans == 5) desorption(pol, q, Site);
+  else {
+    int k = Itrans - 5;
+    if (k > 3) { fail(E_BADEV, Site.x, Site.y, Site.z, Itrans); return; }
+    absorption(pol, q, Site, D.ListCov[k - 1]);
+    pol.CountCov[k - 1]++;
+  }
+}
 template <class Pol>
 __device__ __forceinline__ void apply_event(Pol &pol, P3 Site, int Itrans) {
   RQ q; q.n = 0;

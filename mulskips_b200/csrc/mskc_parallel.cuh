@@ -15,6 +15,8 @@
 #include "mskc_device.cuh"
 #include "../../include/mskc.h"
 #include <algorithm>
+#include <cstdlib>
+#include <cstdio>
 #include <functional>
 #include <string>
 #include <vector>
@@ -26,6 +28,7 @@ struct TileStat {            // written only by the tile's own lane
   int dep[3], evap, abs_, des;
   int dAtoms, dVoids;        // bulk / vacancy list size changes
   int dCrystal[3]; int dCov[3];
+  int maxev, pad;            // most events this tile executed in one colour step
 };
 
 struct SweepState {          // one per context, device resident
@@ -126,29 +129,42 @@ struct TilePol {
   __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
 };
 
-// One colour step: every tile of colour `colour` advances by tau.  ONE LANE PER TILE: the 32 lanes of a
-// warp run 32 independent n-fold-way loops; the list scans are coalesced across lanes (slot-major lists),
-// the transition functions diverge by event type and re-converge in rq_flush / get_prob.
-__global__ void __launch_bounds__(32) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
-  const int wid = blockIdx.x * blockDim.x + threadIdx.x;
+// One colour step: every tile of colour `colour` advances by tau.
+// A TEAM of lanes (1..32, power of two) owns one tile, 32/TEAM tiles share a warp.  The team leader runs
+// the transition function (a serial dependency chain); the whole team shares (a) the rate sum / pick scan
+// over the tile's list and (b) the re-rate requests the event queued (one Get_Prob per lane).  Lists are
+// slot-major, so the leaders' / teams' scans are coalesced across the tiles of a warp.
+template <int TEAM>
+__global__ void __launch_bounds__(32) colour_step_kernel(int colour, uint2 key, int max_events_per_tile, int dbg_lid) {
+  constexpr int TPW = 32 / TEAM;
+  __shared__ RQ sq[TPW];
+  const int lane = threadIdx.x, team = lane / TEAM, tl = lane % TEAM;
+  const unsigned tmask = (TEAM == 32) ? 0xFFFFFFFFu : (((1u << TEAM) - 1u) << (team * TEAM));
+  const int leader = team * TEAM;
+  const int wid = blockIdx.x * TPW + team;
   if (wid >= V.ntc) return;
   const int l = colour * V.ntc + wid;
   const long long NT = V.NT;
   const SweepState ss = *V.ss;
   const double tau = ss.tau;
   double *rate = V.rate + l; unsigned long long *ce = V.ce + l;
-  int n = V.cnt[l];
-  if (V.ntomb[l] > 0) {               // compaction: drop tombstones (swap with last), keep slot[] consistent
-    int i = 0;
-    while (i < n) {
-      if (rate[i * NT] == 0.0) {
-        V.slot[(uint32_t)ce[i * NT]] = 0;
-        n--;
-        if (i < n) { double r = rate[n * NT]; unsigned long long e = ce[n * NT]; rate[i * NT] = r; ce[i * NT] = e; if (r != 0.0) V.slot[(uint32_t)e] = (uint16_t)(i + 1); }
-      } else i++;
+  RQ &q = sq[team];
+  if (tl == 0) {
+    int n = V.cnt[l];
+    if (V.ntomb[l] > 0) {               // compaction: drop tombstones (swap with last), keep slot[] consistent
+      int i = 0;
+      while (i < n) {
+        if (rate[i * NT] == 0.0) {
+          V.slot[(uint32_t)ce[i * NT]] = 0;
+          n--;
+          if (i < n) { double r = rate[n * NT]; unsigned long long e = ce[n * NT]; rate[i * NT] = r; ce[i * NT] = e; if (r != 0.0) V.slot[(uint32_t)e] = (uint16_t)(i + 1); }
+        } else i++;
+      }
+      V.cnt[l] = n; V.ntomb[l] = 0;
     }
-    V.cnt[l] = n; V.ntomb[l] = 0;
+    q.n = 0;
   }
+  __syncwarp(tmask);
   TilePol pol;
   pol.key = key; pol.tile_id = (uint32_t)l; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
   pol.root = ss.tree_root; pol.n_getprob = 0; pol.dAtoms = 0; pol.dVoids = 0;
@@ -156,34 +172,85 @@ __global__ void __launch_bounds__(32) colour_step_kernel(int colour, uint2 key, 
   int nev = 0, ndep[3] = {0, 0, 0}, nevap = 0, nabs = 0, ndes = 0;
   double tloc = 0.0, R = 0.0;
   while (true) {
-    n = V.cnt[l];
-    R = 0.0;
-    for (int i = 0; i < n; i++) R += rate[i * NT];
-    if (!(R > 0.0) || nev >= max_events_per_tile || D.err[0] != 0) break;
-    uint4 rnd = pol.next4();
+    const int n = V.cnt[l];
+    // team-parallel rate sum (strided over the slots), inclusive prefix over the team
+    double part = 0.0;
+    for (int i = tl; i < n; i += TEAM) part += rate[i * NT];
+    double incl = part;
+#pragma unroll
+    for (int o = 1; o < TEAM; o <<= 1) { double v = __shfl_up_sync(tmask, incl, o, TEAM); if (tl >= o) incl += v; }
+    R = __shfl_sync(tmask, incl, leader + TEAM - 1);
+    int stop = 0;
+    if (tl == 0) stop = (nev >= max_events_per_tile) || (D.err[0] != 0);
+    stop = __shfl_sync(tmask, stop, leader);
+    if (stop || !(R > 0.0)) break;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    if (tl == 0) rnd = pol.next4();
+    rnd.x = __shfl_sync(tmask, rnd.x, leader); rnd.y = __shfl_sync(tmask, rnd.y, leader);
+    rnd.z = __shfl_sync(tmask, rnd.z, leader); rnd.w = __shfl_sync(tmask, rnd.w, leader);
     tloc += -log(u53(rnd.x, rnd.y)) / R;
     if (tloc > tau) break;
-    double target = u53(rnd.z, rnd.w) * R, acc = 0.0;
-    int pick = -1, last = -1;
-    for (int i = 0; i < n; i++) { double r = rate[i * NT]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
-    if (pick < 0) pick = last;
-    unsigned long long e = ce[pick * NT];
-    uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
-    P3 Site = cell_xyz((long long)cell);
-    if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
-      uint32_t w = D.state[cell];
-      int T = D.la ? site_T(w, Site) : 0;
-      Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
+    const double target = u53(rnd.z, rnd.w) * R;
+    unsigned m = __ballot_sync(tmask, incl > target) & tmask;
+    int sel = m ? (__ffs(m) - 1) : (leader + TEAM - 1);
+    double before = __shfl_sync(tmask, incl - part, sel);
+    int pick = -1;
+    if (lane == sel) {
+      double acc = before; int last = -1;
+      for (int i = tl; i < n; i += TEAM) { double r = rate[i * NT]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
+      if (pick < 0) pick = last;
     }
-    if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-    apply_event(pol, Site, Itrans);
-    nev++;
+    pick = __shfl_sync(tmask, pick, sel);
+    if (pick < 0) {            // rounding left the chosen lane without a live entry: take any live one
+      int mine = -1;
+      for (int i = tl; i < n; i += TEAM) if (rate[i * NT] > 0.0) { mine = i; break; }
+      unsigned mm = __ballot_sync(tmask, mine >= 0) & tmask;
+      if (!mm) break;
+      pick = __shfl_sync(tmask, mine, __ffs(mm) - 1);
+    }
+    if (tl == 0) {
+      unsigned long long e = ce[pick * NT];
+      uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
+      P3 Site = cell_xyz((long long)cell);
+      if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
+        uint32_t w = D.state[cell];
+        int T = D.la ? site_T(w, Site) : 0;
+        Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
+      }
+      if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
+      if (l == dbg_lid) printf("DBG step %lld ev#%d site %d %d %d Itrans %d w=%08x rate=%g R=%g tloc=%g tau=%g n=%d\n", ss.step, nev, Site.x, Site.y, Site.z, Itrans, D.state[cell], rate[pick * NT], R, tloc, tau, n);
+      apply_event_q(pol, q, Site, Itrans);
+      nev++;
+    }
+    __syncwarp(tmask);
+    // the queued re-rate requests: one Get_Prob per lane, then the list updates (any order: slots are
+    // claimed with atomics and every request concerns a different cell)
+    const int nq = q.n;
+    for (int k0 = 0; k0 < nq; k0 += TEAM) {
+      const int k = k0 + tl;
+      int ev = 0; double p = 0.0;
+      if (k < nq && q.it[k].act != A_ERASE) { RQItem &it = q.it[k]; get_prob(pol, it.Occ, it.NSiC, it.Cov, it.Coor, it.N, it.nn, ev, p); }
+      __syncwarp(tmask);
+      if (k < nq) rq_commit(pol, q.it[k], ev, p);
+      __syncwarp(tmask);
+    }
+    if (tl == 0) q.n = 0;
+    __syncwarp(tmask);
   }
-  V.tile_rate[l] = R;
-  TileStat &st = V.tstat[l];
-  st.events += nev; st.site_updates += pol.n_getprob;
-  for (int i = 0; i < 3; i++) { st.dep[i] += ndep[i]; st.dCrystal[i] += pol.CountCrystal[i]; st.dCov[i] += pol.CountCov[i]; }
-  st.evap += nevap; st.abs_ += nabs; st.des += ndes; st.dAtoms += pol.dAtoms; st.dVoids += pol.dVoids;
+  // team totals -> leader
+  long long ngp = pol.n_getprob; int dA = pol.dAtoms, dV = pol.dVoids;
+#pragma unroll
+  for (int o = TEAM / 2; o > 0; o >>= 1) {
+    ngp += __shfl_down_sync(tmask, ngp, o, TEAM); dA += __shfl_down_sync(tmask, dA, o, TEAM); dV += __shfl_down_sync(tmask, dV, o, TEAM);
+  }
+  if (tl == 0) {
+    V.tile_rate[l] = R;
+    TileStat &st = V.tstat[l];
+    st.events += nev; st.site_updates += ngp;
+    for (int i = 0; i < 3; i++) { st.dep[i] += ndep[i]; st.dCrystal[i] += pol.CountCrystal[i]; st.dCov[i] += pol.CountCov[i]; }
+    st.evap += nevap; st.abs_ += nabs; st.des += ndes; st.dAtoms += dA; st.dVoids += dV;
+    if (nev > st.maxev) st.maxev = nev;
+  }
 }
 
 // Per-sweep bookkeeping ("per-class rate sums"): total rate, active-site count, next tau, clock.
@@ -223,14 +290,16 @@ __global__ void __launch_bounds__(256) reduce_tstat_kernel(const TileStat *ts, i
   for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
     const TileStat &s = ts[t];
     loc[0] += s.events; loc[1] += s.site_updates; loc[2] += s.dep[0]; loc[3] += s.dep[1]; loc[4] += s.dep[2]; loc[5] += s.evap; loc[6] += s.abs_; loc[7] += s.des;
-    loc[8] += s.dAtoms; loc[9] += s.dVoids; loc[10] += s.dCrystal[0]; loc[11] += s.dCrystal[1]; loc[12] += s.dCrystal[2]; loc[13] += s.dCov[0]; loc[14] += s.dCov[1]; loc[15] += s.dCov[2];
+    loc[8] += s.dAtoms; loc[9] += s.dVoids; if (s.maxev > loc[16]) loc[16] = s.maxev; loc[10] += s.dCrystal[0]; loc[11] += s.dCrystal[1]; loc[12] += s.dCrystal[2]; loc[13] += s.dCov[0]; loc[14] += s.dCov[1]; loc[15] += s.dCov[2];
   }
   for (int k = 0; k < 16; k++) atomicAdd((unsigned long long *)&acc[k], (unsigned long long)loc[k]);
+  atomicMax((long long *)&acc[16], loc[16]);
   __syncthreads();
   if (threadIdx.x == 0) {
     out->events = acc[0]; out->site_updates = acc[1]; out->dep[0] = (int)acc[2]; out->dep[1] = (int)acc[3]; out->dep[2] = (int)acc[4];
     out->evap = (int)acc[5]; out->abs_ = (int)acc[6]; out->des = (int)acc[7]; out->dAtoms = (int)acc[8]; out->dVoids = (int)acc[9];
     for (int i = 0; i < 3; i++) { out->dCrystal[i] = (int)acc[10 + i]; out->dCov[i] = (int)acc[13 + i]; }
+    out->maxev = (int)acc[16];
   }
 }
 
@@ -486,7 +555,11 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
 static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
-  const int blocks = (ntc + 31) / 32;
+  int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
+  if (teamsz != 1 && teamsz != 2 && teamsz != 4 && teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
+  const int tpw = 32 / teamsz;
+  const int blocks = (ntc + tpw - 1) / tpw;
+  int dbg_lid = -1; if (const char *e = getenv("MSKC_DBG_LID")) dbg_lid = atoi(e);
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
@@ -507,7 +580,15 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   for (long long s = 0; s < a->n_sweeps; s++) {
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
-      colour_step_kernel<<<blocks, 32, 0, st>>>(order[c][1] * 2 + order[c][0], key, 1 << 20);
+      const int col = order[c][1] * 2 + order[c][0];
+      switch (teamsz) {
+        case 1: colour_step_kernel<1><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+        case 2: colour_step_kernel<2><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+        case 4: colour_step_kernel<4><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+        case 8: colour_step_kernel<8><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+        case 16: colour_step_kernel<16><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+        default: colour_step_kernel<32><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
+      }
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
@@ -534,7 +615,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   r->sweeps_done = a->n_sweeps; r->time = P.h_ss.time; r->total_rate = P.h_ss.total_rate; r->n_active = P.h_ss.n_active;
   for (int i = 0; i < 3; i++) r->count_dep[i] = P.h_tot.dep[i] - before.dep[i];
   r->count_evap = P.h_tot.evap - before.evap; r->count_abs = P.h_tot.abs_ - before.abs_; r->count_des = P.h_tot.des - before.des;
-  r->launches = launches; r->stop_reason = MSKC_STOP_BUDGET;
+  r->launches = launches; r->stop_reason = P.h_tot.maxev;   /* diagnostic: max events of one tile in one colour step */
   (void)ke;
   P.time = P.h_ss.time;
   return 0;
