@@ -171,6 +171,19 @@ int mskc_state_hash(mskc_ctx *h, uint64_t *hash);
 typedef struct { int64_t undercoordinated, coverage, noepi_bulk, bulk, occupied, walls; double mean_height, sq_height; } mskc_census;
 int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms);
 
+/* Test/diagnostic entry points of the sampler's transition code (no counterpart in the reference).
+ * mskc_replay_events applies n GIVEN events one after the other through the same warp-cooperative
+ * transition + re-rate code mskc_run_parallel uses: site_xyz [n][3], event codes as in main.f:335-357,
+ * arm[i] = 0 let IF_Arm_Choice.f decide (ties -> zig-zag), 1 force zig-zag, 2 force arm-chair.  tree_root
+ * stands for Tree(1) in the isolated-atom rate (Get_Prob.f:305).  tests/ replay the CPU oracle's event
+ * trace with it and compare lattice words, bonds and rates bit for bit. */
+int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xyz, const int32_t *event, const int32_t *arm, double tree_root);
+/* the sampler's active-site lists, unordered: site, event class (1..5 as main.f; 100 = deposit/adsorb with
+ * the species drawn when the event fires), rate.  cap = capacity of the arrays, *n = entries found. */
+int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int32_t *event, double *rate, int64_t *n);
+/* the four stored bond targets (absolute coordinates, (0,0,0) = not fixed) of n given cells */
+int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, int32_t *nn);
+
 /* diagnostics: raw per-tile counters of the sublattice sampler (80 B records, colour-major list order) */
 int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles);
 

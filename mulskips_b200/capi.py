@@ -65,7 +65,8 @@ _LIB = None
 SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_upload_state",
            "mskc_init_flat", "mskc_seed", "mskc_get_rng", "mskc_set_clock", "mskc_run_parity", "mskc_run_parallel",
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
-           "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats"]
+           "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
+           "mskc_replay_events", "mskc_download_active", "mskc_download_bonds"]
 
 
 def load_library():
@@ -101,6 +102,9 @@ def load_library():
     lib.mskc_state_hash.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.mskc_census_lattice.argtypes = [vp, C.POINTER(Census), C.POINTER(C.c_float)]
     lib.mskc_debug_tile_stats.argtypes = [vp, C.c_void_p, C.c_int64, i64p]
+    lib.mskc_replay_events.argtypes = [vp, C.c_int64, i32p, i32p, i32p, C.c_double]
+    lib.mskc_download_active.argtypes = [vp, C.c_int64, i32p, i32p, f64p, i64p]
+    lib.mskc_download_bonds.argtypes = [vp, C.c_int64, i32p, i32p]
     for s in SYMBOLS:
         if s != "mskc_last_error":
             getattr(lib, s).restype = C.c_int
@@ -258,6 +262,28 @@ class Mskc:
         a = np.zeros(n.value, dt)
         self._ck(self.lib.mskc_debug_tile_stats(self.h, a.ctypes.data, n.value, C.byref(n)))
         return a
+
+    # -- test/diagnostic entry points of the sampler's transition code -------------------------------
+    def replay_events(self, site_xyz, event, arm, tree_root=1.0):
+        sx, ev, ar = _i32(site_xyz).reshape(-1, 3), _i32(event).reshape(-1), _i32(arm).reshape(-1)
+        assert len(sx) == len(ev) == len(ar)
+        self._ck(self.lib.mskc_replay_events(self.h, len(ev), _p(sx, C.c_int32), _p(ev, C.c_int32), _p(ar, C.c_int32), float(tree_root)))
+
+    def download_active(self):
+        n = C.c_int64()
+        self._ck(self.lib.mskc_download_active(self.h, 0, None, None, None, C.byref(n)))
+        cap = max(n.value, 1)
+        xyz, ev, rate = np.zeros((cap, 3), np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+        self._ck(self.lib.mskc_download_active(self.h, cap, _p(xyz, C.c_int32), _p(ev, C.c_int32), _p(rate, C.c_double), C.byref(n)))
+        k = min(n.value, cap)
+        return xyz[:k], ev[:k], rate[:k]
+
+    def download_bonds(self, xyz):
+        x = _i32(xyz).reshape(-1, 3)
+        nn = np.zeros((max(len(x), 1), 4, 3), np.int32)
+        if len(x):
+            self._ck(self.lib.mskc_download_bonds(self.h, len(x), _p(x, C.c_int32), _p(nn, C.c_int32)))
+        return nn[:len(x)]
 
     def census(self):
         c = Census(); ms = C.c_float()

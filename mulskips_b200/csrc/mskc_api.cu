@@ -28,6 +28,7 @@ struct mskc_ctx {
   short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr;
   int *d_err = nullptr;
   int32_t *d_stage = nullptr;
+  unsigned short *d_arm_tab = nullptr;
   // parity mode
   int NumMcMax = 500000, NumVdMax = 100000, Levels = 20;
   double *d_Tree = nullptr; uint32_t *d_lattind = nullptr, *d_mc_cell = nullptr, *d_void_cell = nullptr; int *d_mc_ev = nullptr;
@@ -132,6 +133,32 @@ extern "C" int mskc_create(int lenx, int leny, int lenz, int ncrystal, int ncov,
   // FIND_NN.f:27,51-52: Pi is a REAL(4) literal; cos/sin from the host libm, as in the CPU reference
   const double Pi = (double)3.14159265358979323f;
   for (int irot = 1; irot <= 2; irot++) { D.rot_c[irot - 1] = cos((double)(2 * irot) * Pi / 3.0); D.rot_s[irot - 1] = sin((double)(2 * irot) * Pi / 3.0); }
+  // arm-chair offsets of FIND_SN.f:66-70 for every bond code: NINT(8.6602254037f * unit(S - C)), S - C = -v(code),
+  // by the reference's own IEEE sequence (divide by the norm, multiply, NINT); entries within 1e-6 of a
+  // rounding tie (where NINT(sn + x) could differ from sn + NINT(x)) and the zero vector stay 0 = "use find_sn()"
+  {
+    std::vector<unsigned short> tab(32768, 0);
+    const double ARM = (double)8.6602254037f;
+    for (int code = 1; code < 32768; code++) {
+      int vx = (code & 31) - 16, vy = ((code >> 5) & 31) - 16, vz = ((code >> 10) & 31) - 16;
+      if (vx == -16 || vy == -16 || vz == -16 || (vx == 0 && vy == 0 && vz == 0)) continue;
+      double ax[3] = {(double)-vx, (double)-vy, (double)-vz};
+      double snorm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+      int o[3]; bool ok = true;
+      for (int k = 0; k < 3; k++) {
+        ax[k] = ax[k] / snorm;
+        double x = ARM * ax[k];
+        double fr = fabs(x) - floor(fabs(x));
+        if (fabs(fr - 0.5) < 1e-6) ok = false;
+        o[k] = (int)(x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5));
+      }
+      if (ok) tab[code] = (unsigned short)((o[0] + 16) | ((o[1] + 16) << 5) | ((o[2] + 16) << 10));
+    }
+    CK(cudaMalloc(&h->d_arm_tab, tab.size() * sizeof(unsigned short)));
+    CK(cudaMemcpyAsync(h->d_arm_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    D.arm_tab = h->d_arm_tab;
+  }
   // AllocateArrays.f:30-43
   h->NumMcMax = nummcmax > 0 ? nummcmax : 500000;
   h->Levels = 0;
@@ -148,7 +175,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
-  cudaFree(h->d_stage);
+  cudaFree(h->d_stage); cudaFree(h->d_arm_tab);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   parallel_free(h->PC);
@@ -340,6 +367,7 @@ extern "C" int mskc_set_clock(mskc_ctx *h, int64_t iter, double time, const int3
   for (int i = 0; i < 3; i++) { if (CountCrystal) S.CountCrystal[i] = CountCrystal[i]; if (CountCov) S.CountCov[i] = CountCov[i]; }
   CK(cudaMemcpy(h->d_ps, &S, sizeof S, cudaMemcpyHostToDevice));
   h->PC.time = time;
+  for (int i = 0; i < 3; i++) { if (CountCrystal) h->PC.baseCrystal[i] = CountCrystal[i]; if (CountCov) h->PC.baseCov[i] = CountCov[i]; }
   return 0;
 }
 
@@ -413,7 +441,7 @@ extern "C" int mskc_get_counters(mskc_ctx *h, mskc_counters *c) {
   c->num_atoms = S.NumAtoms; c->num_voids = S.NumVoids; c->num_adatom = S.NumAdAtom;
   for (int i = 0; i < 3; i++) { c->CountCrystal[i] = S.CountCrystal[i]; c->CountCov[i] = S.CountCov[i]; }
   c->iter = S.Iter; c->time = S.Time;
-  if (h->PC.ran) parallel_fill_counters(h->PC, c);
+  if (h->PC.ran || h->PC.replayed) parallel_fill_counters(h->PC, c);
   return 0;
 }
 
@@ -579,5 +607,85 @@ extern "C" int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, 
   if (ntiles) *ntiles = h->PC.ntiles;
   int64_t n = h->PC.ntiles < max_tiles ? h->PC.ntiles : max_tiles;
   if (out && n > 0) CK(cudaMemcpy(out, h->PC.tstat, (size_t)n * sizeof(TileStat), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---- test/diagnostic entry points of the cooperative transition code --------------------------------------
+extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xyz, const int32_t *event, const int32_t *arm, double tree_root) {
+  if (!h || !site_xyz || !event || !arm) return set_err(h, "mskc_replay_events: NULL argument");
+  if (!h->parallel_ready || !h->have_rates || h->PC.lists_stale) return set_err(h, "mskc_replay_events: rates and a parallel state must be set first");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(h->device));
+  if (upload_consts(h)) return -1;
+  int32_t *d_s = nullptr, *d_e = nullptr, *d_a = nullptr; TileStat *d_out = nullptr; TileStat out{};
+  CK(cudaMalloc(&d_s, (size_t)n * 12)); CK(cudaMalloc(&d_e, (size_t)n * 4)); CK(cudaMalloc(&d_a, (size_t)n * 4)); CK(cudaMalloc(&d_out, sizeof(TileStat)));
+  CK(cudaMemcpyAsync(d_s, site_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_e, event, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_a, arm, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d_out, 0, sizeof(TileStat), h->stream));
+  const int64_t chunk = 1000;                    // tombstones are dropped between chunks (no tile is ever "running" here)
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    const int64_t m = n - i0 < chunk ? n - i0 : chunk;
+    compact_lists_kernel<<<(h->PC.ntiles * 32 + 127) / 128, 128, 0, h->stream>>>(h->PC.ntiles);
+    replay_kernel<<<1, 32, 0, h->stream>>>(d_s + 3 * i0, d_e + i0, d_a + i0, (long long)m, tree_root, d_out);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_s); cudaFree(d_e); cudaFree(d_a); cudaFree(d_out);
+  ParallelCtx &P = h->PC;
+  P.replayed = true;
+  P.h_tot.events += out.events; P.h_tot.site_updates += out.site_updates; P.h_tot.dAtoms += out.dAtoms; P.h_tot.dVoids += out.dVoids;
+  for (int i = 0; i < 3; i++) { P.h_tot.dCrystal[i] += out.dCrystal[i]; P.h_tot.dCov[i] += out.dCov[i]; }
+  if (check_dev_err(h)) return -1;
+  if (out.events != n) return set_err(h, "mskc_replay_events: stopped after %lld of %lld events", (long long)out.events, (long long)n);
+  return 0;
+}
+
+extern "C" int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int32_t *event, double *rate, int64_t *n) {
+  if (!h || !n) return set_err(h, "mskc_download_active: NULL argument");
+  if (!h->parallel_ready) return set_err(h, "mskc_download_active: no parallel state");
+  CK(cudaSetDevice(h->device));
+  ParallelCtx &P = h->PC; DevCtx &D = h->D;
+  std::vector<double> R((size_t)P.ntiles * P.cap); std::vector<unsigned long long> CE(R.size()); std::vector<int> cnt(P.ntiles);
+  CK(cudaMemcpy(R.data(), P.rate, R.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(CE.data(), P.ce, CE.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cnt.data(), P.cnt, cnt.size() * 4, cudaMemcpyDeviceToHost));
+  long long plane = (long long)D.LX * D.LY; int64_t k = 0;
+  for (int l = 0; l < P.ntiles; l++)
+    for (int i = 0; i < cnt[l]; i++) {
+      size_t a = (size_t)l * P.cap + i;
+      if (!(R[a] > 0.0)) continue;
+      if (k < cap) {
+        uint32_t c = (uint32_t)CE[a];
+        if (xyz) { int32_t z = (int32_t)(c / plane); long long r = c - (long long)z * plane; xyz[3 * k + 2] = z; xyz[3 * k + 1] = (int32_t)(r / D.LX); xyz[3 * k] = (int32_t)(r % D.LX); }
+        if (event) event[k] = (int32_t)(CE[a] >> 32);
+        if (rate) rate[k] = R[a];
+      }
+      k++;
+    }
+  *n = k;
+  return 0;
+}
+
+extern "C" int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, int32_t *nn) {
+  if (!h || !xyz || !nn) return set_err(h, "mskc_download_bonds: NULL argument");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  std::vector<uint32_t> cells((size_t)n); std::vector<uint64_t> b((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    const int32_t *p = xyz + 3 * i;
+    if (p[0] < 0 || p[0] >= D.LX || p[1] < 0 || p[1] >= D.LY || p[2] < 0 || p[2] > D.LZ) return set_err(h, "mskc_download_bonds: site outside the box");
+    cells[i] = (uint32_t)((long long)p[0] + (long long)D.LX * ((long long)p[1] + (long long)D.LY * (long long)p[2]));
+  }
+  uint32_t *d_c = nullptr; unsigned long long *d_b = nullptr;
+  CK(cudaMalloc(&d_c, (size_t)n * 4)); CK(cudaMalloc(&d_b, (size_t)n * 8));
+  CK(cudaMemcpyAsync(d_c, cells.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  gather_bonds<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(D.bonds, d_c, d_b, (long long)n);
+  CK(cudaMemcpyAsync(b.data(), d_b, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_c); cudaFree(d_b);
+  for (int64_t i = 0; i < n; i++) h_dec_bonds(D, xyz + 3 * i, b[i], nn + 12 * i);
   return 0;
 }

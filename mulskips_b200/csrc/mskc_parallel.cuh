@@ -7,12 +7,13 @@
 // run concurrently, one warp per tile, each doing its own n-fold way for a time quantum tau.
 //
 // HBM layout added to state[]/bonds[] (mskc_device.cuh):
-//   rate[slot][list] f64, ce[slot][list] u64 {u32 cell, u32 event}: the per-tile active-site lists, slot-major
+//   rate[list][slot] f64, ce[list][slot] u64 {u32 cell, u32 event}: the per-tile active-site lists, tile-major
 //   cnt[tile]           i32  slots in use (tombstones with rate 0 included until the owner compacts)
 //   slot[cell]          u16  1-based slot of the cell in its tile's list, 0 = not listed
 //   tstat[tile]         per-tile counters (events, site updates, per-class counts), summed on demand
 #pragma once
 #include "mskc_device.cuh"
+#include "mskc_coop.cuh"
 #include "../../include/mskc.h"
 #include <algorithm>
 #include <cstdlib>
@@ -37,30 +38,30 @@ struct SweepState {          // one per context, device resident
   long long max_cnt;
 };
 
-// Per-tile active lists, slot-major ("SoA over tiles"): entry k of list l lives at [k*NT + l], and the
-// lists of one colour are contiguous (l = colour*ntc + index), so the 32 lanes of a warp -- 32 tiles of
-// the running colour -- read 32 consecutive words when they scan slot k together.
+// Per-tile active lists, tile-major: entry k of list l lives at [l*cap + k]; the warp that owns tile l
+// streams its list into shared memory with coalesced loads at the start of its colour step.  Lists of one
+// colour are contiguous (l = colour*ntc + index).
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
-  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr, *ntomb = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
+  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
   long long ncell = 0;
   long long base_atoms = 0, base_voids = 0;
   int baseCrystal[3] = {0, 0, 0}, baseCov[3] = {0, 0, 0};
   TileStat h_tot{}; SweepState h_ss{};
   double time = 0.0;
-  bool ran = false, lists_stale = false, listed_flag_in_state = false;
+  bool ran = false, replayed = false, lists_stale = false, listed_flag_in_state = false;
 };
 
 struct TileView {            // what the kernels need (constant memory)
   int tile, ntx, nty, cap, NT, hx, ntc;
-  double *rate; unsigned long long *ce; int *cnt, *ntomb; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
+  double *rate; unsigned long long *ce; int *cnt; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no per-tile generator state in memory ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x, hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -75,181 +76,217 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {       // uniform
 
 __constant__ TileView V;      // the current context's tile lists (uploaded with the DevCtx)
 
+enum { TILE = 24 };           // tile edge in super-lattice units (2 cubic cells)
 __device__ __forceinline__ int list_of(P3 s) {          // list id of the tile that owns site s
-  int tx = s.x / V.tile, ty = s.y / V.tile;
+  int tx = s.x / TILE, ty = s.y / TILE;
   return (((ty & 1) << 1) | (tx & 1)) * V.ntc + (ty >> 1) * V.hx + (tx >> 1);
 }
 
-struct TilePol {
-  uint2 key; uint32_t tile_id; uint32_t step_lo, step_hi; uint32_t draw;
-  double root;
-  long long n_getprob;
-  int CountCrystal[3], CountCov[3];
-  int dAtoms, dVoids;
+// list entry k of tile-list l (tile-major: the owning warp streams its own list with coalesced loads)
+__device__ __forceinline__ long long lidx(int l, int k) { return (long long)l * V.cap + k; }
 
-  __device__ __forceinline__ bool predraw() const { return false; }
-  __device__ __forceinline__ double tree_root() const { return root; }
-  __device__ __forceinline__ uint4 next4() { return philox4x32_10(make_uint4(tile_id, step_lo, step_hi, draw++), key); }
-  __device__ __forceinline__ double uniform() { uint4 r = next4(); return u53(r.x, r.y); }
-
-  __device__ __noinline__ void put(P3 s, long long c, int ev, double p) {
-    int l = list_of(s);
+// List bookkeeping of the cooperative sampler.  The running tile's own list is mirrored in shared memory
+// for the whole colour step (scans and updates never leave the SM) and written back once at the end;
+// entries of cells that belong to other (not running) tiles go straight to those tiles' lists in HBM,
+// slots claimed with atomics because two running tiles can border the same idle tile.
+struct TileLists {
+  int own;                                   // list id of the running tile (-1: none, everything is "foreign")
+  double *s_rate; unsigned long long *s_ce; int *s_n;
+  __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p) {
+    const int l = list_of(s);
     int sl = V.slot[c];
-    if (sl == 0) {
-      int k = atomicAdd(&V.cnt[l], 1);
-      if (k >= V.cap) { atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
-      V.slot[c] = (uint16_t)(k + 1);
-      sl = k + 1;
-    } else if (V.rate[(long long)(sl - 1) * V.NT + l] == 0.0) atomicSub(&V.ntomb[l], 1);       // a tombstone comes back to life
-    long long a = (long long)(sl - 1) * V.NT + l;
-    V.rate[a] = p;
-    V.ce[a] = (unsigned long long)(uint32_t)c | ((unsigned long long)(uint32_t)ev << 32);
-  }
-  __device__ __forceinline__ void add_mc(P3 s, long long c, const P3 nn[4], int ev, double p) {
-    if (p == 0) { fail(E_ADD_ZERO, s.x, s.y, s.z); return; }
-    D.bonds[c] = enc_bonds(s, nn);
-    put(s, c, ev, p);
-  }
-  __device__ __forceinline__ void set_rate(P3 s, long long c, int ev, double p) { put(s, c, ev, p); }
-  __device__ __noinline__ void erase_mc(P3 s, long long c) {
-    int sl = V.slot[c];
-    if (sl) {
-      int l = list_of(s);
-      long long a = (long long)(sl - 1) * V.NT + l;
-      if (V.rate[a] != 0.0) { V.rate[a] = 0.0; atomicAdd(&V.ntomb[l], 1); }     // tombstone; the owner compacts
+    const unsigned long long e = (unsigned long long)c | ((unsigned long long)(uint32_t)ev << 32);
+    if (l == own) {
+      if (sl == 0) {
+        int k = atomicAdd(s_n, 1);
+        if (k >= V.cap) { atomicSub(s_n, 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
+        V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
+      }
+      s_rate[sl - 1] = p; s_ce[sl - 1] = e;
+    } else {
+      if (sl == 0) {
+        int k = atomicAdd(&V.cnt[l], 1);
+        if (k >= V.cap) { atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
+        V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
+      }
+      const long long a = lidx(l, sl - 1);
+      V.rate[a] = p; V.ce[a] = e;
     }
-    D.bonds[c] = 0ull;
   }
-  __device__ __forceinline__ void add_void(P3 s, long long c, const P3 nn[4]) { dVoids++; D.bonds[c] = enc_bonds(s, nn); }
-  __device__ __forceinline__ void erase_void(P3 s, long long c) { dVoids--; D.bonds[c] = 0ull; }
-  __device__ __forceinline__ void add_bulk(P3 s, long long c, const P3 nn[4]) { dAtoms++; D.bonds[c] = enc_bonds(s, nn); }
-  __device__ __forceinline__ void erase_bulk(P3 s, long long c) { dAtoms--; D.bonds[c] = 0ull; }
-  // Coverage on a 4-coordinated empty site: the reference's lookup lands on an unrelated record
-  // (see ParityPol::cov_void_recipr), i.e. such a neighbour is effectively never counted.
-  __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
+  __device__ __forceinline__ void erase(P3 s, uint32_t c) {          // tombstone (rate 0); the owner compacts
+    const int sl = V.slot[c];
+    if (!sl) return;
+    const int l = list_of(s);
+    if (l == own) s_rate[sl - 1] = 0.0; else V.rate[lidx(l, sl - 1)] = 0.0;
+  }
 };
 
-// One colour step: every tile of colour `colour` advances by tau.
-// A TEAM of lanes (1..32, power of two) owns one tile, 32/TEAM tiles share a warp.  The team leader runs
-// the transition function (a serial dependency chain); the whole team shares (a) the rate sum / pick scan
-// over the tile's list and (b) the re-rate requests the event queued (one Get_Prob per lane).  Lists are
-// slot-major, so the leaders' / teams' scans are coalesced across the tiles of a warp.
-template <int TEAM>
-__global__ void __launch_bounds__(32) colour_step_kernel(int colour, uint2 key, int max_events_per_tile, int dbg_lid) {
-  constexpr int TPW = 32 / TEAM;
-  __shared__ RQ sq[TPW];
-  const int lane = threadIdx.x, team = lane / TEAM, tl = lane % TEAM;
-  const unsigned tmask = (TEAM == 32) ? 0xFFFFFFFFu : (((1u << TEAM) - 1u) << (team * TEAM));
-  const int leader = team * TEAM;
-  const int wid = blockIdx.x * TPW + team;
+enum { CS_WARPS = 4 };                        // tiles (warps) per CTA of the colour-step kernel
+enum { CS_COMPACT_ABOVE = 96 };               // tombstones are dropped when a list is loaded with more entries than this
+
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += t; }
+  return v;
+}
+
+// One colour step: every tile of colour `colour` advances by tau; one warp per tile (mskc_coop.cuh).
+__global__ void __launch_bounds__(32 * CS_WARPS) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int wid = blockIdx.x * CS_WARPS + wib;
   if (wid >= V.ntc) return;
+  const int cap = V.cap;
+  double *s_rate = reinterpret_cast<double *>(smem) + (size_t)wib * cap;
+  unsigned long long *s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)CS_WARPS * cap * 8) + (size_t)wib * cap;
+  int *s_n = reinterpret_cast<int *>(smem + (size_t)CS_WARPS * cap * 16) + wib;
   const int l = colour * V.ntc + wid;
-  const long long NT = V.NT;
   const SweepState ss = *V.ss;
-  const double tau = ss.tau;
-  double *rate = V.rate + l; unsigned long long *ce = V.ce + l;
-  RQ &q = sq[team];
-  if (tl == 0) {
-    int n = V.cnt[l];
-    if (V.ntomb[l] > 0) {               // compaction: drop tombstones (swap with last), keep slot[] consistent
-      int i = 0;
-      while (i < n) {
-        if (rate[i * NT] == 0.0) {
-          V.slot[(uint32_t)ce[i * NT]] = 0;
-          n--;
-          if (i < n) { double r = rate[n * NT]; unsigned long long e = ce[n * NT]; rate[i * NT] = r; ce[i * NT] = e; if (r != 0.0) V.slot[(uint32_t)e] = (uint16_t)(i + 1); }
-        } else i++;
+  const double tau = ss.tau, root = ss.tree_root;
+  // ---- load the tile's list (dropping tombstones when it has grown) ------------------------------------
+  {
+    const int n0 = V.cnt[l];
+    const bool compact = n0 > CS_COMPACT_ABOVE;
+    int n = 0;
+#pragma unroll 1
+    for (int base = 0; base < n0; base += 32) {
+      const int i = base + lane;
+      double r = 0.0; unsigned long long e = 0ull;
+      if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
+      if (!compact) { if (i < n0) { s_rate[i] = r; s_ce[i] = e; } }
+      else {
+        const bool live = (i < n0) && (r > 0.0);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+        const int k = n + __popc(m & ((1u << lane) - 1u));
+        if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
+        else if (i < n0) V.slot[(uint32_t)e] = 0;
+        n += __popc(m);
       }
-      V.cnt[l] = n; V.ntomb[l] = 0;
     }
-    q.n = 0;
+    if (!compact) n = n0;
+    if (lane == 0) *s_n = n;
   }
-  __syncwarp(tmask);
-  TilePol pol;
-  pol.key = key; pol.tile_id = (uint32_t)l; pol.step_lo = (uint32_t)ss.step; pol.step_hi = (uint32_t)(ss.step >> 32); pol.draw = 0;
-  pol.root = ss.tree_root; pol.n_getprob = 0; pol.dAtoms = 0; pol.dVoids = 0;
-  for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = 0; pol.CountCov[i] = 0; }
-  int nev = 0, ndep[3] = {0, 0, 0}, nevap = 0, nabs = 0, ndes = 0;
+  __syncwarp();
+  TileLists L; L.own = l; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
+  CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
+  for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
+  int nev = 0, ndep0 = 0, ndep1 = 0, ndep2 = 0, nevap = 0, nabs = 0, ndes = 0;
+  uint32_t draw = 0;
   double tloc = 0.0, R = 0.0;
   while (true) {
-    const int n = V.cnt[l];
-    // team-parallel rate sum (strided over the slots), inclusive prefix over the team
+    const int n = *s_n;
+    // rate sum and inclusive prefix over the list (lane-strided chunks of 32)
     double part = 0.0;
-    for (int i = tl; i < n; i += TEAM) part += rate[i * NT];
-    double incl = part;
-#pragma unroll
-    for (int o = 1; o < TEAM; o <<= 1) { double v = __shfl_up_sync(tmask, incl, o, TEAM); if (tl >= o) incl += v; }
-    R = __shfl_sync(tmask, incl, leader + TEAM - 1);
-    int stop = 0;
-    if (tl == 0) stop = (nev >= max_events_per_tile) || (D.err[0] != 0);
-    stop = __shfl_sync(tmask, stop, leader);
-    if (stop || !(R > 0.0)) break;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    if (tl == 0) rnd = pol.next4();
-    rnd.x = __shfl_sync(tmask, rnd.x, leader); rnd.y = __shfl_sync(tmask, rnd.y, leader);
-    rnd.z = __shfl_sync(tmask, rnd.z, leader); rnd.w = __shfl_sync(tmask, rnd.w, leader);
-    tloc += -log(u53(rnd.x, rnd.y)) / R;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) part += s_rate[i];
+    const double incl = warp_incl_scan(part, lane);
+    R = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (!(R > 0.0) || nev >= max_events_per_tile) break;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
+    tloc += (double)(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f)) / R;
     if (tloc > tau) break;
     const double target = u53(rnd.z, rnd.w) * R;
-    unsigned m = __ballot_sync(tmask, incl > target) & tmask;
-    int sel = m ? (__ffs(m) - 1) : (leader + TEAM - 1);
-    double before = __shfl_sync(tmask, incl - part, sel);
+    // the lane whose chunk contains the target, then the entry inside that lane's strided chunk
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, incl > target);
+    const int sel = m ? (__ffs(m) - 1) : 31;
     int pick = -1;
     if (lane == sel) {
-      double acc = before; int last = -1;
-      for (int i = tl; i < n; i += TEAM) { double r = rate[i * NT]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
+      double acc = incl - part; int last = -1;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) { const double r = s_rate[i]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
       if (pick < 0) pick = last;
     }
-    pick = __shfl_sync(tmask, pick, sel);
-    if (pick < 0) {            // rounding left the chosen lane without a live entry: take any live one
+    pick = __shfl_sync(0xFFFFFFFFu, pick, sel);
+    if (pick < 0) {                  // rounding left the chosen lane without a live entry: take the first live one
       int mine = -1;
-      for (int i = tl; i < n; i += TEAM) if (rate[i * NT] > 0.0) { mine = i; break; }
-      unsigned mm = __ballot_sync(tmask, mine >= 0) & tmask;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) if (s_rate[i] > 0.0) { mine = i; break; }
+      const unsigned mm = __ballot_sync(0xFFFFFFFFu, mine >= 0);
       if (!mm) break;
-      pick = __shfl_sync(tmask, mine, __ffs(mm) - 1);
+      pick = __shfl_sync(0xFFFFFFFFu, mine, __ffs(mm) - 1);
     }
-    if (tl == 0) {
-      unsigned long long e = ce[pick * NT];
-      uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
-      P3 Site = cell_xyz((long long)cell);
-      if (Itrans == EV_DRAW) {                       // species / adsorbate drawn now (Get_Prob.f:164-179)
-        uint32_t w = D.state[cell];
-        int T = D.la ? site_T(w, Site) : 0;
-        Itrans = choose_dep_abs(w_coor(w), T, pol.uniform(), nullptr);
+    const unsigned long long e = s_ce[pick];
+    const uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
+    const P3 Site = cell_xyz((long long)cell);
+    double arm_u = 0.5;
+    {
+      // second counter-based draw: species / adsorbate (Get_Prob.f:164-179) and the IF_Arm_Choice.f tie
+      const uint4 r2 = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
+      arm_u = u53(r2.z, r2.w);
+      if (Itrans == EV_DRAW) {
+        const uint32_t w = D.state[cell];
+        Itrans = choose_dep_abs(w_coor(w), D.la ? site_T(w, Site) : 0, u53(r2.x, r2.y), nullptr);
       }
-      if (Itrans >= 1 && Itrans <= 3) ndep[Itrans - 1]++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-      if (l == dbg_lid) printf("DBG step %lld ev#%d site %d %d %d Itrans %d w=%08x rate=%g R=%g tloc=%g tau=%g n=%d\n", ss.step, nev, Site.x, Site.y, Site.z, Itrans, D.state[cell], rate[pick * NT], R, tloc, tau, n);
-      apply_event_q(pol, q, Site, Itrans);
-      nev++;
     }
-    __syncwarp(tmask);
-    // the queued re-rate requests: one Get_Prob per lane, then the list updates (any order: slots are
-    // claimed with atomics and every request concerns a different cell)
-    const int nq = q.n;
-    for (int k0 = 0; k0 < nq; k0 += TEAM) {
-      const int k = k0 + tl;
-      int ev = 0; double p = 0.0;
-      if (k < nq && q.it[k].act != A_ERASE) { RQItem &it = q.it[k]; get_prob(pol, it.Occ, it.NSiC, it.Cov, it.Coor, it.N, it.nn, ev, p); }
-      __syncwarp(tmask);
-      if (k < nq) rq_commit(pol, q.it[k], ev, p);
-      __syncwarp(tmask);
-    }
-    if (tl == 0) q.n = 0;
-    __syncwarp(tmask);
+    if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
+    coop_event(L, lane, Site, cell, Itrans, root, arm_u, -1, K);
+    nev++;
   }
-  // team totals -> leader
-  long long ngp = pol.n_getprob; int dA = pol.dAtoms, dV = pol.dVoids;
+  // ---- write the list back, reduce the counters -----------------------------------------------------------
+  __syncwarp();
+  const int n = *s_n;
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
+  int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
 #pragma unroll
-  for (int o = TEAM / 2; o > 0; o >>= 1) {
-    ngp += __shfl_down_sync(tmask, ngp, o, TEAM); dA += __shfl_down_sync(tmask, dA, o, TEAM); dV += __shfl_down_sync(tmask, dV, o, TEAM);
-  }
-  if (tl == 0) {
+  for (int k = 0; k < 9; k++) v[k] = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+  if (lane == 0) {
+    V.cnt[l] = n;
     V.tile_rate[l] = R;
     TileStat &st = V.tstat[l];
-    st.events += nev; st.site_updates += ngp;
-    for (int i = 0; i < 3; i++) { st.dep[i] += ndep[i]; st.dCrystal[i] += pol.CountCrystal[i]; st.dCov[i] += pol.CountCov[i]; }
-    st.evap += nevap; st.abs_ += nabs; st.des += ndes; st.dAtoms += dA; st.dVoids += dV;
+    st.events += nev; st.site_updates += v[0];
+    st.dep[0] += ndep0; st.dep[1] += ndep1; st.dep[2] += ndep2; st.evap += nevap; st.abs_ += nabs; st.des += ndes;
+    st.dAtoms += v[1]; st.dVoids += v[2];
+    for (int i = 0; i < 3; i++) { st.dCrystal[i] += v[3 + i]; st.dCov[i] += v[6 + i]; }
     if (nev > st.maxev) st.maxev = nev;
+  }
+}
+
+// Drop the tombstones of every list (one warp per tile) -- the same compaction the colour-step kernel does
+// when it loads a long list; used between replay chunks, where no tile is ever "running".
+__global__ void __launch_bounds__(128) compact_lists_kernel(int ntiles) {
+  const int lane = threadIdx.x & 31, l = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (l >= ntiles) return;
+  const int n0 = V.cnt[l];
+  int n = 0;
+  for (int base = 0; base < n0; base += 32) {       // in place: entry k <= i is written after entry i was read by this warp
+    const int i = base + lane;
+    double r = 0.0; unsigned long long e = 0ull;
+    if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
+    const bool live = (i < n0) && (r > 0.0);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    const int k = n + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (live) { V.rate[lidx(l, k)] = r; V.ce[lidx(l, k)] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
+    else if (i < n0) V.slot[(uint32_t)e] = 0;
+    n += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) V.cnt[l] = n;
+}
+
+// Trace replay (test/diagnostic entry point): ONE warp applies a given event sequence -- site, event code
+// and the IF_Arm_Choice outcome of every event, as the CPU oracle traced them -- through the same
+// cooperative transition code the sampler uses.  Lists are updated in HBM only.
+__global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, const int32_t *ev_code, const int32_t *ev_arm, long long n, double root, TileStat *out) {
+  const int lane = threadIdx.x;
+  TileLists L; L.own = -1; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
+  CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
+  for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
+  long long done = 0;
+  for (long long i = 0; i < n; i++) {
+    P3 S; S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2];
+    const int arm = ev_arm[i];
+    coop_event(L, lane, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    done++;
+    if (D.err[0] != 0) break;
+  }
+  int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
+#pragma unroll
+  for (int k = 0; k < 9; k++) v[k] = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+  if (lane == 0) {
+    out->events += done; out->site_updates += v[0]; out->dAtoms += v[1]; out->dVoids += v[2];
+    for (int i = 0; i < 3; i++) { out->dCrystal[i] += v[3 + i]; out->dCov[i] += v[6 + i]; }
   }
 }
 
@@ -276,7 +313,7 @@ __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= ntiles) return;
   int n = V.cnt[l]; double r = 0;
-  for (int i = 0; i < n; i++) r += V.rate[(long long)i * V.NT + l];
+  for (int i = 0; i < n; i++) r += V.rate[lidx(l, i)];
   V.tile_rate[l] = r;
 }
 
@@ -304,29 +341,21 @@ __global__ void __launch_bounds__(256) reduce_tstat_kernel(const TileStat *ts, i
 }
 
 // ---- the dense "rate kernel": recompute (event class, rate) of every listed site from the lattice ----
-struct RatePol {             // Get_Prob without any bookkeeping side effects
-  double root; long long n_getprob; int CountCrystal[3], CountCov[3];
-  __device__ __forceinline__ bool predraw() const { return false; }
-  __device__ __forceinline__ double tree_root() const { return root; }
-  __device__ __forceinline__ double uniform() { return 0.5; }
-  __device__ __forceinline__ bool cov_void_recipr(P3, long long, P3) const { return false; }
-};
 __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long long *n_sites) {
   long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)ntiles * V.cap;
-  RatePol pol; pol.root = V.ss->tree_root; pol.n_getprob = 0;
+  const double root = V.ss->tree_root;
   unsigned long long mine = 0;
   for (long long k = gid; k < total; k += (long long)gridDim.x * blockDim.x) {
-    int i = (int)(k / ntiles), l = (int)(k - (long long)i * ntiles);
+    int l = (int)(k / V.cap), i = (int)(k - (long long)l * V.cap);
     if (i >= V.cnt[l]) continue;
     double r = V.rate[k];
     if (!(r > 0.0)) continue;
     uint32_t cell = (uint32_t)V.ce[k];
     P3 s = cell_xyz((long long)cell);
     uint32_t w = D.state[cell];
-    P3 nn[4]; dec_bonds(s, D.bonds[cell], nn);
     int ev = 0; double p = 0;
-    get_prob(pol, w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, nn, ev, p);
+    coop_rate(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, D.bonds[cell], root, ev, p);
     if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = (unsigned long long)cell | ((unsigned long long)(uint32_t)ev << 32); mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
@@ -433,7 +462,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[(long long)k * V.NT + t] = p; V.ce[(long long)k * V.NT + t] = (unsigned long long)(uint32_t)c | (4ull << 32); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = (unsigned long long)(uint32_t)c | (4ull << 32); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       } else {
         D.state[c] = (2u << PosCoor);
@@ -442,7 +471,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[(long long)k * V.NT + t] = p; V.ce[(long long)k * V.NT + t] = (unsigned long long)(uint32_t)c | ((unsigned long long)EV_DRAW << 32); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = (unsigned long long)(uint32_t)c | ((unsigned long long)EV_DRAW << 32); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       }
     }
@@ -453,12 +482,12 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
 #define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (err) *err = std::string("CUDA error ") + cudaGetErrorString(e_) + " in " #call; return -1; } } while (0)
 
 static inline void parallel_free(ParallelCtx &P) {
-  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.ntomb); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
+  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
-  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.ntomb = P.ntomb; V.slot = P.slot;
+  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.slot = P.slot;
   V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; return V;
 }
 static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int cap, std::string *err) {
@@ -466,7 +495,6 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   if (H.LX % (2 * tile) || H.LY % (2 * tile)) { if (err) *err = "parallel sampler needs LenX and LenY to be multiples of 48 (24-unit tiles, 2x2 colouring)"; return -1; }
   if (P.rate && P.cap == cap && P.ncell == H.ncell) {
     PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
-    PCK(cudaMemsetAsync(P.ntomb, 0, (size_t)P.ntiles * sizeof(int), st));
     PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
     PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
@@ -479,7 +507,6 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMalloc(&P.rate, (size_t)P.ntiles * cap * sizeof(double)));
   PCK(cudaMalloc(&P.ce, (size_t)P.ntiles * cap * sizeof(unsigned long long)));
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
-  PCK(cudaMalloc(&P.ntomb, (size_t)P.ntiles * sizeof(int)));
   PCK(cudaMalloc(&P.slot, (size_t)H.ncell * sizeof(uint16_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
@@ -488,7 +515,6 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ce, 0, (size_t)P.ntiles * cap * sizeof(unsigned long long), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
-  PCK(cudaMemsetAsync(P.ntomb, 0, (size_t)P.ntiles * sizeof(int), st));
   PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
@@ -517,7 +543,7 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
     int ev = mc_ev[i];
     bool forced = ev == 1 && (mc_rate[i] == (double)1.e-8f || mc_rate[i] == (double)1.e-6f);
     uint32_t e = (ev == 4 || ev == 5 || forced) ? (uint32_t)ev : (uint32_t)EV_DRAW;
-    size_t a = (size_t)cnt[t] * P.ntiles + t;
+    size_t a = (size_t)t * P.cap + cnt[t];
     R[a] = mc_rate[i]; CE[a] = (unsigned long long)c | ((unsigned long long)e << 32);
     slot[c] = (uint16_t)(++cnt[t]);
   }
@@ -526,7 +552,7 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
   PCK(cudaMemcpyAsync(P.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(P.slot, slot.data(), slot.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
   PCK(cudaStreamSynchronize(st));
-  P.base_atoms = n_bulk; P.base_voids = n_void; P.time = 0; P.ran = false; P.lists_stale = false;
+  P.base_atoms = n_bulk; P.base_voids = n_void; P.time = 0; P.ran = false; P.replayed = false; P.lists_stale = false;
   for (int i = 0; i < 3; i++) { P.baseCrystal[i] = 0; P.baseCov[i] = 0; }
   memset(&P.h_tot, 0, sizeof P.h_tot);
   return 0;
@@ -555,11 +581,8 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
 static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
-  int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
-  if (teamsz != 1 && teamsz != 2 && teamsz != 4 && teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
-  const int tpw = 32 / teamsz;
-  const int blocks = (ntc + tpw - 1) / tpw;
-  int dbg_lid = -1; if (const char *e = getenv("MSKC_DBG_LID")) dbg_lid = atoi(e);
+  const int blocks = (ntc + CS_WARPS - 1) / CS_WARPS;
+  const size_t smem = (size_t)CS_WARPS * P.cap * 16 + CS_WARPS * sizeof(int);
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
@@ -581,14 +604,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      switch (teamsz) {
-        case 1: colour_step_kernel<1><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-        case 2: colour_step_kernel<2><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-        case 4: colour_step_kernel<4><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-        case 8: colour_step_kernel<8><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-        case 16: colour_step_kernel<16><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-        default: colour_step_kernel<32><<<blocks, 32, 0, st>>>(col, key, 1 << 20, dbg_lid); break;
-      }
+      colour_step_kernel<<<blocks, 32 * CS_WARPS, smem, st>>>(col, key, 1 << 14);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;

@@ -546,6 +546,7 @@ static void Deposition(Orc *o, int *IndVoid, int IAtom) {
       if (!eq3(cnn[i], Site)) { if (j < 3) cp3(SNSite[j], cnn[i]); else o->q_oob++; j++; }
     orc_find_sn(Site, SiteC, (const int (*)[3])SNSite, NNZig, NNArm, o->LenX, o->LenY);
     int IF_Arm = IF_Arm_Choice(o, NNZig, NNArm);
+    o->last_arm = 1 + IF_Arm;
     for (int i = 0; i < 3; i++) cp3(o->ListAdAtom[*IndVoid].nn[i + 1], IF_Arm ? NNArm[i] : NNZig[i]);
   }
   cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[*IndVoid].nn);
@@ -1349,8 +1350,10 @@ static int iterate_inner(Orc *o) {
       o->framecounter++;
     }
   }
+  OrcTrace *t = NULL;
+  o->last_arm = 0;
   if (o->trace && o->trace_n < o->trace_cap) {
-    OrcTrace *t = &o->trace[o->trace_n++];
+    t = &o->trace[o->trace_n++];
     t->iter = o->Iter; t->ind = Ind; cp3(t->site, o->ListAdAtom[Ind].xyz); t->itrans = Itrans; t->pad = 0; t->tree1 = o->Tree[1]; t->time = o->Time;
   }
   if (Itrans >= 0 && Itrans < 8) o->n_events[Itrans]++; else o->n_events[7]++;
@@ -1364,6 +1367,7 @@ static int iterate_inner(Orc *o) {
     Absorption(o, Ind, o->ListCov[k - 1]);
     o->CountCov[k - 1]++;
   }
+  if (t) t->pad = o->last_arm;
   o->Iter++;
   if (!strcmp(o->ExitStrategy, "Iter")) { if (o->Iter > o->MaxIter) { o->done = 1; return 1; } }
   else if (!strcmp(o->ExitStrategy, "Time")) { if (o->Time > o->MaxTime) { o->done = 1; return 1; } }

@@ -72,6 +72,7 @@ typedef struct Orc {
   char outdir[1024];
   OrcTrace *trace; int64_t trace_cap, trace_n;
   int last_site[3];
+  int last_arm;                        /* 0: last event made no IF_Arm_Choice, 1: it chose zig-zag, 2: arm-chair (goes to OrcTrace.pad) */
   int done;                            /* 1: loop exited after an event, 2: 'few MC particles' stop */
   int fatal; char errmsg[512]; jmp_buf jb; int jb_set;
   size_t scratch;                      /* index of the scratch cell used for out-of-bounds accesses */

@@ -190,6 +190,16 @@ class Oracle:
         return [(p[i].iter, p[i].ind, tuple(p[i].site), p[i].itrans, p[i].tree1, p[i].time) for i in range(n.value)]
 
 
+def trace_arrays(orc: Oracle):
+    """The oracle's event trace as numpy arrays: site [n,3], event code [n], arm decision [n] (0 none, 1 zig-zag, 2 arm-chair)."""
+    n = C.c_int64()
+    p = orc.lib.orc_get_trace(orc.o, C.byref(n))
+    dt = np.dtype([("iter", "<i8"), ("ind", "<i4"), ("site", "<i4", 3), ("itrans", "<i4"), ("arm", "<i4"), ("tree1", "<f8"), ("time", "<f8")])
+    assert dt.itemsize == C.sizeof(OrcTrace)
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value * dt.itemsize,)).view(dt).copy() if n.value else np.zeros(0, dt)
+    return a["site"].copy(), a["itrans"].copy(), a["arm"].copy(), a["tree1"].copy()
+
+
 def upload_oracle_state(orc: Oracle, ctx):
     """Hand the oracle's current state to a CUDA context: the tests' way of giving both sides the same input."""
     t = orc.tables()
