@@ -198,6 +198,13 @@ extern "C" int mskc_set_rates(mskc_ctx *h, const double *PtransE, const double *
   CK(cudaMemcpyAsync(h->d_PDes, h->h_PDes.data(), 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   h->D.PZig = PtransZig;
+  for (int coor = 1; coor <= 3; coor++) {            // same association as total_dep_abs(): (PD1+PD2+PD3) + (PAbs1+PAbs2+PAbs3)
+    const double *PD = h->h_PD.data(), *PA = h->h_PAbs.data();
+    double PDep = PD[0 + 3 * (coor - 1)] + PD[1 + 3 * (coor - 1)] + PD[2 + 3 * (coor - 1)];
+    double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += PA[(k - 1) + 3 * coor];
+    h->D.PDepAbs[coor] = PDep + PAbs;
+  }
+  h->D.PDepAbs[0] = 0.0;
   h->have_rates = true;
   return 0;
 }
@@ -659,7 +666,7 @@ extern "C" int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int3
       if (k < cap) {
         uint32_t c = (uint32_t)CE[a];
         if (xyz) { int32_t z = (int32_t)(c / plane); long long r = c - (long long)z * plane; xyz[3 * k + 2] = z; xyz[3 * k + 1] = (int32_t)(r / D.LX); xyz[3 * k] = (int32_t)(r % D.LX); }
-        if (event) event[k] = (int32_t)(CE[a] >> 32);
+        if (event) event[k] = (int32_t)ce_event(CE[a]);
         if (rate) rate[k] = R[a];
       }
       k++;

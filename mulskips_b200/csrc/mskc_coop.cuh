@@ -77,7 +77,7 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
     if (Coor >= 1 && Coor <= 3) {
       ev = EV_DRAW;
       if (Coor == 1 && w_coor(D.state[ccell(dec_bond(Q, fld(rb, 0)))]) < 2) { ev = 1; p = (double)1.e-8f; }   // Get_Prob.f:183
-      else p = total_dep_abs(Coor, T);
+      else p = D.la ? total_dep_abs(Coor, T) : D.PDepAbs[Coor];
     }
     return;
   }
@@ -166,14 +166,17 @@ struct CoopCounters {                // per-lane partial sums, reduced over the 
   int nsu, dAtoms, dVoids, dCrystal[3], dCov[3];
 };
 
-// ---- one event, executed by the whole warp -------------------------------------------------------------
+// ---- one event, executed by a TEAM of lanes (8, 16 or 32; a power of two) --------------------------------
+// tl = lane index inside the team, tmask = the team's lanes.  Several teams share a warp and run in lock step:
+// everything outside the event-kind specific branches is the same instruction stream for all of them.
 // Itrans: 1..3 deposit species, 4 evaporate, 5 desorb, 6.. adsorb (main.f:335-357).
 // arm_u: uniform used when IF_Arm_Choice.f ties; forced_arm >= 0 overrides the choice (trace replay).
-template <class Lists>
-__device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S, const uint32_t cS, const int Itrans, const double root,
+template <int TEAM, class Lists>
+__device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigned tmask, const P3 S, const uint32_t cS, const int Itrans, const double root,
                                            const double arm_u, const int forced_arm, CoopCounters &K) {
   enum { DEP = 0, EVAP = 1, DES = 2, ABS = 3 };
   const int kind = Itrans <= 3 ? DEP : (Itrans == 4 ? EVAP : (Itrans == 5 ? DES : ABS));
+  const int tshift = (int)(threadIdx.x & 31u) - tl;         // first lane of the team inside the warp
   uint32_t wS = D.state[cS];
   unsigned long long bS = D.bonds[cS];
   const int c0 = w_coor(wS);
@@ -189,13 +192,13 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
       CovNew = D.ListCov[k - 1]; dcv = k - 1;
       wS = (wS & ~255u) | (uint32_t)CovNew;
     }
-    if (lane == 4) {
+    if (tl == 4) {
       if (dsp >= 0 && dsp < 3) K.dCrystal[dsp] += sgn;
       if (dcv >= 0 && dcv < 3) K.dCov[dcv] += sgn;
       D.state[cS] = wS;
     }
   }
-  __syncwarp();                                            // S's new occupancy is visible before any lane looks back at it
+  __syncwarp(tmask);                                       // S's new occupancy is visible before any lane looks back at it
 
   if (kind == DEP && c0 == 1) {                          // deposition.f:49-74: fix bonds 2..4 (cubic or hexagonal continuation)
     const unsigned e = fld(bS, 0);
@@ -219,24 +222,28 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
     if (slow) slow_find_sn(S, C, g, zig, arm);
     // IF_Arm_Choice.f:38-54: lanes 0..2 read the arm-chair cells, 3..5 the zig-zag cells
     int cc = 0;
-    if (lane < 6) { const unsigned f = lane < 3 ? arm[lane % 3] : zig[lane % 3]; cc = w_coor(D.state[ccell(dec_bond(S, f))]); }
-    const unsigned mArm = 7u, mZig = 56u;
-    const int CoorArm = __reduce_add_sync(0xFFFFFFFFu, (mArm >> lane) & 1u ? cc : 0);
-    const int CoorZig = __reduce_add_sync(0xFFFFFFFFu, (mZig >> lane) & 1u ? cc : 0);
+    if (tl < 6) {
+      const int k = tl < 3 ? tl : tl - 3;
+      const unsigned fa = k == 0 ? arm[0] : (k == 1 ? arm[1] : arm[2]), fz = k == 0 ? zig[0] : (k == 1 ? zig[1] : zig[2]);
+      cc = w_coor(D.state[ccell(dec_bond(S, tl < 3 ? fa : fz))]);
+    }
+    const int CoorArm = __shfl_sync(tmask, cc, 0, TEAM) + __shfl_sync(tmask, cc, 1, TEAM) + __shfl_sync(tmask, cc, 2, TEAM);
+    const int CoorZig = __shfl_sync(tmask, cc, 3, TEAM) + __shfl_sync(tmask, cc, 4, TEAM) + __shfl_sync(tmask, cc, 5, TEAM);
     bool IF_Arm = CoorZig < CoorArm || (CoorZig == CoorArm && !(arm_u <= D.PZig));
     if (forced_arm >= 0) IF_Arm = forced_arm != 0;
     bS = (unsigned long long)e;
 #pragma unroll
     for (int i = 0; i < 3; i++) bS |= (unsigned long long)(IF_Arm ? arm[i] : zig[i]) << (16 * (i + 1));
-    if (lane == 4) D.bonds[cS] = bS;
+    if (tl == 4) D.bonds[cS] = bS;
   }
 
   // ---- phase A: lane i < 4 updates neighbour i ---------------------------------------------------
   int act = -1, qOcc = 0, qSp = 0, qCov = 0, qCoor = 0;
   P3 qN = S; uint32_t qc = cS; unsigned long long qrb = bS;
   bool sUp = false, sDown = false;                        // this neighbour raises / lowers S's own coordination
-  if (lane < 4 && !(kind == DES && c0 == 1 && lane > 0)) {  // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
-    const unsigned f = fld(bS, lane);
+  bool keepable = false;                                  // Evaporation.f:229-258: occupied, under-coordinated, reciprocal neighbour of S
+  if (tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
+    const unsigned f = fld(bS, tl);
     const P3 N = dec_bond(S, f);
     const uint32_t cN = ccell(N);
     const uint32_t wN = D.state[cN];
@@ -250,7 +257,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
     else if (kind == DEP) {
       if (wall) sUp = true;                                // deposition.f:231-232
       else if (Occ) {                                      // :191-229 full neighbour
-        if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && lane >= 1); }
+        if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && tl >= 1); }
       } else if (CoorNN == 0) {                            // :88-99 a new active empty site with one fixed bond
         bN = f ? (unsigned long long)((unsigned)NEGC - f) : (unsigned long long)enc_bond_cold(N, S);
         D.bonds[cN] = bN;
@@ -263,7 +270,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
       if (wall) sDown = true;                              // Evaporation.f:211-213
       else if (rec) {
         if (Occ) {                                         // :173-209; a bulk atom becomes active again
-          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_BULK2MC : A_SET;
+          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_BULK2MC : A_SET; keepable = true;
         } else if (CoorNN == 1) {                          // :62-79 orphaned empty site leaves the lattice
           wNew = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
           D.bonds[cN] = 0ull;
@@ -278,25 +285,29 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
     if (wNew != wN) D.state[cN] = wNew;
     qrb = bN;
   }
-  const int Coor = c0 + __popc(__ballot_sync(0xFFFFFFFFu, sUp)) - __popc(__ballot_sync(0xFFFFFFFFu, sDown));
-  __syncwarp();                                            // neighbours' words are final and visible to the whole warp
+  const int Coor = c0 + __popc(__ballot_sync(tmask, sUp)) - __popc(__ballot_sync(tmask, sDown));
+  const unsigned keepm = (__ballot_sync(tmask, keepable) >> tshift) & 15u;
+  __syncwarp(tmask);                                       // neighbours' words are final and visible to the whole team
   // ---- S's own request (lane 4) -----------------------------------------------------------------------
   uint32_t wS2 = wS;
-  if (lane == 4) {
+  if (tl == 4) {
     qCoor = Coor; qCov = CovNew; act = A_SET;
     if (kind <= EVAP) wS2 = MVBITS(wS, Coor, LenCoor, PosCoor);
     if (kind == DEP) { act = A_SETBULK; qOcc = 1; qSp = Itrans; }
     else if (kind == EVAP) {
       if (Coor == 0) act = A_ERASE;
-      else if (Coor == 1) D.bonds[cS] = coop_compact(S, bS);      // Evaporation.f:224-258, after the neighbours' words are final
+      else if (Coor == 1) {                                // Evaporation.f:224-258: keep the last qualifying neighbour only
+        if (!keepm) fail(E_STALE_NBUFF, S.x, S.y, S.z);
+        D.bonds[cS] = (unsigned long long)fld(bS, 31 - __clz((int)(keepm | 1u)));
+      }
     }
   }
   // ---- phase B: lanes 0..4 rate their site -----------------------------------------------------------
   int ev = 0; double p = 0.0;
   if (act >= 0 && act != A_ERASE) { coop_rate(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p); K.nsu++; }
-  __syncwarp();
+  __syncwarp(tmask);
   // S's coordination is written after its neighbours were rated (deposition.f:237-250)
-  if (lane == 4) {
+  if (tl == 4) {
     if (wS2 != wS) D.state[cS] = wS2;
     if (act == A_ERASE) D.bonds[cS] = 0ull;
   }
@@ -309,7 +320,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int lane, const P3 S,
     if (act == A_BULK2MC) K.dAtoms--;
     if (act == A_ERASE || ev == 0) L.erase(qN, qc); else L.put(qN, qc, ev, p);
   }
-  __syncwarp();
+  __syncwarp(tmask);
 }
 
 }  // namespace mskc

@@ -41,6 +41,7 @@ struct DevCtx {
   unsigned long long *bonds;
   const double *PE, *PD, *PAbs, *PDes;   // Fortran-flattened tables (defsystem.f:60-65)
   double PZig;
+  double PDepAbs[4];                // [coor]: sum of the deposition + adsorption rates of an empty site (Get_Prob.f:160-163), plain tables
   int NCrystal, NCov, ListCov[3], ListCrystal[3];
   // LA rate law: host-built tables per integer kelvin (Get_Prob.f:143-148)
   int la, keepT, la_tmin, la_tmax, la_nnz;

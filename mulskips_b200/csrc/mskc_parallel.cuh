@@ -61,7 +61,7 @@ struct TileView {            // what the kernels need (constant memory)
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no per-tile generator state in memory ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll 1
+#pragma unroll
   for (int r = 0; r < 10; r++) {
     uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x, hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -82,8 +82,16 @@ __device__ __forceinline__ int list_of(P3 s) {          // list id of the tile t
   return (((ty & 1) << 1) | (tx & 1)) * V.ntc + (ty >> 1) * V.hx + (tx >> 1);
 }
 
-// list entry k of tile-list l (tile-major: the owning warp streams its own list with coalesced loads)
+// list entry k of tile-list l (tile-major: the owning team streams its own list with coalesced loads)
 __device__ __forceinline__ long long lidx(int l, int k) { return (long long)l * V.cap + k; }
+
+// One list entry: bits 0-31 cell, 32-39 event class, 40-44 / 45-49 x / y inside the tile, 50-63 z -- the site's
+// coordinates come back without integer divisions when the entry fires.
+__host__ __device__ __forceinline__ unsigned long long pack_ce(uint32_t cell, int ev, int x, int y, int z) {
+  return (unsigned long long)cell | ((unsigned long long)(uint32_t)(ev & 255) << 32) | ((unsigned long long)(uint32_t)(x % TILE) << 40) |
+         ((unsigned long long)(uint32_t)(y % TILE) << 45) | ((unsigned long long)(uint32_t)z << 50);
+}
+__host__ __device__ __forceinline__ int ce_event(unsigned long long e) { return (int)((e >> 32) & 255u); }
 
 // List bookkeeping of the cooperative sampler.  The running tile's own list is mirrored in shared memory
 // for the whole colour step (scans and updates never leave the SM) and written back once at the end;
@@ -95,23 +103,15 @@ struct TileLists {
   __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p) {
     const int l = list_of(s);
     int sl = V.slot[c];
-    const unsigned long long e = (unsigned long long)c | ((unsigned long long)(uint32_t)ev << 32);
-    if (l == own) {
-      if (sl == 0) {
-        int k = atomicAdd(s_n, 1);
-        if (k >= V.cap) { atomicSub(s_n, 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
-        V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
-      }
-      s_rate[sl - 1] = p; s_ce[sl - 1] = e;
-    } else {
-      if (sl == 0) {
-        int k = atomicAdd(&V.cnt[l], 1);
-        if (k >= V.cap) { atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
-        V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
-      }
-      const long long a = lidx(l, sl - 1);
-      V.rate[a] = p; V.ce[a] = e;
+    const bool mine = l == own;
+    if (sl == 0) {
+      const int k = mine ? atomicAdd(s_n, 1) : atomicAdd(&V.cnt[l], 1);
+      if (k >= V.cap) { if (mine) atomicSub(s_n, 1); else atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
+      V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
     }
+    const unsigned long long e = pack_ce(c, ev, s.x, s.y, s.z);
+    if (mine) { s_rate[sl - 1] = p; s_ce[sl - 1] = e; }
+    else { const long long a = lidx(l, sl - 1); V.rate[a] = p; V.ce[a] = e; }
   }
   __device__ __forceinline__ void erase(P3 s, uint32_t c) {          // tombstone (rate 0); the owner compacts
     const int sl = V.slot[c];
@@ -121,26 +121,27 @@ struct TileLists {
   }
 };
 
-enum { CS_WARPS = 4 };                        // tiles (warps) per CTA of the colour-step kernel
+enum { CS_THREADS = 128 };                    // CTA size of the colour-step kernel (CS_THREADS / TEAM tiles per CTA)
 enum { CS_COMPACT_ABOVE = 96 };               // tombstones are dropped when a list is loaded with more entries than this
 
-__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += t; }
-  return v;
-}
-
-// One colour step: every tile of colour `colour` advances by tau; one warp per tile (mskc_coop.cuh).
-__global__ void __launch_bounds__(32 * CS_WARPS) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
+// One colour step: every tile of colour `colour` advances by tau.  A TEAM of lanes owns one tile
+// (mskc_coop.cuh); the 32/TEAM teams of a warp run their event loops in lock step.
+template <int TEAM>
+__global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
+  constexpr int TPB = CS_THREADS / TEAM;
   extern __shared__ __align__(16) unsigned char smem[];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int wid = blockIdx.x * CS_WARPS + wib;
+  const int lane = threadIdx.x & 31, tl = threadIdx.x % TEAM, tib = threadIdx.x / TEAM;
+  const int tshift = lane - tl;
+  const unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << TEAM) - 1u);
+  const unsigned tmask = tm << tshift;
+  const int wid = blockIdx.x * TPB + tib;
   if (wid >= V.ntc) return;
   const int cap = V.cap;
-  double *s_rate = reinterpret_cast<double *>(smem) + (size_t)wib * cap;
-  unsigned long long *s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)CS_WARPS * cap * 8) + (size_t)wib * cap;
-  int *s_n = reinterpret_cast<int *>(smem + (size_t)CS_WARPS * cap * 16) + wib;
+  double *s_rate = reinterpret_cast<double *>(smem) + (size_t)tib * cap;
+  unsigned long long *s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)TPB * cap * 8) + (size_t)tib * cap;
+  int *s_n = reinterpret_cast<int *>(smem + (size_t)TPB * cap * 16) + tib;
   const int l = colour * V.ntc + wid;
+  const int x0 = (2 * (wid % V.hx) + (colour & 1)) * TILE, y0 = (2 * (wid / V.hx) + (colour >> 1)) * TILE;   // tile origin (list_of inverted)
   const SweepState ss = *V.ss;
   const double tau = ss.tau, root = ss.tree_root;
   // ---- load the tile's list (dropping tombstones when it has grown) ------------------------------------
@@ -149,24 +150,24 @@ __global__ void __launch_bounds__(32 * CS_WARPS) colour_step_kernel(int colour, 
     const bool compact = n0 > CS_COMPACT_ABOVE;
     int n = 0;
 #pragma unroll 1
-    for (int base = 0; base < n0; base += 32) {
-      const int i = base + lane;
+    for (int base = 0; base < n0; base += TEAM) {
+      const int i = base + tl;
       double r = 0.0; unsigned long long e = 0ull;
       if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
       if (!compact) { if (i < n0) { s_rate[i] = r; s_ce[i] = e; } }
       else {
         const bool live = (i < n0) && (r > 0.0);
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
-        const int k = n + __popc(m & ((1u << lane) - 1u));
+        const unsigned m = (__ballot_sync(tmask, live) >> tshift) & tm;
+        const int k = n + __popc(m & ((1u << tl) - 1u));
         if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
         else if (i < n0) V.slot[(uint32_t)e] = 0;
         n += __popc(m);
       }
     }
     if (!compact) n = n0;
-    if (lane == 0) *s_n = n;
+    if (tl == 0) *s_n = n;
   }
-  __syncwarp();
+  __syncwarp(tmask);
   TileLists L; L.own = l; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
@@ -175,62 +176,63 @@ __global__ void __launch_bounds__(32 * CS_WARPS) colour_step_kernel(int colour, 
   double tloc = 0.0, R = 0.0;
   while (true) {
     const int n = *s_n;
-    // rate sum and inclusive prefix over the list (lane-strided chunks of 32)
+    // rate sum and inclusive prefix over the list (lane-strided chunks)
     double part = 0.0;
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) part += s_rate[i];
-    const double incl = warp_incl_scan(part, lane);
-    R = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    for (int i = tl; i < n; i += TEAM) part += s_rate[i];
+    double incl = part;
+#pragma unroll
+    for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(tmask, incl, o, TEAM); if (tl >= o) incl += t; }
+    R = __shfl_sync(tmask, incl, TEAM - 1, TEAM);
     if (!(R > 0.0) || nev >= max_events_per_tile) break;
+    // one counter-based draw per event: x -> waiting time, y + 20 bits of z -> target, 24 bits -> species, 20 bits -> arm-chair tie
     const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
-    tloc += (double)(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f)) / R;
+    tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)R);
     if (tloc > tau) break;
-    const double target = u53(rnd.z, rnd.w) * R;
+    const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * R;
     // the lane whose chunk contains the target, then the entry inside that lane's strided chunk
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, incl > target);
-    const int sel = m ? (__ffs(m) - 1) : 31;
+    const unsigned m = (__ballot_sync(tmask, incl > target) >> tshift) & tm;
+    const int sel = m ? (__ffs(m) - 1) : TEAM - 1;
     int pick = -1;
-    if (lane == sel) {
+    if (tl == sel) {
       double acc = incl - part; int last = -1;
 #pragma unroll 1
-      for (int i = lane; i < n; i += 32) { const double r = s_rate[i]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
+      for (int i = tl; i < n; i += TEAM) { const double r = s_rate[i]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
       if (pick < 0) pick = last;
     }
-    pick = __shfl_sync(0xFFFFFFFFu, pick, sel);
+    pick = __shfl_sync(tmask, pick, sel, TEAM);
     if (pick < 0) {                  // rounding left the chosen lane without a live entry: take the first live one
       int mine = -1;
 #pragma unroll 1
-      for (int i = lane; i < n; i += 32) if (s_rate[i] > 0.0) { mine = i; break; }
-      const unsigned mm = __ballot_sync(0xFFFFFFFFu, mine >= 0);
+      for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
+      const unsigned mm = (__ballot_sync(tmask, mine >= 0) >> tshift) & tm;
       if (!mm) break;
-      pick = __shfl_sync(0xFFFFFFFFu, mine, __ffs(mm) - 1);
+      pick = __shfl_sync(tmask, mine, __ffs(mm) - 1, TEAM);
     }
     const unsigned long long e = s_ce[pick];
-    const uint32_t cell = (uint32_t)e; int Itrans = (int)(e >> 32);
-    const P3 Site = cell_xyz((long long)cell);
-    double arm_u = 0.5;
-    {
-      // second counter-based draw: species / adsorbate (Get_Prob.f:164-179) and the IF_Arm_Choice.f tie
-      const uint4 r2 = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
-      arm_u = u53(r2.z, r2.w);
-      if (Itrans == EV_DRAW) {
-        const uint32_t w = D.state[cell];
-        Itrans = choose_dep_abs(w_coor(w), D.la ? site_T(w, Site) : 0, u53(r2.x, r2.y), nullptr);
-      }
+    const uint32_t cell = (uint32_t)e; int Itrans = ce_event(e);
+    P3 Site; Site.x = x0 + (int)((e >> 40) & 31u); Site.y = y0 + (int)((e >> 45) & 31u); Site.z = (int)(e >> 50);
+    if (Itrans == EV_DRAW) {         // species / adsorbate drawn now (Get_Prob.f:164-179)
+      const uint32_t w = D.state[cell];
+      const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
+      Itrans = choose_dep_abs(w_coor(w), D.la ? site_T(w, Site) : 0, us, nullptr);
     }
+    const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
     if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-    coop_event(L, lane, Site, cell, Itrans, root, arm_u, -1, K);
+    coop_event<TEAM>(L, tl, tmask, Site, cell, Itrans, root, arm_u, -1, K);
     nev++;
   }
   // ---- write the list back, reduce the counters -----------------------------------------------------------
-  __syncwarp();
+  __syncwarp(tmask);
   const int n = *s_n;
 #pragma unroll 1
-  for (int i = lane; i < n; i += 32) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
+  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
   int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
 #pragma unroll
-  for (int k = 0; k < 9; k++) v[k] = __reduce_add_sync(0xFFFFFFFFu, v[k]);
-  if (lane == 0) {
+  for (int k = 0; k < 9; k++)
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(tmask, v[k], o, TEAM);
+  if (tl == 0) {
     V.cnt[l] = n;
     V.tile_rate[l] = R;
     TileStat &st = V.tstat[l];
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   for (long long i = 0; i < n; i++) {
     P3 S; S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2];
     const int arm = ev_arm[i];
-    coop_event(L, lane, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    coop_event<32>(L, lane, 0xFFFFFFFFu, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
     done++;
     if (D.err[0] != 0) break;
   }
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long l
     uint32_t w = D.state[cell];
     int ev = 0; double p = 0;
     coop_rate(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, D.bonds[cell], root, ev, p);
-    if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = (unsigned long long)cell | ((unsigned long long)(uint32_t)ev << 32); mine++; }
+    if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = pack_ce(cell, ev, s.x, s.y, s.z); mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_sites, mine);
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = (unsigned long long)(uint32_t)c | (4ull << 32); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, 4, x, y, z); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       } else {
         D.state[c] = (2u << PosCoor);
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = (unsigned long long)(uint32_t)c | ((unsigned long long)EV_DRAW << 32); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, EV_DRAW, x, y, z); V.slot[c] = (uint16_t)(k + 1);
         atomicAdd(&counters[1], 1ull);
       }
     }
@@ -544,7 +546,7 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
     bool forced = ev == 1 && (mc_rate[i] == (double)1.e-8f || mc_rate[i] == (double)1.e-6f);
     uint32_t e = (ev == 4 || ev == 5 || forced) ? (uint32_t)ev : (uint32_t)EV_DRAW;
     size_t a = (size_t)t * P.cap + cnt[t];
-    R[a] = mc_rate[i]; CE[a] = (unsigned long long)c | ((unsigned long long)e << 32);
+    R[a] = mc_rate[i]; CE[a] = pack_ce(c, (int)e, x, y, (int)(c / plane));
     slot[c] = (uint16_t)(++cnt[t]);
   }
   PCK(cudaMemcpyAsync(P.rate, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -581,8 +583,18 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
 static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
-  const int blocks = (ntc + CS_WARPS - 1) / CS_WARPS;
-  const size_t smem = (size_t)CS_WARPS * P.cap * 16 + CS_WARPS * sizeof(int);
+  int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
+  if (teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
+  const int tpb = CS_THREADS / teamsz;
+  const int blocks = (ntc + tpb - 1) / tpb;
+  const size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCK(cudaFuncSetAttribute(colour_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 8) * P.cap * 16 + 64)));
+    PCK(cudaFuncSetAttribute(colour_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 16) * P.cap * 16 + 64)));
+    PCK(cudaFuncSetAttribute(colour_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 32) * P.cap * 16 + 64)));
+    attr_set = true;
+  }
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
@@ -604,7 +616,9 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      colour_step_kernel<<<blocks, 32 * CS_WARPS, smem, st>>>(col, key, 1 << 14);
+      if (teamsz == 8) colour_step_kernel<8><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
+      else if (teamsz == 16) colour_step_kernel<16><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
+      else colour_step_kernel<32><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
