@@ -199,7 +199,7 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "colour_step_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "colour_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    roofline = {"bound": "hbm", "kernel": "colour_step_kernel<8>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1), "launch_ms": rr.sweep_kernel_ms / max(n_launch, 1),
                 "share_of_step": rr.sweep_kernel_ms / rr.kernel_ms if rr.kernel_ms else None,
                 "note": "latency/instruction-issue bound: the touched surface set is L2-resident, DRAM traffic << algorithmic bytes (see DESIGN.md)"}
