@@ -272,8 +272,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--box", type=int, nargs=3, default=[4608, 4608, 96])
     ap.add_argument("--len1", type=int, default=24)
-    ap.add_argument("--sweeps", type=int, default=16)
-    ap.add_argument("--ept", type=float, default=8.0)
+    ap.add_argument("--sweeps", type=int, default=32)
+    ap.add_argument("--ept", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -117,7 +117,7 @@ typedef struct {
   double  tau_fixed;         /* >0: use this time quantum instead of the adaptive one               */
   uint64_t seed;             /* Philox key                                                          */
   int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
-  int32_t  flags;            /* bit0: flush L2 between sweeps is the caller's job (unused here)     */
+  int32_t  flags;            /* reserved, 0                                                         */
 } mskc_parallel_args;
 
 typedef struct {

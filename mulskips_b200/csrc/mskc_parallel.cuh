@@ -613,6 +613,8 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   if (timed) { evs.resize((size_t)a->n_sweeps * 8); for (auto &e : evs) PCK(cudaEventCreate(&e)); }
   size_t ke = 0;
   for (long long s = 0; s < a->n_sweeps; s++) {
+    // fixed colour order every sweep (an alternating ABCD/DCBA order was measured WORSE: a colour then runs twice
+    // in a row, doubling its effective quantum -- DESIGN.md section 5.3)
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];

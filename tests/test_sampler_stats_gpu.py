@@ -1,0 +1,100 @@
+"""Statistical tier: the synchronous-sublattice sampler against the serial reference loop (CPU oracle, ran3).
+
+Same start.dat (3C-SiC(001) flat surface, the reference's PVD table, PtransZig 0.8 so that the hexagonal /
+stacking-fault branch of IF_Arm_Choice.f is exercised), same physical time T*, 8 seeds each side, on the
+smallest box the sampler accepts in x-y per colour (96x96: 16 tiles, every tile borders tiles of all other
+colours -- the worst case for the frozen-neighbour approximation).  Tolerances are the north star's:
+growth (atoms deposited by T*) within 2 % (+ the statistical error of the two means), surface roughness,
+surface-site count and the number of non-epitaxial (hexagonal / stacking-fault) bulk atoms within 3 sigma of
+the seed-to-seed spread."""
+import numpy as np
+import pytest
+
+from cases import make_start
+from oracle_binding import Oracle, upload_oracle_state
+
+pytestmark = pytest.mark.gpu
+
+BOX = (96, 96, 240)
+LEN1 = 48
+TSTAR = 1.2e6          # s of KMC time: ~25 atomic layers of growth
+SEEDS = 16
+
+
+def metrics(L):
+    """growth / roughness / defect metrics from a lattice-word array [z][y][x] (WriteMolMolXYZFile.f:77-119 classes)"""
+    occ = ((L >> 23) & 1).astype(bool) & ((L & 255) != 113)
+    coor = (L >> 24) & 7
+    z, y, x = np.nonzero(occ)
+    under = coor[z, y, x] <= 3
+    bulk = coor[z, y, x] == 4
+    x1, y1, z1 = x // 3, y // 3, z // 3
+    cubic = (x % 3 == 0) & (y % 3 == 0) & (z % 3 == 0) & ((x1 & 1) == (y1 & 1)) & ((x1 & 1) == (z1 & 1)) & np.isin((x1 + y1 + z1) & 3, (0, 3))
+    return dict(atoms=float(occ.sum()), surf=float(under.sum()), rough=float(z[under].std()), height=float(z[under].mean()),
+                noepi=float((bulk & ~cubic).sum()), empties=float((((L >> 23) & 1) == 0).astype(bool)[(L != 0)].sum()))
+
+
+def oracle_run(tmp_path, seed):
+    start = make_start("surface", str(tmp_path / f"start{seed}.dat"), lens=(LEN1, 0, 0), maxiter=10**9, outmolmol=10**9, runtype="R", idum=seed, ptranszig=0.8)
+    orc = Oracle(*BOX, start)
+    orc.setup()
+    n = 0
+    while orc.time < TSTAR:
+        n += orc.run(200)
+    m = metrics(orc.lattcoo().copy())
+    m["events"] = float(n)
+    orc.close()
+    return m
+
+
+def sampler_run(tmp_path, seed, ept, flags=0):
+    from mulskips_b200 import Mskc
+    start = make_start("surface", str(tmp_path / f"pstart{seed}.dat"), lens=(LEN1, 0, 0), maxiter=10**9, outmolmol=10**9, runtype="R", idum=seed, ptranszig=0.8)
+    orc = Oracle(*BOX, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*BOX, lc, lv)
+    upload_oracle_state(orc, ctx)
+    orc.close()
+    n = 0; t = 0.0
+    while t < TSTAR:
+        r = ctx.run_parallel(1, events_per_tile=ept, seed=1000 + seed, flags=flags)
+        n += r.events_done; t = r.time
+    m = metrics(ctx.download_lattice())
+    m["events"] = float(n)
+    ctx.close()
+    return m
+
+
+def summarize(rows):
+    keys = rows[0].keys()
+    return {k: (np.mean([r[k] for r in rows]), np.std([r[k] for r in rows], ddof=1)) for k in keys}
+
+
+@pytest.mark.parametrize("ept", [2.0, 4.0])
+def test_sampler_matches_serial_loop(tmp_path, ept):
+    ref = summarize([oracle_run(tmp_path, s) for s in range(1, SEEDS + 1)])
+    par = summarize([sampler_run(tmp_path, s, ept) for s in range(1, SEEDS + 1)])
+    base = 2 * (BOX[0] // 12) * (BOX[1] // 12) * (LEN1 // 3 + 1)          # atoms of the initial slab (z = 0..Len1 step 3)
+    print(f"\nept={ept}   metric: serial mean+-sd | sampler mean+-sd")
+    for k in ref:
+        print(f"  {k:8s} {ref[k][0]:12.2f} +- {ref[k][1]:8.2f} | {par[k][0]:12.2f} +- {par[k][1]:8.2f}")
+    g_ref, g_par = ref["atoms"][0] - base, par["atoms"][0] - base
+    se = np.hypot(ref["atoms"][1], par["atoms"][1]) / np.sqrt(SEEDS)
+    assert g_ref > 1000
+    assert abs(g_par - g_ref) <= 0.02 * g_ref + 3 * se, (g_par, g_ref, se)
+    for k in ("rough", "surf", "noepi", "events"):
+        sd = max(np.hypot(ref[k][1], par[k][1]), 1e-9)
+        assert abs(par[k][0] - ref[k][0]) <= 3 * sd, (k, par[k], ref[k])
+
+
+@pytest.mark.skipif("MSKC_STATS_SCAN" not in __import__("os").environ, reason="diagnostic scan (set MSKC_STATS_SCAN=1)")
+def test_scan_tau(tmp_path):
+    """growth bias vs events_per_tile (diagnostic table, 32 seeds; results in DESIGN.md section 5.3)"""
+    ref = summarize([oracle_run(tmp_path, s) for s in range(1, 33)])
+    base = 2 * (BOX[0] // 12) * (BOX[1] // 12) * (LEN1 // 3 + 1)
+    print(f"\nserial: growth {ref['atoms'][0] - base:.1f} +- {ref['atoms'][1] / np.sqrt(32):.1f}")
+    for flags in (0,):
+        for ept in (2.0, 4.0, 8.0, 16.0):
+            par = summarize([sampler_run(tmp_path, s, ept, flags) for s in range(1, 33)])
+            print(f"ept={ept}: growth {par['atoms'][0] - base:.1f} +- {par['atoms'][1] / np.sqrt(32):.1f}  rough {par['rough'][0]:.2f} (serial {ref['rough'][0]:.2f})  events {par['events'][0]:.0f} (serial {ref['events'][0]:.0f})")
