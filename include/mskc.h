@@ -171,6 +171,20 @@ int mskc_state_hash(mskc_ctx *h, uint64_t *hash);
 typedef struct { int64_t undercoordinated, coverage, noepi_bulk, bulk, occupied, walls; double mean_height, sq_height; } mskc_census;
 int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms);
 
+/* ---- several GPUs: x-decomposed slabs with halo exchange (no counterpart in the reference, which is one
+ * serial process).  The global box global_lenx x leny x lenz is cut into nranks blocks along x;
+ * every rank's context holds its block plus one 24-unit tile column of each neighbour (local LenX =
+ * global_lenx/nranks + 48, periodic across the ranks).  mskc_run_parallel then exchanges the changed records
+ * of the boundary strips after every colour step (NCCL send/recv) and all-reduces the total rate once per
+ * sweep.  With nranks == 1 the rank is its own neighbour: the same pack/apply kernels, no NCCL.  Only the
+ * sampler runs on a slab (serial parity mode is single-GPU by construction).
+ *   rank 0: mskc_comm_unique_id(id)  ->  the host broadcasts the 128 bytes  ->  all: mskc_comm_connect(h, id). */
+int mskc_create_slab(int global_lenx, int leny, int lenz, int ncrystal, int ncov,
+                     const int32_t *listcrystal, const int32_t *listcov,
+                     int rank, int nranks, int device_id, mskc_ctx **out);
+int mskc_comm_unique_id(void *id128);
+int mskc_comm_connect(mskc_ctx *h, const void *id128);
+
 /* Test/diagnostic entry points of the sampler's transition code (no counterpart in the reference).
  * mskc_replay_events applies n GIVEN events one after the other through the same warp-cooperative
  * transition + re-rate code mskc_run_parallel uses: site_xyz [n][3], event codes as in main.f:335-357,

@@ -66,7 +66,8 @@ SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "
            "mskc_init_flat", "mskc_seed", "mskc_get_rng", "mskc_set_clock", "mskc_run_parity", "mskc_run_parallel",
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
-           "mskc_replay_events", "mskc_download_active", "mskc_download_bonds"]
+           "mskc_replay_events", "mskc_download_active", "mskc_download_bonds",
+           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect"]
 
 
 def load_library():
@@ -105,6 +106,9 @@ def load_library():
     lib.mskc_replay_events.argtypes = [vp, C.c_int64, i32p, i32p, i32p, C.c_double]
     lib.mskc_download_active.argtypes = [vp, C.c_int64, i32p, i32p, f64p, i64p]
     lib.mskc_download_bonds.argtypes = [vp, C.c_int64, i32p, i32p]
+    lib.mskc_create_slab.argtypes = [C.c_int] * 5 + [i32p, i32p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.mskc_comm_unique_id.argtypes = [C.c_void_p]
+    lib.mskc_comm_connect.argtypes = [vp, C.c_void_p]
     for s in SYMBOLS:
         if s != "mskc_last_error":
             getattr(lib, s).restype = C.c_int
@@ -127,14 +131,23 @@ def _f64(a):
 class Mskc:
     """One KMC context on one GPU (the module globals of defsystem.f, device resident)."""
 
-    def __init__(self, lenx, leny, lenz, listcrystal, listcov=(), device=0, nummcmax=0):
+    def __init__(self, lenx, leny, lenz, listcrystal, listcov=(), device=0, nummcmax=0, slab=None):
+        """slab=(rank, nranks): lenx is the GLOBAL LenX of an x-decomposed box; this context holds rank's block plus
+        one 24-unit halo tile column on each side (local LenX = lenx/nranks + 48)."""
         self.lib = load_library()
-        self.shape = (lenz + 1, leny, lenx)
-        self.LenX, self.LenY, self.LenZ = lenx, leny, lenz
         lc, lv = _i32(list(listcrystal)), _i32(list(listcov) if len(listcov) else [0])
         h = C.c_void_p()
-        rc = self.lib.mskc_create(lenx, leny, lenz, len(listcrystal), len(listcov), _p(lc, C.c_int32), _p(lv, C.c_int32),
-                                  device, nummcmax, C.byref(h))
+        self.slab = slab
+        if slab is not None:
+            rank, nranks = slab
+            self.global_LenX = lenx
+            rc = self.lib.mskc_create_slab(lenx, leny, lenz, len(listcrystal), len(listcov), _p(lc, C.c_int32), _p(lv, C.c_int32), rank, nranks, device, C.byref(h))
+            lenx = lenx // nranks + 48
+        else:
+            rc = self.lib.mskc_create(lenx, leny, lenz, len(listcrystal), len(listcov), _p(lc, C.c_int32), _p(lv, C.c_int32),
+                                      device, nummcmax, C.byref(h))
+        self.shape = (lenz + 1, leny, lenx)
+        self.LenX, self.LenY, self.LenZ = lenx, leny, lenz
         if rc != 0:
             raise MskcError(self.lib.mskc_last_error(None).decode())
         self.h = h
@@ -153,6 +166,16 @@ class Mskc:
             self.close()
         except Exception:
             pass
+
+    # -- several GPUs ------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        if self.lib.mskc_comm_unique_id(buf) != 0:
+            raise MskcError(self.lib.mskc_last_error(None).decode())
+        return buf.raw
+
+    def comm_connect(self, id128: bytes):
+        self._ck(self.lib.mskc_comm_connect(self.h, C.create_string_buffer(id128, 128)))
 
     # -- tables ------------------------------------------------------------------------------------
     def set_rates(self, PtransE, PtransD, PtransAbs=None, PtransDes=None, PtransZig=1.0):

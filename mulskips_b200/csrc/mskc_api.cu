@@ -178,6 +178,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaFree(h->d_stage); cudaFree(h->d_arm_tab);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
+  if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }
   parallel_free(h->PC);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
   cudaStreamDestroy(h->stream);
@@ -382,6 +383,7 @@ extern "C" int mskc_set_clock(mskc_ctx *h, int64_t iter, double time, const int3
 extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_parity_result *r) {
   if (!h || !a || !r) return set_err(h, "mskc_run_parity: NULL argument");
   if (!h->parity_ready || !h->have_rates) return set_err(h, "mskc_run_parity: rates and state must be uploaded first");
+  if (h->PC.halo) return set_err(h, "mskc_run_parity: serial parity mode is single-GPU (not available on a slab context)");
   CK(cudaSetDevice(h->device));
   if (upload_consts(h)) return -1;
   ParityArgs A{};
@@ -694,5 +696,42 @@ extern "C" int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, i
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d_c); cudaFree(d_b);
   for (int64_t i = 0; i < n; i++) h_dec_bonds(D, xyz + 3 * i, b[i], nn + 12 * i);
+  return 0;
+}
+
+// ---- x-decomposed slabs (several GPUs) -----------------------------------------------------------------------
+extern "C" int mskc_create_slab(int global_lenx, int leny, int lenz, int ncrystal, int ncov, const int32_t *listcrystal, const int32_t *listcov,
+                                int rank, int nranks, int device_id, mskc_ctx **out) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return set_err(nullptr, "mskc_create_slab: rank %d of %d", rank, nranks);
+  if (global_lenx % (48 * nranks) || leny % 48) return set_err(nullptr, "mskc_create_slab: global LenX must be a multiple of 48*nranks and LenY of 48");
+  const int owned = global_lenx / nranks;
+  if (owned < 48) return set_err(nullptr, "mskc_create_slab: fewer than two tile columns per rank");
+  if (mskc_create(owned + 48, leny, lenz, ncrystal, ncov, listcrystal, listcov, device_id, 0, out)) return -1;
+  (*out)->PC.halo = 1; (*out)->PC.rank = rank; (*out)->PC.nranks = nranks;
+  return 0;
+}
+extern "C" int mskc_comm_unique_id(void *id128) {
+  if (!id128) return set_err(nullptr, "mskc_comm_unique_id: NULL argument");
+  std::string e; NcclApi *nccl = nccl_api(&e);
+  if (!nccl) return set_err(nullptr, "%s", e.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = nccl->GetUniqueId(&id);
+  if (r != ncclSuccess) return set_err(nullptr, "ncclGetUniqueId: %s", nccl->GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return 0;
+}
+extern "C" int mskc_comm_connect(mskc_ctx *h, const void *id128) {
+  if (!h || !id128) return set_err(h, "mskc_comm_connect: NULL argument");
+  if (!h->PC.halo) return set_err(h, "mskc_comm_connect: not a slab context (use mskc_create_slab)");
+  if (h->PC.nranks == 1) return 0;
+  CK(cudaSetDevice(h->device));
+  std::string e; NcclApi *nccl = nccl_api(&e);
+  if (!nccl) return set_err(h, "%s", e.c_str());
+  ncclUniqueId id; memcpy(&id, id128, 128);
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = nccl->CommInitRank(&comm, h->PC.nranks, id, h->PC.rank);
+  if (r != ncclSuccess) return set_err(h, "ncclCommInitRank: %s", nccl->GetErrorString(r));
+  h->PC.comm = (void *)comm;
   return 0;
 }

@@ -16,6 +16,8 @@
 #include "mskc_coop.cuh"
 #include "../../include/mskc.h"
 #include <algorithm>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cstdlib>
 #include <cstdio>
 #include <functional>
@@ -45,6 +47,12 @@ struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
   double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
+  // slab mode
+  int halo = 0, rank = 0, nranks = 1;
+  uint32_t *dirty_bits = nullptr, *dirty_cell = nullptr; int *dirty_n = nullptr; int dirty_cap = 0; size_t dirty_words = 0;
+  double *red = nullptr;
+  unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
+  void *comm = nullptr;                 // ncclComm_t
   long long ncell = 0;
   long long base_atoms = 0, base_voids = 0;
   int baseCrystal[3] = {0, 0, 0}, baseCov[3] = {0, 0, 0};
@@ -56,6 +64,11 @@ struct ParallelCtx {
 struct TileView {            // what the kernels need (constant memory)
   int tile, ntx, nty, cap, NT, hx, ntc;
   double *rate; unsigned long long *ce; int *cnt; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
+  // x-decomposed slab (multi-GPU): one halo tile column on each side of the owned block, see "halo exchange" below
+  int halo, nranks;
+  uint32_t *dirty_bits;                 // bitmap over the two 48-unit shared strips (left: x < 48, right: x >= LX-48)
+  uint32_t *dirty_cell; int *dirty_n; int dirty_cap;     // [2][dirty_cap] cells modified this colour step, [2] counts
+  double *red;                          // [4] per-sweep sums that cross ranks: total rate, active sites, (spare)
 };
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: no per-tile generator state in memory ----
@@ -97,10 +110,26 @@ __host__ __device__ __forceinline__ int ce_event(unsigned long long e) { return 
 // for the whole colour step (scans and updates never leave the SM) and written back once at the end;
 // entries of cells that belong to other (not running) tiles go straight to those tiles' lists in HBM,
 // slots claimed with atomics because two running tiles can border the same idle tile.
+// Slab mode: remember every cell of the two shared strips whose record changed in this colour step (once
+// per cell: bitmap + list), for halo_pack_kernel.
+__device__ __noinline__ void mark_dirty(P3 s, uint32_t c) {
+  const int side = s.x < 2 * TILE ? 0 : (s.x >= D.LX - 2 * TILE ? 1 : -1);
+  if (side < 0) return;
+  const int xs = side ? s.x - (D.LX - 2 * TILE) : s.x;
+  const uint32_t bit = (uint32_t)(((side * 2 * TILE + xs) * D.LY + s.y) * (D.LZ + 1) + s.z);
+  const uint32_t m = 1u << (bit & 31u);
+  if (atomicOr(&V.dirty_bits[bit >> 5], m) & m) return;
+  const int k = atomicAdd(&V.dirty_n[side], 1);
+  if (k >= V.dirty_cap) { fail(E_TILE_FULL, s.x, s.y, s.z, -1 - side); return; }
+  V.dirty_cell[(size_t)side * V.dirty_cap + k] = c;
+}
+
 struct TileLists {
   int own;                                   // list id of the running tile (-1: none, everything is "foreign")
+  int mark;                                  // slab mode: log changed cells of the shared strips
   double *s_rate; unsigned long long *s_ce; int *s_n;
   __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p) {
+    if (mark) mark_dirty(s, c);
     const int l = list_of(s);
     int sl = V.slot[c];
     const bool mine = l == own;
@@ -114,6 +143,7 @@ struct TileLists {
     else { const long long a = lidx(l, sl - 1); V.rate[a] = p; V.ce[a] = e; }
   }
   __device__ __forceinline__ void erase(P3 s, uint32_t c) {          // tombstone (rate 0); the owner compacts
+    if (mark) mark_dirty(s, c);
     const int sl = V.slot[c];
     if (!sl) return;
     const int l = list_of(s);
@@ -142,6 +172,7 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
   int *s_n = reinterpret_cast<int *>(smem + (size_t)TPB * cap * 16) + tib;
   const int l = colour * V.ntc + wid;
   const int x0 = (2 * (wid % V.hx) + (colour & 1)) * TILE, y0 = (2 * (wid / V.hx) + (colour >> 1)) * TILE;   // tile origin (list_of inverted)
+  if (V.halo && (x0 == 0 || x0 == D.LX - TILE)) return;       // halo tiles belong to the neighbouring rank
   const SweepState ss = *V.ss;
   const double tau = ss.tau, root = ss.tree_root;
   // ---- load the tile's list (dropping tombstones when it has grown) ------------------------------------
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
     if (tl == 0) *s_n = n;
   }
   __syncwarp(tmask);
-  TileLists L; L.own = l; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
+  TileLists L; L.own = l; L.mark = V.halo; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
   int nev = 0, ndep0 = 0, ndep1 = 0, ndep2 = 0, nevap = 0, nabs = 0, ndes = 0;
@@ -244,6 +275,39 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
   }
 }
 
+// ---- halo exchange (x-decomposed slabs) ------------------------------------------------------
+// Every rank holds its block plus one tile column (24 units) of each neighbour.  Tiles of one colour on both
+// sides of a rank boundary never touch the same cell (section 5.3 of DESIGN.md), so after a colour step the two
+// copies of a shared strip differ only where ONE side wrote: each rank sends the final record of every cell it
+// changed in its two 48-unit strips (its border tile column + its halo column) and applies what it receives.
+struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad; };     // 32 B
+__global__ void __launch_bounds__(256) halo_pack_kernel(int side, int shift /* +-owned width */, HaloRec *out) {
+  const int n = min(V.dirty_n[side], V.dirty_cap);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint32_t c = V.dirty_cell[(size_t)side * V.dirty_cap + k];
+    const P3 s = cell_xyz((long long)c);
+    const int xs = side ? s.x - (D.LX - 2 * TILE) : s.x;
+    const uint32_t bit = (uint32_t)(((side * 2 * TILE + xs) * D.LY + s.y) * (D.LZ + 1) + s.z);
+    atomicAnd(&V.dirty_bits[bit >> 5], ~(1u << (bit & 31u)));
+    HaloRec r; r.cell = (uint32_t)((long long)c + shift); r.state = D.state[c]; r.bonds = D.bonds[c]; r.rate = 0.0; r.ev = 0; r.pad = 0;
+    const int sl = V.slot[c];
+    if (sl) { const long long a = lidx(list_of(s), sl - 1); r.rate = V.rate[a]; r.ev = (uint32_t)ce_event(V.ce[a]); }
+    out[1 + k] = r;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { HaloRec h; h.cell = (uint32_t)n; h.state = 0; h.bonds = 0; h.rate = 0; h.ev = 0; h.pad = 0; out[0] = h; }
+}
+__global__ void halo_reset_kernel() { V.dirty_n[0] = 0; V.dirty_n[1] = 0; }
+__global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in) {
+  const int n = (int)in[0].cell;
+  TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const HaloRec r = in[1 + k];
+    D.state[r.cell] = r.state; D.bonds[r.cell] = r.bonds;
+    const P3 s = cell_xyz((long long)r.cell);
+    if (r.rate > 0.0) L.put(s, r.cell, (int)r.ev, r.rate); else L.erase(s, r.cell);
+  }
+}
+
 // Drop the tombstones of every list (one warp per tile) -- the same compaction the colour-step kernel does
 // when it loads a long list; used between replay chunks, where no tile is ever "running".
 __global__ void __launch_bounds__(128) compact_lists_kernel(int ntiles) {
@@ -272,7 +336,7 @@ __global__ void __launch_bounds__(128) compact_lists_kernel(int ntiles) {
 // cooperative transition code the sampler uses.  Lists are updated in HBM only.
 __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, const int32_t *ev_code, const int32_t *ev_arm, long long n, double root, TileStat *out) {
   const int lane = threadIdx.x;
-  TileLists L; L.own = -1; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
+  TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
   long long done = 0;
@@ -292,22 +356,34 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   }
 }
 
-// Per-sweep bookkeeping ("per-class rate sums"): total rate, active-site count, next tau, clock.
-__global__ void __launch_bounds__(1024) sweep_stats_kernel(int ntiles, double events_per_tile, double tau_fixed, int advance) {
+__device__ __forceinline__ bool halo_list(int l) {        // is tile-list l one of the two halo tile columns?
+  if (!V.halo) return false;
+  const int colour = l / V.ntc, idx = l - colour * V.ntc;
+  const int tx = 2 * (idx % V.hx) + (colour & 1);
+  return tx == 0 || tx == V.ntx - 1;
+}
+// Per-sweep bookkeeping ("per-class rate sums"), stage 1: this rank's total rate and active-site count -> V.red.
+__global__ void __launch_bounds__(1024) sweep_sum_kernel(int ntiles) {
   __shared__ double sR[32]; __shared__ long long sN[32]; __shared__ int sM[32];
   double r = 0.0; long long n = 0; int mx = 0;
-  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { r += V.tile_rate[t]; int c = V.cnt[t]; n += c; mx = max(mx, c); }
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { if (halo_list(t)) continue; r += V.tile_rate[t]; int c = V.cnt[t]; n += c; mx = max(mx, c); }
   for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); }
   if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double R = 0; long long N = 0; int M = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); i++) { R += sR[i]; N += sN[i]; M = max(M, sM[i]); }
-    SweepState &s = *V.ss;
-    if (advance) { s.time += s.tau; s.sweeps++; }
-    s.total_rate = R; s.tree_root = R; s.n_active = N; s.max_cnt = M;
-    s.tau = tau_fixed > 0 ? tau_fixed : (R > 0 ? events_per_tile * (double)ntiles / R : 0.0);
+    V.red[0] = R; V.red[1] = (double)N; V.red[2] = 0.0; V.red[3] = 0.0;
+    V.ss->max_cnt = M;
   }
+}
+// stage 2 (after the all-reduce of V.red over the ranks, if any): clock, next tau, global-coupling terms
+__global__ void sweep_finish_kernel(double ntiles_global, double events_per_tile, double tau_fixed, int advance) {
+  SweepState &s = *V.ss;
+  const double R = V.red[0];
+  if (advance) { s.time += s.tau; s.sweeps++; }
+  s.total_rate = R; s.tree_root = R; s.n_active = (long long)V.red[1];
+  s.tau = tau_fixed > 0 ? tau_fixed : (R > 0 ? events_per_tile * ntiles_global / R : 0.0);
 }
 __global__ void bump_step_kernel(SweepState *ss) { ss->step++; }
 
@@ -315,7 +391,7 @@ __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= ntiles) return;
   int n = V.cnt[l]; double r = 0;
-  for (int i = 0; i < n; i++) r += V.rate[lidx(l, i)];
+  if (!halo_list(l)) for (int i = 0; i < n; i++) r += V.rate[lidx(l, i)];
   V.tile_rate[l] = r;
 }
 
@@ -409,6 +485,7 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
     for (int k = 0; k < 4; k++) {
       uint32_t w = ww[k];
       if (w == 0) continue;
+      if (V.halo) { const int x = (int)((4 * q + k) % D.LX); if (x < TILE || x >= D.LX - TILE) continue; }      // halo columns belong to the neighbours
       int cov = w_cov(w);
       if (cov == 113) { nWall++; continue; }
       if (w_occ(w)) {
@@ -445,6 +522,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
       for (int z = D.LZ - 6; z <= D.LZ - 1; z++) D.state[col + plane * z] = (1u << PosOcc) | 113u;
     }
     if (x % 3 || y % 3) continue;
+    const bool owned = !V.halo || (x >= TILE && x < D.LX - TILE);
     for (int z = (walls ? 6 : 0); z <= Len; z += 1) {
       int kind;
       if (!is_cubic_site(x, y, z, kind)) continue;
@@ -456,7 +534,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
       if (z <= Len - 4) {
         D.state[c] = (1u << (PosSiC + sp - 1)) | (1u << PosOcc) | (4u << PosCoor);
         D.bonds[c] = enc_bonds(s, nn);
-        atomicAdd(&counters[0], 1ull);
+        if (owned) atomicAdd(&counters[0], 1ull);
       } else if (z <= Len - 1) {
         D.state[c] = (1u << (PosSiC + sp - 1)) | (1u << PosOcc) | (2u << PosCoor);
         D.bonds[c] = enc_bonds(s, nn);
@@ -483,14 +561,51 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
 // ---- host side -------------------------------------------------------------------------------------
 #define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { if (err) *err = std::string("CUDA error ") + cudaGetErrorString(e_) + " in " #call; return -1; } } while (0)
 
+// ---- NCCL, loaded at run time (only multi-rank slab runs need it; torch's bundled libnccl.so.2 is reused when
+// the host process has it loaded, else the system one) --------------------------------------------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static inline NcclApi *nccl_api(std::string *err) {
+  static NcclApi api; static bool tried = false;
+  if (api.lib) return &api;
+  if (tried) { if (err) *err = "libnccl.so.2 could not be loaded"; return nullptr; }
+  tried = true;
+  const char *names[] = {getenv("MSKC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) { if (n && *n) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; } }
+  if (!api.lib) { if (err) *err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return nullptr; }
+#define MSKC_SYM(f) *(void **)(&api.f) = dlsym(api.lib, "nccl" #f); if (!api.f) { if (err) *err = "libnccl: missing symbol nccl" #f; api.lib = nullptr; return nullptr; }
+  MSKC_SYM(GetUniqueId) MSKC_SYM(CommInitRank) MSKC_SYM(CommDestroy) MSKC_SYM(Send) MSKC_SYM(Recv) MSKC_SYM(AllReduce) MSKC_SYM(GroupStart) MSKC_SYM(GroupEnd) MSKC_SYM(GetErrorString)
+#undef MSKC_SYM
+  return &api;
+}
+#define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { if (err) *err = std::string("NCCL error ") + nccl->GetErrorString(r_) + " in " #call; return -1; } } while (0)
+
+enum { HALO_CAP = 32768 };         // records per side per colour step (1 MiB messages)
+
 static inline void parallel_free(ParallelCtx &P) {
+  const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
+  cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.red);
+  for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
   cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
+  P.halo = halo; P.rank = rank; P.nranks = nranks; P.comm = comm;
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
   V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.slot = P.slot;
-  V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; return V;
+  V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss;
+  V.halo = P.halo; V.nranks = P.nranks; V.dirty_bits = P.dirty_bits; V.dirty_cell = P.dirty_cell; V.dirty_n = P.dirty_n; V.dirty_cap = P.dirty_cap; V.red = P.red;
+  return V;
 }
 static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int cap, std::string *err) {
   int tile = 24;
@@ -502,6 +617,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
     PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
     PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
+    if (P.halo) { PCK(cudaMemsetAsync(P.dirty_bits, 0, P.dirty_words * 4, st)); PCK(cudaMemsetAsync(P.dirty_n, 0, 2 * sizeof(int), st)); }
     return 0;
   }
   parallel_free(P);
@@ -514,6 +630,20 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
   PCK(cudaMalloc(&P.ss, sizeof(SweepState)));
   PCK(cudaMalloc(&P.tot, sizeof(TileStat)));
+  PCK(cudaMalloc(&P.red, 4 * sizeof(double)));
+  PCK(cudaMemsetAsync(P.red, 0, 4 * sizeof(double), st));
+  if (P.halo) {
+    if (H.LX < 4 * tile) { if (err) *err = "slab mode needs at least two owned tile columns per rank"; return -1; }
+    P.dirty_cap = HALO_CAP;
+    P.dirty_words = ((size_t)4 * tile * H.LY * (H.LZ + 1) + 31) / 32;
+    PCK(cudaMalloc(&P.dirty_bits, P.dirty_words * 4)); PCK(cudaMemsetAsync(P.dirty_bits, 0, P.dirty_words * 4, st));
+    PCK(cudaMalloc(&P.dirty_cell, (size_t)2 * P.dirty_cap * 4));
+    PCK(cudaMalloc(&P.dirty_n, 2 * sizeof(int))); PCK(cudaMemsetAsync(P.dirty_n, 0, 2 * sizeof(int), st));
+    for (int i = 0; i < 2; i++) {
+      PCK(cudaMalloc(&P.sendbuf[i], (size_t)(HALO_CAP + 1) * sizeof(HaloRec))); PCK(cudaMemsetAsync(P.sendbuf[i], 0, sizeof(HaloRec), st));
+      PCK(cudaMalloc(&P.recvbuf[i], (size_t)(HALO_CAP + 1) * sizeof(HaloRec))); PCK(cudaMemsetAsync(P.recvbuf[i], 0, sizeof(HaloRec), st));
+    }
+  }
   PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ce, 0, (size_t)P.ntiles * cap * sizeof(unsigned long long), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
@@ -524,6 +654,45 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   return 0;
 }
 static const int TILE_CAP = 192;
+
+// per-sweep totals: local sums, all-reduce over the ranks of a slab run, then clock / tau / global-coupling terms
+static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, double tau_fixed, int advance, int *launches, std::string *err) {
+  sweep_sum_kernel<<<1, 1024, 0, st>>>(P.ntiles);
+  if (P.nranks > 1) {
+    NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
+    if (!P.comm) { if (err) *err = "slab run with several ranks: call mskc_comm_connect first"; return -1; }
+    NCK(nccl->AllReduce(P.red, P.red, 4, ncclDouble, ncclSum, (ncclComm_t)P.comm, st));
+  }
+  const double owned = (double)(P.ntx - 2 * P.halo) * P.nty * P.nranks;
+  sweep_finish_kernel<<<1, 1, 0, st>>>(owned, ept, tau_fixed, advance);
+  *launches += 2;
+  return 0;
+}
+// after a colour step: send the changed records of the two shared strips to the neighbours, apply theirs
+static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int *launches, std::string *err) {
+  const int owned = H.LX - 2 * P.tile;                         // width of the owned block = shift between the two copies of a strip
+  halo_pack_kernel<<<32, 256, 0, st>>>(0, +owned, (HaloRec *)P.sendbuf[0]);      // my left strip  = the left neighbour's right strip
+  halo_pack_kernel<<<32, 256, 0, st>>>(1, -owned, (HaloRec *)P.sendbuf[1]);      // my right strip = the right neighbour's left strip
+  halo_reset_kernel<<<1, 1, 0, st>>>();
+  const size_t bytes = (size_t)(HALO_CAP + 1) * sizeof(HaloRec);
+  const unsigned char *in0 = P.sendbuf[0], *in1 = P.sendbuf[1];
+  if (P.nranks > 1) {
+    NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
+    if (!P.comm) { if (err) *err = "slab run with several ranks: call mskc_comm_connect first"; return -1; }
+    const int left = (P.rank + P.nranks - 1) % P.nranks, right = (P.rank + 1) % P.nranks;
+    NCK(nccl->GroupStart());
+    NCK(nccl->Send(P.sendbuf[0], bytes, ncclUint8, left, (ncclComm_t)P.comm, st));
+    NCK(nccl->Send(P.sendbuf[1], bytes, ncclUint8, right, (ncclComm_t)P.comm, st));
+    NCK(nccl->Recv(P.recvbuf[0], bytes, ncclUint8, right, (ncclComm_t)P.comm, st));
+    NCK(nccl->Recv(P.recvbuf[1], bytes, ncclUint8, left, (ncclComm_t)P.comm, st));
+    NCK(nccl->GroupEnd());
+    in0 = P.recvbuf[0]; in1 = P.recvbuf[1];
+  }                                                            // one rank: it is its own neighbour on both sides (periodic box)
+  halo_apply_kernel<<<32, 256, 0, st>>>((const HaloRec *)in0);
+  halo_apply_kernel<<<32, 256, 0, st>>>((const HaloRec *)in1);
+  *launches += 5;
+  return 0;
+}
 
 // tile lists from an uploaded MC list (reference order is irrelevant here)
 static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int n_mc, const uint32_t *mc_cell, const int *mc_ev,
@@ -602,8 +771,8 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
     tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
-    sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, ept, a->tau_fixed, 0);
-    launches += 2;
+    if (sweep_totals(P, st, ept, a->tau_fixed, 0, &launches, err)) return -1;
+    launches += 1;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
   // short calls time every colour-step kernel on its own (CUDA events on the launching stream): this is
@@ -624,9 +793,9 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
+      if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
     }
-    sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, ept, a->tau_fixed, 1);
-    launches++;
+    if (sweep_totals(P, st, ept, a->tau_fixed, 1, &launches, err)) return -1;
   }
   reduce_tstat_kernel<<<1, 256, 0, st>>>(P.tstat, P.ntiles, P.tot);
   launches++;
@@ -659,7 +828,7 @@ static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cu
   PCK(cudaEventRecord(e0, st));
   rerate_kernel<<<148 * 8, 256, 0, st>>>(P.ntiles, d_n);
   tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
-  sweep_stats_kernel<<<1, 1024, 0, st>>>(P.ntiles, 4.0, 0.0, 0);
+  { int l_ = 0; if (sweep_totals(P, st, 4.0, 0.0, 0, &l_, err)) return -1; }
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(&h_n, d_n, 8, cudaMemcpyDeviceToHost, st));

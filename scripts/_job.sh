@@ -1,1 +1,2 @@
-MSKC_STATS_SCAN=1 python -m pytest tests/test_sampler_stats_gpu.py -x -q -s -k scan 2>&1 | tail -20
+set -x
+python -m pytest tests/test_slab_gpu.py -x -q -s 2>&1 | tail -15
