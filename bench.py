@@ -138,7 +138,8 @@ def config_dict(args, where):
     bx, by, bz = args.box
     return {"workload": f"3C-SiC(001) flat slab PVD, start-surface.dat rate table, PtransZig=0.8, {bx}x{by}x{bz} super-lattice cells ({bx * by * bz / 1e9:.2f}e9 sites) per GPU, F builder Len1={args.len1}",
             "box_per_gpu": [bx, by, bz], "sweeps_per_step": args.sweeps, "events_per_tile": args.ept, "mode": "synchronous-sublattice sampler (24-unit tiles, 2x2 colours, Philox4x32-10)",
-            "parallelism": f"{args.gpus} independent x-y periodic slab(s), one per GPU", "l2": "inputs (state+bonds+slot, 14 B/cell) >> 126 MB L2; no flush", "where": where}
+            "parallelism": ("one periodic box on one GPU" if args.gpus == 1 else
+                            f"one periodic box of {bx * args.gpus}x{by} cells cut into {args.gpus} x-slabs (one per GPU), 24-unit halo tile columns exchanged after every colour step (NCCL send/recv), total rate all-reduced per sweep"), "l2": "inputs (state+bonds+slot, 14 B/cell) >> 126 MB L2; no flush", "where": where}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -163,8 +164,17 @@ def run_ours(args):
 
     w = workload(args)
     bx, by, bz = args.box
-    ctx = Mskc(bx, by, bz, w["listcrystal"], w["listcov"], device=local)
+    if world > 1:
+        # one global periodic box of world*bx x by cells, cut into x-slabs: halo-tile exchange after every colour step
+        # (NCCL send/recv inside libmskc) and one all-reduce of the total rate per sweep
+        ctx = Mskc(bx * world, by, bz, w["listcrystal"], w["listcov"], device=local, slab=(rank, world))
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_connect(ids[0])
+    else:
+        ctx = Mskc(bx, by, bz, w["listcrystal"], w["listcov"], device=local)
     ctx.set_rates(w["PtransE"], w["PtransD"], w["PtransAbs"], w["PtransDes"], w["PtransZig"])
+    lx = ctx.LenX                      # local LenX (owned block + 2 halo tile columns on a slab)
 
     def fresh():
         ctx.init_flat(args.len1, walls=False, two_species=True)
@@ -208,9 +218,9 @@ def run_ours(args):
     # Per step: H2D of the per-cell input field the reference receives each cycle (SetT.f / the LA socket's
     # SENDFIELD: int32 [LenZ][LenY*LenX]) from pinned memory, the sweeps, and D2H of the whole lattice
     # (what WriteMolMolXYZFile / GETPHASES read).
-    ncell_T = bx * by * bz
+    ncell_T = lx * by * bz
     T_host = torch.full((ncell_T,), 1000, dtype=torch.int32).pin_memory()
-    L_host = torch.empty(((bz + 1) * by * bx,), dtype=torch.int32).pin_memory()
+    L_host = torch.empty(((bz + 1) * by * lx,), dtype=torch.int32).pin_memory()
     i32p = C.POINTER(C.c_int32)
     Tp, Lp = C.cast(T_host.data_ptr(), i32p), C.cast(L_host.data_ptr(), i32p)
     fresh()
@@ -255,7 +265,7 @@ def run_ours(args):
                "data": "synthetic", "config": config_dict(args, "gpu"),
                "site_updates_per_s": su_sum / dt_max, "events_per_step": ev_sum / args.steps, "active_sites_per_gpu": int(n_active),
                "device_ms_per_step": kms / args.steps, "gpu_launches": int(launches),
-               "e2e": {"value": ev2_sum / dt2_max, "unit": UNIT, "h2d_bytes_per_step": 4 * ncell_T, "d2h_bytes_per_step": 4 * (bz + 1) * by * bx,
+               "e2e": {"value": ev2_sum / dt2_max, "unit": UNIT, "h2d_bytes_per_step": 4 * ncell_T, "d2h_bytes_per_step": 4 * (bz + 1) * by * lx,
                        "ms_per_step": 1e3 * dt2_max / args.steps, "what": "mskc_set_temperature(pinned int32 field) + mskc_run_parallel + mskc_download_lattice(pinned) per step", "checksum": occ},
                "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(out))

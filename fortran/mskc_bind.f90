@@ -188,5 +188,21 @@ module mskc_bind
       type(c_ptr), value :: h, xyz, nn
       integer(c_int64_t), value :: n
     end function
+    ! several GPUs: x-decomposed slabs (no counterpart in the reference)
+    integer(c_int) function mskc_create_slab(global_lenx, leny, lenz, ncrystal, ncov, listcrystal, listcov, rank, nranks, device_id, h) &
+        bind(C, name="mskc_create_slab")
+      import :: c_int, c_ptr
+      integer(c_int), value :: global_lenx, leny, lenz, ncrystal, ncov, rank, nranks, device_id
+      type(c_ptr), value :: listcrystal, listcov
+      type(c_ptr) :: h
+    end function
+    integer(c_int) function mskc_comm_unique_id(id128) bind(C, name="mskc_comm_unique_id")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: id128
+    end function
+    integer(c_int) function mskc_comm_connect(h, id128) bind(C, name="mskc_comm_connect")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, id128
+    end function
   end interface
 end module mskc_bind

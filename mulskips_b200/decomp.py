@@ -1,24 +1,42 @@
-"""x-y decomposition helpers for N GPUs of one box: blocks on super-tile (48-unit)
-boundaries, one process per GPU, and the rank aggregation used for whole-job throughput."""
+"""x-decomposition helpers for N GPUs of one box: the global periodic box is cut into N blocks
+along x on super-tile (48-unit) boundaries, one process per GPU; every rank holds its block plus one
+24-unit halo tile column of each neighbour.  Mirrors the arithmetic of mskc_create_slab / halo_exchange
+(csrc/mskc_api.cu, csrc/mskc_parallel.cuh) for host-side code and tests."""
 from __future__ import annotations
 
-
-def slab_grid(world: int):
-    """Process grid gx x gy (gx >= gy) as square as possible: 1x1, 2x1, 2x2, 4x2."""
-    gy = 1
-    for d in range(1, int(world ** 0.5) + 1):
-        if world % d == 0:
-            gy = d
-    return world // gy, gy
+HALO = 24      # one tile column
+UNIT = 48      # 2x2-coloured 24-unit tiles
 
 
-def rank_block(rank: int, world: int, lenx: int, leny: int, unit: int = 48):
-    """(x0, y0, lx, ly) of the rank's x-y block inside a global lenx x leny lattice."""
-    gx, gy = slab_grid(world)
-    if lenx % (gx * unit) or leny % (gy * unit):
-        raise ValueError(f"global box {lenx}x{leny} does not split into {gx}x{gy} blocks on {unit}-unit boundaries")
-    lx, ly = lenx // gx, leny // gy
-    return (rank % gx) * lx, (rank // gx) * ly, lx, ly
+def slab_block(rank: int, world: int, global_lenx: int):
+    """(x0, owned, local_lenx): first global x of the rank's block, its width, and the local array width."""
+    if global_lenx % (UNIT * world):
+        raise ValueError(f"global LenX {global_lenx} does not split into {world} blocks on {UNIT}-unit boundaries")
+    owned = global_lenx // world
+    if owned < UNIT:
+        raise ValueError("fewer than two tile columns per rank")
+    return rank * owned, owned, owned + 2 * HALO
+
+
+def neighbours(rank: int, world: int):
+    """(left, right) ranks of the periodic 1-D process grid (a single rank is its own neighbour)."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def to_local(x_global: int, rank: int, world: int, global_lenx: int) -> int:
+    """local x of a global x that lies in the rank's block or in one of its halo columns"""
+    x0, owned, _ = slab_block(rank, world, global_lenx)
+    d = (x_global - x0) % global_lenx
+    if d >= global_lenx - HALO:
+        d -= global_lenx
+    if not -HALO <= d < owned + HALO:
+        raise ValueError("x is outside the rank's block and halos")
+    return d + HALO
+
+
+def seam_shift(owned: int, side: int) -> int:
+    """index shift that maps a cell of my left (side 0) / right (side 1) 48-unit strip onto the neighbour's copy"""
+    return owned if side == 0 else -owned
 
 
 def aggregate(dist, values, ops, device="cuda"):

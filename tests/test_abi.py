@@ -29,6 +29,13 @@ def test_header_matches_binding(lib):
     assert header_symbols() == sorted(capi.SYMBOLS)
 
 
+def test_fortran_binding_names():
+    """fortran/mskc_bind.f90 (the ISO_C_BINDING module a Fortran host uses) binds exactly the header's symbols."""
+    txt = open(os.path.join(ROOT, "fortran", "mskc_bind.f90")).read()
+    bound = sorted(set(re.findall(r'bind\(C,\s*name="(mskc_[a-z_0-9]+)"\)', txt)))
+    assert bound == header_symbols()
+
+
 def test_exports(lib):
     for s in header_symbols():
         assert hasattr(lib, s), s
