@@ -1,0 +1,594 @@
+// mulskips_host.cpp -- the host program `mulskips.e` over the C ABI of libmskc.so.
+//
+// Drop-in for the reference executable (mulskips-source/main.f, PROGRAM KLMCSiC3C): run in a directory that
+// holds start.dat, reference-style log on stdout, I########.xyz / _d / _v / _w / .src, movie.mos, fort.30,
+// DefAtEnergy.dat and the optional checkpoint / Coor files in the cwd.  The reference is Fortran; no Fortran
+// compiler exists in this image, so the host side is C++ and keeps main.f's structure: parse start.dat
+// (main.f:83-212, mcevent/SetProbability.f), build the initial geometry with the reference's builders
+// (initial/SetSi.f, SetSiC3C.f, SetNC.f, SetNCSp.f), hand LattCoo + the three particle lists to the GPU library,
+// and drive the KMC loop (main.f:304-371) through mskc_run_parity -- which returns at every output frame so the
+// files are written at the reference's cadence -- or, with --parallel, through the sublattice sampler.
+// The loop body itself (everything under mcevent/ and lattice/) runs in CUDA; nothing here computes events.
+//
+// Box size: a compile-time constant in the reference (modules/defsystem.f:27, rewritten by pymulskips before
+// `make`).  Here: --box X Y Z, else $MSKC_BOX, else the LenX line of <exe dir>/modules/defsystem.f if such a
+// file exists (the file pymulskips edits), else 480 480 480 (the regression suite's size).
+#include "../../include/mskc.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+enum { PosIndex = 0, LenIndex = 8, PosT = 9, LenT = 13, PosOcc = 23, PosCoor = 24, LenCoor = 3, PosSi = 27, PosC = 28, PosSiC = 27, LenSiC = 3 };
+const int JumpDia[8][3] = {{3, 3, 3}, {3, -3, -3}, {-3, -3, 3}, {-3, 3, -3}, {3, 3, -3}, {3, -3, 3}, {-3, -3, -3}, {-3, 3, 3}};   // defsystem.f:104-105
+
+[[noreturn]] void die(const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vfprintf(stdout, fmt, ap); va_end(ap); fputc('\n', stdout); fflush(stdout);
+  exit(1);                                                                   // Fortran STOP after the message
+}
+inline int ibits(int32_t w, int pos, int len) { return (int)(((uint32_t)w >> pos) & ((1u << len) - 1u)); }
+inline void mvbits(int from, int len, int32_t &to, int pos) { uint32_t m = ((1u << len) - 1u) << pos; to = (int32_t)(((uint32_t)to & ~m) | (((uint32_t)from << pos) & m)); }
+inline int idxE(int sp, int i1, int i2, int i3, int i4, int i5, int i6) { return (sp - 1) + 3 * (i1 + 4 * (i2 + 4 * (i3 + 4 * (i4 + 4 * (i5 + 4 * i6))))); }
+
+struct Site { int32_t xyz[3]; int32_t nn[4][3]; };
+struct Active : Site { int32_t ev; double p; };
+
+struct Host {
+  int LX = 480, LY = 480, LZ = 480;
+  // start.dat (modules/definitions.f)
+  int NCrystal = 0, NCov = 0, ListCrystal[3] = {0, 0, 0}, ListCov[3] = {0, 0, 0};
+  std::string InitSt, RunType, ExitStrategy, SaveFinalState, SaveCoo, restartfile, coofile;
+  int Len1 = 0, Len2 = 0, Len3 = 0, Len4 = 0, Idum = 0;
+  double PtransZig = 1.0, sf = 1.0, MaxTime = 0, OutTime = 0, alloy = 0;
+  long long MaxIter = 0, OutMolMol = 0;
+  std::vector<double> PE = std::vector<double>(12288, 0.0), PD = std::vector<double>(9, 0.0), PA = std::vector<double>(12, 0.0), PS = std::vector<double>(12, 0.0);
+  // state built by the initialiser (module globals of defsystem.f)
+  std::vector<int32_t> L;                                  // LattCoo(0:LenX-1,0:LenY-1,0:LenZ)
+  std::vector<Active> mc; std::vector<Site> bulk, voids;
+  std::vector<double> Tree; int Levels = 20;               // init-time rate tree: only Tree(1) is consulted (Get_Prob_Ini.f "isolated atom")
+  int CountCrystal[3] = {0, 0, 0}, CountCrystalOld[3] = {0, 0, 0}, CountCov[3] = {0, 0, 0};
+  // ran3 (mcevent/random.f), SAVEd state
+  int r_iff = 0, r_inext = 0, r_inextp = 0, r_ma[56] = {0};
+
+  size_t ci(int x, int y, int z) const { return (size_t)x + (size_t)LX * ((size_t)y + (size_t)LY * (size_t)z); }
+  int32_t &at(const int32_t p[3]) { return L[ci(p[0], p[1], p[2])]; }
+
+  double ran3() {                                          // random.f:22-69
+    const int mbig = 1000000000, mseed = 161803398, mz = 0;
+    const double fac = (double)(1.0f / 1.0e9f);
+    int mj, mk;
+    if (Idum < 0 || r_iff == 0) {
+      r_iff = 1;
+      mj = mseed - std::abs(Idum); mj %= mbig; r_ma[55] = mj; mk = 1;
+      for (int i = 1; i <= 54; i++) { int ii = (21 * i) % 55; r_ma[ii] = mk; mk = mj - mk; if (mk < mz) mk += mbig; mj = r_ma[ii]; }
+      for (int k = 1; k <= 4; k++) for (int i = 1; i <= 55; i++) { r_ma[i] -= r_ma[1 + (i + 30) % 55]; if (r_ma[i] < mz) r_ma[i] += mbig; }
+      r_inext = 0; r_inextp = 31; Idum = 1;
+    }
+    if (++r_inext == 56) r_inext = 1;
+    if (++r_inextp == 56) r_inextp = 1;
+    mj = r_ma[r_inext] - r_ma[r_inextp];
+    if (mj < mz) mj += mbig;
+    r_ma[r_inext] = mj;
+    return mj * fac;
+  }
+  void update_tree(int index, double p) {                 // UpdateTree.f:49-65
+    size_t pos = (size_t)index + ((size_t)1 << (Levels - 1)) - 1;
+    Tree[pos] = p;
+    for (int l = 1; l < Levels; l++) { size_t nb = pos ^ 1; Tree[pos >> 1] = Tree[pos] + Tree[nb]; pos >>= 1; }
+  }
+  void AddMC(const int32_t s[3], const int32_t nn[4][3], int ev, double p) {    // Add.f:24-53
+    if (p == 0) die(" provo ad aggiungere prob nulla %d %d %d", s[0], s[1], s[2]);
+    Active a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); a.ev = ev; a.p = p;
+    mc.push_back(a);
+    if ((int)mc.size() >= 500000) die(" troppe particelle cinetiche");
+    update_tree((int)mc.size(), p);
+  }
+  void AddBulk(const int32_t s[3], const int32_t nn[4][3]) { Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); bulk.push_back(a); }
+
+  // deposition / adsorption draw of Get_Prob.f:160-179 (pre-drawn species; one ran3 call)
+  void draw_dep_abs(int Coor, bool with_abs, int &ev, double &prob) {
+    double PD1 = PD[0 + 3 * (Coor - 1)], PD2 = PD[1 + 3 * (Coor - 1)], PD3 = PD[2 + 3 * (Coor - 1)];
+    double PDep = PD1 + PD2 + PD3, PAbs = 0;
+    if (with_abs) for (int k = 1; k <= 3; k++) PAbs += PA[(k - 1) + 3 * Coor];
+    double Ptot = PDep + PAbs, Pcurr = ran3() * Ptot;
+    if (Pcurr <= PDep) ev = Pcurr <= PD1 ? 1 : (Pcurr > (PD1 + PD2) ? 3 : 2);
+    else if (NCov == 1) ev = 6;
+    else {
+      ev = 0;
+      for (int i = 1; i <= NCov; i++) {
+        double pmin = PDep, pmax = PDep;
+        for (int k = 1; k <= i - 1; k++) pmin += PA[(k - 1) + 3 * Coor];
+        for (int k = 1; k <= i; k++) pmax += PA[(k - 1) + 3 * Coor];
+        if (Pcurr > pmin && Pcurr <= pmax) ev = 5 + i;
+      }
+    }
+    prob = Ptot;
+  }
+  // mcevent/Get_Prob_Ini.f:23-161 (init-time rating: no reciprocity test, walls / coverage count as N_cov)
+  void get_prob_ini(int Occ, int NSiC, int Coor, const int32_t s[3], const int32_t nn[4][3], int &ev, double &prob) {
+    ev = 0; prob = 0.0;
+    if (Occ == 0) {
+      bool draw = false;
+      if (Coor == 1) { if (ibits(at(nn[0]), PosCoor, LenCoor) >= 2) draw = true; else { ev = 1; prob = (double)1.e-6f; } }
+      else if (Coor == 2 || Coor == 3) draw = true;
+      else if (Coor == 4) printf(" %d Get Prob Vacancy Generation\n", Coor);
+      if (draw) draw_dep_abs(Coor, false, ev, prob);
+      return;
+    }
+    int N_Si = 0, N_C = 0, N_B = 0, N_cov = 0;
+    for (int i = 0; i < 4; i++) {
+      int32_t w = at(nn[i]);
+      if (ibits(w, PosIndex, LenIndex) == 0) { int k = ibits(w, PosSiC, LenSiC); N_Si += (k == 1); N_C += (k == 2); N_B += (k == 3); }
+      else N_cov++;
+    }
+    int n = N_Si + N_C + N_B + N_cov;
+    if (n != Coor) die(" %d %d %d %d %d Get Prob Error N_Si+N_C++N_B+N_cov.NE.Coor", Coor, N_Si, N_C, N_B, N_cov);
+    if (n > 3) return;
+    ev = 4;
+    if (n == 0) { prob = (double)100000.f * Tree[1]; printf(" %d Get Prob Isolated Atom\n", Coor); }
+    else prob = PE[idxE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)];
+    (void)s;
+  }
+};
+
+// ---- start.dat ----------------------------------------------------------------------------------------------------
+struct Lines {
+  FILE *f; char buf[4096];
+  const char *next() {
+    if (!fgets(buf, sizeof buf, f)) die(" start.dat: unexpected end of file");
+    size_t l = strlen(buf); while (l && (buf[l - 1] == '\n' || buf[l - 1] == '\r')) buf[--l] = 0;
+    return buf;
+  }
+};
+std::string first_token(const char *s) {
+  while (*s == ' ' || *s == '\t') s++;
+  std::string t;
+  if (*s == '\'' || *s == '"') { char q = *s++; while (*s && *s != q) t += *s++; }
+  else while (*s && *s != ' ' && *s != '\t' && *s != ',' && *s != '/') t += *s++;
+  return t;
+}
+std::string whole_line(const char *s) { std::string t(s); while (!t.empty() && (t.back() == ' ' || t.back() == '\t')) t.pop_back(); return t; }
+double fnum(const char *s, char **end = nullptr) {          // list-directed REAL: accepts 1.0d0
+  char tmp[128]; size_t i = 0;
+  while (*s == ' ' || *s == '\t' || *s == ',') s++;
+  const char *s0 = s;
+  while (*s && *s != ' ' && *s != '\t' && *s != ',' && *s != '!' && i + 1 < sizeof tmp) { char c = *s++; tmp[i++] = (c == 'd' || c == 'D') ? 'e' : c; }
+  tmp[i] = 0;
+  char *e2; double v = strtod(tmp, &e2);
+  if (end) *end = const_cast<char *>(s0 + (e2 - tmp));
+  return v;
+}
+
+void set_probability(Host &H, Lines &in) {                   // mcevent/SetProbability.f:21-143
+  static const int tab[3][4] = {{3, 9, 19, 34}, {18, 50, 100, 172}, {57, 150, 288, 480}};
+  const int nE = tab[H.NCrystal - 1][H.NCov], nd = H.NCrystal + H.NCov;
+  printf(" maxElines %d\n", nE);
+  for (int i = 0; i < nE; i++) {
+    char *p = const_cast<char *>(in.next());
+    int sp = (int)strtol(p, &p, 10); long el = strtol(p, &p, 10); double v = fnum(p);
+    if (sp > H.NCrystal) die(" ERROR: 1st index in evap prob must be <= NCrystal");
+    int ind[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 1; j <= nd; j++) {
+      long d = 1; for (int k = 0; k < nd - j; k++) d *= 10;
+      int digit = (int)((el / d) % 10);
+      if (digit > 3) die(" ERROR: evaporation index digit > 3");
+      if (j <= H.NCrystal) ind[j - 1] = digit; else ind[3 + j - H.NCrystal - 1] = digit;
+    }
+    H.PE[idxE(sp, ind[0], ind[1], ind[2], ind[3], ind[4], ind[5])] = v;
+  }
+  for (int j = 0; j < 3 * H.NCrystal; j++) {
+    char *p = const_cast<char *>(in.next());
+    int sp = (int)strtol(p, &p, 10), el = (int)strtol(p, &p, 10); double v = fnum(p);
+    if (sp > H.NCrystal || el < 1 || el > 3) die(" ERROR: 1st index in depo prob block must be <= NCrystal");
+    H.PD[(sp - 1) + 3 * (el - 1)] = v;
+  }
+  for (int pass = 0; pass < 2; pass++)
+    for (int j = 0; j < 3 * H.NCov; j++) {
+      char *p = const_cast<char *>(in.next());
+      int sp = (int)strtol(p, &p, 10), el = (int)strtol(p, &p, 10); double v = fnum(p);
+      if (sp <= H.NCrystal || sp > H.NCrystal + H.NCov || el < 0 || el > 3) die(" ERROR: 1st index in abs/des prob block");
+      (pass == 0 ? H.PA : H.PS)[(sp - H.NCrystal - 1) + 3 * el] = v;
+    }
+}
+
+void read_start(Host &H, const char *path) {                 // main.f:83-219
+  Lines in; in.f = fopen(path, "r");
+  if (!in.f) die(" cannot open %s", path);
+  printf(" KMC box size:  %d %d %d\n", H.LX, H.LY, H.LZ);
+  { char *p = const_cast<char *>(in.next()); H.NCrystal = (int)strtol(p, &p, 10); H.NCov = (int)strtol(p, &p, 10); }
+  if (H.NCrystal < 1 || H.NCrystal > 3) die(" ERR NOT IMPLEMENTED: NCrystal must be <= 3");
+  if (H.NCov < 0 || H.NCov > 3) die(" ERR NOT IMPLEMENTED: NCov must be <= 3");
+  { char *p = const_cast<char *>(in.next()); for (int i = 0; i < H.NCrystal; i++) H.ListCrystal[i] = (int)strtol(p, &p, 10); }
+  if (H.NCov > 0) { printf("            ***** Simulating CVD *****\n"); char *p = const_cast<char *>(in.next()); for (int i = 0; i < H.NCov; i++) H.ListCov[i] = (int)strtol(p, &p, 10); }
+  else printf("            ***** Simulating PVD or LA *****\n");
+  printf(" Crystal species (NCrystal= %d ) --> Z:", H.NCrystal); for (int i = 0; i < H.NCrystal; i++) printf(" %d", H.ListCrystal[i]); printf("\n");
+  if (H.NCov > 0) { printf(" Coverage species (NCov= %d ) --> Z:", H.NCov); for (int i = 0; i < H.NCov; i++) printf(" %d", H.ListCov[i]); printf("\n"); }
+  H.InitSt = first_token(in.next()).substr(0, 2);
+  if (H.InitSt == "FF") { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); H.Len4 = (int)strtol(p, &p, 10); }
+  else if (H.InitSt == "IN" || H.InitSt == "SH" || H.InitSt == "LA" || H.InitSt == "ST")
+    die(" mulskips.e (B200 host): InitSt %s is not built yet -- geometry from file / temperature field (see DESIGN.md section 9)", H.InitSt.c_str());
+  else { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); }
+  // main.f:142-149 (the ALL(...) test with NCrystal=1 behaves as "not SiGe", SURVEY 8c trap 5)
+  if ((H.NCrystal == 2 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32) || (H.NCrystal == 3 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32 && H.ListCrystal[2] == 5)) {
+    H.alloy = fnum(in.next()); printf(" Ge fraction in substrate:  %.17g\n", H.alloy);
+  }
+  H.PtransZig = fnum(in.next());
+  H.sf = fnum(in.next());
+  printf(" KMC Super-Lattice parameter (ang):  %.17g\n", H.sf);
+  H.ExitStrategy = first_token(in.next()).substr(0, 4);
+  printf(" Exit strategy: %s\n", H.ExitStrategy.c_str());
+  if (H.ExitStrategy == "Iter") { H.MaxIter = strtoll(in.next(), nullptr, 10); H.OutMolMol = strtoll(in.next(), nullptr, 10); printf(" MaxIter:  %lld\n OutMolMol:  %lld\n", H.MaxIter, H.OutMolMol); }
+  else if (H.ExitStrategy == "Time") { H.MaxTime = fnum(in.next()); H.OutTime = fnum(in.next()); printf(" Total simulation time in seconds:  %.17g\n Output frequency in seconds:  %.17g\n", H.MaxTime, H.OutTime); }
+  else die(" ExitStrategy must be Iter or Time");
+  H.RunType = first_token(in.next()).substr(0, 2);
+  if (H.RunType == "T") printf(" ATTENTION! You are running mulskips in test modality,  that is random numbers are not so random!!\n");
+  H.Idum = (int)strtol(in.next(), nullptr, 10);
+  printf(" IDUM %d\n", H.Idum);
+  H.SaveFinalState = first_token(in.next()).substr(0, 2);
+  if (H.SaveFinalState == "T") { H.restartfile = whole_line(in.next()); printf(" ATTENTION! Storing checkpoint file %s\n This will occupy a lot of disk space...\n", H.restartfile.c_str()); }
+  else printf(" SaveFinalState flag is not \"T\": checkpoint file will  not be written.\n");
+  H.SaveCoo = first_token(in.next()).substr(0, 2);
+  if (H.SaveCoo == "T") { H.coofile = whole_line(in.next()); printf(" ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", H.coofile.c_str()); }
+  else printf(" SaveCoo flag is not \"T\": Coor file not stored\n");
+  set_probability(H, in);
+  fclose(in.f);
+  printf(" numParticelle= %d Levels = %d , SizeTree = %d\n", 500000, 20, (1 << 20) - 1);
+}
+
+// ---- initial geometries -------------------------------------------------------------------------------------------
+bool cubic_site(int x, int y, int z, int &kind) {            // the site test of every builder, e.g. SetSi.f:52-57
+  if (x % 3 || y % 3 || z % 3) return false;
+  int x1 = x / 3, y1 = y / 3, z1 = z / 3;
+  if ((x1 % 2) != (y1 % 2) || (x1 % 2) != (z1 % 2)) return false;
+  int m = (x1 + y1 + z1) % 4;
+  if (m == 0) { kind = 0; return true; }
+  if (m == 3) { kind = 1; return true; }
+  return false;
+}
+void dia_nn(const Host &H, int x, int y, int z, int kind, int32_t nn[4][3]) {
+  for (int i = 0; i < 4; i++) {
+    nn[i][0] = x + JumpDia[i + 4 * kind][0]; nn[i][1] = y + JumpDia[i + 4 * kind][1]; nn[i][2] = z + JumpDia[i + 4 * kind][2];
+    if (nn[i][0] >= H.LX) nn[i][0] -= H.LX;
+    if (nn[i][0] < 0) nn[i][0] += H.LX;
+    if (nn[i][1] >= H.LY) nn[i][1] -= H.LY;
+    if (nn[i][1] < 0) nn[i][1] += H.LY;
+  }
+}
+void wall_planes(Host &H, int z0, int z1) {
+  for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << PosOcc; mvbits(113, LenIndex, w, PosIndex); }
+}
+// initial/SetSi.f:25-221 (walls, one species) and initial/SetSiC3C.f:25-199 (no walls, Si/C): flat (001) slab
+void set_flat(Host &H, int Len, bool walls, bool two_species) {
+  int32_t s[3], nn[4][3]; int kind;
+  if (walls) wall_planes(H, 0, 5);
+  auto scan = [&](int z0, int z1, auto &&fn) {
+    for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++)
+      if (cubic_site(x, y, z, kind)) { s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); fn(H.L[H.ci(x, y, z)], (kind && two_species) ? 2 : 1); }
+  };
+  scan(walls ? 6 : 0, Len - 4, [&](int32_t &w, int sp) { w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(4, LenCoor, w, PosCoor); H.AddBulk(s, nn); });
+  scan(Len - 3, Len - 1, [&](int32_t &w, int sp) { w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(2, LenCoor, w, PosCoor); H.AddMC(s, nn, 4, H.PE[idxE(sp, 2, 0, 0, 0, 0, 0)]); });
+  scan(Len, Len, [&](int32_t &w, int) { mvbits(2, LenCoor, w, PosCoor); int ev; double p; H.draw_dep_abs(2, true, ev, p); H.AddMC(s, nn, ev, p); });   // Get_Prob(0,0,0,2,..)
+  if (walls) wall_planes(H, H.LZ - 6, H.LZ - 1);
+}
+// "Set the coordination" / "Set the probability" passes of SetNC.f:60-233 (shared by SetNCSp.f)
+void pass_coordination(Host &H, int z0, int z1, int y0, int y1, int x0, int x1) {
+  int32_t nn[4][3]; int kind;
+  for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+    if (!cubic_site(x, y, z, kind)) continue;
+    int32_t &w = H.L[H.ci(x, y, z)];
+    int Occ = ibits(w, PosOcc, 1), Coor = 0;
+    dia_nn(H, x, y, z, kind, nn);
+    for (int i = 0; i < 4; i++) if (ibits(H.at(nn[i]), PosOcc, 1) > 0) Coor++;
+    if (Occ != 0 && Coor == 0) {
+      w = 0;
+      for (int i = 0; i < 4; i++) { int32_t &wn = H.at(nn[i]); int c = ibits(wn, PosCoor, LenCoor) - 1; if (c < 0) c = 0; mvbits(c, LenCoor, wn, PosCoor); }
+    } else mvbits(Coor, LenCoor, w, PosCoor);
+  }
+}
+void pass_probability(Host &H, int z0, int z1, int y0, int y1, int x0, int x1) {
+  int32_t s[3], nn[4][3], keep[3] = {0, 0, 0}; int kind, ev; double p;
+  for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
+    if (!cubic_site(x, y, z, kind)) continue;
+    int32_t w = H.L[H.ci(x, y, z)];
+    s[0] = x; s[1] = y; s[2] = z;
+    dia_nn(H, x, y, z, kind, nn);
+    int Occ = ibits(w, PosOcc, 1), Coor = ibits(w, PosCoor, LenCoor);
+    if (Occ != 0 && Coor == 0) printf(" error %d %d %d %d %d\n", x, y, z, Occ, Coor);
+    if (Occ == 0) {
+      if (Coor > 0) {
+        if (Coor == 1) {                                     // keep the single occupied neighbour in slot 1 (SetNC.f:166-185)
+          for (int i = 0; i < 4; i++) { if (ibits(H.at(nn[i]), PosOcc, 1) != 0) memcpy(keep, nn[i], 12); nn[i][0] = nn[i][1] = nn[i][2] = 0; }
+          memcpy(nn[0], keep, 12);
+        }
+        H.get_prob_ini(0, 0, Coor, s, nn, ev, p);
+        H.AddMC(s, nn, ev, p);
+      }
+    } else if (Coor <= 3) { H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
+    else H.AddBulk(s, nn);
+  }
+}
+// initial/SetNC.f:25-235 (parallelepiped) and initial/SetNCSp.f (sphere) of 3C-SiC in the box centre
+void set_nc(Host &H, int Len1, int Len2, int Len3, bool sphere) {
+  int kind, LX = H.LX, LY = H.LY, LZ = H.LZ;
+  if (!sphere) { printf(" %d %d\n", LZ / 2 - Len3 / 2, LZ / 2 + Len3 / 2 + 1); printf(" %d %d\n", LX / 2 - Len1 / 2, LX / 2 + Len1 / 2 + 1); }
+  for (int z = LZ / 2 - Len3 / 2; z <= LZ / 2 + Len3 / 2 - 1; z++)
+    for (int y = LY / 2 - Len2 / 2; y <= LY / 2 + Len2 / 2 - 1; y++)
+      for (int x = LX / 2 - Len1 / 2; x <= LX / 2 + Len1 / 2 - 1; x++) {
+        if (sphere && (x - LX / 2) * (x - LX / 2) + (y - LY / 2) * (y - LY / 2) + (z - LZ / 2) * (z - LZ / 2) > Len1 * Len1 / 4) continue;
+        if (cubic_site(x, y, z, kind)) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << (kind ? PosC : PosSi); w |= 1 << PosOcc; }
+      }
+  const int z0 = LZ / 2 - Len3 / 2 - 10, z1 = LZ / 2 + Len3 / 2 + 9, y0 = LY / 2 - Len2 / 2 - 10, y1 = LY / 2 + Len2 / 2 + 9, x0 = LX / 2 - Len1 / 2 - 10, x1 = LX / 2 + Len1 / 2 + 9;
+  pass_coordination(H, z0, z1, y0, y1, x0, x1);
+  pass_probability(H, z0, z1, y0, y1, x0, x1);
+}
+
+// ---- output (inpout/WriteMolMolSource.f, WriteMolMolXYZFile.f, GetOutputFileName.f) ---------------------------------
+void e15_8(double v, char out[32]) {                         // Fortran E15.8: 0.dddddddd E+xx
+  if (v == 0.0) { strcpy(out, " 0.00000000E+00"); return; }
+  char t[40]; snprintf(t, sizeof t, "%.7e", fabs(v));
+  char dig[16]; dig[0] = t[0]; memcpy(dig + 1, t + 2, 7); dig[8] = 0;
+  int ex = atoi(strchr(t, 'e') + 1) + 1;
+  char body[32];
+  if (abs(ex) < 100) snprintf(body, sizeof body, "%s0.%sE%c%02d", v < 0 ? "-" : "", dig, ex < 0 ? '-' : '+', abs(ex));
+  else snprintf(body, sizeof body, "%s0.%s%c%03d", v < 0 ? "-" : "", dig, ex < 0 ? '-' : '+', abs(ex));
+  snprintf(out, 32, "%15s", body);
+}
+void atom_line(FILE *f, const char *el, double sf, int x, int y, int z, const char *tail) { fprintf(f, "%s%10.5f %10.5f %10.5f%s\n", el, sf * x, sf * y, sf * z, tail); }
+
+struct Run { mskc_ctx *h = nullptr; long long Iter = 1, IterOut = 0, framecounter = 0; double Time = 0; int NumAtoms = 0, NumVoids = 0, NumAdAtom = 0; };
+
+#define MS(call) do { if ((call) != 0) die(" %s", mskc_last_error(R.h)); } while (0)
+
+void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, bool on_device) {
+  const int LX = H.LX, LY = H.LY, LZ = H.LZ; const double sf = H.sf;
+  const bool sic = H.NCrystal == 2 && (H.ListCrystal[0] == 6 || H.ListCrystal[1] == 6);
+  std::vector<Site> voids;
+  if (on_device) {                                           // the module globals the writers read, from the device
+    MS(mskc_download_lattice(R.h, H.L.data()));
+    mskc_counters c; MS(mskc_get_counters(R.h, &c));
+    for (int i = 0; i < 3; i++) { H.CountCrystal[i] = c.CountCrystal[i]; H.CountCov[i] = c.CountCov[i]; }
+    voids.resize((size_t)std::max(c.num_voids, 0));
+    if (!voids.empty()) {
+      std::vector<int32_t> vx(3 * voids.size()), vn(12 * voids.size());
+      MS(mskc_download_lists(R.h, nullptr, nullptr, nullptr, nullptr, vx.data(), vn.data(), nullptr, nullptr, 0, nullptr));
+      for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
+    }
+  } else voids = H.voids;
+  if (Iter != 0) {                                           // WriteMolMolSource.f:42-56
+    int s = 0, so = 0; for (int i = 0; i < 3; i++) { s += H.CountCrystal[i]; so += H.CountCrystalOld[i]; }
+    printf(" SUM(CountCrystal) %d\n CountCrystal %d %d %d\n CountCrystalOld %d %d %d\n", s, H.CountCrystal[0], H.CountCrystal[1], H.CountCrystal[2], H.CountCrystalOld[0], H.CountCrystalOld[1], H.CountCrystalOld[2]);
+    float d[3]; for (int i = 0; i < 3; i++) d[i] = (float)(H.CountCrystal[i] - H.CountCrystalOld[i]);
+    printf(" diff %.9g %.9g %.9g\n", d[0], d[1], d[2]);
+    printf(" xGesolid %.17g %.17g %.17g\n", (double)d[0] / (s - so), (double)d[1] / (s - so), (double)d[2] / (s - so));
+    for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
+    if (H.NCov != 0) printf(" CountCov %d %d %d\n", H.CountCov[0], H.CountCov[1], H.CountCov[2]);
+  }
+  if (Iout * 10 >= 1000000000) die(" GetOutputFileName:: Iter can not be represented");
+  char base[64]; snprintf(base, sizeof base, "I%08lld", Iout);
+  printf(" %s\n", base);
+  int NumAtTotal = 0, NumCovTotal = 0, NoEpiBulk = 0, kind;
+  for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          // WriteMolMolXYZFile.f:77-92
+    int32_t w = H.L[H.ci(x, y, z)]; if (w == 0) continue;
+    int cov = ibits(w, PosIndex, LenIndex);
+    if (cov != 113) { int occ = ibits(w, PosOcc, 1), coo = ibits(w, PosCoor, LenCoor); if (occ == 1 && coo <= 3) NumAtTotal++; else if (occ == 0 && cov != 0) NumCovTotal++; }
+  }
+  auto is_noepi = [&](int32_t w, int x, int y, int z) { return ibits(w, PosOcc, 1) == 1 && ibits(w, PosCoor, LenCoor) == 4 && !cubic_site(x, y, z, kind); };
+  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) { int32_t w = H.L[H.ci(x, y, z)]; if (w && is_noepi(w, x, y, z)) NoEpiBulk++; }   // :95-119
+  printf(" %d\n", NoEpiBulk);
+  char e1[32], e2[32], e3[32], et[32], path[128];
+  e15_8(sf * (double)LX, e1); e15_8(sf * (double)LY, e2); e15_8(sf * (double)LZ, e3); e15_8(Time, et);
+  snprintf(path, sizeof path, "%s_d.xyz", base); FILE *fd = fopen(path, "w");
+  snprintf(path, sizeof path, "%s.xyz", base); FILE *fx = fopen(path, "w");
+  snprintf(path, sizeof path, "%s_v.xyz", base); FILE *fv = fopen(path, "w");
+  if (!fd || !fx || !fv) die(" cannot open output files in the working directory");
+  fprintf(fd, " %8d angstroem KMC-time: %s Iter: %12lld\n periodic %s %s %s\n", NoEpiBulk, et, Iter, e1, e2, e3);         // :125-159
+  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t w = H.L[H.ci(x, y, z)];
+    if (w && is_noepi(w, x, y, z)) { int a = ibits(w, PosSiC, LenSiC); if (a == 1) atom_line(fd, "Ge ", sf, x, y, z, "  "); if (a == 2) atom_line(fd, "B ", sf, x, y, z, "  "); if (a == 3) atom_line(fd, "Cl ", sf, x, y, z, "  "); }
+  }
+  fprintf(fx, " %8d angstroem KMC-time: %s Iter: %12lld\n periodic %s %s %s\n", NumAtTotal + (int)voids.size() + NumCovTotal, et, Iter, e1, e2, e3);   // :163-221
+  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t w = H.L[H.ci(x, y, z)]; if (w == 0) continue;
+    int a = ibits(w, PosSiC, LenSiC), coo = ibits(w, PosCoor, LenCoor), cov = ibits(w, PosIndex, LenIndex);
+    if (cov == 1) atom_line(fx, "H ", sf, x, y, z, "  ");
+    if (cov == 17) atom_line(fx, "Cl ", sf, x, y, z, "  ");
+    if (a == 1 && coo <= 3) atom_line(fx, "Si ", sf, x, y, z, "  ");
+    if ((a == 2 || a == 3) && coo <= 3) {
+      if (H.NCrystal < a) die(" ERR: IAt=%d should not happen, NCrystal=%d", a, H.NCrystal);
+      int Z = H.ListCrystal[a - 1]; const char *el = Z == 6 ? "C " : Z == 32 ? "Ge " : Z == 5 ? "B " : nullptr;
+      if (!el) die(" ERROR: 2nd crystal specie can only be C/Ge/B");
+      atom_line(fx, el, sf, x, y, z, "  ");
+    }
+  }
+  for (auto &v : voids) atom_line(fx, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
+  fprintf(fv, " %8d angstroem\n periodic %s %s %s\n", (int)voids.size(), e1, e2, e3);                                     // :228-260
+  for (auto &v : voids) {
+    if (H.NCov == 0 && H.NCrystal == 2 && H.ListCrystal[1] == 6) {
+      int a = 0; for (int j = 0; j < 4; j++) a += ibits(H.at(v.nn[j]), PosSiC, LenSiC);
+      const char *el = a == 4 ? "Mg " : a == 8 ? "He " : a == 7 ? "Ne " : a == 5 ? "Be " : a == 6 ? "Ar " : nullptr;
+      const char *tail = a == 4 ? " # CV (C vacancy)" : a == 8 ? " # SV (Si vacancy)" : a == 7 ? " # SAV (Si antisite vac)" : a == 5 ? " # CAV (C antisite vac)" : " # XV (near 2C and 2Si)";
+      if (!el) die(" ERROR: Weird Defect type was formed...ABORTING");
+      atom_line(fv, el, sf, v.xyz[0], v.xyz[1], v.xyz[2], tail);
+    } else atom_line(fv, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
+  }
+  fclose(fd); fclose(fx); fclose(fv);
+  if (sic) {                                                 // :267-398 antisite pass; it flips species bits in LattCoo and restores them with the LAST entry's type (:386)
+    std::vector<int32_t> bx; std::vector<size_t> bcell;
+    for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      int32_t w = H.L[H.ci(x, y, z)];
+      if (w == 0 || ibits(w, PosIndex, LenIndex) == 113) continue;
+      if (ibits(w, PosOcc, 1) == 1 && ibits(w, PosCoor, LenCoor) == 4) { bx.push_back(x); bx.push_back(y); bx.push_back(z); bcell.push_back(H.ci(x, y, z)); }
+    }
+    std::vector<int32_t> bnn(12 * bcell.size() + 12);
+    if (on_device) { if (!bcell.empty()) MS(mskc_download_bonds(R.h, (int64_t)bcell.size(), bx.data(), bnn.data())); }
+    else {                                        // frame 0: bonds of the bulk list the builder made (z,y,x scan order is not its order: look up by cell)
+      std::vector<uint32_t> idx(H.L.size(), 0xFFFFFFFFu);
+      for (size_t i = 0; i < H.bulk.size(); i++) idx[H.ci(H.bulk[i].xyz[0], H.bulk[i].xyz[1], H.bulk[i].xyz[2])] = (uint32_t)i;
+      for (size_t i = 0; i < bcell.size(); i++) { uint32_t k = idx[bcell[i]]; if (k != 0xFFFFFFFFu) memcpy(&bnn[12 * i], H.bulk[k].nn, 48); else memset(&bnn[12 * i], 0, 48); }
+    }
+    auto ncorr = [&](size_t i) {                              // neighbours of the OTHER species
+      int32_t w = H.L[bcell[i]]; int a = ibits(w, PosSiC, LenSiC), n = 0;
+      const int32_t *nn = &bnn[12 * i];
+      if (a == 1) for (int j = 0; j < 4; j++) n += ibits(H.L[H.ci(nn[3 * j], nn[3 * j + 1], nn[3 * j + 2])], PosC, 1);
+      else if (a == 2) for (int j = 0; j < 4; j++) n += ibits(H.L[H.ci(nn[3 * j], nn[3 * j + 1], nn[3 * j + 2])], PosSi, 1);
+      return n;
+    };
+    std::vector<size_t> wrong; std::vector<int> wtype;
+    for (size_t i = 0; i < bcell.size(); i++)
+      if (ncorr(i) == 0) {
+        int32_t &w = H.L[bcell[i]]; int a = ibits(w, PosSiC, LenSiC);
+        if (a == 1) { w &= ~(1 << PosSi); w |= 1 << PosC; wtype.push_back(1); } else { w &= ~(1 << PosC); w |= 1 << PosSi; wtype.push_back(2); }
+        wrong.push_back(bcell[i]);
+      }
+    int NumAtWrong = 0;
+    for (size_t i = 0; i < bcell.size(); i++) if (ncorr(i) == 3) NumAtWrong++;
+    printf(" NumAtWrong:  %d\n", NumAtWrong);
+    snprintf(path, sizeof path, "%s_w.xyz", base); FILE *fw = fopen(path, "w");
+    if (fw) {
+      fprintf(fw, " %8d angstroem\n periodic %s %s %s\n", NumAtWrong, e1, e2, e3);
+      for (size_t i = 0; i < bcell.size(); i++) if (ncorr(i) == 3) { int a = ibits(H.L[bcell[i]], PosSiC, LenSiC); if (a == 1) atom_line(fw, "Si ", sf, bx[3 * i], bx[3 * i + 1], bx[3 * i + 2], "  "); if (a == 2) atom_line(fw, "C ", sf, bx[3 * i], bx[3 * i + 1], bx[3 * i + 2], "  "); }
+      fclose(fw);
+    }
+    std::vector<int64_t> pc; std::vector<int32_t> pw;
+    for (size_t i = 0; i < wrong.size(); i++) {
+      int32_t &w = H.L[wrong[i]]; int ty = wtype.back();
+      if (ty == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; }
+      pc.push_back((int64_t)wrong[i]); pw.push_back(w);
+    }
+    if (on_device && !pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));      // the device lattice sees what the reference's LattCoo would hold
+  }
+  FILE *f;                                                   // WriteMolMolSource.f:77-112 side files
+  if ((f = fopen("fort.30", "a"))) { fprintf(f, " %.17g\n", Time); fclose(f); }
+  snprintf(path, sizeof path, "%s.src", base);
+  if ((f = fopen(path, "w"))) { fprintf(f, " load xyz %s.xyz\n color temperature\n set background white\n set boundbox true\n zoom 140\n rotate x 41\n rotate y 4\n spacefill 2\n color axes black\n wireframe 2\n color atom green\n wireframe 12\n color atom purple\n set bondmode and\n", base); fclose(f); }
+  if ((f = fopen("movie.mos", Iter == 0 ? "w" : "a"))) { fprintf(f, " source    %s.src\n write gif %s.gif\n zap\n", base, base); fclose(f); }
+  if ((f = fopen("DefAtEnergy.dat", Iter == 0 ? "w" : "a"))) { fprintf(f, " \n"); fclose(f); }
+  fflush(stdout);
+}
+
+bool box_from_defsystem(const char *exe, int box[3]) {      // the line pymulskips rewrites: "INTEGER, PARAMETER :: LenX=480, LenY=480, LenZ=480"
+  std::string p(exe); size_t k = p.find_last_of('/'); p = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/modules/defsystem.f";
+  FILE *f = fopen(p.c_str(), "r"); if (!f) return false;
+  char line[1024]; bool ok = false;
+  while (fgets(line, sizeof line, f)) {
+    const char *a = strstr(line, "LenX="), *b = strstr(line, "LenY="), *c = strstr(line, "LenZ=");
+    if (strstr(line, "PARAMETER") && a && b && c) { box[0] = atoi(a + 5); box[1] = atoi(b + 5); box[2] = atoi(c + 5); ok = true; break; }
+  }
+  fclose(f); return ok;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Host H; Run R;
+  int box[3] = {480, 480, 480}; bool parallel = false; double ept = 4.0; int device = 0; const char *start = "start.dat";
+  bool have_box = false;
+  for (int i = 1; i < argc; i++) {
+    if (!strcmp(argv[i], "--box") && i + 3 < argc) { box[0] = atoi(argv[i + 1]); box[1] = atoi(argv[i + 2]); box[2] = atoi(argv[i + 3]); i += 3; have_box = true; }
+    else if (!strcmp(argv[i], "--parallel")) parallel = true;
+    else if (!strcmp(argv[i], "--events-per-tile") && i + 1 < argc) ept = atof(argv[++i]);
+    else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--device d] [--start file]\n", argv[0]); return 2; }
+  }
+  if (!have_box) { if (const char *e = getenv("MSKC_BOX")) have_box = sscanf(e, "%d %d %d", &box[0], &box[1], &box[2]) == 3; }
+  if (!have_box) box_from_defsystem(argv[0], box);
+  H.LX = box[0]; H.LY = box[1]; H.LZ = box[2];
+  read_start(H, start);
+  H.L.assign((size_t)H.LX * H.LY * (H.LZ + 1), 0);
+  H.Tree.assign((size_t)1 << H.Levels, 0.0);
+  // main.f:225-295
+  if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
+  else if (H.InitSt == "FS") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false); }
+  else if (H.InitSt == "C") set_nc(H, H.Len1, H.Len2, H.Len3, false);
+  else if (H.InitSt == "S") set_nc(H, H.Len1, H.Len1, H.Len1, true);
+  else die(" mulskips.e (B200 host): InitSt %s is not built yet (built: F, FS, C, S; see DESIGN.md section 9)", H.InitSt.c_str());
+  R.NumAtoms = (int)H.bulk.size(); R.NumVoids = 0; R.NumAdAtom = (int)H.mc.size();
+  printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+  write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
+  // ---- hand the state to the GPU (include/mskc.h) ----
+  if (mskc_create(H.LX, H.LY, H.LZ, H.NCrystal, H.NCov, H.ListCrystal, H.ListCov, device, 0, &R.h) != 0) die(" %s", mskc_last_error(nullptr));
+  MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
+  {
+    std::vector<int32_t> mx(3 * H.mc.size() + 3), mn(12 * H.mc.size() + 12), me(H.mc.size() + 1), bx(3 * H.bulk.size() + 3), bn(12 * H.bulk.size() + 12), vx(3), vn(12);
+    std::vector<double> mr(H.mc.size() + 1);
+    for (size_t i = 0; i < H.mc.size(); i++) { memcpy(&mx[3 * i], H.mc[i].xyz, 12); memcpy(&mn[12 * i], H.mc[i].nn, 48); me[i] = H.mc[i].ev; mr[i] = H.mc[i].p; }
+    for (size_t i = 0; i < H.bulk.size(); i++) { memcpy(&bx[3 * i], H.bulk[i].xyz, 12); memcpy(&bn[12 * i], H.bulk[i].nn, 48); }
+    int32_t st[58]; st[0] = H.r_iff; st[1] = H.r_inext; st[2] = H.r_inextp; for (int i = 1; i <= 55; i++) st[2 + i] = H.r_ma[i];
+    MS(mskc_seed(R.h, H.Idum, H.RunType[0], 0, st));
+    MS(mskc_upload_state(R.h, H.L.data(), (int)H.mc.size(), mx.data(), mn.data(), me.data(), mr.data(), (int)H.bulk.size(), bx.data(), bn.data(), 0, vx.data(), vn.data()));
+    MS(mskc_set_clock(R.h, 1, 0.0, H.CountCrystal, H.CountCov));
+  }
+  std::vector<Active>().swap(H.mc); std::vector<Site>().swap(H.bulk);
+  const bool by_time = H.ExitStrategy == "Time";
+  float dev_ms = 0; long long events = 0;
+  if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
+    mskc_parity_args a{}; mskc_parity_result r{};
+    a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;
+    while (true) {
+      a.framecounter = R.framecounter;
+      if (mskc_run_parity(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
+      R.Iter = r.iter; R.IterOut = r.iter_out; R.Time = r.time; R.NumAtoms = r.num_atoms; R.NumVoids = r.num_voids; R.NumAdAtom = r.num_adatom;
+      dev_ms += r.kernel_ms; events += r.events_done;
+      if (r.stop_reason == MSKC_STOP_FEWMC) { printf(" few MC particles: stop MC %lld %d\n", R.Iter, R.NumAdAtom); break; }
+      if (r.stop_reason == MSKC_STOP_FRAME) {                 // main.f:316-333
+        if (!by_time) R.framecounter = R.IterOut / H.OutMolMol;
+        write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter + 1 : R.framecounter, true);
+        printf(" Iter, Time, Site %lld %.17g %d %d %d\n", R.Iter, R.Time, r.last_site[0], r.last_site[1], r.last_site[2]);
+        printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+        if (by_time) R.framecounter++;
+        continue;
+      }
+      break;                                                  // MaxIter / MaxTime
+    }
+  } else {                                                    // production mode: synchronous-sublattice sampler, frames at the same cadence
+    mskc_parallel_args a{}; mskc_parallel_result r{};
+    a.events_per_tile = ept; a.seed = (uint64_t)(H.Idum < 0 ? -H.Idum : H.Idum); a.n_sweeps = 8;
+    long long next_out = H.OutMolMol; double next_t = H.OutTime;
+    while (true) {
+      if (mskc_run_parallel(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
+      events += r.events_done; dev_ms += r.kernel_ms; R.Time = r.time; R.Iter = events + 1; R.IterOut = events;
+      mskc_counters c; MS(mskc_get_counters(R.h, &c)); R.NumAtoms = c.num_atoms; R.NumVoids = c.num_voids; R.NumAdAtom = c.num_adatom;
+      if (r.n_active <= 20) { printf(" few MC particles: stop MC %lld %d\n", R.Iter, (int)r.n_active); break; }
+      bool frame = by_time ? (H.OutTime > 0 && R.Time >= next_t) : (H.OutMolMol > 0 && events >= next_out);
+      if (frame) {
+        R.framecounter++;
+        write_frame(H, R, R.Time, R.IterOut, R.framecounter, true);
+        printf(" Iter, Time, Site %lld %.17g %d %d %d\n", R.Iter, R.Time, 0, 0, 0);
+        printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+        next_out += H.OutMolMol; next_t += H.OutTime;
+      }
+      if (by_time ? R.Time > H.MaxTime : events >= H.MaxIter) break;
+    }
+  }
+  // main.f:374-430: final frame, checkpoint, Coor
+  write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter : (H.OutMolMol > 0 ? R.IterOut / H.OutMolMol : 0), true);
+  if (H.SaveFinalState == "T") {
+    printf(" Writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
+    if (FILE *f = fopen(H.restartfile.c_str(), "w")) {
+      for (int z = 0; z < H.LZ; z++) { for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) fprintf(f, " %11d", H.L[H.ci(x, y, z)]); fputc('\n', f); }
+      fclose(f);
+    }
+    printf(" Done writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
+  }
+  if (H.SaveCoo == "T") {
+    printf(" Writing Coor (LA phases) file %s\n", H.coofile.c_str());
+    if (FILE *f = fopen(H.coofile.c_str(), "w")) {
+      for (int z = 0; z < H.LZ; z++) {
+        for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) { int32_t w = H.L[H.ci(x, y, z)]; int v = ibits(w, PosIndex, LenIndex) == 113 ? 10 : (ibits(w, PosOcc, 1) == 1 ? ibits(w, PosCoor, LenCoor) : 0); fprintf(f, "%4d", v); }
+        fputc('\n', f);
+      }
+      fclose(f);
+    }
+    printf(" Done writing Coor (LA phases) file %s\n", H.coofile.c_str());
+  }
+  fprintf(stderr, "mulskips.e (B200): %lld events, %.1f ms on the device = %.4g events/s (%s mode)\n", events, dev_ms, dev_ms > 0 ? events / (dev_ms * 1e-3) : 0.0, parallel ? "sublattice-sampler" : "serial-parity");
+  mskc_destroy(R.h);
+  return 0;
+}

@@ -1,0 +1,78 @@
+"""The reference's own regression procedure (regression-tests/regression-tests.ipynb) on the B200 host program:
+copy a start.dat into an empty directory, run `mulskips.e | tee log.txt` at the suite's 480^3 box, compare
+I00000000.xyz, I00000001.xyz and the numeric log tokens.
+
+mulskips_b200/bin/mulskips.e is the C++ host over the C ABI with the event loop on the GPU in serial-parity
+mode.  Default: MaxIter cut to 2e5 events and the CPU oracle's command line run on the same start.dat as the
+checker (frames byte-identical, log tokens equal, Time bit-equal) -- the oracle itself is pinned on the full
+goldens by tests/test_oracle_golden.py.  MSKC_FULL_GOLDEN=1: the unmodified start files (1e7 events, ~4 min
+of GPU each at the serial kernel's 4.6e4 events/s) against the reference goldens' sha256 in
+tests/golden/manifest.json; the last full run is recorded in profiles/r01_host_full_goldens.txt."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from cases import GOLDEN, make_start, start_path
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "mulskips_b200", "bin", "mulskips.e")
+ORACLE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
+MAN = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+CASES = ["Si-SL", "surface", "cube", "cube-zigzag", "sphere", "CVD-Si-SiH2"]      # InitSt FS, F, C, C (PtransZig 0.8), S, FS + coverage
+FULL = os.environ.get("MSKC_FULL_GOLDEN") == "1"
+NEV = 200000
+
+
+def _tokens(log, key):
+    for line in open(log):
+        if line.strip().startswith(key):
+            return line.split()
+    return None
+
+
+def _run(exe, d, args=()):
+    with open(d / "log.txt", "w") as out, open(d / "err.txt", "w") as err:
+        rc = subprocess.run([exe, *args], cwd=d, stdout=out, stderr=err).returncode
+    assert rc == 0, open(d / "log.txt").read()[-1500:] + open(d / "err.txt").read()[-1500:]
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not (os.path.exists(EXE) and os.path.exists(ORACLE)):
+        import __graft_entry__ as g
+        g.build()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_regression_case(built, tmp_path, case):
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    if FULL:
+        with open(start_path(case)) as f:
+            (g / "start.dat").write_text(f.read())
+    else:       # CVD-Si-SiH2 exits on KMC time: 0.5 s of it is ~2e5 events
+        make_start(case, str(g / "start.dat"), maxiter=NEV, outmolmol=NEV, maxtime=0.5, outtime=0.5)
+        (o / "start.dat").write_text((g / "start.dat").read_text())
+        _run(ORACLE, o)
+    _run(EXE, g)
+    if FULL:
+        m = MAN[case]
+        for k in (0, 1):
+            b = open(g / f"I0000000{k}.xyz", "rb").read()
+            assert hashlib.sha256(b).hexdigest() == m[f"frame{k}_sha256"], f"{case} frame {k} differs from the reference golden"
+        t = _tokens(g / "log.txt", "Iter, Time, Site")
+        assert int(t[3]) == m["final_iter"] and [int(v) for v in t[5:8]] == m["final_site"] and float(t[4]) == float(m["final_time"])
+        assert [int(v) for v in _tokens(g / "log.txt", "NatNvoidNad")[1:4]] == m["final_lists"]
+        return
+    for name in ("I00000000.xyz", "I00000001.xyz", "I00000000_d.xyz", "I00000001_d.xyz", "I00000000_v.xyz", "I00000001_v.xyz"):
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"{case}: {name} differs from the oracle's"
+    if (o / "I00000001_w.xyz").exists():
+        assert (g / "I00000001_w.xyz").read_bytes() == (o / "I00000001_w.xyz").read_bytes()
+    assert hashlib.sha256((g / "I00000000.xyz").read_bytes()).hexdigest() == MAN[case]["frame0_sha256"]      # frame 0 is the reference golden itself
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "NumAtWrong:"):
+        assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
+    assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
