@@ -215,23 +215,28 @@ def run_ours(args):
                 "note": "latency/instruction-issue bound: the touched surface set is L2-resident, DRAM traffic << algorithmic bytes (see DESIGN.md)"}
 
     # ---- end to end through the C ABI with HOST buffers ------------------------------------------
-    # Per step: H2D of the per-cell input field the reference receives each cycle (SetT.f / the LA socket's
-    # SENDFIELD: int32 [LenZ][LenY*LenX]) from pinned memory, the sweeps, and D2H of the whole lattice
-    # (what WriteMolMolXYZFile / GETPHASES read).
-    ncell_T = lx * by * bz
-    T_host = torch.full((ncell_T,), 1000, dtype=torch.int32).pin_memory()
-    L_host = torch.empty(((bz + 1) * by * lx,), dtype=torch.int32).pin_memory()
-    i32p = C.POINTER(C.c_int32)
-    Tp, Lp = C.cast(T_host.data_ptr(), i32p), C.cast(L_host.data_ptr(), i32p)
+    # One step of what the host program does between two output frames of a PVD/CVD run: (H2D) the step's inputs --
+    # the four rate tables (pymulskips rewrites them per run / per coupled cycle), from pinned memory through
+    # mskc_set_rates; the sweeps; (D2H) the step's result -- the frame: every cell WriteMolMolXYZFile.f prints
+    # (surface atoms, coverage, non-epitaxial bulk), compacted on the device by mskc_extract_frame into pinned memory.
+    u32p, f64p = C.POINTER(C.c_uint32), C.POINTER(C.c_double)
+    tab = torch.from_numpy(np.concatenate([w["PtransE"].ravel(), w["PtransD"].ravel(), w["PtransAbs"].ravel(), w["PtransDes"].ravel()]).astype(np.float64)).pin_memory()
+    tp = tab.data_ptr()
+    fcap = 16 * 1024 * 1024
+    fcell, fword = torch.empty(fcap, dtype=torch.int32).pin_memory(), torch.empty(fcap, dtype=torch.int32).pin_memory()
+    fn, fms = C.c_int64(), C.c_float()
     fresh()
+    frame_ms = []
 
     def e2e_step(i):
-        ctx._ck(ctx.lib.mskc_set_temperature(ctx.h, Tp))
+        ctx._ck(ctx.lib.mskc_set_rates(ctx.h, C.cast(tp, f64p), C.cast(tp + 8 * 12288, f64p), C.cast(tp + 8 * (12288 + 9), f64p), C.cast(tp + 8 * (12288 + 21), f64p), w["PtransZig"]))
         rr_ = ctx.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 5000 + i)
-        ctx._ck(ctx.lib.mskc_download_lattice(ctx.h, Lp))
+        ctx._ck(ctx.lib.mskc_extract_frame(ctx.h, fcap, C.cast(fcell.data_ptr(), u32p), C.cast(fword.data_ptr(), u32p), C.byref(fn), C.byref(fms)))
+        frame_ms.append(fms.value)
         return rr_.events_done
     for i in range(min(args.warmup, 2)):
         e2e_step(i)
+    frame_ms.clear()
     barrier()
     t2 = time.perf_counter()
     ev2 = 0
@@ -239,7 +244,33 @@ def run_ours(args):
         ev2 += e2e_step(10 + i)
     barrier()
     t3 = time.perf_counter()
-    occ = int(((L_host[:: 4097] >> 23) & 1).sum())       # touch the result
+    nrec = min(int(fn.value), fcap)
+    occ = int(((fword[:nrec] >> 23) & 1).sum())          # touch the result
+    h2d_step, d2h_step = 8 * (12288 + 9 + 12 + 12), 8 * nrec
+    fms_avg = sum(frame_ms) / max(len(frame_ms), 1)
+    dense = {"kernel": "frame_extract_kernel", "bound": "hbm", "algorithmic_bytes_per_launch": 4 * (bz + 1) * by * lx, "launch_ms": fms_avg,
+             "achieved": 4 * (bz + 1) * by * lx / (fms_avg * 1e-3) / 1e9 if fms_avg > 0 else 0.0, "unit": "GB/s"}
+    dense["peak"], _ = peaks(); dense["frac"] = dense["achieved"] / dense["peak"]
+
+    # ---- the laser-annealing coupling cycle, for reference (3 steps): per-cell int32 temperature field up
+    # (SetT.f / the socket's SENDFIELD), sweeps, whole lattice down (GETPHASES) -----------------------------------
+    la_cycle = None
+    if world == 1 and not args.no_la_cycle:
+        ncell_T = lx * by * bz
+        T_host = torch.full((ncell_T,), 1000, dtype=torch.int32).pin_memory()
+        L_host = torch.empty(((bz + 1) * by * lx,), dtype=torch.int32).pin_memory()
+        i32p = C.POINTER(C.c_int32)
+        Tp, Lp = C.cast(T_host.data_ptr(), i32p), C.cast(L_host.data_ptr(), i32p)
+        ev3 = 0
+        torch.cuda.synchronize(); t4 = time.perf_counter()
+        for i in range(3):
+            ctx._ck(ctx.lib.mskc_set_temperature(ctx.h, Tp))
+            ev3 += ctx.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 7000 + i).events_done
+            ctx._ck(ctx.lib.mskc_download_lattice(ctx.h, Lp))
+        torch.cuda.synchronize(); t5 = time.perf_counter()
+        la_cycle = {"value": ev3 / (t5 - t4), "unit": UNIT, "h2d_bytes_per_step": 4 * ncell_T, "d2h_bytes_per_step": 4 * (bz + 1) * by * lx, "ms_per_step": 1e3 * (t5 - t4) / 3,
+                    "what": "mskc_set_temperature(pinned int32 field) + mskc_run_parallel + mskc_download_lattice(pinned) per step"}
+        del T_host, L_host
 
     # ---- aggregate over ranks -----------------------------------------------------------------------
     vals = torch.tensor([dt, t3 - t2, float(ev), float(ev2), float(su)], dtype=torch.float64, device="cuda")
@@ -265,9 +296,10 @@ def run_ours(args):
                "data": "synthetic", "config": config_dict(args, "gpu"),
                "site_updates_per_s": su_sum / dt_max, "events_per_step": ev_sum / args.steps, "active_sites_per_gpu": int(n_active),
                "device_ms_per_step": kms / args.steps, "gpu_launches": int(launches),
-               "e2e": {"value": ev2_sum / dt2_max, "unit": UNIT, "h2d_bytes_per_step": 4 * ncell_T, "d2h_bytes_per_step": 4 * (bz + 1) * by * lx,
-                       "ms_per_step": 1e3 * dt2_max / args.steps, "what": "mskc_set_temperature(pinned int32 field) + mskc_run_parallel + mskc_download_lattice(pinned) per step", "checksum": occ},
-               "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+               "e2e": {"value": ev2_sum / dt2_max, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+                       "ms_per_step": 1e3 * dt2_max / args.steps, "frame_cells": nrec,
+                       "what": "per step: mskc_set_rates(pinned tables) + mskc_run_parallel + mskc_extract_frame(device-compacted frame into pinned memory)", "checksum": occ},
+               "e2e_la_cycle": la_cycle, "roofline": roofline, "dense_pass": dense, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(out))
     ctx.close()
     if world > 1:
@@ -285,6 +317,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=32)
     ap.add_argument("--ept", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-la-cycle", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -204,5 +204,10 @@ module mskc_bind
       import :: c_int, c_ptr
       type(c_ptr), value :: h, id128
     end function
+    integer(c_int) function mskc_extract_frame(h, cap, cell, word, n, kernel_ms) bind(C, name="mskc_extract_frame")
+      import :: c_int, c_ptr, c_int64_t
+      type(c_ptr), value :: h, cell, word, n, kernel_ms
+      integer(c_int64_t), value :: cap
+    end function
   end interface
 end module mskc_bind

@@ -198,6 +198,13 @@ int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int32_t *event,
 /* the four stored bond targets (absolute coordinates, (0,0,0) = not fixed) of n given cells */
 int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, int32_t *nn);
 
+/* Frame extraction on the device: (cell index, lattice word) of every cell the reference's frame writers print
+ * (inpout/WriteMolMolXYZFile.f:130-215: under-coordinated atoms and coverage sites for .xyz, non-epitaxial
+ * 4-coordinated atoms for _d.xyz), so that a frame costs one 4 B/cell streaming pass and a download of the
+ * surface only instead of the whole lattice.  Unordered; sort by cell for the reference's z,y,x order.
+ * cap = capacity of the two arrays (host memory), *n = cells found (may exceed cap: call again with more). */
+int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms);
+
 /* diagnostics: raw per-tile counters of the sublattice sampler (80 B records, colour-major list order) */
 int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles);
 

@@ -67,7 +67,7 @@ SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
            "mskc_replay_events", "mskc_download_active", "mskc_download_bonds",
-           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect"]
+           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame"]
 
 
 def load_library():
@@ -109,6 +109,7 @@ def load_library():
     lib.mskc_create_slab.argtypes = [C.c_int] * 5 + [i32p, i32p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     lib.mskc_comm_unique_id.argtypes = [C.c_void_p]
     lib.mskc_comm_connect.argtypes = [vp, C.c_void_p]
+    lib.mskc_extract_frame.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
     for s in SYMBOLS:
         if s != "mskc_last_error":
             getattr(lib, s).restype = C.c_int
@@ -307,6 +308,18 @@ class Mskc:
         if len(x):
             self._ck(self.lib.mskc_download_bonds(self.h, len(x), _p(x, C.c_int32), _p(nn, C.c_int32)))
         return nn[:len(x)]
+
+    def extract_frame(self, cap=None):
+        """(cells, words, kernel_ms) of every cell the reference's frame writers print, sorted by cell (z,y,x order)"""
+        n = C.c_int64(); ms = C.c_float()
+        if cap is None:
+            self._ck(self.lib.mskc_extract_frame(self.h, 0, None, None, C.byref(n), C.byref(ms)))
+            cap = n.value
+        cells, words = np.zeros(max(cap, 1), np.uint32), np.zeros(max(cap, 1), np.uint32)
+        self._ck(self.lib.mskc_extract_frame(self.h, cap, cells.ctypes.data_as(C.POINTER(C.c_uint32)), words.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(n), C.byref(ms)))
+        k = min(n.value, cap)
+        o = np.argsort(cells[:k], kind="stable")
+        return cells[:k][o], words[:k][o], ms.value
 
     def census(self):
         c = Census(); ms = C.c_float()

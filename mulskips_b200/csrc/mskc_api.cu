@@ -28,6 +28,7 @@ struct mskc_ctx {
   short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr;
   int *d_err = nullptr;
   int32_t *d_stage = nullptr;
+  uint32_t *d_frame_cell = nullptr, *d_frame_word = nullptr; unsigned long long *d_frame_n = nullptr; int64_t frame_cap = 0;
   unsigned short *d_arm_tab = nullptr;
   // parity mode
   int NumMcMax = 500000, NumVdMax = 100000, Levels = 20;
@@ -175,7 +176,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
-  cudaFree(h->d_stage); cudaFree(h->d_arm_tab);
+  cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }
@@ -733,5 +734,34 @@ extern "C" int mskc_comm_connect(mskc_ctx *h, const void *id128) {
   ncclResult_t r = nccl->CommInitRank(&comm, h->PC.nranks, id, h->PC.rank);
   if (r != ncclSuccess) return set_err(h, "ncclCommInitRank: %s", nccl->GetErrorString(r));
   h->PC.comm = (void *)comm;
+  return 0;
+}
+
+extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
+  if (!h || !n) return set_err(h, "mskc_extract_frame: NULL argument");
+  if (!h->have_state) return set_err(h, "mskc_extract_frame: no state");
+  CK(cudaSetDevice(h->device));
+  if (cap < 0) cap = 0;
+  if (cap > h->frame_cap || !h->d_frame_n) {
+    cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); h->d_frame_cell = h->d_frame_word = nullptr;
+    h->frame_cap = cap > 0 ? cap : 1;
+    CK(cudaMalloc(&h->d_frame_cell, (size_t)h->frame_cap * 4)); CK(cudaMalloc(&h->d_frame_word, (size_t)h->frame_cap * 4));
+    if (!h->d_frame_n) CK(cudaMalloc(&h->d_frame_n, 8));
+  }
+  if (upload_consts(h)) return -1;
+  CK(cudaMemsetAsync(h->d_frame_n, 0, 8, h->stream));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  frame_extract_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaGetLastError());
+  unsigned long long cnt = 0;
+  CK(cudaMemcpyAsync(&cnt, h->d_frame_n, 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int64_t m = (int64_t)cnt < cap ? (int64_t)cnt : cap;
+  if (m > 0 && cell) CK(cudaMemcpyAsync(cell, h->d_frame_cell, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (m > 0 && word) CK(cudaMemcpyAsync(word, h->d_frame_word, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, h->ev0, h->ev1));
+  *n = (int64_t)cnt;
   return 0;
 }

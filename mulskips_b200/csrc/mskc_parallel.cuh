@@ -510,6 +510,43 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
   if ((threadIdx.x & 31) == 0 && (hz != 0 || hz2 != 0)) { atomicAdd(&hsum[0], hz); atomicAdd(&hsum[1], hz2); }
 }
 
+// Frame extraction (the output scans of inpout/WriteMolMolXYZFile.f:130-215 fused into one streaming pass, 128-bit
+// loads, 4 B/cell of HBM traffic): every cell the reference's frame writers print -- under-coordinated atoms
+// (.xyz), coverage sites (.xyz), non-epitaxial 4-coordinated atoms (_d.xyz) -- is appended as (cell, word) to a
+// compact list with warp-aggregated atomics; the host sorts by cell to get the reference's z,y,x order.
+__global__ void __launch_bounds__(256) frame_extract_kernel(uint32_t *cells, uint32_t *words, unsigned long long cap, unsigned long long *count) {
+  const long long n4 = D.ncell >> 2;
+  const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
+  const unsigned plane = (unsigned)D.LX * (unsigned)D.LY;
+  const int lane = threadIdx.x & 31;
+  for (long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane); q0 < n4; q0 += (long long)gridDim.x * blockDim.x) {
+    const long long q = q0 + lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q < n4) v = S4[q];
+    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t w = ww[k];
+      bool hit = false;
+      if (w != 0 && w_cov(w) != 113) {
+        const uint32_t c = (uint32_t)(4 * q + k);
+        if (w_occ(w)) {
+          if (w_coor(w) <= 3) hit = true;
+          else if (w_coor(w) == 4) { const unsigned z = c / plane, r = c - z * plane, y = r / (unsigned)D.LX, x = r - y * (unsigned)D.LX; int kind; hit = !is_cubic_site((int)x, (int)y, (int)z, kind); }
+        } else hit = w_cov(w) != 0;
+        if (hit && V.halo) { const unsigned x = c % (unsigned)D.LX; if (x < (unsigned)TILE || x >= (unsigned)(D.LX - TILE)) hit = false; }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (m) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (hit) { const unsigned long long i = base + __popc(m & ((1u << lane) - 1u)); if (i < cap) { cells[i] = (uint32_t)(4 * q + k); words[i] = w; } }
+      }
+    }
+  }
+}
+
 // Device-side flat (001) builder: geometry of initial/SetSi.f:25-221 (walls, one species) and
 // initial/SetSiC3C.f:25-199 (no walls, Si/C).  One thread per (x,y) column of cubic sites.
 __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int two_species, unsigned long long *counters) {

@@ -85,3 +85,29 @@ def test_replay(tmp_path, case, box, lens, nev, kw):
     assert (c.num_atoms, c.num_voids) == (s["NumAtoms"], s["NumVoids"])
     assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
     ctx.close(); orc.close()
+
+
+def test_extract_frame_matches_lattice(tmp_path):
+    """mskc_extract_frame (one streaming pass on the device) returns exactly the cells the reference's frame
+    writers print, in z,y,x order, with their lattice words."""
+    from mulskips_b200 import Mskc
+    box = (144, 144, 144)
+    start = make_start("cube-zigzag", str(tmp_path / "start.dat"), lens=(48, 48, 48), maxiter=10**9, outmolmol=10**9)
+    orc = Oracle(*box, start)
+    orc.setup()
+    orc.run(150000)
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    cells, words, ms = ctx.extract_frame()
+    L = orc.lattcoo().reshape(-1).astype(np.uint32)
+    occ, coor, cov = (L >> 23) & 1, (L >> 24) & 7, L & 255
+    idx = np.arange(L.size)
+    z, r = idx // (box[0] * box[1]), idx % (box[0] * box[1]); y, x = r // box[0], r % box[0]
+    x1, y1, z1 = x // 3, y // 3, z // 3
+    cubic = (x % 3 == 0) & (y % 3 == 0) & (z % 3 == 0) & ((x1 & 1) == (y1 & 1)) & ((x1 & 1) == (z1 & 1)) & np.isin((x1 + y1 + z1) & 3, (0, 3))
+    want = (L != 0) & (cov != 113) & (((occ == 1) & (coor <= 3)) | ((occ == 1) & (coor == 4) & ~cubic) | ((occ == 0) & (cov != 0)))
+    assert np.array_equal(cells, idx[want].astype(np.uint32))
+    assert np.array_equal(words, L[want])
+    assert ((occ == 1) & (coor == 4) & ~cubic).sum() > 0          # the hexagonal branch produced non-epitaxial bulk
+    ctx.close(); orc.close()
