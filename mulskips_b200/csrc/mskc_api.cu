@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <string>
 #include <vector>
 
@@ -159,6 +160,39 @@ extern "C" int mskc_create(int lenx, int leny, int lenz, int ncrystal, int ncov,
     CK(cudaMemcpyAsync(h->d_arm_tab, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     D.arm_tab = h->d_arm_tab;
+  }
+  // FIND_NN.f on the ideal bond shell: integer form -(b1+b2)/2 -+ (b1 x b2)/6 against the reference's double-precision
+  // rotation (same IEEE sequence as the device routine) for every tetrahedral pair of the 32 |b|^2 = 27 vectors
+  {
+    auto nint = [](double x) { return (int)(x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5)); };
+    std::vector<std::array<int, 3>> shell;
+    for (int x = -5; x <= 5; x++) for (int y = -5; y <= 5; y++) for (int z = -5; z <= 5; z++) if (x * x + y * y + z * z == 27) shell.push_back({x, y, z});
+    int ok = 1, npairs = 0;
+    for (auto &b1 : shell) for (auto &b2 : shell) {
+      int d = (b1[0] - b2[0]) * (b1[0] - b2[0]) + (b1[1] - b2[1]) * (b1[1] - b2[1]) + (b1[2] - b2[2]) * (b1[2] - b2[2]);
+      if (d != 72) continue;
+      npairs++;
+      double ax[3] = {-(double)b1[0], -(double)b1[1], -(double)b1[2]};
+      double snorm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+      for (int k = 0; k < 3; k++) ax[k] = ax[k] / snorm;
+      double v[3] = {(double)b2[0], (double)b2[1], (double)b2[2]};
+      int c[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+      for (int irot = 0; irot < 2; irot++) {
+        double Cth = D.rot_c[irot], Sth = D.rot_s[irot], Rot[3][3], R[3];
+        for (int i = 0; i < 3; i++) Rot[i][i] = ax[i] * ax[i] * (1 - Cth) + Cth;
+        Rot[1][0] = ax[0] * ax[1] * (1 - Cth) - ax[2] * Sth; Rot[0][1] = ax[0] * ax[1] * (1 - Cth) + ax[2] * Sth;
+        Rot[2][0] = ax[0] * ax[2] * (1 - Cth) + ax[1] * Sth; Rot[0][2] = ax[0] * ax[2] * (1 - Cth) - ax[1] * Sth;
+        Rot[2][1] = ax[1] * ax[2] * (1 - Cth) - ax[0] * Sth; Rot[1][2] = ax[1] * ax[2] * (1 - Cth) + ax[0] * Sth;
+        for (int k = 0; k < 3; k++) { R[k] = 0.0; for (int l = 0; l < 3; l++) R[k] = R[k] + Rot[l][k] * v[l]; }
+        const int sg = irot == 0 ? -1 : 1;
+        for (int k = 0; k < 3; k++) {
+          if ((b1[k] + b2[k]) % 2 || c[k] % 6) ok = 0;
+          if (nint(R[k]) != -(b1[k] + b2[k]) / 2 + sg * (c[k] / 6)) ok = 0;
+          if (fabs(fabs(R[k] - floor(R[k])) - 0.5) < 1e-6) ok = 0;
+        }
+      }
+    }
+    D.nn_exact = (ok && npairs == 120) ? 1 : 0;
   }
   // AllocateArrays.f:30-43
   h->NumMcMax = nummcmax > 0 ? nummcmax : 500000;

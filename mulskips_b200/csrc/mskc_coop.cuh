@@ -60,9 +60,12 @@ __device__ __forceinline__ int cov_index(int cov) {      // position of a covera
 // Occ/NSiC/Cov/Coor are what the caller holds (not re-read), rb the four bonds to rate with (they can
 // differ from the stored ones, Evaporation.f:123).  Deposition/adsorption sites get EV_DRAW: the species
 // is drawn when the event fires (Get_Prob.f:160-179 draws it here; same distribution).
+// FEAT: bit 0 = coverage species exist (NCov > 0), bit 1 = LA rate law; compiled out otherwise (hot-loop code size)
+enum { F_COV = 1, F_LA = 2 };
+template <int FEAT>
 __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, P3 Q, uint32_t cQ, unsigned long long rb, double root, int &ev, double &p) {
   ev = 0; p = 0.0;
-  if (Cov > 0 && Cov < 113) {                            // desorption, :93-123
+  if ((FEAT & F_COV) && Cov > 0 && Cov < 113) {                            // desorption, :93-123
     if (Occ != 0) { fail_cell(E_COVOCC, cQ); return; }
     if (Coor <= 3) {
       const int iCov = cov_index(Cov);
@@ -72,12 +75,12 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
     return;
   }
   int T = 0;
-  if (D.la) T = site_T(D.state[cQ], Q);
+  if ((FEAT & F_LA) && D.la) T = site_T(D.state[cQ], Q);
   if (Occ == 0) {
     if (Coor >= 1 && Coor <= 3) {
       ev = EV_DRAW;
       if (Coor == 1 && w_coor(D.state[ccell(dec_bond(Q, fld(rb, 0)))]) < 2) { ev = 1; p = (double)1.e-8f; }   // Get_Prob.f:183
-      else p = D.la ? total_dep_abs(Coor, T) : D.PDepAbs[Coor];
+      else p = (FEAT & F_LA) ? total_dep_abs(Coor, T) : D.PDepAbs[Coor];
     }
     return;
   }
@@ -98,7 +101,7 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
     if (w_occ(w)) {
       if (CovN == 113) N_wall++;
       else if (rec) { const int s = w_sp(w); N_Si += (s == 1); N_C += (s == 2); N_B += (s == 3); }
-    } else if (CovN != 0 && rec && w_coor(w) < 4) {
+    } else if ((FEAT & F_COV) && CovN != 0 && rec && w_coor(w) < 4) {
       // (coverage on a 4-coordinated empty site: the reference looks it up in the wrong list, see
       // ParityPol::cov_void_recipr, and in effect never counts it)
       const int iCov = cov_index(CovN);
@@ -111,7 +114,8 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
   if (ncry > 3) return;
   ev = 4;
   if (ncry == 0) { p = (double)100000.f * root; return; }
-  p = rate_E(IDXE(NSiC, N_Si + N_wall, N_C, N_B, cv0 & 3, cv1 & 3, cv2 & 3), T);
+  const int idx = IDXE(NSiC, N_Si + N_wall, N_C, N_B, cv0 & 3, cv1 & 3, cv2 & 3);
+  p = (FEAT & F_LA) ? rate_E(idx, T) : __ldg(&D.PE[idx]);
 }
 
 // Evaporation.f:95-122 / :229-258 on bond codes: keep the occupied, under-coordinated, reciprocal
@@ -148,12 +152,27 @@ __device__ __noinline__ int second_bond(P3 S, P3 N, unsigned fNS /* bond code N 
   int Dy = abs(M.y - S.y); Dy = min(Dy, D.LY - Dy);
   const int dz = M.z - S.z;
   if (Dx * Dx + Dy * Dy + dz * dz != 72) return 0;
-  P3 NewSite[2];
-  find_nn(M, S, N, NewSite);
-  unsigned fn[2]; int cnew = 2;
+  P3 NewSite[2]; unsigned fn[2]; int cnew = 2;
+  // FIND_NN.f:46-76 rotates b2 = S-N by +-120 degrees about b1 = M-N.  For two bonds of the ideal shell (|b|^2 = 27,
+  // tetrahedral pair) the rotation is exact in integers: -(b1+b2)/2 -+ (b1 x b2)/6; mskc_create checks this
+  // against the double-precision routine for all 120 such pairs (D.nn_exact).  Anything else rotates in double.
+  const int b1x = cdx(f0), b1y = cdy(f0), b1z = cdz(f0), b2x = cdx(fNS), b2y = cdy(fNS), b2z = cdz(fNS);
+  if (D.nn_exact && f0 != 0u && b1x * b1x + b1y * b1y + b1z * b1z == 27 && b2x * b2x + b2y * b2y + b2z * b2z == 27) {
+    const int cx = b1y * b2z - b1z * b2y, cy = b1z * b2x - b1x * b2z, cz = b1x * b2y - b1y * b2x;
+    const int sx = -(b1x + b2x) / 2, sy = -(b1y + b2y) / 2, sz = -(b1z + b2z) / 2;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const int sg = k == 0 ? -1 : 1;
+      const int ox = sx + sg * (cx / 6), oy = sy + sg * (cy / 6), oz = sz + sg * (cz / 6);
+      fn[k] = (unsigned)(ox + 16) | ((unsigned)(oy + 16) << 5) | ((unsigned)(oz + 16) << 10);
+      NewSite[k] = dec_bond(N, fn[k]);
+    }
+  } else {
+    find_nn(M, S, N, NewSite);
+    fn[0] = enc_bond_cold(N, NewSite[0]); fn[1] = enc_bond_cold(N, NewSite[1]);
+  }
 #pragma unroll 1
   for (int k = 0; k < 2; k++) {
-    fn[k] = enc_bond_cold(N, NewSite[k]);
     const uint32_t c3 = ccell(NewSite[k]);
     const uint32_t w3 = D.state[c3];
     if (w_occ(w3) && w_coor(w3) <= 3 && w_cov(w3) != 113 && recipr_b(NewSite[k], D.bonds[c3], N)) cnew++;
@@ -171,7 +190,7 @@ struct CoopCounters {                // per-lane partial sums, reduced over the 
 // everything outside the event-kind specific branches is the same instruction stream for all of them.
 // Itrans: 1..3 deposit species, 4 evaporate, 5 desorb, 6.. adsorb (main.f:335-357).
 // arm_u: uniform used when IF_Arm_Choice.f ties; forced_arm >= 0 overrides the choice (trace replay).
-template <int TEAM, class Lists>
+template <int TEAM, int FEAT, class Lists>
 __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigned tmask, const P3 S, const uint32_t cS, const int Itrans, const double root,
                                            const double arm_u, const int forced_arm, CoopCounters &K) {
   enum { DEP = 0, EVAP = 1, DES = 2, ABS = 3 };
@@ -185,6 +204,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     int dsp = -1, dcv = -1, sgn = 1;
     if (kind == DEP) { wS = (wS | (1u << PosOcc)) & ~(7u << PosSiC) | ((uint32_t)Itrans << PosSiC); dsp = Itrans - 1; }
     else if (kind == EVAP) { dsp = w_sp(wS) - 1; sgn = -1; wS &= ~((1u << PosOcc) | (7u << PosSiC)); }
+    else if (!(FEAT & F_COV)) { fail_cell(E_BADEV, cS); return; }
     else if (kind == DES) { dcv = cov_index(w_cov(wS)) - 1; sgn = -1; wS &= ~255u; }
     else {
       const int k = Itrans - 5;
@@ -240,6 +260,8 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
   // ---- phase A: lane i < 4 updates neighbour i ---------------------------------------------------
   int act = -1, qOcc = 0, qSp = 0, qCov = 0, qCoor = 0;
   P3 qN = S; uint32_t qc = cS; unsigned long long qrb = bS;
+  int qsl = 0;                                            // the site's list slot, fetched early (off the critical path of the commit)
+  if (tl == 4) qsl = L.slot_of(cS);
   bool sUp = false, sDown = false;                        // this neighbour raises / lowers S's own coordination
   bool keepable = false;                                  // Evaporation.f:229-258: occupied, under-coordinated, reciprocal neighbour of S
   if (tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
@@ -248,6 +270,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     const uint32_t cN = ccell(N);
     const uint32_t wN = D.state[cN];
     unsigned long long bN = D.bonds[cN];
+    qsl = L.slot_of(cN);
     const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN);
     const bool rec = recip_f(N, bN, S, f);
     const bool wall = Occ && CovN == 113;
@@ -280,7 +303,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
           if (CoorNN == 2) D.bonds[cN] = coop_compact(N, bN);          // (rated with the OLD neighbour list, :123)
         }
       }
-    } else if (Occ && !wall && CoorNN <= 3 && rec) { act = A_SET; newCoor = CoorNN; }   // absorption.f:43-72 / desorption.f:54-111
+    } else if ((FEAT & F_COV) && Occ && !wall && CoorNN <= 3 && rec) { act = A_SET; newCoor = CoorNN; }   // absorption.f:43-72 / desorption.f:54-111
     if (newCoor >= 0) { wNew = MVBITS(wN, newCoor, LenCoor, PosCoor); qCoor = newCoor; }
     if (wNew != wN) D.state[cN] = wNew;
     qrb = bN;
@@ -304,7 +327,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
   }
   // ---- phase B: lanes 0..4 rate their site -----------------------------------------------------------
   int ev = 0; double p = 0.0;
-  if (act >= 0 && act != A_ERASE) { coop_rate(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p); K.nsu++; }
+  if (act >= 0 && act != A_ERASE) { coop_rate<FEAT>(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p); K.nsu++; }
   __syncwarp(tmask);
   // S's coordination is written after its neighbours were rated (deposition.f:237-250)
   if (tl == 4) {
@@ -318,7 +341,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     if (act == A_SETBULK && gone) K.dAtoms++;
     if (act == A_VOID2MC) K.dVoids--;
     if (act == A_BULK2MC) K.dAtoms--;
-    if (act == A_ERASE || ev == 0) L.erase(qN, qc); else L.put(qN, qc, ev, p);
+    if (act == A_ERASE || ev == 0) L.erase(qN, qc, qsl); else L.put(qN, qc, ev, p, qsl);
   }
   __syncwarp(tmask);
 }

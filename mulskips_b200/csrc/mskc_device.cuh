@@ -49,6 +49,7 @@ struct DevCtx {
   const double *la_E;               // [(tmax-tmin+1)][la_nnz]
   const double *la_D;               // [(tmax-tmin+1)][9]
   double rot_c[2], rot_s[2];        // cos/sin(2*irot*Pi_f/3), host libm (FIND_NN.f:51-52)
+  int nn_exact;                     // 1: the integer form of FIND_NN.f on the ideal bond shell was verified against the double routine
   const unsigned short *arm_tab;    // [32768] arm-chair offset code per bond code (mskc_coop.cuh), 0 = use find_sn()
   int *err;                         // [8]: code, x, y, z, aux...
 };

@@ -128,10 +128,11 @@ struct TileLists {
   int own;                                   // list id of the running tile (-1: none, everything is "foreign")
   int mark;                                  // slab mode: log changed cells of the shared strips
   double *s_rate; unsigned long long *s_ce; int *s_n;
-  __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p) {
+  __device__ __forceinline__ int slot_of(uint32_t c) const { return V.slot[c]; }
+  // sl = the cell's current slot (slot_of(c)), read by the caller ahead of time
+  __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p, int sl) {
     if (mark) mark_dirty(s, c);
     const int l = list_of(s);
-    int sl = V.slot[c];
     const bool mine = l == own;
     if (sl == 0) {
       const int k = mine ? atomicAdd(s_n, 1) : atomicAdd(&V.cnt[l], 1);
@@ -142,9 +143,8 @@ struct TileLists {
     if (mine) { s_rate[sl - 1] = p; s_ce[sl - 1] = e; }
     else { const long long a = lidx(l, sl - 1); V.rate[a] = p; V.ce[a] = e; }
   }
-  __device__ __forceinline__ void erase(P3 s, uint32_t c) {          // tombstone (rate 0); the owner compacts
+  __device__ __forceinline__ void erase(P3 s, uint32_t c, int sl) {  // tombstone (rate 0); the owner compacts
     if (mark) mark_dirty(s, c);
-    const int sl = V.slot[c];
     if (!sl) return;
     const int l = list_of(s);
     if (l == own) s_rate[sl - 1] = 0.0; else V.rate[lidx(l, sl - 1)] = 0.0;
@@ -156,7 +156,7 @@ enum { CS_COMPACT_ABOVE = 96 };               // tombstones are dropped when a l
 
 // One colour step: every tile of colour `colour` advances by tau.  A TEAM of lanes owns one tile
 // (mskc_coop.cuh); the 32/TEAM teams of a warp run their event loops in lock step.
-template <int TEAM>
+template <int TEAM, int FEAT>
 __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
   constexpr int TPB = CS_THREADS / TEAM;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -246,11 +246,11 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
     if (Itrans == EV_DRAW) {         // species / adsorbate drawn now (Get_Prob.f:164-179)
       const uint32_t w = D.state[cell];
       const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
-      Itrans = choose_dep_abs(w_coor(w), D.la ? site_T(w, Site) : 0, us, nullptr);
+      Itrans = choose_dep_abs(w_coor(w), (FEAT & F_LA) ? site_T(w, Site) : 0, us, nullptr);
     }
     const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
     if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-    coop_event<TEAM>(L, tl, tmask, Site, cell, Itrans, root, arm_u, -1, K);
+    coop_event<TEAM, FEAT>(L, tl, tmask, Site, cell, Itrans, root, arm_u, -1, K);
     nev++;
   }
   // ---- write the list back, reduce the counters -----------------------------------------------------------
@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in) {
     const HaloRec r = in[1 + k];
     D.state[r.cell] = r.state; D.bonds[r.cell] = r.bonds;
     const P3 s = cell_xyz((long long)r.cell);
-    if (r.rate > 0.0) L.put(s, r.cell, (int)r.ev, r.rate); else L.erase(s, r.cell);
+    const int sl = V.slot[r.cell];
+    if (r.rate > 0.0) L.put(s, r.cell, (int)r.ev, r.rate, sl); else L.erase(s, r.cell, sl);
   }
 }
 
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   for (long long i = 0; i < n; i++) {
     P3 S; S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2];
     const int arm = ev_arm[i];
-    coop_event<32>(L, lane, 0xFFFFFFFFu, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    coop_event<32, F_COV | F_LA>(L, lane, 0xFFFFFFFFu, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
     done++;
     if (D.err[0] != 0) break;
   }
@@ -386,6 +387,7 @@ __global__ void sweep_finish_kernel(double ntiles_global, double events_per_tile
   s.tau = tau_fixed > 0 ? tau_fixed : (R > 0 ? events_per_tile * ntiles_global / R : 0.0);
 }
 __global__ void bump_step_kernel(SweepState *ss) { ss->step++; }
+__global__ void reset_maxev_kernel(TileStat *ts, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) ts[i].maxev = 0; }
 
 __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,7 +435,7 @@ __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long l
     P3 s = cell_xyz((long long)cell);
     uint32_t w = D.state[cell];
     int ev = 0; double p = 0;
-    coop_rate(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, D.bonds[cell], root, ev, p);
+    coop_rate<F_COV | F_LA>(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, D.bonds[cell], root, ev, p);
     if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = pack_ce(cell, ev, s.x, s.y, s.z); mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
@@ -790,21 +792,22 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
   int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
-  if (teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
+  if (teamsz != 8 && teamsz != 32) teamsz = 8;
   const int tpb = CS_THREADS / teamsz;
   const int blocks = (ntc + tpb - 1) / tpb;
   const size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCK(cudaFuncSetAttribute(colour_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 8) * P.cap * 16 + 64)));
-    PCK(cudaFuncSetAttribute(colour_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 16) * P.cap * 16 + 64)));
-    PCK(cudaFuncSetAttribute(colour_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)(CS_THREADS / 32) * P.cap * 16 + 64)));
-    attr_set = true;
-  }
+  const int feat = (H.NCov > 0 ? F_COV : 0) | (H.la ? F_LA : 0);
+  // the kernel is instantiated per feature set so that a PVD run does not carry coverage / LA code in its hot loop
+  typedef void (*cs_kernel_t)(int, uint2, int);
+  static const cs_kernel_t kern8[4] = {colour_step_kernel<8, 0>, colour_step_kernel<8, 1>, colour_step_kernel<8, 2>, colour_step_kernel<8, 3>};
+  static const cs_kernel_t kern32[4] = {colour_step_kernel<32, 0>, colour_step_kernel<32, 1>, colour_step_kernel<32, 2>, colour_step_kernel<32, 3>};
+  const cs_kernel_t kern = teamsz == 8 ? kern8[feat] : kern32[feat];
+  PCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 64));
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
   int launches = 0;
+  reset_maxev_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.tstat, P.ntiles);
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
     tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
@@ -824,9 +827,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      if (teamsz == 8) colour_step_kernel<8><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
-      else if (teamsz == 16) colour_step_kernel<16><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
-      else colour_step_kernel<32><<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
+      kern<<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;
