@@ -679,8 +679,8 @@ extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xy
   cudaFree(d_s); cudaFree(d_e); cudaFree(d_a); cudaFree(d_out);
   ParallelCtx &P = h->PC;
   P.replayed = true;
-  P.h_tot.events += out.events; P.h_tot.site_updates += out.site_updates; P.h_tot.dAtoms += out.dAtoms; P.h_tot.dVoids += out.dVoids;
-  for (int i = 0; i < 3; i++) { P.h_tot.dCrystal[i] += out.dCrystal[i]; P.h_tot.dCov[i] += out.dCov[i]; }
+  P.extra.events += out.events; P.extra.site_updates += out.site_updates; P.extra.dAtoms += out.dAtoms; P.extra.dVoids += out.dVoids;
+  for (int i = 0; i < 3; i++) { P.extra.dCrystal[i] += out.dCrystal[i]; P.extra.dCov[i] += out.dCov[i]; }
   if (check_dev_err(h)) return -1;
   if (out.events != n) return set_err(h, "mskc_replay_events: stopped after %lld of %lld events", (long long)out.events, (long long)n);
   return 0;

@@ -57,6 +57,7 @@ struct ParallelCtx {
   long long base_atoms = 0, base_voids = 0;
   int baseCrystal[3] = {0, 0, 0}, baseCov[3] = {0, 0, 0};
   TileStat h_tot{}; SweepState h_ss{};
+  TileStat extra{};                     // events applied outside the colour steps (trace replay), added to the counters
   double time = 0.0;
   bool ran = false, replayed = false, lists_stale = false, listed_flag_in_state = false;
 };
@@ -205,7 +206,11 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
   int nev = 0, ndep0 = 0, ndep1 = 0, ndep2 = 0, nevap = 0, nabs = 0, ndes = 0;
   uint32_t draw = 0;
   double tloc = 0.0, R = 0.0;
-  while (true) {
+  // All teams of the warp stay in the loop until the last one is done, and the full-warp vote at the top is a
+  // convergence point: the teams execute one event per iteration in lock step (a team that is done idles).
+  bool active = true;
+  while (__any_sync(0xFFFFFFFFu, active)) {
+    if (active) do {
     const int n = *s_n;
     // rate sum and inclusive prefix over the list (lane-strided chunks)
     double part = 0.0;
@@ -215,11 +220,11 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
 #pragma unroll
     for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(tmask, incl, o, TEAM); if (tl >= o) incl += t; }
     R = __shfl_sync(tmask, incl, TEAM - 1, TEAM);
-    if (!(R > 0.0) || nev >= max_events_per_tile) break;
+    if (!(R > 0.0) || nev >= max_events_per_tile) { active = false; break; }
     // one counter-based draw per event: x -> waiting time, y + 20 bits of z -> target, 24 bits -> species, 20 bits -> arm-chair tie
     const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
     tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)R);
-    if (tloc > tau) break;
+    if (tloc > tau) { active = false; break; }
     const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * R;
     // the lane whose chunk contains the target, then the entry inside that lane's strided chunk
     const unsigned m = (__ballot_sync(tmask, incl > target) >> tshift) & tm;
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
 #pragma unroll 1
       for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
       const unsigned mm = (__ballot_sync(tmask, mine >= 0) >> tshift) & tm;
-      if (!mm) break;
+      if (!mm) { active = false; break; }
       pick = __shfl_sync(tmask, mine, __ffs(mm) - 1, TEAM);
     }
     const unsigned long long e = s_ce[pick];
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
     if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
     coop_event<TEAM, FEAT>(L, tl, tmask, Site, cell, Itrans, root, arm_u, -1, K);
     nev++;
+    } while (false);
   }
   // ---- write the list back, reduce the counters -----------------------------------------------------------
   __syncwarp(tmask);
@@ -764,7 +770,7 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
   PCK(cudaStreamSynchronize(st));
   P.base_atoms = n_bulk; P.base_voids = n_void; P.time = 0; P.ran = false; P.replayed = false; P.lists_stale = false;
   for (int i = 0; i < 3; i++) { P.baseCrystal[i] = 0; P.baseCov[i] = 0; }
-  memset(&P.h_tot, 0, sizeof P.h_tot);
+  memset(&P.h_tot, 0, sizeof P.h_tot); memset(&P.extra, 0, sizeof P.extra);
   return 0;
 }
 
@@ -880,10 +886,10 @@ static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cu
 }
 
 static inline void parallel_fill_counters(const ParallelCtx &P, mskc_counters *c) {
-  c->num_atoms = (int32_t)(P.base_atoms + P.h_tot.dAtoms); c->num_voids = (int32_t)(P.base_voids + P.h_tot.dVoids);
+  c->num_atoms = (int32_t)(P.base_atoms + P.h_tot.dAtoms + P.extra.dAtoms); c->num_voids = (int32_t)(P.base_voids + P.h_tot.dVoids + P.extra.dVoids);
   c->num_adatom = (int32_t)P.h_ss.n_active;
-  for (int i = 0; i < 3; i++) { c->CountCrystal[i] = P.baseCrystal[i] + P.h_tot.dCrystal[i]; c->CountCov[i] = P.baseCov[i] + P.h_tot.dCov[i]; }
-  c->iter = P.h_tot.events + 1; c->time = P.h_ss.time;
+  for (int i = 0; i < 3; i++) { c->CountCrystal[i] = P.baseCrystal[i] + P.h_tot.dCrystal[i] + P.extra.dCrystal[i]; c->CountCov[i] = P.baseCov[i] + P.h_tot.dCov[i] + P.extra.dCov[i]; }
+  c->iter = P.h_tot.events + P.extra.events + 1; c->time = P.h_ss.time;
 }
 
 }  // namespace mskc
