@@ -53,6 +53,7 @@ struct ParallelCtx {
   double *red = nullptr;
   unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
   void *comm = nullptr;                 // ncclComm_t
+  unsigned int *pack_done = nullptr;
   long long ncell = 0;
   long long base_atoms = 0, base_voids = 0;
   int baseCrystal[3] = {0, 0, 0}, baseCov[3] = {0, 0, 0};
@@ -287,7 +288,11 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
 // copies of a shared strip differ only where ONE side wrote: each rank sends the final record of every cell it
 // changed in its two 48-unit strips (its border tile column + its halo column) and applies what it receives.
 struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad; };     // 32 B
-__global__ void __launch_bounds__(256) halo_pack_kernel(int side, int shift /* +-owned width */, HaloRec *out) {
+// one launch packs both strips (blockIdx.y = side); the last block to finish clears the dirty counters
+__global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of the owned block */, HaloRec *out0, HaloRec *out1, unsigned int *done) {
+  const int side = blockIdx.y;
+  HaloRec *out = side ? out1 : out0;
+  const int shift = side ? -owned : owned;
   const int n = min(V.dirty_n[side], V.dirty_cap);
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint32_t c = V.dirty_cell[(size_t)side * V.dirty_cap + k];
@@ -301,9 +306,15 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(int side, int shift /* +
     out[1 + k] = r;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { HaloRec h; h.cell = (uint32_t)n; h.state = 0; h.bonds = 0; h.rate = 0; h.ev = 0; h.pad = 0; out[0] = h; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1) { V.dirty_n[0] = 0; V.dirty_n[1] = 0; *done = 0u; }
+  }
 }
-__global__ void halo_reset_kernel() { V.dirty_n[0] = 0; V.dirty_n[1] = 0; }
-__global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in) {
+// one launch applies both received buffers (blockIdx.y selects the buffer)
+__global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in0, const HaloRec *in1) {
+  const HaloRec *in = blockIdx.y ? in1 : in0;
   const int n = (int)in[0].cell;
   TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -635,11 +646,11 @@ static inline NcclApi *nccl_api(std::string *err) {
 }
 #define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { if (err) *err = std::string("NCCL error ") + nccl->GetErrorString(r_) + " in " #call; return -1; } } while (0)
 
-enum { HALO_CAP = 32768 };         // records per side per colour step (1 MiB messages)
+enum { HALO_CAP = 16384 };         // records per side per colour step (512 KiB messages)
 
 static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
-  cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.red);
+  cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.pack_done); cudaFree(P.red);
   for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
   cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
@@ -684,6 +695,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
     PCK(cudaMalloc(&P.dirty_bits, P.dirty_words * 4)); PCK(cudaMemsetAsync(P.dirty_bits, 0, P.dirty_words * 4, st));
     PCK(cudaMalloc(&P.dirty_cell, (size_t)2 * P.dirty_cap * 4));
     PCK(cudaMalloc(&P.dirty_n, 2 * sizeof(int))); PCK(cudaMemsetAsync(P.dirty_n, 0, 2 * sizeof(int), st));
+    PCK(cudaMalloc(&P.pack_done, sizeof(unsigned int))); PCK(cudaMemsetAsync(P.pack_done, 0, sizeof(unsigned int), st));
     for (int i = 0; i < 2; i++) {
       PCK(cudaMalloc(&P.sendbuf[i], (size_t)(HALO_CAP + 1) * sizeof(HaloRec))); PCK(cudaMemsetAsync(P.sendbuf[i], 0, sizeof(HaloRec), st));
       PCK(cudaMalloc(&P.recvbuf[i], (size_t)(HALO_CAP + 1) * sizeof(HaloRec))); PCK(cudaMemsetAsync(P.recvbuf[i], 0, sizeof(HaloRec), st));
@@ -716,9 +728,8 @@ static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, doub
 // after a colour step: send the changed records of the two shared strips to the neighbours, apply theirs
 static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int *launches, std::string *err) {
   const int owned = H.LX - 2 * P.tile;                         // width of the owned block = shift between the two copies of a strip
-  halo_pack_kernel<<<32, 256, 0, st>>>(0, +owned, (HaloRec *)P.sendbuf[0]);      // my left strip  = the left neighbour's right strip
-  halo_pack_kernel<<<32, 256, 0, st>>>(1, -owned, (HaloRec *)P.sendbuf[1]);      // my right strip = the right neighbour's left strip
-  halo_reset_kernel<<<1, 1, 0, st>>>();
+  // my left strip = the left neighbour's right strip (cells shift by +owned), my right strip = the right neighbour's left strip
+  halo_pack_kernel<<<dim3(16, 2), 256, 0, st>>>(owned, (HaloRec *)P.sendbuf[0], (HaloRec *)P.sendbuf[1], P.pack_done);
   const size_t bytes = (size_t)(HALO_CAP + 1) * sizeof(HaloRec);
   const unsigned char *in0 = P.sendbuf[0], *in1 = P.sendbuf[1];
   if (P.nranks > 1) {
@@ -733,9 +744,8 @@ static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st
     NCK(nccl->GroupEnd());
     in0 = P.recvbuf[0]; in1 = P.recvbuf[1];
   }                                                            // one rank: it is its own neighbour on both sides (periodic box)
-  halo_apply_kernel<<<32, 256, 0, st>>>((const HaloRec *)in0);
-  halo_apply_kernel<<<32, 256, 0, st>>>((const HaloRec *)in1);
-  *launches += 5;
+  halo_apply_kernel<<<dim3(16, 2), 256, 0, st>>>((const HaloRec *)in0, (const HaloRec *)in1);
+  *launches += 2;
   return 0;
 }
 
