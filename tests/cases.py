@@ -55,3 +55,34 @@ def make_start(case, dst, lens=None, maxiter=None, outmolmol=None, runtype=None,
     with open(dst, "w") as f:
         f.write("\n".join(lines))
     return dst
+
+
+def make_la_case(dirpath, box=(96, 96, 96), lennuc=12.0, maxiter=10**9):
+    """A small synthetic laser-annealing case in the reference's file formats (initial/SetCAD.f, initial/SetT.f):
+    LattGeo (all cells crystal candidates; InitSt LA carves a spherical liquid nucleus below the top air gap) and
+    TempStat (integer kelvin, 1655..1661 like the regression map), plus start.dat = start-LA.dat with the paths,
+    nucleus radius and iteration limits replaced.  Returns the start.dat path."""
+    import numpy as np
+    lx, ly, lz = box
+    geo, tmp = os.path.join(dirpath, "LattGeo.dat"), os.path.join(dirpath, "TempStat.dat")
+    with open(geo, "w") as f:
+        row = " ".join(["1"] * (lx * ly))
+        for _ in range(lz):
+            f.write(row + "\n")
+    rng = np.random.default_rng(7)
+    with open(tmp, "w") as f:
+        for z in range(lz):
+            f.write(" ".join(str(v) for v in (1655 + rng.integers(0, 7, lx * ly))) + "\n")
+    lines = open(start_path("LA")).read().split("\n")
+    lines[3], lines[4] = geo, tmp
+    lines[10] = f"{lennuc} ! LenNuc"
+    i = next(k for k, l in enumerate(lines) if l.split() and l.split()[0] == "Iter")
+    lines[i + 1] = f"{maxiter} ! IterMax"
+    lines[i + 2] = f"{maxiter} ! OutMolMol"
+    lines[i + 5] = "F ! Save final state"
+    del lines[i + 6]                      # the checkpoint file name line
+    lines[i + 6] = "T ! Save final Coor"
+    dst = os.path.join(dirpath, "start.dat")
+    with open(dst, "w") as f:
+        f.write("\n".join(lines))
+    return dst

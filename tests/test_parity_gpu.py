@@ -61,3 +61,43 @@ def test_parity_small(tmp_path, case, box, lens, nev):
     assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
     assert r.site_updates > 0
     ctx.close(); orc.close()
+
+
+def test_parity_laser_annealing(tmp_path):
+    """InitSt LA (config C4): temperature in the lattice word, rates from the host-built exp/erf tables
+    (Get_Prob.f:127-149), on a synthetic nucleus that re-solidifies until the reference's
+    'few MC particles: stop MC' exit.  Bit-exact lattice, Time bits, list sizes, stop reason."""
+    from cases import make_la_case
+    from mulskips_b200 import Mskc
+    box = (96, 96, 96)
+    start = make_la_case(str(tmp_path), box=box, lennuc=18.0)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    assert ctx.state_hash() == orc.hash()
+    total = 0
+    while True:
+        n = orc.run(3000)
+        r = ctx.run_parity(event_budget=3000)
+        total += n
+        assert r.events_done == n
+        s = orc.sizes()
+        assert (r.num_adatom, r.num_atoms, r.num_voids) == (s["NumAdAtom"], s["NumAtoms"], s["NumVoids"])
+        assert bits(r.time) == bits(orc.time)
+        if s["done"]:
+            assert r.stop_reason == 4            # MSKC_STOP_FEWMC
+            break
+    assert total > 5000
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())
+    # SetT.f through the ABI: re-uploading the temperature field leaves the lattice unchanged, a shifted field changes bits 9..21 only
+    L = orc.lattcoo().copy()
+    T = ((L[:-1] >> 9) & 8191).astype(np.int32)
+    ctx.set_temperature(np.where(T == 0, 10, T))
+    assert np.array_equal(ctx.download_lattice(), L)
+    ctx.set_temperature(np.where(T == 0, 10, T + 1))
+    L2 = ctx.download_lattice()
+    assert np.array_equal(L2[:-1] & ~(8191 << 9), L[:-1] & ~(8191 << 9))
+    assert np.array_equal((L2[:-1] >> 9) & 8191, np.where(T == 0, 0, T + 1))
+    ctx.close(); orc.close()

@@ -87,6 +87,30 @@ def test_replay(tmp_path, case, box, lens, nev, kw):
     ctx.close(); orc.close()
 
 
+def test_replay_laser_annealing(tmp_path):
+    """the cooperative transition code with the LA rate law (temperature-indexed tables, T kept in erased words)"""
+    from cases import make_la_case
+    from mulskips_b200 import Mskc
+    box = (96, 96, 96)
+    start = make_la_case(str(tmp_path), box=box, lennuc=18.0)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    orc.set_trace(10**6)
+    n = orc.run(10**6)
+    assert n > 5000
+    site, code, arm, tree1 = trace_arrays(orc)
+    ctx.replay_events(site[:n], code[:n], arm[:n])
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())
+    exp, d = expected_active(orc)
+    xyz, ev, rate = ctx.download_active()
+    got = {tuple(int(v) for v in p): (int(e), np.float64(r).view(np.uint64)) for p, e, r in zip(xyz, ev, rate)}
+    assert got == exp
+    ctx.close(); orc.close()
+
+
 def test_extract_frame_matches_lattice(tmp_path):
     """mskc_extract_frame (one streaming pass on the device) returns exactly the cells the reference's frame
     writers print, in z,y,x order, with their lattice words."""
