@@ -1,2 +1,2 @@
 set -x
-python -m pytest tests/test_parity_gpu.py tests/test_replay_gpu.py -x -q -k "laser" 2>&1 | tail -15
+time MSKC_FULL_GOLDEN=1 python -m pytest tests/test_host_gpu.py -x -q -k "cube-zigzag or sphere" 2>&1 | tail -5
