@@ -117,7 +117,9 @@ typedef struct {
   double  tau_fixed;         /* >0: use this time quantum instead of the adaptive one               */
   uint64_t seed;             /* Philox key                                                          */
   int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
-  int32_t  flags;            /* reserved, 0                                                         */
+  int32_t  flags;            /* bits 0-15: events one tile may execute per colour step before the rest of its
+                              * quantum is carried to its next step (0 = default 3*events_per_tile+4,
+                              * 0xFFFF = no cap); other bits reserved, 0                               */
 } mskc_parallel_args;
 
 typedef struct {

@@ -1,6 +1,6 @@
 // mskc_coop.cuh -- warp-cooperative form of the four KMC transitions (sm_100a).
 //
-// One warp owns one tile of the synchronous-sublattice sampler.  An event at site S touches S and its
+// A team of lanes owns one tile of the synchronous-sublattice sampler.  An event at site S touches S and its
 // four bonded neighbours N0..N3, then re-rates those five sites (each re-rate is a census of that site's
 // own four neighbours).  The serial reference walks these one after the other (mcevent/deposition.f,
 // Evaporation.f, absorption.f, desorption.f + Get_Prob.f); here
@@ -122,13 +122,13 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
 // neighbour (the last one that qualifies) in slot 1, forget the others.
 __device__ __noinline__ unsigned long long coop_compact(P3 me, unsigned long long old) {
   unsigned keep = 0u; bool found = false;
-#pragma unroll 1
+  uint32_t w[4]; unsigned long long b[4];                 // all eight words in flight together (one memory round trip)
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const uint32_t c = ccell(dec_bond(me, fld(old, j))); w[j] = D.state[c]; b[j] = D.bonds[c]; }
+#pragma unroll
   for (int j = 0; j < 4; j++) {
     const unsigned f = fld(old, j);
-    const P3 n = dec_bond(me, f);
-    const uint32_t c = ccell(n);
-    const uint32_t w = D.state[c];
-    if (w_occ(w) && w_coor(w) <= 3 && w_cov(w) != 113 && recip_f(n, D.bonds[c], me, f)) { keep = f; found = true; }
+    if (w_occ(w[j]) && w_coor(w[j]) <= 3 && w_cov(w[j]) != 113 && recip_f(dec_bond(me, f), b[j], me, f)) { keep = f; found = true; }
   }
   if (!found) fail(E_STALE_NBUFF, me.x, me.y, me.z);
   return (unsigned long long)keep;
@@ -171,12 +171,12 @@ __device__ __noinline__ int second_bond(P3 S, P3 N, unsigned fNS /* bond code N 
     find_nn(M, S, N, NewSite);
     fn[0] = enc_bond_cold(N, NewSite[0]); fn[1] = enc_bond_cold(N, NewSite[1]);
   }
-#pragma unroll 1
-  for (int k = 0; k < 2; k++) {
-    const uint32_t c3 = ccell(NewSite[k]);
-    const uint32_t w3 = D.state[c3];
-    if (w_occ(w3) && w_coor(w3) <= 3 && w_cov(w3) != 113 && recipr_b(NewSite[k], D.bonds[c3], N)) cnew++;
-  }
+  uint32_t w3[2]; unsigned long long b3[2];              // both cells' words in flight together
+#pragma unroll
+  for (int k = 0; k < 2; k++) { const uint32_t c3 = ccell(NewSite[k]); w3[k] = D.state[c3]; b3[k] = D.bonds[c3]; }
+#pragma unroll
+  for (int k = 0; k < 2; k++)
+    if (w_occ(w3[k]) && w_coor(w3[k]) <= 3 && w_cov(w3[k]) != 113 && recipr_b(NewSite[k], b3[k], N)) cnew++;
   bN = (unsigned long long)f0 | ((unsigned long long)fNS << 16) | ((unsigned long long)fn[0] << 32) | ((unsigned long long)fn[1] << 48);
   return cnew;
 }
@@ -185,50 +185,55 @@ struct CoopCounters {                // per-lane partial sums, reduced over the 
   int nsu, dAtoms, dVoids, dCrystal[3], dCov[3];
 };
 
-// ---- one event, executed by a TEAM of lanes (8, 16 or 32; a power of two) --------------------------------
-// tl = lane index inside the team, tmask = the team's lanes.  Several teams share a warp and run in lock step:
-// everything outside the event-kind specific branches is the same instruction stream for all of them.
+// ---- one event per TEAM of lanes (8 or 32; a power of two), all teams of the warp in lock step --------------
+// EVERY lane of the warp calls this together (full-mask votes, shuffles and __syncwarp() are the convergence
+// points): tl = lane index inside its team, go = "this team has an event" (a team without one only takes part in
+// the synchronisation).  Loads are issued in code all teams share, the event-kind specific parts are short
+// branches between two convergence points, so the memory round trips of the teams overlap instead of queueing.
 // Itrans: 1..3 deposit species, 4 evaporate, 5 desorb, 6.. adsorb (main.f:335-357).
 // arm_u: uniform used when IF_Arm_Choice.f ties; forced_arm >= 0 overrides the choice (trace replay).
 template <int TEAM, int FEAT, class Lists>
-__device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigned tmask, const P3 S, const uint32_t cS, const int Itrans, const double root,
+__device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, const P3 S, const uint32_t cS, const int Itrans, const double root,
                                            const double arm_u, const int forced_arm, CoopCounters &K) {
   enum { DEP = 0, EVAP = 1, DES = 2, ABS = 3 };
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  constexpr unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
   const int kind = Itrans <= 3 ? DEP : (Itrans == 4 ? EVAP : (Itrans == 5 ? DES : ABS));
   const int tshift = (int)(threadIdx.x & 31u) - tl;         // first lane of the team inside the warp
-  uint32_t wS = D.state[cS];
-  unsigned long long bS = D.bonds[cS];
+  if (!(FEAT & F_COV) && go && kind >= DES) { fail_cell(E_BADEV, cS); go = false; }
+  if ((FEAT & F_COV) && go && kind == ABS && Itrans - 5 > 3) { fail_cell(E_BADEV, cS); go = false; }
+  uint32_t wS = 0u; unsigned long long bS = 0ull;
+  if (go) { wS = D.state[cS]; bS = D.bonds[cS]; }
   const int c0 = w_coor(wS);
   int CovNew = 0;
   {                                                        // S's word: occupancy / species / coverage (coordination follows at the end)
     int dsp = -1, dcv = -1, sgn = 1;
     if (kind == DEP) { wS = (wS | (1u << PosOcc)) & ~(7u << PosSiC) | ((uint32_t)Itrans << PosSiC); dsp = Itrans - 1; }
     else if (kind == EVAP) { dsp = w_sp(wS) - 1; sgn = -1; wS &= ~((1u << PosOcc) | (7u << PosSiC)); }
-    else if (!(FEAT & F_COV)) { fail_cell(E_BADEV, cS); return; }
-    else if (kind == DES) { dcv = cov_index(w_cov(wS)) - 1; sgn = -1; wS &= ~255u; }
-    else {
-      const int k = Itrans - 5;
-      if (k > 3) { fail_cell(E_BADEV, cS); return; }
-      CovNew = D.ListCov[k - 1]; dcv = k - 1;
-      wS = (wS & ~255u) | (uint32_t)CovNew;
+    else if (FEAT & F_COV) {
+      if (kind == DES) { dcv = cov_index(w_cov(wS)) - 1; sgn = -1; wS &= ~255u; }
+      else { const int k = (Itrans - 5) & 3; CovNew = D.ListCov[k ? k - 1 : 0]; dcv = k - 1; wS = (wS & ~255u) | (uint32_t)CovNew; }
     }
-    if (tl == 4) {
+    if (go && tl == 4) {
       if (dsp >= 0 && dsp < 3) K.dCrystal[dsp] += sgn;
       if (dcv >= 0 && dcv < 3) K.dCov[dcv] += sgn;
       D.state[cS] = wS;
     }
   }
-  __syncwarp(tmask);                                       // S's new occupancy is visible before any lane looks back at it
+  __syncwarp();                                            // S's new occupancy is visible before any lane looks back at it
 
-  if (kind == DEP && c0 == 1) {                          // deposition.f:49-74: fix bonds 2..4 (cubic or hexagonal continuation)
-    const unsigned e = fld(bS, 0);
+  // deposition.f:49-74: a 1-coordinated site fixes bonds 2..4 (cubic or hexagonal continuation)
+  const bool fix = go && kind == DEP && c0 == 1;
+  unsigned zig[3] = {0u, 0u, 0u}, arm[3] = {0u, 0u, 0u};
+  const unsigned e = fld(bS, 0);
+  int cc = 0;
+  if (fix) {
     const P3 C = dec_bond(S, e);
     const unsigned long long bC = D.bonds[ccell(C)];
     const unsigned back = (unsigned)NEGC - e;
     unsigned g[3] = {0u, 0u, 0u}; int j = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) { const unsigned f = fld(bC, i); if (f != back) { if (j < 3) g[j] = f; j++; } }
-    unsigned zig[3], arm[3];
     const unsigned ao = (unsigned)__ldg(&D.arm_tab[e]);
     bool slow = (ao == 0u) | (g[0] == 0u) | (g[1] == 0u) | (g[2] == 0u);
 #pragma unroll
@@ -241,30 +246,33 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     }
     if (slow) slow_find_sn(S, C, g, zig, arm);
     // IF_Arm_Choice.f:38-54: lanes 0..2 read the arm-chair cells, 3..5 the zig-zag cells
-    int cc = 0;
     if (tl < 6) {
       const int k = tl < 3 ? tl : tl - 3;
       const unsigned fa = k == 0 ? arm[0] : (k == 1 ? arm[1] : arm[2]), fz = k == 0 ? zig[0] : (k == 1 ? zig[1] : zig[2]);
       cc = w_coor(D.state[ccell(dec_bond(S, tl < 3 ? fa : fz))]);
     }
-    const int CoorArm = __shfl_sync(tmask, cc, 0, TEAM) + __shfl_sync(tmask, cc, 1, TEAM) + __shfl_sync(tmask, cc, 2, TEAM);
-    const int CoorZig = __shfl_sync(tmask, cc, 3, TEAM) + __shfl_sync(tmask, cc, 4, TEAM) + __shfl_sync(tmask, cc, 5, TEAM);
-    bool IF_Arm = CoorZig < CoorArm || (CoorZig == CoorArm && !(arm_u <= D.PZig));
-    if (forced_arm >= 0) IF_Arm = forced_arm != 0;
-    bS = (unsigned long long)e;
+  }
+  {
+    const int CoorArm = __shfl_sync(FULL, cc, 0, TEAM) + __shfl_sync(FULL, cc, 1, TEAM) + __shfl_sync(FULL, cc, 2, TEAM);
+    const int CoorZig = __shfl_sync(FULL, cc, 3, TEAM) + __shfl_sync(FULL, cc, 4, TEAM) + __shfl_sync(FULL, cc, 5, TEAM);
+    if (fix) {
+      bool IF_Arm = CoorZig < CoorArm || (CoorZig == CoorArm && !(arm_u <= D.PZig));
+      if (forced_arm >= 0) IF_Arm = forced_arm != 0;
+      bS = (unsigned long long)e;
 #pragma unroll
-    for (int i = 0; i < 3; i++) bS |= (unsigned long long)(IF_Arm ? arm[i] : zig[i]) << (16 * (i + 1));
-    if (tl == 4) D.bonds[cS] = bS;
+      for (int i = 0; i < 3; i++) bS |= (unsigned long long)(IF_Arm ? arm[i] : zig[i]) << (16 * (i + 1));
+      if (tl == 4) D.bonds[cS] = bS;
+    }
   }
 
   // ---- phase A: lane i < 4 updates neighbour i ---------------------------------------------------
   int act = -1, qOcc = 0, qSp = 0, qCov = 0, qCoor = 0;
   P3 qN = S; uint32_t qc = cS; unsigned long long qrb = bS;
   int qsl = 0;                                            // the site's list slot, fetched early (off the critical path of the commit)
-  if (tl == 4) qsl = L.slot_of(cS);
+  if (go && tl == 4) qsl = L.slot_of(cS);
   bool sUp = false, sDown = false;                        // this neighbour raises / lowers S's own coordination
   bool keepable = false;                                  // Evaporation.f:229-258: occupied, under-coordinated, reciprocal neighbour of S
-  if (tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
+  if (go && tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
     const unsigned f = fld(bS, tl);
     const P3 N = dec_bond(S, f);
     const uint32_t cN = ccell(N);
@@ -308,12 +316,13 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     if (wNew != wN) D.state[cN] = wNew;
     qrb = bN;
   }
-  const int Coor = c0 + __popc(__ballot_sync(tmask, sUp)) - __popc(__ballot_sync(tmask, sDown));
-  const unsigned keepm = (__ballot_sync(tmask, keepable) >> tshift) & 15u;
-  __syncwarp(tmask);                                       // neighbours' words are final and visible to the whole team
+  const unsigned upm = (__ballot_sync(FULL, sUp) >> tshift) & tm, downm = (__ballot_sync(FULL, sDown) >> tshift) & tm;
+  const int Coor = c0 + __popc(upm) - __popc(downm);
+  const unsigned keepm = (__ballot_sync(FULL, keepable) >> tshift) & 15u;
+  __syncwarp();                                            // neighbours' words are final and visible to the whole team
   // ---- S's own request (lane 4) -----------------------------------------------------------------------
   uint32_t wS2 = wS;
-  if (tl == 4) {
+  if (go && tl == 4) {
     qCoor = Coor; qCov = CovNew; act = A_SET;
     if (kind <= EVAP) wS2 = MVBITS(wS, Coor, LenCoor, PosCoor);
     if (kind == DEP) { act = A_SETBULK; qOcc = 1; qSp = Itrans; }
@@ -328,9 +337,9 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
   // ---- phase B: lanes 0..4 rate their site -----------------------------------------------------------
   int ev = 0; double p = 0.0;
   if (act >= 0 && act != A_ERASE) { coop_rate<FEAT>(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p); K.nsu++; }
-  __syncwarp(tmask);
+  __syncwarp();
   // S's coordination is written after its neighbours were rated (deposition.f:237-250)
-  if (tl == 4) {
+  if (go && tl == 4) {
     if (wS2 != wS) D.state[cS] = wS2;
     if (act == A_ERASE) D.bonds[cS] = 0ull;
   }
@@ -343,7 +352,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, const unsigne
     if (act == A_BULK2MC) K.dAtoms--;
     if (act == A_ERASE || ev == 0) L.erase(qN, qc, qsl); else L.put(qN, qc, ev, p, qsl);
   }
-  __syncwarp(tmask);
+  __syncwarp();
 }
 
 }  // namespace mskc

@@ -11,6 +11,7 @@
 //   cnt[tile]           i32  slots in use (tombstones with rate 0 included until the owner compacts)
 //   slot[cell]          u16  1-based slot of the cell in its tile's list, 0 = not listed
 //   tstat[tile]         per-tile counters (events, site updates, per-class counts), summed on demand
+//   lag[tile]           f64  time the tile still owes (its last colour step stopped at the event cap)
 #pragma once
 #include "mskc_device.cuh"
 #include "mskc_coop.cuh"
@@ -45,7 +46,7 @@ struct SweepState {          // one per context, device resident
 // colour are contiguous (l = colour*ntc + index).
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
-  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr;
+  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
   // slab mode
   int halo = 0, rank = 0, nranks = 1;
@@ -66,6 +67,7 @@ struct ParallelCtx {
 struct TileView {            // what the kernels need (constant memory)
   int tile, ntx, nty, cap, NT, hx, ntc;
   double *rate; unsigned long long *ce; int *cnt; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
+  double *lag;                          // [tile] KMC time a tile still owes because its colour step hit the event cap
   // x-decomposed slab (multi-GPU): one halo tile column on each side of the owned block, see "halo exchange" below
   int halo, nranks;
   uint32_t *dirty_bits;                 // bitmap over the two 48-unit shared strips (left: x < 48, right: x >= LX-48)
@@ -153,32 +155,44 @@ struct TileLists {
   }
 };
 
-enum { CS_THREADS = 128 };                    // CTA size of the colour-step kernel (CS_THREADS / TEAM tiles per CTA)
-enum { CS_COMPACT_ABOVE = 96 };               // tombstones are dropped when a list is loaded with more entries than this
+enum { CS_THREADS = 128, CS_MINB = 4 };
+enum { CS_COMPACT_ABOVE = 96 };
+#define CS_BURST 4.0                          /* a state expected to fire more than CS_BURST*cap events per quantum is transient */
+#define CS_MAX_LAG 6.0                        /* quanta of debt beyond which a tile's event cap is lifted */               // tombstones are dropped when a list is loaded with more entries than this
 
 // One colour step: every tile of colour `colour` advances by tau.  A TEAM of lanes owns one tile
-// (mskc_coop.cuh); the 32/TEAM teams of a warp run their event loops in lock step.
+// (mskc_coop.cuh); the 32/TEAM teams of a warp run their event loops in lock step: every lane of the warp
+// executes every iteration (full-mask votes and shuffles are the convergence points), a team without an event
+// only takes part in the synchronisation.
 template <int TEAM, int FEAT>
-__global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uint2 key, int max_events_per_tile) {
+__global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int colour, uint2 key, int event_cap) {
   constexpr int TPB = CS_THREADS / TEAM;
+  constexpr unsigned FULL = 0xFFFFFFFFu;
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, tl = threadIdx.x % TEAM, tib = threadIdx.x / TEAM;
   const int tshift = lane - tl;
-  const unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << TEAM) - 1u);
+  const unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
   const unsigned tmask = tm << tshift;
   const int wid = blockIdx.x * TPB + tib;
-  if (wid >= V.ntc) return;
   const int cap = V.cap;
   double *s_rate = reinterpret_cast<double *>(smem) + (size_t)tib * cap;
   unsigned long long *s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)TPB * cap * 8) + (size_t)tib * cap;
   int *s_n = reinterpret_cast<int *>(smem + (size_t)TPB * cap * 16) + tib;
   const int l = colour * V.ntc + wid;
   const int x0 = (2 * (wid % V.hx) + (colour & 1)) * TILE, y0 = (2 * (wid / V.hx) + (colour >> 1)) * TILE;   // tile origin (list_of inverted)
-  if (V.halo && (x0 == 0 || x0 == D.LX - TILE)) return;       // halo tiles belong to the neighbouring rank
+  // a team beyond the last tile, or on a halo tile (it belongs to the neighbouring rank), idles through the step
+  const bool exists = wid < V.ntc && !(V.halo && (x0 == 0 || x0 == D.LX - TILE));
   const SweepState ss = *V.ss;
-  const double tau = ss.tau, root = ss.tree_root;
+  const double root = ss.tree_root;
+  // Time budget of this step: the quantum plus what the tile still owes.  A step stops after event_cap events
+  // (the slowest tile of a colour bounds the whole launch, and event counts per step have a long tail: bursts
+  // of deposit / re-evaporate pairs on one weakly bound site); the unspent time is carried to the tile's next
+  // step.  A tile that owes more than CS_MAX_LAG quanta runs uncapped, so the debt stays bounded.
+  double budget = ss.tau; int max_events_per_tile = event_cap;
+  if (exists) { const double lg = V.lag[l]; budget += lg; if (lg > CS_MAX_LAG * ss.tau) max_events_per_tile = 1 << 14; }
+  bool capped = false;
   // ---- load the tile's list (dropping tombstones when it has grown) ------------------------------------
-  {
+  if (exists) {
     const int n0 = V.cnt[l];
     const bool compact = n0 > CS_COMPACT_ABOVE;
     int n = 0;
@@ -200,79 +214,101 @@ __global__ void __launch_bounds__(CS_THREADS) colour_step_kernel(int colour, uin
     if (!compact) n = n0;
     if (tl == 0) *s_n = n;
   }
-  __syncwarp(tmask);
-  TileLists L; L.own = l; L.mark = V.halo; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
+  __syncwarp();
+  TileLists L; L.own = exists ? l : -2; L.mark = V.halo; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
   int nev = 0, ndep0 = 0, ndep1 = 0, ndep2 = 0, nevap = 0, nabs = 0, ndes = 0;
   uint32_t draw = 0;
   double tloc = 0.0, R = 0.0;
-  // All teams of the warp stay in the loop until the last one is done, and the full-warp vote at the top is a
-  // convergence point: the teams execute one event per iteration in lock step (a team that is done idles).
-  bool active = true;
-  while (__any_sync(0xFFFFFFFFu, active)) {
-    if (active) do {
-    const int n = *s_n;
+  bool active = exists;
+  while (__any_sync(FULL, active)) {
+    const int n = active ? *s_n : 0;
     // rate sum and inclusive prefix over the list (lane-strided chunks)
     double part = 0.0;
 #pragma unroll 1
     for (int i = tl; i < n; i += TEAM) part += s_rate[i];
     double incl = part;
 #pragma unroll
-    for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(tmask, incl, o, TEAM); if (tl >= o) incl += t; }
-    R = __shfl_sync(tmask, incl, TEAM - 1, TEAM);
-    if (!(R > 0.0) || nev >= max_events_per_tile) { active = false; break; }
+    for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(FULL, incl, o, TEAM); if (tl >= o) incl += t; }
+    const double Rn = __shfl_sync(FULL, incl, TEAM - 1, TEAM);
+    if (active) R = Rn;
+    // the cap never freezes a tile in a transient state that lives much shorter than the quantum (an unstable atom
+    // about to re-evaporate): such a state would also poison the total rate the next quantum is derived from
+    const bool more = active && (Rn > 0.0) && nev < (1 << 14);
+    bool go = more && (nev < max_events_per_tile || Rn * ss.tau >= CS_BURST * (double)event_cap);
+    if (more && !go) capped = true;
     // one counter-based draw per event: x -> waiting time, y + 20 bits of z -> target, 24 bits -> species, 20 bits -> arm-chair tie
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw++), key);
-    tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)R);
-    if (tloc > tau) { active = false; break; }
-    const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * R;
-    // the lane whose chunk contains the target, then the entry inside that lane's strided chunk
-    const unsigned m = (__ballot_sync(tmask, incl > target) >> tshift) & tm;
+    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw), key);
+    if (go) {
+      draw++;
+      tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)Rn);
+      if (tloc > budget) go = false;
+    }
+    const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * Rn;
+    // the lane whose strided chunk contains the target, then the team scans that chunk together
+    const unsigned m = (__ballot_sync(FULL, incl > target) >> tshift) & tm;
     const int sel = m ? (__ffs(m) - 1) : TEAM - 1;
-    int pick = -1;
-    if (tl == sel) {
-      double acc = incl - part; int last = -1;
-#pragma unroll 1
-      for (int i = tl; i < n; i += TEAM) { const double r = s_rate[i]; if (r > 0.0) { last = i; acc += r; if (acc > target) { pick = i; break; } } }
-      if (pick < 0) pick = last;
+    double acc = __shfl_sync(FULL, incl - part, sel, TEAM);        // rate mass before the chosen chunk
+    int pick = -1, last = -1;
+    bool searching = go;
+    for (int j0 = 0; __any_sync(FULL, searching); j0 += TEAM) {
+      const int i = sel + TEAM * (j0 + tl);
+      const double r = (searching && i < n) ? s_rate[i] : 0.0;
+      double in2 = r;
+#pragma unroll
+      for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(FULL, in2, o, TEAM); if (tl >= o) in2 += t; }
+      const unsigned hit = (__ballot_sync(FULL, r > 0.0 && acc + in2 > target) >> tshift) & tm;
+      const unsigned livem = (__ballot_sync(FULL, r > 0.0) >> tshift) & tm;
+      acc += __shfl_sync(FULL, in2, TEAM - 1, TEAM);
+      if (searching) {
+        if (livem) last = sel + TEAM * (j0 + 31 - __clz((int)livem));
+        if (hit) { pick = sel + TEAM * (j0 + __ffs(hit) - 1); searching = false; }
+        else if (sel + TEAM * (j0 + TEAM) >= n) { pick = last; searching = false; }
+      }
     }
-    pick = __shfl_sync(tmask, pick, sel, TEAM);
-    if (pick < 0) {                  // rounding left the chosen lane without a live entry: take the first live one
+    // rounding left the chosen chunk without a live entry: take the first live one of the list
+    const bool lost = go && pick < 0;
+    if (__any_sync(FULL, lost)) {
       int mine = -1;
+      if (lost) {
 #pragma unroll 1
-      for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
-      const unsigned mm = (__ballot_sync(tmask, mine >= 0) >> tshift) & tm;
-      if (!mm) { active = false; break; }
-      pick = __shfl_sync(tmask, mine, __ffs(mm) - 1, TEAM);
+        for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
+      }
+      const unsigned mm = (__ballot_sync(FULL, mine >= 0) >> tshift) & tm;
+      const int first = __shfl_sync(FULL, mine, mm ? __ffs(mm) - 1 : 0, TEAM);
+      if (lost) { if (mm) pick = first; else go = false; }
     }
-    const unsigned long long e = s_ce[pick];
+    active = go;
+    unsigned long long e = 0ull;
+    if (go) e = s_ce[pick];
     const uint32_t cell = (uint32_t)e; int Itrans = ce_event(e);
     P3 Site; Site.x = x0 + (int)((e >> 40) & 31u); Site.y = y0 + (int)((e >> 45) & 31u); Site.z = (int)(e >> 50);
-    if (Itrans == EV_DRAW) {         // species / adsorbate drawn now (Get_Prob.f:164-179)
+    if (go && Itrans == EV_DRAW) {   // species / adsorbate drawn now (Get_Prob.f:164-179)
       const uint32_t w = D.state[cell];
       const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
       Itrans = choose_dep_abs(w_coor(w), (FEAT & F_LA) ? site_T(w, Site) : 0, us, nullptr);
     }
     const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
-    if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++;
-    coop_event<TEAM, FEAT>(L, tl, tmask, Site, cell, Itrans, root, arm_u, -1, K);
-    nev++;
-    } while (false);
+    if (go) { if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++; }
+    coop_event<TEAM, FEAT>(L, tl, go, Site, cell, Itrans, root, arm_u, -1, K);
+    if (go) nev++;
   }
   // ---- write the list back, reduce the counters -----------------------------------------------------------
-  __syncwarp(tmask);
-  const int n = *s_n;
-#pragma unroll 1
-  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
+  __syncwarp();
   int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
 #pragma unroll
   for (int k = 0; k < 9; k++)
 #pragma unroll
-    for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(tmask, v[k], o, TEAM);
+    for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o, TEAM);
+  if (!exists) return;
+  const int n = *s_n;
+#pragma unroll 1
+  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
   if (tl == 0) {
     V.cnt[l] = n;
     V.tile_rate[l] = R;
+    V.lag[l] = capped ? budget - tloc : 0.0;
     TileStat &st = V.tstat[l];
     st.events += nev; st.site_updates += v[0];
     st.dep[0] += ndep0; st.dep[1] += ndep1; st.dep[2] += ndep2; st.evap += nevap; st.abs_ += nabs; st.des += ndes;
@@ -361,7 +397,7 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   for (long long i = 0; i < n; i++) {
     P3 S; S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2];
     const int arm = ev_arm[i];
-    coop_event<32, F_COV | F_LA>(L, lane, 0xFFFFFFFFu, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    coop_event<32, F_COV | F_LA>(L, lane, true, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
     done++;
     if (D.err[0] != 0) break;
   }
@@ -652,14 +688,14 @@ static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
   cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.pack_done); cudaFree(P.red);
   for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
-  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
+  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
   P.halo = halo; P.rank = rank; P.nranks = nranks; P.comm = comm;
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
   V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.slot = P.slot;
-  V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss;
+  V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; V.lag = P.lag;
   V.halo = P.halo; V.nranks = P.nranks; V.dirty_bits = P.dirty_bits; V.dirty_cell = P.dirty_cell; V.dirty_n = P.dirty_n; V.dirty_cap = P.dirty_cap; V.red = P.red;
   return V;
 }
@@ -672,6 +708,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
     PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
     PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
+    PCK(cudaMemsetAsync(P.lag, 0, (size_t)P.ntiles * sizeof(double), st));
     PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
     if (P.halo) { PCK(cudaMemsetAsync(P.dirty_bits, 0, P.dirty_words * 4, st)); PCK(cudaMemsetAsync(P.dirty_n, 0, 2 * sizeof(int), st)); }
     return 0;
@@ -683,6 +720,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
   PCK(cudaMalloc(&P.slot, (size_t)H.ncell * sizeof(uint16_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
+  PCK(cudaMalloc(&P.lag, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
   PCK(cudaMalloc(&P.ss, sizeof(SweepState)));
   PCK(cudaMalloc(&P.tot, sizeof(TileStat)));
@@ -707,6 +745,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
+  PCK(cudaMemsetAsync(P.lag, 0, (size_t)P.ntiles * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
   return 0;
 }
@@ -820,6 +859,12 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   const cs_kernel_t kern = teamsz == 8 ? kern8[feat] : kern32[feat];
   PCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 64));
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
+  // events one tile may execute in one colour step before the rest of its quantum is carried over (flags & 0xFFFF,
+  // 0 = default: three times the mean + 4; 0xFFFF = no cap)
+  int evcap = a->flags & 0xFFFF;
+  if (const char *e = getenv("MSKC_EVCAP")) evcap = atoi(e);
+  if (evcap == 0) evcap = (int)(3.0 * ept) + 4;
+  if (evcap == 0xFFFF) evcap = 1 << 14;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
   int launches = 0;
@@ -843,7 +888,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      kern<<<blocks, CS_THREADS, smem, st>>>(col, key, 1 << 14);
+      kern<<<blocks, CS_THREADS, smem, st>>>(col, key, evcap);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
       launches += 2;

@@ -1,2 +1,3 @@
 set -x
-time MSKC_FULL_GOLDEN=1 python -m pytest tests/test_host_gpu.py -x -q -k "cube-zigzag or sphere" 2>&1 | tail -5
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:colour_step -s 120 -c 1 -o gpurun_out/prof_r01e python scripts/probe_bench.py --ept 4 --sweeps 32 --warm 16 > gpurun_out/ncu_r01e.log 2>&1
+tail -3 gpurun_out/ncu_r01e.log
