@@ -201,7 +201,7 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel: every colour-step launch timed with CUDA events ---------
     rr = ctx.run_parallel(min(args.sweeps, 16), events_per_tile=args.ept, seed=seed + 999)
-    n_launch = 4 * rr.sweeps_done
+    n_launch = rr.sampler_launches
     alg_bytes = B_PER_SITE_UPDATE * rr.site_updates + B_PER_EVENT * rr.events_done
     peak, peak_src = peaks()
     achieved = alg_bytes / (rr.sweep_kernel_ms * 1e-3) / 1e9 if rr.sweep_kernel_ms > 0 else 0.0

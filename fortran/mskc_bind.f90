@@ -51,6 +51,7 @@ module mskc_bind
     integer(c_int32_t) :: launches
     real(c_float)      :: sweep_kernel_ms
     integer(c_int32_t) :: stop_reason
+    integer(c_int32_t) :: sampler_launches, pad
   end type
 
   type, bind(C) :: mskc_counters

@@ -118,7 +118,7 @@ typedef struct {
   uint64_t seed;             /* Philox key                                                          */
   int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
   int32_t  flags;            /* bits 0-15: events one tile may execute per colour step before the rest of its
-                              * quantum is carried to its next step (0 = default 3*events_per_tile+4,
+                              * quantum is carried to its next step (0 = default 3*events_per_tile,
                               * 0xFFFF = no cap); other bits reserved, 0                               */
 } mskc_parallel_args;
 
@@ -132,8 +132,10 @@ typedef struct {
   int64_t count_dep[3], count_evap, count_abs, count_des;
   float   kernel_ms;         /* device time of this call (CUDA events on the library's stream)      */
   int32_t launches;          /* kernels launched by this call                                       */
-  float   sweep_kernel_ms;   /* part of kernel_ms spent in the colour-step kernels                  */
+  float   sweep_kernel_ms;   /* part of kernel_ms spent in the sampler kernels (colour steps / sweep batches) */
   int32_t stop_reason;
+  int32_t sampler_launches;  /* how many sampler kernels those were (short calls time each one)     */
+  int32_t pad;
 } mskc_parallel_result;
 
 /* Synchronous-sublattice sampler: x-y tiles coloured 2x2, every tile of one colour runs its own

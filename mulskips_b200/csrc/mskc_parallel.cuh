@@ -160,6 +160,166 @@ enum { CS_COMPACT_ABOVE = 96 };
 #define CS_BURST 4.0                          /* a state expected to fire more than CS_BURST*cap events per quantum is transient */
 #define CS_MAX_LAG 6.0                        /* quanta of debt beyond which a tile's event cap is lifted */               // tombstones are dropped when a list is loaded with more entries than this
 
+// ---- one tile's colour step, as the team that owns it sees it -----------------------------------------------------
+// Everything here is team-uniform (every lane of the team holds the same value) except K, the per-lane counters.
+struct TileRun {
+  int l, x0, y0;                 // list id, tile origin
+  int nev, max_ev;               // events executed in this step, cap (see CS_BURST / CS_MAX_LAG)
+  bool capped;
+  uint32_t draw;                 // Philox draw counter inside the step
+  unsigned long long step;       // global colour-step counter (Philox counter words)
+  double tloc, budget, R;        // local clock, time budget of the step, current total rate of the tile
+  double tau, debt;              // the quantum, and the time the tile owed when the step began
+  int ndep0, ndep1, ndep2, nevap, nabs, ndes;
+  CoopCounters K;
+};
+__device__ __forceinline__ void tile_reset(TileRun &t) {
+  t.nev = 0; t.capped = false; t.draw = 0u; t.tloc = 0.0; t.R = 0.0;
+  t.ndep0 = t.ndep1 = t.ndep2 = t.nevap = t.nabs = t.ndes = 0;
+  t.K.nsu = 0; t.K.dAtoms = 0; t.K.dVoids = 0;
+  for (int i = 0; i < 3; i++) { t.K.dCrystal[i] = 0; t.K.dCov[i] = 0; }
+}
+// Time budget of a step.  A step stops after event_cap events (the slowest tile of a colour bounds the whole
+// launch, and event counts per step have a long tail: half of the tiles exceed four times the mean at least once
+// in 32 sweeps); the unspent time becomes the tile's debt, paid back at no more than one extra quantum per step so
+// that catching up rarely hits the cap again.  A tile that owes more than CS_MAX_LAG quanta may run twice the cap,
+// beyond four times that it runs uncapped: the debt stays bounded.
+__device__ __forceinline__ void tile_budget(TileRun &t, double tau, int event_cap) {
+  const double lg = V.lag[t.l];
+  t.tau = tau; t.debt = lg; t.budget = tau + fmin(lg, tau);
+  t.max_ev = lg > 4.0 * CS_MAX_LAG * tau ? (1 << 14) : (lg > CS_MAX_LAG * tau ? 2 * event_cap : event_cap);
+}
+// load the tile's list into the team's shared-memory mirror (dropping tombstones when it has grown); team-divergent
+template <int TEAM>
+__device__ __forceinline__ void tile_load(const int l, const int tl, const int tshift, const unsigned tm, double *s_rate, unsigned long long *s_ce, int *s_n) {
+  const unsigned tmask = tm << tshift;
+  const int n0 = V.cnt[l];
+  const bool compact = n0 > CS_COMPACT_ABOVE;
+  int n = 0;
+#pragma unroll 1
+  for (int base = 0; base < n0; base += TEAM) {
+    const int i = base + tl;
+    double r = 0.0; unsigned long long e = 0ull;
+    if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
+    if (!compact) { if (i < n0) { s_rate[i] = r; s_ce[i] = e; } }
+    else {
+      const bool live = (i < n0) && (r > 0.0);
+      const unsigned m = (__ballot_sync(tmask, live) >> tshift) & tm;
+      const int k = n + __popc(m & ((1u << tl) - 1u));
+      if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
+      else if (i < n0) V.slot[(uint32_t)e] = 0;
+      n += __popc(m);
+    }
+  }
+  if (!compact) n = n0;
+  if (tl == 0) *s_n = n;
+}
+// One lock-step iteration: every lane of the warp calls this together; a team with active == false only takes part
+// in the synchronisation.  Returns whether the team executed an event (false for an active team: its step is over).
+template <int TEAM, int FEAT>
+__device__ __forceinline__ bool tile_iteration(TileRun &t, TileLists &L, const bool active, const int tl, const int tshift, const unsigned tm,
+                                               const uint2 key, const double tau, const int event_cap, const double root) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const double *s_rate = L.s_rate;
+  const int n = active ? *L.s_n : 0;
+  // rate sum and inclusive prefix over the list (lane-strided chunks)
+  double part = 0.0;
+#pragma unroll 1
+  for (int i = tl; i < n; i += TEAM) part += s_rate[i];
+  double incl = part;
+#pragma unroll
+  for (int o = 1; o < TEAM; o <<= 1) { const double v = __shfl_up_sync(FULL, incl, o, TEAM); if (tl >= o) incl += v; }
+  const double Rn = __shfl_sync(FULL, incl, TEAM - 1, TEAM);
+  if (active) t.R = Rn;
+  // the cap never freezes a tile in a transient state that lives much shorter than the quantum (an unstable atom
+  // about to re-evaporate): such a state would also poison the total rate the next quantum is derived from
+  const bool more = active && (Rn > 0.0) && t.nev < (1 << 14);
+  bool go = more && (t.nev < t.max_ev || Rn * tau >= CS_BURST * (double)event_cap);
+  if (more && !go) t.capped = true;
+  // one counter-based draw per event: x -> waiting time, y + 20 bits of z -> target, 24 bits -> species, 20 bits -> arm-chair tie
+  const uint4 rnd = philox4x32_10(make_uint4((uint32_t)t.l, (uint32_t)t.step, (uint32_t)(t.step >> 32), t.draw), key);
+  if (go) {
+    t.draw++;
+    t.tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)Rn);
+    if (t.tloc > t.budget) go = false;
+  }
+  const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * Rn;
+  // the lane whose strided chunk contains the target, then the team scans that chunk together
+  const unsigned m = (__ballot_sync(FULL, incl > target) >> tshift) & tm;
+  const int sel = m ? (__ffs(m) - 1) : TEAM - 1;
+  double acc = __shfl_sync(FULL, incl - part, sel, TEAM);        // rate mass before the chosen chunk
+  int pick = -1, last = -1;
+  bool searching = go;
+  for (int j0 = 0; __any_sync(FULL, searching); j0 += TEAM) {
+    const int i = sel + TEAM * (j0 + tl);
+    const double r = (searching && i < n) ? s_rate[i] : 0.0;
+    double in2 = r;
+#pragma unroll
+    for (int o = 1; o < TEAM; o <<= 1) { const double v = __shfl_up_sync(FULL, in2, o, TEAM); if (tl >= o) in2 += v; }
+    const unsigned hit = (__ballot_sync(FULL, r > 0.0 && acc + in2 > target) >> tshift) & tm;
+    const unsigned livem = (__ballot_sync(FULL, r > 0.0) >> tshift) & tm;
+    acc += __shfl_sync(FULL, in2, TEAM - 1, TEAM);
+    if (searching) {
+      if (livem) last = sel + TEAM * (j0 + 31 - __clz((int)livem));
+      if (hit) { pick = sel + TEAM * (j0 + __ffs(hit) - 1); searching = false; }
+      else if (sel + TEAM * (j0 + TEAM) >= n) { pick = last; searching = false; }
+    }
+  }
+  // rounding left the chosen chunk without a live entry: take the first live one of the list
+  const bool lost = go && pick < 0;
+  if (__any_sync(FULL, lost)) {
+    int mine = -1;
+    if (lost) {
+#pragma unroll 1
+      for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
+    }
+    const unsigned mm = (__ballot_sync(FULL, mine >= 0) >> tshift) & tm;
+    const int first = __shfl_sync(FULL, mine, mm ? __ffs(mm) - 1 : 0, TEAM);
+    if (lost) { if (mm) pick = first; else go = false; }
+  }
+  unsigned long long e = 0ull;
+  if (go) e = L.s_ce[pick];
+  const uint32_t cell = (uint32_t)e; int Itrans = ce_event(e);
+  P3 Site; Site.x = t.x0 + (int)((e >> 40) & 31u); Site.y = t.y0 + (int)((e >> 45) & 31u); Site.z = (int)(e >> 50);
+  if (go && Itrans == EV_DRAW) {   // species / adsorbate drawn now (Get_Prob.f:164-179)
+    const uint32_t w = D.state[cell];
+    const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
+    Itrans = choose_dep_abs(w_coor(w), (FEAT & F_LA) ? site_T(w, Site) : 0, us, nullptr);
+  }
+  const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
+  if (go) { if (Itrans == 1) t.ndep0++; else if (Itrans == 2) t.ndep1++; else if (Itrans == 3) t.ndep2++; else if (Itrans == 4) t.nevap++; else if (Itrans == 5) t.ndes++; else t.nabs++; }
+  coop_event<TEAM, FEAT>(L, tl, go, Site, cell, Itrans, root, arm_u, -1, t.K);
+  if (go) t.nev++;
+  return go;
+}
+// End of a tile's step: every lane of the warp calls this together, the teams with fin == true write their list back
+// and add their counters to the tile's statistics.
+template <int TEAM>
+__device__ __forceinline__ void tile_finish(TileRun &t, const TileLists &L, const bool fin, const int tl) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  __syncwarp();
+  int v[9] = {t.K.nsu, t.K.dAtoms, t.K.dVoids, t.K.dCrystal[0], t.K.dCrystal[1], t.K.dCrystal[2], t.K.dCov[0], t.K.dCov[1], t.K.dCov[2]};
+#pragma unroll
+  for (int k = 0; k < 9; k++)
+#pragma unroll
+    for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o, TEAM);
+  if (!fin) return;
+  const int l = t.l, n = *L.s_n;
+#pragma unroll 1
+  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = L.s_rate[i]; V.ce[lidx(l, i)] = L.s_ce[i]; }
+  if (tl == 0) {
+    V.cnt[l] = n;
+    V.tile_rate[l] = t.R;
+    V.lag[l] = t.capped ? t.debt + t.tau - t.tloc : t.debt - fmin(t.debt, t.tau);
+    TileStat &st = V.tstat[l];
+    st.events += t.nev; st.site_updates += v[0];
+    st.dep[0] += t.ndep0; st.dep[1] += t.ndep1; st.dep[2] += t.ndep2; st.evap += t.nevap; st.abs_ += t.nabs; st.des += t.ndes;
+    st.dAtoms += v[1]; st.dVoids += v[2];
+    for (int i = 0; i < 3; i++) { st.dCrystal[i] += v[3 + i]; st.dCov[i] += v[6 + i]; }
+    if (t.nev > st.maxev) st.maxev = t.nev;
+  }
+}
+
 // One colour step: every tile of colour `colour` advances by tau.  A TEAM of lanes owns one tile
 // (mskc_coop.cuh); the 32/TEAM teams of a warp run their event loops in lock step: every lane of the warp
 // executes every iteration (full-mask votes and shuffles are the convergence points), a team without an event
@@ -172,150 +332,25 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int co
   const int lane = threadIdx.x & 31, tl = threadIdx.x % TEAM, tib = threadIdx.x / TEAM;
   const int tshift = lane - tl;
   const unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
-  const unsigned tmask = tm << tshift;
   const int wid = blockIdx.x * TPB + tib;
   const int cap = V.cap;
-  double *s_rate = reinterpret_cast<double *>(smem) + (size_t)tib * cap;
-  unsigned long long *s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)TPB * cap * 8) + (size_t)tib * cap;
-  int *s_n = reinterpret_cast<int *>(smem + (size_t)TPB * cap * 16) + tib;
-  const int l = colour * V.ntc + wid;
-  const int x0 = (2 * (wid % V.hx) + (colour & 1)) * TILE, y0 = (2 * (wid / V.hx) + (colour >> 1)) * TILE;   // tile origin (list_of inverted)
+  TileLists L; L.mark = V.halo;
+  L.s_rate = reinterpret_cast<double *>(smem) + (size_t)tib * cap;
+  L.s_ce = reinterpret_cast<unsigned long long *>(smem + (size_t)TPB * cap * 8) + (size_t)tib * cap;
+  L.s_n = reinterpret_cast<int *>(smem + (size_t)TPB * cap * 16) + tib;
+  TileRun t; tile_reset(t);
+  t.l = colour * V.ntc + wid;
+  t.x0 = (2 * (wid % V.hx) + (colour & 1)) * TILE; t.y0 = (2 * (wid / V.hx) + (colour >> 1)) * TILE;   // tile origin (list_of inverted)
   // a team beyond the last tile, or on a halo tile (it belongs to the neighbouring rank), idles through the step
-  const bool exists = wid < V.ntc && !(V.halo && (x0 == 0 || x0 == D.LX - TILE));
+  const bool exists = wid < V.ntc && !(V.halo && (t.x0 == 0 || t.x0 == D.LX - TILE));
   const SweepState ss = *V.ss;
-  const double root = ss.tree_root;
-  // Time budget of this step: the quantum plus what the tile still owes.  A step stops after event_cap events
-  // (the slowest tile of a colour bounds the whole launch, and event counts per step have a long tail: bursts
-  // of deposit / re-evaporate pairs on one weakly bound site); the unspent time is carried to the tile's next
-  // step.  A tile that owes more than CS_MAX_LAG quanta runs uncapped, so the debt stays bounded.
-  double budget = ss.tau; int max_events_per_tile = event_cap;
-  if (exists) { const double lg = V.lag[l]; budget += lg; if (lg > CS_MAX_LAG * ss.tau) max_events_per_tile = 1 << 14; }
-  bool capped = false;
-  // ---- load the tile's list (dropping tombstones when it has grown) ------------------------------------
-  if (exists) {
-    const int n0 = V.cnt[l];
-    const bool compact = n0 > CS_COMPACT_ABOVE;
-    int n = 0;
-#pragma unroll 1
-    for (int base = 0; base < n0; base += TEAM) {
-      const int i = base + tl;
-      double r = 0.0; unsigned long long e = 0ull;
-      if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
-      if (!compact) { if (i < n0) { s_rate[i] = r; s_ce[i] = e; } }
-      else {
-        const bool live = (i < n0) && (r > 0.0);
-        const unsigned m = (__ballot_sync(tmask, live) >> tshift) & tm;
-        const int k = n + __popc(m & ((1u << tl) - 1u));
-        if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
-        else if (i < n0) V.slot[(uint32_t)e] = 0;
-        n += __popc(m);
-      }
-    }
-    if (!compact) n = n0;
-    if (tl == 0) *s_n = n;
-  }
+  t.step = (unsigned long long)ss.step; t.budget = t.tau = ss.tau; t.debt = 0.0; t.max_ev = event_cap;
+  L.own = exists ? t.l : -2;
+  if (exists) { tile_budget(t, ss.tau, event_cap); tile_load<TEAM>(t.l, tl, tshift, tm, L.s_rate, L.s_ce, L.s_n); }
   __syncwarp();
-  TileLists L; L.own = exists ? l : -2; L.mark = V.halo; L.s_rate = s_rate; L.s_ce = s_ce; L.s_n = s_n;
-  CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
-  for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
-  int nev = 0, ndep0 = 0, ndep1 = 0, ndep2 = 0, nevap = 0, nabs = 0, ndes = 0;
-  uint32_t draw = 0;
-  double tloc = 0.0, R = 0.0;
   bool active = exists;
-  while (__any_sync(FULL, active)) {
-    const int n = active ? *s_n : 0;
-    // rate sum and inclusive prefix over the list (lane-strided chunks)
-    double part = 0.0;
-#pragma unroll 1
-    for (int i = tl; i < n; i += TEAM) part += s_rate[i];
-    double incl = part;
-#pragma unroll
-    for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(FULL, incl, o, TEAM); if (tl >= o) incl += t; }
-    const double Rn = __shfl_sync(FULL, incl, TEAM - 1, TEAM);
-    if (active) R = Rn;
-    // the cap never freezes a tile in a transient state that lives much shorter than the quantum (an unstable atom
-    // about to re-evaporate): such a state would also poison the total rate the next quantum is derived from
-    const bool more = active && (Rn > 0.0) && nev < (1 << 14);
-    bool go = more && (nev < max_events_per_tile || Rn * ss.tau >= CS_BURST * (double)event_cap);
-    if (more && !go) capped = true;
-    // one counter-based draw per event: x -> waiting time, y + 20 bits of z -> target, 24 bits -> species, 20 bits -> arm-chair tie
-    const uint4 rnd = philox4x32_10(make_uint4((uint32_t)l, (uint32_t)ss.step, (uint32_t)(ss.step >> 32), draw), key);
-    if (go) {
-      draw++;
-      tloc += (double)__fdividef(-__logf(((float)rnd.x + 0.5f) * 2.3283064365386963e-10f), (float)Rn);
-      if (tloc > budget) go = false;
-    }
-    const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * Rn;
-    // the lane whose strided chunk contains the target, then the team scans that chunk together
-    const unsigned m = (__ballot_sync(FULL, incl > target) >> tshift) & tm;
-    const int sel = m ? (__ffs(m) - 1) : TEAM - 1;
-    double acc = __shfl_sync(FULL, incl - part, sel, TEAM);        // rate mass before the chosen chunk
-    int pick = -1, last = -1;
-    bool searching = go;
-    for (int j0 = 0; __any_sync(FULL, searching); j0 += TEAM) {
-      const int i = sel + TEAM * (j0 + tl);
-      const double r = (searching && i < n) ? s_rate[i] : 0.0;
-      double in2 = r;
-#pragma unroll
-      for (int o = 1; o < TEAM; o <<= 1) { const double t = __shfl_up_sync(FULL, in2, o, TEAM); if (tl >= o) in2 += t; }
-      const unsigned hit = (__ballot_sync(FULL, r > 0.0 && acc + in2 > target) >> tshift) & tm;
-      const unsigned livem = (__ballot_sync(FULL, r > 0.0) >> tshift) & tm;
-      acc += __shfl_sync(FULL, in2, TEAM - 1, TEAM);
-      if (searching) {
-        if (livem) last = sel + TEAM * (j0 + 31 - __clz((int)livem));
-        if (hit) { pick = sel + TEAM * (j0 + __ffs(hit) - 1); searching = false; }
-        else if (sel + TEAM * (j0 + TEAM) >= n) { pick = last; searching = false; }
-      }
-    }
-    // rounding left the chosen chunk without a live entry: take the first live one of the list
-    const bool lost = go && pick < 0;
-    if (__any_sync(FULL, lost)) {
-      int mine = -1;
-      if (lost) {
-#pragma unroll 1
-        for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
-      }
-      const unsigned mm = (__ballot_sync(FULL, mine >= 0) >> tshift) & tm;
-      const int first = __shfl_sync(FULL, mine, mm ? __ffs(mm) - 1 : 0, TEAM);
-      if (lost) { if (mm) pick = first; else go = false; }
-    }
-    active = go;
-    unsigned long long e = 0ull;
-    if (go) e = s_ce[pick];
-    const uint32_t cell = (uint32_t)e; int Itrans = ce_event(e);
-    P3 Site; Site.x = x0 + (int)((e >> 40) & 31u); Site.y = y0 + (int)((e >> 45) & 31u); Site.z = (int)(e >> 50);
-    if (go && Itrans == EV_DRAW) {   // species / adsorbate drawn now (Get_Prob.f:164-179)
-      const uint32_t w = D.state[cell];
-      const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
-      Itrans = choose_dep_abs(w_coor(w), (FEAT & F_LA) ? site_T(w, Site) : 0, us, nullptr);
-    }
-    const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
-    if (go) { if (Itrans == 1) ndep0++; else if (Itrans == 2) ndep1++; else if (Itrans == 3) ndep2++; else if (Itrans == 4) nevap++; else if (Itrans == 5) ndes++; else nabs++; }
-    coop_event<TEAM, FEAT>(L, tl, go, Site, cell, Itrans, root, arm_u, -1, K);
-    if (go) nev++;
-  }
-  // ---- write the list back, reduce the counters -----------------------------------------------------------
-  __syncwarp();
-  int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
-#pragma unroll
-  for (int k = 0; k < 9; k++)
-#pragma unroll
-    for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o, TEAM);
-  if (!exists) return;
-  const int n = *s_n;
-#pragma unroll 1
-  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = s_rate[i]; V.ce[lidx(l, i)] = s_ce[i]; }
-  if (tl == 0) {
-    V.cnt[l] = n;
-    V.tile_rate[l] = R;
-    V.lag[l] = capped ? budget - tloc : 0.0;
-    TileStat &st = V.tstat[l];
-    st.events += nev; st.site_updates += v[0];
-    st.dep[0] += ndep0; st.dep[1] += ndep1; st.dep[2] += ndep2; st.evap += nevap; st.abs_ += nabs; st.des += ndes;
-    st.dAtoms += v[1]; st.dVoids += v[2];
-    for (int i = 0; i < 3; i++) { st.dCrystal[i] += v[3 + i]; st.dCov[i] += v[6 + i]; }
-    if (nev > st.maxev) st.maxev = nev;
-  }
+  while (__any_sync(FULL, active)) active = tile_iteration<TEAM, FEAT>(t, L, active, tl, tshift, tm, key, ss.tau, event_cap, ss.tree_root);
+  tile_finish<TEAM>(t, L, exists, tl);
 }
 
 // ---- halo exchange (x-decomposed slabs) ------------------------------------------------------
@@ -860,10 +895,10 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   PCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 64));
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   // events one tile may execute in one colour step before the rest of its quantum is carried over (flags & 0xFFFF,
-  // 0 = default: three times the mean + 4; 0xFFFF = no cap)
+  // 0 = default: three times the target mean; 0xFFFF = no cap)
   int evcap = a->flags & 0xFFFF;
   if (const char *e = getenv("MSKC_EVCAP")) evcap = atoi(e);
-  if (evcap == 0) evcap = (int)(3.0 * ept) + 4;
+  if (evcap == 0) evcap = std::max(4, (int)(3.0 * ept));
   if (evcap == 0xFFFF) evcap = 1 << 14;
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
@@ -876,12 +911,13 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     launches += 1;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
-  // short calls time every colour-step kernel on its own (CUDA events on the launching stream): this is
+  // short calls time every sampler kernel on its own (CUDA events on the launching stream): this is
   // the per-launch duration the roofline in bench.py is computed from
   const bool timed = a->n_sweeps > 0 && a->n_sweeps <= 64;
   std::vector<cudaEvent_t> evs;
   if (timed) { evs.resize((size_t)a->n_sweeps * 8); for (auto &e : evs) PCK(cudaEventCreate(&e)); }
   size_t ke = 0;
+  int n_sampler_launches = 0;
   for (long long s = 0; s < a->n_sweeps; s++) {
     // fixed colour order every sweep (an alternating ABCD/DCBA order was measured WORSE: a colour then runs twice
     // in a row, doubling its effective quantum -- DESIGN.md section 5.3)
@@ -891,7 +927,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
       kern<<<blocks, CS_THREADS, smem, st>>>(col, key, evcap);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
-      launches += 2;
+      launches += 2; n_sampler_launches++;
       if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
     }
     if (sweep_totals(P, st, ept, a->tau_fixed, 1, &launches, err)) return -1;
@@ -906,7 +942,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   PCK(cudaEventElapsedTime(&r->kernel_ms, e0, e1));
   if (timed) {
     float tot = 0;
-    for (size_t i = 0; i + 1 < evs.size(); i += 2) { float ms = 0; PCK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); tot += ms; }
+    for (size_t i = 0; i + 1 < ke; i += 2) { float ms = 0; PCK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1])); tot += ms; }
     r->sweep_kernel_ms = tot;
     for (auto &e : evs) cudaEventDestroy(e);
   }
@@ -916,7 +952,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   for (int i = 0; i < 3; i++) r->count_dep[i] = P.h_tot.dep[i] - before.dep[i];
   r->count_evap = P.h_tot.evap - before.evap; r->count_abs = P.h_tot.abs_ - before.abs_; r->count_des = P.h_tot.des - before.des;
   r->launches = launches; r->stop_reason = P.h_tot.maxev;   /* diagnostic: max events of one tile in one colour step */
-  (void)ke;
+  r->sampler_launches = n_sampler_launches;
   P.time = P.h_ss.time;
   return 0;
 }

@@ -5,7 +5,7 @@
 // DefAtEnergy.dat and the optional checkpoint / Coor files in the cwd.  The reference is Fortran; no Fortran
 // compiler exists in this image, so the host side is C++ and keeps main.f's structure: parse start.dat
 // (main.f:83-212, mcevent/SetProbability.f), build the initial geometry with the reference's builders
-// (initial/SetSi.f, SetSiC3C.f, SetNC.f, SetNCSp.f), hand LattCoo + the three particle lists to the GPU library,
+// (initial/SetSi.f, SetSiC3C.f, SetNC.f, SetNCSp.f, SetInvPOff.f, SetSiFINFET.f, SetCAD.f, SetT.f), hand LattCoo + the three particle lists to the GPU library,
 // and drive the KMC loop (main.f:304-371) through mskc_run_parity -- which returns at every output frame so the
 // files are written at the reference's cadence -- or, with --parallel, through the sublattice sampler.
 // The loop body itself (everything under mcevent/ and lattice/) runs in CUDA; nothing here computes events.
@@ -14,6 +14,7 @@
 // `make`).  Here: --box X Y Z, else $MSKC_BOX, else the LenX line of <exe dir>/modules/defsystem.f if such a
 // file exists (the file pymulskips edits), else 480 480 480 (the regression suite's size).
 #include "../../include/mskc.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdint>
@@ -46,6 +47,12 @@ struct Host {
   std::string InitSt, RunType, ExitStrategy, SaveFinalState, SaveCoo, restartfile, coofile;
   int Len1 = 0, Len2 = 0, Len3 = 0, Len4 = 0, Idum = 0;
   double PtransZig = 1.0, sf = 1.0, MaxTime = 0, OutTime = 0, alloy = 0;
+  // InitSt IN / LA (main.f:112-141): geometry and temperature files, LA rate law, nucleus geometry
+  std::string cadfile, tempfile, Homogeneous;
+  double Tm = 0, P0 = 0, sigma = 0, Tflex = 0, LenVac = 0, LenNuc = 0;
+  int tmax = 0;                   // main.f:288-291: only the checkpoint branch of SetCAD.f updates it (the regression log prints 0)
+  int t_lo = 0, t_hi = 0;         // range of the temperature field, for the device's per-kelvin rate tables
+  bool la() const { return InitSt == "LA"; }
   long long MaxIter = 0, OutMolMol = 0;
   std::vector<double> PE = std::vector<double>(12288, 0.0), PD = std::vector<double>(9, 0.0), PA = std::vector<double>(12, 0.0), PS = std::vector<double>(12, 0.0);
   // state built by the initialiser (module globals of defsystem.f)
@@ -90,10 +97,19 @@ struct Host {
     update_tree((int)mc.size(), p);
   }
   void AddBulk(const int32_t s[3], const int32_t nn[4][3]) { Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); bulk.push_back(a); }
+  void AddVoid(const int32_t s[3], const int32_t nn[4][3]) {                    // Add.f:83-101
+    Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); voids.push_back(a);
+    if ((int)voids.size() >= 100000) die(" troppi vuoti");
+  }
+  // LA rate law, Get_Prob.f:143-148 / Get_Prob_Ini.f:75-79 (glibc exp/erf, as the gfortran build)
+  double la_PE(int T, double e) const { return P0 * exp(-e / (0.00008617330350 * T)) * (e != 0.0 ? 1.0 : 0.0); }
+  double la_PD(int T, double d) const { return 0.5 * P0 * exp(-d / (0.00008617330350 * Tm)) * (1.0 + erf((T - Tflex) / sigma)) * (d != 0.0 ? 1.0 : 0.0); }
+  int site_T(const int32_t s[3]) { int t = ibits(at(s), PosT, LenT); if (t == 0) die(" Temperature is zero in get_prob_ini(). %d %d %d", s[0], s[1], s[2]); return t; }
 
   // deposition / adsorption draw of Get_Prob.f:160-179 (pre-drawn species; one ran3 call)
-  void draw_dep_abs(int Coor, bool with_abs, int &ev, double &prob) {
+  void draw_dep_abs(int Coor, bool with_abs, int &ev, double &prob, int T = 0) {
     double PD1 = PD[0 + 3 * (Coor - 1)], PD2 = PD[1 + 3 * (Coor - 1)], PD3 = PD[2 + 3 * (Coor - 1)];
+    if (T > 0) { PD1 = la_PD(T, PD1); PD2 = la_PD(T, PD2); PD3 = la_PD(T, PD3); }
     double PDep = PD1 + PD2 + PD3, PAbs = 0;
     if (with_abs) for (int k = 1; k <= 3; k++) PAbs += PA[(k - 1) + 3 * Coor];
     double Ptot = PDep + PAbs, Pcurr = ran3() * Ptot;
@@ -113,12 +129,13 @@ struct Host {
   // mcevent/Get_Prob_Ini.f:23-161 (init-time rating: no reciprocity test, walls / coverage count as N_cov)
   void get_prob_ini(int Occ, int NSiC, int Coor, const int32_t s[3], const int32_t nn[4][3], int &ev, double &prob) {
     ev = 0; prob = 0.0;
+    const int T = la() ? site_T(s) : 0;
     if (Occ == 0) {
       bool draw = false;
       if (Coor == 1) { if (ibits(at(nn[0]), PosCoor, LenCoor) >= 2) draw = true; else { ev = 1; prob = (double)1.e-6f; } }
       else if (Coor == 2 || Coor == 3) draw = true;
       else if (Coor == 4) printf(" %d Get Prob Vacancy Generation\n", Coor);
-      if (draw) draw_dep_abs(Coor, false, ev, prob);
+      if (draw) draw_dep_abs(Coor, false, ev, prob, T);
       return;
     }
     int N_Si = 0, N_C = 0, N_B = 0, N_cov = 0;
@@ -132,8 +149,7 @@ struct Host {
     if (n > 3) return;
     ev = 4;
     if (n == 0) { prob = (double)100000.f * Tree[1]; printf(" %d Get Prob Isolated Atom\n", Coor); }
-    else prob = PE[idxE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)];
-    (void)s;
+    else { prob = PE[idxE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)]; if (T > 0) prob = la_PE(T, prob); }
   }
 };
 
@@ -211,8 +227,19 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   if (H.NCov > 0) { printf(" Coverage species (NCov= %d ) --> Z:", H.NCov); for (int i = 0; i < H.NCov; i++) printf(" %d", H.ListCov[i]); printf("\n"); }
   H.InitSt = first_token(in.next()).substr(0, 2);
   if (H.InitSt == "FF") { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); H.Len4 = (int)strtol(p, &p, 10); }
-  else if (H.InitSt == "IN" || H.InitSt == "SH" || H.InitSt == "LA" || H.InitSt == "ST")
-    die(" mulskips.e (B200 host): InitSt %s is not built yet -- geometry from file / temperature field (see DESIGN.md section 9)", H.InitSt.c_str());
+  else if (H.InitSt == "SH" || H.InitSt == "ST")
+    die(" mulskips.e (B200 host): InitSt %s is not built (SetShape / tabulated-temperature trench; see DESIGN.md section 10)", H.InitSt.c_str());
+  else if (H.InitSt == "IN") H.cadfile = whole_line(in.next());                         // main.f:108-111, read with '(A)'
+  else if (H.InitSt == "LA") {                                                          // main.f:112-141
+    printf(" ****** MulSKIPs run for laser annealing ******\n");
+    if (H.NCov > 0) die(" ERR NOT IMPLEMENTED: NCov=0 for LA");
+    H.cadfile = whole_line(in.next()); H.tempfile = whole_line(in.next());
+    H.Tm = fnum(in.next()); H.P0 = fnum(in.next()); H.sigma = fnum(in.next()); H.Tflex = fnum(in.next());
+    printf(" Melting temperature in Kelvin:  %.17g\n", H.Tm);
+    H.LenVac = fnum(in.next()); printf(" Top air thickness (ang):  %.17g\n", H.LenVac);
+    H.LenNuc = fnum(in.next()); printf(" Nucleus thickness (ang):  %.17g\n", H.LenNuc);
+    H.Homogeneous = first_token(in.next()).substr(0, 2); printf(" Model homogeneous nucleation: %s\n", H.Homogeneous.c_str());
+  }
   else { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); }
   // main.f:142-149 (the ALL(...) test with NCrystal=1 behaves as "not SiGe", SURVEY 8c trap 5)
   if ((H.NCrystal == 2 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32) || (H.NCrystal == 3 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32 && H.ListCrystal[2] == 5)) {
@@ -235,7 +262,10 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   else printf(" SaveFinalState flag is not \"T\": checkpoint file will  not be written.\n");
   H.SaveCoo = first_token(in.next()).substr(0, 2);
   if (H.SaveCoo == "T") { H.coofile = whole_line(in.next()); printf(" ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", H.coofile.c_str()); }
-  else printf(" SaveCoo flag is not \"T\": Coor file not stored\n");
+  else {
+    if (H.la()) die(" ERR: SaveCoo flag must be \"T\" for LA simulations!");
+    printf(" SaveCoo flag is not \"T\": Coor file not stored\n");
+  }
   set_probability(H, in);
   fclose(in.f);
   printf(" numParticelle= %d Levels = %d , SizeTree = %d\n", 500000, 20, (1 << 20) - 1);
@@ -260,8 +290,9 @@ void dia_nn(const Host &H, int x, int y, int z, int kind, int32_t nn[4][3]) {
     if (nn[i][1] < 0) nn[i][1] += H.LY;
   }
 }
-void wall_planes(Host &H, int z0, int z1) {
-  for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << PosOcc; mvbits(113, LenIndex, w, PosIndex); }
+void wall_planes(Host &H, int z0, int z1, int x0 = 0, int x1 = -1) {
+  if (x1 < 0) x1 = H.LX - 1;
+  for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = x0; x <= x1; x++) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << PosOcc; mvbits(113, LenIndex, w, PosIndex); }
 }
 // initial/SetSi.f:25-221 (walls, one species) and initial/SetSiC3C.f:25-199 (no walls, Si/C): flat (001) slab
 void set_flat(Host &H, int Len, bool walls, bool two_species) {
@@ -276,38 +307,49 @@ void set_flat(Host &H, int Len, bool walls, bool two_species) {
   scan(Len, Len, [&](int32_t &w, int) { mvbits(2, LenCoor, w, PosCoor); int ev; double p; H.draw_dep_abs(2, true, ev, p); H.AddMC(s, nn, ev, p); });   // Get_Prob(0,0,0,2,..)
   if (walls) wall_planes(H, H.LZ - 6, H.LZ - 1);
 }
-// "Set the coordination" / "Set the probability" passes of SetNC.f:60-233 (shared by SetNCSp.f)
-void pass_coordination(Host &H, int z0, int z1, int y0, int y1, int x0, int x1) {
+// "Set the coordination" / "Set the probability" passes shared by the centre-of-box and file-driven builders:
+// SetNC.f:60-233, SetInvPOff.f:105-284, SetSiFINFET.f:120-309 (wall aware), SetCAD.f:196-418 (wall aware, vacancies)
+void pass_coordination(Host &H, int z0, int z1, int y0, int y1, int x0, int x1, bool wallaware = false) {
   int32_t nn[4][3]; int kind;
   for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
-    if (!cubic_site(x, y, z, kind)) continue;
     int32_t &w = H.L[H.ci(x, y, z)];
+    if (wallaware && ibits(w, PosIndex, LenIndex) == 113) continue;
+    if (!cubic_site(x, y, z, kind)) continue;
     int Occ = ibits(w, PosOcc, 1), Coor = 0;
     dia_nn(H, x, y, z, kind, nn);
-    for (int i = 0; i < 4; i++) if (ibits(H.at(nn[i]), PosOcc, 1) > 0) Coor++;
-    if (Occ != 0 && Coor == 0) {
-      w = 0;
+    for (int i = 0; i < 4; i++) {
+      int32_t wn = H.at(nn[i]);
+      if (ibits(wn, PosOcc, 1) == 0) continue;
+      if (!wallaware || Occ > 0 || ibits(wn, PosIndex, LenIndex) != 113) Coor++;       // an empty site does not count walls (SetSiFINFET.f:150-160)
+    }
+    if (Occ != 0 && Coor == 0) {                            // isolated atom: removed, its neighbours forget it
+      int t = ibits(w, PosT, LenT); w = 0; if (H.la()) mvbits(t, LenT, w, PosT);       // (LA keeps the temperature bits, SetCAD.f:228-232)
       for (int i = 0; i < 4; i++) { int32_t &wn = H.at(nn[i]); int c = ibits(wn, PosCoor, LenCoor) - 1; if (c < 0) c = 0; mvbits(c, LenCoor, wn, PosCoor); }
     } else mvbits(Coor, LenCoor, w, PosCoor);
   }
 }
-void pass_probability(Host &H, int z0, int z1, int y0, int y1, int x0, int x1) {
+void pass_probability(Host &H, int z0, int z1, int y0, int y1, int x0, int x1, bool wallaware = false, bool cadvoid = false) {
   int32_t s[3], nn[4][3], keep[3] = {0, 0, 0}; int kind, ev; double p;
   for (int z = z0; z <= z1; z++) for (int y = y0; y <= y1; y++) for (int x = x0; x <= x1; x++) {
-    if (!cubic_site(x, y, z, kind)) continue;
     int32_t w = H.L[H.ci(x, y, z)];
+    if (wallaware && ibits(w, PosIndex, LenIndex) == 113) continue;
+    if (!cubic_site(x, y, z, kind)) continue;
     s[0] = x; s[1] = y; s[2] = z;
     dia_nn(H, x, y, z, kind, nn);
     int Occ = ibits(w, PosOcc, 1), Coor = ibits(w, PosCoor, LenCoor);
     if (Occ != 0 && Coor == 0) printf(" error %d %d %d %d %d\n", x, y, z, Occ, Coor);
     if (Occ == 0) {
       if (Coor > 0) {
-        if (Coor == 1) {                                     // keep the single occupied neighbour in slot 1 (SetNC.f:166-185)
-          for (int i = 0; i < 4; i++) { if (ibits(H.at(nn[i]), PosOcc, 1) != 0) memcpy(keep, nn[i], 12); nn[i][0] = nn[i][1] = nn[i][2] = 0; }
+        if (Coor == 1) {                                     // keep the single occupied (non-wall) neighbour in slot 1 (SetNC.f:166-185)
+          for (int i = 0; i < 4; i++) {
+            int32_t wn = H.at(nn[i]);
+            if (ibits(wn, PosOcc, 1) != 0 && !(wallaware && ibits(wn, PosIndex, LenIndex) == 113)) memcpy(keep, nn[i], 12);
+            nn[i][0] = nn[i][1] = nn[i][2] = 0;
+          }
           memcpy(nn[0], keep, 12);
         }
-        H.get_prob_ini(0, 0, Coor, s, nn, ev, p);
-        H.AddMC(s, nn, ev, p);
+        if (cadvoid && Coor == 4) { printf(" Initializing a vacancy\n"); H.AddVoid(s, nn); }      // SetCAD.f:340-346
+        else { H.get_prob_ini(0, 0, Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
       }
     } else if (Coor <= 3) { H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
     else H.AddBulk(s, nn);
@@ -326,6 +368,122 @@ void set_nc(Host &H, int Len1, int Len2, int Len3, bool sphere) {
   const int z0 = LZ / 2 - Len3 / 2 - 10, z1 = LZ / 2 + Len3 / 2 + 9, y0 = LY / 2 - Len2 / 2 - 10, y1 = LY / 2 + Len2 / 2 + 9, x0 = LX / 2 - Len1 / 2 - 10, x1 = LX / 2 + Len1 / 2 + 9;
   pass_coordination(H, z0, z1, y0, y1, x0, x1);
   pass_probability(H, z0, z1, y0, y1, x0, x1);
+}
+
+void occupy(Host &H, int x, int y, int z, int kind, bool two_species) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << ((kind && two_species) ? PosC : PosSi); w |= 1 << PosOcc; }
+// initial/SetInvPOff.f:22-286: 3C-SiC substrate with an array of inverted pyramids (one in the box centre, one on the corners)
+void set_invp_off(Host &H, int Len, int Len3) {
+  int kind, LX = H.LX, LY = H.LY; int32_t s[3], nn[4][3];
+  const int Lenh = LX / 2 - 1;
+  printf(" %d %d %d\n", Lenh, Len, Len3);
+  for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind)) {
+      occupy(H, x, y, z, kind, true); mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (!cubic_site(x, y, z, kind)) continue;
+    const float zt = 1.10f * (float)(z - Len3);              // REAL(4) arithmetic of SetInvPOff.f:78-82
+    auto pyr = [&](int ax, int ay) { return ((float)(std::abs(ax) + std::abs(ay)) - zt) <= (float)Len; };
+    if (!(pyr(x - Lenh, y - Lenh) || pyr(x, y) || pyr(x - LX, y) || pyr(x, y - LY) || pyr(x - LX, y - LY))) occupy(H, x, y, z, kind, true);
+  }
+  pass_coordination(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
+  pass_probability(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
+}
+// initial/SetSiFINFET.f:25-312: Si fin between two wall blocks, wall cap above
+void set_finfet(Host &H, int Len, int Lenww, int Lenwwtop, int Laperture) {
+  int kind, LX = H.LX, LY = H.LY, LZ = H.LZ;
+  wall_planes(H, 0, 5);
+  wall_planes(H, Lenww, LZ - 7, 0, (int)(0.5f * (float)(LX - Laperture)) - 1);
+  wall_planes(H, Lenww, LZ - 7, (int)(0.5f * (float)(LX + Laperture)), LX - 1);
+  wall_planes(H, Lenwwtop, LZ - 7);
+  wall_planes(H, LZ - 6, LZ - 1);
+  for (int z = 6; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (ibits(H.L[H.ci(x, y, z)], PosIndex, LenIndex) != 113 && cubic_site(x, y, z, kind)) occupy(H, x, y, z, kind, false);
+  pass_coordination(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
+  pass_probability(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
+}
+// One list-directed READ of a plane of LenX*LenY numbers (LattGeo / TempStat / checkpoint files): starts on a fresh
+// record, continues onto following records while values are missing, and drops what is left of the last record read.
+void read_plane(FILE *f, std::vector<double> &buf, const char *what) {
+  static char *line = nullptr; static size_t cap = 0;
+  size_t got = 0;
+  while (got < buf.size()) {
+    if (getline(&line, &cap, f) < 0) die(" short read in %s", what);
+    char *p = line, *e;
+    while (got < buf.size()) { double v = strtod(p, &e); if (e == p) break; buf[got++] = v; p = e; while (*p == ',') p++; }
+  }
+}
+// initial/SetT.f:25-50: integer kelvin of every cell into bits 9-21 (10 marks a wall cell: left alone)
+void set_T(Host &H) {
+  printf(" Reading input temperature file: %s\n", H.tempfile.c_str());
+  FILE *f = fopen(H.tempfile.c_str(), "r"); if (!f) die(" cannot open %s", H.tempfile.c_str());
+  std::vector<double> buf((size_t)H.LX * H.LY);
+  H.t_lo = 1 << 30; H.t_hi = 0;
+  for (int z = 0; z < H.LZ; z++) {
+    read_plane(f, buf, "temperature file");
+    for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) {
+      int t = (int)buf[x + (size_t)H.LX * y];
+      if (t != 10) { mvbits(t, LenT, H.L[H.ci(x, y, z)], PosT); if (t > 0) { H.t_lo = std::min(H.t_lo, t); H.t_hi = std::max(H.t_hi, t); } }
+    }
+  }
+  fclose(f);
+  printf(" Done reading input temperatures file\n");
+}
+// initial/SetCAD.f:25-421: geometry voxelised offline (0 empty, 1 crystal, 10 wall), one z plane per record; RunType 'C'
+// reads a checkpoint (the lattice words themselves) instead.
+void set_cad(Host &H) {
+  int kind, LX = H.LX, LY = H.LY, LZ = H.LZ; const bool la = H.la();
+  std::vector<double> buf((size_t)LX * LY);
+  if (H.alloy > 0) printf(" Setting up a SiGe layer with fraction = %.17g\n", H.alloy); else printf(" Setting up Silicon\n");
+  FILE *f = fopen(H.cadfile.c_str(), "r"); if (!f) die(" cannot open %s", H.cadfile.c_str());
+  if (H.RunType == "C") {                                     // SetCAD.f:54-79
+    printf(" Reading checkpoint file %s\n", H.cadfile.c_str());
+    for (int z = 0; z < LZ; z++) {
+      read_plane(f, buf, "checkpoint file");
+      for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        int32_t &w = H.L[H.ci(x, y, z)]; const int t = ibits(w, PosT, LenT);
+        w = (int32_t)buf[x + (size_t)LX * y];
+        if (la) { mvbits(t, LenT, w, PosT); H.tmax = std::max(H.tmax, t); }
+      }
+    }
+    printf(" Done reading checkpoint file\n");
+  } else {
+    wall_planes(H, 0, 3); wall_planes(H, LZ - 4, LZ - 1);
+    printf(" Reading input geometry file: %s\n", H.cadfile.c_str());
+    // SetCAD.f:99-102 skips the records of the four bottom wall planes.  The build that produced the regression
+    // goldens did not (file record k lands on z = k+4): MSKC_CAD_NOSKIP=1 selects that legacy offset.
+    if (!getenv("MSKC_CAD_NOSKIP")) for (int z = 0; z <= 3; z++) read_plane(f, buf, "geometry file");
+    unsigned long long lcg = 88172645463325252ull;
+    for (int z = 4; z <= LZ - 5; z++) {
+      read_plane(f, buf, "geometry file");
+      for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        const int Id = (int)buf[x + (size_t)LX * y];
+        int32_t &w = H.L[H.ci(x, y, z)];
+        if (Id == 10) { w |= 1 << PosOcc; mvbits(113, LenIndex, w, PosIndex); continue; }
+        if (Id != 1 || !cubic_site(x, y, z, kind)) continue;
+        bool fill = true;
+        if (la) {                                             // solid everywhere but the liquid nucleus (:118-141)
+          if (H.Homogeneous == "T") fill = z <= LZ - (int)((H.LenVac + H.LenNuc) / H.sf);
+          else if (H.Homogeneous == "F") {
+            const int xc = LX / 2, yc = LY / 2, zc = LZ - (int)(H.LenVac / H.sf);
+            fill = (x - xc) * (x - xc) + (y - yc) * (y - yc) + (z - zc) * (z - zc) > (int)((H.LenNuc / H.sf) * (H.LenNuc / H.sf));
+          } else printf(" ERROR: Homogeneous needs to be either T or F\n");
+        }
+        if (!fill) continue;
+        w |= 1 << PosOcc;
+        // alloy species: the reference draws libgfortran's RAND() here (SetCAD.f:145,164,178), which is not part of the
+        // reference sources -- alloy initial configurations are statistically equivalent only
+        double rr = 1.0;
+        if (H.alloy > 0) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0); }
+        w |= 1 << (rr >= H.alloy ? PosSi : PosC);
+      }
+    }
+    printf(" Done reading input geometry file\n");
+    pass_coordination(H, 0, LZ - 1, 0, LY - 1, 0, LX - 1, true);
+  }
+  fclose(f);
+  pass_probability(H, 0, LZ - 1, 0, LY - 1, 0, LX - 1, true, true);
 }
 
 // ---- output (inpout/WriteMolMolSource.f, WriteMolMolXYZFile.f, GetOutputFileName.f) ---------------------------------
@@ -508,24 +666,31 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "FS") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false); }
   else if (H.InitSt == "C") set_nc(H, H.Len1, H.Len2, H.Len3, false);
   else if (H.InitSt == "S") set_nc(H, H.Len1, H.Len1, H.Len1, true);
-  else die(" mulskips.e (B200 host): InitSt %s is not built yet (built: F, FS, C, S; see DESIGN.md section 9)", H.InitSt.c_str());
-  R.NumAtoms = (int)H.bulk.size(); R.NumVoids = 0; R.NumAdAtom = (int)H.mc.size();
+  else if (H.InitSt == "I") set_invp_off(H, H.Len1, H.Len2);
+  else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
+  else if (H.InitSt == "IN") set_cad(H);
+  else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, C, S, I, FF, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
+  R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+  for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
   write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
   // ---- hand the state to the GPU (include/mskc.h) ----
   if (mskc_create(H.LX, H.LY, H.LZ, H.NCrystal, H.NCov, H.ListCrystal, H.ListCov, device, 0, &R.h) != 0) die(" %s", mskc_last_error(nullptr));
   MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
+  if (H.la()) MS(mskc_set_la(R.h, 1, H.Tm, H.P0, H.sigma, H.Tflex, H.t_lo, H.t_hi));
   {
-    std::vector<int32_t> mx(3 * H.mc.size() + 3), mn(12 * H.mc.size() + 12), me(H.mc.size() + 1), bx(3 * H.bulk.size() + 3), bn(12 * H.bulk.size() + 12), vx(3), vn(12);
+    std::vector<int32_t> mx(3 * H.mc.size() + 3), mn(12 * H.mc.size() + 12), me(H.mc.size() + 1), bx(3 * H.bulk.size() + 3), bn(12 * H.bulk.size() + 12), vx(3 * H.voids.size() + 3), vn(12 * H.voids.size() + 12);
+    for (size_t i = 0; i < H.voids.size(); i++) { memcpy(&vx[3 * i], H.voids[i].xyz, 12); memcpy(&vn[12 * i], H.voids[i].nn, 48); }
     std::vector<double> mr(H.mc.size() + 1);
     for (size_t i = 0; i < H.mc.size(); i++) { memcpy(&mx[3 * i], H.mc[i].xyz, 12); memcpy(&mn[12 * i], H.mc[i].nn, 48); me[i] = H.mc[i].ev; mr[i] = H.mc[i].p; }
     for (size_t i = 0; i < H.bulk.size(); i++) { memcpy(&bx[3 * i], H.bulk[i].xyz, 12); memcpy(&bn[12 * i], H.bulk[i].nn, 48); }
     int32_t st[58]; st[0] = H.r_iff; st[1] = H.r_inext; st[2] = H.r_inextp; for (int i = 1; i <= 55; i++) st[2 + i] = H.r_ma[i];
     MS(mskc_seed(R.h, H.Idum, H.RunType[0], 0, st));
-    MS(mskc_upload_state(R.h, H.L.data(), (int)H.mc.size(), mx.data(), mn.data(), me.data(), mr.data(), (int)H.bulk.size(), bx.data(), bn.data(), 0, vx.data(), vn.data()));
+    MS(mskc_upload_state(R.h, H.L.data(), (int)H.mc.size(), mx.data(), mn.data(), me.data(), mr.data(), (int)H.bulk.size(), bx.data(), bn.data(), (int)H.voids.size(), vx.data(), vn.data()));
     MS(mskc_set_clock(R.h, 1, 0.0, H.CountCrystal, H.CountCov));
   }
-  std::vector<Active>().swap(H.mc); std::vector<Site>().swap(H.bulk);
+  std::vector<Active>().swap(H.mc); std::vector<Site>().swap(H.bulk); std::vector<Site>().swap(H.voids);
   const bool by_time = H.ExitStrategy == "Time";
   float dev_ms = 0; long long events = 0;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device

@@ -1,3 +1,3 @@
 set -x
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:colour_step -s 120 -c 1 -o gpurun_out/prof_r01e python scripts/probe_bench.py --ept 4 --sweeps 32 --warm 16 > gpurun_out/ncu_r01e.log 2>&1
-tail -3 gpurun_out/ncu_r01e.log
+(time python -m pytest tests -x -q -m gpu 2>&1 | tail -5) 2>&1
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01d.json 2> gpurun_out/bench_r01d.err; tail -c 3000 gpurun_out/bench_r01d.json; tail -3 gpurun_out/bench_r01d.err

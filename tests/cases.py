@@ -86,3 +86,20 @@ def make_la_case(dirpath, box=(96, 96, 96), lennuc=12.0, maxiter=10**9):
     with open(dst, "w") as f:
         f.write("\n".join(lines))
     return dst
+
+
+def make_cad_case(dirpath, box=(96, 96, 120), maxiter=10**9):
+    """A small synthetic CVD-on-nanostructure case in the reference's file format (initial/SetCAD.f): a crystal ridge
+    (value 1) on a crystal substrate, a wall block (value 10) beside it, empty (0) above; one z plane per record.
+    start.dat = start-CAD.dat (Si + H coverage table) with the path and iteration limits replaced."""
+    import numpy as np
+    lx, ly, lz = box
+    geo = np.zeros((lz, ly, lx), np.int32)
+    geo[:36] = 1                                    # substrate
+    geo[36:60, :, 24:60] = 1                        # ridge along y
+    geo[30:72, :, 72:90] = 10                       # wall block (mask)
+    path = os.path.join(dirpath, "LattGeo.dat")
+    with open(path, "w") as f:
+        for z in range(lz):
+            f.write(" ".join(str(v) for v in geo[z].ravel()) + "\n")
+    return make_start("CAD", os.path.join(dirpath, "start.dat"), maxiter=maxiter, outmolmol=maxiter, paths=[path])

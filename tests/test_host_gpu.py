@@ -15,14 +15,14 @@ import subprocess
 
 import pytest
 
-from cases import GOLDEN, make_start, start_path
+from cases import GOLDEN, make_cad_case, make_la_case, make_start, start_path
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "mulskips_b200", "bin", "mulskips.e")
 ORACLE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
 MAN = json.load(open(os.path.join(GOLDEN, "manifest.json")))
-CASES = ["Si-SL", "surface", "cube", "cube-zigzag", "sphere", "CVD-Si-SiH2"]      # InitSt FS, F, C, C (PtransZig 0.8), S, FS + coverage
+CASES = ["Si-SL", "surface", "cube", "cube-zigzag", "sphere", "inverted-pyramid", "finfet", "CVD-Si-SiH2"]      # InitSt FS, F, C, C (PtransZig 0.8), S, I, FF, FS + coverage
 FULL = os.environ.get("MSKC_FULL_GOLDEN") == "1"
 NEV = 200000
 
@@ -76,3 +76,28 @@ def test_regression_case(built, tmp_path, case):
     for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "NumAtWrong:"):
         assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
     assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
+
+
+@pytest.mark.parametrize("kind", ["CAD", "LA"])
+def test_file_driven_case(built, tmp_path, kind):
+    """InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
+    temperature file, LA rate law, liquid nucleus) through the host program.  The regression inputs (LattGeo / TempStat
+    480x240x240, 100 MB each) live in the reference tree only, so the files here are synthetic ones in the same format at
+    a small box; the oracle's own builders are pinned on the real files by tests/test_oracle_golden.py."""
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    box = (96, 96, 120) if kind == "CAD" else (96, 96, 96)
+    start = make_cad_case(str(tmp_path), box, maxiter=60000) if kind == "CAD" else make_la_case(str(tmp_path), box, maxiter=3000)   # (the nucleus of this box regrows in ~4000 events)
+    for d in (g, o):
+        (d / "start.dat").write_text(open(start).read())
+    args = ["--box", *[str(v) for v in box]]
+    _run(ORACLE, o, args)
+    _run(EXE, g, args)
+    names = ["I00000000.xyz", "I00000001.xyz", "I00000000_d.xyz", "I00000001_d.xyz", "I00000000_v.xyz", "I00000001_v.xyz"]
+    for name in names:
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"{kind}: {name} differs from the oracle's"
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:"):
+        assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
+    assert len(open(g / "I00000000.xyz").readlines()) > 100
+    if kind == "LA":                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
+        assert (g / "LattStat.dat").read_bytes() == (o / "LattStat.dat").read_bytes()
