@@ -5,7 +5,7 @@
 // DefAtEnergy.dat and the optional checkpoint / Coor files in the cwd.  The reference is Fortran; no Fortran
 // compiler exists in this image, so the host side is C++ and keeps main.f's structure: parse start.dat
 // (main.f:83-212, mcevent/SetProbability.f), build the initial geometry with the reference's builders
-// (initial/SetSi.f, SetSiC3C.f, SetNC.f, SetNCSp.f, SetInvPOff.f, SetSiFINFET.f, SetCAD.f, SetT.f), hand LattCoo + the three particle lists to the GPU library,
+// (initial/SetSi.f, SetSiC3C.f, SetSiGex.f, SetNC.f, SetNCSp.f, SetInvPOff.f, SetSiFINFET.f, SetCAD.f, SetT.f), hand LattCoo + the three particle lists to the GPU library,
 // and drive the KMC loop (main.f:304-371) through mskc_run_parity -- which returns at every output frame so the
 // files are written at the reference's cadence -- or, with --parallel, through the sublattice sampler.
 // The loop body itself (everything under mcevent/ and lattice/) runs in CUDA; nothing here computes events.
@@ -294,17 +294,29 @@ void wall_planes(Host &H, int z0, int z1, int x0 = 0, int x1 = -1) {
   if (x1 < 0) x1 = H.LX - 1;
   for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = x0; x <= x1; x++) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << PosOcc; mvbits(113, LenIndex, w, PosIndex); }
 }
-// initial/SetSi.f:25-221 (walls, one species) and initial/SetSiC3C.f:25-199 (no walls, Si/C): flat (001) slab
-void set_flat(Host &H, int Len, bool walls, bool two_species) {
+// initial/SetSi.f:25-221 (walls, one species), initial/SetSiC3C.f:25-199 (no walls, Si/C) and initial/SetSiGex.f:25-256
+// (walls, random Si/Ge alloy, species counted at init): flat (001) slab
+void set_flat(Host &H, int Len, bool walls, bool two_species, bool alloy = false) {
   int32_t s[3], nn[4][3]; int kind;
+  if (alloy) printf(" Setting up SiGe alloy with fraction =  %.17g\n", H.alloy);
+  // SetSiGex.f:60-67 draws libgfortran's RAND() per site; that generator is not part of the reference sources, a
+  // documented LCG stands in (alloy initial configurations are statistically equivalent only)
+  unsigned long long lcg = 88172645463325252ull;
+  auto species = [&]() {
+    if (!alloy) return (kind && two_species) ? 2 : 1;
+    lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+    const int sp = (double)(lcg >> 11) * (1.0 / 9007199254740992.0) > H.alloy ? 1 : 2;
+    H.CountCrystal[sp - 1]++;
+    return sp;
+  };
   if (walls) wall_planes(H, 0, 5);
   auto scan = [&](int z0, int z1, auto &&fn) {
     for (int z = z0; z <= z1; z++) for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++)
-      if (cubic_site(x, y, z, kind)) { s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); fn(H.L[H.ci(x, y, z)], (kind && two_species) ? 2 : 1); }
+      if (cubic_site(x, y, z, kind)) { s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); fn(H.L[H.ci(x, y, z)]); }
   };
-  scan(walls ? 6 : 0, Len - 4, [&](int32_t &w, int sp) { w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(4, LenCoor, w, PosCoor); H.AddBulk(s, nn); });
-  scan(Len - 3, Len - 1, [&](int32_t &w, int sp) { w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(2, LenCoor, w, PosCoor); H.AddMC(s, nn, 4, H.PE[idxE(sp, 2, 0, 0, 0, 0, 0)]); });
-  scan(Len, Len, [&](int32_t &w, int) { mvbits(2, LenCoor, w, PosCoor); int ev; double p; H.draw_dep_abs(2, true, ev, p); H.AddMC(s, nn, ev, p); });   // Get_Prob(0,0,0,2,..)
+  scan(walls ? 6 : 0, Len - 4, [&](int32_t &w) { const int sp = species(); w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(4, LenCoor, w, PosCoor); H.AddBulk(s, nn); });
+  scan(Len - 3, Len - 1, [&](int32_t &w) { const int sp = species(); w |= 1 << (sp == 2 ? PosC : PosSi); w |= 1 << PosOcc; mvbits(2, LenCoor, w, PosCoor); H.AddMC(s, nn, 4, H.PE[idxE(sp, 2, 0, 0, 0, 0, 0)]); });
+  scan(Len, Len, [&](int32_t &w) { mvbits(2, LenCoor, w, PosCoor); int ev; double p; H.draw_dep_abs(2, true, ev, p); H.AddMC(s, nn, ev, p); });   // Get_Prob(0,0,0,2,..)
   if (walls) wall_planes(H, H.LZ - 6, H.LZ - 1);
 }
 // "Set the coordination" / "Set the probability" passes shared by the centre-of-box and file-driven builders:
@@ -664,13 +676,14 @@ int main(int argc, char **argv) {
   // main.f:225-295
   if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
   else if (H.InitSt == "FS") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false); }
+  else if (H.InitSt == "SG") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false, true); }
   else if (H.InitSt == "C") set_nc(H, H.Len1, H.Len2, H.Len3, false);
   else if (H.InitSt == "S") set_nc(H, H.Len1, H.Len1, H.Len1, true);
   else if (H.InitSt == "I") set_invp_off(H, H.Len1, H.Len2);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, C, S, I, FF, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, I, FF, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
   for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];

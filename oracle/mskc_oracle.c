@@ -1022,14 +1022,29 @@ static void set_wall_planes(Orc *o, int z0, int z1, int x0, int x1) {
   }
 }
 
-/* Flat (001) builders: src/initial/SetSi.f:25-221 (walls=1, one species) and SetSiC3C.f:25-199 (walls=0, Si/C) */
+/* species of one substrate site of the SiGe alloy builder (SetSiGex.f:60-67): Si if rr > alloyfraction, else the
+ * second species.  The reference draws libgfortran's RAND() here, which is not part of the reference sources: a
+ * documented 64-bit LCG stands in (alloy initial configurations: parity unpinned, SURVEY 8c trap 6). */
+static int alloy_species(Orc *o) {
+  static uint64_t lcg = 88172645463325252ull;
+  lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+  double rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
+  int sp = rr > o->alloyfraction ? 1 : 2;
+  o->CountCrystal[sp - 1]++;
+  return sp;
+}
+/* Flat (001) builders: src/initial/SetSi.f:25-221 (walls=1, one species), SetSiC3C.f:25-199 (walls=0, Si/C) and
+ * SetSiGex.f:25-256 (walls=1, two_species=2: random alloy, species counted at init) */
 static void set_flat(Orc *o, int Len, int walls, int two_species) {
   int32_t Site[3], NextN[4][3]; int kind, ev; double Prob;
+  const int alloy = two_species == 2;
+  if (alloy) { LOG(o, " Setting up SiGe alloy with fraction =  %.17g\n", o->alloyfraction); two_species = 0; }
   if (walls) set_wall_planes(o, 0, 5, 0, o->LenX - 1);
   for (int z = (walls ? 6 : 0); z <= Len - 4; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
     if (is_cubic_site(x, y, z, &kind)) {
       int32_t *w = &o->LattCoo[CI(o, x, y, z)];
-      *w |= 1 << ((kind && two_species) ? ORC_PosC : ORC_PosSi);
+      int sp0 = alloy ? alloy_species(o) : ((kind && two_species) ? 2 : 1);
+      *w |= 1 << (sp0 == 2 ? ORC_PosC : ORC_PosSi);
       *w |= 1 << ORC_PosOcc;
       MVBITS(4, ORC_LenCoor, w, ORC_PosCoor);
       Site[0] = x; Site[1] = y; Site[2] = z;
@@ -1039,7 +1054,7 @@ static void set_flat(Orc *o, int Len, int walls, int two_species) {
   for (int z = Len - 3; z <= Len - 1; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
     if (is_cubic_site(x, y, z, &kind)) {
       int32_t *w = &o->LattCoo[CI(o, x, y, z)];
-      int sp = (kind && two_species) ? 2 : 1;
+      int sp = alloy ? alloy_species(o) : ((kind && two_species) ? 2 : 1);
       *w |= 1 << (sp == 2 ? ORC_PosC : ORC_PosSi);
       *w |= 1 << ORC_PosOcc;
       MVBITS(2, ORC_LenCoor, w, ORC_PosCoor);
@@ -1307,6 +1322,7 @@ int orc_setup(Orc *o) {
   const char *s = o->InitSt;
   if (!strcmp(s, "F")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 0, 1); }
   else if (!strcmp(s, "FS")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 0); }
+  else if (!strcmp(s, "SG")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 2); }
   else if (!strcmp(s, "C")) set_nc(o, o->Len1, o->Len2, o->Len3, 0);
   else if (!strcmp(s, "S")) set_nc(o, o->Len1, o->Len1, o->Len1, 1);
   else if (!strcmp(s, "I")) set_invp_off(o, o->Len1, o->Len2);

@@ -1,3 +1,2 @@
 set -x
-(time python -m pytest tests -x -q -m gpu 2>&1 | tail -5) 2>&1
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r01d.json 2> gpurun_out/bench_r01d.err; tail -c 3000 gpurun_out/bench_r01d.json; tail -3 gpurun_out/bench_r01d.err
+for t in 4 3 2; do MSKC_TPW=$t python scripts/probe_bench.py --ept 4 --sweeps 32 --warm 16 2>&1 | tail -1; done

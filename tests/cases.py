@@ -103,3 +103,20 @@ def make_cad_case(dirpath, box=(96, 96, 120), maxiter=10**9):
         for z in range(lz):
             f.write(" ".join(str(v) for v in geo[z].ravel()) + "\n")
     return make_start("CAD", os.path.join(dirpath, "start.dat"), maxiter=maxiter, outmolmol=maxiter, paths=[path])
+
+
+def make_sige_case(dirpath, len1=48, fraction=0.3, maxiter=10**9):
+    """Si(1-x)Ge(x) (001) slab, InitSt SG (initial/SetSiGex.f): the two-species PVD table of start-surface.dat read as
+    (Si, Ge), walls, random alloy substrate; the Ge-fraction line follows the Len line (main.f:142-149)."""
+    lines = open(start_path("surface")).read().split("\n")
+    lines[1] = "14 32 ! list of elements of the crystal"
+    lines[2] = "SG ! Initstat"
+    lines[3] = f"{len1} 0 0 ! Len1 Len2 Len3"
+    lines.insert(4, f"{fraction} ! Ge fraction in the substrate")
+    i = next(k for k, l in enumerate(lines) if l.split() and l.split()[0] == "Iter")
+    lines[i + 1] = f"{maxiter} ! IterMax"
+    lines[i + 2] = f"{maxiter} ! OutMolMol"
+    dst = os.path.join(dirpath, "start.dat")
+    with open(dst, "w") as f:
+        f.write("\n".join(lines))
+    return dst

@@ -15,7 +15,7 @@ import subprocess
 
 import pytest
 
-from cases import GOLDEN, make_cad_case, make_la_case, make_start, start_path
+from cases import GOLDEN, make_cad_case, make_la_case, make_sige_case, make_start, start_path
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -78,16 +78,19 @@ def test_regression_case(built, tmp_path, case):
     assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
 
 
-@pytest.mark.parametrize("kind", ["CAD", "LA"])
+@pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe"])
 def test_file_driven_case(built, tmp_path, kind):
-    """InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
+    """InitSt SG (SetSiGex.f), InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
     temperature file, LA rate law, liquid nucleus) through the host program.  The regression inputs (LattGeo / TempStat
     480x240x240, 100 MB each) live in the reference tree only, so the files here are synthetic ones in the same format at
     a small box; the oracle's own builders are pinned on the real files by tests/test_oracle_golden.py."""
     g, o = tmp_path / "gpu", tmp_path / "oracle"
     g.mkdir(); o.mkdir()
     box = (96, 96, 120) if kind == "CAD" else (96, 96, 96)
-    start = make_cad_case(str(tmp_path), box, maxiter=60000) if kind == "CAD" else make_la_case(str(tmp_path), box, maxiter=3000)   # (the nucleus of this box regrows in ~4000 events)
+    if kind == "SiGe":                               # InitSt SG (SetSiGex.f): random-alloy substrate, the C5 slab's second material
+        start = make_sige_case(str(tmp_path), 48, 0.3, maxiter=60000)
+    else:
+        start = make_cad_case(str(tmp_path), box, maxiter=60000) if kind == "CAD" else make_la_case(str(tmp_path), box, maxiter=3000)   # (the nucleus of this box regrows in ~4000 events)
     for d in (g, o):
         (d / "start.dat").write_text(open(start).read())
     args = ["--box", *[str(v) for v in box]]
@@ -101,3 +104,38 @@ def test_file_driven_case(built, tmp_path, kind):
     assert len(open(g / "I00000000.xyz").readlines()) > 100
     if kind == "LA":                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
         assert (g / "LattStat.dat").read_bytes() == (o / "LattStat.dat").read_bytes()
+
+
+def test_checkpoint_restart(built, tmp_path):
+    """SaveFinalState 'T' writes the lattice words (main.f:385-403); RunType 'C' reads them back through the checkpoint
+    branch of SetCAD.f:54-79, rebuilds the lists with ideal diamond bonds (the reference's restart is lossy in exactly
+    this way: with adsorbed coverage or hexagonal bonds its own Get_Prob_Ini census stops the run, so the case here is
+    the laser-annealing one, pure cubic Si) and continues with ran3.  Both legs on the host program, checked against the
+    oracle's."""
+    box = (96, 96, 96)
+    args = ["--box", *[str(v) for v in box]]
+    start = make_la_case(str(tmp_path), box, maxiter=1500)
+    lines = open(start).read().split("\n")
+    i = next(k for k, l in enumerate(lines) if "Save final state" in l)
+    lines[i] = "T ! Save final state"
+    lines.insert(i + 1, "LattChk.dat")
+    first = "\n".join(lines)
+    j = next(k for k, l in enumerate(lines) if "RunType" in l)
+    lines[j] = "C ! RunType: continuation"
+    lines[3] = "LattChk.dat"                       # the geometry path line now names the checkpoint
+    second = "\n".join(lines)
+    out = {}
+    for tag, exe in (("gpu", EXE), ("oracle", ORACLE)):
+        a, b = tmp_path / f"{tag}1", tmp_path / f"{tag}2"
+        a.mkdir(); b.mkdir()
+        (a / "start.dat").write_text(first)
+        _run(exe, a, args)
+        (b / "start.dat").write_text(second)
+        (b / "LattChk.dat").write_bytes((a / "LattChk.dat").read_bytes())
+        _run(exe, b, args)
+        out[tag] = (a, b)
+    assert (out["gpu"][0] / "LattChk.dat").read_bytes() == (out["oracle"][0] / "LattChk.dat").read_bytes()
+    for name in ("I00000000.xyz", "I00000001.xyz", "I00000001_v.xyz", "LattChk.dat", "LattStat.dat"):
+        assert (out["gpu"][1] / name).read_bytes() == (out["oracle"][1] / name).read_bytes(), name
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:"):
+        assert _tokens(out["gpu"][1] / "log.txt", key) == _tokens(out["oracle"][1] / "log.txt", key), key
