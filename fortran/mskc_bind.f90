@@ -89,6 +89,16 @@ module mskc_bind
       integer(c_int), value :: enable, tmin, tmax
       real(c_double), value :: Tm, P0, sigma, Tflex
     end function
+    ! InitSt 'ST' (main.f:215-216): after SetProbabilityFromField, instead of mskc_set_rates.  The ref* module arrays have
+    ! the temperature index FIRST (defsystem.f:77-81); the C side wants one contiguous block per temperature, so pass
+    ! reshape(refPtransE(1:ntemp,:,:,:,:,:,:,:), order=...) copies or fill a (12288,ntemp) buffer block by block.
+    integer(c_int) function mskc_set_rate_field(h, ntemp, reftemp, refPE, refPD, refPAbs, refPDes, PtransZig, tmin, tmax, &
+                                                fixed_temperature) bind(C, name="mskc_set_rate_field")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: h, reftemp, refPE, refPD, refPAbs, refPDes
+      integer(c_int), value :: ntemp, tmin, tmax, fixed_temperature
+      real(c_double), value :: PtransZig
+    end function
     ! after the Set* builder (main.f:225-295): LattCoo and the three lists flattened to int32 arrays
     integer(c_int) function mskc_upload_state(h, LattCoo, n_mc, mc_xyz, mc_nn, mc_event, mc_rate, n_bulk, bulk_xyz, bulk_nn, &
                                               n_void, void_xyz, void_nn) bind(C, name="mskc_upload_state")

@@ -59,6 +59,17 @@ int mskc_set_rates(mskc_ctx *h, const double *PtransE, const double *PtransD,
  * in [tmin,tmax].  enable=0 switches back to plain tables. */
 int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double sigma, double Tflex, int tmin, int tmax);
 
+/* Replaces: the 'ST' tabulated-temperature mode -- mcevent/SetProbabilityFromField.f:21-171 (ntemp blocks of the four
+ * tables at the temperatures reftemp[], Fortran flattening per block as in mskc_set_rates: refPE [ntemp][12288],
+ * refPD [ntemp][9], refPAbs / refPDes [ntemp][12], NULL = zeros) and mcevent/InterpProbFromField.f:22-57 (linear
+ * interpolation with INTEGER distance weights at the site's temperature, Get_Prob.f:76-91).  The interpolated tables
+ * are built on the host for every integer kelvin in [tmin,tmax] (must lie inside reftemp[0]..reftemp[ntemp-1], where
+ * the reference would index out of bounds otherwise), so device rates are the reference's bit for bit.
+ * fixed_temperature > 0 is the Ttop == Tbottom case (initial/SetTrenchSi.f:65-67): interpolate once at that
+ * temperature and use plain tables.  Either way a cleared cell keeps its temperature bits (Evaporation.f:70-74). */
+int mskc_set_rate_field(mskc_ctx *h, int ntemp, const int32_t *reftemp, const double *refPE, const double *refPD,
+                        const double *refPAbs, const double *refPDes, double PtransZig, int tmin, int tmax, int fixed_temperature);
+
 /* Replaces: what the Set* builders leave in module globals (LattCoo + the three particle lists, in
  * REFERENCE LIST ORDER, built through mcevent/Add.f).  Coordinates are absolute, neighbours are
  * [n][4][3] with (0,0,0) = "not fixed" (defdertype.f:32-37).  LattCoo is [(lenz+1)][leny][lenx]. */

@@ -62,7 +62,7 @@ STOP_BUDGET, STOP_MAXITER, STOP_MAXTIME, STOP_FRAME, STOP_FEWMC, STOP_ERROR = 0,
 _LIB = None
 
 # every symbol include/mskc.h declares
-SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_upload_state",
+SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_set_rate_field", "mskc_upload_state",
            "mskc_init_flat", "mskc_seed", "mskc_get_rng", "mskc_set_clock", "mskc_run_parity", "mskc_run_parallel",
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
@@ -87,6 +87,7 @@ def load_library():
     lib.mskc_last_error.restype = C.c_char_p
     lib.mskc_set_rates.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double]
     lib.mskc_set_la.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.mskc_set_rate_field.argtypes = [vp, C.c_int, i32p, f64p, f64p, f64p, f64p, C.c_double, C.c_int, C.c_int, C.c_int]
     lib.mskc_upload_state.argtypes = [vp, i32p, C.c_int, i32p, i32p, i32p, f64p, C.c_int, i32p, i32p, C.c_int, i32p, i32p]
     lib.mskc_init_flat.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.mskc_seed.argtypes = [vp, C.c_int, C.c_int, C.c_int64, i32p]
@@ -188,6 +189,18 @@ class Mskc:
 
     def set_la(self, Tm, P0, sigma, Tflex, tmin, tmax, enable=True):
         self._ck(self.lib.mskc_set_la(self.h, int(enable), Tm, P0, sigma, Tflex, int(tmin), int(tmax)))
+
+    def set_rate_field(self, reftemp, refPE, refPD, refPAbs=None, refPDes=None, PtransZig=1.0, tmin=0, tmax=0, fixed_temperature=0):
+        """'ST' mode (SetProbabilityFromField.f / InterpProbFromField.f): ntemp tabulated blocks of the four tables."""
+        rt = _i32(reftemp).reshape(-1)
+        n = rt.size
+        pe, pd = _f64(refPE).reshape(-1), _f64(refPD).reshape(-1)
+        assert pe.size == n * 12288 and pd.size == n * 9
+        pa = _f64(np.zeros(12 * n) if refPAbs is None else refPAbs).reshape(-1)
+        ps = _f64(np.zeros(12 * n) if refPDes is None else refPDes).reshape(-1)
+        assert pa.size == n * 12 and ps.size == n * 12
+        self._ck(self.lib.mskc_set_rate_field(self.h, n, _p(rt, C.c_int32), _p(pe, C.c_double), _p(pd, C.c_double), _p(pa, C.c_double),
+                                              _p(ps, C.c_double), float(PtransZig), int(tmin), int(tmax), int(fixed_temperature)))
 
     # -- state -------------------------------------------------------------------------------------
     def upload_state(self, LattCoo, mc_xyz, mc_nn, mc_event, mc_rate, bulk_xyz, bulk_nn, void_xyz=None, void_nn=None):

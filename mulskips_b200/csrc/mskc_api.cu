@@ -26,7 +26,7 @@ struct mskc_ctx {
   // tables
   double *d_PE = nullptr, *d_PD = nullptr, *d_PAbs = nullptr, *d_PDes = nullptr;
   std::vector<double> h_PE, h_PD, h_PAbs, h_PDes;
-  short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr;
+  short *d_la_slot = nullptr; double *d_la_E = nullptr, *d_la_D = nullptr, *d_la_A = nullptr, *d_la_S = nullptr;
   int *d_err = nullptr;
   int32_t *d_stage = nullptr;
   uint32_t *d_frame_cell = nullptr, *d_frame_word = nullptr; unsigned long long *d_frame_n = nullptr; int64_t frame_cap = 0;
@@ -211,7 +211,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
   cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
-  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_err);
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }
   parallel_free(h->PC);
@@ -269,6 +269,7 @@ extern "C" int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double
     }
   }
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D);
+  h->d_la_slot = nullptr; h->d_la_E = h->d_la_D = nullptr;
   CK(cudaMalloc(&h->d_la_slot, 12288 * sizeof(short)));
   CK(cudaMalloc(&h->d_la_E, E.size() * sizeof(double)));
   CK(cudaMalloc(&h->d_la_D, Dt.size() * sizeof(double)));
@@ -277,6 +278,84 @@ extern "C" int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double
   CK(cudaMemcpy(h->d_la_D, Dt.data(), Dt.size() * sizeof(double), cudaMemcpyHostToDevice));
   D.la = 1; D.keepT = 1; D.la_tmin = tmin; D.la_tmax = tmax; D.la_nnz = nnz;
   D.la_slot = h->d_la_slot; D.la_E = h->d_la_E; D.la_D = h->d_la_D;
+  return 0;
+}
+
+// mcevent/InterpProbFromField.f:22-57 for one table entry: the two tabulated blocks that bracket `temperature`,
+// mixed with INTEGER distance weights.  Returns false where the reference would index its arrays out of bounds
+// (temperature outside the tabulated range).
+static bool st_bracket(int ntemp, const int32_t *reftemp, int temperature, int *ilower, int *iupper, int *wlower, int *wupper) {
+  for (int i = 0; i < ntemp; i++) if (reftemp[i] - temperature == 0) { *ilower = *iupper = i; *wlower = 1; *wupper = 0; return true; }   // FINDLOC(diff, 0)
+  int up = -1, best = 0;
+  for (int i = 0; i < ntemp; i++) { int d = reftemp[i] - temperature; if (d > 0 && (up < 0 || d < best)) { up = i; best = d; } }   // MINLOC(diff, MASK=diff>0)
+  if (up <= 0) return false;
+  *iupper = up; *ilower = up - 1;
+  *wlower = abs(reftemp[up] - temperature); *wupper = abs(reftemp[up - 1] - temperature);
+  return true;
+}
+static inline double st_mix(int il, int iu, int wl, int wu, double lo, double up) {
+  if (il == iu) return lo;                                                 // exact hit: the block is copied
+  return ((double)wl * lo + (double)wu * up) / (double)(wl + wu);
+}
+
+extern "C" int mskc_set_rate_field(mskc_ctx *h, int ntemp, const int32_t *reftemp, const double *refPE, const double *refPD,
+                                   const double *refPAbs, const double *refPDes, double PtransZig, int tmin, int tmax, int fixed_temperature) {
+  if (!h || !reftemp || !refPE || !refPD) return set_err(h, "mskc_set_rate_field: NULL argument");
+  if (ntemp < 1 || ntemp > 300) return set_err(h, "mskc_set_rate_field: ntemp must be 1..300 (ntempMax, defsystem.f:72)");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  std::vector<double> zero12((size_t)ntemp * 12, 0.0);
+  if (!refPAbs) refPAbs = zero12.data();
+  if (!refPDes) refPDes = zero12.data();
+  int il, iu, wl, wu;
+  if (fixed_temperature > 0) {
+    // SetTrenchSi.f:65-67: Ttop == Tbottom -> interpolate once, plain tables from then on; Evaporation.f:70 still
+    // keeps the temperature bits of a cell it clears
+    if (!st_bracket(ntemp, reftemp, fixed_temperature, &il, &iu, &wl, &wu))
+      return set_err(h, "mskc_set_rate_field: temperature %d K outside the tabulated range %d..%d K", fixed_temperature, reftemp[0], reftemp[ntemp - 1]);
+    std::vector<double> PE(12288), PD(9), PA(12), PS(12);
+    for (int i = 0; i < 12288; i++) PE[i] = st_mix(il, iu, wl, wu, refPE[(size_t)il * 12288 + i], refPE[(size_t)iu * 12288 + i]);
+    for (int i = 0; i < 9; i++) PD[i] = st_mix(il, iu, wl, wu, refPD[(size_t)il * 9 + i], refPD[(size_t)iu * 9 + i]);
+    for (int i = 0; i < 12; i++) PA[i] = st_mix(il, iu, wl, wu, refPAbs[(size_t)il * 12 + i], refPAbs[(size_t)iu * 12 + i]);
+    for (int i = 0; i < 12; i++) PS[i] = st_mix(il, iu, wl, wu, refPDes[(size_t)il * 12 + i], refPDes[(size_t)iu * 12 + i]);
+    int rc = mskc_set_rates(h, PE.data(), PD.data(), PA.data(), PS.data(), PtransZig);
+    if (rc) return rc;
+    D.la = 0; D.keepT = 1;
+    return 0;
+  }
+  if (tmin < 1 || tmax > 8191 || tmax < tmin) return set_err(h, "mskc_set_rate_field: temperature range must lie in 1..8191 K (13-bit field)");
+  if (!st_bracket(ntemp, reftemp, tmin, &il, &iu, &wl, &wu) || !st_bracket(ntemp, reftemp, tmax, &il, &iu, &wl, &wu))
+    return set_err(h, "mskc_set_rate_field: temperature range %d..%d K outside the tabulated range %d..%d K", tmin, tmax, reftemp[0], reftemp[ntemp - 1]);
+  // the plain tables stay defined (block 1) so that mskc_set_la / diagnostics have something to read; the kernels use the per-kelvin ones
+  { int rc = mskc_set_rates(h, refPE, refPD, refPAbs, refPDes, PtransZig); if (rc) return rc; }
+  std::vector<short> slot(12288, -1);
+  int nnz = 0;
+  for (int i = 0; i < 12288; i++) for (int t = 0; t < ntemp; t++) if (refPE[(size_t)t * 12288 + i] != 0.0) { slot[i] = (short)nnz++; break; }
+  if (nnz == 0) nnz = 1;
+  const int nt = tmax - tmin + 1;
+  std::vector<double> E((size_t)nt * nnz, 0.0), Dt((size_t)nt * 9, 0.0), A((size_t)nt * 12, 0.0), S((size_t)nt * 12, 0.0);
+  for (int t = tmin; t <= tmax; t++) {
+    if (!st_bracket(ntemp, reftemp, t, &il, &iu, &wl, &wu)) return set_err(h, "mskc_set_rate_field: reftemp must increase monotonically");
+    const size_t r = (size_t)(t - tmin);
+    for (int i = 0; i < 12288; i++) if (slot[i] >= 0) E[r * nnz + slot[i]] = st_mix(il, iu, wl, wu, refPE[(size_t)il * 12288 + i], refPE[(size_t)iu * 12288 + i]);
+    for (int i = 0; i < 9; i++) Dt[r * 9 + i] = st_mix(il, iu, wl, wu, refPD[(size_t)il * 9 + i], refPD[(size_t)iu * 9 + i]);
+    for (int i = 0; i < 12; i++) A[r * 12 + i] = st_mix(il, iu, wl, wu, refPAbs[(size_t)il * 12 + i], refPAbs[(size_t)iu * 12 + i]);
+    for (int i = 0; i < 12; i++) S[r * 12 + i] = st_mix(il, iu, wl, wu, refPDes[(size_t)il * 12 + i], refPDes[(size_t)iu * 12 + i]);
+  }
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S);
+  h->d_la_slot = nullptr; h->d_la_E = h->d_la_D = h->d_la_A = h->d_la_S = nullptr;
+  CK(cudaMalloc(&h->d_la_slot, 12288 * sizeof(short)));
+  CK(cudaMalloc(&h->d_la_E, E.size() * sizeof(double)));
+  CK(cudaMalloc(&h->d_la_D, Dt.size() * sizeof(double)));
+  CK(cudaMalloc(&h->d_la_A, A.size() * sizeof(double)));
+  CK(cudaMalloc(&h->d_la_S, S.size() * sizeof(double)));
+  CK(cudaMemcpy(h->d_la_slot, slot.data(), 12288 * sizeof(short), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_E, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_D, Dt.data(), Dt.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_A, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_S, S.data(), S.size() * sizeof(double), cudaMemcpyHostToDevice));
+  D.la = 2; D.keepT = 1; D.la_tmin = tmin; D.la_tmax = tmax; D.la_nnz = nnz;
+  D.la_slot = h->d_la_slot; D.la_E = h->d_la_E; D.la_D = h->d_la_D; D.la_A = h->d_la_A; D.la_S = h->d_la_S;
   return 0;
 }
 

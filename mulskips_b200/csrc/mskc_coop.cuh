@@ -60,22 +60,22 @@ __device__ __forceinline__ int cov_index(int cov) {      // position of a covera
 // Occ/NSiC/Cov/Coor are what the caller holds (not re-read), rb the four bonds to rate with (they can
 // differ from the stored ones, Evaporation.f:123).  Deposition/adsorption sites get EV_DRAW: the species
 // is drawn when the event fires (Get_Prob.f:160-179 draws it here; same distribution).
-// FEAT: bit 0 = coverage species exist (NCov > 0), bit 1 = LA rate law; compiled out otherwise (hot-loop code size)
+// FEAT: bit 0 = coverage species exist (NCov > 0), bit 1 = per-kelvin rate tables (LA rate law or 'ST' field); compiled out otherwise (hot-loop code size)
 enum { F_COV = 1, F_LA = 2 };
 template <int FEAT>
 __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, P3 Q, uint32_t cQ, unsigned long long rb, double root, int &ev, double &p) {
   ev = 0; p = 0.0;
+  int T = 0;
+  if ((FEAT & F_LA) && D.la) T = site_T(D.state[cQ], Q);                   // :76-91 ('ST') / :127-141 ('LA')
   if ((FEAT & F_COV) && Cov > 0 && Cov < 113) {                            // desorption, :93-123
     if (Occ != 0) { fail_cell(E_COVOCC, cQ); return; }
     if (Coor <= 3) {
       const int iCov = cov_index(Cov);
       if (iCov == 0 || iCov > D.NCov) { fail_cell(E_COVLIST, cQ); return; }
-      ev = 5; p = __ldg(&D.PDes[(iCov - 1) + 3 * Coor]);
+      ev = 5; p = (FEAT & F_LA) ? rate_Des(iCov, Coor, T) : __ldg(&D.PDes[(iCov - 1) + 3 * Coor]);
     }
     return;
   }
-  int T = 0;
-  if ((FEAT & F_LA) && D.la) T = site_T(D.state[cQ], Q);
   if (Occ == 0) {
     if (Coor >= 1 && Coor <= 3) {
       ev = EV_DRAW;

@@ -43,11 +43,14 @@ struct DevCtx {
   double PZig;
   double PDepAbs[4];                // [coor]: sum of the deposition + adsorption rates of an empty site (Get_Prob.f:160-163), plain tables
   int NCrystal, NCov, ListCov[3], ListCrystal[3];
-  // LA rate law: host-built tables per integer kelvin (Get_Prob.f:143-148)
+  // temperature-dependent rates: host-built tables per integer kelvin.  la = 1: the LA rate law (Get_Prob.f:143-148,
+  // evaporation + deposition); la = 2: the 'ST' tabulated field (InterpProbFromField.f: all four tables, and the
+  // site temperature is consulted for coverage sites too, Get_Prob.f:76-91)
   int la, keepT, la_tmin, la_tmax, la_nnz;
   const short *la_slot;             // [12288] -> column in la_E, -1 where PtransE==0
   const double *la_E;               // [(tmax-tmin+1)][la_nnz]
   const double *la_D;               // [(tmax-tmin+1)][9]
+  const double *la_A, *la_S;        // la = 2 only: [(tmax-tmin+1)][12] absorption / desorption
   double rot_c[2], rot_s[2];        // cos/sin(2*irot*Pi_f/3), host libm (FIND_NN.f:51-52)
   int nn_exact;                     // 1: the integer form of FIND_NN.f on the ideal bond shell was verified against the double routine
   const unsigned short *arm_tab;    // [32768] arm-chair offset code per bond code (mskc_coop.cuh), 0 = use find_sn()
@@ -221,18 +224,25 @@ __device__ __forceinline__ double rate_D(int sp, int coor, int T) {
   int i = (sp - 1) + 3 * (coor - 1);
   return D.la ? __ldg(&D.la_D[(long long)(T - D.la_tmin) * 9 + i]) : __ldg(&D.PD[i]);
 }
-__device__ __forceinline__ double rate_Abs(int k, int coor) { return __ldg(&D.PAbs[(k - 1) + 3 * coor]); }
+__device__ __forceinline__ double rate_Abs(int k, int coor, int T) {
+  int i = (k - 1) + 3 * coor;
+  return D.la == 2 ? __ldg(&D.la_A[(long long)(T - D.la_tmin) * 12 + i]) : __ldg(&D.PAbs[i]);
+}
+__device__ __forceinline__ double rate_Des(int k, int coor, int T) {
+  int i = (k - 1) + 3 * coor;
+  return D.la == 2 ? __ldg(&D.la_S[(long long)(T - D.la_tmin) * 12 + i]) : __ldg(&D.PDes[i]);
+}
 
 // Get_Prob.f:22-52
-__device__ __noinline__ int index_event_abs(int Coor, double Ptmp, double PDepo) {
+__device__ __noinline__ int index_event_abs(int Coor, double Ptmp, double PDepo, int T) {
   if (D.NCov == 1) return 6;
   int res = 0;
   for (int i = 1; i <= D.NCov; i++) {
     double pmin, pmax, s;
-    if (i == 1) { pmin = PDepo; pmax = PDepo + rate_Abs(1, Coor); }
+    if (i == 1) { pmin = PDepo; pmax = PDepo + rate_Abs(1, Coor, T); }
     else {
-      s = 0; for (int k = 1; k <= i - 1; k++) s += rate_Abs(k, Coor); pmin = PDepo + s;
-      s = 0; for (int k = 1; k <= i; k++) s += rate_Abs(k, Coor); pmax = PDepo + s;
+      s = 0; for (int k = 1; k <= i - 1; k++) s += rate_Abs(k, Coor, T); pmin = PDepo + s;
+      s = 0; for (int k = 1; k <= i; k++) s += rate_Abs(k, Coor, T); pmax = PDepo + s;
     }
     if (Ptmp > pmin && Ptmp <= pmax) res = 5 + i;
   }
@@ -242,7 +252,7 @@ __device__ __noinline__ int index_event_abs(int Coor, double Ptmp, double PDepo)
 __device__ __noinline__ int choose_dep_abs(int Coor, int T, double u, double *ptot) {
   double PD1 = rate_D(1, Coor, T), PD2 = rate_D(2, Coor, T), PD3 = rate_D(3, Coor, T);
   double PDep = PD1 + PD2 + PD3;
-  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor);
+  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor, T);
   double Ptot = PDep + PAbs;
   if (ptot) *ptot = Ptot;
   double Pcurr = u * Ptot;
@@ -251,11 +261,11 @@ __device__ __noinline__ int choose_dep_abs(int Coor, int T, double u, double *pt
     if (Pcurr > (PD1 + PD2)) return 3;
     return 2;
   }
-  return index_event_abs(Coor, Pcurr, PDep);
+  return index_event_abs(Coor, Pcurr, PDep, T);
 }
 __device__ __noinline__ double total_dep_abs(int Coor, int T) {
   double PDep = rate_D(1, Coor, T) + rate_D(2, Coor, T) + rate_D(3, Coor, T);
-  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor);
+  double PAbs = 0; for (int k = 1; k <= 3; k++) PAbs += rate_Abs(k, Coor, T);
   return PDep + PAbs;
 }
 
@@ -264,18 +274,18 @@ __device__ __noinline__ double total_dep_abs(int Coor, int T) {
 template <class Pol>
 __device__ __noinline__ void get_prob(Pol &pol, int Occ, int NSiC, int CovInd, int Coor, P3 Site, const P3 NextN[4], int &ev, double &prob) {
   pol.n_getprob++;
+  int T = 0;
+  if (D.la) T = site_T(D.state[cidx(Site)], Site);      // :76-91 ('ST': before the coverage branch) / :127-141 ('LA': NCov = 0)
   if (CovInd > 0 && CovInd < 113) {                     // desorption, :93-123
     if (Occ != 0) { fail(E_COVOCC, Site.x, Site.y, Site.z); return; }
     if (Coor <= 3) {
       int iCov = 0;
       for (int j = 1; j <= D.NCov; j++) if (D.ListCov[j - 1] == CovInd) { iCov = j; break; }
       if (iCov == 0) { fail(E_COVLIST, Site.x, Site.y, Site.z, CovInd); return; }
-      ev = 5; prob = __ldg(&D.PDes[(iCov - 1) + 3 * Coor]);
+      ev = 5; prob = rate_Des(iCov, Coor, T);
     } else { ev = 0; prob = 0.0; }
     return;
   }
-  int T = 0;
-  if (D.la) T = site_T(D.state[cidx(Site)], Site);
   if (Occ == 0) {
     if (Coor == 1) {
       int CoorNN = w_coor(D.state[cidx(NextN[0])]);

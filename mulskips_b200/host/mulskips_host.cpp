@@ -53,6 +53,15 @@ struct Host {
   int tmax = 0;                   // main.f:288-291: only the checkpoint branch of SetCAD.f updates it (the regression log prints 0)
   int t_lo = 0, t_hi = 0;         // range of the temperature field, for the device's per-kelvin rate tables
   bool la() const { return InitSt == "LA"; }
+  // InitSt ST (main.f:109-115, defsystem.f:71-81): trench geometry, temperature ramp, tabulated rate blocks
+  double angle = 0, Ttop = 0, Tbottom = 0;
+  bool fixedT = false;
+  std::string tablefile;
+  int ntemp = 0;
+  std::vector<int32_t> reftemp;
+  std::vector<double> refPE, refPD, refPA, refPS;         // [ntemp][12288], [ntemp][9], [ntemp][12], [ntemp][12]
+  std::vector<int> st_idx;                                // PtransE entries that are non-zero in some block
+  bool st() const { return InitSt == "ST"; }
   long long MaxIter = 0, OutMolMol = 0;
   std::vector<double> PE = std::vector<double>(12288, 0.0), PD = std::vector<double>(9, 0.0), PA = std::vector<double>(12, 0.0), PS = std::vector<double>(12, 0.0);
   // state built by the initialiser (module globals of defsystem.f)
@@ -126,9 +135,30 @@ struct Host {
     }
     prob = Ptot;
   }
+  // mcevent/InterpProbFromField.f:22-57: the working tables := the tabulated blocks mixed at an integer temperature
+  // with INTEGER distance weights (the device library builds its per-kelvin tables with the same expression)
+  void interp_field(int T) {
+    int iu = -1, il, best = 0;
+    for (int i = 0; i < ntemp; i++) if (reftemp[i] == T) { iu = i; break; }
+    if (iu >= 0) {
+      for (int k : st_idx) PE[k] = refPE[(size_t)iu * 12288 + k];
+      for (int i = 0; i < 9; i++) PD[i] = refPD[(size_t)iu * 9 + i];
+      for (int i = 0; i < 12; i++) { PA[i] = refPA[(size_t)iu * 12 + i]; PS[i] = refPS[(size_t)iu * 12 + i]; }
+      return;
+    }
+    for (int i = 0; i < ntemp; i++) { int d = reftemp[i] - T; if (d > 0 && (iu < 0 || d < best)) { iu = i; best = d; } }
+    if (iu <= 0) die(" InterpProbFromField: temperature %d K outside the tabulated range %d..%d K", T, reftemp[0], reftemp[ntemp - 1]);
+    il = iu - 1;
+    const int wl = std::abs(reftemp[iu] - T), wu = std::abs(reftemp[il] - T);
+    auto mix = [&](double lo, double up) { return ((double)wl * lo + (double)wu * up) / (double)(wl + wu); };
+    for (int k : st_idx) PE[k] = mix(refPE[(size_t)il * 12288 + k], refPE[(size_t)iu * 12288 + k]);
+    for (int i = 0; i < 9; i++) PD[i] = mix(refPD[(size_t)il * 9 + i], refPD[(size_t)iu * 9 + i]);
+    for (int i = 0; i < 12; i++) { PA[i] = mix(refPA[(size_t)il * 12 + i], refPA[(size_t)iu * 12 + i]); PS[i] = mix(refPS[(size_t)il * 12 + i], refPS[(size_t)iu * 12 + i]); }
+  }
   // mcevent/Get_Prob_Ini.f:23-161 (init-time rating: no reciprocity test, walls / coverage count as N_cov)
   void get_prob_ini(int Occ, int NSiC, int Coor, const int32_t s[3], const int32_t nn[4][3], int &ev, double &prob) {
     ev = 0; prob = 0.0;
+    if (st() && !fixedT) interp_field(site_T(s));           // Get_Prob_Ini.f:41-56
     const int T = la() ? site_T(s) : 0;
     if (Occ == 0) {
       bool draw = false;
@@ -213,6 +243,54 @@ void set_probability(Host &H, Lines &in) {                   // mcevent/SetProba
     }
 }
 
+void set_probability_from_field(Host &H, Lines &in) {        // mcevent/SetProbabilityFromField.f:21-171
+  static const int tab[3][4] = {{3, 9, 19, 34}, {18, 50, 100, 172}, {57, 150, 288, 480}};
+  H.tablefile = whole_line(in.next());
+  printf(" Reading input probability table: %s\n", H.tablefile.c_str());
+  Lines t; t.f = fopen(H.tablefile.c_str(), "r");
+  if (!t.f) die(" cannot open %s", H.tablefile.c_str());
+  H.ntemp = (int)strtol(t.next(), nullptr, 10);
+  (void)strtol(t.next(), nullptr, 10);                       // nprob: read and never used by the reference
+  if (H.ntemp < 1 || H.ntemp > 300) die(" probability table: ntemp must be 1..300 (ntempMax, defsystem.f:72)");
+  const int nE = tab[H.NCrystal - 1][H.NCov], nd = H.NCrystal + H.NCov;
+  H.reftemp.assign(H.ntemp, 0);
+  H.refPE.assign((size_t)H.ntemp * 12288, 0.0); H.refPD.assign((size_t)H.ntemp * 9, 0.0);
+  H.refPA.assign((size_t)H.ntemp * 12, 0.0); H.refPS.assign((size_t)H.ntemp * 12, 0.0);
+  for (int tb = 0; tb < H.ntemp; tb++) {
+    H.reftemp[tb] = (int)strtol(t.next(), nullptr, 10);
+    if (tb == 0) printf(" maxElines %d\n", nE);
+    for (int i = 0; i < nE; i++) {
+      char *p = const_cast<char *>(t.next());
+      int sp = (int)strtol(p, &p, 10); long el = strtol(p, &p, 10); double v = fnum(p);
+      if (sp > H.NCrystal) die(" ERROR: 1st index in PtransE must be <= NCrystal");
+      int ind[6] = {0, 0, 0, 0, 0, 0};
+      for (int j = 1; j <= nd; j++) {
+        long d = 1; for (int k = 0; k < nd - j; k++) d *= 10;
+        int digit = (int)((el / d) % 10);
+        if (digit > 3) die(" ERROR: evaporation index digit > 3");
+        if (j <= H.NCrystal) ind[j - 1] = digit; else ind[3 + j - H.NCrystal - 1] = digit;
+      }
+      H.refPE[(size_t)tb * 12288 + idxE(sp, ind[0], ind[1], ind[2], ind[3], ind[4], ind[5])] = v;
+    }
+    for (int j = 0; j < 3 * H.NCrystal; j++) {
+      char *p = const_cast<char *>(t.next());
+      int sp = (int)strtol(p, &p, 10), el = (int)strtol(p, &p, 10); double v = fnum(p);
+      if (sp > H.NCrystal || el < 1 || el > 3) die(" ERROR: 1st index in depo prob block must be <= NCrystal");
+      H.refPD[(size_t)tb * 9 + (sp - 1) + 3 * (el - 1)] = v;
+    }
+    for (int pass = 0; pass < 2; pass++)
+      for (int j = 0; j < 3 * H.NCov; j++) {
+        char *p = const_cast<char *>(t.next());
+        int sp = (int)strtol(p, &p, 10), el = (int)strtol(p, &p, 10); double v = fnum(p);
+        if (sp <= H.NCrystal || sp > H.NCrystal + H.NCov || el < 0 || el > 3) die(" ERROR: 1st index in abs/des prob block");
+        (pass == 0 ? H.refPA : H.refPS)[(size_t)tb * 12 + (sp - H.NCrystal - 1) + 3 * el] = v;
+      }
+  }
+  fclose(t.f);
+  for (int i = 0; i < 12288; i++) for (int tb = 0; tb < H.ntemp; tb++) if (H.refPE[(size_t)tb * 12288 + i] != 0.0) { H.st_idx.push_back(i); break; }
+  printf(" Done reading input probability table\n");
+}
+
 void read_start(Host &H, const char *path) {                 // main.f:83-219
   Lines in; in.f = fopen(path, "r");
   if (!in.f) die(" cannot open %s", path);
@@ -227,8 +305,15 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   if (H.NCov > 0) { printf(" Coverage species (NCov= %d ) --> Z:", H.NCov); for (int i = 0; i < H.NCov; i++) printf(" %d", H.ListCov[i]); printf("\n"); }
   H.InitSt = first_token(in.next()).substr(0, 2);
   if (H.InitSt == "FF") { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); H.Len4 = (int)strtol(p, &p, 10); }
-  else if (H.InitSt == "SH" || H.InitSt == "ST")
-    die(" mulskips.e (B200 host): InitSt %s is not built (SetShape / tabulated-temperature trench; see DESIGN.md section 10)", H.InitSt.c_str());
+  else if (H.InitSt == "SH")
+    die(" mulskips.e (B200 host): InitSt %s is not built (SetShape; see DESIGN.md section 10)", H.InitSt.c_str());
+  else if (H.InitSt == "ST") {                                                          // main.f:109-115
+    char *p = const_cast<char *>(in.next());
+    H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10);
+    H.angle = fnum(p, &p); H.Ttop = fnum(p, &p); H.Tbottom = fnum(p, &p);
+    printf(" Temperature on top in Kelvin:  %.17g\n Temperature on bottom in Kelvin:  %.17g\n", H.Ttop, H.Tbottom);
+    H.fixedT = H.Ttop == H.Tbottom;
+  }
   else if (H.InitSt == "IN") H.cadfile = whole_line(in.next());                         // main.f:108-111, read with '(A)'
   else if (H.InitSt == "LA") {                                                          // main.f:112-141
     printf(" ****** MulSKIPs run for laser annealing ******\n");
@@ -266,7 +351,7 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
     if (H.la()) die(" ERR: SaveCoo flag must be \"T\" for LA simulations!");
     printf(" SaveCoo flag is not \"T\": Coor file not stored\n");
   }
-  set_probability(H, in);
+  if (H.st()) set_probability_from_field(H, in); else set_probability(H, in);          // main.f:215-219
   fclose(in.f);
   printf(" numParticelle= %d Levels = %d , SizeTree = %d\n", 500000, 20, (1 << 20) - 1);
 }
@@ -414,6 +499,41 @@ void set_finfet(Host &H, int Len, int Lenww, int Lenwwtop, int Laperture) {
     if (ibits(H.L[H.ci(x, y, z)], PosIndex, LenIndex) != 113 && cubic_site(x, y, z, kind)) occupy(H, x, y, z, kind, false);
   pass_coordination(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
   pass_probability(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
+}
+// initial/SetTrenchSi.f:22-338 (InitSt ST): temperature ramp along z in the lattice words, wall planes at both ends,
+// Si bulk up to z=20, a Si slab up to Len3 with a V-shaped trench (half-width Len at the top, bottom at Len2, side-wall
+// angle in degrees)
+void set_trench_si(Host &H) {
+  const double Pi = (double)3.1415926535897932384626433832795028841971f;      // REAL(4) literal (SetTrenchSi.f:34)
+  int kind, LX = H.LX, LY = H.LY, LZ = H.LZ; int32_t s[3], nn[4][3];
+  const int Len = H.Len1, Len2 = H.Len2, Len3 = H.Len3;
+  const double arad = H.angle * Pi / 180;
+  const int Lenh = LX / 2 - 1;
+  printf(" %d %d %d\n", Lenh, Len, Len3);
+  H.t_lo = 8191; H.t_hi = 0;
+  for (int z = 0; z <= LZ - 1; z++) {
+    const int T = z <= Len3 - 1 ? (int)(H.Tbottom + (H.Ttop - H.Tbottom) * z / (Len3 - 1)) : (int)H.Ttop;
+    H.t_lo = std::min(H.t_lo, T); H.t_hi = std::max(H.t_hi, T);
+    for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) mvbits(T, LenT, H.L[H.ci(x, y, z)], PosT);
+  }
+  if (H.fixedT) H.interp_field((int)H.Ttop);                                  // :65-67
+  wall_planes(H, 0, 3);
+  wall_planes(H, LZ - 4, LZ - 1);
+  for (int z = 4; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind)) {
+      occupy(H, x, y, z, kind, false);
+      mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      s[0] = x; s[1] = y; s[2] = z;
+      dia_nn(H, x, y, z, kind, nn);
+      H.AddBulk(s, nn);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (!cubic_site(x, y, z, kind)) continue;
+    const bool in_trench = ((double)std::abs(x - Lenh) <= ((double)Len - (double)(Len3 - z) * cos(arad) / sin(arad))) && (z > Len2 && z < Len3);
+    if (!in_trench) occupy(H, x, y, z, kind, false);
+  }
+  pass_coordination(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
+  pass_probability(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
 }
 // One list-directed READ of a plane of LenX*LenY numbers (LattGeo / TempStat / checkpoint files): starts on a fresh
 // record, continues onto following records while values are missing, and drops what is left of the last record read.
@@ -681,16 +801,19 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "S") set_nc(H, H.Len1, H.Len1, H.Len1, true);
   else if (H.InitSt == "I") set_invp_off(H, H.Len1, H.Len2);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
+  else if (H.InitSt == "ST") set_trench_si(H);
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, I, FF, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, I, FF, ST, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
   for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
   write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
   // ---- hand the state to the GPU (include/mskc.h) ----
   if (mskc_create(H.LX, H.LY, H.LZ, H.NCrystal, H.NCov, H.ListCrystal, H.ListCov, device, 0, &R.h) != 0) die(" %s", mskc_last_error(nullptr));
-  MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
+  if (H.st()) MS(mskc_set_rate_field(R.h, H.ntemp, H.reftemp.data(), H.refPE.data(), H.refPD.data(), H.refPA.data(), H.refPS.data(), H.PtransZig,
+                                     H.t_lo, H.t_hi, H.fixedT ? (int)H.Ttop : 0));
+  else MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
   if (H.la()) MS(mskc_set_la(R.h, 1, H.Tm, H.P0, H.sigma, H.Tflex, H.t_lo, H.t_hi));
   {
     std::vector<int32_t> mx(3 * H.mc.size() + 3), mn(12 * H.mc.size() + 12), me(H.mc.size() + 1), bx(3 * H.bulk.size() + 3), bn(12 * H.bulk.size() + 12), vx(3 * H.voids.size() + 3), vn(12 * H.voids.size() + 12);

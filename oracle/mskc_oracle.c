@@ -342,6 +342,41 @@ static int site_temperature(Orc *o, const int32_t Site[3], const char *who) {
   if (t == 0) orc_fatal(o, "Temperature is zero in %s.", who);
   return t;
 }
+/* src/mcevent/InterpProbFromField.f:22-57 ('ST' mode): overwrite the four working tables with the blocks of the
+ * probability-table file interpolated at an integer temperature, weights are INTEGER distances.  Entries that are
+ * zero in every block interpolate to (w*0+w*0)/(w+w) = 0, so only the others are visited. */
+static void interp_prob_from_field(Orc *o, int temperature) {
+  int iupper = 0, ilower, exact = 0;
+  for (int i = 1; i <= o->ntemp; i++) if (o->reftempvalues[i - 1] - temperature == 0) { iupper = i; exact = 1; break; }   /* FINDLOC */
+  if (exact) {
+    const double *E = o->refPE + (size_t)(iupper - 1) * 12288;
+    for (int k = 0; k < o->st_nnz; k++) o->PtransE[o->st_idx[k]] = E[o->st_idx[k]];
+    memcpy(o->PtransD, o->refPD + (size_t)(iupper - 1) * 9, 9 * sizeof(double));
+    memcpy(o->PtransAbs, o->refPAbs + (size_t)(iupper - 1) * 12, 12 * sizeof(double));
+    memcpy(o->PtransDes, o->refPDes + (size_t)(iupper - 1) * 12, 12 * sizeof(double));
+    return;
+  }
+  int best = 0;
+  for (int i = 1; i <= o->ntemp; i++) {                                      /* MINLOC(diff, MASK=diff>0): first minimum */
+    int d = o->reftempvalues[i - 1] - temperature;
+    if (d > 0 && (iupper == 0 || d < best)) { iupper = i; best = d; }
+  }
+  ilower = iupper - 1;
+  if (iupper == 0 || ilower == 0)      /* the reference indexes its arrays out of bounds here */
+    orc_fatal(o, "InterpProbFromField: temperature %d K outside the tabulated range %d..%d K", temperature, o->reftempvalues[0], o->reftempvalues[o->ntemp - 1]);
+  int wlower = abs(o->reftempvalues[iupper - 1] - temperature), wupper = abs(o->reftempvalues[ilower - 1] - temperature);
+  const double *El = o->refPE + (size_t)(ilower - 1) * 12288, *Eu = o->refPE + (size_t)(iupper - 1) * 12288;
+#define ST_MIX(lo, up) (((double)wlower * (lo) + (double)wupper * (up)) / (double)(wlower + wupper))
+  for (int k = 0; k < o->st_nnz; k++) { int i = o->st_idx[k]; o->PtransE[i] = ST_MIX(El[i], Eu[i]); }
+  for (int i = 0; i < 9; i++) o->PtransD[i] = ST_MIX(o->refPD[(size_t)(ilower - 1) * 9 + i], o->refPD[(size_t)(iupper - 1) * 9 + i]);
+  for (int i = 0; i < 12; i++) o->PtransAbs[i] = ST_MIX(o->refPAbs[(size_t)(ilower - 1) * 12 + i], o->refPAbs[(size_t)(iupper - 1) * 12 + i]);
+  for (int i = 0; i < 12; i++) o->PtransDes[i] = ST_MIX(o->refPDes[(size_t)(ilower - 1) * 12 + i], o->refPDes[(size_t)(iupper - 1) * 12 + i]);
+#undef ST_MIX
+}
+/* the 'ST' hook at the top of Get_Prob.f:76-91 and Get_Prob_Ini.f:41-56 */
+static inline void st_hook(Orc *o, const int32_t Site[3], const char *who) {
+  if (o->InitSt[0] == 'S' && o->InitSt[1] == 'T' && !o->fixedT) interp_prob_from_field(o, site_temperature(o, Site, who));
+}
 /* the whole-table work the reference does on every call (Get_Prob.f:143-152); results unused */
 static void faithful_table_cost(Orc *o, int la, int temperature) {
   if (!o->PEcopy) o->PEcopy = (double *)malloc((3 * 4096 + 9) * sizeof(double));
@@ -391,6 +426,7 @@ static void draw_dep_abs(Orc *o, int Coor, const double PD[4], int *ev, double *
 /* src/mcevent/Get_Prob.f:54-331 */
 static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int32_t Site[3], const int32_t NextN[4][3], int *Index_Event, double *Prob_Event) {
   o->n_getprob++;
+  st_hook(o, Site, "get_prob()");
   if (CovInd > 0 && CovInd < 113) {                       /* desorption, :93-123 */
     if (Occ != 0) orc_fatal(o, "ERROR Covind!=0 with Occ!=0 in get_prob");
     if (Coor <= 3) {
@@ -477,6 +513,7 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
 static void Get_Prob_Ini(Orc *o, int Occ, int NSiC, int Coor, const int32_t Site[3], const int32_t NextN[4][3], int *Index_Event, double *Prob_Event) {
   int la = (strcmp(o->InitSt, "LA") == 0), temperature = 0;
   o->n_getprob++;
+  st_hook(o, Site, "get_prob_ini()");
   if (la) temperature = site_temperature(o, Site, "get_prob_ini()");
   if (o->faithful_cost) faithful_table_cost(o, la, temperature);
   if (Occ == 0) {
@@ -827,7 +864,7 @@ Orc *orc_create(int lenx, int leny, int lenz, int nummcmax) {
 void orc_destroy(Orc *o) {
   if (!o) return;
   free(o->LattCoo); free(o->LattInd); free(o->ListAdAtom); free(o->ListAtom); free(o->ListVoid);
-  free(o->Tree); free(o->PEcopy); free(o->trace); free(o);
+  free(o->Tree); free(o->PEcopy); free(o->trace); free(o->refPE); free(o->refPD); free(o->refPAbs); free(o->refPDes); free(o->st_idx); free(o);
 }
 int orc_sizeof_mc(void) { return (int)sizeof(OrcMC); }
 
@@ -904,6 +941,65 @@ static int set_probability(Orc *o, FILE *f) {
   return 0;
 }
 
+/* src/mcevent/SetProbabilityFromField.f:21-171: the last line of start.dat names a table file holding ntemp blocks,
+ * each = one temperature + the evaporation / deposition / absorption / desorption lines of SetProbability.f */
+static int set_probability_from_field(Orc *o, FILE *f) {
+  char line[4096];
+  static const int tab[3][4] = {{3, 9, 19, 34}, {18, 50, 100, 172}, {57, 150, 288, 480}};
+  if (!next_line(f, line, sizeof line)) orc_fatal(o, "start.dat: EOF before the probability-table file name");
+  strncpy(o->tempfilename, line, sizeof o->tempfilename - 1); trim_trailing(o->tempfilename);
+  LOG(o, " Reading input probability table: %s\n", o->tempfilename);
+  FILE *t = fopen(o->tempfilename, "r");
+  if (!t) orc_fatal(o, "cannot open %s", o->tempfilename);
+  if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF"); o->ntemp = (int)strtol(line, NULL, 10);
+  if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF"); o->nprob = (int)strtol(line, NULL, 10);
+  if (o->ntemp < 1 || o->ntemp > 300) orc_fatal(o, "probability table: ntemp must be 1..300 (ntempMax, defsystem.f:72)");
+  if (o->NCrystal < 1 || o->NCrystal > 3 || o->NCov < 0 || o->NCov > 3) orc_fatal(o, "ERROR: NCrystal and NCov must be <= 3 3");
+  int maxElines = tab[o->NCrystal - 1][o->NCov], nd = o->NCrystal + o->NCov;
+  free(o->refPE); free(o->refPD); free(o->refPAbs); free(o->refPDes); free(o->st_idx);
+  o->refPE = (double *)calloc((size_t)o->ntemp * 12288, sizeof(double));
+  o->refPD = (double *)calloc((size_t)o->ntemp * 9, sizeof(double));
+  o->refPAbs = (double *)calloc((size_t)o->ntemp * 12, sizeof(double));
+  o->refPDes = (double *)calloc((size_t)o->ntemp * 12, sizeof(double));
+  for (int tb = 0; tb < o->ntemp; tb++) {
+    if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF at block %d", tb + 1);
+    o->reftempvalues[tb] = (int)strtol(line, NULL, 10);
+    if (tb == 0) LOG(o, " maxElines %d\n", maxElines);
+    for (int i = 1; i <= maxElines; i++) {
+      if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF in evaporation block");
+      char *p = line; int indsp = (int)strtol(p, &p, 10); long elind = strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+      if (indsp > o->NCrystal) orc_fatal(o, "ERROR: 1st index in PtransE must be <= NCrystal");
+      int ind[6] = {0, 0, 0, 0, 0, 0};
+      for (int j = 1; j <= nd; j++) {
+        long d = 1; for (int k = 0; k < nd - j; k++) d *= 10;
+        int digit = (int)((elind / d) % 10);
+        if (digit > 3) orc_fatal(o, "evaporation index digit > 3");
+        if (j <= o->NCrystal) ind[j - 1] = digit; else ind[3 + j - o->NCrystal - 1] = digit;
+      }
+      o->refPE[(size_t)tb * 12288 + IDXE(indsp, ind[0], ind[1], ind[2], ind[3], ind[4], ind[5])] = v;
+    }
+    for (int j = 1; j <= o->NCrystal * 3; j++) {
+      if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF in deposition block");
+      char *p = line; int indsp = (int)strtol(p, &p, 10); int el = (int)strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+      if (indsp > o->NCrystal || el < 1 || el > 3) orc_fatal(o, "ERROR: 1st index in depo prob block must be <= NCrystal");
+      o->refPD[(size_t)tb * 9 + IDXD(indsp, el)] = v;
+    }
+    for (int pass = 0; pass < 2; pass++)
+      for (int j = 1; j <= o->NCov * 3; j++) {
+        if (!next_line(t, line, sizeof line)) orc_fatal(o, "probability table: EOF in abs/des block");
+        char *p = line; int indsp = (int)strtol(p, &p, 10); int el = (int)strtol(p, &p, 10); double v = fortran_strtod(p, &p);
+        if (indsp <= o->NCrystal || indsp > o->NCrystal + o->NCov || el < 0 || el > 3) orc_fatal(o, "ERROR: 1st index in abs/des prob block");
+        (pass == 0 ? o->refPAbs : o->refPDes)[(size_t)tb * 12 + IDXA(indsp - o->NCrystal, el)] = v;
+      }
+  }
+  fclose(t);
+  o->st_idx = (int *)malloc(12288 * sizeof(int)); o->st_nnz = 0;
+  for (int i = 0; i < 12288; i++) for (int tb = 0; tb < o->ntemp; tb++) if (o->refPE[(size_t)tb * 12288 + i] != 0.0) { o->st_idx[o->st_nnz++] = i; break; }
+  memset(o->PtransE, 0, sizeof o->PtransE);
+  LOG(o, " Done reading input probability table\n");
+  return 0;
+}
+
 /* src/main.f:83-219 */
 int orc_read_start(Orc *o, const char *path) {
   FILE *f = fopen(path, "r");
@@ -927,7 +1023,12 @@ int orc_read_start(Orc *o, const char *path) {
   if (o->NCov > 0) { LOG(o, " Coverage species (NCov= %d ) --> Z:", o->NCov); for (int i = 0; i < o->NCov; i++) LOG(o, " %d", o->ListCov[i]); LOG(o, "\n"); }
   NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->InitSt, tok, 2); o->InitSt[2] = 0;
   if (!strcmp(o->InitSt, "FF")) { NEXT(); char *p = line; o->Len1 = (int)strtol(p, &p, 10); o->Len2 = (int)strtol(p, &p, 10); o->Len3 = (int)strtol(p, &p, 10); o->Len4 = (int)strtol(p, &p, 10); }
-  else if (!strcmp(o->InitSt, "ST")) orc_fatal(o, "oracle: InitSt ST not restated");
+  else if (!strcmp(o->InitSt, "ST")) {                       /* main.f:109-115 */
+    NEXT(); char *p = line; o->Len1 = (int)strtol(p, &p, 10); o->Len2 = (int)strtol(p, &p, 10); o->Len3 = (int)strtol(p, &p, 10);
+    o->angle = fortran_strtod(p, &p); o->Ttop = fortran_strtod(p, &p); o->Tbottom = fortran_strtod(p, &p);
+    LOG(o, " Temperature on top in Kelvin:  %.17g\n Temperature on bottom in Kelvin:  %.17g\n", o->Ttop, o->Tbottom);
+    if (o->Ttop == o->Tbottom) o->fixedT = 1;
+  }
   else if (!strcmp(o->InitSt, "IN") || !strcmp(o->InitSt, "SH")) { NEXT(); strncpy(o->cadfilename, line, sizeof o->cadfilename - 1); trim_trailing(o->cadfilename); }
   else if (!strcmp(o->InitSt, "LA")) {
     LOG(o, " ****** MulSKIPs run for laser annealing ******\n");
@@ -984,7 +1085,8 @@ int orc_read_start(Orc *o, const char *path) {
     if (!strcmp(o->InitSt, "LA")) orc_fatal(o, "ERR: SaveCoo flag must be \"T\" for LA simulations!");
     LOG(o, " SaveCoo flag is not \"T\": Coor file not stored\n");
   }
-  set_probability(o, f);
+  if (!strcmp(o->InitSt, "ST")) set_probability_from_field(o, f);      /* main.f:215-219 */
+  else set_probability(o, f);
   LOG(o, " numParticelle= %d Levels = %d , SizeTree = %d\n", o->NumMcMax, o->Levels, o->SizeTree);
 #undef NEXT
   o->jb_set = 0;
@@ -1216,6 +1318,39 @@ static void set_finfet(Orc *o, int Len, int Lenww, int Lenwwtop, int Laperture) 
   pass_probability(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1, 0);
 }
 
+/* src/initial/SetTrenchSi.f:22-338 (InitSt 'ST'): temperature ramp along z written into the lattice words, wall
+ * planes at both ends, Si bulk up to z=20, then a Si slab up to Len3 with a V-shaped trench of half-width Len at
+ * the top, bottom at Len2 and side-wall angle `angle` (degrees) */
+static void set_trench_si(Orc *o, int Len, int Len2, int Len3, double angle, double Ttop, double Tbottom) {
+  const double Pi = (double)3.1415926535897932384626433832795028841971f;       /* REAL(4) literal, SetTrenchSi.f:34 */
+  int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ; int32_t Site[3], NextN[4][3];
+  double arad = angle * Pi / 180;
+  int Lenh = LX / 2 - 1;
+  LOG(o, " %d %d %d\n", Lenh, Len, Len3);
+  for (int z = 0; z <= LZ - 1; z++) {                                            /* :44-62 */
+    int temperature = z <= Len3 - 1 ? (int)(Tbottom + (Ttop - Tbottom) * z / (Len3 - 1)) : (int)Ttop;
+    for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) MVBITS(temperature, ORC_LenT, &o->LattCoo[CI(o, x, y, z)], ORC_PosT);
+  }
+  if (o->fixedT) interp_prob_from_field(o, (int)Ttop);                          /* :65-67 */
+  set_wall_planes(o, 0, 3, 0, LX - 1);
+  set_wall_planes(o, LZ - 4, LZ - 1, 0, LX - 1);
+  for (int z = 4; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      occupy(o, x, y, z, kind, 0);
+      MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    int in_trench = ((double)abs(x - Lenh) <= ((double)Len - (double)(Len3 - z) * cos(arad) / sin(arad))) && (z > Len2 && z < Len3);   /* :138-139 */
+    if (!in_trench) occupy(o, x, y, z, kind, 0);
+  }
+  pass_coordination(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0);
+  pass_probability(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0, 0);
+}
+
 /* list-directed READ of one plane (LattGeo / TempStat files): take n values starting on a fresh
  * record, continue onto following records only if the record is short, and DISCARD whatever is left
  * on the last record read -- the regression LattGeo file has a line with one value too many. */
@@ -1329,7 +1464,8 @@ int orc_setup(Orc *o) {
   else if (!strcmp(s, "FF")) {
     o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;
     set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
-  } else if (!strcmp(s, "IN")) set_cad(o);
+  } else if (!strcmp(s, "ST")) set_trench_si(o, o->Len1, o->Len2, o->Len3, o->angle, o->Ttop, o->Tbottom);
+  else if (!strcmp(s, "IN")) set_cad(o);
   else if (!strcmp(s, "LA")) { o->tmax = 0; set_T(o); set_cad(o); LOG(o, " Max temperature is:  %d K\n", o->tmax); }
   else orc_fatal(o, "initialization not_implemented in oracle: %s", s);
   LOG(o, " Atoms,Voids,AdAtoms %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
@@ -1659,6 +1795,15 @@ void orc_get_tables(Orc *o, double *PE, double *PD, double *PAbs, double *PDes, 
   memcpy(PE, o->PtransE, sizeof o->PtransE); memcpy(PD, o->PtransD, sizeof o->PtransD);
   memcpy(PAbs, o->PtransAbs, sizeof o->PtransAbs); memcpy(PDes, o->PtransDes, sizeof o->PtransDes);
   scal[0] = o->PtransZig; scal[1] = o->sf; scal[2] = o->Tm; scal[3] = o->P0; scal[4] = o->sigma; scal[5] = o->Tflex; scal[6] = o->MaxTime; scal[7] = o->OutTime;
+}
+/* 'ST' mode: sizes {ntemp, fixedT, INT(Ttop)} and the tabulated blocks (NULL pointers are skipped) */
+void orc_get_field(Orc *o, int32_t info[4], int32_t *reftemp, double *refPE, double *refPD, double *refPAbs, double *refPDes) {
+  info[0] = o->ntemp; info[1] = o->fixedT; info[2] = (int)o->Ttop; info[3] = 0;
+  if (reftemp) memcpy(reftemp, o->reftempvalues, (size_t)o->ntemp * sizeof(int32_t));
+  if (refPE) memcpy(refPE, o->refPE, (size_t)o->ntemp * 12288 * sizeof(double));
+  if (refPD) memcpy(refPD, o->refPD, (size_t)o->ntemp * 9 * sizeof(double));
+  if (refPAbs) memcpy(refPAbs, o->refPAbs, (size_t)o->ntemp * 12 * sizeof(double));
+  if (refPDes) memcpy(refPDes, o->refPDes, (size_t)o->ntemp * 12 * sizeof(double));
 }
 void orc_get_species(Orc *o, int32_t out[8]) {
   out[0] = o->NCrystal; out[1] = o->NCov; for (int i = 0; i < 3; i++) { out[2 + i] = o->ListCrystal[i]; out[5 + i] = o->ListCov[i]; }

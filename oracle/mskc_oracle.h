@@ -54,6 +54,11 @@ typedef struct Orc {
   int Len1, Len2, Len3, Len4;
   double sf, alloyfraction, Tm, P0, sigma, Tflex, LenVac, LenNuc;
   int tmax;
+  /* InitSt 'ST' (src/main.f:109-115, src/modules/defsystem.f:71-81): trench geometry + tabulated rates */
+  double angle, Ttop, Tbottom;
+  int fixedT, ntemp, nprob, reftempvalues[300];
+  double *refPE, *refPD, *refPAbs, *refPDes;   /* [ntemp][12288], [ntemp][9], [ntemp][12], [ntemp][12] */
+  int st_nnz; int *st_idx;                      /* PtransE entries that are non-zero in some block (the others interpolate to 0) */
   char cadfilename[2048], tempfilename[2048], coofilename[2048], restartfilename[2048];
   int64_t MaxIter, OutMolMol, Iter, IterOut, framecounter;
   double MaxTime, OutTime, Time;

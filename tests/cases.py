@@ -6,13 +6,16 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 CASES = ["Si-SL", "surface", "cube", "cube-zigzag", "sphere", "inverted-pyramid", "finfet", "CVD-Si-SiH2", "CAD", "LA"]
+# further reference input files kept as fixtures (no golden output exists for them in the reference):
+#   start-SiGeBdoped.dat = examples/ex5-CVD-IO/CVD-SiGeBdoped/start.dat (3 crystal + 2 coverage species, 288 evaporation classes)
 
 
 def start_path(case):
     return os.path.join(GOLDEN, f"start-{case}.dat")
 
 
-def make_start(case, dst, lens=None, maxiter=None, outmolmol=None, runtype=None, idum=None, ptranszig=None, maxtime=None, outtime=None, paths=None):
+def make_start(case, dst, lens=None, maxiter=None, outmolmol=None, runtype=None, idum=None, ptranszig=None, maxtime=None, outtime=None, paths=None,
+               alloyfraction=None):
     """Copy tests/golden/start-<case>.dat to dst with some of the positional lines replaced.
     The grammar is the one of mulskips-source/main.f:83-212."""
     lines = open(start_path(case)).read().split("\n")
@@ -31,6 +34,10 @@ def make_start(case, dst, lens=None, maxiter=None, outmolmol=None, runtype=None,
     else:
         if lens is not None:
             lines[i] = " ".join(str(v) for v in lens) + " ! Len"
+        i += 1
+    if lines[1].split()[:2] == ["14", "32"]:   # SiGe: the Ge-fraction line follows (main.f:142-149)
+        if alloyfraction is not None:
+            lines[i] = f"{alloyfraction} ! Ge fraction in substrate"
         i += 1
     if ptranszig is not None:
         lines[i] = f"{ptranszig} ! PtransZig"
@@ -119,4 +126,36 @@ def make_sige_case(dirpath, len1=48, fraction=0.3, maxiter=10**9):
     dst = os.path.join(dirpath, "start.dat")
     with open(dst, "w") as f:
         f.write("\n".join(lines))
+    return dst
+
+
+def make_st_case(dirpath, lens=(20, 45, 90), angle=54.7, ttop=1080.0, tbottom=920.0, maxiter=10**9, runtype="R",
+                 temps=(900, 950, 1000, 1100)):
+    """Silicon trench with a temperature ramp along z and tabulated rates, InitSt ST (initial/SetTrenchSi.f,
+    mcevent/SetProbabilityFromField.f, mcevent/InterpProbFromField.f): Si + H coverage, the probability-table file
+    holds one block per tabulated temperature (the CVD-Si-SiH2 regression table scaled by an Arrhenius-like factor),
+    start.dat ends with the table path instead of the rate lines.  ttop == tbottom gives the fixedT variant."""
+    import math
+    base_e = [("10", 2226.5697760341627), ("11", 981.1791875933076), ("12", 432.3747715110884), ("13", 190.53394670735102),
+              ("20", 34.804675968079124), ("21", 15.337324730794487), ("22", 6.7586760501256276),
+              ("30", 0.010861139302185713), ("31", 0.004786162082841824)]
+    out = [str(len(temps)), "18"]
+    for t in temps:
+        f = math.exp(-3.0 * (1000.0 / t - 1.0))
+        out.append(str(t))
+        out += [f"1 {d} {v * f!r}" for d, v in base_e]
+        out += [f"1 {c} {85.49860227606791 * (1.5 - 0.5 * f)!r}" for c in (1, 2, 3)]
+        out += [f"2 {c} {287.0271459302869 / f!r}" for c in (1, 2, 3)]
+        out += [f"2 {c} {40.27023414006161 * f!r}" for c in (1, 2, 3)]
+    table = os.path.join(dirpath, "probtable.dat")
+    with open(table, "w") as fh:
+        fh.write("\n".join(out) + "\n")
+    start = "\n".join([
+        "1 1 ! NCrystal NCov", "14 ! crystal species", "1 ! coverage species", "ST ! InitSt",
+        f"{lens[0]} {lens[1]} {lens[2]} {angle!r} {ttop!r} {tbottom!r} ! Len1 Len2 Len3 angle Ttop Tbottom",
+        "1.0 ! PtransZig", "0.4525 ! sf", "Iter", f"{maxiter} ! IterMax", f"{maxiter} ! OutMolMol", f"{runtype} ! RunType",
+        "9117116 ! IDUM", "F ! Save final state", "F ! Save final Coor", table, ""])
+    dst = os.path.join(dirpath, "start.dat")
+    with open(dst, "w") as fh:
+        fh.write(start)
     return dst

@@ -53,6 +53,7 @@ def load_oracle():
     lib.orc_export_lists.argtypes = [vp] + [C.c_void_p] * 8
     lib.orc_get_tables.argtypes = [vp] + [C.c_void_p] * 5
     lib.orc_get_species.argtypes = [vp, C.c_void_p]
+    lib.orc_get_field.argtypes = [vp] + [C.c_void_p] * 6
     lib.orc_get_run.argtypes = [vp, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
     lib.orc_get_rng.argtypes = [vp, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.orc_get_counts.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -153,6 +154,15 @@ class Oracle:
         return dict(PtransE=PE, PtransD=PD, PtransAbs=PA, PtransDes=PS, PtransZig=sc[0], sf=sc[1], Tm=sc[2], P0=sc[3], sigma=sc[4], Tflex=sc[5],
                     MaxTime=sc[6], OutTime=sc[7])
 
+    def field(self):
+        """'ST' mode: the tabulated rate blocks of the probability-table file (SetProbabilityFromField.f)."""
+        info = np.zeros(4, np.int32)
+        self.lib.orc_get_field(self.o, info.ctypes.data, None, None, None, None, None)
+        n = int(info[0])
+        rt, E, D, A, S = np.zeros(n, np.int32), np.zeros((n, 12288)), np.zeros((n, 9)), np.zeros((n, 12)), np.zeros((n, 12))
+        self.lib.orc_get_field(self.o, info.ctypes.data, rt.ctypes.data, E.ctypes.data, D.ctypes.data, A.ctypes.data, S.ctypes.data)
+        return dict(ntemp=n, fixedT=int(info[1]), Ttop=int(info[2]), reftemp=rt, refPE=E, refPD=D, refPAbs=A, refPDes=S)
+
     def species(self):
         a = np.zeros(8, np.int32)
         self.lib.orc_get_species(self.o, a.ctypes.data)
@@ -203,9 +213,16 @@ def trace_arrays(orc: Oracle):
 def upload_oracle_state(orc: Oracle, ctx):
     """Hand the oracle's current state to a CUDA context: the tests' way of giving both sides the same input."""
     t = orc.tables()
-    ctx.set_rates(t["PtransE"], t["PtransD"], t["PtransAbs"], t["PtransDes"], t["PtransZig"])
     L = orc.lattcoo()
     rp = orc.run_params()
+    if rp["InitSt"] == "ST":
+        fl = orc.field()
+        T = (L[:-1] >> 9) & 8191
+        tv = T[T > 0]
+        ctx.set_rate_field(fl["reftemp"], fl["refPE"], fl["refPD"], fl["refPAbs"], fl["refPDes"], t["PtransZig"], int(tv.min()), int(tv.max()),
+                           fixed_temperature=fl["Ttop"] if fl["fixedT"] else 0)
+    else:
+        ctx.set_rates(t["PtransE"], t["PtransD"], t["PtransAbs"], t["PtransDes"], t["PtransZig"])
     if rp["InitSt"] == "LA":
         T = (L[:-1] >> 9) & 8191
         tv = T[T > 0]

@@ -1,0 +1,50 @@
+"""Host logic of the drop-in executable without a GPU: mulskips_b200/bin/mulskips.e parses start.dat, builds the
+initial geometry with the reference's builders, writes frame 0 and the start-up log lines, and only then asks the
+CUDA library for a device (on a box without one it stops there, loudly: no CPU fallback).  Frame 0 and the list
+sizes must equal the oracle's for the start files no reference golden covers (InitSt ST, SG with 3+2 species)."""
+import os
+import subprocess
+
+import pytest
+
+from cases import make_st_case, make_start
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "mulskips_b200", "bin", "mulskips.e")
+ORACLE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
+
+
+def _tokens(text, key):
+    for line in text.splitlines():
+        if line.strip().startswith(key):
+            return line.split()
+    return None
+
+
+@pytest.mark.parametrize("kind", ["ST-ramp", "ST-fixedT", "SiGeBdoped"])
+def test_frame0_and_startup_log(tmp_path, kind):
+    if not (os.path.exists(EXE) and os.path.exists(ORACLE)):
+        import __graft_entry__ as g
+        g.build()
+    g, o = tmp_path / "host", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    if kind.startswith("ST"):
+        box = (96, 48, 144)
+        kw = dict(ttop=1000.0, tbottom=1000.0) if kind.endswith("fixedT") else {}
+        start = make_st_case(str(tmp_path), maxiter=1, **kw)
+    else:
+        box = (96, 96, 240)
+        start = make_start("SiGeBdoped", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=1, outmolmol=1)
+    args = ["--box", *[str(v) for v in box]]
+    logs = {}
+    for d, exe in ((g, EXE), (o, ORACLE)):
+        (d / "start.dat").write_text(open(start).read())
+        r = subprocess.run([exe, *args], cwd=d, capture_output=True, text=True)
+        logs[d] = r.stdout
+        if exe == ORACLE:
+            assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    for name in ("I00000000.xyz", "I00000000_d.xyz", "I00000000_v.xyz"):
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"{kind}: {name}"
+    assert len((g / "I00000000.xyz").read_text().splitlines()) > 50
+    for key in ("Atoms,Voids,AdAtoms", "maxElines", "Temperature on top", "Reading input probability table"):
+        assert _tokens(logs[g], key) == _tokens(logs[o], key), key

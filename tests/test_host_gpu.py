@@ -15,7 +15,7 @@ import subprocess
 
 import pytest
 
-from cases import GOLDEN, make_cad_case, make_la_case, make_sige_case, make_start, start_path
+from cases import GOLDEN, make_cad_case, make_la_case, make_sige_case, make_st_case, make_start, start_path
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -78,7 +78,7 @@ def test_regression_case(built, tmp_path, case):
     assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
 
 
-@pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe"])
+@pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe", "ST", "ST-fixedT", "SiGeBdoped"])
 def test_file_driven_case(built, tmp_path, kind):
     """InitSt SG (SetSiGex.f), InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
     temperature file, LA rate law, liquid nucleus) through the host program.  The regression inputs (LattGeo / TempStat
@@ -87,7 +87,13 @@ def test_file_driven_case(built, tmp_path, kind):
     g, o = tmp_path / "gpu", tmp_path / "oracle"
     g.mkdir(); o.mkdir()
     box = (96, 96, 120) if kind == "CAD" else (96, 96, 96)
-    if kind == "SiGe":                               # InitSt SG (SetSiGex.f): random-alloy substrate, the C5 slab's second material
+    if kind.startswith("ST"):                        # InitSt ST (SetTrenchSi.f + SetProbabilityFromField.f): trench, temperature ramp, tabulated rate blocks
+        box = (96, 48, 144)
+        start = make_st_case(str(tmp_path), maxiter=60000, **(dict(ttop=1000.0, tbottom=1000.0) if kind.endswith("fixedT") else {}))
+    elif kind == "SiGeBdoped":                       # examples/ex5-CVD-IO/CVD-SiGeBdoped/start.dat: 3 crystal + 2 coverage species, 288 evaporation classes
+        box = (96, 96, 240)
+        start = make_start("SiGeBdoped", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=60000, outmolmol=60000)
+    elif kind == "SiGe":                               # InitSt SG (SetSiGex.f): random-alloy substrate, the C5 slab's second material
         start = make_sige_case(str(tmp_path), 48, 0.3, maxiter=60000)
     else:
         start = make_cad_case(str(tmp_path), box, maxiter=60000) if kind == "CAD" else make_la_case(str(tmp_path), box, maxiter=3000)   # (the nucleus of this box regrows in ~4000 events)

@@ -19,6 +19,8 @@ SMALL = [
     ("cube-zigzag", (144, 144, 144), (48, 48, 48), 300000),
     ("sphere", (144, 144, 144), (60, 0, 0), 300000),
     ("CVD-Si-SiH2", (96, 96, 96), (48, 0, 0), 400000),
+    # examples/ex5-CVD-IO/CVD-SiGeBdoped: Si/Ge/B crystal species + Cl/H coverage, 288 evaporation classes, InitSt SG
+    ("SiGeBdoped", (96, 96, 240), (48, 0, 0), 300000),
 ]
 
 
@@ -60,6 +62,43 @@ def test_parity_small(tmp_path, case, box, lens, nev):
     c = ctx.counters()
     assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
     assert r.site_updates > 0
+    ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("variant", ["ramp", "fixedT", "ramp-T"])
+def test_parity_tabulated_field(tmp_path, variant):
+    """InitSt ST: trench builder with a temperature ramp along z, the four rate tables interpolated
+    between tabulated temperatures at every site's own temperature (InterpProbFromField.f) -- on the device a
+    per-kelvin table built by mskc_set_rate_field.  'fixedT' is the Ttop == Tbottom variant (one interpolation,
+    SetTrenchSi.f:65-67); 'ramp-T' uses the reference's test-mode random stream (RunType T)."""
+    from cases import make_st_case
+    from mulskips_b200 import Mskc
+    box = (96, 48, 144)
+    kw = dict(ttop=1000.0, tbottom=1000.0) if variant == "fixedT" else {}
+    start = make_st_case(str(tmp_path), runtype="T" if variant.endswith("-T") else "R", **kw)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    assert ctx.state_hash() == orc.hash()
+    for chunk in (1, 999, 199000):
+        r = ctx.run_parity(event_budget=chunk)
+        assert orc.run(chunk) == chunk and r.events_done == chunk
+        s = orc.sizes()
+        assert (r.num_adatom, r.num_atoms, r.num_voids) == (s["NumAdAtom"], s["NumAtoms"], s["NumVoids"])
+        assert bits(r.time) == bits(orc.time)
+        assert tuple(r.last_site) == orc.last_site()
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())
+    assert bits(r.tree_root) == bits(orc.tree_root)
+    d, g = orc.lists(), ctx.download_lists()
+    for k in ("mc_xyz", "mc_nn", "mc_event", "void_xyz", "void_nn"):
+        assert np.array_equal(d[k], g[k]), k
+    assert np.array_equal(d["mc_rate"].view(np.uint64), g["mc_rate"].view(np.uint64))
+    cc, cv = orc.counts()
+    c = ctx.counters()
+    assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
+    assert cv[0] > 100 and cc[0] != 0          # adsorption and growth both happened
     ctx.close(); orc.close()
 
 

@@ -22,6 +22,7 @@ CASES = [
     ("cube-zigzag", (144, 144, 144), (48, 48, 48), 200000, {}),
     ("sphere", (144, 144, 144), (60, 0, 0), 100000, {}),
     ("CVD-Si-SiH2", (96, 96, 96), (48, 0, 0), 300000, {}),
+    ("SiGeBdoped", (96, 96, 240), (48, 0, 0), 200000, {}),       # 3 crystal + 2 coverage species (ex5-CVD-IO/CVD-SiGeBdoped)
 ]
 
 
@@ -108,6 +109,37 @@ def test_replay_laser_annealing(tmp_path):
     xyz, ev, rate = ctx.download_active()
     got = {tuple(int(v) for v in p): (int(e), np.float64(r).view(np.uint64)) for p, e, r in zip(xyz, ev, rate)}
     assert got == exp
+    ctx.close(); orc.close()
+
+
+def test_replay_tabulated_field(tmp_path):
+    """the cooperative transition code with the 'ST' per-kelvin tables (all four tables temperature dependent, the
+    site temperature consulted for coverage sites too, T kept in erased words)"""
+    from cases import make_st_case
+    from mulskips_b200 import Mskc
+    box = (96, 48, 144)
+    start = make_st_case(str(tmp_path))
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    n = 150000
+    orc.set_trace(n)
+    assert orc.run(n) == n
+    site, code, arm, tree1 = trace_arrays(orc)
+    ctx.replay_events(site, code, arm, tree_root=1.0)
+    Lo = orc.lattcoo()
+    assert np.array_equal(ctx.download_lattice(), Lo)
+    exp, d = expected_active(orc)
+    xyz, ev, rate = ctx.download_active()
+    got = {tuple(int(v) for v in p): (int(e), np.float64(r).view(np.uint64)) for p, e, r in zip(xyz, ev, rate)}
+    assert set(got) == set(exp)
+    bad = [s for s, v in exp.items() if got[s] != v and not ((int(Lo[s[2], s[1], s[0]]) >> 23) & 1 and ((int(Lo[s[2], s[1], s[0]]) >> 24) & 7) == 0)]
+    assert len(bad) <= orc.quirks()["wl_cov"], bad[:5]
+    # the sampler itself runs on the temperature-dependent tables
+    p = ctx.run_parallel(n_sweeps=20, events_per_tile=2.0, seed=3)
+    assert p.events_done > 0
     ctx.close(); orc.close()
 
 
