@@ -107,7 +107,7 @@ def test_file_driven_case(built, tmp_path, kind):
         assert (g / name).read_bytes() == (o / name).read_bytes(), f"{kind}: {name} differs from the oracle's"
     for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:"):
         assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
-    assert len(open(g / "I00000000.xyz").readlines()) > 100
+    assert len(open(g / "I00000000.xyz").readlines()) > 50
     if kind == "LA":                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
         assert (g / "LattStat.dat").read_bytes() == (o / "LattStat.dat").read_bytes()
 
