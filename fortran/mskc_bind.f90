@@ -10,7 +10,8 @@ module mskc_bind
   implicit none
 
   integer(c_int), parameter :: MSKC_STOP_BUDGET = 0, MSKC_STOP_MAXITER = 1, MSKC_STOP_MAXTIME = 2, &
-                               MSKC_STOP_FRAME = 3, MSKC_STOP_FEWMC = 4, MSKC_STOP_ERROR = -1
+                               MSKC_STOP_FRAME = 3, MSKC_STOP_FEWMC = 4, MSKC_STOP_RESOLIDIFIED = 5, MSKC_STOP_ERROR = -1
+  integer(c_int), parameter :: MSKC_TREE_SRC = 0, MSKC_TREE_LA = 1
 
   type, bind(C) :: mskc_parity_args
     integer(c_int64_t) :: max_iter
@@ -55,7 +56,7 @@ module mskc_bind
   end type
 
   type, bind(C) :: mskc_counters
-    integer(c_int32_t) :: num_atoms, num_voids, num_adatom, pad
+    integer(c_int32_t) :: num_atoms, num_voids, num_adatom, num_adatom_occ
     integer(c_int32_t) :: CountCrystal(3), CountCov(3)
     integer(c_int64_t) :: iter
     real(c_double)     :: time
@@ -98,6 +99,19 @@ module mskc_bind
       type(c_ptr), value :: h, reftemp, refPE, refPD, refPAbs, refPDes
       integer(c_int), value :: ntemp, tmin, tmax, fixed_temperature
       real(c_double), value :: PtransZig
+    end function
+    ! mulskips-source-LaserAnnealing/main.f: once after mskc_create (species at bits 28-29, event codes 1-2/3/4/4+k) ...
+    integer(c_int) function mskc_set_tree_variant(h, variant) bind(C, name="mskc_set_tree_variant")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h
+      integer(c_int), value :: variant
+    end function
+    ! ... and after SetCAD (la/main.f:578-611): Tm, P0, sigma, Tflex(:NCrystal), InitCountCrystal, NumOcc0, NumAdAtomOcc
+    integer(c_int) function mskc_set_la_fork(h, enable, Tm, P0, sigma, Tflex, tmin, tmax, InitCountCrystal, num_occ0, num_adatom_occ) &
+        bind(C, name="mskc_set_la_fork")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, Tm, P0, sigma, Tflex, InitCountCrystal
+      integer(c_int), value :: enable, tmin, tmax, num_occ0, num_adatom_occ
     end function
     ! after the Set* builder (main.f:225-295): LattCoo and the three lists flattened to int32 arrays
     integer(c_int) function mskc_upload_state(h, LattCoo, n_mc, mc_xyz, mc_nn, mc_event, mc_rate, n_bulk, bulk_xyz, bulk_nn, &

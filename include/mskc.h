@@ -37,6 +37,8 @@ enum {
   MSKC_STOP_FRAME = 3,    /* output boundary reached AFTER the pick/time update and BEFORE the
                              event is applied (main.f:316-333): write the frame, call again       */
   MSKC_STOP_FEWMC = 4,    /* "few MC particles: stop MC" (main.f:307-310)                         */
+  MSKC_STOP_RESOLIDIFIED = 5, /* LaserAnnealing fork: NumAtoms+NumAdAtomOcc > NumOcc0
+                             (mulskips-source-LaserAnnealing/main.f:714-723)                      */
   MSKC_STOP_ERROR = -1
 };
 
@@ -69,6 +71,28 @@ int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double sigma, dou
  * temperature and use plain tables.  Either way a cleared cell keeps its temperature bits (Evaporation.f:70-74). */
 int mskc_set_rate_field(mskc_ctx *h, int ntemp, const int32_t *reftemp, const double *refPE, const double *refPD,
                         const double *refPAbs, const double *refPDes, double PtransZig, int tmin, int tmax, int fixed_temperature);
+
+/* The older LaserAnnealing fork (mulskips-source-LaserAnnealing, "la/"; what examples/ex4-LA-SiGe drives through
+ * sockets) differs from mulskips-source in three ways this library honours:
+ *  (1) layout: species at bits 28-29 (la/modules/defsystem.f:99-100) and event codes 1-2 deposit, 3 evaporate,
+ *      4 desorb, 4+k adsorb (la/main.f:671-699).  mskc_set_tree_variant(h, MSKC_TREE_LA) makes every entry point
+ *      that carries lattice words or event codes (upload_state, download_lattice, patch_lattice, download_lists,
+ *      download_active, replay_events, extract_frame) speak that layout; the device keeps one internal layout.
+ *  (2) rate law (la/mcevent/Get_Prob.f:142-152): Tm, P0, sigma, Tflex per crystal species and the solidification
+ *      rate scaled by the liquid fraction FLOAT(CountLiquid(k))/SUM(CountLiquid), CountLiquid = InitCountCrystal -
+ *      CountCrystal re-evaluated before every event (la/main.f:636).  Factors come from host-built tables (glibc
+ *      exp/erf) and are multiplied in the reference's order, so serial-parity rates are bit-identical.
+ *  (3) loop (la/main.f:675-681,714-723): in a Si/Ge melt a deposition of an exhausted species becomes the other one;
+ *      the run stops (MSKC_STOP_RESOLIDIFIED) once NumAtoms + NumAdAtomOcc exceeds num_occ0.  num_adatom_occ is the
+ *      builder's count of occupied ad-atoms (la/initial/SetCAD.f:544,595); the serial-parity loop updates it where
+ *      la/mcevent/deposition.f:219,246,253 and Evaporation.f:47,192 do, mskc_get_counters returns it.
+ * The sampler (mskc_run_parallel) uses CountLiquid as of the start of the call and derives the occupied count from a
+ * lattice census; call it with few sweeps per call when the melt composition changes quickly.
+ * Call after mskc_set_rates (and again after a new mskc_set_rates); enable = 0 switches the law off. */
+enum { MSKC_TREE_SRC = 0, MSKC_TREE_LA = 1 };
+int mskc_set_tree_variant(mskc_ctx *h, int variant);
+int mskc_set_la_fork(mskc_ctx *h, int enable, const double *Tm, const double *P0, const double *sigma, const double *Tflex /* [ncrystal] each */,
+                     int tmin, int tmax, const int32_t *InitCountCrystal /* [3] */, int num_occ0, int num_adatom_occ);
 
 /* Replaces: what the Set* builders leave in module globals (LattCoo + the three particle lists, in
  * REFERENCE LIST ORDER, built through mcevent/Add.f).  Coordinates are absolute, neighbours are
@@ -168,7 +192,8 @@ int mskc_download_lattice(mskc_ctx *h, int32_t *LattCoo);
  * species bits in place): n (cell index, word) pairs */
 int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const int32_t *word);
 typedef struct {
-  int32_t num_atoms, num_voids, num_adatom, pad;
+  int32_t num_atoms, num_voids, num_adatom;
+  int32_t num_adatom_occ;     /* LaserAnnealing fork: occupied ad-atoms (NumAdAtomOcc), 0 otherwise */
   int32_t CountCrystal[3], CountCov[3];
   int64_t iter; double time;
 } mskc_counters;

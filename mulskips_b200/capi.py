@@ -48,7 +48,7 @@ class ParallelResult(C.Structure):
 
 
 class Counters(C.Structure):
-    _fields_ = [("num_atoms", C.c_int32), ("num_voids", C.c_int32), ("num_adatom", C.c_int32), ("pad", C.c_int32),
+    _fields_ = [("num_atoms", C.c_int32), ("num_voids", C.c_int32), ("num_adatom", C.c_int32), ("num_adatom_occ", C.c_int32),
                 ("CountCrystal", C.c_int32 * 3), ("CountCov", C.c_int32 * 3), ("iter", C.c_int64), ("time", C.c_double)]
 
 
@@ -57,12 +57,13 @@ class Census(C.Structure):
                 ("occupied", C.c_int64), ("walls", C.c_int64), ("mean_height", C.c_double), ("sq_height", C.c_double)]
 
 
-STOP_BUDGET, STOP_MAXITER, STOP_MAXTIME, STOP_FRAME, STOP_FEWMC, STOP_ERROR = 0, 1, 2, 3, 4, -1
+STOP_BUDGET, STOP_MAXITER, STOP_MAXTIME, STOP_FRAME, STOP_FEWMC, STOP_RESOLIDIFIED, STOP_ERROR = 0, 1, 2, 3, 4, 5, -1
+TREE_SRC, TREE_LA = 0, 1
 
 _LIB = None
 
 # every symbol include/mskc.h declares
-SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_set_rate_field", "mskc_upload_state",
+SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "mskc_set_la", "mskc_set_rate_field", "mskc_set_tree_variant", "mskc_set_la_fork", "mskc_upload_state",
            "mskc_init_flat", "mskc_seed", "mskc_get_rng", "mskc_set_clock", "mskc_run_parity", "mskc_run_parallel",
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
@@ -88,6 +89,8 @@ def load_library():
     lib.mskc_set_rates.argtypes = [vp, f64p, f64p, f64p, f64p, C.c_double]
     lib.mskc_set_la.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
     lib.mskc_set_rate_field.argtypes = [vp, C.c_int, i32p, f64p, f64p, f64p, f64p, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.mskc_set_tree_variant.argtypes = [vp, C.c_int]
+    lib.mskc_set_la_fork.argtypes = [vp, C.c_int, f64p, f64p, f64p, f64p, C.c_int, C.c_int, i32p, C.c_int, C.c_int]
     lib.mskc_upload_state.argtypes = [vp, i32p, C.c_int, i32p, i32p, i32p, f64p, C.c_int, i32p, i32p, C.c_int, i32p, i32p]
     lib.mskc_init_flat.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     lib.mskc_seed.argtypes = [vp, C.c_int, C.c_int, C.c_int64, i32p]
@@ -201,6 +204,19 @@ class Mskc:
         assert pa.size == n * 12 and ps.size == n * 12
         self._ck(self.lib.mskc_set_rate_field(self.h, n, _p(rt, C.c_int32), _p(pe, C.c_double), _p(pd, C.c_double), _p(pa, C.c_double),
                                               _p(ps, C.c_double), float(PtransZig), int(tmin), int(tmax), int(fixed_temperature)))
+
+    def set_tree_variant(self, variant):
+        """TREE_LA: lattice words and event codes cross the boundary in the LaserAnnealing fork's layout."""
+        self._ck(self.lib.mskc_set_tree_variant(self.h, int(variant)))
+
+    def set_la_fork(self, Tm, P0, sigma, Tflex, tmin, tmax, InitCountCrystal, num_occ0, num_adatom_occ, enable=True):
+        """The LaserAnnealing fork's rate law and loop rules (mulskips-source-LaserAnnealing/mcevent/Get_Prob.f:142-152, main.f:634-726)."""
+        def arr(a):
+            v = np.zeros(3); a = np.atleast_1d(np.asarray(a, dtype=np.float64)); v[:len(a)] = a; return v
+        tm, p0, sg, tf = arr(Tm), arr(P0), arr(sigma), arr(Tflex)
+        ic = np.zeros(3, np.int32); ic[:len(InitCountCrystal)] = InitCountCrystal
+        self._ck(self.lib.mskc_set_la_fork(self.h, int(enable), _p(tm, C.c_double), _p(p0, C.c_double), _p(sg, C.c_double), _p(tf, C.c_double),
+                                           int(tmin), int(tmax), _p(ic, C.c_int32), int(num_occ0), int(num_adatom_occ)))
 
     # -- state -------------------------------------------------------------------------------------
     def upload_state(self, LattCoo, mc_xyz, mc_nn, mc_event, mc_rate, bulk_xyz, bulk_nn, void_xyz=None, void_nn=None):

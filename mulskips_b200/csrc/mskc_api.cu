@@ -42,7 +42,18 @@ struct mskc_ctx {
   bool parallel_ready = false;
   bool have_rates = false, have_state = false;
   int idum = 0, runtype = 'R';
+  // LaserAnnealing fork (include/mskc.h: mskc_set_tree_variant / mskc_set_la_fork)
+  int tree_variant = 0;
+  double *d_la3_F = nullptr;
+  int fork_occ = 0, fork_occ0 = 0;
 };
+
+// lattice words and event codes of the LaserAnnealing fork <-> the internal (mulskips-source) ones
+static inline uint32_t word_to_dev(uint32_t w) { return (w & ~(7u << 27)) | (((w >> 28) & 3u) << 27); }     // la/modules/defsystem.f:99-100 -> src/modules/defsystem.f:90-91
+static inline uint32_t word_from_dev(uint32_t w) { return (w & ~(7u << 27)) | (((w >> 27) & 3u) << 28); }
+static inline int ev_to_dev(int e) { return e <= 2 ? e : e + 1; }                                           // la/main.f:671-699 -> src/main.f:335-357
+static inline int ev_from_dev(int e) { return (e <= 2 || e == 100) ? e : e - 1; }
+static int push_fork_CL(mskc_ctx *h);
 
 static int upload_consts(mskc_ctx *h);
 static int set_err(mskc_ctx *h, const char *fmt, ...) {
@@ -211,7 +222,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
   cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
-  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S); cudaFree(h->d_err);
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S); cudaFree(h->d_la3_F); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }
   parallel_free(h->PC);
@@ -278,6 +289,79 @@ extern "C" int mskc_set_la(mskc_ctx *h, int enable, double Tm, double P0, double
   CK(cudaMemcpy(h->d_la_D, Dt.data(), Dt.size() * sizeof(double), cudaMemcpyHostToDevice));
   D.la = 1; D.keepT = 1; D.la_tmin = tmin; D.la_tmax = tmax; D.la_nnz = nnz;
   D.la_slot = h->d_la_slot; D.la_E = h->d_la_E; D.la_D = h->d_la_D;
+  return 0;
+}
+
+extern "C" int mskc_set_tree_variant(mskc_ctx *h, int variant) {
+  if (!h) return set_err(h, "mskc_set_tree_variant: NULL handle");
+  if (variant != MSKC_TREE_SRC && variant != MSKC_TREE_LA) return set_err(h, "mskc_set_tree_variant: unknown variant %d", variant);
+  if (variant == MSKC_TREE_LA && h->D.NCrystal > 2) return set_err(h, "mskc_set_tree_variant: the LaserAnnealing fork has two species bits (NCrystal <= 2)");
+  h->tree_variant = variant;
+  return 0;
+}
+
+extern "C" int mskc_set_la_fork(mskc_ctx *h, int enable, const double *Tm, const double *P0, const double *sigma, const double *Tflex,
+                                int tmin, int tmax, const int32_t *InitCountCrystal, int num_occ0, int num_adatom_occ) {
+  if (!h) return set_err(h, "mskc_set_la_fork: NULL handle");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  if (!enable) { D.la = 0; D.keepT = 0; return 0; }
+  if (!Tm || !P0 || !sigma || !Tflex || !InitCountCrystal) return set_err(h, "mskc_set_la_fork: NULL argument");
+  if (!h->have_rates) return set_err(h, "mskc_set_la_fork: call mskc_set_rates first");
+  if (D.NCrystal > 2) return set_err(h, "mskc_set_la_fork: the LaserAnnealing fork knows two crystal species");
+  if (tmin < 1 || tmax > 8191 || tmax < tmin) return set_err(h, "mskc_set_la_fork: temperature range must lie in 1..8191 K (13-bit field)");
+  const double kb = 0.00008617330350;               // la/mcevent/Get_Prob.f:70
+  std::vector<short> slot(12288, -1);
+  int nnz = 0;
+  for (int i = 0; i < 12288; i++) if (h->h_PE[i] != 0.0) slot[i] = (short)nnz++;
+  if (nnz == 0) nnz = 1;
+  const int nt = tmax - tmin + 1;
+  std::vector<double> E((size_t)nt * nnz, 0.0), F((size_t)nt * 3, 0.0);
+  for (int t = tmin; t <= tmax; t++) {
+    const int temperature = t;
+    for (int i = 0; i < 12288; i++) if (slot[i] >= 0) {   // :144-146  PE(k,...) = P0(k) * EXP(-PtransE(k,...)/(kb*temperature)) * merge
+      const int k = i % 3;
+      E[(size_t)(t - tmin) * nnz + slot[i]] = k < D.NCrystal ? P0[k] * exp(-h->h_PE[i] / (kb * temperature)) * 1.0 : 0.0;
+    }
+    for (int k = 0; k < D.NCrystal; k++) F[(size_t)(t - tmin) * 3 + k] = 1.0 + erf((temperature - Tflex[k]) / sigma[k]);   // :150
+  }
+  for (int k = 0; k < 3; k++) {
+    D.la3_halfP0[k] = k < D.NCrystal ? 0.5 * P0[k] : 0.0;
+    D.la3_init[k] = InitCountCrystal[k];
+    for (int c = 0; c < 3; c++) {
+      const double d = h->h_PD[k + 3 * c];
+      D.la3_expD[k + 3 * c] = k < D.NCrystal ? exp(-d / (kb * Tm[k])) : 0.0;     // :149
+      D.la3_merge[k + 3 * c] = d != 0.0 ? 1.0 : 0.0;                              // :151
+    }
+  }
+  D.la3_swap = (D.NCrystal == 2 && D.ListCrystal[0] == 14 && D.ListCrystal[1] == 32) ? 1 : 0;    // la/main.f:675-676
+  cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la3_F);
+  h->d_la_slot = nullptr; h->d_la_E = nullptr; h->d_la3_F = nullptr;
+  CK(cudaMalloc(&h->d_la_slot, 12288 * sizeof(short)));
+  CK(cudaMalloc(&h->d_la_E, E.size() * sizeof(double)));
+  CK(cudaMalloc(&h->d_la3_F, F.size() * sizeof(double)));
+  CK(cudaMemcpy(h->d_la_slot, slot.data(), 12288 * sizeof(short), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la_E, E.data(), E.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_la3_F, F.data(), F.size() * sizeof(double), cudaMemcpyHostToDevice));
+  D.la = 3; D.keepT = 1; D.la_tmin = tmin; D.la_tmax = tmax; D.la_nnz = nnz;
+  D.la_slot = h->d_la_slot; D.la_E = h->d_la_E; D.la3_F = h->d_la3_F;
+  h->fork_occ = num_adatom_occ; h->fork_occ0 = num_occ0;
+  if (h->parity_ready) {                               // state already uploaded: the two counters go into the loop state
+    h->h_ps.NumAdAtomOcc = num_adatom_occ; h->h_ps.NumOcc0 = num_occ0;
+    CK(cudaMemcpy(&h->d_ps->NumAdAtomOcc, &h->h_ps.NumAdAtomOcc, 2 * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+// la = 3: CountLiquid for the kernels that do not walk the serial loop (sampler, re-rate, trace replay): as of now
+static int push_fork_CL(mskc_ctx *h) {
+  if (h->D.la != 3) return 0;
+  mskc_counters c;
+  if (mskc_get_counters(h, &c)) return -1;
+  int cl[4];
+  for (int k = 0; k < 3; k++) cl[k] = h->D.la3_init[k] - c.CountCrystal[k];
+  cl[3] = cl[0] + cl[1] + cl[2];
+  CK(cudaMemcpyToSymbol(g_la_CL, cl, sizeof cl));
   return 0;
 }
 
@@ -410,6 +494,15 @@ extern "C" int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
   CK(cudaSetDevice(h->device));
   DevCtx &D = h->D;
   if (ensure_parity_buffers(h)) return -1;
+  std::vector<uint32_t> conv; std::vector<int32_t> conv_ev;
+  if (h->tree_variant == MSKC_TREE_LA) {               // the caller speaks the LaserAnnealing fork's layout
+    conv.resize((size_t)D.ncell);
+    for (long long i = 0; i < D.ncell; i++) conv[(size_t)i] = word_to_dev((uint32_t)LattCoo[i]);
+    LattCoo = (const int32_t *)conv.data();
+    conv_ev.resize((size_t)n_mc + 1);
+    for (int i = 0; i < n_mc; i++) conv_ev[i] = ev_to_dev(mc_event[i]);
+    mc_event = conv_ev.data();
+  }
   CK(cudaMemcpyAsync(D.state, LattCoo, D.ncell * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   // bonds + lattind are assembled on the host (sparse) and scattered on the device
   size_t nrec = (size_t)n_mc + n_bulk + n_void;
@@ -448,6 +541,7 @@ extern "C" int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
   memset(&S, 0, sizeof S);
   S.idum = idum; S.runtype = runtype ? runtype : 'R'; S.r_iff = iff; S.r_inext = inext; S.r_inextp = inextp; S.counter = counter; memcpy(S.r_ma, ma, sizeof ma);
   S.Iter = 1; S.Time = 0.0; S.NumAdAtom = n_mc; S.NumAtoms = n_bulk; S.NumVoids = n_void;
+  S.NumAdAtomOcc = h->fork_occ; S.NumOcc0 = h->fork_occ0;
   CK(cudaMemcpyAsync(h->d_ps, &S, sizeof S, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->d_err, 0, 8 * sizeof(int), h->stream));
   CK(cudaStreamSynchronize(h->stream));
@@ -541,6 +635,7 @@ extern "C" int mskc_download_lattice(mskc_ctx *h, int32_t *LattCoo) {
   CK(cudaMemcpyAsync(LattCoo, h->D.state, h->D.ncell * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   if (h->PC.listed_flag_in_state) { for (long long i = 0; i < h->D.ncell; i++) LattCoo[i] &= ~(int32_t)(1u << 30); }
+  if (h->tree_variant == MSKC_TREE_LA) for (long long i = 0; i < h->D.ncell; i++) LattCoo[i] = (int32_t)word_from_dev((uint32_t)LattCoo[i]);
   return 0;
 }
 extern "C" int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const int32_t *word) {
@@ -548,7 +643,8 @@ extern "C" int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const
   CK(cudaSetDevice(h->device));
   for (int i = 0; i < n; i++) {
     if (cell[i] < 0 || cell[i] >= h->D.ncell) return set_err(h, "mskc_patch_lattice: cell out of range");
-    CK(cudaMemcpyAsync(h->D.state + cell[i], word + i, 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->tree_variant == MSKC_TREE_LA) { const uint32_t w = word_to_dev((uint32_t)word[i]); CK(cudaMemcpy(h->D.state + cell[i], &w, 4, cudaMemcpyHostToDevice)); }
+    else CK(cudaMemcpyAsync(h->D.state + cell[i], word + i, 4, cudaMemcpyHostToDevice, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -561,10 +657,16 @@ extern "C" int mskc_get_counters(mskc_ctx *h, mskc_counters *c) {
   if (!h->parity_ready) { parallel_fill_counters(h->PC, c); return 0; }
   ParityState &S = h->h_ps;
   CK(cudaMemcpy(&S, h->d_ps, sizeof S, cudaMemcpyDeviceToHost));
-  c->num_atoms = S.NumAtoms; c->num_voids = S.NumVoids; c->num_adatom = S.NumAdAtom;
+  c->num_atoms = S.NumAtoms; c->num_voids = S.NumVoids; c->num_adatom = S.NumAdAtom; c->num_adatom_occ = S.NumAdAtomOcc;
   for (int i = 0; i < 3; i++) { c->CountCrystal[i] = S.CountCrystal[i]; c->CountCov[i] = S.CountCov[i]; }
   c->iter = S.Iter; c->time = S.Time;
-  if (h->PC.ran || h->PC.replayed) parallel_fill_counters(h->PC, c);
+  if (h->PC.ran || h->PC.replayed) {
+    parallel_fill_counters(h->PC, c);
+    if (h->D.la == 3) {       // the sampler does not carry NumAdAtomOcc: occupied ad-atoms = occupied, under-coordinated, non-wall cells
+      mskc_census cs; if (mskc_census_lattice(h, &cs, nullptr)) return -1;
+      c->num_adatom_occ = (int32_t)cs.undercoordinated;
+    }
+  }
   return 0;
 }
 
@@ -602,7 +704,7 @@ extern "C" int mskc_download_lists(mskc_ctx *h, int32_t *mc_xyz, int32_t *mc_nn,
       int32_t p[3]; xyz_of(cells[i], p);
       if (mc_xyz) memcpy(mc_xyz + 3 * i, p, 12);
       if (mc_nn) h_dec_bonds(D, p, b[i], mc_nn + 12 * i);
-      if (mc_event) mc_event[i] = evs[i];
+      if (mc_event) mc_event[i] = h->tree_variant == MSKC_TREE_LA ? ev_from_dev(evs[i]) : evs[i];
       if (mc_rate) mc_rate[i] = rates[i];
     }
   }
@@ -711,6 +813,7 @@ extern "C" int mskc_run_parallel(mskc_ctx *h, const mskc_parallel_args *a, mskc_
   CK(cudaSetDevice(h->device));
   if (h->PC.lists_stale) return set_err(h, "mskc_run_parallel: the state was advanced in parity mode; upload it again to rebuild the tile lists");
   if (upload_consts(h)) return -1;
+  if (push_fork_CL(h)) return -1;
   if (parallel_run(h->PC, h->D, h->stream, h->ev0, h->ev1, a, r, &h->err)) { g_last_error = h->err; return -1; }
   return check_dev_err(h);
 }
@@ -718,6 +821,7 @@ extern "C" int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate
   if (!h || !h->parallel_ready) return set_err(h, "mskc_rerate_all: no parallel state");
   CK(cudaSetDevice(h->device));
   if (upload_consts(h)) return -1;
+  if (push_fork_CL(h)) return -1;
   if (parallel_rerate(h->PC, h->D, h->stream, h->ev0, h->ev1, n_sites, total_rate, kernel_ms, &h->err)) { g_last_error = h->err; return -1; }
   return check_dev_err(h);
 }
@@ -743,6 +847,9 @@ extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xy
   int32_t *d_s = nullptr, *d_e = nullptr, *d_a = nullptr; TileStat *d_out = nullptr; TileStat out{};
   CK(cudaMalloc(&d_s, (size_t)n * 12)); CK(cudaMalloc(&d_e, (size_t)n * 4)); CK(cudaMalloc(&d_a, (size_t)n * 4)); CK(cudaMalloc(&d_out, sizeof(TileStat)));
   CK(cudaMemcpyAsync(d_s, site_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+  std::vector<int32_t> conv_ev;
+  if (h->tree_variant == MSKC_TREE_LA) { conv_ev.resize((size_t)n); for (int64_t i = 0; i < n; i++) conv_ev[(size_t)i] = ev_to_dev(event[i]); event = conv_ev.data(); }
+  if (push_fork_CL(h)) return -1;
   CK(cudaMemcpyAsync(d_e, event, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(d_a, arm, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(d_out, 0, sizeof(TileStat), h->stream));
@@ -754,7 +861,7 @@ extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xy
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(&out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->stream));               // (also keeps conv_ev alive until the copy is done)
   cudaFree(d_s); cudaFree(d_e); cudaFree(d_a); cudaFree(d_out);
   ParallelCtx &P = h->PC;
   P.replayed = true;
@@ -782,7 +889,7 @@ extern "C" int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int3
       if (k < cap) {
         uint32_t c = (uint32_t)CE[a];
         if (xyz) { int32_t z = (int32_t)(c / plane); long long r = c - (long long)z * plane; xyz[3 * k + 2] = z; xyz[3 * k + 1] = (int32_t)(r / D.LX); xyz[3 * k] = (int32_t)(r % D.LX); }
-        if (event) event[k] = (int32_t)ce_event(CE[a]);
+        if (event) event[k] = h->tree_variant == MSKC_TREE_LA ? ev_from_dev((int)ce_event(CE[a])) : (int32_t)ce_event(CE[a]);
         if (rate) rate[k] = R[a];
       }
       k++;
@@ -874,6 +981,7 @@ extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint
   if (m > 0 && cell) CK(cudaMemcpyAsync(cell, h->d_frame_cell, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
   if (m > 0 && word) CK(cudaMemcpyAsync(word, h->d_frame_word, (size_t)m * 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (h->tree_variant == MSKC_TREE_LA && word) for (int64_t i = 0; i < m; i++) word[i] = word_from_dev(word[i]);
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, h->ev0, h->ev1));
   *n = (int64_t)cnt;
   return 0;

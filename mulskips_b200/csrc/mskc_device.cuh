@@ -51,6 +51,14 @@ struct DevCtx {
   const double *la_E;               // [(tmax-tmin+1)][la_nnz]
   const double *la_D;               // [(tmax-tmin+1)][9]
   const double *la_A, *la_S;        // la = 2 only: [(tmax-tmin+1)][12] absorption / desorption
+  // la = 3: the LaserAnnealing fork's law (mulskips-source-LaserAnnealing/mcevent/Get_Prob.f:142-152): per-species
+  // P0 / Tm / sigma / Tflex, melting from la_E as above, solidification = 0.5*P0(k) * FLOAT(CountLiquid(k))/SUM(CountLiquid)
+  // * EXP(-PtransD/(kb*Tm(k))) * (1+ERF((T-Tflex(k))/sigma(k))) * merge, multiplied left to right on the device from
+  // host-built factors (glibc exp/erf) so that the product is the CPU's bit for bit
+  double la3_halfP0[3], la3_expD[9], la3_merge[9];
+  const double *la3_F;              // [(tmax-tmin+1)][3]: 1 + erf((T - Tflex(k)) / sigma(k))
+  int la3_init[3];                  // InitCountCrystal (la/main.f:596-602)
+  int la3_swap;                     // Si/Ge melt: deposit the other species once one is used up (la/main.f:675-681)
   double rot_c[2], rot_s[2];        // cos/sin(2*irot*Pi_f/3), host libm (FIND_NN.f:51-52)
   int nn_exact;                     // 1: the integer form of FIND_NN.f on the ideal bond shell was verified against the double routine
   const unsigned short *arm_tab;    // [32768] arm-chair offset code per bond code (mskc_coop.cuh), 0 = use find_sn()
@@ -61,6 +69,9 @@ struct DevCtx {
 // copies on the stack of the non-inlined transition functions).  mskc_api.cu uploads the handle's
 // DevCtx before launching (one context is "current" per device at a time).
 __constant__ DevCtx D;
+// la = 3: CountLiquid(1..3) and its sum as of the top of the current iteration (la/main.f:636).  The serial-parity
+// kernel rewrites it before every event; the sampler and the trace replay take it from the host per call / per event.
+__device__ int g_la_CL[4];
 
 // cold path, kept out of line so the hot code stays small (the kernels are instruction-fetch sensitive)
 __device__ __noinline__ void fail(int code, int a = 0, int b = 0, int c = 0, int d = 0) {
@@ -220,8 +231,18 @@ __device__ __forceinline__ double rate_E(int idx, int T) {
   int slot = D.la_slot[idx];
   return slot < 0 ? 0.0 : __ldg(&D.la_E[(long long)(T - D.la_tmin) * D.la_nnz + slot]);
 }
+__device__ __noinline__ double rate_D_fork(int sp, int i, int T) {
+  if (sp > D.NCrystal) return 0.0;                        // the module array PD(k>NCrystal,:) is never written
+  const volatile int *cl = g_la_CL;
+  double v = D.la3_halfP0[sp - 1] * (double)(float)cl[sp - 1];
+  v = v / (double)cl[3];
+  v = v * D.la3_expD[i];
+  v = v * __ldg(&D.la3_F[(long long)(T - D.la_tmin) * 3 + (sp - 1)]);
+  return v * D.la3_merge[i];
+}
 __device__ __forceinline__ double rate_D(int sp, int coor, int T) {
   int i = (sp - 1) + 3 * (coor - 1);
+  if (D.la == 3) return rate_D_fork(sp, i, T);
   return D.la ? __ldg(&D.la_D[(long long)(T - D.la_tmin) * 9 + i]) : __ldg(&D.PD[i]);
 }
 __device__ __forceinline__ double rate_Abs(int k, int coor, int T) {
@@ -363,7 +384,7 @@ __device__ __noinline__ bool arm_choice(Pol &pol, const P3 Zig[3], const P3 Arm[
 // tiles converge again for the expensive part, and the hot code stays small.  The order of list / tree
 // operations (hence parity mode's bit-exactness) is unchanged; Get_Prob of a neighbour never reads
 // what a later neighbour's update writes (neighbours of one site are not bonded to each other).
-enum { A_NEW = 0, A_SETVOID, A_SETBULK, A_SET, A_VOID2MC, A_BULK2MC, A_ERASE };
+enum { A_NEW = 0, A_SETVOID, A_SETBULK, A_SET, A_VOID2MC, A_BULK2MC, A_ERASE, A_SETSELF /* the site that was just filled (deposition.f:237-250) */ };
 struct RQItem { P3 N; long long c; P3 nn[4]; int Occ, NSiC, Cov, Coor, act, pre; uint32_t pre_w; };
 struct RQ { int n; RQItem it[6]; };
 __device__ __forceinline__ void rq_push(RQ &q, int act, P3 N, long long c, int Occ, int NSiC, int Cov, int Coor, const P3 nn[4], int pre = 0, uint32_t pre_w = 0) {
@@ -377,10 +398,12 @@ __device__ __forceinline__ void rq_commit(Pol &pol, RQItem &it, int ev, double p
   switch (it.act) {
     case A_NEW: if (ev != 0) pol.add_mc(it.N, it.c, it.nn, ev, p); break;
     case A_SETVOID: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_void(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
-    case A_SETBULK: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); } else pol.set_rate(it.N, it.c, ev, p); break;
+    // NumAdAtomOcc follows la/mcevent/deposition.f:219,246,253 and la/mcevent/Evaporation.f:47,192
+    case A_SETBULK: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); pol.NumAdAtomOcc--; } else pol.set_rate(it.N, it.c, ev, p); break;
+    case A_SETSELF: if (ev == 0) { pol.erase_mc(it.N, it.c); pol.add_bulk(it.N, it.c, it.nn); pol.NumAdAtomOcc--; } else { pol.set_rate(it.N, it.c, ev, p); pol.NumAdAtomOcc++; } break;
     case A_SET: pol.set_rate(it.N, it.c, ev, p); break;
     case A_VOID2MC: pol.erase_void(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
-    case A_BULK2MC: pol.erase_bulk(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); break;
+    case A_BULK2MC: pol.erase_bulk(it.N, it.c); pol.add_mc(it.N, it.c, it.nn, ev, p); pol.NumAdAtomOcc++; break;
     default: pol.erase_mc(it.N, it.c); break;
   }
 }
@@ -485,7 +508,7 @@ __device__ __noinline__ void deposition(Pol &pol, RQ &q, P3 Site, int IAtom) {
     }
   }
   uint32_t wS2 = (Coor != CoorOld) ? MVBITS(wS, Coor, LenCoor, PosCoor) : wS;
-  rq_push(q, A_SETBULK, Site, cS, 1, IAtom, 0, Coor, NextN, 1, wS2);
+  rq_push(q, A_SETSELF, Site, cS, 1, IAtom, 0, Coor, NextN, 1, wS2);
 }
 
 // Evaporation.f:95-122 / :229-258: keep only the occupied, under-coordinated, reciprocal neighbour and
@@ -509,6 +532,7 @@ __device__ __noinline__ void evaporation(Pol &pol, RQ &q, P3 Site) {
   uint32_t wS = D.state[cS];
   int IAtom = w_sp(wS);
   if (IAtom >= 1 && IAtom <= 3) pol.CountCrystal[IAtom - 1]--;
+  pol.NumAdAtomOcc--;
   int Coor = w_coor(wS);
   wS = MVBITS(wS, 0, 1, PosOcc);
   wS = MVBITS(wS, 0, LenSiC, PosSiC);

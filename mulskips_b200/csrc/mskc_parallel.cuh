@@ -429,9 +429,19 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
   long long done = 0;
+  const bool fork = D.la == 3;
+  int cl0[3] = {0, 0, 0};
+  if (fork) { cl0[0] = g_la_CL[0]; cl0[1] = g_la_CL[1]; cl0[2] = g_la_CL[2]; }
   for (long long i = 0; i < n; i++) {
     P3 S; S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2];
     const int arm = ev_arm[i];
+    if (fork) {                                    // la/main.f:636: CountLiquid as of the top of this iteration
+      int c[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) c[k] = cl0[k] - __reduce_add_sync(0xFFFFFFFFu, K.dCrystal[k]);
+      if (lane == 0) { volatile int *cl = g_la_CL; cl[0] = c[0]; cl[1] = c[1]; cl[2] = c[2]; cl[3] = c[0] + c[1] + c[2]; }
+      __syncwarp();
+    }
     coop_event<32, F_COV | F_LA>(L, lane, true, S, (uint32_t)cidx(S), ev_code[i], root, 0.5, arm == 0 ? -1 : arm - 1, K);
     done++;
     if (D.err[0] != 0) break;

@@ -21,6 +21,7 @@ struct ParityState {
   double Time;
   int NumAdAtom, NumAtoms, NumVoids;
   int CountCrystal[3], CountCov[3];
+  int NumAdAtomOcc, NumOcc0;                // LaserAnnealing fork: occupied ad-atoms, stop threshold (la/main.f:714-723)
   int idum, runtype, r_iff, r_inext, r_inextp, r_ma[56];
   int pending, pend_ind, pend_itrans;       // an event picked but not yet applied (frame boundary)
   int last_site[3];
@@ -44,6 +45,7 @@ __constant__ ParityView PV;
 struct ParityPol {
   int NumAdAtom, NumAtoms, NumVoids;
   int CountCrystal[3], CountCov[3];
+  int NumAdAtomOcc;
   long long n_getprob, n_ran3;
 
   __device__ __forceinline__ bool predraw() const { return true; }
@@ -163,6 +165,8 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
   pol.NumAdAtom = S.NumAdAtom; pol.NumAtoms = S.NumAtoms; pol.NumVoids = S.NumVoids;
   for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = S.CountCrystal[i]; pol.CountCov[i] = S.CountCov[i]; }
   pol.n_getprob = 0; pol.n_ran3 = 0;
+  pol.NumAdAtomOcc = S.NumAdAtomOcc;
+  const bool fork = D.la == 3;
   long long Iter = S.Iter, done = 0;
   double Time = S.Time;
   long long framecounter = A.framecounter;
@@ -174,6 +178,10 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
     else {
       if (A.event_budget > 0 && done >= A.event_budget) { stop = 0; break; }
       S.IterOut = Iter;
+      if (fork) {                                  // la/main.f:636  CountLiquid = InitCountCrystal - CountCrystal
+        int c0 = D.la3_init[0] - pol.CountCrystal[0], c1 = D.la3_init[1] - pol.CountCrystal[1], c2 = D.la3_init[2] - pol.CountCrystal[2];
+        volatile int *cl = g_la_CL; cl[0] = c0; cl[1] = c1; cl[2] = c2; cl[3] = c0 + c1 + c2;
+      }
       if (pol.NumAdAtom <= 20) { stop = 4; break; }
       int idx = 1;
       for (int lev = 0; lev < nlev; lev++) {
@@ -196,15 +204,18 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
       if (frame) { S.pending = 1; S.pend_ind = Ind; S.pend_itrans = Itrans; stop = 3; break; }
     }
     P3 Site = cell_xyz((long long)PV.mc_cell[Ind]);
+    // la/main.f:675-681: once a species of the Si/Ge melt is used up, the other one solidifies in its place
+    if (fork && D.la3_swap && (Itrans == 1 || Itrans == 2) && pol.CountCrystal[Itrans - 1] >= D.la3_init[Itrans - 1]) Itrans = Itrans % 2 + 1;
     apply_event(pol, Site, Itrans);
     done++;
     Iter++;
     if (D.err[0] != 0) { stop = -1; break; }
     if (!A.exit_on_time) { if (Iter > A.max_iter) { stop = 1; break; } }
     else if (Time > A.max_time) { stop = 2; break; }
+    if (fork && pol.NumAtoms + pol.NumAdAtomOcc > S.NumOcc0) { stop = 5; break; }       // la/main.f:714-723
   }
   S.Iter = Iter; S.Time = Time; S.framecounter = framecounter;
-  S.NumAdAtom = pol.NumAdAtom; S.NumAtoms = pol.NumAtoms; S.NumVoids = pol.NumVoids;
+  S.NumAdAtom = pol.NumAdAtom; S.NumAtoms = pol.NumAtoms; S.NumVoids = pol.NumVoids; S.NumAdAtomOcc = pol.NumAdAtomOcc;
   for (int i = 0; i < 3; i++) { S.CountCrystal[i] = pol.CountCrystal[i]; S.CountCov[i] = pol.CountCov[i]; }
   S.events_done = done; S.site_updates = pol.n_getprob;
   S.stop_reason = stop;

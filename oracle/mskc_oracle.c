@@ -27,6 +27,14 @@ static void orc_fatal(Orc *o, const char *fmt, ...) {
 }
 #define LOG(o, ...) do { if ((o)->log) fprintf((o)->log, __VA_ARGS__); } while (0)
 
+/* species bits and event codes of the two source trees: src/ (modules/defsystem.f:90-91, main.f:335-357) and the older
+ * LaserAnnealing fork la/ (la/modules/defsystem.f:99-100, la/main.f:671-699), selected at run time by o->la_tree */
+#define PSI(o) ((o)->la_tree ? 28 : 27)
+#define PC_(o) ((o)->la_tree ? 29 : 28)
+#define PSIC(o) ((o)->la_tree ? 28 : 27)
+#define LSIC(o) ((o)->la_tree ? 2 : 3)
+#define EV_EVAP(o) ((o)->la_tree ? 3 : 4)
+#define EV_DES(o) ((o)->la_tree ? 4 : 5)
 static inline int IBITS(int32_t w, int pos, int len) { return (int)(((uint32_t)w >> pos) & ((1u << len) - 1u)); }
 static inline void MVBITS(int from, int len, int32_t *to, int pos) {
   uint32_t m = ((1u << len) - 1u);
@@ -337,6 +345,16 @@ static inline double la_PE(Orc *o, int temperature, double e) {
 static inline double la_PD(Orc *o, int temperature, double d) {
   return 0.5 * o->P0 * exp(-d / (KB * o->Tm)) * (1.0 + erf((temperature - o->Tflex) / o->sigma)) * (d != 0.0 ? 1.0 : 0.0);
 }
+/* la/ fork, la/mcevent/Get_Prob.f:142-152: per-species parameters, solidification scaled by the liquid fraction of
+ * species k (FLOAT() is REAL(4); evaluation left to right) */
+static inline double la_PE_k(Orc *o, int temperature, int k, double e) {
+  return o->P0_k[k - 1] * exp(-e / (KB * temperature)) * (e != 0.0 ? 1.0 : 0.0);
+}
+static inline double la_PD_k(Orc *o, int temperature, int k, double d) {
+  int sum = o->CountLiquid[0] + o->CountLiquid[1] + o->CountLiquid[2];
+  return 0.5 * o->P0_k[k - 1] * (double)(float)o->CountLiquid[k - 1] / (double)sum * exp(-d / (KB * o->Tm_k[k - 1]))
+         * (1.0 + erf((temperature - o->Tflex_k[k - 1]) / o->sigma_k[k - 1])) * (d != 0.0 ? 1.0 : 0.0);
+}
 static int site_temperature(Orc *o, const int32_t Site[3], const char *who) {
   int t = IBITS(LC(o, Site), ORC_PosT, ORC_LenT);
   if (t == 0) orc_fatal(o, "Temperature is zero in %s.", who);
@@ -393,7 +411,7 @@ static void faithful_table_cost(Orc *o, int la, int temperature) {
 /* src/mcevent/Get_Prob.f:22-52 */
 static int IndexEvent_Abs(Orc *o, int Coor, double Ptmp, double PDepo) {
   int res = 0;
-  if (o->NCov == 1) return 6;
+  if (o->NCov == 1) return EV_DES(o) + 1;
   if (o->NCov >= 2) {
     for (int i = 1; i <= o->NCov; i++) {
       double pmin, pmax, s;
@@ -402,7 +420,7 @@ static int IndexEvent_Abs(Orc *o, int Coor, double Ptmp, double PDepo) {
         s = 0; for (int k = 1; k <= i - 1; k++) s += o->PtransAbs[IDXA(k, Coor)]; pmin = PDepo + s;
         s = 0; for (int k = 1; k <= i; k++) s += o->PtransAbs[IDXA(k, Coor)]; pmax = PDepo + s;
       }
-      if (Ptmp > pmin && Ptmp <= pmax) res = 5 + i;
+      if (Ptmp > pmin && Ptmp <= pmax) res = EV_DES(o) + i;
     }
   }
   if (res == 0) o->q_anom++;
@@ -430,7 +448,7 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
   if (CovInd > 0 && CovInd < 113) {                       /* desorption, :93-123 */
     if (Occ != 0) orc_fatal(o, "ERROR Covind!=0 with Occ!=0 in get_prob");
     if (Coor <= 3) {
-      *Index_Event = 5;
+      *Index_Event = EV_DES(o);
       int iCov = 0;
       for (int j = 1; j <= o->NCov; j++) if (o->ListCov[j - 1] == CovInd) { iCov = j; break; }
       if (iCov == 0) orc_fatal(o, "ERROR: could not find CovInd=%d inside ListCov", CovInd);
@@ -446,7 +464,8 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
     if (Occ == 0) {
       double PD[4] = {0, 0, 0, 0};
       if (Coor >= 1 && Coor <= 3)
-        for (int k = 1; k <= 3; k++) PD[k] = la ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)]) : o->PtransD[IDXD(k, Coor)];
+        for (int k = 1; k <= 3; k++) PD[k] = !la ? o->PtransD[IDXD(k, Coor)] : !o->la_tree ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)])
+                                             : k <= o->NCrystal ? la_PD_k(o, temperature, k, o->PtransD[IDXD(k, Coor)]) : 0.0;   /* la/: module PD(k>NCrystal,:) stays 0 */
       if (Coor == 1) {
         int CoorNN = IBITS(LC(o, NextN[0]), ORC_PosCoor, ORC_LenCoor);
         if (CoorNN >= 2) draw_dep_abs(o, Coor, PD, Index_Event, Prob_Event);
@@ -470,7 +489,7 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
             if (CoorNN >= 1 && CoorNN <= 3) NextNN = mc_nn(o, IndNN);
             else { NextNN = bulk_nn(o, IndNN); if (CoorNN != 4) o->q_wl_iso++; }
             if (recipr(NextNN, Site)) {
-              int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+              int SiOrC = IBITS(w, PSIC(o), LSIC(o));
               if (SiOrC == 1) N_Si++;
               if (SiOrC == 2) N_C++;
               if (SiOrC == 3) N_B++;
@@ -492,16 +511,16 @@ static void Get_Prob(Orc *o, int Occ, int NSiC, int CovInd, int Coor, const int3
       if (ncry != Coor)
         orc_fatal(o, "%d %d %d %d %d Get Prob Error N_Si+N_C+N_B+N_wall.NE.Coor site %d %d %d", Coor, N_Si, N_C, N_B, N_wall, Site[0], Site[1], Site[2]);
       if (ncry > 3) { *Index_Event = 0; *Prob_Event = 0.0; }
-      else if (ncry == 0) { *Index_Event = 4; *Prob_Event = (double)100000.f * o->Tree[1]; }
+      else if (ncry == 0) { *Index_Event = EV_EVAP(o); *Prob_Event = (double)100000.f * o->Tree[1]; }
       else {
-        *Index_Event = 4;
+        *Index_Event = EV_EVAP(o);
         int c1 = 0, c2 = 0, c3 = 0;
         if (o->NCov == 1) c1 = covNN[0];
         else if (o->NCov == 2) { c1 = covNN[0]; c2 = covNN[1]; }
         else if (o->NCov == 3) { c1 = covNN[0]; c2 = covNN[1]; c3 = covNN[2]; }
         double e = o->PtransE[IDXE(NSiC, N_Si + N_wall, N_C, N_B, c1 & 3, c2 & 3, c3 & 3)];
         if ((c1 | c2 | c3) > 3) o->q_oob++;
-        *Prob_Event = la ? la_PE(o, temperature, e) : e;
+        *Prob_Event = !la ? e : o->la_tree ? la_PE_k(o, temperature, NSiC, e) : la_PE(o, temperature, e);
       }
     }
   }
@@ -519,7 +538,8 @@ static void Get_Prob_Ini(Orc *o, int Occ, int NSiC, int Coor, const int32_t Site
   if (Occ == 0) {
     double PD[4] = {0, 0, 0, 0};
     if (Coor >= 1 && Coor <= 3)
-      for (int k = 1; k <= 3; k++) PD[k] = la ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)]) : o->PtransD[IDXD(k, Coor)];
+      for (int k = 1; k <= 3; k++) PD[k] = !la ? o->PtransD[IDXD(k, Coor)] : !o->la_tree ? la_PD(o, temperature, o->PtransD[IDXD(k, Coor)])
+                                           : k <= o->NCrystal ? la_PD_k(o, temperature, k, o->PtransD[IDXD(k, Coor)]) : 0.0;
     int draw = 0;
     if (Coor == 1) {
       int CoorNN = IBITS(LC(o, NextN[0]), ORC_PosCoor, ORC_LenCoor);
@@ -541,7 +561,7 @@ static void Get_Prob_Ini(Orc *o, int Occ, int NSiC, int Coor, const int32_t Site
       int32_t w = LC(o, NextN[i]);
       int CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
       if (CovInd == 0) {
-        int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        int SiOrC = IBITS(w, PSIC(o), LSIC(o));
         if (SiOrC == 1) N_Si++;
         if (SiOrC == 2) N_C++;
         if (SiOrC == 3) N_B++;
@@ -550,11 +570,11 @@ static void Get_Prob_Ini(Orc *o, int Occ, int NSiC, int Coor, const int32_t Site
     int n = N_Si + N_C + N_B + N_cov;
     if (n != Coor) orc_fatal(o, "%d %d %d %d %d Get Prob Error N_Si+N_C++N_B+N_cov.NE.Coor", Coor, N_Si, N_C, N_B, N_cov);
     if (n > 3) { *Index_Event = 0; *Prob_Event = 0.0; }
-    else if (n == 0) { *Index_Event = 4; *Prob_Event = (double)100000.f * o->Tree[1]; LOG(o, " %d Get Prob Isolated Atom\n", Coor); }
+    else if (n == 0) { *Index_Event = EV_EVAP(o); *Prob_Event = (double)100000.f * o->Tree[1]; LOG(o, " %d Get Prob Isolated Atom\n", Coor); }
     else {
-      *Index_Event = 4;
+      *Index_Event = EV_EVAP(o);
       double e = o->PtransE[IDXE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)];
-      *Prob_Event = la ? la_PE(o, temperature, e) : e;
+      *Prob_Event = !la ? e : o->la_tree ? la_PE_k(o, temperature, NSiC, e) : la_PE(o, temperature, e);
     }
   }
 }
@@ -572,7 +592,7 @@ static void Deposition(Orc *o, int *IndVoid, int IAtom) {
   cp3(Site, o->ListAdAtom[*IndVoid].xyz);
   int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor), CoorOld = Coor;
   MVBITS(1, ORC_LenOcc, &LC(o, Site), ORC_PosOcc);
-  MVBITS(IAtom, ORC_LenSiC, &LC(o, Site), ORC_PosSiC);
+  MVBITS(IAtom, LSIC(o), &LC(o, Site), PSIC(o));
   if (Coor == 1) {                                         /* :49-74 */
     cp3(SiteC, o->ListAdAtom[*IndVoid].nn[0]);
     int IndNN = LI(o, SiteC);
@@ -646,9 +666,9 @@ static void Deposition(Orc *o, int *IndVoid, int IAtom) {
           if (recipr((const int32_t (*)[3])NextNN, Site)) {
             CoorNN++;
             MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
-            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            int SiOrC = IBITS(*wN, PSIC(o), LSIC(o));
             Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
-            if (Index_Event == 0) { EraseMC(o, NextN[i]); AddBulk(o, NextN[i], (const int32_t (*)[3])NextNN); }
+            if (Index_Event == 0) { EraseMC(o, NextN[i]); AddBulk(o, NextN[i], (const int32_t (*)[3])NextNN); o->NumAdAtomOcc--; }   /* la/deposition.f:219 */
             else { set_rate(o, IndNN, Index_Event, Prob); orc_update_tree(o, IndNN, Prob); }
             if (CoorOld == 1 && i >= 1) Coor++;
           }
@@ -659,8 +679,8 @@ static void Deposition(Orc *o, int *IndVoid, int IAtom) {
   *IndVoid = LI(o, Site);
   if (Coor != CoorOld) MVBITS(Coor, ORC_LenCoor, &LC(o, Site), ORC_PosCoor);
   Get_Prob(o, 1, IAtom, 0, Coor, Site, (const int32_t (*)[3])NextN, &Index_Event, &Prob);
-  if (Index_Event == 0) { EraseMC(o, Site); AddBulk(o, Site, (const int32_t (*)[3])NextN); }
-  else { set_rate(o, *IndVoid, Index_Event, Prob); orc_update_tree(o, *IndVoid, Prob); }
+  if (Index_Event == 0) { EraseMC(o, Site); AddBulk(o, Site, (const int32_t (*)[3])NextN); o->NumAdAtomOcc--; }             /* la/deposition.f:246 */
+  else { set_rate(o, *IndVoid, Index_Event, Prob); orc_update_tree(o, *IndVoid, Prob); o->NumAdAtomOcc++; }                /* la/deposition.f:253 */
 }
 
 /* the "keep only the occupied reciprocal neighbour" compaction, Evaporation.f:95-122 and :229-258.
@@ -689,11 +709,12 @@ static void Evaporation(Orc *o, int *IndAtom) {
   int Index_Event = 0; double Prob = 0;
   int keepT = (strcmp(o->InitSt, "LA") == 0 || strcmp(o->InitSt, "ST") == 0);
   cp3(Site, o->ListAdAtom[*IndAtom].xyz);
-  int IAtom = IBITS(LC(o, Site), ORC_PosSiC, ORC_LenSiC);
+  int IAtom = IBITS(LC(o, Site), PSIC(o), LSIC(o));
+  o->NumAdAtomOcc--;                                       /* la/Evaporation.f:47 */
   if (IAtom >= 1 && IAtom <= 3) o->CountCrystal[IAtom - 1]--; else o->q_oob++;
   int Coor = IBITS(LC(o, Site), ORC_PosCoor, ORC_LenCoor);
   MVBITS(0, ORC_LenOcc, &LC(o, Site), ORC_PosOcc);
-  MVBITS(0, ORC_LenSiC, &LC(o, Site), ORC_PosSiC);
+  MVBITS(0, LSIC(o), &LC(o, Site), PSIC(o));
   cpnn(NextN, (const int32_t (*)[3])o->ListAdAtom[*IndAtom].nn);
   for (int i = 0; i < 4; i++) {
     int32_t *wN = &LC(o, NextN[i]);
@@ -747,17 +768,18 @@ static void Evaporation(Orc *o, int *IndAtom) {
           if (recipr((const int32_t (*)[3])NextNN, Site)) {
             CoorNN = 3;
             MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
-            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            int SiOrC = IBITS(*wN, PSIC(o), LSIC(o));
             Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
             EraseBulk(o, NextN[i]);
             AddMC(o, NextN[i], (const int32_t (*)[3])NextNN, Index_Event, Prob);
+            o->NumAdAtomOcc++;                             /* la/Evaporation.f:192 */
           }
         } else {                                           /* :191-209 */
           cpnn(NextNN, mc_nn(o, IndNN));
           if (recipr((const int32_t (*)[3])NextNN, Site)) {
             CoorNN--;
             MVBITS(CoorNN, ORC_LenCoor, wN, ORC_PosCoor);
-            int SiOrC = IBITS(*wN, ORC_PosSiC, ORC_LenSiC);
+            int SiOrC = IBITS(*wN, PSIC(o), LSIC(o));
             Get_Prob(o, 1, SiOrC, CovInd, CoorNN, NextN[i], (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
             set_rate(o, IndNN, Index_Event, Prob);
             orc_update_tree(o, IndNN, Prob);
@@ -792,7 +814,7 @@ static void rerate_occ_nn(Orc *o, const int32_t Site[3], const int32_t N[3], int
       if (!need_le3 && CoorN > 3) o->q_wl_des++;
       int32_t NextNN[4][3]; cpnn(NextNN, mc_nn(o, IndNN));
       if (recipr((const int32_t (*)[3])NextNN, Site)) {
-        int SiOrC = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        int SiOrC = IBITS(w, PSIC(o), LSIC(o));
         Get_Prob(o, 1, SiOrC, CovIndN, CoorN, N, (const int32_t (*)[3])NextNN, &Index_Event, &Prob);
         set_rate(o, IndNN, Index_Event, Prob);
         orc_update_tree(o, IndNN, Prob);
@@ -834,6 +856,7 @@ static void Desorption(Orc *o, int IndAtom) {
   orc_update_tree(o, IndAtom, Prob);
 }
 
+void orc_set_variant(Orc *o, int la_tree) { o->la_tree = la_tree != 0; }
 /* ------------------------------------------------------------------ create */
 Orc *orc_create(int lenx, int leny, int lenz, int nummcmax) {
   Orc *o = (Orc *)calloc(1, sizeof(Orc));
@@ -1035,23 +1058,32 @@ int orc_read_start(Orc *o, const char *path) {
     if (o->NCov > 0) orc_fatal(o, "ERR NOT IMPLEMENTED: NCov=0 for LA");
     NEXT(); strncpy(o->cadfilename, line, sizeof o->cadfilename - 1); trim_trailing(o->cadfilename);
     NEXT(); strncpy(o->tempfilename, line, sizeof o->tempfilename - 1); trim_trailing(o->tempfilename);
+    if (o->la_tree) {                                        /* la/main.f:420-424: one value per crystal species */
+      double *dst[4] = {o->Tm_k, o->P0_k, o->sigma_k, o->Tflex_k};
+      for (int q = 0; q < 4; q++) { NEXT(); char *p = line; for (int k = 0; k < o->NCrystal; k++) dst[q][k] = fortran_strtod(p, &p); }
+      o->Tm = o->Tm_k[0]; o->P0 = o->P0_k[0]; o->sigma = o->sigma_k[0]; o->Tflex = o->Tflex_k[0];
+      LOG(o, " Melting temperature in Kelvin: "); for (int k = 0; k < o->NCrystal; k++) LOG(o, " %.17g", o->Tm_k[k]); LOG(o, "\n");
+    } else {
     NEXT(); o->Tm = fortran_strtod(line, NULL);
     NEXT(); o->P0 = fortran_strtod(line, NULL);
     NEXT(); o->sigma = fortran_strtod(line, NULL);
     NEXT(); o->Tflex = fortran_strtod(line, NULL);
     LOG(o, " Melting temperature in Kelvin:  %.17g\n", o->Tm);
+    }
     NEXT(); o->LenVac = fortran_strtod(line, NULL);
     LOG(o, " Top air thickness (ang):  %.17g\n", o->LenVac);
     NEXT(); o->LenNuc = fortran_strtod(line, NULL);
     LOG(o, " Nucleus thickness (ang):  %.17g\n", o->LenNuc);
     NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->Homogeneous, tok, 2);
     LOG(o, " Model homogeneous nucleation: %s\n", o->Homogeneous);
+    if (o->la_tree && !strcmp(o->Homogeneous, "D")) orc_fatal(o, "oracle: Homogeneous 'D' (SetSiGeSF stacking-fault seed) not restated");
   } else { NEXT(); char *p = line; o->Len1 = (int)strtol(p, &p, 10); o->Len2 = (int)strtol(p, &p, 10); o->Len3 = (int)strtol(p, &p, 10); }
   /* SiGe alloy fraction, main.f:142-149; trap 5 of SURVEY 8(c) */
   if ((o->NCrystal == 2 && o->ListCrystal[0] == 14 && o->ListCrystal[1] == 32) ||
       (o->NCrystal == 3 && o->ListCrystal[0] == 14 && o->ListCrystal[1] == 32 && o->ListCrystal[2] == 5)) {
     NEXT(); o->alloyfraction = fortran_strtod(line, NULL);
     LOG(o, " Ge fraction in substrate:  %.17g\n", o->alloyfraction);
+    if (o->la_tree) { NEXT(); o->LenSiGe = fortran_strtod(line, NULL); LOG(o, " SiGe thickness (ang):  %.17g\n", o->LenSiGe); }   /* la/main.f:441-442 */
   } else o->alloyfraction = 0.0;
   NEXT(); o->PtransZig = fortran_strtod(line, NULL);
   NEXT(); o->sf = fortran_strtod(line, NULL);
@@ -1080,7 +1112,8 @@ int orc_read_start(Orc *o, const char *path) {
   NEXT(); tok_str(line, tok, sizeof tok); strncpy(o->SaveCoo, tok, 2);
   if (!strcmp(o->SaveCoo, "T")) {
     NEXT(); strncpy(o->coofilename, line, sizeof o->coofilename - 1); trim_trailing(o->coofilename);
-    LOG(o, " ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", o->coofilename);
+    if (o->la_tree && !strcmp(o->coofilename, "None")) LOG(o, " Phases passed through sockets...\n");
+    else LOG(o, " ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", o->coofilename);
   } else {
     if (!strcmp(o->InitSt, "LA")) orc_fatal(o, "ERR: SaveCoo flag must be \"T\" for LA simulations!");
     LOG(o, " SaveCoo flag is not \"T\": Coor file not stored\n");
@@ -1146,7 +1179,7 @@ static void set_flat(Orc *o, int Len, int walls, int two_species) {
     if (is_cubic_site(x, y, z, &kind)) {
       int32_t *w = &o->LattCoo[CI(o, x, y, z)];
       int sp0 = alloy ? alloy_species(o) : ((kind && two_species) ? 2 : 1);
-      *w |= 1 << (sp0 == 2 ? ORC_PosC : ORC_PosSi);
+      *w |= 1 << (sp0 == 2 ? PC_(o) : PSI(o));
       *w |= 1 << ORC_PosOcc;
       MVBITS(4, ORC_LenCoor, w, ORC_PosCoor);
       Site[0] = x; Site[1] = y; Site[2] = z;
@@ -1157,13 +1190,13 @@ static void set_flat(Orc *o, int Len, int walls, int two_species) {
     if (is_cubic_site(x, y, z, &kind)) {
       int32_t *w = &o->LattCoo[CI(o, x, y, z)];
       int sp = alloy ? alloy_species(o) : ((kind && two_species) ? 2 : 1);
-      *w |= 1 << (sp == 2 ? ORC_PosC : ORC_PosSi);
+      *w |= 1 << (sp == 2 ? PC_(o) : PSI(o));
       *w |= 1 << ORC_PosOcc;
       MVBITS(2, ORC_LenCoor, w, ORC_PosCoor);
       Site[0] = x; Site[1] = y; Site[2] = z;
       dia_nn(o, x, y, z, kind, NextN);
       Prob = o->PtransE[IDXE(sp, 2, 0, 0, 0, 0, 0)];
-      AddMC(o, Site, (const int32_t (*)[3])NextN, 4, Prob);
+      AddMC(o, Site, (const int32_t (*)[3])NextN, EV_EVAP(o), Prob);
     }
   for (int z = Len; z <= Len; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++)
     if (is_cubic_site(x, y, z, &kind)) {
@@ -1238,16 +1271,17 @@ static void pass_probability(Orc *o, int z0, int z1, int y0, int y1, int x0, int
       }
     } else {
       if (Coor <= 3) {
-        int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        int IAt = IBITS(w, PSIC(o), LSIC(o));
         Get_Prob_Ini(o, 1, IAt, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
         AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+        o->NumAdAtomOcc++;                                   /* la/SetCAD.f:544,595 */
       } else AddBulk(o, Site, (const int32_t (*)[3])NextN);
     }
   }
 }
 static inline void occupy(Orc *o, int x, int y, int z, int kind, int two_species) {
   int32_t *w = &o->LattCoo[CI(o, x, y, z)];
-  *w |= 1 << ((kind && two_species) ? ORC_PosC : ORC_PosSi);
+  *w |= 1 << ((kind && two_species) ? PC_(o) : PSI(o));
   *w |= 1 << ORC_PosOcc;
 }
 
@@ -1389,7 +1423,7 @@ static void set_T(Orc *o) {
 static void set_cad(Orc *o) {
   int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ, la = !strcmp(o->InitSt, "LA");
   size_t n = (size_t)LX * LY; double *buf = (double *)malloc(n * sizeof(double));
-  double LenSiGe = 0.0;     /* un-initialised local in the reference (SetCAD.f:38); irrelevant while alloyfraction==0 */
+  double LenSiGe = o->la_tree ? o->LenSiGe : 0.0;     /* src/: un-initialised local (SetCAD.f:38), irrelevant while alloyfraction==0; la/: read from start.dat */
   if (o->alloyfraction > 0) LOG(o, " Setting up a SiGe layer with fraction = %.17g\n", o->alloyfraction);
   else LOG(o, " Setting up Silicon\n");
   if (o->RunType[0] == 'C') {
@@ -1422,10 +1456,17 @@ static void set_cad(Orc *o) {
         else if (Id == 1 && is_cubic_site(x, y, z, &kind)) {
           int fill = 0;
           if (la) {
+            /* la/SetCAD.f:140,163,190 count the solid sites below the air gap before the nucleus is carved out.  NOTE: only
+             * the socket branch of la/SetCAD.f (:108-255) does this; its file branch (:257-336) leaves NumOcc0 = 0, which
+             * stops the run after the first event -- the oracle counts in both (the la/ fork is driven through sockets) */
+            if (o->la_tree && z <= (LZ - (int)(o->LenVac / o->sf))) o->NumOcc0++;
             if (!strcmp(o->Homogeneous, "T")) fill = (z <= (LZ - (int)((o->LenVac + o->LenNuc) / o->sf)));
             else if (!strcmp(o->Homogeneous, "F")) {
               int x0 = LX / 2, y0 = LY / 2, z0 = LZ - (int)(o->LenVac / o->sf);
               fill = ((x - x0) * (x - x0) + (y - y0) * (y - y0) + (z - z0) * (z - z0)) > (int)((o->LenNuc / o->sf) * (o->LenNuc / o->sf));
+            } else if (o->la_tree && !strcmp(o->Homogeneous, "R")) {      /* la/SetCAD.f:186-207: semi-cylindrical nucleus along y */
+              int x0 = LX / 2, z0 = LZ - (int)(o->LenVac / o->sf);
+              fill = ((x - x0) * (x - x0) + (z - z0) * (z - z0)) > (int)((o->LenNuc / o->sf) * (o->LenNuc / o->sf));
             } else LOG(o, " ERROR: Homogeneous needs to be either T or F\n");
           } else fill = 1;
           if (fill) {
@@ -1437,13 +1478,22 @@ static void set_cad(Orc *o) {
               static uint64_t lcg = 88172645463325252ull; lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
               rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
             }
-            *w |= 1 << (rr >= o->alloyfraction ? ORC_PosSi : ORC_PosC);
+            *w |= 1 << (rr >= o->alloyfraction ? PSI(o) : PC_(o));
+            if (o->la_tree) o->CountCrystal[rr >= o->alloyfraction ? 0 : 1]++;                 /* la/SetCAD.f:150-155 */
           }
         }
       }
     }
     fclose(f);
     LOG(o, " Done reading input geometry file\n");
+    if (o->la_tree) {                                          /* la/SetCAD.f:343-351 */
+      int sum = o->CountCrystal[0] + o->CountCrystal[1] + o->CountCrystal[2];
+      for (int k = 0; k < o->NCrystal; k++) {
+        if (o->ListCrystal[k] == 14) o->InitCountCrystal[k] = o->CountCrystal[k] + (int)((o->NumOcc0 - sum) * (1 - o->alloyfraction));
+        else if (o->ListCrystal[k] == 32) o->InitCountCrystal[k] = o->CountCrystal[k] + (int)((o->NumOcc0 - sum) * o->alloyfraction);
+      }
+      for (int k = 0; k < 3; k++) o->CountLiquid[k] = o->InitCountCrystal[k] - o->CountCrystal[k];
+    }
     pass_coordination(o, 0, LZ - 1, 0, LY - 1, 0, LX - 1, 1);
   }
   free(buf);
@@ -1455,6 +1505,7 @@ int orc_setup(Orc *o) {
   o->jb_set = 1;
   if (setjmp(o->jb)) { o->jb_set = 0; return -2; }
   const char *s = o->InitSt;
+  if (o->la_tree && strcmp(s, "LA") && strcmp(s, "IN")) orc_fatal(o, "oracle: the la/ tree variant restates InitSt LA and IN only");
   if (!strcmp(s, "F")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 0, 1); }
   else if (!strcmp(s, "FS")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 0); }
   else if (!strcmp(s, "SG")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 2); }
@@ -1468,6 +1519,20 @@ int orc_setup(Orc *o) {
   else if (!strcmp(s, "IN")) set_cad(o);
   else if (!strcmp(s, "LA")) { o->tmax = 0; set_T(o); set_cad(o); LOG(o, " Max temperature is:  %d K\n", o->tmax); }
   else orc_fatal(o, "initialization not_implemented in oracle: %s", s);
+  if (o->la_tree) {                                            /* la/main.f:592-611,628 */
+    o->NumOcc1 = o->NumAtoms + o->NumAdAtomOcc;
+    for (int k = 1; k <= o->NCrystal; k++) {
+      if (k == 1) o->InitCountCrystal[0] = o->CountCrystal[0] + (int)((o->NumOcc0 - o->NumOcc1) * (1 - o->alloyfraction));
+      else if (k == 2) o->InitCountCrystal[1] = o->CountCrystal[1] + (int)((o->NumOcc0 - o->NumOcc1) * o->alloyfraction);
+    }
+    LOG(o, " \n Initial number of occupied sites (before nucleation):  %d\n", o->NumOcc0);
+    LOG(o, " Initial CountCrystal (before nucleation):  %d %d %d\n", o->InitCountCrystal[0], o->InitCountCrystal[1], o->InitCountCrystal[2]);
+    LOG(o, " Initial number of occupied sites (after nucleation):  %d\n", o->NumOcc1);
+    LOG(o, " Initial CountCrystal (after nucleation):  %d %d %d\n", o->CountCrystal[0], o->CountCrystal[1], o->CountCrystal[2]);
+    LOG(o, " Initial number of liquid sites (after nucleation):  %d\n", o->NumOcc0 - o->NumOcc1);
+    LOG(o, " Initial CountLiquid (after nucleation):  %d %d %d\n \n", o->CountLiquid[0], o->CountLiquid[1], o->CountLiquid[2]);
+    LOG(o, " Atoms,Voids,AdAtoms,AdAtomsOcc %d %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom, o->NumAdAtomOcc);
+  } else
   LOG(o, " Atoms,Voids,AdAtoms %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
   for (int i = 0; i < 3; i++) o->CountCrystalOld[i] = o->CountCrystal[i];
   orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
@@ -1480,7 +1545,12 @@ int orc_setup(Orc *o) {
 static int iterate_inner(Orc *o) {
   int Ind; double Patom;
   o->IterOut = o->Iter;
-  if (o->NumAdAtom <= 20) { LOG(o, " few MC particles: stop MC %lld %d\n", (long long)o->Iter, o->NumAdAtom); o->done = 2; return 1; }
+  if (o->la_tree) for (int k = 0; k < 3; k++) o->CountLiquid[k] = o->InitCountCrystal[k] - o->CountCrystal[k];   /* la/main.f:636 */
+  if (o->NumAdAtom <= 20) {
+    if (o->la_tree) LOG(o, " few MC particles: stop MC %lld %d %d\n", (long long)o->Iter, o->NumAdAtom, o->NumAdAtomOcc);
+    else LOG(o, " few MC particles: stop MC %lld %d\n", (long long)o->Iter, o->NumAdAtom);
+    o->done = 2; return 1;
+  }
   pick_tree_event(o, &Ind, &Patom);
   o->Time = o->Time + 1.0 / o->Tree[1];
   int Itrans = o->ListAdAtom[Ind].ev;
@@ -1491,14 +1561,16 @@ static int iterate_inner(Orc *o) {
       orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
       const int32_t *S = o->ListAdAtom[Ind].xyz;
       LOG(o, " Iter, Time, Site %lld %.17g %d %d %d\n", (long long)o->Iter, o->Time, S[0], S[1], S[2]);
-      LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
+      if (o->la_tree) LOG(o, " NatNvoidNadNadocc %d %d %d %d\n Number of occupied sites:  %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom, o->NumAdAtomOcc, o->NumAtoms + o->NumAdAtomOcc);
+      else LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
     }
   } else if (!strcmp(o->ExitStrategy, "Time")) {
     if (o->Time >= ((double)(o->framecounter + 1) * o->OutTime)) {
       orc_write_frame(o, o->Time, o->IterOut, o->framecounter + 1);
       const int32_t *S = o->ListAdAtom[Ind].xyz;
       LOG(o, " Iter, Time, Site %lld %.17g %d %d %d\n", (long long)o->Iter, o->Time, S[0], S[1], S[2]);
-      LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
+      if (o->la_tree) LOG(o, " NatNvoidNadNadocc %d %d %d %d\n Number of occupied sites:  %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom, o->NumAdAtomOcc, o->NumAtoms + o->NumAdAtomOcc);
+      else LOG(o, " NatNvoidNad %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom);
       o->framecounter++;
     }
   }
@@ -1509,13 +1581,16 @@ static int iterate_inner(Orc *o) {
     t->iter = o->Iter; t->ind = Ind; cp3(t->site, o->ListAdAtom[Ind].xyz); t->itrans = Itrans; t->pad = 0; t->tree1 = o->Tree[1]; t->time = o->Time;
   }
   if (Itrans >= 0 && Itrans < 8) o->n_events[Itrans]++; else o->n_events[7]++;
-  if (Itrans <= 3) {
+  if (Itrans < EV_EVAP(o)) {
+    /* la/main.f:675-681: SiGe melt pool -- when species Itrans has been fully re-solidified, deposit the other one */
+    if (o->la_tree && !strcmp(o->InitSt, "LA") && o->NCrystal == 2 && o->ListCrystal[0] == 14 && o->ListCrystal[1] == 32 && Itrans >= 1)
+      if (o->CountCrystal[Itrans - 1] >= o->InitCountCrystal[Itrans - 1]) { Itrans = Itrans % 2 + 1; if (t) t->itrans = Itrans; }
     Deposition(o, &Ind, Itrans);
     if (Itrans >= 1) o->CountCrystal[Itrans - 1]++;
-  } else if (Itrans == 4) Evaporation(o, &Ind);
-  else if (Itrans == 5) Desorption(o, Ind);
+  } else if (Itrans == EV_EVAP(o)) Evaporation(o, &Ind);
+  else if (Itrans == EV_DES(o)) Desorption(o, Ind);
   else {
-    int k = Itrans - 5; if (k > 3) { o->q_oob++; k = 3; }
+    int k = Itrans - EV_DES(o); if (k > 3) { o->q_oob++; k = 3; }
     Absorption(o, Ind, o->ListCov[k - 1]);
     o->CountCov[k - 1]++;
   }
@@ -1523,6 +1598,13 @@ static int iterate_inner(Orc *o) {
   o->Iter++;
   if (!strcmp(o->ExitStrategy, "Iter")) { if (o->Iter > o->MaxIter) { o->done = 1; return 1; } }
   else if (!strcmp(o->ExitStrategy, "Time")) { if (o->Time > o->MaxTime) { o->done = 1; return 1; } }
+  if (o->la_tree) {                                            /* la/main.f:714-723: the melt pool has re-solidified */
+    o->NumOcc = o->NumAtoms + o->NumAdAtomOcc;
+    if (o->NumOcc > o->NumOcc0) {
+      LOG(o, " \n Current number of occupied sites:  %d\n    > initial number of occupied sites:  %d\n ... STOPPING MulSKIPS ...\n \n", o->NumOcc, o->NumOcc0);
+      o->done = 1; return 1;
+    }
+  }
   return 0;
 }
 int orc_iterate(Orc *o) {
@@ -1609,6 +1691,21 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
   double sf = o->sf;
   char e1[32], e2[32], e3[32], et[32], base[64], path[2048];
   int sic = (o->NCrystal == 2 && (o->ListCrystal[0] == 6 || o->ListCrystal[1] == 6 || o->ListCrystal[2] == 6));
+  if (o->la_tree) {                                       /* la/inpout/WriteMolMolSource.f:42-67 */
+    int s = 0, so = 0, sl = 0; for (int i = 0; i < 3; i++) { s += o->CountCrystal[i]; so += o->CountCrystalOld[i]; sl += o->CountLiquid[i]; }
+    if (o->NCrystal > 1) LOG(o, " SUM(CountCrystal) %d\n", s);
+    LOG(o, " CountCrystal %d %d %d\n xCrystal %.9g %.9g %.9g\n", o->CountCrystal[0], o->CountCrystal[1], o->CountCrystal[2],
+        (float)o->CountCrystal[0] / s, (float)o->CountCrystal[1] / s, (float)o->CountCrystal[2] / s);
+    LOG(o, " CountLiquid %d %d %d\n xLiquid %.9g %.9g %.9g\n", o->CountLiquid[0], o->CountLiquid[1], o->CountLiquid[2],
+        (float)o->CountLiquid[0] / sl, (float)o->CountLiquid[1] / sl, (float)o->CountLiquid[2] / sl);
+    if (Iter > 1) {
+      float d[3]; for (int i = 0; i < 3; i++) d[i] = (float)(o->CountCrystal[i] - o->CountCrystalOld[i]);
+      LOG(o, " diffCrystal %.9g %.9g %.9g\n", d[0], d[1], d[2]);
+      LOG(o, " Atom fraction from last check: %.17g %.17g %.17g\n", (double)d[0] / (s - so), (double)d[1] / (s - so), (double)d[2] / (s - so));
+      for (int i = 0; i < 3; i++) o->CountCrystalOld[i] = o->CountCrystal[i];
+    }
+    if (o->NCov != 0) LOG(o, " CountCov %d %d %d\n", o->CountCov[0], o->CountCov[1], o->CountCov[2]);
+  } else
   if (Iter != 0) {                                        /* WriteMolMolSource.f:42-56 */
     int s = 0, so = 0; for (int i = 0; i < 3; i++) { s += o->CountCrystal[i]; so += o->CountCrystalOld[i]; }
     LOG(o, " SUM(CountCrystal) %d\n CountCrystal %d %d %d\n CountCrystalOld %d %d %d\n", s, o->CountCrystal[0], o->CountCrystal[1], o->CountCrystal[2], o->CountCrystalOld[0], o->CountCrystalOld[1], o->CountCrystalOld[2]);
@@ -1657,7 +1754,7 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
     for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       int32_t w = o->LattCoo[CI(o, x, y, z)];
       if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4 && noepi_bulk(x, y, z)) {
-        int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC);
+        int IAt = IBITS(w, PSIC(o), LSIC(o));
         if (IAt == 1) atom_line(fd, "Ge ", sf, x, y, z, "  ");
         if (IAt == 2) atom_line(fd, "B ", sf, x, y, z, "  ");
         if (IAt == 3) atom_line(fd, "Cl ", sf, x, y, z, "  ");
@@ -1670,7 +1767,7 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
     for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       int32_t w = o->LattCoo[CI(o, x, y, z)];
       if (w == 0) continue;
-      int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC), Coo = IBITS(w, ORC_PosCoor, ORC_LenCoor), CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
+      int IAt = IBITS(w, PSIC(o), LSIC(o)), Coo = IBITS(w, ORC_PosCoor, ORC_LenCoor), CovInd = IBITS(w, ORC_PosIndex, ORC_LenIndex);
       if (CovInd == 1) atom_line(fx, "H ", sf, x, y, z, "  ");
       if (CovInd == 17) atom_line(fx, "Cl ", sf, x, y, z, "  ");
       if (IAt == 1 && Coo <= 3) atom_line(fx, "Si ", sf, x, y, z, "  ");
@@ -1690,12 +1787,12 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
       int x = o->ListVoid[i].xyz[0], y = o->ListVoid[i].xyz[1], z = o->ListVoid[i].xyz[2];
       if (o->NCov == 0 && o->NCrystal == 2 && o->ListCrystal[1] == 6) {
         int IAt = 0;
-        for (int j = 0; j < 4; j++) IAt += IBITS(LC(o, o->ListVoid[i].nn[j]), ORC_PosSiC, ORC_LenSiC);
-        if (IAt == 4) atom_line(fv, "Mg ", sf, x, y, z, " # CV (C vacancy)");
-        else if (IAt == 8) atom_line(fv, "He ", sf, x, y, z, " # SV (Si vacancy)");
+        for (int j = 0; j < 4; j++) IAt += IBITS(LC(o, o->ListVoid[i].nn[j]), PSIC(o), LSIC(o));
+        if (IAt == 4) atom_line(fv, "Mg ", sf, x, y, z, o->la_tree ? " # SV (Si vacancy)" : " # CV (C vacancy)");       /* la/WriteMolMolXYZFile.f:66-67 swaps the two comments */
+        else if (IAt == 8) atom_line(fv, "He ", sf, x, y, z, o->la_tree ? " # CV (C vacancy)" : " # SV (Si vacancy)");
         else if (IAt == 7) atom_line(fv, "Ne ", sf, x, y, z, " # SAV (Si antisite vac)");
         else if (IAt == 5) atom_line(fv, "Be ", sf, x, y, z, " # CAV (C antisite vac)");
-        else if (IAt == 6) atom_line(fv, "Ar ", sf, x, y, z, " # XV (near 2C and 2Si)");
+        else if (IAt == 6) atom_line(fv, "Ar ", sf, x, y, z, o->la_tree ? " # surrounded by 2C-2Si" : " # XV (near 2C and 2Si)");
         else orc_fatal(o, "ERROR: Weird Defect type was formed...ABORTING");
       } else atom_line(fv, "O ", sf, x, y, z, "  ");
     }
@@ -1703,19 +1800,19 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
   if (sic) {                                              /* :267-398, including the restore quirk at :386 */
     int NumIsWrong = 0, NumAtWrong = 0, cap = 1024;
     int32_t (*buf)[4] = (int32_t (*)[4])malloc((size_t)cap * sizeof *buf);
-#define NCORR(w, x, y, z, out) do { int ia_ = IBITS(w, ORC_PosSiC, ORC_LenSiC); const int32_t (*nn_)[3] = bulk_nn(o, o->LattInd[CI(o, x, y, z)]); out = 0; \
-      if (ia_ == 1) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), ORC_PosC, 1); \
-      else if (ia_ == 2) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), ORC_PosSi, 1); } while (0)
+#define NCORR(w, x, y, z, out) do { int ia_ = IBITS(w, PSIC(o), LSIC(o)); const int32_t (*nn_)[3] = bulk_nn(o, o->LattInd[CI(o, x, y, z)]); out = 0; \
+      if (ia_ == 1) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), PC_(o), 1); \
+      else if (ia_ == 2) for (int i_ = 0; i_ < 4; i_++) out += IBITS(LC(o, nn_[i_]), PSI(o), 1); } while (0)
     for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       int32_t *w = &o->LattCoo[CI(o, x, y, z)];
       if (*w == 0 || IBITS(*w, ORC_PosIndex, ORC_LenIndex) == 113) continue;
       if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(*w, ORC_PosCoor, ORC_LenCoor) == 4) {
-        int IAt = IBITS(*w, ORC_PosSiC, ORC_LenSiC), n; NCORR(*w, x, y, z, n);
+        int IAt = IBITS(*w, PSIC(o), LSIC(o)), n; NCORR(*w, x, y, z, n);
         if (n == 0) {
           if (NumIsWrong == cap) { cap *= 2; buf = (int32_t (*)[4])realloc(buf, (size_t)cap * sizeof *buf); }
           buf[NumIsWrong][0] = x; buf[NumIsWrong][1] = y; buf[NumIsWrong][2] = z;
-          if (IAt == 1) { *w &= ~(1 << ORC_PosSi); *w |= 1 << ORC_PosC; buf[NumIsWrong][3] = 1; }
-          else { *w &= ~(1 << ORC_PosC); *w |= 1 << ORC_PosSi; buf[NumIsWrong][3] = 2; }
+          if (IAt == 1) { *w &= ~(1 << PSI(o)); *w |= 1 << PC_(o); buf[NumIsWrong][3] = 1; }
+          else { *w &= ~(1 << PC_(o)); *w |= 1 << PSI(o); buf[NumIsWrong][3] = 2; }
           NumIsWrong++;
         }
       }
@@ -1734,15 +1831,15 @@ int orc_write_frame(Orc *o, double Time, int64_t Iter, int64_t Iout) {
         if (w == 0) continue;
         if (IBITS(w, ORC_PosOcc, ORC_LenOcc) == 1 && IBITS(w, ORC_PosCoor, ORC_LenCoor) == 4) {
           int n; NCORR(w, x, y, z, n);
-          if (n == 3) { int IAt = IBITS(w, ORC_PosSiC, ORC_LenSiC); if (IAt == 1) atom_line(fw, "Si ", sf, x, y, z, "  "); if (IAt == 2) atom_line(fw, "C ", sf, x, y, z, "  "); }
+          if (n == 3) { int IAt = IBITS(w, PSIC(o), LSIC(o)); if (IAt == 1) atom_line(fw, "Si ", sf, x, y, z, "  "); if (IAt == 2) atom_line(fw, "C ", sf, x, y, z, "  "); }
         }
       }
     }
     for (int i = 0; i < NumIsWrong; i++) {
       int32_t *w = &o->LattCoo[CI(o, buf[i][0], buf[i][1], buf[i][2])];
       int ty = buf[NumIsWrong - 1][3];                    /* :386 uses the LAST entry's type for all */
-      if (ty == 1) { *w &= ~(1 << ORC_PosC); *w |= 1 << ORC_PosSi; }
-      else { *w &= ~(1 << ORC_PosSi); *w |= 1 << ORC_PosC; }
+      if (ty == 1) { *w &= ~(1 << PC_(o)); *w |= 1 << PSI(o); }
+      else { *w &= ~(1 << PSI(o)); *w |= 1 << PC_(o); }
     }
     free(buf);
 #undef NCORR
@@ -1805,6 +1902,13 @@ void orc_get_field(Orc *o, int32_t info[4], int32_t *reftemp, double *refPE, dou
   if (refPAbs) memcpy(refPAbs, o->refPAbs, (size_t)o->ntemp * 12 * sizeof(double));
   if (refPDes) memcpy(refPDes, o->refPDes, (size_t)o->ntemp * 12 * sizeof(double));
 }
+/* LaserAnnealing-fork state: ints {la_tree, NumAdAtomOcc, NumOcc0, NumOcc1, InitCountCrystal[3], CountLiquid[3]}, doubles {Tm[3], P0[3], sigma[3], Tflex[3]} */
+void orc_get_fork(Orc *o, int32_t iv[10], double dv[12]) {
+  iv[0] = o->la_tree; iv[1] = o->NumAdAtomOcc; iv[2] = o->NumOcc0; iv[3] = o->NumOcc1;
+  for (int k = 0; k < 3; k++) { iv[4 + k] = o->InitCountCrystal[k]; iv[7 + k] = o->CountLiquid[k]; dv[k] = o->Tm_k[k]; dv[3 + k] = o->P0_k[k]; dv[6 + k] = o->sigma_k[k]; dv[9 + k] = o->Tflex_k[k]; }
+}
+/* test hook: lower the stop threshold of la/main.f:714-723 so that the rule fires while the melt is still rich */
+void orc_set_numocc0(Orc *o, int v) { o->NumOcc0 = v; }
 void orc_get_species(Orc *o, int32_t out[8]) {
   out[0] = o->NCrystal; out[1] = o->NCov; for (int i = 0; i < 3; i++) { out[2 + i] = o->ListCrystal[i]; out[5 + i] = o->ListCov[i]; }
 }

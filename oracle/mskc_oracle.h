@@ -54,6 +54,12 @@ typedef struct Orc {
   int Len1, Len2, Len3, Len4;
   double sf, alloyfraction, Tm, P0, sigma, Tflex, LenVac, LenNuc;
   int tmax;
+  /* LaserAnnealing fork "la/" (mulskips-source-LaserAnnealing): species at bits 28-29, event codes 1-2 / 3 / 4 / 4+k,
+   * per-species LA law with the liquid-fraction coupling, occupied-ad-atom counter and the NumOcc0 stop rule
+   * (la/modules/defsystem.f:36-37,46,82-83,99-100; la/main.f:634-726; la/mcevent/Get_Prob.f:142-152) */
+  int la_tree;
+  double Tm_k[3], P0_k[3], sigma_k[3], Tflex_k[3], LenSiGe;
+  int Len5, NumAdAtomOcc, NumOcc, NumOcc0, NumOcc1, InitCountCrystal[3], CountLiquid[3];
   /* InitSt 'ST' (src/main.f:109-115, src/modules/defsystem.f:71-81): trench geometry + tabulated rates */
   double angle, Ttop, Tbottom;
   int fixedT, ntemp, nprob, reftempvalues[300];
@@ -84,6 +90,8 @@ typedef struct Orc {
 } Orc;
 
 Orc *orc_create(int lenx, int leny, int lenz, int nummcmax);
+/* 1: follow the LaserAnnealing fork (la/) instead of mulskips-source (src/); call before orc_read_start */
+void orc_set_variant(Orc *o, int la_tree);
 void orc_destroy(Orc *o);
 /* parse start.dat (src/main.f:83-219 incl. SetProbability); returns 0 ok */
 int orc_read_start(Orc *o, const char *path);

@@ -13,7 +13,7 @@
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 int main(int argc, char **argv) {
-  int bx = 480, by = 480, bz = 480, nmc = 0, faithful = 0, files = 1, quiet = 0; long long maxiter = -1;
+  int bx = 480, by = 480, bz = 480, nmc = 0, faithful = 0, files = 1, quiet = 0, la_tree = 0; long long maxiter = -1;
   const char *start = "start.dat";
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--box") && i + 3 < argc) { bx = atoi(argv[i + 1]); by = atoi(argv[i + 2]); bz = atoi(argv[i + 3]); i += 3; }
@@ -21,12 +21,14 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--faithful-cost")) faithful = 1;
     else if (!strcmp(argv[i], "--no-files")) files = 0;
     else if (!strcmp(argv[i], "--quiet")) quiet = 1;
+    else if (!strcmp(argv[i], "--la-tree")) la_tree = 1;
     else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
     else if (!strcmp(argv[i], "--maxiter") && i + 1 < argc) maxiter = atoll(argv[++i]);
-    else { fprintf(stderr, "usage: %s [--box X Y Z] [--nummcmax N] [--faithful-cost] [--no-files] [--quiet] [--start f] [--maxiter n]\n", argv[0]); return 2; }
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--nummcmax N] [--faithful-cost] [--no-files] [--quiet] [--la-tree] [--start f] [--maxiter n]\n", argv[0]); return 2; }
   }
   Orc *o = orc_create(bx, by, bz, nmc);
   if (!o) { fprintf(stderr, "allocation failed\n"); return 2; }
+  orc_set_variant(o, la_tree);        /* follow mulskips-source-LaserAnnealing instead of mulskips-source */
   o->log = quiet ? NULL : stdout; o->write_files = files; o->faithful_cost = faithful;
   if (orc_read_start(o, start)) { fprintf(stderr, "start.dat: %s\n", o->errmsg); return 3; }
   if (maxiter > 0 && o->MaxIter > maxiter) o->MaxIter = maxiter;

@@ -159,3 +159,45 @@ def make_st_case(dirpath, lens=(20, 45, 90), angle=54.7, ttop=1080.0, tbottom=92
     with open(dst, "w") as fh:
         fh.write(start)
     return dst
+
+
+def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sige=True, tbase=1480, homogeneous="F", fraction=0.3, lensige=25.0):
+    """A laser-annealing case for the LaserAnnealing fork (mulskips-source-LaserAnnealing/main.f:380-520 grammar): one
+    Tm / P0 / sigma / Tflex value per crystal species, Si(1-x)Ge(x) with the Ge-fraction and SiGe-thickness lines, the
+    18-line two-species evaporation table (energies per bond: Si 0.96 eV, Ge 0.70 eV) and 6 deposition lines.  Geometry
+    and temperature files in the formats of initial/SetCAD.f / initial/SetT.f (what the socket arrays carry)."""
+    import numpy as np
+    lx, ly, lz = box
+    geo, tmp = os.path.join(dirpath, "LattGeo.dat"), os.path.join(dirpath, "TempStat.dat")
+    z0 = lz - int(18.2 / 0.4525)                      # top of the sample: air (0) above, as the FEM side sends it
+    with open(geo, "w") as f:
+        for z in range(lz):
+            f.write(" ".join(["1" if z <= z0 else "0"] * (lx * ly)) + "\n")
+    rng = np.random.default_rng(11)
+    with open(tmp, "w") as f:
+        for z in range(lz):
+            f.write(" ".join(str(v) for v in (tbase + rng.integers(0, 7, lx * ly))) + "\n")
+    ncry = 2 if sige else 1
+    L = [f"{ncry} 0 ! NCrystal NCov", "14 32 ! crystal species" if sige else "14 ! crystal species", "LA ! InitSt", geo, tmp,
+         ("1688 1210" if sige else "1688") + " ! Tm", ("1.33e17 2.596e16" if sige else "1.33e17") + " ! P0",
+         ("280 210" if sige else "280") + " ! sigma", ("1080 900" if sige else "1080") + " ! Tflex",
+         "18.2 ! LenVac", f"{lennuc} ! LenNuc", f"{homogeneous} ! Homogeneous"]
+    if sige:
+        L += [f"{fraction} ! Ge fraction", f"{lensige} ! LenSiGe"]
+    L += ["1.0 ! PtransZig", "0.4525 ! sf", "Iter", f"{maxiter} ! IterMax", f"{maxiter} ! OutMolMol", "R ! RunType", "9117116 ! IDUM",
+          "F ! Save final state", "T ! Save final Coor", "LattStat.dat"]
+    e = {1: 0.96, 2: 0.70}
+    if sige:
+        for sp in (1, 2):
+            for n1 in range(4):
+                for n2 in range(4):
+                    if 1 <= n1 + n2 <= 3:
+                        L.append(f"{sp} {n1}{n2} {0.5 * (e[sp] * (n1 + n2) + e[1] * n1 + e[2] * n2)!r}")
+        for sp, sc in ((1, 1.0), (2, 0.72)):
+            L += [f"{sp} {c} {v * sc!r}" for c, v in ((1, 1.86), (2, 1.92), (3, 1.98))]
+    else:
+        L += ["1 1 0.96", "1 2 1.92", "1 3 2.88", "1 1 1.86", "1 2 1.92", "1 3 1.98"]
+    dst = os.path.join(dirpath, "start.dat")
+    with open(dst, "w") as f:
+        f.write("\n".join(L) + "\n")
+    return dst

@@ -54,6 +54,9 @@ def load_oracle():
     lib.orc_get_tables.argtypes = [vp] + [C.c_void_p] * 5
     lib.orc_get_species.argtypes = [vp, C.c_void_p]
     lib.orc_get_field.argtypes = [vp] + [C.c_void_p] * 6
+    lib.orc_get_fork.argtypes = [vp, C.c_void_p, C.c_void_p]
+    lib.orc_set_variant.argtypes = [vp, C.c_int]
+    lib.orc_set_numocc0.argtypes = [vp, C.c_int]
     lib.orc_get_run.argtypes = [vp, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
     lib.orc_get_rng.argtypes = [vp, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.orc_get_counts.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -76,11 +79,13 @@ def load_oracle():
 
 
 class Oracle:
-    def __init__(self, lenx, leny, lenz, start_path, nummcmax=0, outdir=None, logpath=None, write_files=False):
+    def __init__(self, lenx, leny, lenz, start_path, nummcmax=0, outdir=None, logpath=None, write_files=False, la_tree=False):
         self.lib = load_oracle()
         self.o = self.lib.orc_create(lenx, leny, lenz, nummcmax)
         if not self.o:
             raise MemoryError("orc_create")
+        self.la_tree = bool(la_tree)
+        self.lib.orc_set_variant(self.o, int(self.la_tree))     # True: follow mulskips-source-LaserAnnealing instead of mulskips-source
         self.LenX, self.LenY, self.LenZ = lenx, leny, lenz
         self.lib.orc_set_io(self.o, outdir.encode() if outdir else None, logpath.encode() if logpath else None, int(write_files))
         if self.lib.orc_read_start(self.o, start_path.encode()) != 0:
@@ -163,6 +168,16 @@ class Oracle:
         self.lib.orc_get_field(self.o, info.ctypes.data, rt.ctypes.data, E.ctypes.data, D.ctypes.data, A.ctypes.data, S.ctypes.data)
         return dict(ntemp=n, fixedT=int(info[1]), Ttop=int(info[2]), reftemp=rt, refPE=E, refPD=D, refPAbs=A, refPDes=S)
 
+    def set_numocc0(self, v):
+        self.lib.orc_set_numocc0(self.o, int(v))
+
+    def fork(self):
+        """LaserAnnealing-fork bookkeeping (la/main.f:592-611, la/modules/defsystem.f:36-37,46,82)."""
+        iv, dv = np.zeros(10, np.int32), np.zeros(12)
+        self.lib.orc_get_fork(self.o, iv.ctypes.data, dv.ctypes.data)
+        return dict(la_tree=int(iv[0]), NumAdAtomOcc=int(iv[1]), NumOcc0=int(iv[2]), NumOcc1=int(iv[3]), InitCountCrystal=iv[4:7].copy(),
+                    CountLiquid=iv[7:10].copy(), Tm=dv[0:3].copy(), P0=dv[3:6].copy(), sigma=dv[6:9].copy(), Tflex=dv[9:12].copy())
+
     def species(self):
         a = np.zeros(8, np.int32)
         self.lib.orc_get_species(self.o, a.ctypes.data)
@@ -223,7 +238,14 @@ def upload_oracle_state(orc: Oracle, ctx):
                            fixed_temperature=fl["Ttop"] if fl["fixedT"] else 0)
     else:
         ctx.set_rates(t["PtransE"], t["PtransD"], t["PtransAbs"], t["PtransDes"], t["PtransZig"])
-    if rp["InitSt"] == "LA":
+    if orc.la_tree:
+        ctx.set_tree_variant(1)
+    if rp["InitSt"] == "LA" and orc.la_tree:
+        fk = orc.fork()
+        T = (L[:-1] >> 9) & 8191
+        tv = T[T > 0]
+        ctx.set_la_fork(fk["Tm"], fk["P0"], fk["sigma"], fk["Tflex"], int(tv.min()), int(tv.max()), fk["InitCountCrystal"], fk["NumOcc0"], fk["NumAdAtomOcc"])
+    elif rp["InitSt"] == "LA":
         T = (L[:-1] >> 9) & 8191
         tv = T[T > 0]
         ctx.set_la(t["Tm"], t["P0"], t["sigma"], t["Tflex"], int(tv.min()), int(tv.max()))

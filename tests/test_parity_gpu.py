@@ -140,3 +140,58 @@ def test_parity_laser_annealing(tmp_path):
     assert np.array_equal(L2[:-1] & ~(8191 << 9), L[:-1] & ~(8191 << 9))
     assert np.array_equal((L2[:-1] >> 9) & 8191, np.where(T == 0, 0, T + 1))
     ctx.close(); orc.close()
+
+
+@pytest.mark.parametrize("species,phase1", [("SiGe", 100000), ("Si", 20000)])
+def test_parity_la_fork(tmp_path, species, phase1):
+    """The LaserAnnealing fork (mulskips-source-LaserAnnealing, SURVEY 8 row a-LA) in serial-parity mode: species bits
+    28-29 and event codes 1-2/3 at the boundary (mskc_set_tree_variant), per-species Tm/P0/sigma/Tflex, solidification
+    rates scaled by the liquid fraction CountLiquid(k)/SUM(CountLiquid) re-evaluated before every event, Si<->Ge swap
+    when a species is used up, NumAdAtomOcc bookkeeping and the NumOcc0 stop rule (la/main.f:634-726).  Phase 1: a
+    melt nucleus re-solidifies (Ge segregates into the liquid); every chunk: list sizes, Time bits, NumAdAtomOcc.
+    Phase 2: the stop threshold is lowered on both sides to a few atoms above the current count so that the rule fires
+    while the melt is still rich (when the melt is used up the reference divides by SUM(CountLiquid) = 0).  At the end:
+    lattice words in the fork's layout, lists, rates as raw bits, species counters."""
+    from cases import make_la_tree_case
+    from mulskips_b200 import Mskc
+    box = (96, 96, 96)
+    start = make_la_tree_case(str(tmp_path), box=box, sige=(species == "SiGe"), tbase=1480 if species == "SiGe" else 1655)
+    orc = Oracle(*box, start, la_tree=True)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())       # round trip through the layout conversion
+    total = 0
+    for chunk in (1, 999, phase1 // 2 - 1000, phase1 // 2):
+        n = orc.run(chunk)
+        r = ctx.run_parity(event_budget=chunk)
+        total += n
+        s = orc.sizes()
+        assert n == chunk and r.events_done == n, (r.events_done, n, total)
+        assert (r.num_adatom, r.num_atoms, r.num_voids) == (s["NumAdAtom"], s["NumAtoms"], s["NumVoids"]), total
+        assert bits(r.time) == bits(orc.time), total
+        assert ctx.counters().num_adatom_occ == orc.fork()["NumAdAtomOcc"]
+    fk = orc.fork()
+    assert fk["CountLiquid"][0] > 0
+    occ0 = s["NumAtoms"] + fk["NumAdAtomOcc"] + 5
+    orc.set_numocc0(occ0)
+    T = (orc.lattcoo()[:-1] >> 9) & 8191
+    ctx.set_la_fork(fk["Tm"], fk["P0"], fk["sigma"], fk["Tflex"], int(T[T > 0].min()), int(T.max()), fk["InitCountCrystal"], occ0, fk["NumAdAtomOcc"])
+    n = orc.run(200000)
+    r = ctx.run_parity(event_budget=200000)
+    s, fk = orc.sizes(), orc.fork()
+    assert s["done"] == 1 and r.stop_reason == 5 and r.events_done == n      # MSKC_STOP_RESOLIDIFIED
+    assert s["NumAtoms"] + fk["NumAdAtomOcc"] > occ0
+    assert bits(r.time) == bits(orc.time)
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())
+    d, g = orc.lists(), ctx.download_lists()
+    for k in ("mc_xyz", "mc_nn", "mc_event", "void_xyz", "void_nn"):
+        assert np.array_equal(d[k], g[k]), k
+    assert np.array_equal(d["mc_rate"].view(np.uint64), g["mc_rate"].view(np.uint64))
+    cc, cv = orc.counts()
+    c = ctx.counters()
+    assert list(c.CountCrystal) == list(cc) and c.num_adatom_occ == fk["NumAdAtomOcc"]
+    if species == "SiGe":
+        assert cc[1] > 0
+    ctx.close(); orc.close()

@@ -167,3 +167,46 @@ def test_extract_frame_matches_lattice(tmp_path):
     assert np.array_equal(words, L[want])
     assert len(cells) > 100
     ctx.close(); orc.close()
+
+
+def test_replay_la_fork(tmp_path):
+    """the cooperative transition code under the LaserAnnealing fork's law: the liquid-fraction factor of the
+    solidification rates follows the trace event by event (replay kernel), event codes and lattice words cross the
+    boundary in the fork's layout"""
+    from cases import make_la_tree_case
+    from mulskips_b200 import Mskc
+    box = (96, 96, 96)
+    start = make_la_tree_case(str(tmp_path), box=box)
+    orc = Oracle(*box, start, la_tree=True)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    n = 120000
+    orc.set_trace(n)
+    assert orc.run(n) == n
+    site, code, arm, tree1 = trace_arrays(orc)
+    assert set(np.unique(code)) <= {1, 2, 3}
+    ctx.replay_events(site, code, arm, tree_root=1.0)
+    Lo = orc.lattcoo()
+    assert np.array_equal(ctx.download_lattice(), Lo)
+    cc, _ = orc.counts()
+    assert list(ctx.counters().CountCrystal) == list(cc)
+    # every listed site: same class; evaporation rates bit-equal.  Deposition sites carry the liquid fraction of the
+    # moment they were last rated on both sides, so those are bit-equal too.
+    d = orc.lists()
+    exp = {}
+    for xyz, ev, rate in zip(d["mc_xyz"], d["mc_event"], d["mc_rate"]):
+        forced = ev == 1 and rate in (float(np.float32(1e-8)), float(np.float32(1e-6)))
+        exp[tuple(int(v) for v in xyz)] = (int(ev) if (ev == 3 or forced) else 100, np.float64(rate).view(np.uint64))
+    xyz, ev, rate = ctx.download_active()
+    got = {tuple(int(v) for v in p): (int(e), np.float64(r).view(np.uint64)) for p, e, r in zip(xyz, ev, rate)}
+    assert set(got) == set(exp)
+    bad = [s for s, v in exp.items() if got[s] != v and not ((int(Lo[s[2], s[1], s[0]]) >> 23) & 1 and ((int(Lo[s[2], s[1], s[0]]) >> 24) & 7) == 0)]
+    assert not bad, bad[:5]
+    # sampler on the fork's law (CountLiquid frozen per call), occupied count from the census
+    p = ctx.run_parallel(n_sweeps=10, events_per_tile=2.0, seed=5)
+    assert p.events_done > 0
+    c = ctx.counters()
+    assert c.num_adatom_occ > 0
+    ctx.close(); orc.close()
