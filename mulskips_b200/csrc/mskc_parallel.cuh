@@ -450,6 +450,7 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
 #pragma unroll
   for (int k = 0; k < 9; k++) v[k] = __reduce_add_sync(0xFFFFFFFFu, v[k]);
   if (lane == 0) {
+    if (fork) { volatile int *cl = g_la_CL; cl[0] = cl0[0] - v[3]; cl[1] = cl0[1] - v[4]; cl[2] = cl0[2] - v[5]; cl[3] = cl[0] + cl[1] + cl[2]; }   // for the next chunk
     out->events += done; out->site_updates += v[0]; out->dAtoms += v[1]; out->dVoids += v[2];
     for (int i = 0; i < 3; i++) { out->dCrystal[i] += v[3 + i]; out->dCov[i] += v[6 + i]; }
   }

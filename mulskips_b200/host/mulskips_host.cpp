@@ -26,7 +26,10 @@
 
 namespace {
 
-enum { PosIndex = 0, LenIndex = 8, PosT = 9, LenT = 13, PosOcc = 23, PosCoor = 24, LenCoor = 3, PosSi = 27, PosC = 28, PosSiC = 27, LenSiC = 3 };
+enum { PosIndex = 0, LenIndex = 8, PosT = 9, LenT = 13, PosOcc = 23, PosCoor = 24, LenCoor = 3 };
+// species bits and the evaporation code: mulskips-source (modules/defsystem.f:90-91, main.f:335-357) by default; --la-tree
+// selects the LaserAnnealing fork's (mulskips-source-LaserAnnealing/modules/defsystem.f:99-100, main.f:671-699)
+int PosSi = 27, PosC = 28, PosSiC = 27, LenSiC = 3, EvEvap = 4;
 const int JumpDia[8][3] = {{3, 3, 3}, {3, -3, -3}, {-3, -3, 3}, {-3, 3, -3}, {3, 3, -3}, {3, -3, 3}, {-3, -3, -3}, {-3, 3, 3}};   // defsystem.f:104-105
 
 [[noreturn]] void die(const char *fmt, ...) {
@@ -62,6 +65,16 @@ struct Host {
   std::vector<double> refPE, refPD, refPA, refPS;         // [ntemp][12288], [ntemp][9], [ntemp][12], [ntemp][12]
   std::vector<int> st_idx;                                // PtransE entries that are non-zero in some block
   bool st() const { return InitSt == "ST"; }
+  // --la-tree: the LaserAnnealing fork (la/main.f:380-520, 592-611, 634-726; la/modules/defsystem.f:36-37,46,82-83)
+  bool la_tree = false;
+  double Tm_k[3] = {0, 0, 0}, P0_k[3] = {0, 0, 0}, sigma_k[3] = {0, 0, 0}, Tflex_k[3] = {0, 0, 0}, LenSiGe = 0;
+  int NumAdAtomOcc = 0, NumOcc0 = 0, NumOcc1 = 0, InitCountCrystal[3] = {0, 0, 0}, CountLiquid[3] = {0, 0, 0};
+  double la_PE_k(int T, int k, double e) const { return P0_k[k - 1] * exp(-e / (0.00008617330350 * T)) * (e != 0.0 ? 1.0 : 0.0); }   // la/mcevent/Get_Prob_Ini.f:76-78
+  double la_PD_k(int T, int k, double d) const {                                                                                    // la/mcevent/Get_Prob_Ini.f:80-83
+    const int sum = CountLiquid[0] + CountLiquid[1] + CountLiquid[2];
+    return 0.5 * P0_k[k - 1] * (double)(float)CountLiquid[k - 1] / (double)sum * exp(-d / (0.00008617330350 * Tm_k[k - 1]))
+           * (1.0 + erf((T - Tflex_k[k - 1]) / sigma_k[k - 1])) * (d != 0.0 ? 1.0 : 0.0);
+  }
   long long MaxIter = 0, OutMolMol = 0;
   std::vector<double> PE = std::vector<double>(12288, 0.0), PD = std::vector<double>(9, 0.0), PA = std::vector<double>(12, 0.0), PS = std::vector<double>(12, 0.0);
   // state built by the initialiser (module globals of defsystem.f)
@@ -118,7 +131,8 @@ struct Host {
   // deposition / adsorption draw of Get_Prob.f:160-179 (pre-drawn species; one ran3 call)
   void draw_dep_abs(int Coor, bool with_abs, int &ev, double &prob, int T = 0) {
     double PD1 = PD[0 + 3 * (Coor - 1)], PD2 = PD[1 + 3 * (Coor - 1)], PD3 = PD[2 + 3 * (Coor - 1)];
-    if (T > 0) { PD1 = la_PD(T, PD1); PD2 = la_PD(T, PD2); PD3 = la_PD(T, PD3); }
+    if (T > 0 && la_tree) { PD1 = la_PD_k(T, 1, PD1); PD2 = NCrystal >= 2 ? la_PD_k(T, 2, PD2) : 0.0; PD3 = 0.0; }
+    else if (T > 0) { PD1 = la_PD(T, PD1); PD2 = la_PD(T, PD2); PD3 = la_PD(T, PD3); }
     double PDep = PD1 + PD2 + PD3, PAbs = 0;
     if (with_abs) for (int k = 1; k <= 3; k++) PAbs += PA[(k - 1) + 3 * Coor];
     double Ptot = PDep + PAbs, Pcurr = ran3() * Ptot;
@@ -177,9 +191,9 @@ struct Host {
     int n = N_Si + N_C + N_B + N_cov;
     if (n != Coor) die(" %d %d %d %d %d Get Prob Error N_Si+N_C++N_B+N_cov.NE.Coor", Coor, N_Si, N_C, N_B, N_cov);
     if (n > 3) return;
-    ev = 4;
+    ev = EvEvap;
     if (n == 0) { prob = (double)100000.f * Tree[1]; printf(" %d Get Prob Isolated Atom\n", Coor); }
-    else { prob = PE[idxE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)]; if (T > 0) prob = la_PE(T, prob); }
+    else { prob = PE[idxE(NSiC, N_Si + N_cov, N_C, N_B, 0, 0, 0)]; if (T > 0) prob = la_tree ? la_PE_k(T, NSiC, prob) : la_PE(T, prob); }
   }
 };
 
@@ -319,16 +333,25 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
     printf(" ****** MulSKIPs run for laser annealing ******\n");
     if (H.NCov > 0) die(" ERR NOT IMPLEMENTED: NCov=0 for LA");
     H.cadfile = whole_line(in.next()); H.tempfile = whole_line(in.next());
+    if (H.la_tree) {                                                                    // la/main.f:420-424: one value per crystal species
+      double *dst[4] = {H.Tm_k, H.P0_k, H.sigma_k, H.Tflex_k};
+      for (int q = 0; q < 4; q++) { char *p = const_cast<char *>(in.next()); for (int k = 0; k < H.NCrystal; k++) dst[q][k] = fnum(p, &p); }
+      H.Tm = H.Tm_k[0]; H.P0 = H.P0_k[0]; H.sigma = H.sigma_k[0]; H.Tflex = H.Tflex_k[0];
+      printf(" Melting temperature in Kelvin: "); for (int k = 0; k < H.NCrystal; k++) printf(" %.17g", H.Tm_k[k]); printf("\n");
+    } else {
     H.Tm = fnum(in.next()); H.P0 = fnum(in.next()); H.sigma = fnum(in.next()); H.Tflex = fnum(in.next());
     printf(" Melting temperature in Kelvin:  %.17g\n", H.Tm);
+    }
     H.LenVac = fnum(in.next()); printf(" Top air thickness (ang):  %.17g\n", H.LenVac);
     H.LenNuc = fnum(in.next()); printf(" Nucleus thickness (ang):  %.17g\n", H.LenNuc);
     H.Homogeneous = first_token(in.next()).substr(0, 2); printf(" Model homogeneous nucleation: %s\n", H.Homogeneous.c_str());
+    if (H.la_tree && H.Homogeneous == "D") die(" mulskips.e (B200 host): Homogeneous 'D' (SetSiGeSF stacking-fault seed) is not built");
   }
   else { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); }
   // main.f:142-149 (the ALL(...) test with NCrystal=1 behaves as "not SiGe", SURVEY 8c trap 5)
   if ((H.NCrystal == 2 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32) || (H.NCrystal == 3 && H.ListCrystal[0] == 14 && H.ListCrystal[1] == 32 && H.ListCrystal[2] == 5)) {
     H.alloy = fnum(in.next()); printf(" Ge fraction in substrate:  %.17g\n", H.alloy);
+    if (H.la_tree) { H.LenSiGe = fnum(in.next()); printf(" SiGe thickness (ang):  %.17g\n", H.LenSiGe); }        // la/main.f:441-442
   }
   H.PtransZig = fnum(in.next());
   H.sf = fnum(in.next());
@@ -346,7 +369,11 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   if (H.SaveFinalState == "T") { H.restartfile = whole_line(in.next()); printf(" ATTENTION! Storing checkpoint file %s\n This will occupy a lot of disk space...\n", H.restartfile.c_str()); }
   else printf(" SaveFinalState flag is not \"T\": checkpoint file will  not be written.\n");
   H.SaveCoo = first_token(in.next()).substr(0, 2);
-  if (H.SaveCoo == "T") { H.coofile = whole_line(in.next()); printf(" ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", H.coofile.c_str()); }
+  if (H.SaveCoo == "T") {
+    H.coofile = whole_line(in.next());
+    if (H.la_tree && H.coofile == "None") printf(" Phases passed through sockets...\n");
+    else printf(" ATTENTION! Storing final Coor file %s\n This might occupy a a lot of disk space...\n", H.coofile.c_str());
+  }
   else {
     if (H.la()) die(" ERR: SaveCoo flag must be \"T\" for LA simulations!");
     printf(" SaveCoo flag is not \"T\": Coor file not stored\n");
@@ -448,7 +475,7 @@ void pass_probability(Host &H, int z0, int z1, int y0, int y1, int x0, int x1, b
         if (cadvoid && Coor == 4) { printf(" Initializing a vacancy\n"); H.AddVoid(s, nn); }      // SetCAD.f:340-346
         else { H.get_prob_ini(0, 0, Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
       }
-    } else if (Coor <= 3) { H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
+    } else if (Coor <= 3) { H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); H.NumAdAtomOcc++; }      // (la/initial/SetCAD.f:544,595)
     else H.AddBulk(s, nn);
   }
 }
@@ -596,6 +623,12 @@ void set_cad(Host &H) {
         if (Id != 1 || !cubic_site(x, y, z, kind)) continue;
         bool fill = true;
         if (la) {                                             // solid everywhere but the liquid nucleus (:118-141)
+          // la/initial/SetCAD.f:140,161,185 (the branch fed by the socket array): solid sites below the air gap, before nucleation
+          if (H.la_tree && z <= LZ - (int)(H.LenVac / H.sf)) H.NumOcc0++;
+          if (H.la_tree && H.Homogeneous == "R") {             // la/initial/SetCAD.f:186-207: semi-cylindrical nucleus along y
+            const int xc = LX / 2, zc = LZ - (int)(H.LenVac / H.sf);
+            fill = (x - xc) * (x - xc) + (z - zc) * (z - zc) > (int)((H.LenNuc / H.sf) * (H.LenNuc / H.sf));
+          } else
           if (H.Homogeneous == "T") fill = z <= LZ - (int)((H.LenVac + H.LenNuc) / H.sf);
           else if (H.Homogeneous == "F") {
             const int xc = LX / 2, yc = LY / 2, zc = LZ - (int)(H.LenVac / H.sf);
@@ -607,11 +640,23 @@ void set_cad(Host &H) {
         // alloy species: the reference draws libgfortran's RAND() here (SetCAD.f:145,164,178), which is not part of the
         // reference sources -- alloy initial configurations are statistically equivalent only
         double rr = 1.0;
-        if (H.alloy > 0) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0); }
+        // (SetCAD.f:141-145: Si below the SiGe layer.  mulskips-source never sets LenSiGe; the fork reads it from start.dat)
+        if (H.alloy > 0 && !(la && z <= LZ - (int)((H.LenVac + (H.la_tree ? H.LenSiGe : 0.0)) / H.sf))) {
+          lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
+        }
         w |= 1 << (rr >= H.alloy ? PosSi : PosC);
+        if (H.la_tree) H.CountCrystal[rr >= H.alloy ? 0 : 1]++;                                                     // la/initial/SetCAD.f:150-155
       }
     }
     printf(" Done reading input geometry file\n");
+    if (H.la_tree) {                                          // la/initial/SetCAD.f:343-351
+      const int sum = H.CountCrystal[0] + H.CountCrystal[1] + H.CountCrystal[2];
+      for (int k = 0; k < H.NCrystal; k++) {
+        if (H.ListCrystal[k] == 14) H.InitCountCrystal[k] = H.CountCrystal[k] + (int)((H.NumOcc0 - sum) * (1 - H.alloy));
+        else if (H.ListCrystal[k] == 32) H.InitCountCrystal[k] = H.CountCrystal[k] + (int)((H.NumOcc0 - sum) * H.alloy);
+      }
+      for (int k = 0; k < 3; k++) H.CountLiquid[k] = H.InitCountCrystal[k] - H.CountCrystal[k];
+    }
     pass_coordination(H, 0, LZ - 1, 0, LY - 1, 0, LX - 1, true);
   }
   fclose(f);
@@ -642,7 +687,8 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   if (on_device) {                                           // the module globals the writers read, from the device
     MS(mskc_download_lattice(R.h, H.L.data()));
     mskc_counters c; MS(mskc_get_counters(R.h, &c));
-    for (int i = 0; i < 3; i++) { H.CountCrystal[i] = c.CountCrystal[i]; H.CountCov[i] = c.CountCov[i]; }
+    for (int i = 0; i < 3; i++) { H.CountCrystal[i] = c.CountCrystal[i]; H.CountCov[i] = c.CountCov[i]; H.CountLiquid[i] = H.InitCountCrystal[i] - c.CountCrystal[i]; }
+    H.NumAdAtomOcc = c.num_adatom_occ;
     voids.resize((size_t)std::max(c.num_voids, 0));
     if (!voids.empty()) {
       std::vector<int32_t> vx(3 * voids.size()), vn(12 * voids.size());
@@ -650,6 +696,21 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
       for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
     }
   } else voids = H.voids;
+  if (H.la_tree) {                                          // la/inpout/WriteMolMolSource.f:42-67
+    int s = 0, so = 0, sl = 0; for (int i = 0; i < 3; i++) { s += H.CountCrystal[i]; so += H.CountCrystalOld[i]; sl += H.CountLiquid[i]; }
+    if (H.NCrystal > 1) printf(" SUM(CountCrystal) %d\n", s);
+    printf(" CountCrystal %d %d %d\n xCrystal %.9g %.9g %.9g\n", H.CountCrystal[0], H.CountCrystal[1], H.CountCrystal[2],
+           (float)H.CountCrystal[0] / s, (float)H.CountCrystal[1] / s, (float)H.CountCrystal[2] / s);
+    printf(" CountLiquid %d %d %d\n xLiquid %.9g %.9g %.9g\n", H.CountLiquid[0], H.CountLiquid[1], H.CountLiquid[2],
+           (float)H.CountLiquid[0] / sl, (float)H.CountLiquid[1] / sl, (float)H.CountLiquid[2] / sl);
+    if (Iter > 1) {
+      float d[3]; for (int i = 0; i < 3; i++) d[i] = (float)(H.CountCrystal[i] - H.CountCrystalOld[i]);
+      printf(" diffCrystal %.9g %.9g %.9g\n", d[0], d[1], d[2]);
+      printf(" Atom fraction from last check: %.17g %.17g %.17g\n", (double)d[0] / (s - so), (double)d[1] / (s - so), (double)d[2] / (s - so));
+      for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
+    }
+    if (H.NCov != 0) printf(" CountCov %d %d %d\n", H.CountCov[0], H.CountCov[1], H.CountCov[2]);
+  } else
   if (Iter != 0) {                                           // WriteMolMolSource.f:42-56
     int s = 0, so = 0; for (int i = 0; i < 3; i++) { s += H.CountCrystal[i]; so += H.CountCrystalOld[i]; }
     printf(" SUM(CountCrystal) %d\n CountCrystal %d %d %d\n CountCrystalOld %d %d %d\n", s, H.CountCrystal[0], H.CountCrystal[1], H.CountCrystal[2], H.CountCrystalOld[0], H.CountCrystalOld[1], H.CountCrystalOld[2]);
@@ -702,7 +763,8 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     if (H.NCov == 0 && H.NCrystal == 2 && H.ListCrystal[1] == 6) {
       int a = 0; for (int j = 0; j < 4; j++) a += ibits(H.at(v.nn[j]), PosSiC, LenSiC);
       const char *el = a == 4 ? "Mg " : a == 8 ? "He " : a == 7 ? "Ne " : a == 5 ? "Be " : a == 6 ? "Ar " : nullptr;
-      const char *tail = a == 4 ? " # CV (C vacancy)" : a == 8 ? " # SV (Si vacancy)" : a == 7 ? " # SAV (Si antisite vac)" : a == 5 ? " # CAV (C antisite vac)" : " # XV (near 2C and 2Si)";
+      const char *tail = a == 4 ? (H.la_tree ? " # SV (Si vacancy)" : " # CV (C vacancy)") : a == 8 ? (H.la_tree ? " # CV (C vacancy)" : " # SV (Si vacancy)")      // la/inpout/WriteMolMolXYZFile.f:66-70
+                         : a == 7 ? " # SAV (Si antisite vac)" : a == 5 ? " # CAV (C antisite vac)" : (H.la_tree ? " # surrounded by 2C-2Si" : " # XV (near 2C and 2Si)");
       if (!el) die(" ERROR: Weird Defect type was formed...ABORTING");
       atom_line(fv, el, sf, v.xyz[0], v.xyz[1], v.xyz[2], tail);
     } else atom_line(fv, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
@@ -782,10 +844,11 @@ int main(int argc, char **argv) {
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--box") && i + 3 < argc) { box[0] = atoi(argv[i + 1]); box[1] = atoi(argv[i + 2]); box[2] = atoi(argv[i + 3]); i += 3; have_box = true; }
     else if (!strcmp(argv[i], "--parallel")) parallel = true;
+    else if (!strcmp(argv[i], "--la-tree")) { H.la_tree = true; PosSi = 28; PosC = 29; PosSiC = 28; LenSiC = 2; EvEvap = 3; }
     else if (!strcmp(argv[i], "--events-per-tile") && i + 1 < argc) ept = atof(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
-    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--device d] [--start file]\n", argv[0]); return 2; }
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--la-tree] [--device d] [--start file]\n", argv[0]); return 2; }
   }
   if (!have_box) { if (const char *e = getenv("MSKC_BOX")) have_box = sscanf(e, "%d %d %d", &box[0], &box[1], &box[2]) == 3; }
   if (!have_box) box_from_defsystem(argv[0], box);
@@ -794,6 +857,7 @@ int main(int argc, char **argv) {
   H.L.assign((size_t)H.LX * H.LY * (H.LZ + 1), 0);
   H.Tree.assign((size_t)1 << H.Levels, 0.0);
   // main.f:225-295
+  if (H.la_tree && H.InitSt != "LA" && H.InitSt != "IN") die(" mulskips.e (B200 host): --la-tree (the LaserAnnealing fork) is built for InitSt LA and IN");
   if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
   else if (H.InitSt == "FS") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false); }
   else if (H.InitSt == "SG") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false, true); }
@@ -806,6 +870,20 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
   else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, I, FF, ST, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
+  if (H.la_tree) {                                            // la/main.f:592-611,628
+    H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;
+    for (int k = 1; k <= H.NCrystal; k++) {
+      if (k == 1) H.InitCountCrystal[0] = H.CountCrystal[0] + (int)((H.NumOcc0 - H.NumOcc1) * (1 - H.alloy));
+      else if (k == 2) H.InitCountCrystal[1] = H.CountCrystal[1] + (int)((H.NumOcc0 - H.NumOcc1) * H.alloy);
+    }
+    printf(" \n Initial number of occupied sites (before nucleation):  %d\n", H.NumOcc0);
+    printf(" Initial CountCrystal (before nucleation):  %d %d %d\n", H.InitCountCrystal[0], H.InitCountCrystal[1], H.InitCountCrystal[2]);
+    printf(" Initial number of occupied sites (after nucleation):  %d\n", H.NumOcc1);
+    printf(" Initial CountCrystal (after nucleation):  %d %d %d\n", H.CountCrystal[0], H.CountCrystal[1], H.CountCrystal[2]);
+    printf(" Initial number of liquid sites (after nucleation):  %d\n", H.NumOcc0 - H.NumOcc1);
+    printf(" Initial CountLiquid (after nucleation):  %d %d %d\n \n", H.CountLiquid[0], H.CountLiquid[1], H.CountLiquid[2]);
+    printf(" Atoms,Voids,AdAtoms,AdAtomsOcc %d %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom, H.NumAdAtomOcc);
+  } else
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
   for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
   write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
@@ -814,7 +892,9 @@ int main(int argc, char **argv) {
   if (H.st()) MS(mskc_set_rate_field(R.h, H.ntemp, H.reftemp.data(), H.refPE.data(), H.refPD.data(), H.refPA.data(), H.refPS.data(), H.PtransZig,
                                      H.t_lo, H.t_hi, H.fixedT ? (int)H.Ttop : 0));
   else MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
-  if (H.la()) MS(mskc_set_la(R.h, 1, H.Tm, H.P0, H.sigma, H.Tflex, H.t_lo, H.t_hi));
+  if (H.la_tree) MS(mskc_set_tree_variant(R.h, MSKC_TREE_LA));
+  if (H.la() && H.la_tree) MS(mskc_set_la_fork(R.h, 1, H.Tm_k, H.P0_k, H.sigma_k, H.Tflex_k, H.t_lo, H.t_hi, H.InitCountCrystal, H.NumOcc0, H.NumAdAtomOcc));
+  else if (H.la()) MS(mskc_set_la(R.h, 1, H.Tm, H.P0, H.sigma, H.Tflex, H.t_lo, H.t_hi));
   {
     std::vector<int32_t> mx(3 * H.mc.size() + 3), mn(12 * H.mc.size() + 12), me(H.mc.size() + 1), bx(3 * H.bulk.size() + 3), bn(12 * H.bulk.size() + 12), vx(3 * H.voids.size() + 3), vn(12 * H.voids.size() + 12);
     for (size_t i = 0; i < H.voids.size(); i++) { memcpy(&vx[3 * i], H.voids[i].xyz, 12); memcpy(&vn[12 * i], H.voids[i].nn, 48); }
@@ -837,12 +917,22 @@ int main(int argc, char **argv) {
       if (mskc_run_parity(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
       R.Iter = r.iter; R.IterOut = r.iter_out; R.Time = r.time; R.NumAtoms = r.num_atoms; R.NumVoids = r.num_voids; R.NumAdAtom = r.num_adatom;
       dev_ms += r.kernel_ms; events += r.events_done;
-      if (r.stop_reason == MSKC_STOP_FEWMC) { printf(" few MC particles: stop MC %lld %d\n", R.Iter, R.NumAdAtom); break; }
+      if (r.stop_reason == MSKC_STOP_FEWMC) {
+        if (H.la_tree) { mskc_counters c; MS(mskc_get_counters(R.h, &c)); printf(" few MC particles: stop MC %lld %d %d\n", R.Iter, R.NumAdAtom, c.num_adatom_occ); }
+        else printf(" few MC particles: stop MC %lld %d\n", R.Iter, R.NumAdAtom);
+        break;
+      }
+      if (r.stop_reason == MSKC_STOP_RESOLIDIFIED) {          // la/main.f:714-723
+        mskc_counters c; MS(mskc_get_counters(R.h, &c));
+        printf(" \n Current number of occupied sites:  %d\n    > initial number of occupied sites:  %d\n ... STOPPING MulSKIPS ...\n \n", c.num_atoms + c.num_adatom_occ, H.NumOcc0);
+        break;
+      }
       if (r.stop_reason == MSKC_STOP_FRAME) {                 // main.f:316-333
         if (!by_time) R.framecounter = R.IterOut / H.OutMolMol;
         write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter + 1 : R.framecounter, true);
         printf(" Iter, Time, Site %lld %.17g %d %d %d\n", R.Iter, R.Time, r.last_site[0], r.last_site[1], r.last_site[2]);
-        printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+        if (H.la_tree) printf(" NatNvoidNadNadocc %d %d %d %d\n Number of occupied sites:  %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom, H.NumAdAtomOcc, R.NumAtoms + H.NumAdAtomOcc);
+        else printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
         if (by_time) R.framecounter++;
         continue;
       }

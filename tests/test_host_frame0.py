@@ -7,7 +7,7 @@ import subprocess
 
 import pytest
 
-from cases import make_st_case, make_start
+from cases import make_la_tree_case, make_st_case, make_start
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "mulskips_b200", "bin", "mulskips.e")
@@ -21,7 +21,7 @@ def _tokens(text, key):
     return None
 
 
-@pytest.mark.parametrize("kind", ["ST-ramp", "ST-fixedT", "SiGeBdoped"])
+@pytest.mark.parametrize("kind", ["ST-ramp", "ST-fixedT", "SiGeBdoped", "LA-fork-SiGe", "LA-fork-Si"])
 def test_frame0_and_startup_log(tmp_path, kind):
     if not (os.path.exists(EXE) and os.path.exists(ORACLE)):
         import __graft_entry__ as g
@@ -32,10 +32,13 @@ def test_frame0_and_startup_log(tmp_path, kind):
         box = (96, 48, 144)
         kw = dict(ttop=1000.0, tbottom=1000.0) if kind.endswith("fixedT") else {}
         start = make_st_case(str(tmp_path), maxiter=1, **kw)
+    elif kind.startswith("LA-fork"):                 # the LaserAnnealing fork's grammar, layout and start-up bookkeeping (--la-tree)
+        box = (96, 96, 96)
+        start = make_la_tree_case(str(tmp_path), box=box, maxiter=1, sige=kind.endswith("SiGe"), tbase=1480 if kind.endswith("SiGe") else 1655)
     else:
         box = (96, 96, 240)
         start = make_start("SiGeBdoped", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=1, outmolmol=1)
-    args = ["--box", *[str(v) for v in box]]
+    args = ["--box", *[str(v) for v in box]] + (["--la-tree"] if kind.startswith("LA-fork") else [])
     logs = {}
     for d, exe in ((g, EXE), (o, ORACLE)):
         (d / "start.dat").write_text(open(start).read())
@@ -46,5 +49,6 @@ def test_frame0_and_startup_log(tmp_path, kind):
     for name in ("I00000000.xyz", "I00000000_d.xyz", "I00000000_v.xyz"):
         assert (g / name).read_bytes() == (o / name).read_bytes(), f"{kind}: {name}"
     assert len((g / "I00000000.xyz").read_text().splitlines()) > 50
-    for key in ("Atoms,Voids,AdAtoms", "maxElines", "Temperature on top", "Reading input probability table"):
+    for key in ("Atoms,Voids,AdAtoms", "maxElines", "Temperature on top", "Reading input probability table", "Initial number of occupied sites (before",
+                "Initial CountCrystal (before", "Initial CountLiquid", "Initial number of liquid sites", "CountLiquid", "xLiquid"):
         assert _tokens(logs[g], key) == _tokens(logs[o], key), key

@@ -15,7 +15,7 @@ import subprocess
 
 import pytest
 
-from cases import GOLDEN, make_cad_case, make_la_case, make_sige_case, make_st_case, make_start, start_path
+from cases import GOLDEN, make_cad_case, make_la_case, make_la_tree_case, make_sige_case, make_st_case, make_start, start_path
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -78,7 +78,7 @@ def test_regression_case(built, tmp_path, case):
     assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
 
 
-@pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe", "ST", "ST-fixedT", "SiGeBdoped"])
+@pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe", "ST", "ST-fixedT", "SiGeBdoped", "LA-fork"])
 def test_file_driven_case(built, tmp_path, kind):
     """InitSt SG (SetSiGex.f), InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
     temperature file, LA rate law, liquid nucleus) through the host program.  The regression inputs (LattGeo / TempStat
@@ -87,7 +87,9 @@ def test_file_driven_case(built, tmp_path, kind):
     g, o = tmp_path / "gpu", tmp_path / "oracle"
     g.mkdir(); o.mkdir()
     box = (96, 96, 120) if kind == "CAD" else (96, 96, 96)
-    if kind.startswith("ST"):                        # InitSt ST (SetTrenchSi.f + SetProbabilityFromField.f): trench, temperature ramp, tabulated rate blocks
+    if kind == "LA-fork":                            # mulskips-source-LaserAnnealing semantics (--la-tree): SiGe melt nucleus, liquid-fraction coupling
+        start = make_la_tree_case(str(tmp_path), box, maxiter=60000)
+    elif kind.startswith("ST"):                      # InitSt ST (SetTrenchSi.f + SetProbabilityFromField.f): trench, temperature ramp, tabulated rate blocks
         box = (96, 48, 144)
         start = make_st_case(str(tmp_path), maxiter=60000, **(dict(ttop=1000.0, tbottom=1000.0) if kind.endswith("fixedT") else {}))
     elif kind == "SiGeBdoped":                       # examples/ex5-CVD-IO/CVD-SiGeBdoped/start.dat: 3 crystal + 2 coverage species, 288 evaporation classes
@@ -99,16 +101,16 @@ def test_file_driven_case(built, tmp_path, kind):
         start = make_cad_case(str(tmp_path), box, maxiter=60000) if kind == "CAD" else make_la_case(str(tmp_path), box, maxiter=3000)   # (the nucleus of this box regrows in ~4000 events)
     for d in (g, o):
         (d / "start.dat").write_text(open(start).read())
-    args = ["--box", *[str(v) for v in box]]
+    args = ["--box", *[str(v) for v in box]] + (["--la-tree"] if kind == "LA-fork" else [])
     _run(ORACLE, o, args)
     _run(EXE, g, args)
     names = ["I00000000.xyz", "I00000001.xyz", "I00000000_d.xyz", "I00000001_d.xyz", "I00000000_v.xyz", "I00000001_v.xyz"]
     for name in names:
         assert (g / name).read_bytes() == (o / name).read_bytes(), f"{kind}: {name} differs from the oracle's"
-    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:"):
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:", "Number of occupied sites"):
         assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
     assert len(open(g / "I00000000.xyz").readlines()) > 50
-    if kind == "LA":                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
+    if kind in ("LA", "LA-fork"):                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
         assert (g / "LattStat.dat").read_bytes() == (o / "LattStat.dat").read_bytes()
 
 
