@@ -23,6 +23,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <netdb.h>
+#include <sys/socket.h>
+#include <unistd.h>
 
 namespace {
 
@@ -65,6 +68,9 @@ struct Host {
   std::vector<double> refPE, refPD, refPA, refPS;         // [ntemp][12288], [ntemp][9], [ntemp][12], [ntemp][12]
   std::vector<int> st_idx;                                // PtransE entries that are non-zero in some block
   bool st() const { return InitSt == "ST"; }
+  // socket-driven run (la/main.f:75-345): geometry a, temperature b (received), phases c, Ge fraction d (sent back); all
+  // INTEGER(LenZ, LenX*LenY) in Fortran order, i.e. element (z, x+LenX*y) at z + LenZ*(x+LenX*y) (la/modules/defsystem.f:88-91)
+  std::vector<int32_t> sock_a, sock_b, sock_c, sock_d;
   // --la-tree: the LaserAnnealing fork (la/main.f:380-520, 592-611, 634-726; la/modules/defsystem.f:36-37,46,82-83)
   bool la_tree = false;
   double Tm_k[3] = {0, 0, 0}, P0_k[3] = {0, 0, 0}, sigma_k[3] = {0, 0, 0}, Tflex_k[3] = {0, 0, 0}, LenSiGe = 0;
@@ -574,20 +580,27 @@ void read_plane(FILE *f, std::vector<double> &buf, const char *what) {
   }
 }
 // initial/SetT.f:25-50: integer kelvin of every cell into bits 9-21 (10 marks a wall cell: left alone)
+// plane z of an array received through the socket (la/initial/SetCAD.f:117, la/initial/SetT.f:42)
+void socket_plane(const Host &H, const std::vector<int32_t> &arr, int z, std::vector<double> &buf) {
+  for (size_t i = 0; i < buf.size(); i++) buf[i] = (double)arr[(size_t)z + (size_t)H.LZ * i];
+}
 void set_T(Host &H) {
-  printf(" Reading input temperature file: %s\n", H.tempfile.c_str());
-  FILE *f = fopen(H.tempfile.c_str(), "r"); if (!f) die(" cannot open %s", H.tempfile.c_str());
+  const bool from_socket = H.tempfile == "None";                // la/initial/SetT.f:34-50
+  FILE *f = nullptr;
+  if (from_socket) { printf(" b(1,1) %d\n Setting temperatures in LattCoo from array received via sockets\n", H.sock_b.empty() ? 0 : H.sock_b[0]); if (H.sock_b.empty()) die(" no temperature array received"); }
+  else { printf(" Reading input temperature file: %s\n", H.tempfile.c_str()); f = fopen(H.tempfile.c_str(), "r"); if (!f) die(" cannot open %s", H.tempfile.c_str()); }
   std::vector<double> buf((size_t)H.LX * H.LY);
   H.t_lo = 1 << 30; H.t_hi = 0;
   for (int z = 0; z < H.LZ; z++) {
+    if (from_socket) socket_plane(H, H.sock_b, z, buf); else
     read_plane(f, buf, "temperature file");
     for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) {
       int t = (int)buf[x + (size_t)H.LX * y];
       if (t != 10) { mvbits(t, LenT, H.L[H.ci(x, y, z)], PosT); if (t > 0) { H.t_lo = std::min(H.t_lo, t); H.t_hi = std::max(H.t_hi, t); } }
     }
   }
-  fclose(f);
-  printf(" Done reading input temperatures file\n");
+  if (f) fclose(f);
+  printf(from_socket ? " Done setting temperatures in LattCoo\n" : " Done reading input temperatures file\n");
 }
 // initial/SetCAD.f:25-421: geometry voxelised offline (0 empty, 1 crystal, 10 wall), one z plane per record; RunType 'C'
 // reads a checkpoint (the lattice words themselves) instead.
@@ -595,7 +608,9 @@ void set_cad(Host &H) {
   int kind, LX = H.LX, LY = H.LY, LZ = H.LZ; const bool la = H.la();
   std::vector<double> buf((size_t)LX * LY);
   if (H.alloy > 0) printf(" Setting up a SiGe layer with fraction = %.17g\n", H.alloy); else printf(" Setting up Silicon\n");
-  FILE *f = fopen(H.cadfile.c_str(), "r"); if (!f) die(" cannot open %s", H.cadfile.c_str());
+  const bool from_socket = H.cadfile == "None" && H.RunType != "C";      // la/initial/SetCAD.f:109
+  FILE *f = from_socket ? nullptr : fopen(H.cadfile.c_str(), "r"); if (!f && !from_socket) die(" cannot open %s", H.cadfile.c_str());
+  if (from_socket && H.sock_a.empty()) die(" no geometry array received");
   if (H.RunType == "C") {                                     // SetCAD.f:54-79
     printf(" Reading checkpoint file %s\n", H.cadfile.c_str());
     for (int z = 0; z < LZ; z++) {
@@ -609,12 +624,14 @@ void set_cad(Host &H) {
     printf(" Done reading checkpoint file\n");
   } else {
     wall_planes(H, 0, 3); wall_planes(H, LZ - 4, LZ - 1);
+    if (from_socket) printf(" a(1,1) %d\n Setting input geometry from sockets\n", H.sock_a[0]); else
     printf(" Reading input geometry file: %s\n", H.cadfile.c_str());
     // SetCAD.f:99-102 skips the records of the four bottom wall planes.  The build that produced the regression
     // goldens did not (file record k lands on z = k+4): MSKC_CAD_NOSKIP=1 selects that legacy offset.
-    if (!getenv("MSKC_CAD_NOSKIP")) for (int z = 0; z <= 3; z++) read_plane(f, buf, "geometry file");
+    if (!from_socket && !getenv("MSKC_CAD_NOSKIP")) for (int z = 0; z <= 3; z++) read_plane(f, buf, "geometry file");
     unsigned long long lcg = 88172645463325252ull;
     for (int z = 4; z <= LZ - 5; z++) {
+      if (from_socket) socket_plane(H, H.sock_a, z, buf); else
       read_plane(f, buf, "geometry file");
       for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
         const int Id = (int)buf[x + (size_t)LX * y];
@@ -648,7 +665,7 @@ void set_cad(Host &H) {
         if (H.la_tree) H.CountCrystal[rr >= H.alloy ? 0 : 1]++;                                                     // la/initial/SetCAD.f:150-155
       }
     }
-    printf(" Done reading input geometry file\n");
+    printf(from_socket ? " Done setting input geometry from sockets\n" : " Done reading input geometry file\n");
     if (H.la_tree) {                                          // la/initial/SetCAD.f:343-351
       const int sum = H.CountCrystal[0] + H.CountCrystal[1] + H.CountCrystal[2];
       for (int k = 0; k < H.NCrystal; k++) {
@@ -659,7 +676,7 @@ void set_cad(Host &H) {
     }
     pass_coordination(H, 0, LZ - 1, 0, LY - 1, 0, LX - 1, true);
   }
-  fclose(f);
+  if (f) fclose(f);
   pass_probability(H, 0, LZ - 1, 0, LY - 1, 0, LX - 1, true, true);
 }
 
@@ -837,10 +854,29 @@ bool box_from_defsystem(const char *exe, int box[3]) {      // the line pymulski
 
 }  // namespace
 
+// la/sockets/sockets.c + fsockets.f: 12-byte headers and INTEGER(4) arrays over a TCP connection to the python server
+struct Wire {
+  int fd = -1;
+  void connect_to(const char *host, int port) {
+    printf("  driver - connecting to host %s\n  on port %d  using an internet socket.\n", host, port);
+    char ps[16]; snprintf(ps, sizeof ps, "%d", port);
+    addrinfo hints{}, *res = nullptr; hints.ai_socktype = SOCK_STREAM; hints.ai_family = AF_INET;
+    if (getaddrinfo(host, ps, &hints, &res) != 0 || !res) die(" Error fetching host data. Wrong host name?");
+    fd = socket(res->ai_family, res->ai_socktype, res->ai_protocol);
+    if (fd < 0 || connect(fd, res->ai_addr, res->ai_addrlen) < 0) die(" Error opening INET socket: wrong port or server unreachable");
+    freeaddrinfo(res);
+  }
+  bool rd(void *p, size_t n) { char *c = (char *)p; while (n) { ssize_t k = read(fd, c, n); if (k <= 0) return false; c += k; n -= (size_t)k; } return true; }
+  void wr(const void *p, size_t n) { const char *c = (const char *)p; while (n) { ssize_t k = write(fd, c, n); if (k <= 0) die(" Error writing to socket: server has quit or connection broke"); c += k; n -= (size_t)k; } }
+  bool get_header(std::string &h) { char b[13]; if (!rd(b, 12)) return false; b[12] = 0; h = b; while (!h.empty() && h.back() == ' ') h.pop_back(); return true; }
+  void put_header(const char *m) { char b[13]; snprintf(b, sizeof b, "%-12s", m); wr(b, 12); }
+};
+
 int main(int argc, char **argv) {
   Host H; Run R;
   int box[3] = {480, 480, 480}; bool parallel = false; double ept = 4.0; int device = 0; const char *start = "start.dat";
   bool have_box = false;
+  const char *sock_host = "localhost"; int sock_port = -1;     // la/main.f:102-131: -h hostname -p port => socket-driven run
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--box") && i + 3 < argc) { box[0] = atoi(argv[i + 1]); box[1] = atoi(argv[i + 2]); box[2] = atoi(argv[i + 3]); i += 3; have_box = true; }
     else if (!strcmp(argv[i], "--parallel")) parallel = true;
@@ -848,11 +884,17 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--events-per-tile") && i + 1 < argc) ept = atof(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
-    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--la-tree] [--device d] [--start file]\n", argv[0]); return 2; }
+    else if (!strcmp(argv[i], "-h") && i + 1 < argc) sock_host = argv[++i];
+    else if (!strcmp(argv[i], "-p") && i + 1 < argc) sock_port = atoi(argv[++i]);
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file]\n", argv[0]); return 2; }
   }
   if (!have_box) { if (const char *e = getenv("MSKC_BOX")) have_box = sscanf(e, "%d %d %d", &box[0], &box[1], &box[2]) == 3; }
   if (!have_box) box_from_defsystem(argv[0], box);
   H.LX = box[0]; H.LY = box[1]; H.LZ = box[2];
+  bool by_time = false;
+  float dev_ms = 0; long long events = 0;
+  // ---- first cycle: input, initial structure, upload (main.f:83-300; la/main.f:348-631 with LAcounter = 0) ----
+  auto init_run = [&]() {
   read_start(H, start);
   H.L.assign((size_t)H.LX * H.LY * (H.LZ + 1), 0);
   H.Tree.assign((size_t)1 << H.Levels, 0.0);
@@ -907,8 +949,10 @@ int main(int argc, char **argv) {
     MS(mskc_set_clock(R.h, 1, 0.0, H.CountCrystal, H.CountCov));
   }
   std::vector<Active>().swap(H.mc); std::vector<Site>().swap(H.bulk); std::vector<Site>().swap(H.voids);
-  const bool by_time = H.ExitStrategy == "Time";
-  float dev_ms = 0; long long events = 0;
+  by_time = H.ExitStrategy == "Time";
+  };
+  // ---- the KMC loop between two calls of the host (main.f:304-371) ----
+  auto kmc_loop = [&]() {
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;
@@ -958,7 +1002,9 @@ int main(int argc, char **argv) {
       if (by_time ? R.Time > H.MaxTime : events >= H.MaxIter) break;
     }
   }
+  };
   // main.f:374-430: final frame, checkpoint, Coor
+  auto finish_run = [&]() {
   write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter : (H.OutMolMol > 0 ? R.IterOut / H.OutMolMol : 0), true);
   if (H.SaveFinalState == "T") {
     printf(" Writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
@@ -968,6 +1014,16 @@ int main(int argc, char **argv) {
     }
     printf(" Done writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
   }
+  if (H.SaveCoo == "T" && H.la_tree && H.coofile == "None") {          // la/main.f:795-817: phases and species go back through the socket
+    printf(" Sending phases and Ge fraction back to LA code \n");
+    H.sock_c.assign((size_t)H.LZ * H.LX * H.LY, 0); H.sock_d.assign((size_t)H.LZ * H.LX * H.LY, 0);
+    for (int z = 0; z < H.LZ; z++) for (int y = 0; y < H.LY; y++) for (int x = 0; x < H.LX; x++) {
+      const int32_t w = H.L[H.ci(x, y, z)]; const size_t k = (size_t)z + (size_t)H.LZ * ((size_t)x + (size_t)H.LX * y);
+      if (ibits(w, PosIndex, LenIndex) == 113) { H.sock_c[k] = 10; H.sock_d[k] = 10; }
+      else if (ibits(w, PosOcc, 1) == 1) { H.sock_c[k] = ibits(w, PosCoor, LenCoor); H.sock_d[k] = ibits(w, PosSiC, LenSiC); }
+    }
+    printf(" Done sending phases and Ge fraction back to LA code \n");
+  } else
   if (H.SaveCoo == "T") {
     printf(" Writing Coor (LA phases) file %s\n", H.coofile.c_str());
     if (FILE *f = fopen(H.coofile.c_str(), "w")) {
@@ -978,6 +1034,72 @@ int main(int argc, char **argv) {
       fclose(f);
     }
     printf(" Done writing Coor (LA phases) file %s\n", H.coofile.c_str());
+  }
+  };
+  if (sock_port < 0) { init_run(); kmc_loop(); finish_run(); }
+  else {
+    // ---- socket-driven run: la/main.f:160-345 (message loop) and :346-852 (one KMC leg per temperature map) ----
+    if (!H.la_tree) die(" mulskips.e (B200 host): the socket loop is the LaserAnnealing fork's: use --la-tree -p port");
+    Wire S; S.connect_to(sock_host, sock_port);
+    const size_t narr = (size_t)H.LZ * H.LX * H.LY;
+    bool isinit = false, phasesready = false, xgeready = false, geoisinit = false, fieldisinit = false;
+    long long LAcounter = 0;
+    auto get_array = [&](bool have, const std::vector<int32_t> &arr, const char *what) {
+      if (!isinit) printf(" Driver not iniliasied.\n");
+      else if (!have) printf(" Driver does not have %s to send\n", what);
+      else { S.put_header("DATAREADY"); printf(" @ message to server: DATAREADY\n"); S.wr(arr.data(), narr * 4); }
+    };
+    while (true) {
+      printf(" Current status: geoisinit, fieldisinit, phasesready, XGeready %c %c %c %c\n", geoisinit ? 'T' : 'F', fieldisinit ? 'T' : 'F', phasesready ? 'T' : 'F', xgeready ? 'T' : 'F');
+      fflush(stdout);
+      std::string header;
+      if (!S.get_header(header)) { printf(" server has quit or connection broke\n"); break; }
+      printf(" @ message from server: %s\n", header.c_str());
+      if (header == "STATUS") {
+        const char *reply = !isinit ? "NEEDINIT" : (phasesready || xgeready) ? "HAVEDATA" : "READY";
+        S.put_header(reply); printf(" @ message to server: %s\n", reply);
+      } else if (header == "INIT") { printf("  Initializing system from server\n"); isinit = true; }
+      else if (header == "SENDGEO" || header == "SENDFIELD") {
+        if (!isinit) printf(" Driver not iniliasied.\n");
+        else if (phasesready || xgeready) printf(" Driver has data to send back to server\n");
+        else {
+          std::vector<int32_t> &dst = header == "SENDGEO" ? H.sock_a : H.sock_b;
+          dst.resize(narr);
+          if (!S.rd(dst.data(), narr * 4)) die(" Error reading from socket: server has quit or connection broke");
+          printf(" Received array from server:\n");
+          (header == "SENDGEO" ? geoisinit : fieldisinit) = true;
+        }
+      }
+      else if (header == "GETGEO") get_array(geoisinit, H.sock_a, "data");
+      else if (header == "GETFIELD") get_array(fieldisinit, H.sock_b, "data");
+      else if (header == "GETPHASES") { get_array(phasesready, H.sock_c, "phases"); if (isinit && phasesready) phasesready = false; }
+      else if (header == "GETXGE") { get_array(xgeready, H.sock_d, "Ge fraction"); if (isinit && xgeready) xgeready = false; }
+      else if (header == "EXIT") break;                        // pymulskips/sockets.py:196-200 (the Fortran driver stops on it as an unexpected header)
+      else { printf("  unexpected header %s\n", header.c_str()); break; }
+      if (!geoisinit || !fieldisinit) continue;                // la/main.f:343
+      printf(" KMC ACTUALLY STARTING NOW: geoisinit, fieldisinit, phasesready, XGeready %c %c %c %c\n", geoisinit ? 'T' : 'F', fieldisinit ? 'T' : 'F', phasesready ? 'T' : 'F', xgeready ? 'T' : 'F');
+      if (LAcounter == 0) init_run();
+      else {
+        // la/main.f:616-631: the new temperature map goes into the lattice words (initial/SetT.f), the rates of the sites
+        // already listed stay as they are until events touch them; clock, iteration and frame counters restart
+        std::vector<int32_t> T(narr); int lo = H.t_lo, hi = H.t_hi;
+        for (size_t i = 0; i < (size_t)H.LX * H.LY; i++) for (int z = 0; z < H.LZ; z++) { const int t = H.sock_b[(size_t)z + (size_t)H.LZ * i]; T[(size_t)z * H.LX * H.LY + i] = t; if (t != 10 && t > 0) { lo = std::min(lo, t); hi = std::max(hi, t); } }
+        printf(" b(1,1) %d\n Setting temperatures in LattCoo from array received via sockets\n", H.sock_b[0]);
+        MS(mskc_set_temperature(R.h, T.data()));
+        printf(" Done setting temperatures in LattCoo\n");
+        mskc_counters c; MS(mskc_get_counters(R.h, &c));
+        if (lo < H.t_lo || hi > H.t_hi) { H.t_lo = lo; H.t_hi = hi; MS(mskc_set_la_fork(R.h, 1, H.Tm_k, H.P0_k, H.sigma_k, H.Tflex_k, H.t_lo, H.t_hi, H.InitCountCrystal, H.NumOcc0, c.num_adatom_occ)); }
+        MS(mskc_set_clock(R.h, 1, 0.0, c.CountCrystal, c.CountCov));
+        R.Iter = 1; R.IterOut = 0; R.framecounter = 0; R.Time = 0.0;
+        R.NumAtoms = c.num_atoms; R.NumVoids = c.num_voids; R.NumAdAtom = c.num_adatom;
+        printf(" Atoms,Voids,AdAtoms,AdAtomsOcc %d %d %d %d\n", c.num_atoms, c.num_voids, c.num_adatom, c.num_adatom_occ);
+        for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = c.CountCrystal[i];
+        write_frame(H, R, 0.0, 0, 0, true);
+      }
+      kmc_loop();
+      finish_run();
+      fieldisinit = false; phasesready = true; xgeready = true; LAcounter++;
+    }
   }
   fprintf(stderr, "mulskips.e (B200): %lld events, %.1f ms on the device = %.4g events/s (%s mode)\n", events, dev_ms, dev_ms > 0 ? events / (dev_ms * 1e-3) : 0.0, parallel ? "sublattice-sampler" : "serial-parity");
   mskc_destroy(R.h);

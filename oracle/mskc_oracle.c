@@ -1907,6 +1907,19 @@ void orc_get_fork(Orc *o, int32_t iv[10], double dv[12]) {
   iv[0] = o->la_tree; iv[1] = o->NumAdAtomOcc; iv[2] = o->NumOcc0; iv[3] = o->NumOcc1;
   for (int k = 0; k < 3; k++) { iv[4 + k] = o->InitCountCrystal[k]; iv[7 + k] = o->CountLiquid[k]; dv[k] = o->Tm_k[k]; dv[3 + k] = o->P0_k[k]; dv[6 + k] = o->sigma_k[k]; dv[9 + k] = o->Tflex_k[k]; }
 }
+/* la/main.f:616-631 -- the second and later legs of a socket-driven run: a new temperature map is written into the
+ * lattice words (la/initial/SetT.f:36-50, T[z][x+LenX*y], 10 = wall left alone), nothing is re-rated, the clock and the
+ * iteration / frame counters restart and frame 0 is written again */
+void orc_next_leg(Orc *o, const int32_t *T) {
+  for (int z = 0; z < o->LenZ; z++) for (int y = 0; y < o->LenY; y++) for (int x = 0; x < o->LenX; x++) {
+    int t = T[(size_t)z * o->LenX * o->LenY + x + (size_t)o->LenX * y];
+    if (t != 10) MVBITS(t, ORC_LenT, &o->LattCoo[CI(o, x, y, z)], ORC_PosT);
+  }
+  o->Time = 0.0; o->Iter = 1; o->IterOut = 0; o->framecounter = 0; o->done = 0;
+  LOG(o, " Atoms,Voids,AdAtoms,AdAtomsOcc %d %d %d %d\n", o->NumAtoms, o->NumVoids, o->NumAdAtom, o->NumAdAtomOcc);
+  for (int i = 0; i < 3; i++) o->CountCrystalOld[i] = o->CountCrystal[i];
+  orc_write_frame(o, o->Time, o->IterOut, o->framecounter);
+}
 /* test hook: lower the stop threshold of la/main.f:714-723 so that the rule fires while the melt is still rich */
 void orc_set_numocc0(Orc *o, int v) { o->NumOcc0 = v; }
 void orc_get_species(Orc *o, int32_t out[8]) {

@@ -161,7 +161,8 @@ def make_st_case(dirpath, lens=(20, 45, 90), angle=54.7, ttop=1080.0, tbottom=92
     return dst
 
 
-def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sige=True, tbase=1480, homogeneous="F", fraction=0.3, lensige=25.0):
+def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sige=True, tbase=1480, homogeneous="F", fraction=0.3, lensige=25.0,
+                      sockets=False):
     """A laser-annealing case for the LaserAnnealing fork (mulskips-source-LaserAnnealing/main.f:380-520 grammar): one
     Tm / P0 / sigma / Tflex value per crystal species, Si(1-x)Ge(x) with the Ge-fraction and SiGe-thickness lines, the
     18-line two-species evaporation table (energies per bond: Si 0.96 eV, Ge 0.70 eV) and 6 deposition lines.  Geometry
@@ -178,6 +179,8 @@ def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sig
         for z in range(lz):
             f.write(" ".join(str(v) for v in (tbase + rng.integers(0, 7, lx * ly))) + "\n")
     ncry = 2 if sige else 1
+    if sockets:          # geometry, temperature and phases travel through the socket (la/main.f:160-345): the three paths are 'None'
+        geo = tmp = "None"
     L = [f"{ncry} 0 ! NCrystal NCov", "14 32 ! crystal species" if sige else "14 ! crystal species", "LA ! InitSt", geo, tmp,
          ("1688 1210" if sige else "1688") + " ! Tm", ("1.33e17 2.596e16" if sige else "1.33e17") + " ! P0",
          ("280 210" if sige else "280") + " ! sigma", ("1080 900" if sige else "1080") + " ! Tflex",
@@ -185,7 +188,7 @@ def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sig
     if sige:
         L += [f"{fraction} ! Ge fraction", f"{lensige} ! LenSiGe"]
     L += ["1.0 ! PtransZig", "0.4525 ! sf", "Iter", f"{maxiter} ! IterMax", f"{maxiter} ! OutMolMol", "R ! RunType", "9117116 ! IDUM",
-          "F ! Save final state", "T ! Save final Coor", "LattStat.dat"]
+          "F ! Save final state", "T ! Save final Coor", "None" if sockets else "LattStat.dat"]
     e = {1: 0.96, 2: 0.70}
     if sige:
         for sp in (1, 2):

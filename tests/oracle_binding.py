@@ -57,6 +57,7 @@ def load_oracle():
     lib.orc_get_fork.argtypes = [vp, C.c_void_p, C.c_void_p]
     lib.orc_set_variant.argtypes = [vp, C.c_int]
     lib.orc_set_numocc0.argtypes = [vp, C.c_int]
+    lib.orc_next_leg.argtypes = [vp, C.c_void_p]
     lib.orc_get_run.argtypes = [vp, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
     lib.orc_get_rng.argtypes = [vp, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.orc_get_counts.argtypes = [vp, C.c_void_p, C.c_void_p]
@@ -167,6 +168,12 @@ class Oracle:
         rt, E, D, A, S = np.zeros(n, np.int32), np.zeros((n, 12288)), np.zeros((n, 9)), np.zeros((n, 12)), np.zeros((n, 12))
         self.lib.orc_get_field(self.o, info.ctypes.data, rt.ctypes.data, E.ctypes.data, D.ctypes.data, A.ctypes.data, S.ctypes.data)
         return dict(ntemp=n, fixedT=int(info[1]), Ttop=int(info[2]), reftemp=rt, refPE=E, refPD=D, refPAbs=A, refPDes=S)
+
+    def next_leg(self, T):
+        """second and later legs of a socket-driven laser-annealing run (la/main.f:616-631): T is [LenZ][LenY*LenX] int32"""
+        T = np.ascontiguousarray(T, dtype=np.int32)
+        assert T.size == self.LenZ * self.LenY * self.LenX
+        self.lib.orc_next_leg(self.o, T.ctypes.data)
 
     def set_numocc0(self, v):
         self.lib.orc_set_numocc0(self.o, int(v))

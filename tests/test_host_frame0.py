@@ -52,3 +52,51 @@ def test_frame0_and_startup_log(tmp_path, kind):
     for key in ("Atoms,Voids,AdAtoms", "maxElines", "Temperature on top", "Reading input probability table", "Initial number of occupied sites (before",
                 "Initial CountCrystal (before", "Initial CountLiquid", "Initial number of liquid sites", "CountLiquid", "xLiquid"):
         assert _tokens(logs[g], key) == _tokens(logs[o], key), key
+
+
+def test_socket_handshake_and_first_frame(tmp_path):
+    """The laser-annealing socket loop (mulskips-source-LaserAnnealing/main.f:160-345): the driver connects, answers
+    STATUS with NEEDINIT / READY, takes the geometry and temperature arrays, and builds the same initial structure as
+    the file-driven run (frame 0 equal to the oracle's).  Without a GPU it stops when it asks the CUDA library for a
+    device; with one it runs the single event allowed here and reports HAVEDATA."""
+    import numpy as np
+    from la_socket_server import Server
+    box = (96, 96, 96)
+    g, o = tmp_path / "host", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    twin = make_la_tree_case(str(o), box=box, maxiter=1)                      # file-driven twin for the oracle
+    start = make_la_tree_case(str(g), box=box, maxiter=1, sockets=True)
+    geo = np.loadtxt(o / "LattGeo.dat", dtype=np.int32)                        # [LenZ][LenX*LenY]
+    tmp = np.loadtxt(o / "TempStat.dat", dtype=np.int32)
+    r = subprocess.run([ORACLE, "--la-tree", "--box", *[str(v) for v in box]], cwd=o, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-800:]
+    srv = Server((box[2], box[0] * box[1]), timeout=60.0)
+    out = open(g / "log.txt", "w")
+    p = subprocess.Popen([EXE, "--la-tree", "-p", str(srv.port), "--box", *[str(v) for v in box]], cwd=g, stdout=out, stderr=subprocess.STDOUT)
+    try:
+        srv.accept()
+        assert srv.status() == "NEEDINIT"
+        srv.init()
+        assert srv.status() == "READY"
+        srv.send("geo", geo)
+        assert srv.status() == "READY"
+        srv.send("field", tmp)
+        try:                                   # GPU present: one event, then the phases are on offer
+            if srv.wait_status("HAVEDATA") == "HAVEDATA":
+                c = srv.get("phases")
+                assert c.shape == (box[2], box[0] * box[1]) and c.max() == 10
+            srv.exit()
+        except (ConnectionError, OSError):
+            pass                               # no GPU: the driver stopped at mskc_create, after frame 0
+        p.wait(timeout=120)
+    finally:
+        srv.close()
+        if p.poll() is None:
+            p.kill()
+        out.close()
+    log = (g / "log.txt").read_text()
+    assert "@ message to server: NEEDINIT" in log and "Setting input geometry from sockets" in log
+    for name in ("I00000000.xyz", "I00000000_v.xyz"):
+        assert (g / name).read_bytes() == (o / name).read_bytes(), name
+    for key in ("Atoms,Voids,AdAtoms", "Initial number of occupied sites (before", "Initial CountLiquid"):
+        assert _tokens(log, key) == _tokens(r.stdout, key), key

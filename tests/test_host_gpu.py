@@ -147,3 +147,67 @@ def test_checkpoint_restart(built, tmp_path):
         assert (out["gpu"][1] / name).read_bytes() == (out["oracle"][1] / name).read_bytes(), name
     for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "Max temperature is:"):
         assert _tokens(out["gpu"][1] / "log.txt", key) == _tokens(out["oracle"][1] / "log.txt", key), key
+
+
+def test_socket_driven_laser_annealing(built, tmp_path):
+    """The LaserAnnealing fork end to end: the host program as socket client of a server that speaks the
+    protocol of pymulskips/sockets.py.  Leg 1: geometry + temperature arrive through the socket, 30 000 events, phases
+    (coordination of every occupied cell, 10 = wall) and species go back.  Leg 2: a new, colder temperature map; the
+    lattice keeps its listed rates until events touch them (la/main.f:616-631), clock and frame counters restart.
+    Checked against the oracle driven through the same two legs: phases, species map and the frames of both legs."""
+    import numpy as np
+    from la_socket_server import Server
+    from oracle_binding import Oracle
+    box = (96, 96, 96)
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    twin = make_la_tree_case(str(o), box=box, maxiter=30000)
+    make_la_tree_case(str(g), box=box, maxiter=30000, sockets=True)
+    geo = np.loadtxt(o / "LattGeo.dat", dtype=np.int32)
+    t1 = np.loadtxt(o / "TempStat.dat", dtype=np.int32)
+    t2 = t1 - 25
+    orc = Oracle(*box, twin, la_tree=True, outdir=str(o), write_files=True)
+    orc.setup()
+
+    def phases(L):                                   # la/main.f:795-817
+        L = L[:-1].astype(np.int64)
+        wall = (L & 255) == 113
+        occ = ((L >> 23) & 1) == 1
+        c = np.where(wall, 10, np.where(occ, (L >> 24) & 7, 0))
+        d = np.where(wall, 10, np.where(occ, (L >> 28) & 3, 0))
+        return c.reshape(box[2], -1).astype(np.int32), d.reshape(box[2], -1).astype(np.int32)
+
+    srv = Server((box[2], box[0] * box[1]), timeout=240.0)
+    out = open(g / "log.txt", "w")
+    p = subprocess.Popen([EXE, "--la-tree", "-p", str(srv.port), "--box", *[str(v) for v in box]], cwd=g, stdout=out, stderr=subprocess.STDOUT)
+    try:
+        srv.accept()
+        assert srv.status() == "NEEDINIT"
+        srv.init()
+        srv.send("geo", geo)
+        srv.send("field", t1)
+        srv.wait_status("HAVEDATA")
+        c1, d1 = srv.get("phases"), srv.get("xge")
+        orc.run(10**9); orc.finish()
+        ec1, ed1 = phases(orc.lattcoo())
+        assert np.array_equal(c1, ec1) and np.array_equal(d1, ed1)
+        frame1 = (g / "I00000001.xyz").read_bytes()
+        assert frame1 == (o / "I00000001.xyz").read_bytes()
+        assert srv.status() == "READY"
+        srv.send("field", t2)
+        srv.wait_status("HAVEDATA")
+        c2, d2 = srv.get("phases"), srv.get("xge")
+        orc.next_leg(t2)
+        orc.run(10**9); orc.finish()
+        ec2, ed2 = phases(orc.lattcoo())
+        assert np.array_equal(c2, ec2) and np.array_equal(d2, ed2)
+        assert not np.array_equal(c1, c2)
+        assert (g / "I00000001.xyz").read_bytes() == (o / "I00000001.xyz").read_bytes() != frame1
+        srv.exit()
+        assert p.wait(timeout=60) == 0
+    finally:
+        srv.close()
+        if p.poll() is None:
+            p.kill()
+        out.close()
+    orc.close()
