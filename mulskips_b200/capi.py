@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "lib", "libmskc.so")
+    # MSKC_LIB: an A/B build of the same library (scripts/probe_*.py); the default is the in-tree build
+    return os.environ.get("MSKC_LIB") or os.path.join(_HERE, "lib", "libmskc.so")
 
 
 class MskcError(RuntimeError):

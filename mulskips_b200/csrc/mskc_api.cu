@@ -597,6 +597,7 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   ParityArgs A{};
   A.max_iter = a->max_iter; A.out_every = a->out_every; A.framecounter = a->framecounter; A.max_time = a->max_time; A.out_time = a->out_time;
   A.exit_on_time = a->exit_on_time;
+  CK(cudaFuncSetAttribute(parity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParShared)));
   // The kernel is launched in slices so that a single launch stays well below any watchdog.
   const long long slice = 2000000;
   long long remaining = a->event_budget > 0 ? a->event_budget : -1;
@@ -605,7 +606,7 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   while (true) {
     A.event_budget = (remaining < 0 || remaining > slice) ? slice : remaining;
     CK(cudaEventRecord(h->ev0, h->stream));
-    parity_kernel<<<1, 32, 0, h->stream>>>(A);
+    parity_kernel<<<1, 32, sizeof(ParShared), h->stream>>>(A);
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_ps, h->d_ps, sizeof(ParityState), cudaMemcpyDeviceToHost, h->stream));

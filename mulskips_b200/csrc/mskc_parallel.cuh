@@ -155,8 +155,16 @@ struct TileLists {
   }
 };
 
-enum { CS_THREADS = 128, CS_MINB = 4 };
-enum { CS_COMPACT_ABOVE = 96 };
+// tuning knobs (overridable at compile time for A/B builds): resident blocks per SM the register allocation aims at,
+// and the list length above which a tile drops its tombstones when it loads its list
+#ifndef MSKC_CS_MINB
+#define MSKC_CS_MINB 4
+#endif
+#ifndef MSKC_COMPACT_ABOVE
+#define MSKC_COMPACT_ABOVE 96
+#endif
+enum { CS_THREADS = 128, CS_MINB = MSKC_CS_MINB };
+enum { CS_COMPACT_ABOVE = MSKC_COMPACT_ABOVE };
 #define CS_BURST 4.0                          /* a state expected to fire more than CS_BURST*cap events per quantum is transient */
 #define CS_MAX_LAG 6.0                        /* quanta of debt beyond which a tile's event cap is lifted */               // tombstones are dropped when a list is loaded with more entries than this
 
@@ -795,7 +803,10 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
   return 0;
 }
-static const int TILE_CAP = 192;
+#ifndef MSKC_TILE_CAP
+#define MSKC_TILE_CAP 192
+#endif
+static const int TILE_CAP = MSKC_TILE_CAP;
 
 // per-sweep totals: local sums, all-reduce over the ranks of a slab run, then clock / tau / global-coupling terms
 static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, double tau_fixed, int advance, int *launches, std::string *err) {
@@ -896,7 +907,8 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   if (teamsz != 8 && teamsz != 32) teamsz = 8;
   const int tpb = CS_THREADS / teamsz;
   const int blocks = (ntc + tpb - 1) / tpb;
-  const size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
+  size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
+  if (const char *e = getenv("MSKC_SMEM_PAD")) smem += (size_t)atoi(e);      // diagnostic: fewer resident blocks per SM
   const int feat = (H.NCov > 0 ? F_COV : 0) | (H.la ? F_LA : 0);
   // the kernel is instantiated per feature set so that a PVD run does not carry coverage / LA code in its hot loop
   typedef void (*cs_kernel_t)(int, uint2, int);

@@ -42,6 +42,18 @@ struct ParityView {
 };
 __constant__ ParityView PV;
 
+// The single thread that walks the loop keeps what it touches on every event on chip: the top 13 levels of the rate
+// tree (nodes 1..8191, 64 KB; the descent of PickTreeEvent.f and the re-sums of UpdateTree.f are chains of dependent
+// loads) and the state of ran3.  While the loop runs the mirrored nodes live in shared memory only; all 32 lanes load
+// the mirror at the start of a launch and write it back at its end, so downloads and the next launch see the
+// complete tree in global memory.
+enum { PAR_TOP = 8192 };
+struct ParShared { double top[PAR_TOP]; int ma[56]; int inext, inextp, iff, idum; };
+extern __shared__ __align__(16) unsigned char par_smem[];
+__device__ __forceinline__ ParShared &PSH() { return *reinterpret_cast<ParShared *>(par_smem); }
+__device__ __forceinline__ double tree_ld(int i) { return i < PAR_TOP ? PSH().top[i] : PV.Tree[i]; }
+__device__ __forceinline__ void tree_st(int i, double v) { if (i < PAR_TOP) PSH().top[i] = v; else PV.Tree[i] = v; }
+
 struct ParityPol {
   int NumAdAtom, NumAtoms, NumVoids;
   int CountCrystal[3], CountCov[3];
@@ -49,27 +61,27 @@ struct ParityPol {
   long long n_getprob, n_ran3;
 
   __device__ __forceinline__ bool predraw() const { return true; }
-  __device__ __forceinline__ double tree_root() const { return PV.Tree[1]; }
+  __device__ __forceinline__ double tree_root() const { return PSH().top[1]; }
 
   // mcevent/random.f:22-69
   __device__ __noinline__ double uniform() {
     const int mbig = 1000000000, mseed = 161803398, mz = 0;
     const double fac = (double)(1.0f / 1.0e9f);
-    ParityState &s = *PV.ps;
-    int *ma = s.r_ma, mj, mk;
+    ParShared &s = PSH();
+    int *ma = s.ma, mj, mk;
     n_ran3++;
-    if (s.idum < 0 || s.r_iff == 0) {
-      s.r_iff = 1;
+    if (s.idum < 0 || s.iff == 0) {
+      s.iff = 1;
       mj = mseed - abs(s.idum); mj = mj % mbig; ma[55] = mj; mk = 1;
       for (int i = 1; i <= 54; i++) { int ii = (21 * i) % 55; ma[ii] = mk; mk = mj - mk; if (mk < mz) mk += mbig; mj = ma[ii]; }
       for (int k = 1; k <= 4; k++) for (int i = 1; i <= 55; i++) { ma[i] = ma[i] - ma[1 + (i + 30) % 55]; if (ma[i] < mz) ma[i] += mbig; }
-      s.r_inext = 0; s.r_inextp = 31; s.idum = 1;
+      s.inext = 0; s.inextp = 31; s.idum = 1;
     }
-    if (++s.r_inext == 56) s.r_inext = 1;
-    if (++s.r_inextp == 56) s.r_inextp = 1;
-    mj = ma[s.r_inext] - ma[s.r_inextp];
+    if (++s.inext == 56) s.inext = 1;
+    if (++s.inextp == 56) s.inextp = 1;
+    mj = ma[s.inext] - ma[s.inextp];
     if (mj < mz) mj += mbig;
-    ma[s.r_inext] = mj;
+    ma[s.inext] = mj;
     return mj * fac;
   }
 
@@ -79,16 +91,23 @@ struct ParityPol {
     if (P == 0 && Index < NumAdAtom) { fail(E_TREE_ZERO, Index); return; }
     if (Index > NumAdAtom) { fail(E_TREE_IDX, Index, NumAdAtom); return; }
     int Pos = Index + PV.leaf0 - 1;
-    double sib[24];
-    int nlev = PV.Levels - 1;
+    const int nlev = PV.Levels - 1;
+    // levels below the mirror (global memory): ng of them, at most 11 (Levels <= 24); the sibling loads are
+    // independent and issued together
+    const int ng = nlev > 12 ? nlev - 12 : 0;              // nodes Pos >> l with l < ng have index >= PAR_TOP
+    double sib[11];
 #pragma unroll
-    for (int l = 0; l < 24; l++) if (l < nlev) sib[l] = PV.Tree[(Pos >> l) ^ 1];
-    PV.Tree[Pos] = P;
+    for (int l = 0; l < 11; l++) if (l < ng) sib[l] = PV.Tree[(Pos >> l) ^ 1];
+    tree_st(Pos, P);
     double v = P;
 #pragma unroll
-    for (int l = 0; l < 24; l++) if (l < nlev) { v = v + sib[l]; PV.Tree[Pos >> (l + 1)] = v; }
+    for (int l = 0; l < 11; l++) if (l < ng) { v = v + sib[l]; tree_st(Pos >> (l + 1), v); }
+    // mirrored levels: shared memory only
+    double *top = PSH().top;
+#pragma unroll 1
+    for (int l = ng; l < nlev; l++) { v = v + top[(Pos >> l) ^ 1]; top[Pos >> (l + 1)] = v; }
   }
-  __device__ __forceinline__ double leaf(int Index) const { return PV.Tree[Index + PV.leaf0 - 1]; }
+  __device__ __forceinline__ double leaf(int Index) const { return tree_ld(Index + PV.leaf0 - 1); }
 
   // mcevent/Add.f:24-53
   __device__ __noinline__ void add_mc(P3 s, long long c, const P3 nn[4], int ev, double p) {
@@ -157,11 +176,31 @@ struct ParityPol {
   }
 };
 
+__device__ void parity_loop(const ParityArgs &A);
 // mcevent/PickTreeEvent.f:25-70 + main.f:304-371
 __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ParityPol pol;
+  if (blockIdx.x != 0) return;
   ParityState &S = *PV.ps;
+  {                                               // fill the on-chip mirror (all 32 lanes), then lane 0 walks the loop alone
+    ParShared &sh = PSH();
+    const int ntop = min((int)PAR_TOP, 1 << PV.Levels);
+    for (int i = threadIdx.x; i < ntop; i += 32) sh.top[i] = PV.Tree[i];
+    for (int i = threadIdx.x; i < 56; i += 32) sh.ma[i] = S.r_ma[i];
+    if (threadIdx.x == 0) { sh.inext = S.r_inext; sh.inextp = S.r_inextp; sh.iff = S.r_iff; sh.idum = S.idum; }
+    __syncwarp();
+  }
+  if (threadIdx.x == 0) parity_loop(A);
+  __syncwarp();
+  {                                               // write the mirror back
+    const ParShared &sh = PSH();
+    const int ntop = min((int)PAR_TOP, 1 << PV.Levels);
+    for (int i = 1 + threadIdx.x; i < ntop; i += 32) PV.Tree[i] = sh.top[i];
+  }
+}
+
+__device__ __noinline__ void parity_loop(const ParityArgs &A) {
+  ParityState &S = *PV.ps;
+  ParityPol pol;
   pol.NumAdAtom = S.NumAdAtom; pol.NumAtoms = S.NumAtoms; pol.NumVoids = S.NumVoids;
   for (int i = 0; i < 3; i++) { pol.CountCrystal[i] = S.CountCrystal[i]; pol.CountCov[i] = S.CountCov[i]; }
   pol.n_getprob = 0; pol.n_ran3 = 0;
@@ -172,6 +211,9 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
   long long framecounter = A.framecounter;
   int stop = 0;
   const int nlev = PV.Levels - 1;
+  const int runtype = S.runtype;
+  long long counter = S.counter;
+  int nli = (int)(counter % 1000);                 // numberslist cursor: index mod(counter-1,1000)+1 of the NEXT draw (PickTreeEvent.f:44)
   while (true) {
     int Ind, Itrans;
     if (S.pending) { Ind = S.pend_ind; Itrans = S.pend_itrans; S.pending = 0; }
@@ -184,17 +226,22 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
       }
       if (pol.NumAdAtom <= 20) { stop = 4; break; }
       int idx = 1;
+      const double root = PSH().top[1];
+      double node = root;                          // Tree(idx): the child taken at the previous level, already loaded
       for (int lev = 0; lev < nlev; lev++) {
         double r;
-        if (S.runtype == 'T') { S.counter++; r = (double)NUMBERSLIST[(S.counter - 1) % 1000]; }
+        if (runtype == 'T') { counter++; r = (double)NUMBERSLIST[nli]; nli = nli == 999 ? 0 : nli + 1; }
         else r = pol.uniform();
-        double Patom = r * PV.Tree[idx];
+        const double Patom = r * node;
         idx <<= 1;
-        if (PV.Tree[idx] < Patom) idx++;
+        double left, right;                        // Tree(2i), Tree(2i+1): one 16-byte load below the mirrored levels
+        if (idx < PAR_TOP) { left = PSH().top[idx]; right = PSH().top[idx + 1]; }
+        else { const double2 ch = *reinterpret_cast<const double2 *>(&PV.Tree[idx]); left = ch.x; right = ch.y; }
+        if (left < Patom) { idx++; node = right; } else node = left;
       }
       Ind = idx - PV.leaf0 + 1;
       if (Ind > pol.NumAdAtom) { fail(E_PICK, Ind, pol.NumAdAtom); stop = -1; break; }
-      Time = Time + 1.0 / PV.Tree[1];
+      Time = Time + 1.0 / root;
       Itrans = PV.mc_ev[Ind];
       P3 s = cell_xyz((long long)PV.mc_cell[Ind]);
       S.last_site[0] = s.x; S.last_site[1] = s.y; S.last_site[2] = s.z;
@@ -214,7 +261,8 @@ __global__ void __launch_bounds__(32, 1) parity_kernel(ParityArgs A) {
     else if (Time > A.max_time) { stop = 2; break; }
     if (fork && pol.NumAtoms + pol.NumAdAtomOcc > S.NumOcc0) { stop = 5; break; }       // la/main.f:714-723
   }
-  S.Iter = Iter; S.Time = Time; S.framecounter = framecounter;
+  S.Iter = Iter; S.Time = Time; S.framecounter = framecounter; S.counter = counter;
+  { const ParShared &sh = PSH(); for (int i = 0; i < 56; i++) S.r_ma[i] = sh.ma[i]; S.r_inext = sh.inext; S.r_inextp = sh.inextp; S.r_iff = sh.iff; S.idum = sh.idum; }
   S.NumAdAtom = pol.NumAdAtom; S.NumAtoms = pol.NumAtoms; S.NumVoids = pol.NumVoids; S.NumAdAtomOcc = pol.NumAdAtomOcc;
   for (int i = 0; i < 3; i++) { S.CountCrystal[i] = pol.CountCrystal[i]; S.CountCov[i] = pol.CountCov[i]; }
   S.events_done = done; S.site_updates = pol.n_getprob;
