@@ -1286,7 +1286,7 @@ static inline void occupy(Orc *o, int x, int y, int z, int kind, int two_species
 }
 
 /* src/initial/SetNC.f:25-235 (sphere=0) and SetNCSp.f (sphere=1) */
-static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere) {
+static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere, int two_species) {
   int kind, LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
   if (!sphere) { LOG(o, " %d %d\n", LZ / 2 - Len3 / 2, LZ / 2 + Len3 / 2 + 1); LOG(o, " %d %d\n", LX / 2 - Len1 / 2, LX / 2 + Len1 / 2 + 1); }
   for (int z = LZ / 2 - Len3 / 2; z <= LZ / 2 + Len3 / 2 - 1; z++)
@@ -1296,7 +1296,7 @@ static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere) {
           int d2 = (x - LX / 2) * (x - LX / 2) + (y - LY / 2) * (y - LY / 2) + (z - LZ / 2) * (z - LZ / 2);
           if (d2 > Len1 * Len1 / 4) continue;
         }
-        if (is_cubic_site(x, y, z, &kind)) occupy(o, x, y, z, kind, 1);
+        if (is_cubic_site(x, y, z, &kind)) occupy(o, x, y, z, kind, two_species);
       }
   pass_coordination(o, LZ / 2 - Len3 / 2 - 10, LZ / 2 + Len3 / 2 + 9, LY / 2 - Len2 / 2 - 10, LY / 2 + Len2 / 2 + 9,
                     LX / 2 - Len1 / 2 - 10, LX / 2 + Len1 / 2 + 9, 0);
@@ -1304,14 +1304,16 @@ static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere) {
                    LX / 2 - Len1 / 2 - 10, LX / 2 + Len1 / 2 + 9, 0, 0);
 }
 
-/* src/initial/SetInvPOff.f:22-286 */
-static void set_invp_off(Orc *o, int Len, int Len3) {
+/* src/initial/SetInvPOff.f:22-286 (only = 0: Si/C sublattices, pyramid faces with the REAL(4) slope 1.10), and its
+ * single-species twins SetInvPSi.f (only = 1: Si on both sublattices) and SetInvPC.f (only = 2: C on both), whose
+ * pyramid test is the all-integer ABS(x-..)+ABS(y-..)-(z-Len3) <= Len */
+static void set_invp_off(Orc *o, int Len, int Len3, int only) {
   int kind, LX = o->LenX, LY = o->LenY; int32_t Site[3], NextN[4][3];
   int Lenh = LX / 2 - 1;
   LOG(o, " %d %d %d\n", Lenh, Len, Len3);
   for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
     if (is_cubic_site(x, y, z, &kind)) {
-      occupy(o, x, y, z, kind, 1);
+      occupy(o, x, y, z, only == 2 ? 1 : kind, only != 1);
       MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
       Site[0] = x; Site[1] = y; Site[2] = z;
       dia_nn(o, x, y, z, kind, NextN);
@@ -1323,13 +1325,13 @@ static void set_invp_off(Orc *o, int Len, int Len3) {
     if ((x1 % 2) != (y1 % 2) || (x1 % 2) != (z1 % 2)) continue;
     /* mixed INTEGER/REAL(4) expression of SetInvPOff.f:78-82: 1.10 is REAL(4) */
     float zt = 1.10f * (float)(z - Len3);
-#define PYR(ax, ay) (((float)(abs(ax) + abs(ay)) - zt) <= (float)Len)
+#define PYR(ax, ay) (only ? (abs(ax) + abs(ay) - (z - Len3)) <= Len : ((float)(abs(ax) + abs(ay)) - zt) <= (float)Len)
     int inside = PYR(x - Lenh, y - Lenh) || PYR(x, y) || PYR(x - LX, y) || PYR(x, y - LY) || PYR(x - LX, y - LY);
 #undef PYR
     if (!inside) {
       int m = (x1 + y1 + z1) % 4;
-      if (m == 0) occupy(o, x, y, z, 0, 1);
-      else if (m == 3) occupy(o, x, y, z, 1, 1);
+      if (m == 0) occupy(o, x, y, z, only == 2 ? 1 : 0, only != 1);
+      else if (m == 3) occupy(o, x, y, z, 1, only != 1);
     }
   }
   pass_coordination(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0);
@@ -1350,6 +1352,28 @@ static void set_finfet(Orc *o, int Len, int Lenww, int Lenwwtop, int Laperture) 
   }
   pass_coordination(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1);
   pass_probability(o, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, 1, 0);
+}
+
+/* src/initial/SetTrench.f:22-283 (InitSt 'T'): 3C-SiC slab up to Len3 with a rectangular trench of half-width Len between
+ * Len2 and Len3, no walls, bulk up to z=20 */
+static void set_trench(Orc *o, int Len, int Len2, int Len3) {
+  int kind, LX = o->LenX, LY = o->LenY; int32_t Site[3], NextN[4][3];
+  int Lenh = LX / 2 - 1;
+  LOG(o, " %d %d %d\n", Lenh, Len, Len3);
+  for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (is_cubic_site(x, y, z, &kind)) {
+      occupy(o, x, y, z, kind, 1);
+      MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    if (!(abs(x - Lenh) <= Len && z > Len2 && z < Len3)) occupy(o, x, y, z, kind, 1);
+  }
+  pass_coordination(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0);
+  pass_probability(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0, 0);
 }
 
 /* src/initial/SetTrenchSi.f:22-338 (InitSt 'ST'): temperature ramp along z written into the lattice words, wall
@@ -1509,9 +1533,13 @@ int orc_setup(Orc *o) {
   if (!strcmp(s, "F")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 0, 1); }
   else if (!strcmp(s, "FS")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 0); }
   else if (!strcmp(s, "SG")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 2); }
-  else if (!strcmp(s, "C")) set_nc(o, o->Len1, o->Len2, o->Len3, 0);
-  else if (!strcmp(s, "S")) set_nc(o, o->Len1, o->Len1, o->Len1, 1);
-  else if (!strcmp(s, "I")) set_invp_off(o, o->Len1, o->Len2);
+  else if (!strcmp(s, "C")) set_nc(o, o->Len1, o->Len2, o->Len3, 0, 1);
+  else if (!strcmp(s, "S")) set_nc(o, o->Len1, o->Len1, o->Len1, 1, 1);
+  else if (!strcmp(s, "SS")) set_nc(o, o->Len1, o->Len1, o->Len1, 1, 0);      /* SetNCSpSi.f: the sphere of SetNCSp.f in pure Si */
+  else if (!strcmp(s, "I")) set_invp_off(o, o->Len1, o->Len2, 0);
+  else if (!strcmp(s, "D")) set_invp_off(o, o->Len1, o->Len2, 2);             /* SetInvPC.f */
+  else if (!strcmp(s, "Z")) set_invp_off(o, o->Len1, o->Len2, 1);             /* SetInvPSi.f */
+  else if (!strcmp(s, "T")) set_trench(o, o->Len1, o->Len2, o->Len3);         /* SetTrench.f */
   else if (!strcmp(s, "FF")) {
     o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;
     set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
