@@ -486,14 +486,14 @@ void pass_probability(Host &H, int z0, int z1, int y0, int y1, int x0, int x1, b
   }
 }
 // initial/SetNC.f:25-235 (parallelepiped) and initial/SetNCSp.f (sphere) of 3C-SiC in the box centre
-void set_nc(Host &H, int Len1, int Len2, int Len3, bool sphere) {
+void set_nc(Host &H, int Len1, int Len2, int Len3, bool sphere, bool two_species = true) {      // two_species = false: SetNCSpSi.f
   int kind, LX = H.LX, LY = H.LY, LZ = H.LZ;
   if (!sphere) { printf(" %d %d\n", LZ / 2 - Len3 / 2, LZ / 2 + Len3 / 2 + 1); printf(" %d %d\n", LX / 2 - Len1 / 2, LX / 2 + Len1 / 2 + 1); }
   for (int z = LZ / 2 - Len3 / 2; z <= LZ / 2 + Len3 / 2 - 1; z++)
     for (int y = LY / 2 - Len2 / 2; y <= LY / 2 + Len2 / 2 - 1; y++)
       for (int x = LX / 2 - Len1 / 2; x <= LX / 2 + Len1 / 2 - 1; x++) {
         if (sphere && (x - LX / 2) * (x - LX / 2) + (y - LY / 2) * (y - LY / 2) + (z - LZ / 2) * (z - LZ / 2) > Len1 * Len1 / 4) continue;
-        if (cubic_site(x, y, z, kind)) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << (kind ? PosC : PosSi); w |= 1 << PosOcc; }
+        if (cubic_site(x, y, z, kind)) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << ((kind && two_species) ? PosC : PosSi); w |= 1 << PosOcc; }
       }
   const int z0 = LZ / 2 - Len3 / 2 - 10, z1 = LZ / 2 + Len3 / 2 + 9, y0 = LY / 2 - Len2 / 2 - 10, y1 = LY / 2 + Len2 / 2 + 9, x0 = LX / 2 - Len1 / 2 - 10, x1 = LX / 2 + Len1 / 2 + 9;
   pass_coordination(H, z0, z1, y0, y1, x0, x1);
@@ -502,20 +502,23 @@ void set_nc(Host &H, int Len1, int Len2, int Len3, bool sphere) {
 
 void occupy(Host &H, int x, int y, int z, int kind, bool two_species) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << ((kind && two_species) ? PosC : PosSi); w |= 1 << PosOcc; }
 // initial/SetInvPOff.f:22-286: 3C-SiC substrate with an array of inverted pyramids (one in the box centre, one on the corners)
-void set_invp_off(Host &H, int Len, int Len3) {
+// initial/SetInvPOff.f (only = 0: Si/C sublattices, REAL(4) slope 1.10) and its single-species twins initial/SetInvPSi.f
+// (only = 1) and initial/SetInvPC.f (only = 2), whose pyramid test is all-integer with slope 1
+void set_invp_off(Host &H, int Len, int Len3, int only = 0) {
   int kind, LX = H.LX, LY = H.LY; int32_t s[3], nn[4][3];
+  auto fill = [&](int x, int y, int z, int k) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << (only == 2 ? PosC : (only == 1 ? PosSi : (k ? PosC : PosSi))); w |= 1 << PosOcc; };
   const int Lenh = LX / 2 - 1;
   printf(" %d %d %d\n", Lenh, Len, Len3);
   for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
     if (cubic_site(x, y, z, kind)) {
-      occupy(H, x, y, z, kind, true); mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      fill(x, y, z, kind); mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
       s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn);
     }
   for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
     if (!cubic_site(x, y, z, kind)) continue;
     const float zt = 1.10f * (float)(z - Len3);              // REAL(4) arithmetic of SetInvPOff.f:78-82
-    auto pyr = [&](int ax, int ay) { return ((float)(std::abs(ax) + std::abs(ay)) - zt) <= (float)Len; };
-    if (!(pyr(x - Lenh, y - Lenh) || pyr(x, y) || pyr(x - LX, y) || pyr(x, y - LY) || pyr(x - LX, y - LY))) occupy(H, x, y, z, kind, true);
+    auto pyr = [&](int ax, int ay) { return only ? (std::abs(ax) + std::abs(ay) - (z - Len3)) <= Len : ((float)(std::abs(ax) + std::abs(ay)) - zt) <= (float)Len; };
+    if (!(pyr(x - Lenh, y - Lenh) || pyr(x, y) || pyr(x - LX, y) || pyr(x, y - LY) || pyr(x - LX, y - LY))) fill(x, y, z, kind);
   }
   pass_coordination(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
   pass_probability(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
@@ -532,6 +535,21 @@ void set_finfet(Host &H, int Len, int Lenww, int Lenwwtop, int Laperture) {
     if (ibits(H.L[H.ci(x, y, z)], PosIndex, LenIndex) != 113 && cubic_site(x, y, z, kind)) occupy(H, x, y, z, kind, false);
   pass_coordination(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
   pass_probability(H, 6, Lenwwtop + 9, 0, LY - 1, 0, LX - 1, true);
+}
+// initial/SetTrench.f:22-283 (InitSt T): 3C-SiC slab up to Len3 with a rectangular trench (half-width Len, between Len2 and Len3)
+void set_trench(Host &H) {
+  int kind, LX = H.LX, LY = H.LY; int32_t s[3], nn[4][3];
+  const int Len = H.Len1, Len2 = H.Len2, Len3 = H.Len3, Lenh = LX / 2 - 1;
+  printf(" %d %d %d\n", Lenh, Len, Len3);
+  for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind)) {
+      occupy(H, x, y, z, kind, true); mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn);
+    }
+  for (int z = 21; z <= Len3 - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind) && !(std::abs(x - Lenh) <= Len && z > Len2 && z < Len3)) occupy(H, x, y, z, kind, true);
+  pass_coordination(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
+  pass_probability(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
 }
 // initial/SetTrenchSi.f:22-338 (InitSt ST): temperature ramp along z in the lattice words, wall planes at both ends,
 // Si bulk up to z=20, a Si slab up to Len3 with a V-shaped trench (half-width Len at the top, bottom at Len2, side-wall
@@ -905,12 +923,16 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "SG") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false, true); }
   else if (H.InitSt == "C") set_nc(H, H.Len1, H.Len2, H.Len3, false);
   else if (H.InitSt == "S") set_nc(H, H.Len1, H.Len1, H.Len1, true);
+  else if (H.InitSt == "SS") set_nc(H, H.Len1, H.Len1, H.Len1, true, false);
   else if (H.InitSt == "I") set_invp_off(H, H.Len1, H.Len2);
+  else if (H.InitSt == "D") set_invp_off(H, H.Len1, H.Len2, 2);
+  else if (H.InitSt == "Z") set_invp_off(H, H.Len1, H.Len2, 1);
+  else if (H.InitSt == "T") set_trench(H);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "ST") set_trench_si(H);
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, I, FF, ST, IN, LA; see DESIGN.md section 9)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, SS, I, D, Z, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;

@@ -15,12 +15,14 @@ def start_path(case):
 
 
 def make_start(case, dst, lens=None, maxiter=None, outmolmol=None, runtype=None, idum=None, ptranszig=None, maxtime=None, outtime=None, paths=None,
-               alloyfraction=None):
+               alloyfraction=None, initst=None):
     """Copy tests/golden/start-<case>.dat to dst with some of the positional lines replaced.
     The grammar is the one of mulskips-source/main.f:83-212."""
     lines = open(start_path(case)).read().split("\n")
     ncov = int(lines[0].split()[1])
     i = 2 + (1 if ncov > 0 else 0)          # InitSt line
+    if initst is not None:                  # another builder on the same table (main.f:225-295)
+        lines[i] = f"{initst} ! InitSt"
     initst = lines[i].split()[0]
     i += 1
     if initst in ("IN", "SH"):

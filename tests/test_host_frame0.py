@@ -54,6 +54,42 @@ def test_frame0_and_startup_log(tmp_path, kind):
         assert _tokens(logs[g], key) == _tokens(logs[o], key), key
 
 
+# further builders of main.f:225-295 on the regression tables: (InitSt, table of, Len line, box)
+# (these small pitted slabs etch away under the regression tables -- the builders put no wall under z = 0 -- so the
+# follow-up run is kept short of the moment the etch front reaches the bottom plane)
+MORE_BUILDERS = [("SS", "Si-SL", (60, 0, 0), (144, 144, 144), 30000), ("D", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 1000),
+                 ("Z", "Si-SL", (30, 93, 0), (96, 96, 144), 5000), ("T", "cube", (20, 45, 90), (96, 48, 144), 30000)]
+
+
+@pytest.mark.parametrize("initst,table,lens,box,nrun", MORE_BUILDERS, ids=[b[0] for b in MORE_BUILDERS])
+def test_more_builders_frame0(tmp_path, initst, table, lens, box, nrun):
+    """SetNCSpSi.f (SS), SetInvPC.f (D), SetInvPSi.f (Z), SetTrench.f (T): the host program's initial structure, list
+    sizes and frame 0 equal the oracle's; the oracle then runs nrun events on it without tripping a consistency check."""
+    if not (os.path.exists(EXE) and os.path.exists(ORACLE)):
+        import __graft_entry__ as g
+        g.build()
+    g, o = tmp_path / "host", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    start = make_start(table, str(tmp_path / "start.dat"), lens=lens, maxiter=1, outmolmol=1, initst=initst)
+    args = ["--box", *[str(v) for v in box]]
+    logs = {}
+    for d, exe in ((g, EXE), (o, ORACLE)):
+        (d / "start.dat").write_text(open(start).read())
+        r = subprocess.run([exe, *args], cwd=d, capture_output=True, text=True)
+        logs[d] = r.stdout
+        if exe == ORACLE:
+            assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    long = tmp_path / "long"
+    long.mkdir()
+    make_start(table, str(long / "start.dat"), lens=lens, maxiter=nrun, outmolmol=nrun, initst=initst)
+    r = subprocess.run([ORACLE, *args, "--no-files"], cwd=long, capture_output=True, text=True)
+    assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-1000:] + r.stderr[-500:]
+    for name in ("I00000000.xyz", "I00000000_d.xyz", "I00000000_v.xyz"):
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"{initst}: {name}"
+    assert len((g / "I00000000.xyz").read_text().splitlines()) > 50
+    assert _tokens(logs[g], "Atoms,Voids,AdAtoms") == _tokens(logs[o], "Atoms,Voids,AdAtoms")
+
+
 def test_socket_handshake_and_first_frame(tmp_path):
     """The laser-annealing socket loop (mulskips-source-LaserAnnealing/main.f:160-345): the driver connects, answers
     STATUS with NEEDINIT / READY, takes the geometry and temperature arrays, and builds the same initial structure as

@@ -211,3 +211,26 @@ def test_socket_driven_laser_annealing(built, tmp_path):
             p.kill()
         out.close()
     orc.close()
+
+
+MORE_BUILDERS = [("SS", "Si-SL", (60, 0, 0), (144, 144, 144), 30000), ("D", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 1000),
+                 ("Z", "Si-SL", (30, 93, 0), (96, 96, 144), 5000), ("T", "cube", (20, 45, 90), (96, 48, 144), 30000)]
+
+
+@pytest.mark.parametrize("initst,table,lens,box,nrun", MORE_BUILDERS, ids=[b[0] for b in MORE_BUILDERS])
+def test_more_builders(built, tmp_path, initst, table, lens, box, nrun):
+    """SetNCSpSi.f (SS), SetInvPC.f (D), SetInvPSi.f (Z), SetTrench.f (T) through the host program with the loop on the
+    GPU: every output file and the log tokens equal the oracle's (SS ends on 'few MC particles', the others on MaxIter)."""
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    make_start(table, str(g / "start.dat"), lens=lens, maxiter=nrun, outmolmol=nrun, initst=initst)
+    (o / "start.dat").write_text((g / "start.dat").read_text())
+    args = ["--box", *[str(v) for v in box]]
+    _run(ORACLE, o, args)
+    _run(EXE, g, args)
+    names = sorted(p.name for p in o.glob("I*.xyz"))
+    assert "I00000000.xyz" in names and len(names) >= 3
+    for name in names:
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"{initst}: {name} differs from the oracle's"
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "few MC particles"):
+        assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
