@@ -919,6 +919,15 @@ int main(int argc, char **argv) {
   // main.f:225-295
   if (H.la_tree && H.InitSt != "LA" && H.InitSt != "IN") die(" mulskips.e (B200 host): --la-tree (the LaserAnnealing fork) is built for InitSt LA and IN");
   if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
+  else if (H.InitSt == "Fw") {                               // SetSiC3Cww.f: SetSiC3C.f between wall planes, plus a wall block from Len2 up
+    H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24;
+    set_flat(H, H.Len1, true, true); wall_planes(H, H.Len2, H.LZ - 7);
+  } else if (H.InitSt == "Fa") {                             // SetSiC3Cwwaperture.f: the wall block leaves an aperture of Len3 along x
+    H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24;
+    set_flat(H, H.Len1, true, true);
+    if ((int)(0.5f * (float)(H.LX - H.Len3)) - 1 >= 0) wall_planes(H, H.Len2, H.LZ - 7, 0, (int)(0.5f * (float)(H.LX - H.Len3)) - 1);
+    wall_planes(H, H.Len2, H.LZ - 7, (int)(0.5f * (float)(H.LX + H.Len3)), H.LX - 1);
+  }
   else if (H.InitSt == "FS") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false); }
   else if (H.InitSt == "SG") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, true, false, true); }
   else if (H.InitSt == "C") set_nc(H, H.Len1, H.Len2, H.Len3, false);
@@ -932,7 +941,7 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "ST") set_trench_si(H);
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, FS, SG, C, S, SS, I, D, Z, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;

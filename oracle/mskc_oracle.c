@@ -1531,6 +1531,16 @@ int orc_setup(Orc *o) {
   const char *s = o->InitSt;
   if (o->la_tree && strcmp(s, "LA") && strcmp(s, "IN")) orc_fatal(o, "oracle: the la/ tree variant restates InitSt LA and IN only");
   if (!strcmp(s, "F")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 0, 1); }
+  else if (!strcmp(s, "Fw")) {                                 /* SetSiC3Cww.f: SetSiC3C.f between wall planes, plus a wall block from Len2 up */
+    o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24;
+    set_flat(o, o->Len1, 1, 1);
+    set_wall_planes(o, o->Len2, o->LenZ - 7, 0, o->LenX - 1);
+  } else if (!strcmp(s, "Fa")) {                               /* SetSiC3Cwwaperture.f: the wall block leaves an aperture of Len3 along x */
+    o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24;
+    set_flat(o, o->Len1, 1, 1);
+    set_wall_planes(o, o->Len2, o->LenZ - 7, 0, (int)(0.5f * (float)(o->LenX - o->Len3)) - 1);
+    set_wall_planes(o, o->Len2, o->LenZ - 7, (int)(0.5f * (float)(o->LenX + o->Len3)), o->LenX - 1);
+  }
   else if (!strcmp(s, "FS")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 0); }
   else if (!strcmp(s, "SG")) { o->Len1 -= o->Len1 % 24; set_flat(o, o->Len1, 1, 2); }
   else if (!strcmp(s, "C")) set_nc(o, o->Len1, o->Len2, o->Len3, 0, 1);
