@@ -506,7 +506,16 @@ void occupy(Host &H, int x, int y, int z, int kind, bool two_species) { int32_t 
 // (only = 1) and initial/SetInvPC.f (only = 2), whose pyramid test is all-integer with slope 1
 void set_invp_off(Host &H, int Len, int Len3, int only = 0) {
   int kind, LX = H.LX, LY = H.LY; int32_t s[3], nn[4][3];
-  auto fill = [&](int x, int y, int z, int k) { int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << (only == 2 ? PosC : (only == 1 ? PosSi : (k ? PosC : PosSi))); w |= 1 << PosOcc; };
+  // antiphase-domain variants (integer pyramid test): SetInvPwOnlySiorC.f (only = 3), SetInvPwOnlyCorSi.f (4), SetInvPwAPB.f (5):
+  // the ideal Si/C assignment inside one domain, the swapped one outside
+  auto fill = [&](int x, int y, int z, int k) {
+    if (only >= 3) {
+      const bool quad = (x < LX / 2 && y >= LY / 2) || (x >= LX / 2 && y < LY / 2);
+      const bool ideal = only == 3 ? quad : only == 4 ? !quad : (x + y <= LY);
+      if (!ideal) k = !k;
+    }
+    int32_t &w = H.L[H.ci(x, y, z)]; w |= 1 << (only == 2 ? PosC : (only == 1 ? PosSi : (k ? PosC : PosSi))); w |= 1 << PosOcc;
+  };
   const int Lenh = LX / 2 - 1;
   printf(" %d %d %d\n", Lenh, Len, Len3);
   for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
@@ -936,12 +945,15 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "I") set_invp_off(H, H.Len1, H.Len2);
   else if (H.InitSt == "D") set_invp_off(H, H.Len1, H.Len2, 2);
   else if (H.InitSt == "Z") set_invp_off(H, H.Len1, H.Len2, 1);
+  else if (H.InitSt == "K") set_invp_off(H, H.Len1, H.Len2, 3);
+  else if (H.InitSt == "L") set_invp_off(H, H.Len1, H.Len2, 4);
+  else if (H.InitSt == "J") set_invp_off(H, H.Len1, H.Len2, 5);
   else if (H.InitSt == "T") set_trench(H);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "ST") set_trench_si(H);
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;

@@ -1307,13 +1307,22 @@ static void set_nc(Orc *o, int Len1, int Len2, int Len3, int sphere, int two_spe
 /* src/initial/SetInvPOff.f:22-286 (only = 0: Si/C sublattices, pyramid faces with the REAL(4) slope 1.10), and its
  * single-species twins SetInvPSi.f (only = 1: Si on both sublattices) and SetInvPC.f (only = 2: C on both), whose
  * pyramid test is the all-integer ABS(x-..)+ABS(y-..)-(z-Len3) <= Len */
+/* ... and the antiphase-domain variants (all with the integer pyramid test): SetInvPwOnlySiorC.f (only = 3: Si/C as in the
+ * ideal crystal where (x<LenX/2 and y>=LenY/2) or (x>=LenX/2 and y<LenY/2), swapped elsewhere), SetInvPwOnlyCorSi.f
+ * (only = 4: the two domains exchanged) and SetInvPwAPB.f (only = 5: ideal where x+y <= LenY, swapped elsewhere) */
+static inline int invp_kind(const Orc *o, int only, int x, int y, int kind) {
+  if (only < 3) return kind;
+  int quad = (x < o->LenX / 2 && y >= o->LenY / 2) || (x >= o->LenX / 2 && y < o->LenY / 2);
+  int ideal = only == 3 ? quad : only == 4 ? !quad : (x + y <= o->LenY);
+  return ideal ? kind : !kind;
+}
 static void set_invp_off(Orc *o, int Len, int Len3, int only) {
   int kind, LX = o->LenX, LY = o->LenY; int32_t Site[3], NextN[4][3];
   int Lenh = LX / 2 - 1;
   LOG(o, " %d %d %d\n", Lenh, Len, Len3);
   for (int z = 0; z <= 20; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
     if (is_cubic_site(x, y, z, &kind)) {
-      occupy(o, x, y, z, only == 2 ? 1 : kind, only != 1);
+      occupy(o, x, y, z, only == 2 ? 1 : invp_kind(o, only, x, y, kind), only != 1);
       MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
       Site[0] = x; Site[1] = y; Site[2] = z;
       dia_nn(o, x, y, z, kind, NextN);
@@ -1330,8 +1339,8 @@ static void set_invp_off(Orc *o, int Len, int Len3, int only) {
 #undef PYR
     if (!inside) {
       int m = (x1 + y1 + z1) % 4;
-      if (m == 0) occupy(o, x, y, z, only == 2 ? 1 : 0, only != 1);
-      else if (m == 3) occupy(o, x, y, z, 1, only != 1);
+      if (m == 0) occupy(o, x, y, z, only == 2 ? 1 : invp_kind(o, only, x, y, 0), only != 1);
+      else if (m == 3) occupy(o, x, y, z, invp_kind(o, only, x, y, 1), only != 1);
     }
   }
   pass_coordination(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0);
@@ -1549,6 +1558,9 @@ int orc_setup(Orc *o) {
   else if (!strcmp(s, "I")) set_invp_off(o, o->Len1, o->Len2, 0);
   else if (!strcmp(s, "D")) set_invp_off(o, o->Len1, o->Len2, 2);             /* SetInvPC.f */
   else if (!strcmp(s, "Z")) set_invp_off(o, o->Len1, o->Len2, 1);             /* SetInvPSi.f */
+  else if (!strcmp(s, "K")) set_invp_off(o, o->Len1, o->Len2, 3);             /* SetInvPwOnlySiorC.f */
+  else if (!strcmp(s, "L")) set_invp_off(o, o->Len1, o->Len2, 4);             /* SetInvPwOnlyCorSi.f */
+  else if (!strcmp(s, "J")) set_invp_off(o, o->Len1, o->Len2, 5);             /* SetInvPwAPB.f */
   else if (!strcmp(s, "T")) set_trench(o, o->Len1, o->Len2, o->Len3);         /* SetTrench.f */
   else if (!strcmp(s, "FF")) {
     o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;

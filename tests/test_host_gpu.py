@@ -215,7 +215,9 @@ def test_socket_driven_laser_annealing(built, tmp_path):
 
 MORE_BUILDERS = [("SS", "Si-SL", (60, 0, 0), (144, 144, 144), 30000), ("D", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 1000),
                  ("Z", "Si-SL", (30, 93, 0), (96, 96, 144), 5000), ("T", "cube", (20, 45, 90), (96, 48, 144), 30000),
-                 ("Fw", "surface", (48, 96, 0), (96, 96, 144), 30000), ("Fa", "surface", (48, 72, 48), (96, 96, 144), 30000)]
+                 ("Fw", "surface", (48, 96, 0), (96, 96, 144), 30000), ("Fa", "surface", (48, 72, 48), (96, 96, 144), 30000),
+                 ("K", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 2000), ("L", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 2000),
+                 ("J", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 2000)]
 
 
 @pytest.mark.parametrize("initst,table,lens,box,nrun", MORE_BUILDERS, ids=[b[0] for b in MORE_BUILDERS])
