@@ -14,6 +14,8 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -321,10 +323,26 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-la-cycle", action="store_true")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(keep, 1)
+        os.close(keep)
+    lines = [l for l in buf.getvalue().splitlines() if l.strip()]
+    for l in lines[:-1]:
+        print(l, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
