@@ -49,3 +49,62 @@ def test_analyze_reads_frame0(tmp_path, case):
     h, hg = an.get_surface_height(str(f0)), an.get_surface_height(golden)
     assert h == hg and h > 0
     assert len(an.read_output_files(str(tmp_path), "vacancies")) >= 1 and len(an.read_output_files(str(tmp_path), "defects")) >= 1
+
+
+def test_reference_socket_server_drives_the_host(tmp_path):
+    """The reference's OWN server classes (pymulskips/sockets.py: InterfaceSocket, Driver, Status) against the host
+    program as socket client: STATUS -> NEEDINIT, INIT, STATUS -> READY, SENDGEO, SENDFIELD.  The client builds its
+    structure from the two arrays (frame 0 appears); without a GPU it then stops at mskc_create, with one it runs the
+    single event allowed here and offers the phases."""
+    import numpy as np
+    from cases import make_la_tree_case
+    p = os.path.join(REF, "pymulskips", "sockets.py")
+    if not os.path.exists(p):
+        pytest.skip("reference tree not mounted")
+    spec = importlib.util.spec_from_file_location("pymulskips_sockets", p)
+    S = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(S)
+    if not os.path.exists(EXE):
+        import __graft_entry__ as g
+        g.build()
+    box = (96, 96, 96)
+    files = tmp_path / "files"; run = tmp_path / "run"
+    files.mkdir(); run.mkdir()
+    make_la_tree_case(str(files), box=box, maxiter=1)                          # only for its LattGeo / TempStat arrays
+    make_la_tree_case(str(run), box=box, maxiter=1, sockets=True)
+    geo = np.loadtxt(files / "LattGeo.dat", dtype=np.int32)
+    tmp = np.loadtxt(files / "TempStat.dat", dtype=np.int32)
+    import socket as pysocket
+    probe = pysocket.socket(); probe.bind(("127.0.0.1", 0)); port = probe.getsockname()[1]; probe.close()
+    iface = S.InterfaceSocket(address="127.0.0.1", port=port)
+    iface.open()
+    iface.server.settimeout(60)
+    out = open(run / "log.txt", "w")
+    proc = subprocess.Popen([EXE, "--la-tree", "-h", "127.0.0.1", "-p", str(port), "--box", *[str(v) for v in box]], cwd=run, stdout=out, stderr=subprocess.STDOUT)
+    try:
+        client, _ = iface.server.accept()
+        drv = S.Driver(client)           # (no timeout on `client`: Driver re-wraps the same descriptor as a blocking socket)
+        assert drv.get_status() == (S.Status.Up | S.Status.NeedsInit)
+        drv.initialise()
+        assert drv.get_status() == (S.Status.Up | S.Status.Ready)
+        drv.send_data(geo, "geo")
+        assert drv.get_status() == (S.Status.Up | S.Status.Ready)
+        drv.send_data(tmp, "field")
+        try:
+            st = drv.get_status()
+            if st & S.Status.HasData:                                           # GPU present
+                c = drv.get_data(np.zeros(geo.shape, np.int32), "phases")
+                assert c.shape == geo.shape and c.max() == 10
+                drv.shutdown()
+        except Exception:
+            pass
+        proc.wait(timeout=120)
+    finally:
+        iface.close()
+        if proc.poll() is None:
+            proc.kill()
+        out.close()
+    log = (run / "log.txt").read_text()
+    assert "@ message to server: NEEDINIT" in log and "@ message to server: READY" in log
+    assert "Setting input geometry from sockets" in log and "Setting temperatures in LattCoo from array received via sockets" in log
+    assert (run / "I00000000.xyz").exists() and len((run / "I00000000.xyz").read_text().splitlines()) > 100
