@@ -6,6 +6,7 @@
 #include "mskc_parallel.cuh"
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -348,7 +349,8 @@ extern "C" int mskc_set_la_fork(mskc_ctx *h, int enable, const double *Tm, const
   h->fork_occ = num_adatom_occ; h->fork_occ0 = num_occ0;
   if (h->parity_ready) {                               // state already uploaded: the two counters go into the loop state
     h->h_ps.NumAdAtomOcc = num_adatom_occ; h->h_ps.NumOcc0 = num_occ0;
-    CK(cudaMemcpy(&h->d_ps->NumAdAtomOcc, &h->h_ps.NumAdAtomOcc, 2 * sizeof(int), cudaMemcpyHostToDevice));
+    static_assert(offsetof(ParityState, NumOcc0) == offsetof(ParityState, NumAdAtomOcc) + sizeof(int), "the two counters are copied together");
+    CK(cudaMemcpy(reinterpret_cast<char *>(h->d_ps) + offsetof(ParityState, NumAdAtomOcc), &h->h_ps.NumAdAtomOcc, 2 * sizeof(int), cudaMemcpyHostToDevice));
   }
   return 0;
 }
