@@ -1029,12 +1029,20 @@ int main(int argc, char **argv) {
     mskc_parallel_args a{}; mskc_parallel_result r{};
     a.events_per_tile = ept; a.seed = (uint64_t)(H.Idum < 0 ? -H.Idum : H.Idum); a.n_sweeps = 8;
     long long next_out = H.OutMolMol; double next_t = H.OutTime;
+    // a leg of a socket-driven run starts its own clock and iteration count (la/main.f:621-624); the sampler's clock runs on
+    long long leg_events = 0;
+    double t_leg0 = 0.0;
+    { mskc_counters c0; MS(mskc_get_counters(R.h, &c0)); t_leg0 = c0.time; }
     while (true) {
       if (mskc_run_parallel(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
-      events += r.events_done; dev_ms += r.kernel_ms; R.Time = r.time; R.Iter = events + 1; R.IterOut = events;
+      events += r.events_done; leg_events += r.events_done; dev_ms += r.kernel_ms; R.Time = r.time - t_leg0; R.Iter = leg_events + 1; R.IterOut = leg_events;
       mskc_counters c; MS(mskc_get_counters(R.h, &c)); R.NumAtoms = c.num_atoms; R.NumVoids = c.num_voids; R.NumAdAtom = c.num_adatom;
       if (r.n_active <= 20) { printf(" few MC particles: stop MC %lld %d\n", R.Iter, (int)r.n_active); break; }
-      bool frame = by_time ? (H.OutTime > 0 && R.Time >= next_t) : (H.OutMolMol > 0 && events >= next_out);
+      if (H.la_tree && H.la() && c.num_atoms + c.num_adatom_occ > H.NumOcc0) {            // la/main.f:714-723, checked once per call of the sampler
+        printf(" \n Current number of occupied sites:  %d\n    > initial number of occupied sites:  %d\n ... STOPPING MulSKIPS ...\n \n", c.num_atoms + c.num_adatom_occ, H.NumOcc0);
+        break;
+      }
+      bool frame = by_time ? (H.OutTime > 0 && R.Time >= next_t) : (H.OutMolMol > 0 && leg_events >= next_out);
       if (frame) {
         R.framecounter++;
         write_frame(H, R, R.Time, R.IterOut, R.framecounter, true);
@@ -1042,7 +1050,7 @@ int main(int argc, char **argv) {
         printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
         next_out += H.OutMolMol; next_t += H.OutTime;
       }
-      if (by_time ? R.Time > H.MaxTime : events >= H.MaxIter) break;
+      if (by_time ? R.Time > H.MaxTime : leg_events >= H.MaxIter) break;
     }
   }
   };

@@ -237,3 +237,35 @@ def test_more_builders(built, tmp_path, initst, table, lens, box, nrun):
         assert (g / name).read_bytes() == (o / name).read_bytes(), f"{initst}: {name} differs from the oracle's"
     for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad", "few MC particles"):
         assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
+
+
+@pytest.mark.parametrize("kind", ["surface", "LA-fork"])
+def test_host_parallel_mode(built, tmp_path, kind):
+    """`mulskips.e --parallel`: the production mode of the drop-in (synchronous-sublattice sampler) writes the same set of
+    files at the same cadence as the serial loop; with --la-tree the sampler runs on the fork's law (CountLiquid per call,
+    occupied count from the census).  Statistical equivalence is tests/test_sampler_stats_gpu.py's subject; here: the run
+    completes, frames are well-formed and the crystal evolved."""
+    box = (96, 96, 240) if kind == "surface" else (96, 96, 96)
+    args = ["--parallel", "--box", *[str(v) for v in box]]
+    if kind == "surface":
+        make_start("surface", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=40000, outmolmol=20000, runtype="R")
+    else:
+        make_la_tree_case(str(tmp_path), box, maxiter=40000)
+        lines = (tmp_path / "start.dat").read_text().split("\n")
+        i = next(k for k, l in enumerate(lines) if "OutMolMol" in l)
+        lines[i] = "20000 ! OutMolMol"
+        (tmp_path / "start.dat").write_text("\n".join(lines))
+        args.append("--la-tree")
+    _run(EXE, tmp_path, args)
+    frames = sorted(p.name for p in tmp_path.glob("I*[0-9].xyz"))
+    assert frames[0] == "I00000000.xyz" and len(frames) >= 2
+    n0 = int(open(tmp_path / frames[0]).readline().split()[0])
+    n1 = int(open(tmp_path / frames[-1]).readline().split()[0])
+    assert n0 > 50 and n1 > 50
+    body0 = open(tmp_path / frames[0]).read().split("\n", 2)[2]
+    body1 = open(tmp_path / frames[-1]).read().split("\n", 2)[2]
+    assert body0 != body1
+    t = _tokens(tmp_path / "log.txt", "Iter, Time, Site")
+    assert t is not None and int(t[3]) > 20000 and float(t[4]) > 0
+    err = open(tmp_path / "err.txt").read()
+    assert "sublattice-sampler" in err
