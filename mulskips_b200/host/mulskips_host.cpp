@@ -85,6 +85,7 @@ struct Host {
   std::vector<double> PE = std::vector<double>(12288, 0.0), PD = std::vector<double>(9, 0.0), PA = std::vector<double>(12, 0.0), PS = std::vector<double>(12, 0.0);
   // state built by the initialiser (module globals of defsystem.f)
   std::vector<int32_t> L;                                  // LattCoo(0:LenX-1,0:LenY-1,0:LenZ)
+  std::vector<int32_t> LI;                                 // LattInd (defsystem.f:50), 1-based list positions; kept for the builders that look records up (SetShape.f)
   std::vector<Active> mc; std::vector<Site> bulk, voids;
   std::vector<double> Tree; int Levels = 20;               // init-time rate tree: only Tree(1) is consulted (Get_Prob_Ini.f "isolated atom")
   int CountCrystal[3] = {0, 0, 0}, CountCrystalOld[3] = {0, 0, 0}, CountCov[3] = {0, 0, 0};
@@ -121,12 +122,54 @@ struct Host {
     if (p == 0) die(" provo ad aggiungere prob nulla %d %d %d", s[0], s[1], s[2]);
     Active a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); a.ev = ev; a.p = p;
     mc.push_back(a);
+    if (!LI.empty() && in_box(s)) LI[ci(s[0], s[1], s[2])] = (int32_t)mc.size();
     if ((int)mc.size() >= 500000) die(" troppe particelle cinetiche");
     update_tree((int)mc.size(), p);
   }
-  void AddBulk(const int32_t s[3], const int32_t nn[4][3]) { Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); bulk.push_back(a); }
+  void AddBulk(const int32_t s[3], const int32_t nn[4][3]) {
+    Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); bulk.push_back(a);
+    if (!LI.empty() && in_box(s)) LI[ci(s[0], s[1], s[2])] = (int32_t)bulk.size();
+  }
+  bool in_box(const int32_t s[3]) const { return s[0] >= 0 && s[0] < LX && s[1] >= 0 && s[1] < LY && s[2] >= 0 && s[2] <= LZ; }
+  int32_t word(const int32_t p[3]) const { return in_box(p) ? L[ci(p[0], p[1], p[2])] : 0; }        // (the reference reads outside its array there)
+  void EraseBulk(const int32_t s[3]) {                                           // Erase.f:84-128: the last record moves into the hole
+    const int ind = LI[ci(s[0], s[1], s[2])];
+    if (ind == 0 || ind > (int)bulk.size()) die(" err: EraseBulk %d %d %d %d", ind, s[0], s[1], s[2]);
+    if (ind != (int)bulk.size()) { bulk[ind - 1] = bulk.back(); LI[ci(bulk[ind - 1].xyz[0], bulk[ind - 1].xyz[1], bulk[ind - 1].xyz[2])] = ind; }
+    bulk.pop_back();
+    LI[ci(s[0], s[1], s[2])] = 0;
+  }
+  static bool lists(const int32_t nn[4][3], const int32_t s[3]) { for (int j = 0; j < 4; j++) if (nn[j][0] == s[0] && nn[j][1] == s[1] && nn[j][2] == s[2]) return true; return false; }
+  // mcevent/Get_Prob.f:213-323 for an occupied site without coverage of its own: census of the four neighbours with the
+  // reciprocity test against the neighbour's record (ListAdAtom or ListAtom by its coordination), then the table look-up
+  void get_prob_occupied(int NSiC, int Coor, const int32_t s[3], const int32_t nn[4][3], int &ev, double &prob) {
+    int N_Si = 0, N_C = 0, N_B = 0, N_wall = 0, cov[3] = {0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+      const int32_t w = word(nn[i]);
+      const int OccN = ibits(w, PosOcc, 1), CovN = ibits(w, PosIndex, LenIndex), CoorNN = ibits(w, PosCoor, LenCoor);
+      if (OccN != 0) {
+        if (CovN == 113) { N_wall++; continue; }
+        const int ind = LI[ci(nn[i][0], nn[i][1], nn[i][2])];
+        const bool in_mc = CoorNN >= 1 && CoorNN <= 3;
+        if (ind < 1 || ind > (int)(in_mc ? mc.size() : bulk.size())) die(" Get_Prob: neighbour %d %d %d of %d %d %d is in no list", nn[i][0], nn[i][1], nn[i][2], s[0], s[1], s[2]);
+        const int32_t (*rec)[3] = in_mc ? mc[ind - 1].nn : bulk[ind - 1].nn;
+        if (lists(rec, s)) { const int k = ibits(w, PosSiC, LenSiC); N_Si += (k == 1); N_C += (k == 2); N_B += (k == 3); }
+      } else if (CovN != 0) {
+        const int ind = LI[ci(nn[i][0], nn[i][1], nn[i][2])];
+        if (ind >= 1 && ind <= (int)mc.size() && lists(mc[ind - 1].nn, s)) for (int j = 0; j < NCov; j++) if (ListCov[j] == CovN) cov[j]++;
+      }
+    }
+    const int ncry = N_Si + N_C + N_B + N_wall;
+    if (ncry != Coor) die(" %d %d %d %d %d Get Prob Error N_Si+N_C+N_B+N_wall.NE.Coor", Coor, N_Si, N_C, N_B, N_wall);
+    ev = 0; prob = 0.0;
+    if (ncry > 3) return;
+    ev = EvEvap;
+    if (ncry == 0) prob = (double)100000.f * Tree[1];
+    else prob = PE[idxE(NSiC, N_Si + N_wall, N_C, N_B, NCov >= 1 ? cov[0] & 3 : 0, NCov >= 2 ? cov[1] & 3 : 0, NCov >= 3 ? cov[2] & 3 : 0)];
+  }
   void AddVoid(const int32_t s[3], const int32_t nn[4][3]) {                    // Add.f:83-101
     Site a; memcpy(a.xyz, s, 12); memcpy(a.nn, nn, 48); voids.push_back(a);
+    if (!LI.empty() && in_box(s)) LI[ci(s[0], s[1], s[2])] = (int32_t)voids.size();
     if ((int)voids.size() >= 100000) die(" troppi vuoti");
   }
   // LA rate law, Get_Prob.f:143-148 / Get_Prob_Ini.f:75-79 (glibc exp/erf, as the gfortran build)
@@ -325,8 +368,7 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   if (H.NCov > 0) { printf(" Coverage species (NCov= %d ) --> Z:", H.NCov); for (int i = 0; i < H.NCov; i++) printf(" %d", H.ListCov[i]); printf("\n"); }
   H.InitSt = first_token(in.next()).substr(0, 2);
   if (H.InitSt == "FF") { char *p = const_cast<char *>(in.next()); H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10); H.Len4 = (int)strtol(p, &p, 10); }
-  else if (H.InitSt == "SH")
-    die(" mulskips.e (B200 host): InitSt %s is not built (SetShape; see DESIGN.md section 10)", H.InitSt.c_str());
+  else if (H.InitSt == "SH") H.cadfile = whole_line(in.next());                         // main.f:116-117
   else if (H.InitSt == "ST") {                                                          // main.f:109-115
     char *p = const_cast<char *>(in.next());
     H.Len1 = (int)strtol(p, &p, 10); H.Len2 = (int)strtol(p, &p, 10); H.Len3 = (int)strtol(p, &p, 10);
@@ -594,6 +636,149 @@ void set_trench_si(Host &H) {
   }
   pass_coordination(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
   pass_probability(H, 21, Len3 + 9, 0, LY - 1, 0, LX - 1);
+}
+// lattice/FIND_NN.f:25-77: the two missing tetrahedral partners of SiteC given two of them (rotation by 120 and 240 degrees
+// about the first bond; Pi is a REAL(4) literal widened, libm cos/sin/sqrt as the gfortran build)
+void find_nn(const Host &H, const int32_t S1[3], const int32_t S2[3], const int32_t SC[3], int32_t out[2][3]) {
+  const double Pi = (double)3.14159265358979323f;
+  auto isign = [](int a, int b) { return b >= 0 ? std::abs(a) : -std::abs(a); };
+  auto nint = [](double x) { return (int)(x >= 0 ? floor(x + 0.5) : -floor(-x + 0.5)); };
+  int a1[3] = {S1[0], S1[1], S1[2]}, a2[3] = {S2[0], S2[1], S2[2]};
+  if (std::abs(SC[0] - a1[0]) > H.LX / 2) a1[0] += isign(H.LX, SC[0] - a1[0]);
+  if (std::abs(SC[1] - a1[1]) > H.LY / 2) a1[1] += isign(H.LY, SC[1] - a1[1]);
+  if (std::abs(SC[0] - a2[0]) > H.LX / 2) a2[0] += isign(H.LX, SC[0] - a2[0]);
+  if (std::abs(SC[1] - a2[1]) > H.LY / 2) a2[1] += isign(H.LY, SC[1] - a2[1]);
+  double ax[3], Rot[3][3], R[3];
+  for (int k = 0; k < 3; k++) ax[k] = (double)SC[k] - (double)a1[k];
+  const double snorm = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  for (int k = 0; k < 3; k++) ax[k] = ax[k] / snorm;
+  for (int irot = 1; irot <= 2; irot++) {
+    const double Cth = cos((double)(2 * irot) * Pi / 3.0), Sth = sin((double)(2 * irot) * Pi / 3.0);
+    for (int i = 0; i < 3; i++) Rot[i][i] = ax[i] * ax[i] * (1 - Cth) + Cth;
+    Rot[1][0] = ax[0] * ax[1] * (1 - Cth) - ax[2] * Sth; Rot[0][1] = ax[0] * ax[1] * (1 - Cth) + ax[2] * Sth;
+    Rot[2][0] = ax[0] * ax[2] * (1 - Cth) + ax[1] * Sth; Rot[0][2] = ax[0] * ax[2] * (1 - Cth) - ax[1] * Sth;
+    Rot[2][1] = ax[1] * ax[2] * (1 - Cth) - ax[0] * Sth; Rot[1][2] = ax[1] * ax[2] * (1 - Cth) + ax[0] * Sth;
+    for (int k = 0; k < 3; k++) { R[k] = 0.0; for (int l = 0; l < 3; l++) R[k] = R[k] + Rot[l][k] * ((double)a2[l] - (double)SC[l]); }
+    for (int k = 0; k < 3; k++) out[irot - 1][k] = nint(R[k]) + SC[k];
+    if (out[irot - 1][0] >= H.LX) out[irot - 1][0] -= H.LX;
+    if (out[irot - 1][0] < 0) out[irot - 1][0] += H.LX;
+    if (out[irot - 1][1] >= H.LY) out[irot - 1][1] -= H.LY;
+    if (out[irot - 1][1] < 0) out[irot - 1][1] += H.LY;
+  }
+}
+// initial/SetShape.f:25-507 (InitSt SH; main.f:281-286): an arbitrary structure from a list "sym x y z" of filled sites.
+// Neighbours are found on the whole first shell (32 vectors, cubic + hexagonal bonds); three passes then restore the
+// reciprocity of the bonds and list the empty sites around the under-coordinated atoms.
+void set_shape(Host &H) {
+  const int LX = H.LX, LY = H.LY, LZ = H.LZ;
+  H.LI.assign(H.L.size(), 0);
+  printf(" Reading input geometry file (SHAPE):  %s\n", H.cadfile.c_str());
+  Lines in; in.f = fopen(H.cadfile.c_str(), "r"); if (!in.f) die(" cannot open %s", H.cadfile.c_str());
+  const int NFilled = (int)strtol(in.next(), nullptr, 10);
+  in.next();                                                 // the second line is skipped (:54)
+  for (int ia = 0; ia < NFilled; ia++) {
+    char sym[8]; int x, y, z;
+    if (sscanf(in.next(), " %7s %d %d %d", sym, &x, &y, &z) != 4) die(" shape file: bad record %d", ia + 1);
+    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) die(" shape file: site %d %d %d outside the box", x, y, z);
+    int32_t &w = H.L[H.ci(x, y, z)];
+    w |= 1 << PosOcc;
+    if (z >= LZ - 4 || z <= 3) mvbits(113, LenIndex, w, PosIndex);
+    else if (!strcmp(sym, "Si")) w |= 1 << PosSi;
+    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) w |= 1 << PosC;
+  }
+  fclose(in.f);
+  printf(" Done reading input geometry file\n");
+  int shell[32][3], n = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++) if (i * i + j * j + k * k == 27) { shell[n][0] = i; shell[n][1] = j; shell[n][2] = k; n++; }
+  int32_t s[3], q[3], nd[4][3], nn[4][3], fresh[2][3]; int ev; double p;
+  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {       // pass 1, :83-181
+    int32_t &w = H.L[H.ci(x, y, z)];
+    if (ibits(w, PosOcc, 1) == 0) continue;
+    s[0] = x; s[1] = y; s[2] = z;
+    memset(nd, 0, sizeof nd);
+    int Coord = 0;
+    for (int i = 0; i < 32; i++) {
+      for (int k = 0; k < 3; k++) q[k] = s[k] + shell[i][k];
+      if (q[0] >= LX) q[0] -= LX;
+      if (q[0] < 0) q[0] += LX;
+      if (q[1] >= LY) q[1] -= LY;
+      if (q[1] < 0) q[1] += LY;
+      if (ibits(H.word(q), PosOcc, 1) > 0) {
+        if (Coord >= 4) die(" SetShape: site %d %d %d has more than four occupied shell sites", x, y, z);
+        memcpy(nd[Coord++], q, 12);
+      }
+    }
+    mvbits(Coord, LenCoor, w, PosCoor);
+    if (Coord <= 3) {
+      int32_t keep[3]; memcpy(keep, nd[2], 12);
+      find_nn(H, nd[0], nd[1], s, fresh);
+      memcpy(nd[2], fresh[0], 12); memcpy(nd[3], fresh[1], 12);
+      if (Coord == 3 && !Host::lists(nd, keep)) printf(" Coord.eq.3 wrong check Buf %d %d %d\n", keep[0], keep[1], keep[2]);
+      H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coord, s, nd, ev, p);
+      H.AddMC(s, nd, ev, p);
+    } else H.AddBulk(s, nd);
+  }
+  auto recipr_coor = [&](const int32_t site[3], const int32_t bonds[4][3], int Coor) {                 // :366-385 / :413-432
+    for (int j = 0; j < 4; j++) {
+      const int32_t wn = H.word(bonds[j]);
+      if (ibits(wn, PosOcc, 1) == 0) continue;
+      const int ind = H.LI[H.ci(bonds[j][0], bonds[j][1], bonds[j][2])];
+      const bool in_bulk = ibits(wn, PosCoor, LenCoor) == 4;
+      if (ind < 1 || ind > (int)(in_bulk ? H.bulk.size() : H.mc.size())) die(" SetShape: occupied site %d %d %d is in no list (a wall or a site outside z = 4..LenZ-5 bonded to the shape)", bonds[j][0], bonds[j][1], bonds[j][2]);
+      const int32_t (*rec)[3] = in_bulk ? H.bulk[ind - 1].nn : H.mc[ind - 1].nn;
+      if (!Host::lists(rec, site)) Coor--;
+    }
+    return Coor;
+  };
+  for (size_t i = 0; i < H.mc.size(); i++) {                                                            // pass 2, :358-398
+    memcpy(s, H.mc[i].xyz, 12); memcpy(nn, H.mc[i].nn, 48);
+    int32_t &w = H.at(s);
+    const int old = ibits(w, PosCoor, LenCoor), Coor = recipr_coor(s, nn, old);
+    if (Coor == old) continue;
+    mvbits(Coor, LenCoor, w, PosCoor);
+    H.get_prob_occupied(ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p);
+    H.mc[i].ev = ev; H.mc[i].p = p; H.update_tree((int)i + 1, p);
+  }
+  const size_t N0 = H.bulk.size();                                                                      // pass 3, :404-449 (loop bound fixed at entry)
+  for (size_t i = 0; i < N0; i++) {
+    if (i >= H.bulk.size()) break;                          // (the reference reads zeroed records here: z = 0 < 13, skipped)
+    memcpy(s, H.bulk[i].xyz, 12);
+    if (s[2] < 13) continue;
+    memcpy(nn, H.bulk[i].nn, 48);
+    int32_t &w = H.at(s);
+    const int old = ibits(w, PosCoor, LenCoor), Coor = recipr_coor(s, nn, old);
+    if (Coor == old) continue;
+    mvbits(Coor, LenCoor, w, PosCoor);
+    H.get_prob_occupied(ibits(w, PosSiC, LenSiC), Coor, s, nn, ev, p);
+    H.EraseBulk(s);
+    H.AddMC(s, nn, ev, p);
+  }
+  const size_t nold = H.mc.size();                                                                      // pass 4, :455-503
+  for (size_t i = 0; i < nold; i++) {
+    int32_t from[3]; memcpy(from, H.mc[i].xyz, 12);
+    for (int j = 0; j < 4; j++) {
+      memcpy(s, H.mc[i].nn[j], 12);
+      if (!H.in_box(s)) die(" SetShape: bond of %d %d %d leaves the box", from[0], from[1], from[2]);
+      int32_t &w = H.at(s);
+      if (ibits(w, PosOcc, 1) != 0) continue;
+      memset(nn, 0, sizeof nn);
+      const int Coor = ibits(w, PosCoor, LenCoor) + 1;
+      if (Coor == 1) {
+        memcpy(nn[0], from, 12);
+        mvbits(Coor, LenCoor, w, PosCoor);
+        H.get_prob_ini(0, 0, Coor, s, nn, ev, p);
+        H.AddMC(s, nn, ev, p);
+      } else if (Coor == 2 || Coor == 3) {
+        const int ind = H.LI[H.ci(s[0], s[1], s[2])];
+        memcpy(nn, H.mc[ind - 1].nn, 48);
+        if (Coor == 2) { memcpy(nn[1], from, 12); find_nn(H, nn[0], nn[1], s, fresh); memcpy(nn[2], fresh[0], 12); memcpy(nn[3], fresh[1], 12); }
+        mvbits(Coor, LenCoor, w, PosCoor);
+        H.get_prob_ini(0, 0, Coor, s, nn, ev, p);
+        if (Coor == 2) memcpy(H.mc[ind - 1].nn, nn, 48);
+        H.mc[ind - 1].ev = ev; H.mc[ind - 1].p = p; H.update_tree(ind, p);
+      } else die(" Vacancy in the SF setting");
+    }
+  }
 }
 // One list-directed READ of a plane of LenX*LenY numbers (LattGeo / TempStat / checkpoint files): starts on a fresh
 // record, continues onto following records while values are missing, and drops what is left of the last record read.
@@ -903,6 +1088,7 @@ int main(int argc, char **argv) {
   Host H; Run R;
   int box[3] = {480, 480, 480}; bool parallel = false; double ept = 4.0; int device = 0; const char *start = "start.dat";
   bool have_box = false;
+  const char *dump_state = nullptr;                             // --dump-state file: what is about to be uploaded, as text (tests compare it with the oracle's state)
   const char *sock_host = "localhost"; int sock_port = -1;     // la/main.f:102-131: -h hostname -p port => socket-driven run
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--box") && i + 3 < argc) { box[0] = atoi(argv[i + 1]); box[1] = atoi(argv[i + 2]); box[2] = atoi(argv[i + 3]); i += 3; have_box = true; }
@@ -911,6 +1097,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--events-per-tile") && i + 1 < argc) ept = atof(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
+    else if (!strcmp(argv[i], "--dump-state") && i + 1 < argc) dump_state = argv[++i];
     else if (!strcmp(argv[i], "-h") && i + 1 < argc) sock_host = argv[++i];
     else if (!strcmp(argv[i], "-p") && i + 1 < argc) sock_port = atoi(argv[++i]);
     else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file]\n", argv[0]); return 2; }
@@ -951,9 +1138,10 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "T") set_trench(H);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "ST") set_trench_si(H);
+  else if (H.InitSt == "SH") set_shape(H);
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, FF, ST, IN, LA; see DESIGN.md section 10)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, FF, ST, IN, SH, LA; see DESIGN.md section 10)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;
@@ -972,6 +1160,21 @@ int main(int argc, char **argv) {
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
   for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
   write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
+  if (dump_state) {
+    // the module globals the builder left, in list order: rates as raw bits, the ran3 stream position, a 64-bit FNV-1a of LattCoo
+    FILE *f = fopen(dump_state, "w"); if (!f) die(" cannot write %s", dump_state);
+    unsigned long long hsh = 1469598103934665603ull;
+    for (int32_t w : H.L) for (int b = 0; b < 4; b++) { hsh ^= (unsigned long long)(((uint32_t)w >> (8 * b)) & 255u); hsh *= 1099511628211ull; }
+    fprintf(f, "sizes %zu %zu %zu\nlattice_fnv %016llx\ncounts %d %d %d %d %d %d\nran3 %d %d %d %d", H.mc.size(), H.bulk.size(), H.voids.size(), hsh,
+            H.CountCrystal[0], H.CountCrystal[1], H.CountCrystal[2], H.CountCov[0], H.CountCov[1], H.CountCov[2], H.Idum, H.r_iff, H.r_inext, H.r_inextp);
+    for (int i = 1; i <= 55; i++) fprintf(f, " %d", H.r_ma[i]);
+    fputc('\n', f);
+    auto put_site = [&](const char *tag, const Site &a) { fprintf(f, "%s %d %d %d", tag, a.xyz[0], a.xyz[1], a.xyz[2]); for (int j = 0; j < 4; j++) fprintf(f, " %d %d %d", a.nn[j][0], a.nn[j][1], a.nn[j][2]); };
+    for (const Active &a : H.mc) { put_site("mc", a); unsigned long long bits; memcpy(&bits, &a.p, 8); fprintf(f, " %d %016llx\n", a.ev, bits); }
+    for (const Site &a : H.bulk) { put_site("bulk", a); fputc('\n', f); }
+    for (const Site &a : H.voids) { put_site("void", a); fputc('\n', f); }
+    fclose(f);
+  }
   // ---- hand the state to the GPU (include/mskc.h) ----
   if (mskc_create(H.LX, H.LY, H.LZ, H.NCrystal, H.NCov, H.ListCrystal, H.ListCov, device, 0, &R.h) != 0) die(" %s", mskc_last_error(nullptr));
   if (H.st()) MS(mskc_set_rate_field(R.h, H.ntemp, H.reftemp.data(), H.refPE.data(), H.refPD.data(), H.refPA.data(), H.refPS.data(), H.PtransZig,

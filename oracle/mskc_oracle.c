@@ -880,6 +880,7 @@ Orc *orc_create(int lenx, int leny, int lenz, int nummcmax) {
   o->Iter = 1; o->IterOut = 0; o->MaxIter = 2100000000; o->OutMolMol = 100000000;
   o->MaxTime = 100000000.0; o->OutTime = 10000000.0; o->Time = 0.0;
   o->Len1 = o->Len2 = o->Len3 = o->Len4 = 120;
+  o->alloy_lcg = 88172645463325252ull;                   /* stand-in for libgfortran's RAND() state (one stream per run, as a process has) */
   strcpy(o->outdir, ".");
   if (!o->LattCoo || !o->LattInd || !o->ListAdAtom || !o->Tree) { orc_destroy(o); return NULL; }
   return o;
@@ -1161,9 +1162,8 @@ static void set_wall_planes(Orc *o, int z0, int z1, int x0, int x1) {
  * second species.  The reference draws libgfortran's RAND() here, which is not part of the reference sources: a
  * documented 64-bit LCG stands in (alloy initial configurations: parity unpinned, SURVEY 8c trap 6). */
 static int alloy_species(Orc *o) {
-  static uint64_t lcg = 88172645463325252ull;
-  lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
-  double rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
+  o->alloy_lcg = o->alloy_lcg * 6364136223846793005ull + 1442695040888963407ull;
+  double rr = (double)(o->alloy_lcg >> 11) * (1.0 / 9007199254740992.0);
   int sp = rr > o->alloyfraction ? 1 : 2;
   o->CountCrystal[sp - 1]++;
   return sp;
@@ -1418,6 +1418,143 @@ static void set_trench_si(Orc *o, int Len, int Len2, int Len3, double angle, dou
   pass_probability(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0, 0);
 }
 
+/* src/initial/SetShape.f:25-507 (InitSt 'SH') and its caller src/main.f:281-286: an arbitrary structure given as a list of
+ * filled sites "sym x y z" (lattice units; planes z<=3 and z>=LenZ-4 become walls), neighbours found by scanning the whole
+ * first shell of the super-lattice (the 32 vectors with |v|^2 = 27: cubic and hexagonal bonds), then three passes that
+ * restore reciprocity of the bonds and create the empty active sites around the under-coordinated atoms */
+static void set_shape(Orc *o) {
+  int LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
+  char line[4096], sym[8];
+  LOG(o, " Reading input geometry file (SHAPE):  %s\n", o->cadfilename);
+  FILE *f = fopen(o->cadfilename, "r");
+  if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
+  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");
+  int NFilled = (int)strtol(line, NULL, 10);
+  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");          /* second line skipped, :54 */
+  for (int ia = 0; ia < NFilled; ia++) {
+    int x, y, z;
+    if (!next_line(f, line, sizeof line) || sscanf(line, " %7s %d %d %d", sym, &x, &y, &z) != 4) orc_fatal(o, "shape file: bad record %d", ia + 1);
+    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) orc_fatal(o, "shape file: site %d %d %d outside the box", x, y, z);
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    *w |= 1 << ORC_PosOcc;
+    if (z >= LZ - 4 || z <= 3) MVBITS(113, ORC_LenIndex, w, ORC_PosIndex);
+    else if (!strcmp(sym, "Si")) *w |= 1 << PSI(o);
+    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) *w |= 1 << PC_(o);
+  }
+  fclose(f);
+  LOG(o, " Done reading input geometry file\n");
+  int ListNN[32][3], nlist = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++)
+    if (i * i + j * j + k * k == 27) { ListNN[nlist][0] = i; ListNN[nlist][1] = j; ListNN[nlist][2] = k; nlist++; }
+  int32_t Site[3], NNSite[3], NextND[4][3], NextN[4][3], Buf[3]; int NewSites[2][3], ev; double Prob;
+  /* pass 1, :83-181: coordination from the full shell, bonds = the occupied shell sites (+ FIND_NN for the missing two) */
+  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 0) continue;
+    int Coord = 0, j = 0;
+    Site[0] = x; Site[1] = y; Site[2] = z;
+    memset(NextND, 0, sizeof NextND);
+    for (int i = 0; i < 32; i++) {
+      for (int k = 0; k < 3; k++) NNSite[k] = Site[k] + ListNN[i][k];
+      if (NNSite[0] >= LX) NNSite[0] -= LX;
+      if (NNSite[0] < 0) NNSite[0] += LX;
+      if (NNSite[1] >= LY) NNSite[1] -= LY;
+      if (NNSite[1] < 0) NNSite[1] += LY;
+      if (IBITS(LC(o, NNSite), ORC_PosOcc, ORC_LenOcc) > 0) {
+        Coord++;
+        if (j >= 4) orc_fatal(o, "SetShape: site %d %d %d has more than four occupied shell sites (the reference overruns NextND)", x, y, z);
+        cp3(NextND[j++], NNSite);
+      }
+    }
+    MVBITS(Coord, ORC_LenCoor, w, ORC_PosCoor);
+    if (Coord <= 3) {
+      cp3(Buf, NextND[2]);
+      orc_find_nn(NextND[0], NextND[1], Site, NewSites, LX, LY);
+      for (int k = 0; k < 3; k++) { NextND[2][k] = NewSites[0][k]; NextND[3][k] = NewSites[1][k]; }
+      if (Coord == 3) {
+        int Check = 1;
+        for (int i = 0; i < 4; i++) if (eq3(NextND[i], Buf)) Check = 0;
+        if (Check) LOG(o, " Coord.eq.3 wrong check Buf %d %d %d\n", Buf[0], Buf[1], Buf[2]);
+      }
+      int IAt = IBITS(*w, PSIC(o), LSIC(o));
+      Get_Prob_Ini(o, 1, IAt, Coord, Site, (const int32_t (*)[3])NextND, &ev, &Prob);
+      AddMC(o, Site, (const int32_t (*)[3])NextND, ev, Prob);
+    } else AddBulk(o, Site, (const int32_t (*)[3])NextND);
+  }
+  /* the reciprocity census shared by passes 2 and 3, :366-385 / :413-432 */
+#define SH_RECIPR_COOR(CoorVar) do { \
+    for (int j = 0; j < 4; j++) { \
+      int32_t wn = LC(o, NextN[j]); \
+      if (IBITS(wn, ORC_PosOcc, ORC_LenOcc) != 0) { \
+        int CoorNN = IBITS(wn, ORC_PosCoor, ORC_LenCoor), IndNN = LI(o, NextN[j]); \
+        const int32_t (*NextNN)[3] = CoorNN == 4 ? bulk_nn(o, IndNN) : mc_nn(o, IndNN); \
+        if (!recipr(NextNN, Site)) CoorVar--; \
+      } \
+    } } while (0)
+  /* pass 2, :358-398: active atoms lose the bonds their partner does not return */
+  for (int i = 1; i <= o->NumAdAtom; i++) {
+    cp3(Site, o->ListAdAtom[i].xyz); cpnn(NextN, o->ListAdAtom[i].nn);
+    int32_t *w = &LC(o, Site);
+    int Coor = IBITS(*w, ORC_PosCoor, ORC_LenCoor), Coorold = Coor;
+    SH_RECIPR_COOR(Coor);
+    if (Coor != Coorold) {
+      int IndS = LI(o, Site), IAt = IBITS(*w, PSIC(o), LSIC(o));
+      MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+      Get_Prob(o, 1, IAt, 0, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+      set_rate(o, IndS, ev, Prob); orc_update_tree(o, IndS, Prob);
+    }
+  }
+  /* pass 3, :404-449: bulk atoms (z >= 13) with a non-reciprocal bond become active; the loop bound is the list size at
+   * entry while EraseBulk swaps the last record into the hole, exactly as the Fortran DO does */
+  int N0 = o->NumAtoms;
+  for (int i = 1; i <= N0; i++) {
+    cp3(Site, o->ListAtom[i].xyz);
+    if (Site[2] < 13) continue;
+    cpnn(NextN, o->ListAtom[i].nn);
+    int32_t *w = &LC(o, Site);
+    int Coor = IBITS(*w, ORC_PosCoor, ORC_LenCoor), Coorold = Coor;
+    SH_RECIPR_COOR(Coor);
+    if (Coor != Coorold) {
+      int IAt = IBITS(*w, PSIC(o), LSIC(o));
+      MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+      Get_Prob(o, 1, IAt, 0, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+      EraseBulk(o, Site);
+      AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+    }
+  }
+#undef SH_RECIPR_COOR
+  /* pass 4, :455-503: the empty sites bonded to the active atoms join the active list */
+  int NumAdAtomold = o->NumAdAtom;
+  for (int i = 1; i <= NumAdAtomold; i++) {
+    cp3(NNSite, o->ListAdAtom[i].xyz);
+    for (int j = 0; j < 4; j++) {
+      cp3(Site, o->ListAdAtom[i].nn[j]);
+      int32_t *w = &LC(o, Site);
+      if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) != 0) continue;
+      memset(NextN, 0, sizeof NextN);
+      int Coor = IBITS(*w, ORC_PosCoor, ORC_LenCoor) + 1;
+      if (Coor == 1) {
+        cp3(NextN[0], NNSite);
+        MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+        Get_Prob_Ini(o, 0, 0, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+        AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+      } else if (Coor == 2 || Coor == 3) {
+        int IndS = LI(o, Site);
+        cpnn(NextN, o->ListAdAtom[IndS].nn);
+        if (Coor == 2) {
+          cp3(NextN[1], NNSite);
+          orc_find_nn(NextN[0], NextN[1], Site, NewSites, LX, LY);
+          for (int k = 0; k < 3; k++) { NextN[2][k] = NewSites[0][k]; NextN[3][k] = NewSites[1][k]; }
+        }
+        MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+        Get_Prob_Ini(o, 0, 0, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+        if (Coor == 2) cpnn(o->ListAdAtom[IndS].nn, NextN);
+        set_rate(o, IndS, ev, Prob); orc_update_tree(o, IndS, Prob);
+      } else orc_fatal(o, "Vacancy in the SF setting");
+    }
+  }
+}
+
 /* list-directed READ of one plane (LattGeo / TempStat files): take n values starting on a fresh
  * record, continue onto following records only if the record is short, and DISCARD whatever is left
  * on the last record read -- the regression LattGeo file has a line with one value too many. */
@@ -1508,8 +1645,8 @@ static void set_cad(Orc *o) {
              * with alloyfraction==0 every draw selects Si, which is all the goldens exercise. */
             double rr = 1.0;
             if (o->alloyfraction > 0 && !(la && z <= (LZ - (int)((o->LenVac + LenSiGe) / o->sf)))) {
-              static uint64_t lcg = 88172645463325252ull; lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
-              rr = (double)(lcg >> 11) * (1.0 / 9007199254740992.0);
+              o->alloy_lcg = o->alloy_lcg * 6364136223846793005ull + 1442695040888963407ull;
+              rr = (double)(o->alloy_lcg >> 11) * (1.0 / 9007199254740992.0);
             }
             *w |= 1 << (rr >= o->alloyfraction ? PSI(o) : PC_(o));
             if (o->la_tree) o->CountCrystal[rr >= o->alloyfraction ? 0 : 1]++;                 /* la/SetCAD.f:150-155 */
@@ -1566,6 +1703,7 @@ int orc_setup(Orc *o) {
     o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;
     set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
   } else if (!strcmp(s, "ST")) set_trench_si(o, o->Len1, o->Len2, o->Len3, o->angle, o->Ttop, o->Tbottom);
+  else if (!strcmp(s, "SH")) set_shape(o);
   else if (!strcmp(s, "IN")) set_cad(o);
   else if (!strcmp(s, "LA")) { o->tmax = 0; set_T(o); set_cad(o); LOG(o, " Max temperature is:  %d K\n", o->tmax); }
   else orc_fatal(o, "initialization not_implemented in oracle: %s", s);

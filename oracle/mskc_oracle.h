@@ -72,6 +72,7 @@ typedef struct Orc {
   /* ran3 state (src/mcevent/random.f:32-34, SAVEd) */
   int r_iff, r_inext, r_inextp, r_ma[56];
   int64_t counter;                     /* numberslist cursor (src/modules/definitions.f:35) */
+  uint64_t alloy_lcg;                  /* state of the documented LCG that stands in for RAND() in the alloy builders */
   int32_t NBuff_evap[3];               /* Evaporation.f's un-initialised NBuff, kept across calls */
   /* bookkeeping added by the oracle */
   int64_t n_getprob, n_ran3, n_events[8];

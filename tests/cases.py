@@ -206,3 +206,43 @@ def make_la_tree_case(dirpath, box=(96, 96, 96), lennuc=18.0, maxiter=10**9, sig
     with open(dst, "w") as f:
         f.write("\n".join(L) + "\n")
     return dst
+
+
+def make_shape_case(dirpath, box=(144, 144, 144), lens=(48, 48, 48), maxiter=10**9, table="cube"):
+    """InitSt SH (initial/SetShape.f): a shape file "sym x y z" per filled site.  The shape is the parallelepiped of
+    initial/SetNC.f with the 0- and 1-coordinated atoms peeled off (SetShape.f:98 expects that; coordination counted on the
+    full first shell, as SetShape does), written in z,y,x order; start.dat = the cube's table with InitSt SH + the path."""
+    lx, ly, lz = box
+    l1, l2, l3 = lens
+    sites = {}
+    for z in range(lz // 2 - l3 // 2, lz // 2 + l3 // 2):
+        for y in range(ly // 2 - l2 // 2, ly // 2 + l2 // 2):
+            for x in range(lx // 2 - l1 // 2, lx // 2 + l1 // 2):
+                if x % 3 or y % 3 or z % 3:
+                    continue
+                x1, y1, z1 = x // 3, y // 3, z // 3
+                if (x1 % 2) != (y1 % 2) or (x1 % 2) != (z1 % 2):
+                    continue
+                m = (x1 + y1 + z1) % 4
+                if m in (0, 3):
+                    sites[(x, y, z)] = "Si" if m == 0 else "C"
+    shell = [(i, j, k) for k in range(-6, 7) for j in range(-6, 7) for i in range(-6, 7) if i * i + j * j + k * k == 27]
+    while True:
+        weak = [s for s in sites if sum(((s[0] + d[0]) % lx, (s[1] + d[1]) % ly, s[2] + d[2]) in sites for d in shell) <= 1]
+        if not weak:
+            break
+        for s in weak:
+            del sites[s]
+    shape = os.path.join(dirpath, "shape.xyz")
+    with open(shape, "w") as f:
+        f.write(f"{len(sites)}\nparallelepiped, 0- and 1-coordinated atoms removed\n")
+        for (x, y, z), sym in sorted(sites.items(), key=lambda kv: (kv[0][2], kv[0][1], kv[0][0])):
+            f.write(f"{sym} {x} {y} {z}\n")
+    dst = os.path.join(dirpath, "start.dat")
+    make_start(table, dst, initst="SH", maxiter=maxiter, outmolmol=maxiter)
+    lines = open(dst).read().split("\n")
+    i = next(k for k, l in enumerate(lines) if l.split() and l.split()[0] == "SH")
+    lines[i + 1] = shape                       # the Len line of the cube's file becomes the path line (main.f:116-117)
+    with open(dst, "w") as f:
+        f.write("\n".join(lines))
+    return dst

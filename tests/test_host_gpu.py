@@ -269,3 +269,24 @@ def test_host_parallel_mode(built, tmp_path, kind):
     assert t is not None and int(t[3]) > 20000 and float(t[4]) > 0
     err = open(tmp_path / "err.txt").read()
     assert "sublattice-sampler" in err
+
+
+def test_shape_builder(built, tmp_path):
+    """InitSt SH (initial/SetShape.f): a structure given as a list of filled sites, neighbours found on the whole first
+    shell, through the host program with the loop on the GPU; every output file and the log tokens equal the oracle's."""
+    from cases import make_shape_case
+    box = (144, 144, 144)
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    start = make_shape_case(str(tmp_path), box=box, maxiter=60000)
+    for d in (g, o):
+        (d / "start.dat").write_text(open(start).read())
+    args = ["--box", *[str(v) for v in box]]
+    _run(ORACLE, o, args)
+    _run(EXE, g, args)
+    names = sorted(p.name for p in o.glob("I*.xyz"))
+    assert len(names) >= 6
+    for name in names:
+        assert (g / name).read_bytes() == (o / name).read_bytes(), f"SH: {name} differs from the oracle's"
+    for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad"):
+        assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
