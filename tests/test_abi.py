@@ -73,3 +73,30 @@ def test_product_does_not_touch_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", "Makefile")):
                     t = open(os.path.join(dp, f), errors="ignore").read()
                     assert "oracle_binding" not in t and "mskc_oracle" not in t and "libmskc_oracle" not in t, os.path.join(dp, f)
+
+
+def test_null_handle_is_an_error_not_a_crash(lib):
+    """Every entry point that takes a handle returns a negative status for a NULL handle and leaves a message in
+    mskc_last_error(NULL) -- errors come back as int + text, never as a crash or an exception across the boundary
+    (include/mskc.h conventions).  No compute call is made: nothing here needs a GPU."""
+    null = C.c_void_p(None)
+    calls = {
+        "mskc_set_rates": (null, None, None, None, None, C.c_double(1.0)),
+        "mskc_set_la": (null, 1, C.c_double(1688.0), C.c_double(1e17), C.c_double(280.0), C.c_double(1080.0), 1600, 1700),
+        "mskc_set_rate_field": (null, 1, None, None, None, None, None, C.c_double(1.0), 900, 1000, 0),
+        "mskc_set_tree_variant": (null, 1),
+        "mskc_set_la_fork": (null, 1, None, None, None, None, 1600, 1700, None, 0, 0),
+        "mskc_upload_state": (null, None, 0, None, None, None, None, 0, None, None, 0, None, None),
+        "mskc_run_parity": (null, None, None),
+        "mskc_run_parallel": (null, None, None),
+        "mskc_download_lattice": (null, None),
+        "mskc_get_counters": (null, None),
+        "mskc_set_temperature": (null, None),
+        "mskc_extract_frame": (null, 0, None, None, None, None),
+        "mskc_replay_events": (null, 0, None, None, None, C.c_double(1.0)),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc < 0, name
+        msg = lib.mskc_last_error(None).decode()
+        assert msg, name
