@@ -1,4 +1,5 @@
-"""Probe of the serial-parity kernel: one reduced regression case, N events in one launch (for ncu / timing)."""
+"""Probe of the serial-parity kernel: one reduced regression case, N events in one launch (for ncu / timing).
+Lives under tests/ because it takes its initial state from the oracle (test infrastructure)."""
 import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
