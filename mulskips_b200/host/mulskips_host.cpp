@@ -666,58 +666,11 @@ void find_nn(const Host &H, const int32_t S1[3], const int32_t S2[3], const int3
     if (out[irot - 1][1] < 0) out[irot - 1][1] += H.LY;
   }
 }
-// initial/SetShape.f:25-507 (InitSt SH; main.f:281-286): an arbitrary structure from a list "sym x y z" of filled sites.
-// Neighbours are found on the whole first shell (32 vectors, cubic + hexagonal bonds); three passes then restore the
-// reciprocity of the bonds and list the empty sites around the under-coordinated atoms.
-void set_shape(Host &H) {
-  const int LX = H.LX, LY = H.LY, LZ = H.LZ;
-  H.LI.assign(H.L.size(), 0);
-  printf(" Reading input geometry file (SHAPE):  %s\n", H.cadfile.c_str());
-  Lines in; in.f = fopen(H.cadfile.c_str(), "r"); if (!in.f) die(" cannot open %s", H.cadfile.c_str());
-  const int NFilled = (int)strtol(in.next(), nullptr, 10);
-  in.next();                                                 // the second line is skipped (:54)
-  for (int ia = 0; ia < NFilled; ia++) {
-    char sym[8]; int x, y, z;
-    if (sscanf(in.next(), " %7s %d %d %d", sym, &x, &y, &z) != 4) die(" shape file: bad record %d", ia + 1);
-    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) die(" shape file: site %d %d %d outside the box", x, y, z);
-    int32_t &w = H.L[H.ci(x, y, z)];
-    w |= 1 << PosOcc;
-    if (z >= LZ - 4 || z <= 3) mvbits(113, LenIndex, w, PosIndex);
-    else if (!strcmp(sym, "Si")) w |= 1 << PosSi;
-    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) w |= 1 << PosC;
-  }
-  fclose(in.f);
-  printf(" Done reading input geometry file\n");
-  int shell[32][3], n = 0;
-  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++) if (i * i + j * j + k * k == 27) { shell[n][0] = i; shell[n][1] = j; shell[n][2] = k; n++; }
-  int32_t s[3], q[3], nd[4][3], nn[4][3], fresh[2][3]; int ev; double p;
-  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {       // pass 1, :83-181
-    int32_t &w = H.L[H.ci(x, y, z)];
-    if (ibits(w, PosOcc, 1) == 0) continue;
-    s[0] = x; s[1] = y; s[2] = z;
-    memset(nd, 0, sizeof nd);
-    int Coord = 0;
-    for (int i = 0; i < 32; i++) {
-      for (int k = 0; k < 3; k++) q[k] = s[k] + shell[i][k];
-      if (q[0] >= LX) q[0] -= LX;
-      if (q[0] < 0) q[0] += LX;
-      if (q[1] >= LY) q[1] -= LY;
-      if (q[1] < 0) q[1] += LY;
-      if (ibits(H.word(q), PosOcc, 1) > 0) {
-        if (Coord >= 4) die(" SetShape: site %d %d %d has more than four occupied shell sites", x, y, z);
-        memcpy(nd[Coord++], q, 12);
-      }
-    }
-    mvbits(Coord, LenCoor, w, PosCoor);
-    if (Coord <= 3) {
-      int32_t keep[3]; memcpy(keep, nd[2], 12);
-      find_nn(H, nd[0], nd[1], s, fresh);
-      memcpy(nd[2], fresh[0], 12); memcpy(nd[3], fresh[1], 12);
-      if (Coord == 3 && !Host::lists(nd, keep)) printf(" Coord.eq.3 wrong check Buf %d %d %d\n", keep[0], keep[1], keep[2]);
-      H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coord, s, nd, ev, p);
-      H.AddMC(s, nd, ev, p);
-    } else H.AddBulk(s, nd);
-  }
+// The three closing passes shared by SetShape.f:356-503 and SetSiCSF.f:325-470: (2) active atoms lose the bonds their partner does
+// not return, (3) bulk atoms (z >= 13) with a non-reciprocal bond become active, (4) the empty sites bonded to the active atoms
+// join the active list
+void shape_passes(Host &H) {
+  int32_t s[3], nn[4][3], fresh[2][3]; int ev; double p;
   auto recipr_coor = [&](const int32_t site[3], const int32_t bonds[4][3], int Coor) {                 // :366-385 / :413-432
     for (int j = 0; j < 4; j++) {
       const int32_t wn = H.word(bonds[j]);
@@ -779,6 +732,144 @@ void set_shape(Host &H) {
       } else die(" Vacancy in the SF setting");
     }
   }
+}
+// initial/SetShape.f:25-507 (InitSt SH; main.f:281-286): an arbitrary structure from a list "sym x y z" of filled sites.
+// Neighbours are found on the whole first shell (32 vectors, cubic + hexagonal bonds); three passes then restore the
+// reciprocity of the bonds and list the empty sites around the under-coordinated atoms.
+void set_shape(Host &H) {
+  const int LX = H.LX, LY = H.LY, LZ = H.LZ;
+  H.LI.assign(H.L.size(), 0);
+  printf(" Reading input geometry file (SHAPE):  %s\n", H.cadfile.c_str());
+  Lines in; in.f = fopen(H.cadfile.c_str(), "r"); if (!in.f) die(" cannot open %s", H.cadfile.c_str());
+  const int NFilled = (int)strtol(in.next(), nullptr, 10);
+  in.next();                                                 // the second line is skipped (:54)
+  for (int ia = 0; ia < NFilled; ia++) {
+    char sym[8]; int x, y, z;
+    if (sscanf(in.next(), " %7s %d %d %d", sym, &x, &y, &z) != 4) die(" shape file: bad record %d", ia + 1);
+    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) die(" shape file: site %d %d %d outside the box", x, y, z);
+    int32_t &w = H.L[H.ci(x, y, z)];
+    w |= 1 << PosOcc;
+    if (z >= LZ - 4 || z <= 3) mvbits(113, LenIndex, w, PosIndex);
+    else if (!strcmp(sym, "Si")) w |= 1 << PosSi;
+    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) w |= 1 << PosC;
+  }
+  fclose(in.f);
+  printf(" Done reading input geometry file\n");
+  int shell[32][3], n = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++) if (i * i + j * j + k * k == 27) { shell[n][0] = i; shell[n][1] = j; shell[n][2] = k; n++; }
+  int32_t s[3], q[3], nd[4][3], fresh[2][3]; int ev; double p;
+  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {       // pass 1, :83-181
+    int32_t &w = H.L[H.ci(x, y, z)];
+    if (ibits(w, PosOcc, 1) == 0) continue;
+    s[0] = x; s[1] = y; s[2] = z;
+    memset(nd, 0, sizeof nd);
+    int Coord = 0;
+    for (int i = 0; i < 32; i++) {
+      for (int k = 0; k < 3; k++) q[k] = s[k] + shell[i][k];
+      if (q[0] >= LX) q[0] -= LX;
+      if (q[0] < 0) q[0] += LX;
+      if (q[1] >= LY) q[1] -= LY;
+      if (q[1] < 0) q[1] += LY;
+      if (ibits(H.word(q), PosOcc, 1) > 0) {
+        if (Coord >= 4) die(" SetShape: site %d %d %d has more than four occupied shell sites", x, y, z);
+        memcpy(nd[Coord++], q, 12);
+      }
+    }
+    mvbits(Coord, LenCoor, w, PosCoor);
+    if (Coord <= 3) {
+      int32_t keep[3]; memcpy(keep, nd[2], 12);
+      find_nn(H, nd[0], nd[1], s, fresh);
+      memcpy(nd[2], fresh[0], 12); memcpy(nd[3], fresh[1], 12);
+      if (Coord == 3 && !Host::lists(nd, keep)) printf(" Coord.eq.3 wrong check Buf %d %d %d\n", keep[0], keep[1], keep[2]);
+      H.get_prob_ini(1, ibits(w, PosSiC, LenSiC), Coord, s, nd, ev, p);
+      H.AddMC(s, nd, ev, p);
+    } else H.AddBulk(s, nd);
+  }
+  shape_passes(H);
+}
+// initial/SetSiCSF.f:25-473 (InitSt E; main.f:267-272: Len = Len1, vertex VSF = (Len2, Len3, Len1-Len2)): a 3C-SiC (001) slab with a
+// triple stacking fault -- the atoms of two {111} planes through the vertex are shifted off the cubic sub-lattice by (2,2,4) and
+// (-2,-2,-4) -- then the shell neighbour search of SetShape.f for the atoms the cubic bonds do not explain, and the same closing passes
+void set_sic_sf(Host &H, int Len, const int VSF[3]) {
+  const int LX = H.LX, LY = H.LY;
+  H.LI.assign(H.L.size(), 0);
+  int kind; int32_t s[3], q[3], nn[4][3], nd[4][3], fresh[2][3]; int ev; double p;
+  const int BoxSF = Len - VSF[2];
+  int shell[32][3], n = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++) if (i * i + j * j + k * k == 27) { shell[n][0] = i; shell[n][1] = j; shell[n][2] = k; n++; }
+  if (VSF[0] + BoxSF > LX || VSF[1] + BoxSF > LY || BoxSF <= 0) die(" error SF dimension is not correctly set");
+  if (!(cubic_site(VSF[0], VSF[1], VSF[2], kind) && kind == 0)) die(" SF Vertex position in wrong Site %d %d %d %d", VSF[0], VSF[1], VSF[2], Len);
+  printf(" SF Vertex position in a Si Site %d %d %d %d\n", VSF[0], VSF[1], VSF[2], Len);
+  for (int z = 0; z <= 12; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind)) {
+      occupy(H, x, y, z, kind, true); mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn);
+    }
+  for (int z = 13; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          // :114-168
+    if (!cubic_site(x, y, z, kind)) continue;
+    int p1 = -1, p2 = -1;
+    if (x >= VSF[0] && y >= VSF[1] && z >= VSF[2]) { const int d = (x - VSF[0]) + (y - VSF[1]) - (z - VSF[2]); p1 = d - (kind ? 3 : 12); p2 = d - (kind ? 15 : 24); }
+    if (p1 == 0) { if (x + 2 < LX && y + 2 < LY && z + 4 < Len) occupy(H, x + 2, y + 2, z + 4, kind, true); }
+    else if (p2 == 0) { if (x - 2 > 0 && y - 2 > 0 && z - 4 > 0) occupy(H, x - 2, y - 2, z - 4, kind, true); }
+    else occupy(H, x, y, z, kind, true);
+  }
+  // cubic bonds by sub-lattice (integer divisions, also for the shifted atoms); the whole first shell when fewer than two are filled
+  int Coor, Coord;
+  auto neighbours = [&](int x, int y, int z) {
+    Coor = 0; Coord = 0;
+    s[0] = x; s[1] = y; s[2] = z;
+    dia_nn(H, x, y, z, ((x / 3 + y / 3 + z / 3) % 4 == 3) ? 1 : 0, nn);
+    for (int i = 0; i < 4; i++) if (ibits(H.word(nn[i]), PosOcc, 1) > 0) Coor++;
+    if (Coor >= 2) return;
+    memset(nd, 0, sizeof nd);
+    for (int i = 0; i < 32; i++) {
+      for (int k = 0; k < 3; k++) q[k] = s[k] + shell[i][k];
+      if (q[0] >= LX) q[0] -= LX;
+      if (q[0] < 0) q[0] += LX;
+      if (q[1] >= LY) q[1] -= LY;
+      if (q[1] < 0) q[1] += LY;
+      if (ibits(H.word(q), PosOcc, 1) > 0) {
+        if (Coord >= 4) die(" SetSiCSF: site %d %d %d has more than four occupied shell sites", x, y, z);
+        memcpy(nd[Coord++], q, 12);
+      }
+    }
+  };
+  auto bond_check = [&](int m) {
+    for (int i = 0; i < m - 1; i++) for (int k = i + 1; k < m; k++) {
+      const int d = (nd[i][0] - nd[k][0]) * (nd[i][0] - nd[k][0]) + (nd[i][1] - nd[k][1]) * (nd[i][1] - nd[k][1]) + (nd[i][2] - nd[k][2]) * (nd[i][2] - nd[k][2]);
+      if (d != 72) printf(" not correct bonds direction\n %d %d %d %d %d %d\n", nd[i][0], nd[i][1], nd[i][2], nd[k][0], nd[k][1], nd[k][2]);
+    }
+  };
+  for (int z = 13; z <= Len + 6; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          // :171-229
+    int32_t &w = H.L[H.ci(x, y, z)];
+    if (ibits(w, PosOcc, 1) == 0) continue;
+    neighbours(x, y, z);
+    if (Coord > Coor) { bond_check(Coord); if (Coord <= 1) w = 0; }
+    else if (Coor <= 1) w = 0;
+  }
+  for (int z = 13; z <= Len + 6; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          // :231-323
+    int32_t &w = H.L[H.ci(x, y, z)];
+    if (ibits(w, PosOcc, 1) == 0) continue;
+    neighbours(x, y, z);
+    const int IAt = ibits(w, PosSiC, LenSiC);
+    if (Coord > Coor) {
+      mvbits(Coord, LenCoor, w, PosCoor);
+      if (Coord <= 3) {
+        int32_t keep[3]; memcpy(keep, nd[2], 12);
+        find_nn(H, nd[0], nd[1], s, fresh);
+        memcpy(nd[2], fresh[0], 12); memcpy(nd[3], fresh[1], 12);
+        if (Coord == 3 && !Host::lists(nd, keep)) printf(" Coord.eq.3 wrong check Buf %d %d %d\n", keep[0], keep[1], keep[2]);
+        bond_check(4);
+        H.get_prob_ini(1, IAt, Coord, s, nd, ev, p);
+        H.AddMC(s, nd, ev, p);
+      } else H.AddBulk(s, nd);
+    } else {
+      mvbits(Coor, LenCoor, w, PosCoor);
+      if (Coor <= 3) { H.get_prob_ini(1, IAt, Coor, s, nn, ev, p); H.AddMC(s, nn, ev, p); }
+      else H.AddBulk(s, nn);
+    }
+  }
+  shape_passes(H);
 }
 // One list-directed READ of a plane of LenX*LenY numbers (LattGeo / TempStat / checkpoint files): starts on a fresh
 // record, continues onto following records while values are missing, and drops what is left of the last record read.
@@ -1139,9 +1230,14 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "ST") set_trench_si(H);
   else if (H.InitSt == "SH") set_shape(H);
+  else if (H.InitSt == "E") {                                 // main.f:267-272
+    const int VSF[3] = {H.Len2, H.Len3, H.Len1 - H.Len2};
+    printf(" %d %d %d %d\n", H.Len1, VSF[0], VSF[1], VSF[2]);
+    set_sic_sf(H, H.Len1, VSF);
+  }
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, FF, ST, IN, SH, LA; see DESIGN.md section 10)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, E, FF, ST, IN, SH, LA; see DESIGN.md section 10)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;

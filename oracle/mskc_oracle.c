@@ -1418,69 +1418,12 @@ static void set_trench_si(Orc *o, int Len, int Len2, int Len3, double angle, dou
   pass_probability(o, 21, Len3 + 9, 0, LY - 1, 0, LX - 1, 0, 0);
 }
 
-/* src/initial/SetShape.f:25-507 (InitSt 'SH') and its caller src/main.f:281-286: an arbitrary structure given as a list of
- * filled sites "sym x y z" (lattice units; planes z<=3 and z>=LenZ-4 become walls), neighbours found by scanning the whole
- * first shell of the super-lattice (the 32 vectors with |v|^2 = 27: cubic and hexagonal bonds), then three passes that
- * restore reciprocity of the bonds and create the empty active sites around the under-coordinated atoms */
-static void set_shape(Orc *o) {
-  int LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
-  char line[4096], sym[8];
-  LOG(o, " Reading input geometry file (SHAPE):  %s\n", o->cadfilename);
-  FILE *f = fopen(o->cadfilename, "r");
-  if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
-  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");
-  int NFilled = (int)strtol(line, NULL, 10);
-  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");          /* second line skipped, :54 */
-  for (int ia = 0; ia < NFilled; ia++) {
-    int x, y, z;
-    if (!next_line(f, line, sizeof line) || sscanf(line, " %7s %d %d %d", sym, &x, &y, &z) != 4) orc_fatal(o, "shape file: bad record %d", ia + 1);
-    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) orc_fatal(o, "shape file: site %d %d %d outside the box", x, y, z);
-    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
-    *w |= 1 << ORC_PosOcc;
-    if (z >= LZ - 4 || z <= 3) MVBITS(113, ORC_LenIndex, w, ORC_PosIndex);
-    else if (!strcmp(sym, "Si")) *w |= 1 << PSI(o);
-    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) *w |= 1 << PC_(o);
-  }
-  fclose(f);
-  LOG(o, " Done reading input geometry file\n");
-  int ListNN[32][3], nlist = 0;
-  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++)
-    if (i * i + j * j + k * k == 27) { ListNN[nlist][0] = i; ListNN[nlist][1] = j; ListNN[nlist][2] = k; nlist++; }
-  int32_t Site[3], NNSite[3], NextND[4][3], NextN[4][3], Buf[3]; int NewSites[2][3], ev; double Prob;
-  /* pass 1, :83-181: coordination from the full shell, bonds = the occupied shell sites (+ FIND_NN for the missing two) */
-  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
-    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
-    if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 0) continue;
-    int Coord = 0, j = 0;
-    Site[0] = x; Site[1] = y; Site[2] = z;
-    memset(NextND, 0, sizeof NextND);
-    for (int i = 0; i < 32; i++) {
-      for (int k = 0; k < 3; k++) NNSite[k] = Site[k] + ListNN[i][k];
-      if (NNSite[0] >= LX) NNSite[0] -= LX;
-      if (NNSite[0] < 0) NNSite[0] += LX;
-      if (NNSite[1] >= LY) NNSite[1] -= LY;
-      if (NNSite[1] < 0) NNSite[1] += LY;
-      if (IBITS(LC(o, NNSite), ORC_PosOcc, ORC_LenOcc) > 0) {
-        Coord++;
-        if (j >= 4) orc_fatal(o, "SetShape: site %d %d %d has more than four occupied shell sites (the reference overruns NextND)", x, y, z);
-        cp3(NextND[j++], NNSite);
-      }
-    }
-    MVBITS(Coord, ORC_LenCoor, w, ORC_PosCoor);
-    if (Coord <= 3) {
-      cp3(Buf, NextND[2]);
-      orc_find_nn(NextND[0], NextND[1], Site, NewSites, LX, LY);
-      for (int k = 0; k < 3; k++) { NextND[2][k] = NewSites[0][k]; NextND[3][k] = NewSites[1][k]; }
-      if (Coord == 3) {
-        int Check = 1;
-        for (int i = 0; i < 4; i++) if (eq3(NextND[i], Buf)) Check = 0;
-        if (Check) LOG(o, " Coord.eq.3 wrong check Buf %d %d %d\n", Buf[0], Buf[1], Buf[2]);
-      }
-      int IAt = IBITS(*w, PSIC(o), LSIC(o));
-      Get_Prob_Ini(o, 1, IAt, Coord, Site, (const int32_t (*)[3])NextND, &ev, &Prob);
-      AddMC(o, Site, (const int32_t (*)[3])NextND, ev, Prob);
-    } else AddBulk(o, Site, (const int32_t (*)[3])NextND);
-  }
+/* The three closing passes shared by SetShape.f:356-503 and SetSiCSF.f:325-470: (2) active atoms lose the bonds their
+ * partner does not return, (3) bulk atoms (z >= 13) with a non-reciprocal bond become active, (4) the empty sites bonded
+ * to the active atoms join the active list */
+static void shape_passes(Orc *o) {
+  int LX = o->LenX, LY = o->LenY;
+  int32_t Site[3], NNSite[3], NextN[4][3]; int NewSites[2][3], ev; double Prob;
   /* the reciprocity census shared by passes 2 and 3, :366-385 / :413-432 */
 #define SH_RECIPR_COOR(CoorVar) do { \
     for (int j = 0; j < 4; j++) { \
@@ -1553,6 +1496,175 @@ static void set_shape(Orc *o) {
       } else orc_fatal(o, "Vacancy in the SF setting");
     }
   }
+}
+
+/* src/initial/SetShape.f:25-507 (InitSt 'SH') and its caller src/main.f:281-286: an arbitrary structure given as a list of
+ * filled sites "sym x y z" (lattice units; planes z<=3 and z>=LenZ-4 become walls), neighbours found by scanning the whole
+ * first shell of the super-lattice (the 32 vectors with |v|^2 = 27: cubic and hexagonal bonds), then three passes that
+ * restore reciprocity of the bonds and create the empty active sites around the under-coordinated atoms */
+static void set_shape(Orc *o) {
+  int LX = o->LenX, LY = o->LenY, LZ = o->LenZ;
+  char line[4096], sym[8];
+  LOG(o, " Reading input geometry file (SHAPE):  %s\n", o->cadfilename);
+  FILE *f = fopen(o->cadfilename, "r");
+  if (!f) orc_fatal(o, "cannot open %s", o->cadfilename);
+  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");
+  int NFilled = (int)strtol(line, NULL, 10);
+  if (!next_line(f, line, sizeof line)) orc_fatal(o, "shape file: EOF");          /* second line skipped, :54 */
+  for (int ia = 0; ia < NFilled; ia++) {
+    int x, y, z;
+    if (!next_line(f, line, sizeof line) || sscanf(line, " %7s %d %d %d", sym, &x, &y, &z) != 4) orc_fatal(o, "shape file: bad record %d", ia + 1);
+    if (x < 0 || x >= LX || y < 0 || y >= LY || z < 0 || z > LZ) orc_fatal(o, "shape file: site %d %d %d outside the box", x, y, z);
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    *w |= 1 << ORC_PosOcc;
+    if (z >= LZ - 4 || z <= 3) MVBITS(113, ORC_LenIndex, w, ORC_PosIndex);
+    else if (!strcmp(sym, "Si")) *w |= 1 << PSI(o);
+    else if (!strcmp(sym, "C") || !strcmp(sym, "Ge")) *w |= 1 << PC_(o);
+  }
+  fclose(f);
+  LOG(o, " Done reading input geometry file\n");
+  int ListNN[32][3], nlist = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++)
+    if (i * i + j * j + k * k == 27) { ListNN[nlist][0] = i; ListNN[nlist][1] = j; ListNN[nlist][2] = k; nlist++; }
+  int32_t Site[3], NNSite[3], NextND[4][3], Buf[3]; int NewSites[2][3], ev; double Prob;
+  /* pass 1, :83-181: coordination from the full shell, bonds = the occupied shell sites (+ FIND_NN for the missing two) */
+  for (int z = 4; z <= LZ - 5; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 0) continue;
+    int Coord = 0, j = 0;
+    Site[0] = x; Site[1] = y; Site[2] = z;
+    memset(NextND, 0, sizeof NextND);
+    for (int i = 0; i < 32; i++) {
+      for (int k = 0; k < 3; k++) NNSite[k] = Site[k] + ListNN[i][k];
+      if (NNSite[0] >= LX) NNSite[0] -= LX;
+      if (NNSite[0] < 0) NNSite[0] += LX;
+      if (NNSite[1] >= LY) NNSite[1] -= LY;
+      if (NNSite[1] < 0) NNSite[1] += LY;
+      if (IBITS(LC(o, NNSite), ORC_PosOcc, ORC_LenOcc) > 0) {
+        Coord++;
+        if (j >= 4) orc_fatal(o, "SetShape: site %d %d %d has more than four occupied shell sites (the reference overruns NextND)", x, y, z);
+        cp3(NextND[j++], NNSite);
+      }
+    }
+    MVBITS(Coord, ORC_LenCoor, w, ORC_PosCoor);
+    if (Coord <= 3) {
+      cp3(Buf, NextND[2]);
+      orc_find_nn(NextND[0], NextND[1], Site, NewSites, LX, LY);
+      for (int k = 0; k < 3; k++) { NextND[2][k] = NewSites[0][k]; NextND[3][k] = NewSites[1][k]; }
+      if (Coord == 3) {
+        int Check = 1;
+        for (int i = 0; i < 4; i++) if (eq3(NextND[i], Buf)) Check = 0;
+        if (Check) LOG(o, " Coord.eq.3 wrong check Buf %d %d %d\n", Buf[0], Buf[1], Buf[2]);
+      }
+      int IAt = IBITS(*w, PSIC(o), LSIC(o));
+      Get_Prob_Ini(o, 1, IAt, Coord, Site, (const int32_t (*)[3])NextND, &ev, &Prob);
+      AddMC(o, Site, (const int32_t (*)[3])NextND, ev, Prob);
+    } else AddBulk(o, Site, (const int32_t (*)[3])NextND);
+  }
+  shape_passes(o);
+}
+
+/* src/initial/SetSiCSF.f:25-473 (InitSt 'E'; main.f:267-272 passes Len = Len1 and the vertex VSF = (Len2, Len3, Len1-Len2)):
+ * a 3C-SiC (001) slab with a triple stacking fault -- the atoms of two {111} planes through the vertex are shifted off the
+ * cubic sub-lattice by (2,2,4) and (-2,-2,-4) -- then the neighbour search of SetShape.f for the atoms the cubic bonds do
+ * not explain, and the same three closing passes */
+static void set_sic_sf(Orc *o, int Len, const int VSF[3]) {
+  int LX = o->LenX, LY = o->LenY, kind;
+  int32_t Site[3], NNSite[3], NextN[4][3], NextND[4][3], Buf[3]; int NewSites[2][3], ev; double Prob;
+  int BoxSF = Len - VSF[2];
+  int ListNN[32][3], nlist = 0;
+  for (int k = -6; k <= 6; k++) for (int j = -6; j <= 6; j++) for (int i = -6; i <= 6; i++)
+    if (i * i + j * j + k * k == 27) { ListNN[nlist][0] = i; ListNN[nlist][1] = j; ListNN[nlist][2] = k; nlist++; }
+  if (VSF[0] + BoxSF > LX || VSF[1] + BoxSF > LY || BoxSF <= 0) orc_fatal(o, "error SF dimension is not correctly set");
+  if (!(is_cubic_site(VSF[0], VSF[1], VSF[2], &kind) && kind == 0)) { LOG(o, " SF Vertex position in wrong Site %d %d %d %d\n", VSF[0], VSF[1], VSF[2], Len); orc_fatal(o, "SF Vertex position in wrong Site"); }
+  LOG(o, " SF Vertex position in a Si Site %d %d %d %d\n", VSF[0], VSF[1], VSF[2], Len);
+  for (int z = 0; z <= 12; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)               /* :64-111 */
+    if (is_cubic_site(x, y, z, &kind)) {
+      occupy(o, x, y, z, kind, 1);
+      MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  for (int z = 13; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          /* :114-168 */
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    int p1 = -1, p2 = -1;
+    if (x >= VSF[0] && y >= VSF[1] && z >= VSF[2]) {
+      int d = (x - VSF[0]) + (y - VSF[1]) - (z - VSF[2]);
+      p1 = d - (kind ? 3 : 12); p2 = d - (kind ? 15 : 24);
+    }
+    int tx = x, ty = y, tz = z, put = 1;
+    if (p1 == 0) { put = (x + 2 < LX && y + 2 < LY && z + 4 < Len); tx = x + 2; ty = y + 2; tz = z + 4; }
+    else if (p2 == 0) { put = (x - 2 > 0 && y - 2 > 0 && z - 4 > 0); tx = x - 2; ty = y - 2; tz = z - 4; }
+    if (put) occupy(o, tx, ty, tz, kind, 1);
+  }
+  /* neighbours of an occupied cell: the cubic bonds by sub-lattice (x/3 etc. are integer divisions, also for the shifted
+   * atoms), and, when fewer than two of them are filled, the whole first shell (:173-211, :233-270) */
+#define SF_NEIGHBOURS() do { \
+    Coor = 0; Coord = 0; nd = 0; \
+    Site[0] = x; Site[1] = y; Site[2] = z; \
+    dia_nn(o, x, y, z, ((x / 3 + y / 3 + z / 3) % 4 == 3) ? 1 : 0, NextN); \
+    for (int i = 0; i < 4; i++) if (IBITS(LC(o, NextN[i]), ORC_PosOcc, ORC_LenOcc) > 0) Coor++; \
+    if (Coor < 2) { \
+      memset(NextND, 0, sizeof NextND); \
+      for (int i = 0; i < 32; i++) { \
+        for (int k = 0; k < 3; k++) NNSite[k] = Site[k] + ListNN[i][k]; \
+        if (NNSite[0] >= LX) NNSite[0] -= LX; \
+        if (NNSite[0] < 0) NNSite[0] += LX; \
+        if (NNSite[1] >= LY) NNSite[1] -= LY; \
+        if (NNSite[1] < 0) NNSite[1] += LY; \
+        if (IBITS(LC(o, NNSite), ORC_PosOcc, ORC_LenOcc) > 0) { \
+          Coord++; \
+          if (nd >= 4) orc_fatal(o, "SetSiCSF: site %d %d %d has more than four occupied shell sites (the reference overruns NextND)", x, y, z); \
+          cp3(NextND[nd++], NNSite); \
+        } \
+      } \
+    } } while (0)
+#define SF_BOND_CHECK(n) do { \
+    for (int i = 0; i < (n) - 1; i++) for (int k = i + 1; k < (n); k++) { \
+      int DSN = (NextND[i][0] - NextND[k][0]) * (NextND[i][0] - NextND[k][0]) + (NextND[i][1] - NextND[k][1]) * (NextND[i][1] - NextND[k][1]) + \
+                (NextND[i][2] - NextND[k][2]) * (NextND[i][2] - NextND[k][2]); \
+      if (DSN != 72) LOG(o, " not correct bonds direction\n %d %d %d %d %d %d\n", NextND[i][0], NextND[i][1], NextND[i][2], NextND[k][0], NextND[k][1], NextND[k][2]); \
+    } } while (0)
+  int Coor, Coord, nd;
+  for (int z = 13; z <= Len + 6; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          /* :171-229 peel off what stays <= 1-coordinated */
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 0) continue;
+    SF_NEIGHBOURS();
+    if (Coord > Coor) { SF_BOND_CHECK(nd); if (Coord <= 1) *w = 0; }
+    else if (Coor <= 1) *w = 0;
+  }
+  for (int z = 13; z <= Len + 6; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          /* :231-323 lists */
+    int32_t *w = &o->LattCoo[CI(o, x, y, z)];
+    if (IBITS(*w, ORC_PosOcc, ORC_LenOcc) == 0) continue;
+    SF_NEIGHBOURS();
+    int IAt = IBITS(*w, PSIC(o), LSIC(o));
+    if (Coord > Coor) {
+      MVBITS(Coord, ORC_LenCoor, w, ORC_PosCoor);
+      if (Coord <= 3) {
+        cp3(Buf, NextND[2]);
+        orc_find_nn(NextND[0], NextND[1], Site, NewSites, LX, LY);
+        for (int k = 0; k < 3; k++) { NextND[2][k] = NewSites[0][k]; NextND[3][k] = NewSites[1][k]; }
+        if (Coord == 3) {
+          int Check = 1;
+          for (int i = 0; i < 4; i++) if (eq3(NextND[i], Buf)) Check = 0;
+          if (Check) LOG(o, " Coord.eq.3 wrong check Buf %d %d %d\n", Buf[0], Buf[1], Buf[2]);
+        }
+        SF_BOND_CHECK(4);
+        Get_Prob_Ini(o, 1, IAt, Coord, Site, (const int32_t (*)[3])NextND, &ev, &Prob);
+        AddMC(o, Site, (const int32_t (*)[3])NextND, ev, Prob);
+      } else AddBulk(o, Site, (const int32_t (*)[3])NextND);
+    } else {
+      MVBITS(Coor, ORC_LenCoor, w, ORC_PosCoor);
+      if (Coor <= 3) {
+        Get_Prob_Ini(o, 1, IAt, Coor, Site, (const int32_t (*)[3])NextN, &ev, &Prob);
+        AddMC(o, Site, (const int32_t (*)[3])NextN, ev, Prob);
+      } else AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  }
+#undef SF_NEIGHBOURS
+#undef SF_BOND_CHECK
+  shape_passes(o);
 }
 
 /* list-directed READ of one plane (LattGeo / TempStat files): take n values starting on a fresh
@@ -1704,6 +1816,11 @@ int orc_setup(Orc *o) {
     set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
   } else if (!strcmp(s, "ST")) set_trench_si(o, o->Len1, o->Len2, o->Len3, o->angle, o->Ttop, o->Tbottom);
   else if (!strcmp(s, "SH")) set_shape(o);
+  else if (!strcmp(s, "E")) {                                  /* main.f:267-272 */
+    int VSF[3] = {o->Len2, o->Len3, o->Len1 - o->Len2};
+    LOG(o, " %d %d %d %d\n", o->Len1, VSF[0], VSF[1], VSF[2]);
+    set_sic_sf(o, o->Len1, VSF);
+  }
   else if (!strcmp(s, "IN")) set_cad(o);
   else if (!strcmp(s, "LA")) { o->tmax = 0; set_T(o); set_cad(o); LOG(o, " Max temperature is:  %d K\n", o->tmax); }
   else orc_fatal(o, "initialization not_implemented in oracle: %s", s);
