@@ -871,6 +871,31 @@ void set_sic_sf(Host &H, int Len, const int VSF[3]) {
   }
   shape_passes(H);
 }
+// initial/SetAPBSymZimb1.f:25-497 (SUBROUTINE SetAFBSymZimb1, InitSt A): 3C-SiC (001) slab whose upper half carries two antiphase
+// domains (ideal Si/C inside the four corner diamonds |x|+|y| < Lenh, swapped outside Lenh+3, an empty seam between).  Faithful to
+// the routine's bookkeeping: every cubic site of z = 0..Len-4 enters the bulk list, occupied or not; coordination 4 is written only
+// at z = 0; the closing probability pass (z = 21..Len) lists the 4-coordinated atoms a second time.
+void set_afb_sym_zimb1(Host &H, int Len) {
+  int kind, LX = H.LX, LY = H.LY; int32_t s[3], nn[4][3];
+  const int Lenh = LX / 2 - 1 + 24;
+  for (int z = 0; z <= Len / 2 - 4; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)
+    if (cubic_site(x, y, z, kind)) {
+      occupy(H, x, y, z, kind, true);
+      if (z == 0) mvbits(4, LenCoor, H.L[H.ci(x, y, z)], PosCoor);
+      s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn);
+    }
+  for (int z = Len / 2 - 3; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+    if (!cubic_site(x, y, z, kind)) continue;
+    const int d[4] = {std::abs(x) + std::abs(y), std::abs(x - LX) + std::abs(y), std::abs(x) + std::abs(y - LY), std::abs(x - LX) + std::abs(y - LY)};
+    const bool inside = d[0] < Lenh || d[1] < Lenh || d[2] < Lenh || d[3] < Lenh;
+    const bool outside = d[0] > Lenh + 3 && d[1] > Lenh + 3 && d[2] > Lenh + 3 && d[3] > Lenh + 3;
+    if (inside) occupy(H, x, y, z, kind, true);
+    else if (outside) occupy(H, x, y, z, !kind, true);
+    if (z <= Len - 4) { s[0] = x; s[1] = y; s[2] = z; dia_nn(H, x, y, z, kind, nn); H.AddBulk(s, nn); }
+  }
+  pass_coordination(H, 1, Len, 0, LY - 1, 0, LX - 1);
+  pass_probability(H, 21, Len, 0, LY - 1, 0, LX - 1);
+}
 // One list-directed READ of a plane of LenX*LenY numbers (LattGeo / TempStat / checkpoint files): starts on a fresh
 // record, continues onto following records while values are missing, and drops what is left of the last record read.
 void read_plane(FILE *f, std::vector<double> &buf, const char *what) {
@@ -1229,6 +1254,7 @@ int main(int argc, char **argv) {
   else if (H.InitSt == "T") set_trench(H);
   else if (H.InitSt == "FF") { H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24; H.Len3 -= H.Len3 % 24; H.Len4 -= H.Len4 % 24; set_finfet(H, H.Len1, H.Len2, H.Len3, H.Len4); }
   else if (H.InitSt == "ST") set_trench_si(H);
+  else if (H.InitSt == "A") set_afb_sym_zimb1(H, H.Len1);
   else if (H.InitSt == "SH") set_shape(H);
   else if (H.InitSt == "E") {                                 // main.f:267-272
     const int VSF[3] = {H.Len2, H.Len3, H.Len1 - H.Len2};
@@ -1237,7 +1263,7 @@ int main(int argc, char **argv) {
   }
   else if (H.InitSt == "IN") set_cad(H);
   else if (H.InitSt == "LA") { set_T(H); set_cad(H); printf(" Max temperature is:  %d K\n", H.tmax); }
-  else die(" mulskips.e (B200 host): InitSt %s is not built (built: F, Fw, Fa, FS, SG, C, S, SS, I, D, Z, J, K, L, T, E, FF, ST, IN, SH, LA; see DESIGN.md section 10)", H.InitSt.c_str());
+  else die(" mulskips.e (B200 host): InitSt %s is not built (all 22 codes of main.f:225-295 are built)", H.InitSt.c_str());
   R.NumAtoms = (int)H.bulk.size(); R.NumVoids = (int)H.voids.size(); R.NumAdAtom = (int)H.mc.size();
   if (H.la_tree) {                                            // la/main.f:592-611,628
     H.NumOcc1 = R.NumAtoms + H.NumAdAtomOcc;

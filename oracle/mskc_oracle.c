@@ -1667,6 +1667,40 @@ static void set_sic_sf(Orc *o, int Len, const int VSF[3]) {
   shape_passes(o);
 }
 
+/* src/initial/SetAPBSymZimb1.f:25-497 (SUBROUTINE SetAFBSymZimb1, InitSt 'A'): 3C-SiC (001) slab whose upper half carries two
+ * antiphase domains -- the ideal Si/C assignment inside the four corner diamonds |x|+|y| < Lenh (periodic images), the
+ * swapped one outside |x|+|y| > Lenh+3, an empty seam in between.  Faithful to the routine's bookkeeping: every cubic site
+ * of z = 0..Len-4 goes into the bulk list whether occupied or not (:42-178), coordination 4 is written only at z = 0, and
+ * the closing "set the probability" pass (z = 21..Len) lists the 4-coordinated atoms a second time (:474) */
+static void set_afb_sym_zimb1(Orc *o, int Len) {
+  int kind, LX = o->LenX, LY = o->LenY; int32_t Site[3], NextN[4][3];
+  int Lenh = LX / 2 - 1 + 24;
+  for (int z = 0; z <= Len / 2 - 4; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++)          /* epi substrate */
+    if (is_cubic_site(x, y, z, &kind)) {
+      occupy(o, x, y, z, kind, 1);
+      if (z == 0) MVBITS(4, ORC_LenCoor, &o->LattCoo[CI(o, x, y, z)], ORC_PosCoor);
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+#define AFB_IN(cmp, d) ((abs(x) + abs(y) cmp (d)) || (abs(x - LX) + abs(y) cmp (d)) || (abs(x) + abs(y - LY) cmp (d)) || (abs(x - LX) + abs(y - LY) cmp (d)))
+#define AFB_OUT(d) ((abs(x) + abs(y) > (d)) && (abs(x - LX) + abs(y) > (d)) && (abs(x) + abs(y - LY) > (d)) && (abs(x - LX) + abs(y - LY) > (d)))
+  for (int z = Len / 2 - 3; z <= Len - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {  /* :99-178 (bulk list) and :181-259 (top three planes, no list) */
+    if (!is_cubic_site(x, y, z, &kind)) continue;
+    if (AFB_IN(<, Lenh)) occupy(o, x, y, z, kind, 1);
+    else if (AFB_OUT(Lenh + 3)) occupy(o, x, y, z, !kind, 1);
+    if (z <= Len - 4) {
+      Site[0] = x; Site[1] = y; Site[2] = z;
+      dia_nn(o, x, y, z, kind, NextN);
+      AddBulk(o, Site, (const int32_t (*)[3])NextN);
+    }
+  }
+#undef AFB_IN
+#undef AFB_OUT
+  pass_coordination(o, 1, Len, 0, LY - 1, 0, LX - 1, 0);
+  pass_probability(o, 21, Len, 0, LY - 1, 0, LX - 1, 0, 0);
+}
+
 /* list-directed READ of one plane (LattGeo / TempStat files): take n values starting on a fresh
  * record, continue onto following records only if the record is short, and DISCARD whatever is left
  * on the last record read -- the regression LattGeo file has a line with one value too many. */
@@ -1815,6 +1849,7 @@ int orc_setup(Orc *o) {
     o->Len1 -= o->Len1 % 24; o->Len2 -= o->Len2 % 24; o->Len3 -= o->Len3 % 24; o->Len4 -= o->Len4 % 24;
     set_finfet(o, o->Len1, o->Len2, o->Len3, o->Len4);
   } else if (!strcmp(s, "ST")) set_trench_si(o, o->Len1, o->Len2, o->Len3, o->angle, o->Ttop, o->Tbottom);
+  else if (!strcmp(s, "A")) set_afb_sym_zimb1(o, o->Len1);
   else if (!strcmp(s, "SH")) set_shape(o);
   else if (!strcmp(s, "E")) {                                  /* main.f:267-272 */
     int VSF[3] = {o->Len2, o->Len3, o->Len1 - o->Len2};

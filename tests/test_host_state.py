@@ -32,6 +32,7 @@ CASES = {
     "ST": (lambda d: make_st_case(d), (96, 48, 144), False),
     "SH": (lambda d: make_shape_case(d), (144, 144, 144), False),
     "E": (lambda d: make_start("cube", f"{d}/start.dat", lens=(60, 24, 24), initst="E"), (96, 96, 144), False),
+    "A": (lambda d: make_start("surface", f"{d}/start.dat", lens=(72, 0, 0), initst="A"), (144, 144, 120), False),
     "T": (lambda d: make_start("cube", f"{d}/start.dat", lens=(20, 45, 90), initst="T"), (96, 48, 144), False),
     "K": (lambda d: make_start("inverted-pyramid", f"{d}/start.dat", lens=(30, 93, 0), initst="K"), (96, 96, 144), False),
     "Fa": (lambda d: make_start("surface", f"{d}/start.dat", lens=(48, 72, 48), initst="Fa"), (96, 96, 144), False),
