@@ -9,7 +9,15 @@
  *
  * Parity status: PINNED against the reference's own golden vectors
  * (regression-tests/input-and-references-files/{I0000000[01],log}-<case>)
- * by tests/test_oracle_golden.py; see DESIGN.md section "Oracle".
+ * by tests/test_oracle_golden.py for the ten regression cases, i.e. the
+ * event loop, the rate rules, both random streams, the writers and the
+ * builders FS, F, C, S, I, FF, IN, LA; see DESIGN.md section "Oracle".
+ * PARITY UNPINNED (the reference holds no golden output for them; they are
+ * restated from the sources and exercised only against themselves and the
+ * CUDA path): InitSt 'ST' (tabulated-temperature mode), the LaserAnnealing
+ * fork variant (orc_set_variant), the builders Fw, Fa, SG with a non-zero Ge
+ * fraction (libgfortran's RAND() is not part of the reference sources), A,
+ * SS, D, Z, J, K, L, T, E, SH.
  */
 #ifndef MSKC_ORACLE_H
 #define MSKC_ORACLE_H
