@@ -246,3 +246,41 @@ def make_shape_case(dirpath, box=(144, 144, 144), lens=(48, 48, 48), maxiter=10*
     with open(dst, "w") as f:
         f.write("\n".join(lines))
     return dst
+
+
+def make_sic_cvd_case(dirpath, lens=(48, 0, 0), ptranszig=0.8, maxiter=10**9, runtype="R"):
+    """BASELINE config 2: 3C-SiC(001) CVD with hydrogen coverage and hexagonal-phase nucleation on a flat F
+    slab -- NCrystal 2 (Si, C), NCov 1 (H): the 50-line evaporation table = the 18 values of start-surface.dat for every
+    crystal census (n_Si, n_C), halved per adsorbed-H neighbour; deposition = start-surface.dat; absorption 1e-5 and
+    desorption 1e-4 per site (synthetic, on the SiC table's time unit: the H rates of start-CVD-Si-SiH2.dat belong to a
+    table 1e5 times faster and, scaled, leave the surface H-passivated and etching), so that the crystal grows with a few
+    per cent of H coverage."""
+    src = open(start_path("surface")).read().split("\n")
+    evap = {}
+    dep = []
+    for l in src:
+        t = l.split()
+        if len(t) >= 3 and t[0] in ("1", "2") and len(t[1]) == 2 and t[1].isdigit():
+            evap[(int(t[0]), int(t[1][0]), int(t[1][1]))] = float(t[2])
+        elif len(t) >= 3 and t[0] in ("1", "2") and t[1] in ("1", "2", "3") and "PtransD" in l:
+            dep.append(f"{t[0]} {t[1]} {t[2]}")
+    assert len(evap) == 18 and len(dep) == 6
+    L = ["2 1 ! NCrystal NCov", "14 6 ! crystal species", "1 ! coverage species (H)", "F ! InitSt", f"{lens[0]} {lens[1]} {lens[2]} ! Len1 Len2 Len3",
+         f"{ptranszig} ! PtransZig", "0.38583333333333333 ! sf", "Iter", f"{maxiter} ! IterMax", f"{maxiter} ! OutMolMol", f"{runtype} ! RunType",
+         "9117116 ! IDUM", "F ! Save final state", "F ! Save final Coor"]
+    n = 0
+    for sp in (1, 2):
+        for (s, n1, n2), v in sorted(evap.items()):
+            if s != sp:
+                continue
+            for nh in range(0, 4 - (n1 + n2) + 1):
+                L.append(f"{sp} {n1}{n2}{nh} {v * 0.5 ** nh!r}")
+                n += 1
+    assert n == 50
+    L += dep
+    L += [f"3 {c} 1e-05" for c in (1, 2, 3)]
+    L += [f"3 {c} 0.0001" for c in (1, 2, 3)]
+    dst = os.path.join(dirpath, "start.dat")
+    with open(dst, "w") as f:
+        f.write("\n".join(L) + "\n")
+    return dst

@@ -9,7 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import make_cad_case, make_la_case, make_la_tree_case, make_shape_case, make_sige_case, make_st_case, make_start
+from cases import make_cad_case, make_la_case, make_la_tree_case, make_shape_case, make_sic_cvd_case, make_sige_case, make_st_case, make_start
 from oracle_binding import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,6 +25,7 @@ CASES = {
     "finfet": (lambda d: make_start("finfet", f"{d}/start.dat", lens=(48, 72, 120, 48)), (96, 96, 168), False),
     "CVD-Si-SiH2": (lambda d: make_start("CVD-Si-SiH2", f"{d}/start.dat", lens=(48, 0, 0)), (96, 96, 96), False),
     "SiGeBdoped": (lambda d: make_start("SiGeBdoped", f"{d}/start.dat", lens=(48, 0, 0)), (96, 96, 240), False),
+    "SiC-CVD-H (BASELINE config 2)": (lambda d: make_sic_cvd_case(d, lens=(96, 0, 0)), (240, 240, 288), False),
     "SiGe": (lambda d: make_sige_case(d, 48, 0.3), (96, 96, 96), False),
     "CAD": (lambda d: make_cad_case(d, (96, 96, 120)), (96, 96, 120), False),
     "LA": (lambda d: make_la_case(d, (96, 96, 96)), (96, 96, 96), False),
