@@ -192,6 +192,16 @@ module mskc_bind
       import :: c_int, c_ptr
       type(c_ptr), value :: h, c, kernel_ms
     end function
+    integer(c_int) function mskc_replay_teams(h, n, site_xyz, event, arm, tree_root, n_iterations, n_shared) bind(C, name="mskc_replay_teams")
+      import :: c_int, c_ptr, c_int64_t, c_double
+      type(c_ptr), value :: h, site_xyz, event, arm, n_iterations, n_shared
+      integer(c_int64_t), value :: n
+      real(c_double), value :: tree_root
+    end function
+    integer(c_int) function mskc_check_flags(h, n_sites, n_flag_mismatch, n_coor_mismatch, kernel_ms) bind(C, name="mskc_check_flags")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, n_sites, n_flag_mismatch, n_coor_mismatch, kernel_ms
+    end function
     integer(c_int) function mskc_debug_tile_stats(h, out, max_tiles, ntiles) bind(C, name="mskc_debug_tile_stats")
       import :: c_int, c_ptr, c_int64_t
       type(c_ptr), value :: h, out, ntiles

@@ -232,6 +232,11 @@ int mskc_comm_connect(mskc_ctx *h, const void *id128);
  * stands for Tree(1) in the isolated-atom rate (Get_Prob.f:305).  tests/ replay the CPU oracle's event
  * trace with it and compare lattice words, bonds and rates bit for bit. */
 int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xyz, const int32_t *event, const int32_t *arm, double tree_root);
+/* the same trace through the instantiation mskc_run_parallel launches: four 8-lane teams of one warp in lock step,
+ * feature set (coverage / per-kelvin tables) as the sampler picks it.  Consecutive events more than 48 units apart
+ * in x or y touch disjoint cells and share a lock-step iteration (up to four), so teams run concurrently and idle
+ * exactly as tiles do in a colour step; *n_iterations / *n_shared = iterations run / iterations with >= 2 events. */
+int mskc_replay_teams(mskc_ctx *h, int64_t n, const int32_t *site_xyz, const int32_t *event, const int32_t *arm, double tree_root, int64_t *n_iterations, int64_t *n_shared);
 /* the sampler's active-site lists, unordered: site, event class (1..5 as main.f; 100 = deposit/adsorb with
  * the species drawn when the event fires), rate.  cap = capacity of the arrays, *n = entries found. */
 int mskc_download_active(mskc_ctx *h, int64_t cap, int32_t *xyz, int32_t *event, double *rate, int64_t *n);
@@ -244,6 +249,12 @@ int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, int32_t *nn)
  * surface only instead of the whole lattice.  Unordered; sort by cell for the reference's z,y,x order.
  * cap = capacity of the two arrays (host memory), *n = cells found (may exceed cap: call again with more). */
 int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms);
+
+/* diagnostics: the sampler keeps the neighbour census of every site incrementally (two flag bits per bond: species of
+ * the occupied, reciprocal neighbour -- what Get_Prob.f:216-291 recounts at every call).  This recomputes the census of
+ * every cell that carries bonds in one dense pass and counts the cells whose stored flags differ (must be 0), and the
+ * cells whose coordination differs from their census (the reference's own consistency stop, Get_Prob.f:293). */
+int mskc_check_flags(mskc_ctx *h, int64_t *n_sites, int64_t *n_flag_mismatch, int64_t *n_coor_mismatch, float *kernel_ms);
 
 /* diagnostics: raw per-tile counters of the sublattice sampler (80 B records, colour-major list order) */
 int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles);

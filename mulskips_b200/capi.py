@@ -69,7 +69,7 @@ SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
            "mskc_replay_events", "mskc_download_active", "mskc_download_bonds",
-           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame"]
+           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame", "mskc_check_flags", "mskc_replay_teams"]
 
 
 def load_library():
@@ -115,6 +115,8 @@ def load_library():
     lib.mskc_comm_unique_id.argtypes = [C.c_void_p]
     lib.mskc_comm_connect.argtypes = [vp, C.c_void_p]
     lib.mskc_extract_frame.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
+    lib.mskc_replay_teams.argtypes = [vp, C.c_int64, i32p, i32p, i32p, C.c_double, i64p, i64p]
+    lib.mskc_check_flags.argtypes = [vp, i64p, i64p, i64p, C.POINTER(C.c_float)]
     for s in SYMBOLS:
         if s != "mskc_last_error":
             getattr(lib, s).restype = C.c_int
@@ -323,6 +325,14 @@ class Mskc:
         assert len(sx) == len(ev) == len(ar)
         self._ck(self.lib.mskc_replay_events(self.h, len(ev), _p(sx, C.c_int32), _p(ev, C.c_int32), _p(ar, C.c_int32), float(tree_root)))
 
+    def replay_teams(self, site_xyz, event, arm, tree_root=1.0):
+        """the trace through coop_event<8, FEAT>, four teams in lock step; returns (iterations, iterations shared by >= 2 events)"""
+        sx, ev, ar = _i32(site_xyz).reshape(-1, 3), _i32(event).reshape(-1), _i32(arm).reshape(-1)
+        assert len(sx) == len(ev) == len(ar)
+        nit, nsh = C.c_int64(), C.c_int64()
+        self._ck(self.lib.mskc_replay_teams(self.h, len(ev), _p(sx, C.c_int32), _p(ev, C.c_int32), _p(ar, C.c_int32), float(tree_root), C.byref(nit), C.byref(nsh)))
+        return nit.value, nsh.value
+
     def download_active(self):
         n = C.c_int64()
         self._ck(self.lib.mskc_download_active(self.h, 0, None, None, None, C.byref(n)))
@@ -350,6 +360,12 @@ class Mskc:
         k = min(n.value, cap)
         o = np.argsort(cells[:k], kind="stable")
         return cells[:k][o], words[:k][o], ms.value
+
+    def check_flags(self):
+        """(sites, stored census flags that differ from a fresh census, sites whose coordination differs from the census, ms)"""
+        n, bad, coor, ms = C.c_int64(), C.c_int64(), C.c_int64(), C.c_float()
+        self._ck(self.lib.mskc_check_flags(self.h, C.byref(n), C.byref(bad), C.byref(coor), C.byref(ms)))
+        return n.value, bad.value, coor.value, ms.value
 
     def census(self):
         c = Census(); ms = C.c_float()

@@ -70,6 +70,7 @@ static int set_err(mskc_ctx *h, const char *fmt, ...) {
 // no kernel of another context is in flight when the constants change (one host thread per process).
 static int upload_consts(mskc_ctx *h) {
   CK(cudaSetDevice(h->device));
+  h->D.aux = h->PC.aux;
   TileView tv = tile_view(h->PC);
   ParityView pv{};
   pv.Tree = h->d_Tree; pv.Levels = h->Levels; pv.NumMcMax = h->NumMcMax; pv.NumVdMax = h->NumVdMax; pv.leaf0 = 1 << (h->Levels - 1);
@@ -101,6 +102,7 @@ static const char *dev_err_text(int code) {
     case E_STALE_NBUFF: return "Evaporation: no reciprocal occupied neighbour left (reference uses an uninitialised buffer here)";
     case E_TRANGE: return "site temperature outside the table range given to mskc_set_la";
     case E_BADEV: return "invalid event code";
+    case E_FLAGS: return "incremental census flags disagree with the full neighbour census";
   }
   return "unknown device error";
 }
@@ -522,7 +524,7 @@ extern "C" int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
   CK(cudaMemcpyAsync(d_rb, rb.data(), rb.size() * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(D.bonds, 0, D.ncell * sizeof(unsigned long long), h->stream));
   CK(cudaMemsetAsync(h->d_lattind, 0, D.ncell * sizeof(uint32_t), h->stream));
-  if (nrec) scatter_records<<<(unsigned)((nrec + 255) / 256), 256, 0, h->stream>>>(D.bonds, h->d_lattind, d_rc, d_rb, d_rind, (long long)nrec);
+  if (nrec) MSKC_LAUNCH(scatter_records, (unsigned)((nrec + 255) / 256), 256, 0, h->stream, D.bonds, h->d_lattind, d_rc, d_rb, d_rind, (long long)nrec);
   // MC list, void list, rate tree
   std::vector<uint32_t> mcc((size_t)h->NumMcMax + 2, 0xFFFFFFFFu), vdc((size_t)h->NumVdMax + 2, 0xFFFFFFFFu);
   std::vector<int> mce((size_t)h->NumMcMax + 2, 0);
@@ -551,8 +553,13 @@ extern "C" int mskc_upload_state(mskc_ctx *h, const int32_t *LattCoo,
   h->parity_ready = true; h->have_state = true;
   // the parallel sampler's tile lists are (re)built lazily from the uploaded MC list
   if (parallel_build_from_lists(h->PC, D, h->stream, n_mc, mcc.data() + 1, mce.data() + 1, mc_rate, n_bulk, n_void, &h->err)) { g_last_error = h->err; return -1; }
+  if (!h->PC.lists_stale) {                            // census flags of every site (dense pass; mskc_coop.cuh)
+    if (upload_consts(h)) return -1;
+    unsigned long long o[3];
+    if (parallel_census_flags(h->PC, h->D, h->stream, 0, o, nullptr, nullptr, nullptr, &h->err)) { g_last_error = h->err; return -1; }
+  }
   h->parallel_ready = true;
-  return 0;
+  return check_dev_err(h);
 }
 
 extern "C" int mskc_seed(mskc_ctx *h, int idum, int runtype, int64_t counter0, const int32_t *ran3_state) {
@@ -608,7 +615,7 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   while (true) {
     A.event_budget = (remaining < 0 || remaining > slice) ? slice : remaining;
     CK(cudaEventRecord(h->ev0, h->stream));
-    parity_kernel<<<1, 32, sizeof(ParShared), h->stream>>>(A);
+    MSKC_LAUNCH(parity_kernel, 1, 32, sizeof(ParShared), h->stream, A);
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_ps, h->d_ps, sizeof(ParityState), cudaMemcpyDeviceToHost, h->stream));
@@ -688,7 +695,7 @@ extern "C" int mskc_download_lists(mskc_ctx *h, int32_t *mc_xyz, int32_t *mc_nn,
     uint32_t *d_c = nullptr; unsigned long long *d_b = nullptr;
     CK(cudaMalloc(&d_c, cells.size() * 4)); CK(cudaMalloc(&d_b, cells.size() * 8));
     CK(cudaMemcpy(d_c, cells.data(), cells.size() * 4, cudaMemcpyHostToDevice));
-    gather_bonds<<<(unsigned)((cells.size() + 255) / 256), 256, 0, h->stream>>>(D.bonds, d_c, d_b, (long long)cells.size());
+    MSKC_LAUNCH(gather_bonds, (unsigned)((cells.size() + 255) / 256), 256, 0, h->stream, D.bonds, d_c, d_b, (long long)cells.size());
     CK(cudaMemcpyAsync(out.data(), d_b, cells.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_c); cudaFree(d_b);
@@ -728,7 +735,7 @@ extern "C" int mskc_download_lists(mskc_ctx *h, int32_t *mc_xyz, int32_t *mc_nn,
     uint32_t *d_c = nullptr; unsigned long long *d_cnt = nullptr;
     CK(cudaMalloc(&d_c, (size_t)cap * 4)); CK(cudaMalloc(&d_cnt, 8)); CK(cudaMemset(d_cnt, 0, 8));
     if (upload_consts(h)) return -1;
-    collect_bulk<<<1184, 256, 0, h->stream>>>(d_c, cap, d_cnt);
+    MSKC_LAUNCH(collect_bulk, 1184, 256, 0, h->stream, d_c, cap, d_cnt);
     unsigned long long cnt = 0;
     CK(cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -775,7 +782,7 @@ extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
   if (!h->d_stage) CK(cudaMalloc(&h->d_stage, n * 4));        // staging plane stack, kept for the next upload
   if (upload_consts(h)) return -1;
   CK(cudaMemcpyAsync(h->d_stage, T, n * 4, cudaMemcpyHostToDevice, h->stream));
-  set_temperature_kernel<<<1184, 256, 0, h->stream>>>(h->d_stage, (long long)n);
+  MSKC_LAUNCH(set_temperature_kernel, 1184, 256, 0, h->stream, h->d_stage, (long long)n);
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -788,7 +795,7 @@ extern "C" int mskc_census_lattice(mskc_ctx *h, mskc_census *c, float *kernel_ms
   CK(cudaMalloc(&d_out, 8 * 8)); CK(cudaMalloc(&d_h, 2 * 8));
   CK(cudaMemsetAsync(d_out, 0, 64, h->stream)); CK(cudaMemsetAsync(d_h, 0, 16, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
-  census_kernel<<<148 * 8, 256, 0, h->stream>>>(d_out, d_h);
+  MSKC_LAUNCH(census_kernel, 148 * 8, 256, 0, h->stream, d_out, d_h);
   CK(cudaEventRecord(h->ev1, h->stream));
   unsigned long long o[8]; double hh[2];
   CK(cudaMemcpyAsync(o, d_out, 64, cudaMemcpyDeviceToHost, h->stream));
@@ -829,6 +836,20 @@ extern "C" int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate
   return check_dev_err(h);
 }
 
+// diagnostic / test entry point: recompute the census flags of every cell with bonds and compare them with the stored
+// (incrementally maintained) ones; also counts cells whose coordination differs from their census
+extern "C" int mskc_check_flags(mskc_ctx *h, int64_t *n_sites, int64_t *n_flag_mismatch, int64_t *n_coor_mismatch, float *kernel_ms) {
+  if (!h || !h->parallel_ready || h->PC.lists_stale) return set_err(h, "mskc_check_flags: no parallel state");
+  CK(cudaSetDevice(h->device));
+  if (upload_consts(h)) return -1;
+  unsigned long long o[3] = {0, 0, 0};
+  if (parallel_census_flags(h->PC, h->D, h->stream, 1, o, kernel_ms, h->ev0, h->ev1, &h->err)) { g_last_error = h->err; return -1; }
+  if (n_sites) *n_sites = (int64_t)o[0];
+  if (n_flag_mismatch) *n_flag_mismatch = (int64_t)o[1];
+  if (n_coor_mismatch) *n_coor_mismatch = (int64_t)o[2];
+  return check_dev_err(h);
+}
+
 // diagnostics: raw per-tile counters (TileStat, 80 B each: i64 events, i64 site_updates, i32 dep[3], evap, abs, des, dAtoms, dVoids,
 // dCrystal[3], dCov[3], maxev, pad), list id order (colour-major)
 extern "C" int mskc_debug_tile_stats(mskc_ctx *h, void *out, int64_t max_tiles, int64_t *ntiles) {
@@ -859,8 +880,8 @@ extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xy
   const int64_t chunk = 1000;                    // tombstones are dropped between chunks (no tile is ever "running" here)
   for (int64_t i0 = 0; i0 < n; i0 += chunk) {
     const int64_t m = n - i0 < chunk ? n - i0 : chunk;
-    compact_lists_kernel<<<(h->PC.ntiles * 32 + 127) / 128, 128, 0, h->stream>>>(h->PC.ntiles);
-    replay_kernel<<<1, 32, 0, h->stream>>>(d_s + 3 * i0, d_e + i0, d_a + i0, (long long)m, tree_root, d_out);
+    MSKC_LAUNCH(compact_lists_kernel, (h->PC.ntiles * 32 + 127) / 128, 128, 0, h->stream, h->PC.ntiles);
+    MSKC_LAUNCH(replay_kernel, 1, 32, 0, h->stream, d_s + 3 * i0, d_e + i0, d_a + i0, (long long)m, tree_root, d_out);
   }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(&out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
@@ -872,6 +893,67 @@ extern "C" int mskc_replay_events(mskc_ctx *h, int64_t n, const int32_t *site_xy
   for (int i = 0; i < 3; i++) { P.extra.dCrystal[i] += out.dCrystal[i]; P.extra.dCov[i] += out.dCov[i]; }
   if (check_dev_err(h)) return -1;
   if (out.events != n) return set_err(h, "mskc_replay_events: stopped after %lld of %lld events", (long long)out.events, (long long)n);
+  return 0;
+}
+
+// The same trace through coop_event<8, FEAT>, four teams in lock step (the instantiation mskc_run_parallel launches).
+// Consecutive events whose sites are more than 48 units apart in x or y (minimum image) touch disjoint cells
+// (mskc_parallel.cuh: writes reach 8, reads 16 units), so up to four of them share a lock-step iteration.
+extern "C" int mskc_replay_teams(mskc_ctx *h, int64_t n, const int32_t *site_xyz, const int32_t *event, const int32_t *arm, double tree_root, int64_t *n_iterations, int64_t *n_shared) {
+  if (!h || !site_xyz || !event || !arm) return set_err(h, "mskc_replay_teams: NULL argument");
+  if (!h->parallel_ready || !h->have_rates || h->PC.lists_stale) return set_err(h, "mskc_replay_teams: rates and a parallel state must be set first");
+  if (h->D.la == 3) return set_err(h, "mskc_replay_teams: the LaserAnnealing fork's per-event liquid fraction needs the serial replay (mskc_replay_events)");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(h->device));
+  if (upload_consts(h)) return -1;
+  const DevCtx &D = h->D;
+  std::vector<int32_t> conv_ev;
+  if (h->tree_variant == MSKC_TREE_LA) { conv_ev.resize((size_t)n); for (int64_t i = 0; i < n; i++) conv_ev[(size_t)i] = ev_to_dev(event[i]); event = conv_ev.data(); }
+  // greedy batching of consecutive commuting events; the first event of iteration b goes to team b % 4
+  auto far = [&](int64_t a, int64_t b) {
+    int dx = abs(site_xyz[3 * a] - site_xyz[3 * b]), dy = abs(site_xyz[3 * a + 1] - site_xyz[3 * b + 1]);
+    dx = std::min(dx, D.LX - dx); dy = std::min(dy, D.LY - dy);
+    return dx > 48 || dy > 48;
+  };
+  std::vector<int32_t> batch; int64_t nb = 0, shared = 0;
+  for (int64_t i = 0; i < n;) {
+    int64_t j = i + 1;
+    while (j < n && j - i < 4) { bool ok = true; for (int64_t k = i; k < j; k++) ok = ok && far(k, j); if (!ok) break; j++; }
+    int32_t row[4] = {-1, -1, -1, -1};
+    for (int64_t k = i; k < j; k++) row[(nb + (k - i)) & 3] = (int32_t)k;
+    batch.insert(batch.end(), row, row + 4);
+    if (j - i > 1) shared++;
+    nb++; i = j;
+  }
+  int32_t *d_s = nullptr, *d_e = nullptr, *d_a = nullptr, *d_b = nullptr; TileStat *d_out = nullptr; TileStat out{};
+  CK(cudaMalloc(&d_s, (size_t)n * 12)); CK(cudaMalloc(&d_e, (size_t)n * 4)); CK(cudaMalloc(&d_a, (size_t)n * 4)); CK(cudaMalloc(&d_b, batch.size() * 4)); CK(cudaMalloc(&d_out, sizeof(TileStat)));
+  CK(cudaMemcpyAsync(d_s, site_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_e, event, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_a, arm, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_b, batch.data(), batch.size() * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d_out, 0, sizeof(TileStat), h->stream));
+  const int feat = (D.NCov > 0 ? F_COV : 0) | (D.la ? F_LA : 0);
+  typedef void (*rp_kernel_t)(const int32_t *, const int32_t *, const int32_t *, const int32_t *, long long, double, TileStat *);
+  static const rp_kernel_t kern[4] = {replay_teams_kernel<0>, replay_teams_kernel<1>, replay_teams_kernel<2>, replay_teams_kernel<3>};
+  const rp_kernel_t k = kern[feat];
+  const int64_t chunk = 1000;                    // iterations per launch; tombstones are dropped between launches
+  for (int64_t b0 = 0; b0 < nb; b0 += chunk) {
+    const int64_t m = nb - b0 < chunk ? nb - b0 : chunk;
+    MSKC_LAUNCH(compact_lists_kernel, (h->PC.ntiles * 32 + 127) / 128, 128, 0, h->stream, h->PC.ntiles);
+    MSKC_LAUNCH(k, 1, 32, 0, h->stream, d_s, d_e, d_a, d_b + 4 * b0, (long long)m, tree_root, d_out);
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&out, d_out, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_s); cudaFree(d_e); cudaFree(d_a); cudaFree(d_b); cudaFree(d_out);
+  ParallelCtx &P = h->PC;
+  P.replayed = true;
+  P.extra.events += out.events; P.extra.site_updates += out.site_updates; P.extra.dAtoms += out.dAtoms; P.extra.dVoids += out.dVoids;
+  for (int i = 0; i < 3; i++) { P.extra.dCrystal[i] += out.dCrystal[i]; P.extra.dCov[i] += out.dCov[i]; }
+  if (n_iterations) *n_iterations = nb;
+  if (n_shared) *n_shared = shared;
+  if (check_dev_err(h)) return -1;
+  if (out.events != n) return set_err(h, "mskc_replay_teams: stopped after %lld of %lld events", (long long)out.events, (long long)n);
   return 0;
 }
 
@@ -915,7 +997,7 @@ extern "C" int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, i
   uint32_t *d_c = nullptr; unsigned long long *d_b = nullptr;
   CK(cudaMalloc(&d_c, (size_t)n * 4)); CK(cudaMalloc(&d_b, (size_t)n * 8));
   CK(cudaMemcpyAsync(d_c, cells.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
-  gather_bonds<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(D.bonds, d_c, d_b, (long long)n);
+  MSKC_LAUNCH(gather_bonds, (unsigned)((n + 255) / 256), 256, 0, h->stream, D.bonds, d_c, d_b, (long long)n);
   CK(cudaMemcpyAsync(b.data(), d_b, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d_c); cudaFree(d_b);
@@ -974,7 +1056,7 @@ extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint
   if (upload_consts(h)) return -1;
   CK(cudaMemsetAsync(h->d_frame_n, 0, 8, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
-  frame_extract_kernel<<<148 * 8, 256, 0, h->stream>>>(h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
+  MSKC_LAUNCH(frame_extract_kernel, 148 * 8, 256, 0, h->stream, h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   unsigned long long cnt = 0;

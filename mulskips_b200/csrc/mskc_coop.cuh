@@ -1,26 +1,36 @@
 // mskc_coop.cuh -- warp-cooperative form of the four KMC transitions (sm_100a).
 //
 // A team of lanes owns one tile of the synchronous-sublattice sampler.  An event at site S touches S and its
-// four bonded neighbours N0..N3, then re-rates those five sites (each re-rate is a census of that site's
-// own four neighbours).  The serial reference walks these one after the other (mcevent/deposition.f,
-// Evaporation.f, absorption.f, desorption.f + Get_Prob.f); here
-//   lanes 0..3  handle neighbour i  (phase A: coordination / bond update of N_i, phase B: its re-rate)
-//   lane  4     handles S itself    (its bonds when they are fixed at deposition, its re-rate, its final word)
+// four bonded neighbours N0..N3 and re-rates those five sites.  The serial reference walks these one after the
+// other (mcevent/deposition.f, Evaporation.f, absorption.f, desorption.f) and every re-rate is a fresh census of
+// that site's own four neighbours (Get_Prob.f:216-291: 4 lattice words + 4 bond lists, i.e. 20 more cells per
+// event).  Here
+//   lanes 0..3  handle neighbour i  (phase A: coordination / bond / census-flag update of N_i, then its rate)
+//   lane  4     handles S itself    (its bonds when they are fixed at deposition, its rate, its final word)
 //   lanes 0..5  read the six zig-zag / arm-chair candidate cells of IF_Arm_Choice.f together
-// so the dependent chain of an event is  S -> {N_i} -> {neighbours of N_i}  = 3..4 memory round trips
-// instead of ~15, and every lane runs the same small code (the hot loop is kept near the 32 KB L1.5
-// instruction cache: single call sites, cold paths out of line).  The rules themselves are those of
-// mskc_device.cuh (the serial templates the parity kernel uses); tests/test_replay_gpu.py replays the
-// oracle's event trace through this code and compares lattice words, bonds and (event class, rate) of
-// every active site bit for bit.
+// and the census is INCREMENTAL: every cell carries, next to its list slot, two bits per bond that say which
+// crystal species the occupied, reciprocal neighbour on that bond has (aux[] below).  An event updates the flag of
+// the bond that points back at S in each neighbour it touches -- exactly where the reference changes that
+// neighbour's coordination -- so the rate of a re-rated occupied site is a table look-up on its own record and
+// the dependent chain of an event is  S -> {N_i}  (+ one more hop only where the reference itself reads further:
+// IF_Arm_Choice candidates, the two new bonds of FIND_NN.f).  The census of S itself falls out of phase A (each lane
+// holds its neighbour's word and bond list), so S's flags are recomputed, not trusted, at every event, and the
+// reference's consistency stop `N_Si+N_C+N_B+N_wall.NE.Coor` (Get_Prob.f:293) is kept for every rated site.
+// Runs with coverage species (FEAT & F_COV) still rate occupied sites with the full census (coop_rate): a
+// coverage neighbour's contribution depends on ITS coordination (Get_Prob.f:262-291), which changes without the
+// reference re-rating the sites around it; there the flags are maintained and cross-checked against the census.
+//
+// tests/test_replay_gpu.py replays the oracle's event trace through this code (one 32-lane team, and four 8-lane
+// teams in lock step) and compares lattice words, bonds, census flags and (event class, rate) of every active site
+// bit for bit.
 //
 // Geometry without floating point: bonds are stored as 15-bit relative codes (mskc_device.cuh), so
 //   zig-zag continuation  (FIND_SN.f:60-64)  2*Cent - SN            ==  -(bond of C)          exact integers
 //   arm-chair continuation(FIND_SN.f:66-70)  SN + 8.66*unit(S - C)  ==  bond of C + e + armoff(e)
 // with armoff(e) = NINT(8.6602254037f * unit(-e)) tabulated on the host for all 31^3 bond codes by the same
 // IEEE sequence (entries closer than 1e-6 to a rounding tie are left out and take the double-precision
-// fallback find_sn()).  FIND_NN.f's rotation stays in double precision (one lane, only when an empty site
-// receives its second neighbour).
+// fallback find_sn()).  FIND_NN.f's rotation is exact in integers on the ideal bond shell (checked at start-up
+// against the double-precision routine, D.nn_exact) and stays in double precision elsewhere.
 #pragma once
 #include "mskc_device.cuh"
 
@@ -31,6 +41,12 @@ enum { NEGC = 0x8420 };            // code(-v) = NEGC - code(v): every 5-bit fie
 __device__ __forceinline__ unsigned fld(unsigned long long b, int i) { return (unsigned)(b >> (16 * i)) & 0xFFFFu; }
 __device__ __forceinline__ bool lists_code(unsigned long long b, unsigned code) {
   return (fld(b, 0) == code) | (fld(b, 1) == code) | (fld(b, 2) == code) | (fld(b, 3) == code);
+}
+// index of the (last) field of b that equals code, -1 if none
+__device__ __forceinline__ int find_code(unsigned long long b, unsigned code) {
+  int j = -1;
+  j = fld(b, 0) == code ? 0 : j; j = fld(b, 1) == code ? 1 : j; j = fld(b, 2) == code ? 2 : j; j = fld(b, 3) == code ? 3 : j;
+  return j;
 }
 __device__ __noinline__ bool recipr_cold(P3 n, unsigned long long bn, P3 me) { return recipr_b(n, bn, me); }
 // "does cell n (bond word bn) list `me`?", given the field f under which me lists n (n = me + v(f)).
@@ -52,8 +68,58 @@ __device__ __forceinline__ uint32_t ccell(P3 p) {
   if ((unsigned)p.z > (unsigned)D.LZ) { fail(E_OOB, p.x, p.y, p.z); return 0u; }
   return (uint32_t)p.x + (uint32_t)D.LX * ((uint32_t)p.y + (uint32_t)D.LY * (uint32_t)p.z);
 }
+// neighbour of site s along bond code f: coordinates (x, y wrapped, branch-free) and cell index.  f == 0 ("not
+// fixed") is the absolute origin, as the reference's NextNXYZ = 0; z outside 0..LenZ raises E_OOB (cell 0 returned).
+__device__ __forceinline__ uint32_t nbr(const P3 s, const unsigned f, P3 &n) {
+  int x = s.x + cdx(f), y = s.y + cdy(f), z = s.z + cdz(f);
+  x += (x < 0 ? D.LX : 0) - (x >= D.LX ? D.LX : 0);
+  y += (y < 0 ? D.LY : 0) - (y >= D.LY ? D.LY : 0);
+  if (f == 0u) { x = 0; y = 0; z = 0; }
+  n.x = x; n.y = y; n.z = z;
+  if ((unsigned)z > (unsigned)D.LZ) { fail(E_OOB, x, y, z); return 0u; }
+  return (uint32_t)x + (uint32_t)D.LX * ((uint32_t)y + (uint32_t)D.LY * (uint32_t)z);
+}
 __device__ __forceinline__ int cov_index(int cov) {      // position of a coverage id in ListCov (1-based), 0 = absent
   return cov == D.ListCov[0] ? 1 : (cov == D.ListCov[1] ? 2 : (cov == D.ListCov[2] ? 3 : 0));
+}
+
+// ---- aux[cell]: list slot + census flags ---------------------------------------------------------------------
+//   bits  0-15  1-based slot of the cell in its tile's active list (0 = not listed)
+//   bits 16-23  census flags, 2 bits per bond i at 16+2i: 0 = the neighbour on bond i is not counted, 1..3 = crystal
+//               species of the occupied neighbour that lists this cell back; a wall neighbour of an OCCUPIED site is 1
+//               (Get_Prob.f:311 adds N_wall to the first index; an empty site's coordination does not count walls)
+// The two halves are written with separate 16-bit / 8-bit stores, never read-modify-write.
+enum { AUX_FLAG0 = 16 };
+__device__ __forceinline__ int aux_slot(uint32_t a) { return (int)(a & 0xFFFFu); }
+__device__ __forceinline__ unsigned aux_flags(uint32_t a) { return (a >> AUX_FLAG0) & 0xFFu; }
+__device__ __forceinline__ unsigned flag_get(unsigned fl, int j) { return (fl >> (2 * j)) & 3u; }
+__device__ __forceinline__ unsigned flag_set(unsigned fl, int j, unsigned v) { return (fl & ~(3u << (2 * j))) | (v << (2 * j)); }
+__device__ __forceinline__ void st_slot(uint32_t c, int slot) { reinterpret_cast<unsigned short *>(D.aux)[2 * (size_t)c] = (unsigned short)slot; }
+__device__ __forceinline__ void st_flags(uint32_t c, unsigned fl) { reinterpret_cast<unsigned char *>(D.aux)[4 * (size_t)c + 2] = (unsigned char)fl; }
+// species counts of a flag byte: n1 | n2 << 4 | n3 << 8
+__device__ __forceinline__ unsigned flag_counts(unsigned fl) {
+  const unsigned lo = fl & 0x55u, hi = (fl >> 1) & 0x55u;
+  return (unsigned)__popc(lo & ~hi) | ((unsigned)__popc(hi & ~lo) << 4) | ((unsigned)__popc(lo & hi) << 8);
+}
+// census flags of one cell from scratch (the dense pass after an upload, and the checker): Get_Prob.f:216-291 without
+// the coverage part.  Q's own word decides whether walls count.
+__device__ __forceinline__ unsigned census_flags(const P3 Q, const uint32_t wQ, const unsigned long long bQ) {
+  unsigned fl = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const unsigned f = fld(bQ, i);
+    if (f == 0u) continue;
+    const int z = Q.z + cdz(f);
+    if ((unsigned)z > (unsigned)D.LZ) continue;          // bond leaving the box (bottom layer of a slab without walls)
+    P3 n; const uint32_t c = nbr(Q, f, n);
+    const uint32_t w = D.state[c];
+    if (!w_occ(w)) continue;
+    if (w_cov(w) == 113) { if (w_occ(wQ)) fl |= 1u << (2 * i); continue; }
+    bool rec = lists_code(D.bonds[c], (unsigned)NEGC - f);
+    if ((Q.x | Q.y | Q.z) == 0) rec |= lists_code(D.bonds[c], 0u);
+    if (rec) fl |= (unsigned)(w_sp(w) & 3) << (2 * i);
+  }
+  return fl;
 }
 
 // ---- rate of one site: mcevent/Get_Prob.f:54-331 ---------------------------------------------------
@@ -62,8 +128,9 @@ __device__ __forceinline__ int cov_index(int cov) {      // position of a covera
 // is drawn when the event fires (Get_Prob.f:160-179 draws it here; same distribution).
 // FEAT: bit 0 = coverage species exist (NCov > 0), bit 1 = per-kelvin rate tables (LA rate law or 'ST' field); compiled out otherwise (hot-loop code size)
 enum { F_COV = 1, F_LA = 2 };
+// full-census form (coverage runs, the dense re-rate pass): reads the four neighbours' words and bond lists
 template <int FEAT>
-__device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, P3 Q, uint32_t cQ, unsigned long long rb, double root, int &ev, double &p) {
+__device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, P3 Q, uint32_t cQ, unsigned long long rb, double root, int &ev, double &p, unsigned *flags_out = nullptr) {
   ev = 0; p = 0.0;
   int T = 0;
   if ((FEAT & F_LA) && D.la) T = site_T(D.state[cQ], Q);                   // :76-91 ('ST') / :127-141 ('LA')
@@ -90,6 +157,7 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
   for (int i = 0; i < 4; i++) { const uint32_t c = ccell(dec_bond(Q, fld(rb, i))); wn[i] = D.state[c]; bn[i] = D.bonds[c]; }
   const bool qorigin = (Q.x | Q.y | Q.z) == 0;
   int N_Si = 0, N_C = 0, N_B = 0, N_wall = 0, cv0 = 0, cv1 = 0, cv2 = 0;
+  unsigned fl = 0u;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const uint32_t w = wn[i];
@@ -99,8 +167,8 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
     if (f == 0u) rec = recipr_cold(dec_bond(Q, 0u), bn[i], Q);
     if (qorigin) rec |= lists_code(bn[i], 0u);
     if (w_occ(w)) {
-      if (CovN == 113) N_wall++;
-      else if (rec) { const int s = w_sp(w); N_Si += (s == 1); N_C += (s == 2); N_B += (s == 3); }
+      if (CovN == 113) { N_wall++; fl |= 1u << (2 * i); }
+      else if (rec) { const int s = w_sp(w); N_Si += (s == 1); N_C += (s == 2); N_B += (s == 3); fl |= (unsigned)(s & 3) << (2 * i); }
     } else if ((FEAT & F_COV) && CovN != 0 && rec && w_coor(w) < 4) {
       // (coverage on a 4-coordinated empty site: the reference looks it up in the wrong list, see
       // ParityPol::cov_void_recipr, and in effect never counts it)
@@ -109,6 +177,7 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
       cv0 += (iCov == 1); cv1 += (iCov == 2); cv2 += (iCov == 3);
     }
   }
+  if (flags_out) *flags_out = fl;
   const int ncry = N_Si + N_C + N_B + N_wall;
   if (ncry != Coor) { fail(E_CENSUS, Q.x, Q.y, Q.z, Coor * 16 + ncry); return; }
   if (ncry > 3) return;
@@ -117,21 +186,30 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
   const int idx = IDXE(NSiC, N_Si + N_wall, N_C, N_B, cv0 & 3, cv1 & 3, cv2 & 3);
   p = (FEAT & F_LA) ? rate_E(idx, T) : __ldg(&D.PE[idx]);
 }
-
-// Evaporation.f:95-122 / :229-258 on bond codes: keep the occupied, under-coordinated, reciprocal
-// neighbour (the last one that qualifies) in slot 1, forget the others.
-__device__ __noinline__ unsigned long long coop_compact(P3 me, unsigned long long old) {
-  unsigned keep = 0u; bool found = false;
-  uint32_t w[4]; unsigned long long b[4];                 // all eight words in flight together (one memory round trip)
-#pragma unroll
-  for (int j = 0; j < 4; j++) { const uint32_t c = ccell(dec_bond(me, fld(old, j))); w[j] = D.state[c]; b[j] = D.bonds[c]; }
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const unsigned f = fld(old, j);
-    if (w_occ(w[j]) && w_coor(w[j]) <= 3 && w_cov(w[j]) != 113 && recip_f(dec_bond(me, f), b[j], me, f)) { keep = f; found = true; }
+// incremental form (no coverage species): the census is the site's flag byte; nb1 = coordination of the site's
+// first-bond neighbour as the lattice holds it when the reference would rate the site (Get_Prob.f:182-183)
+template <int FEAT>
+__device__ __forceinline__ void flag_rate(int Occ, int NSiC, int Coor, uint32_t wQ, uint32_t cQ, unsigned fl, int nb1, double root, int &ev, double &p) {
+  ev = 0; p = 0.0;
+  int T = 0;
+  if ((FEAT & F_LA) && D.la) T = site_T(wQ, cell_xyz((long long)cQ));      // :127-141
+  if (Occ == 0) {
+    if (Coor >= 1 && Coor <= 3) {
+      ev = EV_DRAW;
+      if (Coor == 1 && nb1 < 2) { ev = 1; p = (double)1.e-8f; }            // Get_Prob.f:183
+      else p = (FEAT & F_LA) ? total_dep_abs(Coor, T) : D.PDepAbs[Coor];
+    }
+    return;
   }
-  if (!found) fail(E_STALE_NBUFF, me.x, me.y, me.z);
-  return (unsigned long long)keep;
+  const unsigned cn = flag_counts(fl);
+  const int n1 = (int)(cn & 15u), n2 = (int)((cn >> 4) & 15u), n3 = (int)(cn >> 8);
+  const int ncry = n1 + n2 + n3;
+  if (ncry != Coor) { P3 q = cell_xyz((long long)cQ); fail(E_CENSUS, q.x, q.y, q.z, Coor * 16 + ncry); return; }   // :293
+  if (ncry > 3) return;
+  ev = 4;
+  if (ncry == 0) { p = (double)100000.f * root; return; }
+  const int idx = IDXE(NSiC, n1, n2, n3, 0, 0, 0);
+  p = (FEAT & F_LA) ? rate_E(idx, T) : __ldg(&D.PE[idx]);
 }
 
 // double-precision fallback of the bond fixing (cold): serial find_sn on absolute coordinates
@@ -141,44 +219,11 @@ __device__ __noinline__ void slow_find_sn(P3 S, P3 C, const unsigned g[3], unsig
   find_sn(S, C, SN, Z, A);
   for (int i = 0; i < 3; i++) { zig[i] = enc_bond_cold(S, Z[i]); arm[i] = enc_bond_cold(S, A[i]); }
 }
-
-// deposition.f:100-142: an empty site N with one fixed bond (to M) receives its second neighbour S: the
-// other two bonds follow by rotation (FIND_NN.f), and already-present reciprocal atoms there count.
-// Returns the new coordination (0 = the two known neighbours are not a tetrahedral pair: nothing happens).
-__device__ __noinline__ int second_bond(P3 S, P3 N, unsigned fNS /* bond code N -> S */, unsigned long long &bN) {
-  const unsigned f0 = fld(bN, 0);
-  const P3 M = dec_bond(N, f0);
-  int Dx = abs(M.x - S.x); Dx = min(Dx, D.LX - Dx);
-  int Dy = abs(M.y - S.y); Dy = min(Dy, D.LY - Dy);
-  const int dz = M.z - S.z;
-  if (Dx * Dx + Dy * Dy + dz * dz != 72) return 0;
-  P3 NewSite[2]; unsigned fn[2]; int cnew = 2;
-  // FIND_NN.f:46-76 rotates b2 = S-N by +-120 degrees about b1 = M-N.  For two bonds of the ideal shell (|b|^2 = 27,
-  // tetrahedral pair) the rotation is exact in integers: -(b1+b2)/2 -+ (b1 x b2)/6; mskc_create checks this
-  // against the double-precision routine for all 120 such pairs (D.nn_exact).  Anything else rotates in double.
-  const int b1x = cdx(f0), b1y = cdy(f0), b1z = cdz(f0), b2x = cdx(fNS), b2y = cdy(fNS), b2z = cdz(fNS);
-  if (D.nn_exact && f0 != 0u && b1x * b1x + b1y * b1y + b1z * b1z == 27 && b2x * b2x + b2y * b2y + b2z * b2z == 27) {
-    const int cx = b1y * b2z - b1z * b2y, cy = b1z * b2x - b1x * b2z, cz = b1x * b2y - b1y * b2x;
-    const int sx = -(b1x + b2x) / 2, sy = -(b1y + b2y) / 2, sz = -(b1z + b2z) / 2;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int sg = k == 0 ? -1 : 1;
-      const int ox = sx + sg * (cx / 6), oy = sy + sg * (cy / 6), oz = sz + sg * (cz / 6);
-      fn[k] = (unsigned)(ox + 16) | ((unsigned)(oy + 16) << 5) | ((unsigned)(oz + 16) << 10);
-      NewSite[k] = dec_bond(N, fn[k]);
-    }
-  } else {
-    find_nn(M, S, N, NewSite);
-    fn[0] = enc_bond_cold(N, NewSite[0]); fn[1] = enc_bond_cold(N, NewSite[1]);
-  }
-  uint32_t w3[2]; unsigned long long b3[2];              // both cells' words in flight together
-#pragma unroll
-  for (int k = 0; k < 2; k++) { const uint32_t c3 = ccell(NewSite[k]); w3[k] = D.state[c3]; b3[k] = D.bonds[c3]; }
-#pragma unroll
-  for (int k = 0; k < 2; k++)
-    if (w_occ(w3[k]) && w_coor(w3[k]) <= 3 && w_cov(w3[k]) != 113 && recipr_b(NewSite[k], b3[k], N)) cnew++;
-  bN = (unsigned long long)f0 | ((unsigned long long)fNS << 16) | ((unsigned long long)fn[0] << 32) | ((unsigned long long)fn[1] << 48);
-  return cnew;
+// deposition.f:100-142 off the ideal shell (cold): the two new bonds of FIND_NN.f by the double-precision rotation
+__device__ __noinline__ void slow_find_nn(P3 S, P3 N, unsigned f0, unsigned fn[2]) {
+  P3 NewSite[2];
+  find_nn(dec_bond(N, f0), S, N, NewSite);
+  fn[0] = enc_bond_cold(N, NewSite[0]); fn[1] = enc_bond_cold(N, NewSite[1]);
 }
 
 struct CoopCounters {                // per-lane partial sums, reduced over the warp at the end of a step
@@ -189,7 +234,7 @@ struct CoopCounters {                // per-lane partial sums, reduced over the 
 // EVERY lane of the warp calls this together (full-mask votes, shuffles and __syncwarp() are the convergence
 // points): tl = lane index inside its team, go = "this team has an event" (a team without one only takes part in
 // the synchronisation).  Loads are issued in code all teams share, the event-kind specific parts are short
-// branches between two convergence points, so the memory round trips of the teams overlap instead of queueing.
+// predicated stretches between two convergence points, so the memory round trips of the teams overlap.
 // Itrans: 1..3 deposit species, 4 evaporate, 5 desorb, 6.. adsorb (main.f:335-357).
 // arm_u: uniform used when IF_Arm_Choice.f ties; forced_arm >= 0 overrides the choice (trace replay).
 template <int TEAM, int FEAT, class Lists>
@@ -202,8 +247,10 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
   const int tshift = (int)(threadIdx.x & 31u) - tl;         // first lane of the team inside the warp
   if (!(FEAT & F_COV) && go && kind >= DES) { fail_cell(E_BADEV, cS); go = false; }
   if ((FEAT & F_COV) && go && kind == ABS && Itrans - 5 > 3) { fail_cell(E_BADEV, cS); go = false; }
-  uint32_t wS = 0u; unsigned long long bS = 0ull;
-  if (go) { wS = D.state[cS]; bS = D.bonds[cS]; }
+  if (go && kind == DEP && Itrans < 1) { fail_cell(E_BADEV, cS); go = false; }
+  // ---- S's record (team-uniform: the lanes of a team load the same three words) ------------------------------
+  uint32_t wS = 0u, aS = 0u; unsigned long long bS = 0ull;
+  if (go) { wS = D.state[cS]; bS = D.bonds[cS]; aS = D.aux[cS]; }
   const int c0 = w_coor(wS);
   int CovNew = 0;
   {                                                        // S's word: occupancy / species / coverage (coordination follows at the end)
@@ -217,42 +264,42 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
     if (go && tl == 4) {
       if (dsp >= 0 && dsp < 3) K.dCrystal[dsp] += sgn;
       if (dcv >= 0 && dcv < 3) K.dCov[dcv] += sgn;
-      D.state[cS] = wS;
+      if (FEAT & F_COV) D.state[cS] = wS;                  // the census of a neighbour looks back at S (coverage runs only)
     }
   }
-  __syncwarp();                                            // S's new occupancy is visible before any lane looks back at it
+  if (FEAT & F_COV) __syncwarp();                          // S's new occupancy is visible before any lane looks back at it
 
-  // deposition.f:49-74: a 1-coordinated site fixes bonds 2..4 (cubic or hexagonal continuation)
+  // ---- deposition.f:49-74: a 1-coordinated site fixes bonds 2..4 (cubic or hexagonal continuation) -------------
   const bool fix = go && kind == DEP && c0 == 1;
-  unsigned zig[3] = {0u, 0u, 0u}, arm[3] = {0u, 0u, 0u};
-  const unsigned e = fld(bS, 0);
-  int cc = 0;
-  if (fix) {
-    const P3 C = dec_bond(S, e);
-    const unsigned long long bC = D.bonds[ccell(C)];
-    const unsigned back = (unsigned)NEGC - e;
-    unsigned g[3] = {0u, 0u, 0u}; int j = 0;
+  if (__any_sync(FULL, fix)) {
+    unsigned zig[3] = {0u, 0u, 0u}, arm[3] = {0u, 0u, 0u};
+    const unsigned e = fld(bS, 0);
+    int cc = 0;
+    if (fix) {
+      P3 C; const uint32_t cC = nbr(S, e, C);
+      const unsigned long long bC = D.bonds[cC];
+      const unsigned back = (unsigned)NEGC - e;
+      unsigned g[3] = {0u, 0u, 0u}; int j = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) { const unsigned f = fld(bC, i); if (f != back) { if (j < 3) g[j] = f; j++; } }
-    const unsigned ao = (unsigned)__ldg(&D.arm_tab[e]);
-    bool slow = (ao == 0u) | (g[0] == 0u) | (g[1] == 0u) | (g[2] == 0u);
+      for (int i = 0; i < 4; i++) { const unsigned f = fld(bC, i); if (f != back) { if (j < 3) g[j] = f; j++; } }
+      const unsigned ao = (unsigned)__ldg(&D.arm_tab[e]);
+      bool slow = (ao == 0u) | (g[0] == 0u) | (g[1] == 0u) | (g[2] == 0u);
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      zig[i] = (unsigned)NEGC - g[i];
-      // componentwise g + e + ao on the biased fields: (a+16)+(b+16)+(c+16) = (a+b+c+16)+32
-      const unsigned sx = (g[i] & 31u) + (e & 31u) + (ao & 31u), sy = ((g[i] >> 5) & 31u) + ((e >> 5) & 31u) + ((ao >> 5) & 31u), sz = (g[i] >> 10) + (e >> 10) + (ao >> 10);
-      slow |= (sx - 33u > 30u) | (sy - 33u > 30u) | (sz - 33u > 30u);
-      arm[i] = (sx - 32u) | ((sy - 32u) << 5) | ((sz - 32u) << 10);
+      for (int i = 0; i < 3; i++) {
+        zig[i] = (unsigned)NEGC - g[i];
+        // componentwise g + e + ao on the biased fields: (a+16)+(b+16)+(c+16) = (a+b+c+16)+32
+        const unsigned sx = (g[i] & 31u) + (e & 31u) + (ao & 31u), sy = ((g[i] >> 5) & 31u) + ((e >> 5) & 31u) + ((ao >> 5) & 31u), sz = (g[i] >> 10) + (e >> 10) + (ao >> 10);
+        slow |= (sx - 33u > 30u) | (sy - 33u > 30u) | (sz - 33u > 30u);
+        arm[i] = (sx - 32u) | ((sy - 32u) << 5) | ((sz - 32u) << 10);
+      }
+      if (slow) slow_find_sn(S, C, g, zig, arm);
+      // IF_Arm_Choice.f:38-54: lanes 0..2 read the arm-chair cells, 3..5 the zig-zag cells
+      if (tl < 6) {
+        const int k = tl < 3 ? tl : tl - 3;
+        const unsigned fa = k == 0 ? arm[0] : (k == 1 ? arm[1] : arm[2]), fz = k == 0 ? zig[0] : (k == 1 ? zig[1] : zig[2]);
+        P3 X; cc = w_coor(D.state[nbr(S, tl < 3 ? fa : fz, X)]);
+      }
     }
-    if (slow) slow_find_sn(S, C, g, zig, arm);
-    // IF_Arm_Choice.f:38-54: lanes 0..2 read the arm-chair cells, 3..5 the zig-zag cells
-    if (tl < 6) {
-      const int k = tl < 3 ? tl : tl - 3;
-      const unsigned fa = k == 0 ? arm[0] : (k == 1 ? arm[1] : arm[2]), fz = k == 0 ? zig[0] : (k == 1 ? zig[1] : zig[2]);
-      cc = w_coor(D.state[ccell(dec_bond(S, tl < 3 ? fa : fz))]);
-    }
-  }
-  {
     const int CoorArm = __shfl_sync(FULL, cc, 0, TEAM) + __shfl_sync(FULL, cc, 1, TEAM) + __shfl_sync(FULL, cc, 2, TEAM);
     const int CoorZig = __shfl_sync(FULL, cc, 3, TEAM) + __shfl_sync(FULL, cc, 4, TEAM) + __shfl_sync(FULL, cc, 5, TEAM);
     if (fix) {
@@ -266,91 +313,178 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
   }
 
   // ---- phase A: lane i < 4 updates neighbour i ---------------------------------------------------
-  int act = -1, qOcc = 0, qSp = 0, qCov = 0, qCoor = 0;
-  P3 qN = S; uint32_t qc = cS; unsigned long long qrb = bS;
-  int qsl = 0;                                            // the site's list slot, fetched early (off the critical path of the commit)
-  if (go && tl == 4) qsl = L.slot_of(cS);
+  // the request this lane will rate and commit (lanes 0..3: neighbour i, lane 4: S)
+  int act = -1, qOcc = 0, qSp = 0, qCov = 0, qCoor = 0, nb1 = 4;
+  P3 qN = S; uint32_t qc = cS, qw = wS, qaux = aS; unsigned long long qrb = bS;
+  unsigned qfl = aux_flags(aS), qfl0 = qfl;               // census flags of the request's site: new, and as stored
+  unsigned sflag = 0u;                                    // what this neighbour contributes to S's census after the event
   bool sUp = false, sDown = false;                        // this neighbour raises / lowers S's own coordination
   bool keepable = false;                                  // Evaporation.f:229-258: occupied, under-coordinated, reciprocal neighbour of S
+  int fcoor = 0;                                          // coordination of this neighbour as the lattice holds it after phase A
+  int xmode = 0;                                          // 1: second bond (two more cells), 2: coordination of the old first neighbour (one cell)
+  unsigned xf0 = 0u, xf1 = 0u, xfb = 0u; uint32_t wN0 = 0u;
   if (go && tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
     const unsigned f = fld(bS, tl);
-    const P3 N = dec_bond(S, f);
-    const uint32_t cN = ccell(N);
-    const uint32_t wN = D.state[cN];
+    P3 N; const uint32_t cN = nbr(S, f, N);
+    const uint32_t wN = D.state[cN], aN = D.aux[cN];
     unsigned long long bN = D.bonds[cN];
-    qsl = L.slot_of(cN);
     const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN);
     const bool rec = recip_f(N, bN, S, f);
     const bool wall = Occ && CovN == 113;
-    qN = N; qc = cN; qCov = CovN; qOcc = Occ; qSp = Occ ? w_sp(wN) : 0;
+    const unsigned fb = (unsigned)NEGC - f;                // the bond N -> S
+    const int jS = find_code(bN, fb);                      // where N lists S (its census flag for S lives there)
+    unsigned flN = aux_flags(aN);
+    qN = N; qc = cN; qCov = CovN; qOcc = Occ; qSp = Occ ? w_sp(wN) : 0; qaux = aN; qfl0 = flN; wN0 = wN;
     int newCoor = -1; uint32_t wNew = wN;
+    const unsigned long long bN0 = bN;
+    unsigned long long rbN = bN;                           // the bond list the site is rated with (Evaporation.f:123: the OLD one)
     if (Occ && !wall && CovN != 0 && kind <= EVAP) fail_cell(E_NNCOV, cN);
     else if (kind == DEP) {
-      if (wall) sUp = true;                                // deposition.f:231-232
+      if (wall) { sUp = true; sflag = 1u; }                // deposition.f:231-232
       else if (Occ) {                                      // :191-229 full neighbour
-        if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && tl >= 1); }
+        if (rec) sflag = (unsigned)(w_sp(wN) & 3);
+        if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && tl >= 1); if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }
       } else if (CoorNN == 0) {                            // :88-99 a new active empty site with one fixed bond
-        bN = f ? (unsigned long long)((unsigned)NEGC - f) : (unsigned long long)enc_bond_cold(N, S);
-        D.bonds[cN] = bN;
-        newCoor = 1; act = A_NEW;
-      } else if (CoorNN == 1) {                            // :100-160 second bond: complete the tetrahedron
-        const int cnew = second_bond(S, N, f ? (unsigned)NEGC - f : enc_bond_cold(N, S), bN);
-        if (cnew) { D.bonds[cN] = bN; newCoor = cnew; act = A_SETVOID; }
-      } else if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETVOID; }   // :161-190
+        bN = f ? (unsigned long long)fb : (unsigned long long)enc_bond_cold(N, S);
+        rbN = bN;
+        newCoor = 1; act = A_NEW; flN = (unsigned)Itrans; nb1 = c0;   // rated against S's OLD coordination (deposition.f:237-250 writes it last)
+      } else if (CoorNN == 1) {                            // :100-160 second bond: complete the tetrahedron (two more cells, below)
+        const unsigned f0 = fld(bN, 0);
+        const int dx = cdx(f0) + cdx(f), dy = cdy(f0) + cdy(f), dz = cdz(f0) + cdz(f);      // M - S = (M - N) + (N - S)
+        int Dx = abs(dx); Dx = min(Dx, D.LX - Dx);
+        int Dy = abs(dy); Dy = min(Dy, D.LY - Dy);
+        if (f0 != 0u && f != 0u && Dx * Dx + Dy * Dy + dz * dz == 72) {
+          // FIND_NN.f:46-76 rotates b2 = S-N by +-120 degrees about b1 = M-N.  For two bonds of the ideal shell (|b|^2 = 27,
+          // tetrahedral pair) the rotation is exact in integers: -(b1+b2)/2 -+ (b1 x b2)/6 (D.nn_exact, checked at start-up)
+          const int b1x = cdx(f0), b1y = cdy(f0), b1z = cdz(f0), b2x = cdx(fb), b2y = cdy(fb), b2z = cdz(fb);
+          unsigned fn[2];
+          if (D.nn_exact && b1x * b1x + b1y * b1y + b1z * b1z == 27 && b2x * b2x + b2y * b2y + b2z * b2z == 27) {
+            const int cx = b1y * b2z - b1z * b2y, cy = b1z * b2x - b1x * b2z, cz = b1x * b2y - b1y * b2x;
+            const int sx = -(b1x + b2x) / 2, sy = -(b1y + b2y) / 2, sz = -(b1z + b2z) / 2;
+            fn[0] = (unsigned)(sx - cx / 6 + 16) | ((unsigned)(sy - cy / 6 + 16) << 5) | ((unsigned)(sz - cz / 6 + 16) << 10);
+            fn[1] = (unsigned)(sx + cx / 6 + 16) | ((unsigned)(sy + cy / 6 + 16) << 5) | ((unsigned)(sz + cz / 6 + 16) << 10);
+          } else slow_find_nn(S, N, f0, fn);
+          xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb;
+        } else if (f0 == 0u || f == 0u) {                  // unfixed first bond: the general distance test on coordinates
+          const P3 M = dec_bond(N, f0);
+          int Ex = abs(M.x - S.x); Ex = min(Ex, D.LX - Ex);
+          int Ey = abs(M.y - S.y); Ey = min(Ey, D.LY - Ey);
+          const int ez = M.z - S.z;
+          if (Ex * Ex + Ey * Ey + ez * ez == 72) { unsigned fn[2]; slow_find_nn(S, N, f0, fn); xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = f ? fb : enc_bond_cold(N, S); }
+        }
+      } else if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETVOID; if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }   // :161-190
     } else if (kind == EVAP) {
       if (wall) sDown = true;                              // Evaporation.f:211-213
       else if (rec) {
         if (Occ) {                                         // :173-209; a bulk atom becomes active again
-          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_BULK2MC : A_SET; keepable = true;
+          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_BULK2MC : A_SET; keepable = true; sflag = (unsigned)(w_sp(wN) & 3);
+          if (jS >= 0) flN = flag_set(flN, jS, 0u);
         } else if (CoorNN == 1) {                          // :62-79 orphaned empty site leaves the lattice
           wNew = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
-          D.bonds[cN] = 0ull;
+          bN = 0ull; flN = 0u;
           act = A_ERASE; qCov = 0;
-        } else if (CoorNN >= 2 && CoorNN <= 4) {           // :80-164; 4: a vacancy becomes active again
+        } else if (CoorNN == 2) {                          // :80-128 back to one bond: keep the occupied reciprocal neighbour that is left
+          newCoor = 1; act = A_SET;
+          const unsigned others = jS >= 0 ? flag_set(flN, jS, 0u) : flN;
+          int k = -1;
+#pragma unroll
+          for (int j = 0; j < 4; j++) if (flag_get(others, j)) k = j;
+          if (k < 0) { fail(E_STALE_NBUFF, N.x, N.y, N.z); k = 0; }
+          const unsigned fk = fld(bN, k);
+          flN = flag_get(others, k);
+          // (rated with the OLD neighbour list, Evaporation.f:123: what matters is the coordination of the old first neighbour)
+          const unsigned f0 = fld(bN, 0);
+          if (f0 == fb) nb1 = c0;                          // it is S, whose word still holds its old coordination
+          else { xmode = 2; xf0 = f0; }
+          bN = (unsigned long long)fk;
+        } else if (CoorNN == 3 || CoorNN == 4) {           // :129-164; 4: a vacancy becomes active again
           newCoor = CoorNN - 1; act = CoorNN == 4 ? A_VOID2MC : A_SET;
-          if (CoorNN == 2) D.bonds[cN] = coop_compact(N, bN);          // (rated with the OLD neighbour list, :123)
+          if (jS >= 0) flN = flag_set(flN, jS, 0u);
         }
       }
     } else if ((FEAT & F_COV) && Occ && !wall && CoorNN <= 3 && rec) { act = A_SET; newCoor = CoorNN; }   // absorption.f:43-72 / desorption.f:54-111
     if (newCoor >= 0) { wNew = MVBITS(wN, newCoor, LenCoor, PosCoor); qCoor = newCoor; }
-    if (wNew != wN) D.state[cN] = wNew;
-    qrb = bN;
+    if (xmode != 1) {                                      // (a second bond is committed after its two extra cells were seen)
+      if (wNew != wN) D.state[cN] = wNew;
+      if (bN != bN0) D.bonds[cN] = bN;
+    }
+    qw = wNew; qrb = rbN; qfl = flN; fcoor = w_coor(wNew);
+  }
+  // ---- the cells one more bond away that the reference itself reads (all lanes that need some, together) -----------
+  if (__any_sync(FULL, xmode != 0)) {
+    if (xmode == 1) {                                      // deposition.f:107-142: already-present reciprocal atoms on the two new bonds count
+      P3 X0, X1; const uint32_t c0x = nbr(qN, xf0, X0), c1x = nbr(qN, xf1, X1);
+      const uint32_t w0 = D.state[c0x], w1 = D.state[c1x];
+      const unsigned long long b0 = D.bonds[c0x], b1 = D.bonds[c1x];
+      const bool norigin = (qN.x | qN.y | qN.z) == 0;
+      bool r0 = xf0 ? lists_code(b0, (unsigned)NEGC - xf0) : recipr_cold(X0, b0, qN);
+      bool r1 = xf1 ? lists_code(b1, (unsigned)NEGC - xf1) : recipr_cold(X1, b1, qN);
+      if (norigin) { r0 |= lists_code(b0, 0u); r1 |= lists_code(b1, 0u); }
+      const bool q0 = w_occ(w0) && w_coor(w0) <= 3 && w_cov(w0) != 113 && r0;
+      const bool q1 = w_occ(w1) && w_coor(w1) <= 3 && w_cov(w1) != 113 && r1;
+      const unsigned f0 = fld(qrb, 0);
+      const unsigned long long bN = (unsigned long long)f0 | ((unsigned long long)xfb << 16) | ((unsigned long long)xf0 << 32) | ((unsigned long long)xf1 << 48);
+      const int cnew = 2 + (q0 ? 1 : 0) + (q1 ? 1 : 0);
+      qfl = flag_get(qfl, 0) | ((unsigned)Itrans << 2) | ((q0 ? (unsigned)(w_sp(w0) & 3) : 0u) << 4) | ((q1 ? (unsigned)(w_sp(w1) & 3) : 0u) << 6);
+      qw = MVBITS(wN0, cnew, LenCoor, PosCoor); qCoor = cnew; fcoor = cnew; act = A_SETVOID;
+      D.state[qc] = qw; D.bonds[qc] = bN; qrb = bN;
+    } else if (xmode == 2) {
+      P3 X; nb1 = w_coor(D.state[nbr(qN, xf0, X)]);
+    }
   }
   const unsigned upm = (__ballot_sync(FULL, sUp) >> tshift) & tm, downm = (__ballot_sync(FULL, sDown) >> tshift) & tm;
   const int Coor = c0 + __popc(upm) - __popc(downm);
   const unsigned keepm = (__ballot_sync(FULL, keepable) >> tshift) & 15u;
-  __syncwarp();                                            // neighbours' words are final and visible to the whole team
+  const unsigned sf0 = (__ballot_sync(FULL, (sflag & 1u) != 0u) >> tshift) & 15u, sf1 = (__ballot_sync(FULL, (sflag & 2u) != 0u) >> tshift) & 15u;
+  const int fcoor0 = __shfl_sync(FULL, fcoor, 0, TEAM);    // the first neighbour's coordination after phase A
+  if (FEAT & F_COV) __syncwarp();                          // neighbours' words are final and visible to the whole team
   // ---- S's own request (lane 4) -----------------------------------------------------------------------
   uint32_t wS2 = wS;
   if (go && tl == 4) {
-    qCoor = Coor; qCov = CovNew; act = A_SET;
-    if (kind <= EVAP) wS2 = MVBITS(wS, Coor, LenCoor, PosCoor);
+    // S's census, recomputed from what the four lanes saw: bit pairs (sf1,sf0) of lane i -> flag of bond i
+    unsigned flS = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) flS |= (((sf0 >> i) & 1u) | (((sf1 >> i) & 1u) << 1)) << (2 * i);
+    qCoor = Coor; qCov = CovNew; act = A_SET; qw = wS; qfl = qfl0;
+    if (kind <= EVAP) { wS2 = MVBITS(wS, Coor, LenCoor, PosCoor); qfl = flS; }
     if (kind == DEP) { act = A_SETBULK; qOcc = 1; qSp = Itrans; }
     else if (kind == EVAP) {
-      if (Coor == 0) act = A_ERASE;
+      if (Coor == 0) { act = A_ERASE; qfl = 0u; }
       else if (Coor == 1) {                                // Evaporation.f:224-258: keep the last qualifying neighbour only
         if (!keepm) fail(E_STALE_NBUFF, S.x, S.y, S.z);
-        D.bonds[cS] = (unsigned long long)fld(bS, 31 - __clz((int)(keepm | 1u)));
+        const int k = 31 - __clz((int)(keepm | 1u));
+        D.bonds[cS] = (unsigned long long)fld(bS, k);
+        qfl = flag_get(flS, k);
+        nb1 = fcoor0;                                      // rated with the OLD list (Evaporation.f:216-223): its first entry is N0
       }
-    }
+    } else if (c0 == 1) nb1 = fcoor0;                      // desorption / adsorption on a 1-coordinated site
+    qw = wS2;
   }
   // ---- phase B: lanes 0..4 rate their site -----------------------------------------------------------
   int ev = 0; double p = 0.0;
-  if (act >= 0 && act != A_ERASE) { coop_rate<FEAT>(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p); K.nsu++; }
-  __syncwarp();
+  if (act >= 0 && act != A_ERASE) {
+    if (FEAT & F_COV) {
+      unsigned cf = qfl;
+      coop_rate<FEAT>(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p, &cf);
+      if (qOcc && cf != qfl && !(qCov > 0 && qCov < 113)) fail(E_FLAGS, qN.x, qN.y, qN.z, (int)(cf | (qfl << 8)));
+    } else flag_rate<FEAT>(qOcc, qSp, qCoor, qw, qc, qfl, nb1, root, ev, p);
+    K.nsu++;
+  }
+  if (FEAT & F_COV) __syncwarp();
   // S's coordination is written after its neighbours were rated (deposition.f:237-250)
   if (go && tl == 4) {
-    if (wS2 != wS) D.state[cS] = wS2;
+    if (!(FEAT & F_COV) || wS2 != wS) D.state[cS] = wS2;
     if (act == A_ERASE) D.bonds[cS] = 0ull;
   }
-  // ---- phase C: list bookkeeping (mskc_device.cuh: rq_commit) -------------------------------------------
+  // ---- phase C: census flags, list bookkeeping (mskc_device.cuh: rq_commit) -------------------------------------------
   if (act >= 0) {
+    if (qfl != qfl0) st_flags(qc, qfl);
     const bool gone = (ev == 0) && (act == A_SETVOID || act == A_SETBULK);   // the site left the active set
     if (act == A_SETVOID && gone) K.dVoids++;
     if (act == A_SETBULK && gone) K.dAtoms++;
     if (act == A_VOID2MC) K.dVoids--;
     if (act == A_BULK2MC) K.dAtoms--;
-    if (act == A_ERASE || ev == 0) L.erase(qN, qc, qsl); else L.put(qN, qc, ev, p, qsl);
+    if (act == A_ERASE || ev == 0) L.erase(qN, qc, aux_slot(qaux)); else L.put(qN, qc, ev, p, aux_slot(qaux));
   }
   __syncwarp();
 }

@@ -16,7 +16,13 @@
 // TilePol (mskc_parallel.cuh: per-tile active lists for the synchronous-sublattice sampler).
 #pragma once
 #include <cstdint>
+#ifndef MSKC_EMU
 #include <cuda_runtime.h>
+// kernel launch / dynamic shared memory, spelled through macros so that tests/emu/cuda_emu.h (a functional SIMT
+// emulator used by the GPU-less test container, test infrastructure only) can compile these sources with g++
+#define MSKC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MSKC_DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
 
 namespace mskc {
 
@@ -28,7 +34,8 @@ enum {
   E_NONE = 0, E_OOB = 1 /* z out of range */, E_FARBOND = 2, E_TREE_ZERO = 3 /* UpdateTree.f:38 */, E_TREE_IDX = 4 /* UpdateTree.f:44 */,
   E_PICK = 5 /* PickTreeEvent.f:58 */, E_ADD_ZERO = 6 /* Add.f:38 */, E_MC_FULL = 7 /* Add.f:42 */, E_VOID_FULL = 8 /* Add.f:94 */,
   E_ERASE = 9 /* Erase.f:47 */, E_COVOCC = 10 /* Get_Prob.f:94 */, E_COVLIST = 11 /* Get_Prob.f:108 */, E_CENSUS = 12 /* Get_Prob.f:293 */,
-  E_TEMP0 = 13 /* Get_Prob.f:133 */, E_NNCOV = 14 /* deposition.f:194 */, E_TILE_FULL = 15, E_STALE_NBUFF = 16, E_TRANGE = 17, E_BADEV = 18
+  E_TEMP0 = 13 /* Get_Prob.f:133 */, E_NNCOV = 14 /* deposition.f:194 */, E_TILE_FULL = 15, E_STALE_NBUFF = 16, E_TRANGE = 17, E_BADEV = 18,
+  E_FLAGS = 19 /* incremental census flags disagree with the full census (mskc_coop.cuh) */
 };
 
 struct P3 { int x, y, z; };
@@ -39,6 +46,7 @@ struct DevCtx {
   long long ncell;                  // LX*LY*(LZ+1)
   uint32_t *state;
   unsigned long long *bonds;
+  uint32_t *aux;                    // sampler: list slot (bits 0-15) + census flags (bits 16-23) per cell, see mskc_coop.cuh
   const double *PE, *PD, *PAbs, *PDes;   // Fortran-flattened tables (defsystem.f:60-65)
   double PZig;
   double PDepAbs[4];                // [coor]: sum of the deposition + adsorption rates of an empty site (Get_Prob.f:160-163), plain tables
@@ -101,9 +109,13 @@ __device__ __forceinline__ P3 cell_xyz(long long c) {     // ncell < 2^32 (mskc_
   p.z = (int)z; p.y = (int)y; p.x = (int)(r - y * (unsigned)D.LX); return p;
 }
 // fire-and-forget loads that pull a cell's words into L1 (results unused; volatile asm is not eliminated)
+#ifndef MSKC_EMU
 __device__ __forceinline__ void touch32(const void *p) { unsigned v; asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); }
 __device__ __forceinline__ void touch64(const void *p) { unsigned long long v; asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); }
-__device__ __forceinline__ void touch16(const void *p) { unsigned short v; asm volatile("ld.global.ca.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); }
+#else
+__device__ __forceinline__ void touch32(const void *) {}
+__device__ __forceinline__ void touch64(const void *) {}
+#endif
 __device__ __forceinline__ bool in_box(P3 p) {
   return (unsigned)p.x < (unsigned)D.LX && (unsigned)p.y < (unsigned)D.LY && (unsigned)p.z <= (unsigned)D.LZ;
 }

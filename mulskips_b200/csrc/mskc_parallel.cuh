@@ -9,7 +9,8 @@
 // HBM layout added to state[]/bonds[] (mskc_device.cuh):
 //   rate[list][slot] f64, ce[list][slot] u64 {u32 cell, u32 event}: the per-tile active-site lists, tile-major
 //   cnt[tile]           i32  slots in use (tombstones with rate 0 included until the owner compacts)
-//   slot[cell]          u16  1-based slot of the cell in its tile's list, 0 = not listed
+//   aux[cell]           u32  bits 0-15: 1-based slot of the cell in its tile's list (0 = not listed); bits 16-23: the
+//                            cell's census flags (mskc_coop.cuh)
 //   tstat[tile]         per-tile counters (events, site updates, per-class counts), summed on demand
 //   lag[tile]           f64  time the tile still owes (its last colour step stopped at the event cap)
 #pragma once
@@ -18,7 +19,9 @@
 #include "../../include/mskc.h"
 #include <algorithm>
 #include <dlfcn.h>
+#ifndef MSKC_EMU
 #include <nccl.h>
+#endif
 #include <cstdlib>
 #include <cstdio>
 #include <functional>
@@ -46,7 +49,7 @@ struct SweepState {          // one per context, device resident
 // colour are contiguous (l = colour*ntc + index).
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
-  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint16_t *slot = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
+  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint32_t *aux = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
   // slab mode
   int halo = 0, rank = 0, nranks = 1;
@@ -66,7 +69,7 @@ struct ParallelCtx {
 
 struct TileView {            // what the kernels need (constant memory)
   int tile, ntx, nty, cap, NT, hx, ntc;
-  double *rate; unsigned long long *ce; int *cnt; uint16_t *slot; double *tile_rate; TileStat *tstat; SweepState *ss;
+  double *rate; unsigned long long *ce; int *cnt; double *tile_rate; TileStat *tstat; SweepState *ss;
   double *lag;                          // [tile] KMC time a tile still owes because its colour step hit the event cap
   // x-decomposed slab (multi-GPU): one halo tile column on each side of the owned block, see "halo exchange" below
   int halo, nranks;
@@ -132,7 +135,7 @@ struct TileLists {
   int own;                                   // list id of the running tile (-1: none, everything is "foreign")
   int mark;                                  // slab mode: log changed cells of the shared strips
   double *s_rate; unsigned long long *s_ce; int *s_n;
-  __device__ __forceinline__ int slot_of(uint32_t c) const { return V.slot[c]; }
+  __device__ __forceinline__ int slot_of(uint32_t c) const { return aux_slot(D.aux[c]); }
   // sl = the cell's current slot (slot_of(c)), read by the caller ahead of time
   __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p, int sl) {
     if (mark) mark_dirty(s, c);
@@ -141,7 +144,7 @@ struct TileLists {
     if (sl == 0) {
       const int k = mine ? atomicAdd(s_n, 1) : atomicAdd(&V.cnt[l], 1);
       if (k >= V.cap) { if (mine) atomicSub(s_n, 1); else atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
-      V.slot[c] = (uint16_t)(k + 1); sl = k + 1;
+      st_slot(c, k + 1); sl = k + 1;
     }
     const unsigned long long e = pack_ce(c, ev, s.x, s.y, s.z);
     if (mine) { s_rate[sl - 1] = p; s_ce[sl - 1] = e; }
@@ -214,8 +217,8 @@ __device__ __forceinline__ void tile_load(const int l, const int tl, const int t
       const bool live = (i < n0) && (r > 0.0);
       const unsigned m = (__ballot_sync(tmask, live) >> tshift) & tm;
       const int k = n + __popc(m & ((1u << tl) - 1u));
-      if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
-      else if (i < n0) V.slot[(uint32_t)e] = 0;
+      if (live) { s_rate[k] = r; s_ce[k] = e; if (k != i) st_slot((uint32_t)e, k + 1); }
+      else if (i < n0) st_slot((uint32_t)e, 0);
       n += __popc(m);
     }
   }
@@ -336,7 +339,7 @@ template <int TEAM, int FEAT>
 __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int colour, uint2 key, int event_cap) {
   constexpr int TPB = CS_THREADS / TEAM;
   constexpr unsigned FULL = 0xFFFFFFFFu;
-  extern __shared__ __align__(16) unsigned char smem[];
+  MSKC_DYN_SHARED(smem);
   const int lane = threadIdx.x & 31, tl = threadIdx.x % TEAM, tib = threadIdx.x / TEAM;
   const int tshift = lane - tl;
   const unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int co
 // sides of a rank boundary never touch the same cell (section 5.3 of DESIGN.md), so after a colour step the two
 // copies of a shared strip differ only where ONE side wrote: each rank sends the final record of every cell it
 // changed in its two 48-unit strips (its border tile column + its halo column) and applies what it receives.
-struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad; };     // 32 B
+struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad /* census flags */; };     // 32 B
 // one launch packs both strips (blockIdx.y = side); the last block to finish clears the dirty counters
 __global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of the owned block */, HaloRec *out0, HaloRec *out1, unsigned int *done) {
   const int side = blockIdx.y;
@@ -380,7 +383,8 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of th
     const uint32_t bit = (uint32_t)(((side * 2 * TILE + xs) * D.LY + s.y) * (D.LZ + 1) + s.z);
     atomicAnd(&V.dirty_bits[bit >> 5], ~(1u << (bit & 31u)));
     HaloRec r; r.cell = (uint32_t)((long long)c + shift); r.state = D.state[c]; r.bonds = D.bonds[c]; r.rate = 0.0; r.ev = 0; r.pad = 0;
-    const int sl = V.slot[c];
+    const uint32_t ax = D.aux[c]; const int sl = aux_slot(ax);
+    r.pad = aux_flags(ax);
     if (sl) { const long long a = lidx(list_of(s), sl - 1); r.rate = V.rate[a]; r.ev = (uint32_t)ce_event(V.ce[a]); }
     out[1 + k] = r;
   }
@@ -400,7 +404,8 @@ __global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in0, con
     const HaloRec r = in[1 + k];
     D.state[r.cell] = r.state; D.bonds[r.cell] = r.bonds;
     const P3 s = cell_xyz((long long)r.cell);
-    const int sl = V.slot[r.cell];
+    const int sl = aux_slot(D.aux[r.cell]);
+    st_flags(r.cell, r.pad);
     if (r.rate > 0.0) L.put(s, r.cell, (int)r.ev, r.rate, sl); else L.erase(s, r.cell, sl);
   }
 }
@@ -420,8 +425,8 @@ __global__ void __launch_bounds__(128) compact_lists_kernel(int ntiles) {
     const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
     const int k = n + __popc(m & ((1u << lane) - 1u));
     __syncwarp();
-    if (live) { V.rate[lidx(l, k)] = r; V.ce[lidx(l, k)] = e; if (k != i) V.slot[(uint32_t)e] = (uint16_t)(k + 1); }
-    else if (i < n0) V.slot[(uint32_t)e] = 0;
+    if (live) { V.rate[lidx(l, k)] = r; V.ce[lidx(l, k)] = e; if (k != i) st_slot((uint32_t)e, k + 1); }
+    else if (i < n0) st_slot((uint32_t)e, 0);
     n += __popc(m);
     __syncwarp();
   }
@@ -460,6 +465,36 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   if (lane == 0) {
     if (fork) { volatile int *cl = g_la_CL; cl[0] = cl0[0] - v[3]; cl[1] = cl0[1] - v[4]; cl[2] = cl0[2] - v[5]; cl[3] = cl[0] + cl[1] + cl[2]; }   // for the next chunk
     out->events += done; out->site_updates += v[0]; out->dAtoms += v[1]; out->dVoids += v[2];
+    for (int i = 0; i < 3; i++) { out->dCrystal[i] += v[3 + i]; out->dCov[i] += v[6 + i]; }
+  }
+}
+
+// Trace replay through the instantiation the sampler itself runs: four 8-lane teams in lock step, FEAT as
+// mskc_run_parallel picks it.  batch[4*b + t] = index of the event team t applies in lock-step iteration b, or -1 (the
+// team idles through the iteration, as a tile without an event does).  Events of one iteration commute (the host puts
+// only events more than two tile edges apart into one iteration), so the outcome equals the serial trace.
+template <int FEAT>
+__global__ void __launch_bounds__(32) replay_teams_kernel(const int32_t *ev_site, const int32_t *ev_code, const int32_t *ev_arm, const int32_t *batch, long long nbatch, double root, TileStat *out) {
+  const int lane = threadIdx.x, team = lane >> 3, tl = lane & 7;
+  TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
+  CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
+  for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
+  long long done = 0;
+  for (long long b = 0; b < nbatch; b++) {
+    const int i = batch[4 * b + team];
+    const bool go = i >= 0;
+    P3 S; S.x = S.y = S.z = 0; int code = 4, arm = 0;
+    if (go) { S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2]; code = ev_code[i]; arm = ev_arm[i]; }
+    coop_event<8, FEAT>(L, tl, go, S, go ? (uint32_t)cidx(S) : 0u, code, root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    if (go && tl == 0) done++;
+    if (__any_sync(0xFFFFFFFFu, D.err[0] != 0)) break;
+  }
+  int v[9] = {K.nsu, K.dAtoms, K.dVoids, K.dCrystal[0], K.dCrystal[1], K.dCrystal[2], K.dCov[0], K.dCov[1], K.dCov[2]};
+#pragma unroll
+  for (int k = 0; k < 9; k++) v[k] = __reduce_add_sync(0xFFFFFFFFu, v[k]);
+  const long long dn = (long long)__reduce_add_sync(0xFFFFFFFFu, (int)done);
+  if (lane == 0) {
+    out->events += dn; out->site_updates += v[0]; out->dAtoms += v[1]; out->dVoids += v[2];
     for (int i = 0; i < 3; i++) { out->dCrystal[i] += v[3 + i]; out->dCov[i] += v[6 + i]; }
   }
 }
@@ -542,11 +577,38 @@ __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long l
     P3 s = cell_xyz((long long)cell);
     uint32_t w = D.state[cell];
     int ev = 0; double p = 0;
-    coop_rate<F_COV | F_LA>(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, D.bonds[cell], root, ev, p);
+    const unsigned long long b = D.bonds[cell];
+    st_flags(cell, census_flags(s, w, b));
+    coop_rate<F_COV | F_LA>(w_occ(w), w_sp(w), w_occ(w) ? 0 : w_cov(w), w_coor(w), s, cell, b, root, ev, p);
     if (ev != 0 && p > 0) { V.rate[k] = p; V.ce[k] = pack_ce(cell, ev, s.x, s.y, s.z); mine++; }
   }
   for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, o);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_sites, mine);
+}
+
+// ---- the dense census pass: census flags of every cell that carries bonds (after an upload / a device-side build;
+// mode 1 = check: count cells whose stored flags differ from the census, and cells whose flag count differs from the
+// coordination in their lattice word) -- Get_Prob.f:216-291 as one streaming pass over bonds[] (8 B/cell)
+__global__ void __launch_bounds__(256) census_flags_kernel(int check, unsigned long long *out /* [3]: sites, flag mismatches, coordination mismatches */) {
+  unsigned long long nsite = 0, nbad = 0, ncoor = 0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < D.ncell; c += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long b = D.bonds[c];
+    if (b == 0ull) continue;
+    const uint32_t w = D.state[c];
+    const P3 q = cell_xyz(c);
+    const unsigned fl = census_flags(q, w, b);
+    nsite++;
+    if (check) { if (fl != aux_flags(D.aux[c])) nbad++; }
+    else st_flags((uint32_t)c, fl);
+    // consistency of the lattice word with the census (Get_Prob.f:293), where every bond stays inside the box
+    bool inside = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const unsigned f = fld(b, i); if (f && (unsigned)(q.z + cdz(f)) > (unsigned)D.LZ) inside = false; }
+    const unsigned nz = (fl | (fl >> 1)) & 0x55u;
+    if (inside && w_cov(w) != 113 && __popc(nz) != w_coor(w)) ncoor++;
+  }
+  for (int o = 16; o > 0; o >>= 1) { nsite += __shfl_down_sync(0xFFFFFFFFu, nsite, o); nbad += __shfl_down_sync(0xFFFFFFFFu, nbad, o); ncoor += __shfl_down_sync(0xFFFFFFFFu, ncoor, o); }
+  if ((threadIdx.x & 31) == 0) { if (nsite) atomicAdd(&out[0], nsite); if (nbad) atomicAdd(&out[1], nbad); if (ncoor) atomicAdd(&out[2], ncoor); }
 }
 
 // ---- helper kernels used by mskc_api.cu ----------------------------------------------------------
@@ -688,7 +750,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, 4, x, y, z); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, 4, x, y, z); st_slot((uint32_t)c, k + 1);
         atomicAdd(&counters[1], 1ull);
       } else {
         D.state[c] = (2u << PosCoor);
@@ -697,7 +759,7 @@ __global__ void __launch_bounds__(256) init_flat_kernel(int Len, int walls, int 
         int t = list_of(s);
         int k = atomicAdd(&V.cnt[t], 1);
         if (k >= V.cap) { fail(E_TILE_FULL, x, y, z, t); continue; }
-        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, EV_DRAW, x, y, z); V.slot[c] = (uint16_t)(k + 1);
+        V.rate[lidx(t, k)] = p; V.ce[lidx(t, k)] = pack_ce((uint32_t)c, EV_DRAW, x, y, z); st_slot((uint32_t)c, k + 1);
         atomicAdd(&counters[1], 1ull);
       }
     }
@@ -742,13 +804,13 @@ static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
   cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.pack_done); cudaFree(P.red);
   for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
-  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.slot); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
+  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.aux); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
   P.halo = halo; P.rank = rank; P.nranks = nranks; P.comm = comm;
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
-  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.slot = P.slot;
+  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt;
   V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; V.lag = P.lag;
   V.halo = P.halo; V.nranks = P.nranks; V.dirty_bits = P.dirty_bits; V.dirty_cell = P.dirty_cell; V.dirty_n = P.dirty_n; V.dirty_cap = P.dirty_cap; V.red = P.red;
   return V;
@@ -759,7 +821,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   if (P.rate && P.cap == cap && P.ncell == H.ncell) {
     PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
     PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
-    PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
+    PCK(cudaMemsetAsync(P.aux, 0, (size_t)H.ncell * sizeof(uint32_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
     PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
     PCK(cudaMemsetAsync(P.lag, 0, (size_t)P.ntiles * sizeof(double), st));
@@ -772,7 +834,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMalloc(&P.rate, (size_t)P.ntiles * cap * sizeof(double)));
   PCK(cudaMalloc(&P.ce, (size_t)P.ntiles * cap * sizeof(unsigned long long)));
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
-  PCK(cudaMalloc(&P.slot, (size_t)H.ncell * sizeof(uint16_t)));
+  PCK(cudaMalloc(&P.aux, (size_t)H.ncell * sizeof(uint32_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.lag, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.tstat, (size_t)P.ntiles * sizeof(TileStat)));
@@ -796,11 +858,25 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ce, 0, (size_t)P.ntiles * cap * sizeof(unsigned long long), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
-  PCK(cudaMemsetAsync(P.slot, 0, (size_t)H.ncell * sizeof(uint16_t), st));
+  PCK(cudaMemsetAsync(P.aux, 0, (size_t)H.ncell * sizeof(uint32_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
   PCK(cudaMemsetAsync(P.lag, 0, (size_t)P.ntiles * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ss, 0, sizeof(SweepState), st));
+  return 0;
+}
+// census flags of every cell with bonds (check = 0: write them; 1: compare with the stored ones); out[3] as the kernel's
+static inline int parallel_census_flags(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int check, unsigned long long out[3], float *ms, cudaEvent_t e0, cudaEvent_t e1, std::string *err) {
+  unsigned long long *d = nullptr;
+  PCK(cudaMalloc(&d, 24)); PCK(cudaMemsetAsync(d, 0, 24, st));
+  if (e0) PCK(cudaEventRecord(e0, st));
+  MSKC_LAUNCH(census_flags_kernel, 148 * 8, 256, 0, st, check, d);
+  if (e1) PCK(cudaEventRecord(e1, st));
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(out, d, 24, cudaMemcpyDeviceToHost, st));
+  PCK(cudaStreamSynchronize(st));
+  if (ms && e0 && e1) PCK(cudaEventElapsedTime(ms, e0, e1));
+  cudaFree(d);
   return 0;
 }
 #ifndef MSKC_TILE_CAP
@@ -810,14 +886,14 @@ static const int TILE_CAP = MSKC_TILE_CAP;
 
 // per-sweep totals: local sums, all-reduce over the ranks of a slab run, then clock / tau / global-coupling terms
 static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, double tau_fixed, int advance, int *launches, std::string *err) {
-  sweep_sum_kernel<<<1, 1024, 0, st>>>(P.ntiles);
+  MSKC_LAUNCH(sweep_sum_kernel, 1, 1024, 0, st, P.ntiles);
   if (P.nranks > 1) {
     NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
     if (!P.comm) { if (err) *err = "slab run with several ranks: call mskc_comm_connect first"; return -1; }
     NCK(nccl->AllReduce(P.red, P.red, 4, ncclDouble, ncclSum, (ncclComm_t)P.comm, st));
   }
   const double owned = (double)(P.ntx - 2 * P.halo) * P.nty * P.nranks;
-  sweep_finish_kernel<<<1, 1, 0, st>>>(owned, ept, tau_fixed, advance);
+  MSKC_LAUNCH(sweep_finish_kernel, 1, 1, 0, st, owned, ept, tau_fixed, advance);
   *launches += 2;
   return 0;
 }
@@ -825,7 +901,7 @@ static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, doub
 static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int *launches, std::string *err) {
   const int owned = H.LX - 2 * P.tile;                         // width of the owned block = shift between the two copies of a strip
   // my left strip = the left neighbour's right strip (cells shift by +owned), my right strip = the right neighbour's left strip
-  halo_pack_kernel<<<dim3(16, 2), 256, 0, st>>>(owned, (HaloRec *)P.sendbuf[0], (HaloRec *)P.sendbuf[1], P.pack_done);
+  MSKC_LAUNCH(halo_pack_kernel, dim3(16, 2), 256, 0, st, owned, (HaloRec *)P.sendbuf[0], (HaloRec *)P.sendbuf[1], P.pack_done);
   const size_t bytes = (size_t)(HALO_CAP + 1) * sizeof(HaloRec);
   const unsigned char *in0 = P.sendbuf[0], *in1 = P.sendbuf[1];
   if (P.nranks > 1) {
@@ -840,7 +916,7 @@ static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st
     NCK(nccl->GroupEnd());
     in0 = P.recvbuf[0]; in1 = P.recvbuf[1];
   }                                                            // one rank: it is its own neighbour on both sides (periodic box)
-  halo_apply_kernel<<<dim3(16, 2), 256, 0, st>>>((const HaloRec *)in0, (const HaloRec *)in1);
+  MSKC_LAUNCH(halo_apply_kernel, dim3(16, 2), 256, 0, st, (const HaloRec *)in0, (const HaloRec *)in1);
   *launches += 2;
   return 0;
 }
@@ -851,7 +927,7 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
   if (H.LX % 48 || H.LY % 48) { P.lists_stale = true; return 0; }      // parity-only box
   if (parallel_alloc(P, H, st, TILE_CAP, err)) return -1;
   std::vector<double> R((size_t)P.ntiles * P.cap, 0.0); std::vector<unsigned long long> CE((size_t)P.ntiles * P.cap, 0ull);
-  std::vector<int> cnt(P.ntiles, 0); std::vector<uint16_t> slot((size_t)H.ncell, 0);
+  std::vector<int> cnt(P.ntiles, 0); std::vector<uint32_t> slot((size_t)H.ncell, 0);
   long long plane = (long long)H.LX * H.LY;
   const int hx = P.ntx / 2, ntc = (P.ntx / 2) * (P.nty / 2);
   for (int i = 0; i < n_mc; i++) {
@@ -867,12 +943,12 @@ static inline int parallel_build_from_lists(ParallelCtx &P, const DevCtx &H, cud
     uint32_t e = (ev == 4 || ev == 5 || forced) ? (uint32_t)ev : (uint32_t)EV_DRAW;
     size_t a = (size_t)t * P.cap + cnt[t];
     R[a] = mc_rate[i]; CE[a] = pack_ce(c, (int)e, x, y, (int)(c / plane));
-    slot[c] = (uint16_t)(++cnt[t]);
+    slot[c] = (uint32_t)(++cnt[t]);
   }
   PCK(cudaMemcpyAsync(P.rate, R.data(), R.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(P.ce, CE.data(), CE.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
   PCK(cudaMemcpyAsync(P.cnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  PCK(cudaMemcpyAsync(P.slot, slot.data(), slot.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  PCK(cudaMemcpyAsync(P.aux, slot.data(), slot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
   PCK(cudaStreamSynchronize(st));
   P.base_atoms = n_bulk; P.base_voids = n_void; P.time = 0; P.ran = false; P.replayed = false; P.lists_stale = false;
   for (int i = 0; i < 3; i++) { P.baseCrystal[i] = 0; P.baseCov[i] = 0; }
@@ -890,11 +966,12 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
   PCK(cudaMemsetAsync(H.bonds, 0, (size_t)H.ncell * sizeof(unsigned long long), st));
   unsigned long long *d_cnt = nullptr, h_cnt[2];
   PCK(cudaMalloc(&d_cnt, 16)); PCK(cudaMemsetAsync(d_cnt, 0, 16, st));
-  init_flat_kernel<<<148 * 8, 256, 0, st>>>(len1, walls, two_species, d_cnt);
+  MSKC_LAUNCH(init_flat_kernel, 148 * 8, 256, 0, st, len1, walls, two_species, d_cnt);
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, st));
   PCK(cudaStreamSynchronize(st));
   cudaFree(d_cnt);
+  { unsigned long long o[3]; if (parallel_census_flags(P, H, st, 0, o, nullptr, nullptr, nullptr, err)) return -1; }
   P.base_atoms = (long long)h_cnt[0]; P.base_voids = 0; P.time = 0; P.ran = false; P.lists_stale = false;
   memset(&P.h_tot, 0, sizeof P.h_tot);
   return 0;
@@ -926,10 +1003,10 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
   TileStat before = P.h_tot;
   int launches = 0;
-  reset_maxev_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.tstat, P.ntiles);
+  MSKC_LAUNCH(reset_maxev_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.tstat, P.ntiles);
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
-    tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
+    MSKC_LAUNCH(tile_rate_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.ntiles);
     if (sweep_totals(P, st, ept, a->tau_fixed, 0, &launches, err)) return -1;
     launches += 1;
   }
@@ -947,15 +1024,15 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      kern<<<blocks, CS_THREADS, smem, st>>>(col, key, evcap);
+      MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, key, evcap);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
-      bump_step_kernel<<<1, 1, 0, st>>>(P.ss);
+      MSKC_LAUNCH(bump_step_kernel, 1, 1, 0, st, P.ss);
       launches += 2; n_sampler_launches++;
       if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
     }
     if (sweep_totals(P, st, ept, a->tau_fixed, 1, &launches, err)) return -1;
   }
-  reduce_tstat_kernel<<<1, 256, 0, st>>>(P.tstat, P.ntiles, P.tot);
+  MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
   launches++;
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
@@ -984,8 +1061,8 @@ static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cu
   unsigned long long *d_n = nullptr, h_n = 0;
   PCK(cudaMalloc(&d_n, 8)); PCK(cudaMemsetAsync(d_n, 0, 8, st));
   PCK(cudaEventRecord(e0, st));
-  rerate_kernel<<<148 * 8, 256, 0, st>>>(P.ntiles, d_n);
-  tile_rate_kernel<<<(P.ntiles + 255) / 256, 256, 0, st>>>(P.ntiles);
+  MSKC_LAUNCH(rerate_kernel, 148 * 8, 256, 0, st, P.ntiles, d_n);
+  MSKC_LAUNCH(tile_rate_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.ntiles);
   { int l_ = 0; if (sweep_totals(P, st, 4.0, 0.0, 0, &l_, err)) return -1; }
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());

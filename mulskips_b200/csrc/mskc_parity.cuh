@@ -49,8 +49,12 @@ __constant__ ParityView PV;
 // complete tree in global memory.
 enum { PAR_TOP = 8192 };
 struct ParShared { double top[PAR_TOP]; int ma[56]; int inext, inextp, iff, idum; };
+#ifndef MSKC_EMU
 extern __shared__ __align__(16) unsigned char par_smem[];
 __device__ __forceinline__ ParShared &PSH() { return *reinterpret_cast<ParShared *>(par_smem); }
+#else
+__device__ __forceinline__ ParShared &PSH() { return *reinterpret_cast<ParShared *>(emu::dyn_smem()); }
+#endif
 __device__ __forceinline__ double tree_ld(int i) { return i < PAR_TOP ? PSH().top[i] : PV.Tree[i]; }
 __device__ __forceinline__ void tree_st(int i, double v) { if (i < PAR_TOP) PSH().top[i] = v; else PV.Tree[i] = v; }
 

@@ -22,7 +22,9 @@ def _has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    if _has_gpu():
+    # MSKC_EMU=1 (with MSKC_LIB pointing at tests/emu/_build/libmskc.so): run the GPU tests against the SIMT-emulated
+    # copy of the library -- a debugging aid of the GPU-less build container, never a substitute for the B200 run
+    if _has_gpu() or os.environ.get("MSKC_EMU") == "1":
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for it in items:

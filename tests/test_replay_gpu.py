@@ -37,25 +37,8 @@ def expected_active(orc):
     return out, d
 
 
-@pytest.mark.parametrize("case,box,lens,nev,kw", CASES, ids=[c[0] for c in CASES])
-def test_replay(tmp_path, case, box, lens, nev, kw):
-    from mulskips_b200 import Mskc
-    base = case.split("-zig")[0] if "-zig0" in case else case
-    start = make_start(base, str(tmp_path / "start.dat"), lens=lens, maxiter=10**9, outmolmol=10**9, maxtime=1e30, outtime=1e30, **kw)
-    orc = Oracle(*box, start)
-    orc.setup()
-    lc, lv = orc.species()
-    ctx = Mskc(*box, lc, lv)
-    upload_oracle_state(orc, ctx)
-    orc.set_trace(nev)
-    assert orc.run(nev) == nev
-    site, code, arm, tree1 = trace_arrays(orc)
-    assert len(code) == nev
-    done = 0
-    for chunk in (1, 9, 990, nev - 1000):
-        ctx.replay_events(site[done:done + chunk], code[done:done + chunk], arm[done:done + chunk], tree_root=1.0)
-        done += chunk
-    # lattice words
+def check_against_oracle(orc, ctx):
+    """lattice words, active set with (class, rate bits), bonds of every listed site, counters, census flags"""
     L, Lo = ctx.download_lattice(), orc.lattcoo()
     assert np.array_equal(L, Lo), f"{np.count_nonzero(L != Lo)} lattice words differ"
     # active sites: same set, same class, same rate bits (isolated atoms carry 100000*Tree(1): skipped)
@@ -85,6 +68,66 @@ def test_replay(tmp_path, case, box, lens, nev, kw):
     s = orc.sizes()
     assert (c.num_atoms, c.num_voids) == (s["NumAtoms"], s["NumVoids"])
     assert list(c.CountCrystal) == list(cc) and list(c.CountCov) == list(cv)
+    # the incrementally maintained neighbour census of every site equals a fresh census of the final lattice
+    nsites, bad_flags, bad_coor, _ = ctx.check_flags()
+    assert nsites > 0 and bad_flags == 0, (nsites, bad_flags, bad_coor)
+
+
+@pytest.mark.parametrize("case,box,lens,nev,kw", CASES, ids=[c[0] for c in CASES])
+def test_replay(tmp_path, case, box, lens, nev, kw):
+    from mulskips_b200 import Mskc
+    base = case.split("-zig")[0] if "-zig0" in case else case
+    start = make_start(base, str(tmp_path / "start.dat"), lens=lens, maxiter=10**9, outmolmol=10**9, maxtime=1e30, outtime=1e30, **kw)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    orc.set_trace(nev)
+    assert orc.run(nev) == nev
+    site, code, arm, tree1 = trace_arrays(orc)
+    assert len(code) == nev
+    done = 0
+    for chunk in (1, 9, 990, nev - 1000):
+        ctx.replay_events(site[done:done + chunk], code[done:done + chunk], arm[done:done + chunk], tree_root=1.0)
+        done += chunk
+    check_against_oracle(orc, ctx)
+    ctx.close(); orc.close()
+
+
+# the instantiation the sampler launches -- coop_event<8, FEAT>, four teams of a warp in lock step, FEAT = 0 for the
+# PVD cases (rates from the incremental census flags), F_COV for the CVD cases (full census + flag cross-check) -- on
+# 192 x 192 boxes, where consecutive trace events are often far enough apart to share a lock-step iteration
+TEAM_CASES = [
+    ("Si-SL", (192, 192, 240), (216, 0, 0), 120000, {}),
+    ("surface", (192, 192, 240), (48, 0, 0), 300000, {}),
+    ("surface-zig0.5", (192, 192, 240), (48, 0, 0), 300000, dict(ptranszig=0.5, runtype="R")),
+    ("cube-zigzag", (192, 192, 144), (48, 48, 48), 200000, {}),
+    ("CVD-Si-SiH2", (192, 192, 96), (48, 0, 0), 300000, {}),
+    ("SiGeBdoped", (192, 192, 240), (48, 0, 0), 200000, {}),
+]
+
+
+@pytest.mark.parametrize("case,box,lens,nev,kw", TEAM_CASES, ids=[c[0] for c in TEAM_CASES])
+def test_replay_teams(tmp_path, case, box, lens, nev, kw):
+    from mulskips_b200 import Mskc
+    base = case.split("-zig")[0] if "-zig0" in case else case
+    start = make_start(base, str(tmp_path / "start.dat"), lens=lens, maxiter=10**9, outmolmol=10**9, maxtime=1e30, outtime=1e30, **kw)
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    ctx = Mskc(*box, lc, lv)
+    upload_oracle_state(orc, ctx)
+    orc.set_trace(nev)
+    assert orc.run(nev) == nev
+    site, code, arm, tree1 = trace_arrays(orc)
+    done, iters, shared = 0, 0, 0
+    for chunk in (1, 7, 992, nev - 1000):
+        a, b = ctx.replay_teams(site[done:done + chunk], code[done:done + chunk], arm[done:done + chunk], tree_root=1.0)
+        iters += a; shared += b
+        done += chunk
+    assert iters < nev and shared > nev // 50, (iters, shared)        # teams really ran side by side
+    check_against_oracle(orc, ctx)
     ctx.close(); orc.close()
 
 
