@@ -52,7 +52,7 @@ module mskc_bind
     integer(c_int32_t) :: launches
     real(c_float)      :: sweep_kernel_ms
     integer(c_int32_t) :: stop_reason
-    integer(c_int32_t) :: sampler_launches, pad
+    integer(c_int32_t) :: sampler_launches, max_tile_events
   end type
 
   type, bind(C) :: mskc_counters

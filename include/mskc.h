@@ -168,9 +168,9 @@ typedef struct {
   float   kernel_ms;         /* device time of this call (CUDA events on the library's stream)      */
   int32_t launches;          /* kernels launched by this call                                       */
   float   sweep_kernel_ms;   /* part of kernel_ms spent in the sampler kernels (colour steps / sweep batches) */
-  int32_t stop_reason;
+  int32_t stop_reason;       /* MSKC_STOP_BUDGET (the sweeps asked for were run) or MSKC_STOP_FEWMC (main.f:307-310) */
   int32_t sampler_launches;  /* how many sampler kernels those were (short calls time each one)     */
-  int32_t pad;
+  int32_t max_tile_events;   /* diagnostic: most events one tile executed in one colour step        */
 } mskc_parallel_result;
 
 /* Synchronous-sublattice sampler: x-y tiles coloured 2x2, every tile of one colour runs its own

@@ -255,6 +255,7 @@ extern "C" int mskc_set_rates(mskc_ctx *h, const double *PtransE, const double *
     h->D.PDepAbs[coor] = PDep + PAbs;
   }
   h->D.PDepAbs[0] = 0.0;
+  for (int i = 0; i < 9; i++) h->D.cPD[i] = h->h_PD[i];
   h->have_rates = true;
   return 0;
 }

@@ -62,6 +62,14 @@ __device__ __forceinline__ int cdy(unsigned f) { return (int)((f >> 5) & 31u) - 
 __device__ __forceinline__ int cdz(unsigned f) { return (int)((f >> 10) & 31u) - 16; }
 
 __device__ __noinline__ unsigned enc_bond_cold(P3 s, P3 n) { return enc_bond(s, n); }
+// bond code of `to` seen from `from` (minimum image), 0x10000 (matches no stored field) when it is out of the code's range
+__device__ __noinline__ unsigned code_or_none(P3 from, P3 to) {
+  int dx = to.x - from.x, dy = to.y - from.y, dz = to.z - from.z;
+  if (dx > D.LX / 2) dx -= D.LX; else if (dx < -(D.LX / 2)) dx += D.LX;
+  if (dy > D.LY / 2) dy -= D.LY; else if (dy < -(D.LY / 2)) dy += D.LY;
+  if (dx < -15 || dx > 15 || dy < -15 || dy > 15 || dz < -15 || dz > 15) return 0x10000u;
+  return (unsigned)(dx + 16) | ((unsigned)(dy + 16) << 5) | ((unsigned)(dz + 16) << 10);
+}
 __device__ __noinline__ void fail_cell(int code, uint32_t c) { P3 p = cell_xyz((long long)c); fail(code, p.x, p.y, p.z); }
 // cell index of a site whose x,y are already wrapped (dec_bond output): only z can leave the box
 __device__ __forceinline__ uint32_t ccell(P3 p) {
@@ -108,16 +116,12 @@ __device__ __forceinline__ unsigned census_flags(const P3 Q, const uint32_t wQ, 
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const unsigned f = fld(bQ, i);
-    if (f == 0u) continue;
-    const int z = Q.z + cdz(f);
-    if ((unsigned)z > (unsigned)D.LZ) continue;          // bond leaving the box (bottom layer of a slab without walls)
-    P3 n; const uint32_t c = nbr(Q, f, n);
+    if (f != 0u && (unsigned)(Q.z + cdz(f)) > (unsigned)D.LZ) continue;   // bond leaving the box (bottom layer of a slab without walls)
+    P3 n; const uint32_t c = nbr(Q, f, n);               // f == 0: the absolute origin, like the reference's NextNXYZ = 0
     const uint32_t w = D.state[c];
     if (!w_occ(w)) continue;
     if (w_cov(w) == 113) { if (w_occ(wQ)) fl |= 1u << (2 * i); continue; }
-    bool rec = lists_code(D.bonds[c], (unsigned)NEGC - f);
-    if ((Q.x | Q.y | Q.z) == 0) rec |= lists_code(D.bonds[c], 0u);
-    if (rec) fl |= (unsigned)(w_sp(w) & 3) << (2 * i);
+    if (recip_f(n, D.bonds[c], Q, f)) fl |= (unsigned)(w_sp(w) & 3) << (2 * i);
   }
   return fl;
 }
@@ -237,21 +241,35 @@ struct CoopCounters {                // per-lane partial sums, reduced over the 
 // predicated stretches between two convergence points, so the memory round trips of the teams overlap.
 // Itrans: 1..3 deposit species, 4 evaporate, 5 desorb, 6.. adsorb (main.f:335-357).
 // arm_u: uniform used when IF_Arm_Choice.f ties; forced_arm >= 0 overrides the choice (trace replay).
+// the species / adsorbate of a deposition event, drawn when it fires (Get_Prob.f:160-179 pre-draws it; same distribution):
+// plain tables come from the constant bank, per-kelvin tables take the general routine
+template <int FEAT>
+__device__ __forceinline__ int draw_dep_abs(int Coor, uint32_t wS, uint32_t cS, double u) {
+  if ((FEAT & F_LA) && D.la) return choose_dep_abs(Coor, site_T(wS, cell_xyz((long long)cS)), u, nullptr);
+  const int c = Coor < 1 ? 1 : (Coor > 3 ? 3 : Coor);
+  const double PD1 = D.cPD[3 * (c - 1)], PD2 = D.cPD[3 * (c - 1) + 1], PD3 = D.cPD[3 * (c - 1) + 2];
+  const double PDep = PD1 + PD2 + PD3;
+  const double Pcurr = u * D.PDepAbs[c];
+  if (!(FEAT & F_COV) || Pcurr <= PDep) return Pcurr <= PD1 ? 1 : (Pcurr > (PD1 + PD2) ? 3 : 2);
+  return index_event_abs(c, Pcurr, PDep, 0);
+}
+
 template <int TEAM, int FEAT, class Lists>
-__device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, const P3 S, const uint32_t cS, const int Itrans, const double root,
-                                           const double arm_u, const int forced_arm, CoopCounters &K) {
+__device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const P3 S, const uint32_t cS, int Itrans, const double root,
+                                          const double arm_u, const int forced_arm, CoopCounters &K, const double species_u = 0.5) {
   enum { DEP = 0, EVAP = 1, DES = 2, ABS = 3 };
   constexpr unsigned FULL = 0xFFFFFFFFu;
   constexpr unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
-  const int kind = Itrans <= 3 ? DEP : (Itrans == 4 ? EVAP : (Itrans == 5 ? DES : ABS));
   const int tshift = (int)(threadIdx.x & 31u) - tl;         // first lane of the team inside the warp
-  if (!(FEAT & F_COV) && go && kind >= DES) { fail_cell(E_BADEV, cS); go = false; }
-  if ((FEAT & F_COV) && go && kind == ABS && Itrans - 5 > 3) { fail_cell(E_BADEV, cS); go = false; }
-  if (go && kind == DEP && Itrans < 1) { fail_cell(E_BADEV, cS); go = false; }
   // ---- S's record (team-uniform: the lanes of a team load the same three words) ------------------------------
   uint32_t wS = 0u, aS = 0u; unsigned long long bS = 0ull;
   if (go) { wS = D.state[cS]; bS = D.bonds[cS]; aS = D.aux[cS]; }
   const int c0 = w_coor(wS);
+  if (Itrans == EV_DRAW) Itrans = go ? draw_dep_abs<FEAT>(c0, wS, cS, species_u) : 4;
+  const int kind = Itrans <= 3 ? DEP : (Itrans == 4 ? EVAP : (Itrans == 5 ? DES : ABS));
+  if (!(FEAT & F_COV) && go && kind >= DES) { fail_cell(E_BADEV, cS); go = false; }
+  if ((FEAT & F_COV) && go && kind == ABS && Itrans - 5 > 3) { fail_cell(E_BADEV, cS); go = false; }
+  if (go && kind == DEP && Itrans < 1) { fail_cell(E_BADEV, cS); go = false; }
   int CovNew = 0;
   {                                                        // S's word: occupancy / species / coverage (coordination follows at the end)
     int dsp = -1, dcv = -1, sgn = 1;
@@ -262,8 +280,8 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
       else { const int k = (Itrans - 5) & 3; CovNew = D.ListCov[k ? k - 1 : 0]; dcv = k - 1; wS = (wS & ~255u) | (uint32_t)CovNew; }
     }
     if (go && tl == 4) {
-      if (dsp >= 0 && dsp < 3) K.dCrystal[dsp] += sgn;
-      if (dcv >= 0 && dcv < 3) K.dCov[dcv] += sgn;
+      K.dCrystal[0] += dsp == 0 ? sgn : 0; K.dCrystal[1] += dsp == 1 ? sgn : 0; K.dCrystal[2] += dsp == 2 ? sgn : 0;
+      if (FEAT & F_COV) { K.dCov[0] += dcv == 0 ? sgn : 0; K.dCov[1] += dcv == 1 ? sgn : 0; K.dCov[2] += dcv == 2 ? sgn : 0; }
       if (FEAT & F_COV) D.state[cS] = wS;                  // the census of a neighbour looks back at S (coverage runs only)
     }
   }
@@ -331,8 +349,10 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
     const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN);
     const bool rec = recip_f(N, bN, S, f);
     const bool wall = Occ && CovN == 113;
-    const unsigned fb = (unsigned)NEGC - f;                // the bond N -> S
-    const int jS = find_code(bN, fb);                      // where N lists S (its census flag for S lives there)
+    // the bond N -> S, and where N lists S (its census flag for S lives there).  Bonds to / from the absolute origin are
+    // stored as 0 like the reference's NextNXYZ = 0, hence the two special cases
+    const unsigned fb = f ? (unsigned)NEGC - f : code_or_none(N, S);
+    const int jS = find_code(bN, (S.x | S.y | S.z) ? fb : 0u);
     unsigned flN = aux_flags(aN);
     qN = N; qc = cN; qCov = CovN; qOcc = Occ; qSp = Occ ? w_sp(wN) : 0; qaux = aN; qfl0 = flN; wN0 = wN;
     int newCoor = -1; uint32_t wNew = wN;
@@ -345,7 +365,8 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
         if (rec) sflag = (unsigned)(w_sp(wN) & 3);
         if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && tl >= 1); if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }
       } else if (CoorNN == 0) {                            // :88-99 a new active empty site with one fixed bond
-        bN = f ? (unsigned long long)fb : (unsigned long long)enc_bond_cold(N, S);
+        if (fb > 0xFFFFu) fail(E_FARBOND, S.x, S.y, S.z);
+        bN = (unsigned long long)(fb & 0xFFFFu);
         rbN = bN;
         newCoor = 1; act = A_NEW; flN = (unsigned)Itrans; nb1 = c0;   // rated against S's OLD coordination (deposition.f:237-250 writes it last)
       } else if (CoorNN == 1) {                            // :100-160 second bond: complete the tetrahedron (two more cells, below)
@@ -370,7 +391,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
           int Ex = abs(M.x - S.x); Ex = min(Ex, D.LX - Ex);
           int Ey = abs(M.y - S.y); Ey = min(Ey, D.LY - Ey);
           const int ez = M.z - S.z;
-          if (Ex * Ex + Ey * Ey + ez * ez == 72) { unsigned fn[2]; slow_find_nn(S, N, f0, fn); xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = f ? fb : enc_bond_cold(N, S); }
+          if (Ex * Ex + Ey * Ey + ez * ez == 72) { unsigned fn[2]; slow_find_nn(S, N, f0, fn); xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb; }
         }
       } else if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETVOID; if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }   // :161-190
     } else if (kind == EVAP) {
@@ -487,6 +508,7 @@ __device__ __forceinline__ void coop_event(Lists &L, const int tl, bool go, cons
     if (act == A_ERASE || ev == 0) L.erase(qN, qc, aux_slot(qaux)); else L.put(qN, qc, ev, p, aux_slot(qaux));
   }
   __syncwarp();
+  return Itrans;
 }
 
 }  // namespace mskc

@@ -50,6 +50,7 @@ struct DevCtx {
   const double *PE, *PD, *PAbs, *PDes;   // Fortran-flattened tables (defsystem.f:60-65)
   double PZig;
   double PDepAbs[4];                // [coor]: sum of the deposition + adsorption rates of an empty site (Get_Prob.f:160-163), plain tables
+  double cPD[9];                    // PtransD(sp, coor) again, in the constant bank (species draw of the sampler)
   int NCrystal, NCov, ListCov[3], ListCrystal[3];
   // temperature-dependent rates: host-built tables per integer kelvin.  la = 1: the LA rate law (Get_Prob.f:143-148,
   // evaporation + deposition); la = 2: the 'ST' tabulated field (InterpProbFromField.f: all four tables, and the

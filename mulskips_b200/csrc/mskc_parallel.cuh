@@ -49,7 +49,7 @@ struct SweepState {          // one per context, device resident
 // colour are contiguous (l = colour*ntc + index).
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
-  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr; uint32_t *aux = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
+  double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr, *live = nullptr; uint32_t *aux = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
   TileStat *tstat = nullptr; SweepState *ss = nullptr; TileStat *tot = nullptr;
   // slab mode
   int halo = 0, rank = 0, nranks = 1;
@@ -69,7 +69,7 @@ struct ParallelCtx {
 
 struct TileView {            // what the kernels need (constant memory)
   int tile, ntx, nty, cap, NT, hx, ntc;
-  double *rate; unsigned long long *ce; int *cnt; double *tile_rate; TileStat *tstat; SweepState *ss;
+  double *rate; unsigned long long *ce; int *cnt, *live /* entries with rate > 0 as of the tile's last own step */; double *tile_rate; TileStat *tstat; SweepState *ss;
   double *lag;                          // [tile] KMC time a tile still owes because its colour step hit the event cap
   // x-decomposed slab (multi-GPU): one halo tile column on each side of the owned block, see "halo exchange" below
   int halo, nranks;
@@ -136,25 +136,28 @@ struct TileLists {
   int mark;                                  // slab mode: log changed cells of the shared strips
   double *s_rate; unsigned long long *s_ce; int *s_n;
   __device__ __forceinline__ int slot_of(uint32_t c) const { return aux_slot(D.aux[c]); }
-  // sl = the cell's current slot (slot_of(c)), read by the caller ahead of time
+  // sl = the cell's current slot (slot_of(c)), read by the caller ahead of time.  The entry lives in the shared-memory mirror
+  // when the cell belongs to the running tile, else in that tile's list in HBM (generic pointers: one store path).
   __device__ __forceinline__ void put(P3 s, uint32_t c, int ev, double p, int sl) {
     if (mark) mark_dirty(s, c);
     const int l = list_of(s);
     const bool mine = l == own;
     if (sl == 0) {
-      const int k = mine ? atomicAdd(s_n, 1) : atomicAdd(&V.cnt[l], 1);
-      if (k >= V.cap) { if (mine) atomicSub(s_n, 1); else atomicSub(&V.cnt[l], 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
+      int *cnt = mine ? s_n : &V.cnt[l];
+      const int k = atomicAdd(cnt, 1);
+      if (k >= V.cap) { atomicSub(cnt, 1); fail(E_TILE_FULL, s.x, s.y, s.z, l); return; }
       st_slot(c, k + 1); sl = k + 1;
     }
-    const unsigned long long e = pack_ce(c, ev, s.x, s.y, s.z);
-    if (mine) { s_rate[sl - 1] = p; s_ce[sl - 1] = e; }
-    else { const long long a = lidx(l, sl - 1); V.rate[a] = p; V.ce[a] = e; }
+    double *rp = mine ? s_rate + (sl - 1) : V.rate + lidx(l, sl - 1);
+    unsigned long long *cp = mine ? s_ce + (sl - 1) : V.ce + lidx(l, sl - 1);
+    *rp = p; *cp = pack_ce(c, ev, s.x, s.y, s.z);
   }
   __device__ __forceinline__ void erase(P3 s, uint32_t c, int sl) {  // tombstone (rate 0); the owner compacts
     if (mark) mark_dirty(s, c);
     if (!sl) return;
     const int l = list_of(s);
-    if (l == own) s_rate[sl - 1] = 0.0; else V.rate[lidx(l, sl - 1)] = 0.0;
+    double *rp = l == own ? s_rate + (sl - 1) : V.rate + lidx(l, sl - 1);
+    *rp = 0.0;
   }
 };
 
@@ -164,7 +167,7 @@ struct TileLists {
 #define MSKC_CS_MINB 4
 #endif
 #ifndef MSKC_COMPACT_ABOVE
-#define MSKC_COMPACT_ABOVE 96
+#define MSKC_COMPACT_ABOVE 64
 #endif
 enum { CS_THREADS = 128, CS_MINB = MSKC_CS_MINB };
 enum { CS_COMPACT_ABOVE = MSKC_COMPACT_ABOVE };
@@ -227,16 +230,18 @@ __device__ __forceinline__ void tile_load(const int l, const int tl, const int t
 }
 // One lock-step iteration: every lane of the warp calls this together; a team with active == false only takes part
 // in the synchronisation.  Returns whether the team executed an event (false for an active team: its step is over).
+// Selection (the n-fold way inside the tile): every lane sums a CONTIGUOUS chunk of the list mirror, a team-wide scan
+// of the eight partial sums finds the lane whose chunk holds the target, and that lane walks its chunk.
 template <int TEAM, int FEAT>
 __device__ __forceinline__ bool tile_iteration(TileRun &t, TileLists &L, const bool active, const int tl, const int tshift, const unsigned tm,
                                                const uint2 key, const double tau, const int event_cap, const double root) {
   constexpr unsigned FULL = 0xFFFFFFFFu;
   const double *s_rate = L.s_rate;
   const int n = active ? *L.s_n : 0;
-  // rate sum and inclusive prefix over the list (lane-strided chunks)
+  const int chunk = (n + TEAM - 1) / TEAM, i0 = tl * chunk, i1 = min(n, i0 + chunk);
   double part = 0.0;
 #pragma unroll 1
-  for (int i = tl; i < n; i += TEAM) part += s_rate[i];
+  for (int i = i0; i < i1; i++) part += s_rate[i];
   double incl = part;
 #pragma unroll
   for (int o = 1; o < TEAM; o <<= 1) { const double v = __shfl_up_sync(FULL, incl, o, TEAM); if (tl >= o) incl += v; }
@@ -255,52 +260,32 @@ __device__ __forceinline__ bool tile_iteration(TileRun &t, TileLists &L, const b
     if (t.tloc > t.budget) go = false;
   }
   const double target = ((double)(((unsigned long long)rnd.y << 20) | (rnd.z >> 12)) + 0.5) * (1.0 / 4503599627370496.0) * Rn;
-  // the lane whose strided chunk contains the target, then the team scans that chunk together
-  const unsigned m = (__ballot_sync(FULL, incl > target) >> tshift) & tm;
-  const int sel = m ? (__ffs(m) - 1) : TEAM - 1;
-  double acc = __shfl_sync(FULL, incl - part, sel, TEAM);        // rate mass before the chosen chunk
-  int pick = -1, last = -1;
-  bool searching = go;
-  for (int j0 = 0; __any_sync(FULL, searching); j0 += TEAM) {
-    const int i = sel + TEAM * (j0 + tl);
-    const double r = (searching && i < n) ? s_rate[i] : 0.0;
-    double in2 = r;
-#pragma unroll
-    for (int o = 1; o < TEAM; o <<= 1) { const double v = __shfl_up_sync(FULL, in2, o, TEAM); if (tl >= o) in2 += v; }
-    const unsigned hit = (__ballot_sync(FULL, r > 0.0 && acc + in2 > target) >> tshift) & tm;
-    const unsigned livem = (__ballot_sync(FULL, r > 0.0) >> tshift) & tm;
-    acc += __shfl_sync(FULL, in2, TEAM - 1, TEAM);
-    if (searching) {
-      if (livem) last = sel + TEAM * (j0 + 31 - __clz((int)livem));
-      if (hit) { pick = sel + TEAM * (j0 + __ffs(hit) - 1); searching = false; }
-      else if (sel + TEAM * (j0 + TEAM) >= n) { pick = last; searching = false; }
-    }
-  }
-  // rounding left the chosen chunk without a live entry: take the first live one of the list
-  const bool lost = go && pick < 0;
-  if (__any_sync(FULL, lost)) {
-    int mine = -1;
-    if (lost) {
+  // the lane whose chunk contains the target (rounding: the last lane with rate mass), then that lane walks its chunk
+  const unsigned hitm = (__ballot_sync(FULL, part > 0.0 && incl > target) >> tshift) & tm;
+  const unsigned massm = (__ballot_sync(FULL, part > 0.0) >> tshift) & tm;
+  const int sel = hitm ? (__ffs(hitm) - 1) : (massm ? 31 - __clz((int)massm) : 0);
+  int pick = -1;
+  if (go && tl == sel) {
+    double acc = incl - part;
 #pragma unroll 1
-      for (int i = tl; i < n; i += TEAM) if (s_rate[i] > 0.0) { mine = i; break; }
+    for (int i = i0; i < i1; i++) {
+      const double r = s_rate[i];
+      if (r > 0.0) { pick = i; acc += r; if (acc > target) break; }
     }
-    const unsigned mm = (__ballot_sync(FULL, mine >= 0) >> tshift) & tm;
-    const int first = __shfl_sync(FULL, mine, mm ? __ffs(mm) - 1 : 0, TEAM);
-    if (lost) { if (mm) pick = first; else go = false; }
   }
+  pick = __shfl_sync(FULL, pick, sel, TEAM);
+  if (go && pick < 0) go = false;                        // (cannot happen while Rn > 0)
   unsigned long long e = 0ull;
   if (go) e = L.s_ce[pick];
-  const uint32_t cell = (uint32_t)e; int Itrans = ce_event(e);
+  const uint32_t cell = (uint32_t)e;
   P3 Site; Site.x = t.x0 + (int)((e >> 40) & 31u); Site.y = t.y0 + (int)((e >> 45) & 31u); Site.z = (int)(e >> 50);
-  if (go && Itrans == EV_DRAW) {   // species / adsorbate drawn now (Get_Prob.f:164-179)
-    const uint32_t w = D.state[cell];
-    const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);
-    Itrans = choose_dep_abs(w_coor(w), (FEAT & F_LA) ? site_T(w, Site) : 0, us, nullptr);
-  }
+  const double us = ((double)(((rnd.z & 0xFFFu) << 12) | (rnd.w >> 20)) + 0.5) * (1.0 / 16777216.0);   // species / adsorbate (Get_Prob.f:164-179)
   const double arm_u = ((double)(rnd.w & 0xFFFFFu) + 0.5) * (1.0 / 1048576.0);
-  if (go) { if (Itrans == 1) t.ndep0++; else if (Itrans == 2) t.ndep1++; else if (Itrans == 3) t.ndep2++; else if (Itrans == 4) t.nevap++; else if (Itrans == 5) t.ndes++; else t.nabs++; }
-  coop_event<TEAM, FEAT>(L, tl, go, Site, cell, Itrans, root, arm_u, -1, t.K);
-  if (go) t.nev++;
+  const int Itrans = coop_event<TEAM, FEAT>(L, tl, go, Site, cell, go ? ce_event(e) : 4, root, arm_u, -1, t.K, us);
+  if (go) {
+    t.ndep0 += Itrans == 1; t.ndep1 += Itrans == 2; t.ndep2 += Itrans == 3; t.nevap += Itrans == 4; t.ndes += Itrans == 5; t.nabs += Itrans > 5;
+    t.nev++;
+  }
   return go;
 }
 // End of a tile's step: every lane of the warp calls this together, the teams with fin == true write their list back
@@ -314,12 +299,16 @@ __device__ __forceinline__ void tile_finish(TileRun &t, const TileLists &L, cons
   for (int k = 0; k < 9; k++)
 #pragma unroll
     for (int o = TEAM / 2; o > 0; o >>= 1) v[k] += __shfl_xor_sync(FULL, v[k], o, TEAM);
+  const unsigned fin_mask = __ballot_sync(FULL, fin);
   if (!fin) return;
   const int l = t.l, n = *L.s_n;
+  int live = 0;
 #pragma unroll 1
-  for (int i = tl; i < n; i += TEAM) { V.rate[lidx(l, i)] = L.s_rate[i]; V.ce[lidx(l, i)] = L.s_ce[i]; }
+  for (int i = tl; i < n; i += TEAM) { const double r = L.s_rate[i]; live += r > 0.0; V.rate[lidx(l, i)] = r; V.ce[lidx(l, i)] = L.s_ce[i]; }
+#pragma unroll
+  for (int o = TEAM / 2; o > 0; o >>= 1) live += __shfl_xor_sync(fin_mask, live, o, TEAM);
   if (tl == 0) {
-    V.cnt[l] = n;
+    V.cnt[l] = n; V.live[l] = live;
     V.tile_rate[l] = t.R;
     V.lag[l] = t.capped ? t.debt + t.tau - t.tloc : t.debt - fmin(t.debt, t.tau);
     TileStat &st = V.tstat[l];
@@ -433,6 +422,33 @@ __global__ void __launch_bounds__(128) compact_lists_kernel(int ntiles) {
   if (lane == 0) V.cnt[l] = n;
 }
 
+// Slab mode: the two halo tile columns mirror the neighbours' border tiles.  They never run here, so tile_load never
+// drops their tombstones; one warp per halo tile does it once per sweep (lists of idle tiles, nothing else touches them
+// between two kernels of the stream).
+__global__ void __launch_bounds__(128) compact_halo_kernel() {
+  const int lane = threadIdx.x & 31, w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= 2 * V.nty) return;
+  const int tx = w < V.nty ? 0 : V.ntx - 1, ty = w % V.nty;
+  const int l = (((ty & 1) << 1) | (tx & 1)) * V.ntc + (ty >> 1) * V.hx + (tx >> 1);
+  const int n0 = V.cnt[l];
+  if (n0 <= CS_COMPACT_ABOVE / 2) return;
+  int n = 0;
+  for (int base = 0; base < n0; base += 32) {
+    const int i = base + lane;
+    double r = 0.0; unsigned long long e = 0ull;
+    if (i < n0) { r = V.rate[lidx(l, i)]; e = V.ce[lidx(l, i)]; }
+    const bool live = (i < n0) && (r > 0.0);
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, live);
+    const int k = n + __popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (live) { V.rate[lidx(l, k)] = r; V.ce[lidx(l, k)] = e; if (k != i) st_slot((uint32_t)e, k + 1); }
+    else if (i < n0) st_slot((uint32_t)e, 0);
+    n += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) V.cnt[l] = n;
+}
+
 // Trace replay (test/diagnostic entry point): ONE warp applies a given event sequence -- site, event code
 // and the IF_Arm_Choice outcome of every event, as the CPU oracle traced them -- through the same
 // cooperative transition code the sampler uses.  Lists are updated in HBM only.
@@ -509,7 +525,7 @@ __device__ __forceinline__ bool halo_list(int l) {        // is tile-list l one 
 __global__ void __launch_bounds__(1024) sweep_sum_kernel(int ntiles) {
   __shared__ double sR[32]; __shared__ long long sN[32]; __shared__ int sM[32];
   double r = 0.0; long long n = 0; int mx = 0;
-  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { if (halo_list(t)) continue; r += V.tile_rate[t]; int c = V.cnt[t]; n += c; mx = max(mx, c); }
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { if (halo_list(t)) continue; r += V.tile_rate[t]; n += V.live[t]; mx = max(mx, V.cnt[t]); }
   for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); }
   if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; }
   __syncthreads();
@@ -534,9 +550,9 @@ __global__ void reset_maxev_kernel(TileStat *ts, int n) { int i = blockIdx.x * b
 __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= ntiles) return;
-  int n = V.cnt[l]; double r = 0;
-  if (!halo_list(l)) for (int i = 0; i < n; i++) r += V.rate[lidx(l, i)];
-  V.tile_rate[l] = r;
+  int n = V.cnt[l], live = 0; double r = 0;
+  if (!halo_list(l)) for (int i = 0; i < n; i++) { const double v = V.rate[lidx(l, i)]; r += v; live += v > 0.0; }
+  V.tile_rate[l] = r; V.live[l] = live;
 }
 
 __global__ void __launch_bounds__(256) reduce_tstat_kernel(const TileStat *ts, int ntiles, TileStat *out) {
@@ -659,16 +675,18 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
       if (V.halo) { const int x = (int)((4 * q + k) % D.LX); if (x < TILE || x >= D.LX - TILE) continue; }      // halo columns belong to the neighbours
       int cov = w_cov(w);
       if (cov == 113) { nWall++; continue; }
+      // plane ranges as the reference scans them: census 1 (atoms with coordination <= 3, coverage sites) over planes
+      // 1..LenZ-1 (WriteMolMolXYZFile.f:77-92), census 2 (non-epitaxial bulk) over planes 0..LenZ-1 (:95-119)
+      const long long c = 4 * q + k; const int z = (int)(c / plane);
       if (w_occ(w)) {
         nOcc++;
-        long long c = 4 * q + k; int z = (int)(c / plane);
-        if (w_coor(w) <= 3) { nUnder++; hz += z; hz2 += (double)z * z; }
+        if (w_coor(w) <= 3) { if (z >= 1 && z <= D.LZ - 1) { nUnder++; hz += z; hz2 += (double)z * z; } }
         else if (w_coor(w) == 4) {
           nBulk++;
           int r = (int)(c - (long long)z * plane), y = r / D.LX, x = r - y * D.LX, kind;
-          if (!is_cubic_site(x, y, z, kind)) nNoEpi++;
+          if (z <= D.LZ - 1 && !is_cubic_site(x, y, z, kind)) nNoEpi++;
         }
-      } else if (cov != 0) nCov++;
+      } else if (cov != 0 && z >= 1 && z <= D.LZ - 1) nCov++;
     }
   }
   unsigned long long vals[6] = {nUnder, nCov, nNoEpi, nBulk, nOcc, nWall};
@@ -804,13 +822,13 @@ static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
   cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.pack_done); cudaFree(P.red);
   for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
-  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.aux); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
+  cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.live); cudaFree(P.aux); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
   P.halo = halo; P.rank = rank; P.nranks = nranks; P.comm = comm;
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
-  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt;
+  V.rate = P.rate; V.ce = P.ce; V.cnt = P.cnt; V.live = P.live;
   V.tile_rate = P.tile_rate; V.tstat = P.tstat; V.ss = P.ss; V.lag = P.lag;
   V.halo = P.halo; V.nranks = P.nranks; V.dirty_bits = P.dirty_bits; V.dirty_cell = P.dirty_cell; V.dirty_n = P.dirty_n; V.dirty_cap = P.dirty_cap; V.red = P.red;
   return V;
@@ -820,6 +838,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   if (H.LX % (2 * tile) || H.LY % (2 * tile)) { if (err) *err = "parallel sampler needs LenX and LenY to be multiples of 48 (24-unit tiles, 2x2 colouring)"; return -1; }
   if (P.rate && P.cap == cap && P.ncell == H.ncell) {
     PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
+    PCK(cudaMemsetAsync(P.live, 0, (size_t)P.ntiles * sizeof(int), st));
     PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
     PCK(cudaMemsetAsync(P.aux, 0, (size_t)H.ncell * sizeof(uint32_t), st));
     PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
@@ -834,6 +853,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMalloc(&P.rate, (size_t)P.ntiles * cap * sizeof(double)));
   PCK(cudaMalloc(&P.ce, (size_t)P.ntiles * cap * sizeof(unsigned long long)));
   PCK(cudaMalloc(&P.cnt, (size_t)P.ntiles * sizeof(int)));
+  PCK(cudaMalloc(&P.live, (size_t)P.ntiles * sizeof(int)));
   PCK(cudaMalloc(&P.aux, (size_t)H.ncell * sizeof(uint32_t)));
   PCK(cudaMalloc(&P.tile_rate, (size_t)P.ntiles * sizeof(double)));
   PCK(cudaMalloc(&P.lag, (size_t)P.ntiles * sizeof(double)));
@@ -858,6 +878,7 @@ static inline int parallel_alloc(ParallelCtx &P, const DevCtx &H, cudaStream_t s
   PCK(cudaMemsetAsync(P.rate, 0, (size_t)P.ntiles * cap * sizeof(double), st));
   PCK(cudaMemsetAsync(P.ce, 0, (size_t)P.ntiles * cap * sizeof(unsigned long long), st));
   PCK(cudaMemsetAsync(P.cnt, 0, (size_t)P.ntiles * sizeof(int), st));
+    PCK(cudaMemsetAsync(P.live, 0, (size_t)P.ntiles * sizeof(int), st));
   PCK(cudaMemsetAsync(P.aux, 0, (size_t)H.ncell * sizeof(uint32_t), st));
   PCK(cudaMemsetAsync(P.tstat, 0, (size_t)P.ntiles * sizeof(TileStat), st));
   PCK(cudaMemsetAsync(P.tile_rate, 0, (size_t)P.ntiles * sizeof(double), st));
@@ -1030,6 +1051,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
       launches += 2; n_sampler_launches++;
       if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
     }
+    if (P.halo) { MSKC_LAUNCH(compact_halo_kernel, (2 * P.nty * 32 + 127) / 128, 128, 0, st); launches++; }
     if (sweep_totals(P, st, ept, a->tau_fixed, 1, &launches, err)) return -1;
   }
   MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
@@ -1051,7 +1073,8 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   r->sweeps_done = a->n_sweeps; r->time = P.h_ss.time; r->total_rate = P.h_ss.total_rate; r->n_active = P.h_ss.n_active;
   for (int i = 0; i < 3; i++) r->count_dep[i] = P.h_tot.dep[i] - before.dep[i];
   r->count_evap = P.h_tot.evap - before.evap; r->count_abs = P.h_tot.abs_ - before.abs_; r->count_des = P.h_tot.des - before.des;
-  r->launches = launches; r->stop_reason = P.h_tot.maxev;   /* diagnostic: max events of one tile in one colour step */
+  r->launches = launches; r->max_tile_events = P.h_tot.maxev;
+  r->stop_reason = r->n_active <= 20 ? MSKC_STOP_FEWMC : MSKC_STOP_BUDGET;      // main.f:307-310 on the live active-site count
   r->sampler_launches = n_sampler_launches;
   P.time = P.h_ss.time;
   return 0;

@@ -19,5 +19,5 @@ for i, m in enumerate(a.modes):
     os.environ["MSKC_EVCAP"] = m
     r = ctx.run_parallel(a.sweeps, events_per_tile=a.ept, seed=2 + i)
     print(f"evcap={m}: {r.events_done} ev, {r.kernel_ms:.2f} ms total, sampler kernels {r.sweep_kernel_ms:.2f} ms in {r.sampler_launches} launches, {r.events_done / r.kernel_ms * 1e3:.4g} ev/s, "
-          f"active={r.n_active} maxev={r.stop_reason} ev/tile/step={r.events_done / (a.sweeps * 4 * (a.box[0] // 48) * (a.box[1] // 48)):.2f} t={r.time:.5g}", flush=True)
+          f"active={r.n_active} maxev={r.max_tile_events} ev/tile/step={r.events_done / (a.sweeps * 4 * (a.box[0] // 48) * (a.box[1] // 48)):.2f} t={r.time:.5g}", flush=True)
 ctx.close()

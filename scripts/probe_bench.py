@@ -23,7 +23,7 @@ for ept in a.ept:
     ctx.run_parallel(a.warm, events_per_tile=ept, seed=1)
     r = ctx.run_parallel(a.sweeps, events_per_tile=ept, seed=2)
     print(f"TEAM={os.environ.get('MSKC_TEAM','def')} ept={ept}: {r.events_done} ev, {r.kernel_ms:.2f} ms, {r.events_done / r.kernel_ms * 1e3:.4g} ev/s, su/ev={r.site_updates / max(r.events_done,1):.2f} "
-          f"active={r.n_active} maxev={r.stop_reason} us/colourstep={r.sweep_kernel_ms * 1e3 / (4 * a.sweeps):.1f} ev/tile/step={r.events_done / (a.sweeps * 4 * (a.box[0] // 48) * (a.box[1] // 48)):.2f}", flush=True)
+          f"active={r.n_active} maxev={r.max_tile_events} us/colourstep={r.sweep_kernel_ms * 1e3 / (4 * a.sweeps):.1f} ev/tile/step={r.events_done / (a.sweeps * 4 * (a.box[0] // 48) * (a.box[1] // 48)):.2f}", flush=True)
 if a.tiles:
     ts = ctx.tile_stats()
     print("per-tile events percentiles (50,90,99,99.9,100):", np.percentile(ts["events"], [50, 90, 99, 99.9, 100]), "maxev", ts["maxev"].max(), "maxev pct", np.percentile(ts["maxev"], [50, 90, 99, 100]))

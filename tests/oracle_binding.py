@@ -40,6 +40,7 @@ def load_oracle():
     lib.orc_run.argtypes = [vp, C.c_int64]
     lib.orc_run.restype = C.c_int64
     lib.orc_finish.argtypes = [vp]
+    lib.orc_write_frame.argtypes = [vp, C.c_double, C.c_int64, C.c_int64]
     lib.orc_state_hash.argtypes = [vp]
     lib.orc_state_hash.restype = C.c_uint64
     lib.orc_lattcoo.argtypes = [vp]
@@ -119,6 +120,12 @@ class Oracle:
 
     def finish(self):
         self.lib.orc_finish(self.o)
+
+    def write_frame(self, iout):
+        """one frame through the oracle's WriteMolMolSource / WriteMolMolXYZFile (into outdir when write_files is set)"""
+        s = self.sizes()
+        if self.lib.orc_write_frame(self.o, C.c_double(self.time), C.c_int64(s["Iter"]), C.c_int64(iout)) != 0:
+            raise RuntimeError("oracle frame: " + self.lib.orc_errmsg(self.o).decode())
 
     def sizes(self):
         a = (C.c_int64 * 8)()
@@ -232,8 +239,9 @@ def trace_arrays(orc: Oracle):
     return a["site"].copy(), a["itrans"].copy(), a["arm"].copy(), a["tree1"].copy()
 
 
-def upload_oracle_state(orc: Oracle, ctx):
-    """Hand the oracle's current state to a CUDA context: the tests' way of giving both sides the same input."""
+def upload_oracle_state(orc: Oracle, ctx, trange=None):
+    """Hand the oracle's current state to a CUDA context: the tests' way of giving both sides the same input.
+    trange = (tmin, tmax): temperature range of the per-kelvin LA tables (default: the range found in the lattice)."""
     t = orc.tables()
     L = orc.lattcoo()
     rp = orc.run_params()
@@ -255,7 +263,8 @@ def upload_oracle_state(orc: Oracle, ctx):
     elif rp["InitSt"] == "LA":
         T = (L[:-1] >> 9) & 8191
         tv = T[T > 0]
-        ctx.set_la(t["Tm"], t["P0"], t["sigma"], t["Tflex"], int(tv.min()), int(tv.max()))
+        lo, hi = trange if trange else (int(tv.min()), int(tv.max()))
+        ctx.set_la(t["Tm"], t["P0"], t["sigma"], t["Tflex"], lo, hi)
     d = orc.lists()
     st, counter, idum = orc.rng()
     ctx.seed(idum, rp["RunType"][0], counter, st)

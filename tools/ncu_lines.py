@@ -55,6 +55,9 @@ def text(l):
     p = os.path.join(os.path.dirname(os.path.abspath(lib)), "..", "csrc", f)
     if f not in src: src[f] = open(p).read().split("\n") if os.path.exists(p) else []
     return src[f][n - 1].strip()[:100] if 0 < n <= len(src[f]) else ""
+print("top lines by executed instructions:")
+for l, e in ex.most_common(topn):
+    print(f"  {100 * e / tot_ex:5.1f}% ex {100 * st[l] / max(tot_st, 1):5.1f}% smp  {l}  {text(l)}")
 print("top lines by stall samples:")
 for l, s in st.most_common(topn):
     top = ",".join(f"{k[6:]}:{v}" for k, v in stall_kind[l].most_common(3))
