@@ -32,6 +32,7 @@ struct mskc_ctx {
   int32_t *d_stage = nullptr;
   uint32_t *d_frame_cell = nullptr, *d_frame_word = nullptr; unsigned long long *d_frame_n = nullptr; int64_t frame_cap = 0;
   unsigned short *d_arm_tab = nullptr;
+  uint32_t *d_pa_tab = nullptr;
   // parity mode
   int NumMcMax = 500000, NumVdMax = 100000, Levels = 20;
   double *d_Tree = nullptr; uint32_t *d_lattind = nullptr, *d_mc_cell = nullptr, *d_void_cell = nullptr; int *d_mc_ev = nullptr;
@@ -175,6 +176,16 @@ extern "C" int mskc_create(int lenx, int leny, int lenz, int ncrystal, int ncov,
     CK(cudaStreamSynchronize(h->stream));
     D.arm_tab = h->d_arm_tab;
   }
+  // the neighbour-update rules of the four events as a table (mskc_coop.cuh: pa_rule)
+  {
+    std::vector<uint32_t> tab(PA_ENTRIES, 0u);
+    for (int kind = 0; kind < 4; kind++) for (int occ = 0; occ < 2; occ++) for (int wall = 0; wall < 2; wall++) for (int rec = 0; rec < 2; rec++) for (int c = 0; c <= 5; c++)
+      tab[pa_index(kind, occ, wall, rec, c)] = pa_rule(kind, occ, wall && occ, rec, c);
+    CK(cudaMalloc(&h->d_pa_tab, tab.size() * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(h->d_pa_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    D.pa_tab = h->d_pa_tab;
+  }
   // FIND_NN.f on the ideal bond shell: integer form -(b1+b2)/2 -+ (b1 x b2)/6 against the reference's double-precision
   // rotation (same IEEE sequence as the device routine) for every tetrahedral pair of the 32 |b|^2 = 27 vectors
   {
@@ -224,7 +235,7 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->D.state); cudaFree(h->D.bonds);
   cudaFree(h->d_PE); cudaFree(h->d_PD); cudaFree(h->d_PAbs); cudaFree(h->d_PDes);
-  cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
+  cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_pa_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S); cudaFree(h->d_la3_F); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
   if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }

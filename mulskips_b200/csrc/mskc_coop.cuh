@@ -230,6 +230,60 @@ __device__ __noinline__ void slow_find_nn(P3 S, P3 N, unsigned f0, unsigned fn[2
   fn[0] = enc_bond_cold(N, NewSite[0]); fn[1] = enc_bond_cold(N, NewSite[1]);
 }
 
+// ---- what an event does to ONE neighbour N of its site S: the rules of deposition.f:78-235, Evaporation.f:51-215,
+// absorption.f:43-72 and desorption.f:54-111 as a table over (event kind, N occupied, N wall, N lists S, coordination of N).
+// Entry layout:
+enum {
+  PA_ACT = 15,        // bits 0-3: request + 1 (A_NEW ... of mskc_device.cuh), 0 = N is not re-rated
+  PA_COOR = 4,        // bits 4-5: coordination of N: 0 unchanged, 1 +1, 2 -1, 3 := 1
+  PA_SAME = 1 << 6,   // re-rate at the unchanged coordination (absorption / desorption)
+  PA_SUP = 1 << 7,    // N raises S's coordination (a wall next to a deposited atom, deposition.f:231-232)
+  PA_SUPFIX = 1 << 8, // ... only when S has just fixed this bond (S was 1-coordinated, bonds 2..4, deposition.f:218-220)
+  PA_SDOWN = 1 << 9,  // N lowers S's coordination (a wall next to an evaporated atom, Evaporation.f:211-213)
+  PA_KEEP = 1 << 10,  // N may be the one neighbour S keeps (Evaporation.f:229-258)
+  PA_SFLAG = 11,      // bits 11-12: N in S's census afterwards: 0 not counted, 1 as a wall, 2 with its species
+  PA_FLAG = 13,       // bits 13-15: N's census flags: 0 unchanged, 1 the flag for S := deposited species, 2 the flag for S := 0,
+                      //             3 all := (deposited species on bond 1), 4 all := 0
+  PA_SPECIAL = 16,    // bits 16-18: PA_NEWSITE ... below
+  PA_NEWSITE = 1, PA_SECOND = 2, PA_ORPHAN = 3, PA_COMPACT = 4,
+  PA_ENTRIES = 192
+};
+__host__ __device__ __forceinline__ int pa_index(int kind, int Occ, int wall, int rec, int Coor) {
+  return kind | (Occ << 2) | ((wall ? 1 : 0) << 3) | ((rec ? 1 : 0) << 4) | ((Coor > 5 ? 5 : Coor) << 5);
+}
+// the rules, stated once (host side: mskc_create fills the table with this)
+static inline uint32_t pa_rule(int kind, int Occ, int wall, int rec, int C) {
+  const uint32_t INC = 1u << PA_COOR, DEC = 2u << PA_COOR, ONE = 3u << PA_COOR;
+  const uint32_t F_SET = 1u << PA_FLAG, F_CLR = 2u << PA_FLAG, F_NEW = 3u << PA_FLAG, F_ZERO = 4u << PA_FLAG;
+  const uint32_t S_WALL = 1u << PA_SFLAG, S_SPEC = 2u << PA_SFLAG;
+  auto ACT = [](int a) { return (uint32_t)(a + 1); };
+  if (kind == 0) {                                           // deposition at S (deposition.f:78-235)
+    if (Occ && wall) return PA_SUP | S_WALL;                                                   // :231-232
+    if (Occ) {                                                                                 // :191-229 full neighbour
+      uint32_t e = rec ? S_SPEC : 0u;
+      if (C <= 3 && rec) e |= ACT(A_SETBULK) | INC | PA_SUPFIX | F_SET;
+      return e;
+    }
+    if (C == 0) return ACT(A_NEW) | ONE | F_NEW | ((uint32_t)PA_NEWSITE << PA_SPECIAL);        // :88-99
+    if (C == 1) return (uint32_t)PA_SECOND << PA_SPECIAL;                                      // :100-160
+    if (C <= 3 && rec) return ACT(A_SETVOID) | INC | F_SET;                                    // :161-190
+    return 0u;
+  }
+  if (kind == 1) {                                           // evaporation of S (Evaporation.f:51-215)
+    if (Occ && wall) return PA_SDOWN;                                                          // :211-213
+    if (!rec) return 0u;
+    if (Occ) return ACT(C == 4 ? A_BULK2MC : A_SET) | DEC | PA_KEEP | S_SPEC | F_CLR;           // :173-209
+    if (C == 1) return ACT(A_ERASE) | F_ZERO | ((uint32_t)PA_ORPHAN << PA_SPECIAL);            // :62-79
+    if (C == 2) return ACT(A_SET) | ONE | ((uint32_t)PA_COMPACT << PA_SPECIAL);                // :80-128
+    if (C == 3) return ACT(A_SET) | DEC | F_CLR;                                               // :129-145
+    if (C == 4) return ACT(A_VOID2MC) | DEC | F_CLR;                                           // :146-164
+    return 0u;
+  }
+  // adsorption on / desorption from S (absorption.f:43-72, desorption.f:54-111): the occupied reciprocal neighbours are re-rated
+  if (Occ && !wall && C <= 3 && rec) return ACT(A_SET) | PA_SAME;
+  return 0u;
+}
+
 struct CoopCounters {                // per-lane partial sums, reduced over the warp at the end of a step
   int nsu, dAtoms, dVoids, dCrystal[3], dCov[3];
 };
@@ -346,7 +400,7 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
     P3 N; const uint32_t cN = nbr(S, f, N);
     const uint32_t wN = D.state[cN], aN = D.aux[cN];
     unsigned long long bN = D.bonds[cN];
-    const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN);
+    const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN), spN = w_sp(wN) & 3;
     const bool rec = recip_f(N, bN, S, f);
     const bool wall = Occ && CovN == 113;
     // the bond N -> S, and where N lists S (its census flag for S lives there).  Bonds to / from the absolute origin are
@@ -355,76 +409,69 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
     const int jS = find_code(bN, (S.x | S.y | S.z) ? fb : 0u);
     unsigned flN = aux_flags(aN);
     qN = N; qc = cN; qCov = CovN; qOcc = Occ; qSp = Occ ? w_sp(wN) : 0; qaux = aN; qfl0 = flN; wN0 = wN;
-    int newCoor = -1; uint32_t wNew = wN;
     const unsigned long long bN0 = bN;
     unsigned long long rbN = bN;                           // the bond list the site is rated with (Evaporation.f:123: the OLD one)
-    if (Occ && !wall && CovN != 0 && kind <= EVAP) fail_cell(E_NNCOV, cN);
-    else if (kind == DEP) {
-      if (wall) { sUp = true; sflag = 1u; }                // deposition.f:231-232
-      else if (Occ) {                                      // :191-229 full neighbour
-        if (rec) sflag = (unsigned)(w_sp(wN) & 3);
-        if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETBULK; sUp = (c0 == 1 && tl >= 1); if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }
-      } else if (CoorNN == 0) {                            // :88-99 a new active empty site with one fixed bond
-        if (fb > 0xFFFFu) fail(E_FARBOND, S.x, S.y, S.z);
-        bN = (unsigned long long)(fb & 0xFFFFu);
-        rbN = bN;
-        newCoor = 1; act = A_NEW; flN = (unsigned)Itrans; nb1 = c0;   // rated against S's OLD coordination (deposition.f:237-250 writes it last)
-      } else if (CoorNN == 1) {                            // :100-160 second bond: complete the tetrahedron (two more cells, below)
-        const unsigned f0 = fld(bN, 0);
-        const int dx = cdx(f0) + cdx(f), dy = cdy(f0) + cdy(f), dz = cdz(f0) + cdz(f);      // M - S = (M - N) + (N - S)
-        int Dx = abs(dx); Dx = min(Dx, D.LX - Dx);
-        int Dy = abs(dy); Dy = min(Dy, D.LY - Dy);
-        if (f0 != 0u && f != 0u && Dx * Dx + Dy * Dy + dz * dz == 72) {
-          // FIND_NN.f:46-76 rotates b2 = S-N by +-120 degrees about b1 = M-N.  For two bonds of the ideal shell (|b|^2 = 27,
-          // tetrahedral pair) the rotation is exact in integers: -(b1+b2)/2 -+ (b1 x b2)/6 (D.nn_exact, checked at start-up)
-          const int b1x = cdx(f0), b1y = cdy(f0), b1z = cdz(f0), b2x = cdx(fb), b2y = cdy(fb), b2z = cdz(fb);
-          unsigned fn[2];
-          if (D.nn_exact && b1x * b1x + b1y * b1y + b1z * b1z == 27 && b2x * b2x + b2y * b2y + b2z * b2z == 27) {
-            const int cx = b1y * b2z - b1z * b2y, cy = b1z * b2x - b1x * b2z, cz = b1x * b2y - b1y * b2x;
-            const int sx = -(b1x + b2x) / 2, sy = -(b1y + b2y) / 2, sz = -(b1z + b2z) / 2;
-            fn[0] = (unsigned)(sx - cx / 6 + 16) | ((unsigned)(sy - cy / 6 + 16) << 5) | ((unsigned)(sz - cz / 6 + 16) << 10);
-            fn[1] = (unsigned)(sx + cx / 6 + 16) | ((unsigned)(sy + cy / 6 + 16) << 5) | ((unsigned)(sz + cz / 6 + 16) << 10);
-          } else slow_find_nn(S, N, f0, fn);
-          xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb;
-        } else if (f0 == 0u || f == 0u) {                  // unfixed first bond: the general distance test on coordinates
-          const P3 M = dec_bond(N, f0);
-          int Ex = abs(M.x - S.x); Ex = min(Ex, D.LX - Ex);
-          int Ey = abs(M.y - S.y); Ey = min(Ey, D.LY - Ey);
-          const int ez = M.z - S.z;
-          if (Ex * Ex + Ey * Ey + ez * ez == 72) { unsigned fn[2]; slow_find_nn(S, N, f0, fn); xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb; }
-        }
-      } else if (CoorNN <= 3 && rec) { newCoor = CoorNN + 1; act = A_SETVOID; if (jS >= 0) flN = flag_set(flN, jS, (unsigned)Itrans); }   // :161-190
-    } else if (kind == EVAP) {
-      if (wall) sDown = true;                              // Evaporation.f:211-213
-      else if (rec) {
-        if (Occ) {                                         // :173-209; a bulk atom becomes active again
-          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_BULK2MC : A_SET; keepable = true; sflag = (unsigned)(w_sp(wN) & 3);
-          if (jS >= 0) flN = flag_set(flN, jS, 0u);
-        } else if (CoorNN == 1) {                          // :62-79 orphaned empty site leaves the lattice
-          wNew = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
-          bN = 0ull; flN = 0u;
-          act = A_ERASE; qCov = 0;
-        } else if (CoorNN == 2) {                          // :80-128 back to one bond: keep the occupied reciprocal neighbour that is left
-          newCoor = 1; act = A_SET;
-          const unsigned others = jS >= 0 ? flag_set(flN, jS, 0u) : flN;
-          int k = -1;
+    // what happens to this neighbour is a pure function of (event kind, its occupancy, wall, reciprocity, coordination):
+    // one table look-up (pa_rule() below states the reference's rules) instead of a branch per case, so that the
+    // sixteen neighbour lanes of a warp -- four events of any kinds -- run one instruction stream
+    unsigned e = __ldg(&D.pa_tab[pa_index(kind, Occ, wall, rec, CoorNN)]);
+    if (Occ && !wall && CovN != 0 && kind <= EVAP) { fail_cell(E_NNCOV, cN); e = 0u; }    // deposition.f:194-198
+    act = (int)(e & PA_ACT) - 1;
+    const unsigned cop = (e >> PA_COOR) & 3u;
+    const int newCoor = cop == 1u ? CoorNN + 1 : (cop == 2u ? CoorNN - 1 : (cop == 3u ? 1 : ((e & PA_SAME) ? CoorNN : -1)));
+    sUp = (e & PA_SUP) || ((e & PA_SUPFIX) && c0 == 1 && tl >= 1);
+    sDown = (e & PA_SDOWN) != 0u; keepable = (e & PA_KEEP) != 0u;
+    const unsigned sm = (e >> PA_SFLAG) & 3u;
+    sflag = sm == 1u ? 1u : (sm == 2u ? (unsigned)spN : 0u);
+    const unsigned fop = (e >> PA_FLAG) & 7u, spc = (e >> PA_SPECIAL) & 7u;
+    const unsigned jmask = jS >= 0 ? 3u << (2 * jS) : 0u, jval = jS >= 0 ? (unsigned)Itrans << (2 * jS) : 0u;
+    flN = fop == 1u ? ((flN & ~jmask) | jval) : (fop == 2u ? (flN & ~jmask) : (fop == 3u ? (unsigned)Itrans : (fop == 4u ? 0u : flN)));
+    uint32_t wNew = newCoor >= 0 ? MVBITS(wN, newCoor, LenCoor, PosCoor) : wN;
+    if (newCoor >= 0) qCoor = newCoor;
+    if (spc == PA_NEWSITE) {                               // deposition.f:88-99: a new active empty site with one fixed bond
+      if (fb > 0xFFFFu) fail(E_FARBOND, S.x, S.y, S.z);
+      bN = (unsigned long long)(fb & 0xFFFFu); rbN = bN;
+      nb1 = c0;                                            // rated against S's OLD coordination (deposition.f:237-250 writes it last)
+    } else if (spc == PA_ORPHAN) {                         // Evaporation.f:62-79: an orphaned empty site leaves the lattice
+      wNew = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
+      bN = 0ull; qCov = 0;
+    } else if (spc == PA_COMPACT) {                        // Evaporation.f:80-128: back to one bond: keep the occupied reciprocal neighbour that is left
+      const unsigned others = flN & ~jmask;
+      int k = -1;
 #pragma unroll
-          for (int j = 0; j < 4; j++) if (flag_get(others, j)) k = j;
-          if (k < 0) { fail(E_STALE_NBUFF, N.x, N.y, N.z); k = 0; }
-          const unsigned fk = fld(bN, k);
-          flN = flag_get(others, k);
-          // (rated with the OLD neighbour list, Evaporation.f:123: what matters is the coordination of the old first neighbour)
-          const unsigned f0 = fld(bN, 0);
-          if (f0 == fb) nb1 = c0;                          // it is S, whose word still holds its old coordination
-          else { xmode = 2; xf0 = f0; }
-          bN = (unsigned long long)fk;
-        } else if (CoorNN == 3 || CoorNN == 4) {           // :129-164; 4: a vacancy becomes active again
-          newCoor = CoorNN - 1; act = CoorNN == 4 ? A_VOID2MC : A_SET;
-          if (jS >= 0) flN = flag_set(flN, jS, 0u);
-        }
+      for (int j = 0; j < 4; j++) if (flag_get(others, j)) k = j;
+      if (k < 0) { fail(E_STALE_NBUFF, N.x, N.y, N.z); k = 0; }
+      flN = flag_get(others, k);
+      // (rated with the OLD neighbour list, Evaporation.f:123: what matters is the coordination of the old first neighbour)
+      const unsigned f0 = fld(bN, 0);
+      if (f0 == fb) nb1 = c0;                              // it is S, whose word still holds its old coordination
+      else { xmode = 2; xf0 = f0; }
+      bN = (unsigned long long)fld(bN, k);
+    } else if (spc == PA_SECOND) {                         // deposition.f:100-160: second bond: complete the tetrahedron (two more cells, below)
+      const unsigned f0 = fld(bN, 0);
+      const int dx = cdx(f0) + cdx(f), dy = cdy(f0) + cdy(f), dz = cdz(f0) + cdz(f);      // M - S = (M - N) + (N - S)
+      int Dx = abs(dx); Dx = min(Dx, D.LX - Dx);
+      int Dy = abs(dy); Dy = min(Dy, D.LY - Dy);
+      if (f0 != 0u && f != 0u && Dx * Dx + Dy * Dy + dz * dz == 72) {
+        // FIND_NN.f:46-76 rotates b2 = S-N by +-120 degrees about b1 = M-N.  For two bonds of the ideal shell (|b|^2 = 27,
+        // tetrahedral pair) the rotation is exact in integers: -(b1+b2)/2 -+ (b1 x b2)/6 (D.nn_exact, checked at start-up)
+        const int b1x = cdx(f0), b1y = cdy(f0), b1z = cdz(f0), b2x = cdx(fb), b2y = cdy(fb), b2z = cdz(fb);
+        unsigned fn[2];
+        if (D.nn_exact && b1x * b1x + b1y * b1y + b1z * b1z == 27 && b2x * b2x + b2y * b2y + b2z * b2z == 27) {
+          const int cx = b1y * b2z - b1z * b2y, cy = b1z * b2x - b1x * b2z, cz = b1x * b2y - b1y * b2x;
+          const int sx = -(b1x + b2x) / 2, sy = -(b1y + b2y) / 2, sz = -(b1z + b2z) / 2;
+          fn[0] = (unsigned)(sx - cx / 6 + 16) | ((unsigned)(sy - cy / 6 + 16) << 5) | ((unsigned)(sz - cz / 6 + 16) << 10);
+          fn[1] = (unsigned)(sx + cx / 6 + 16) | ((unsigned)(sy + cy / 6 + 16) << 5) | ((unsigned)(sz + cz / 6 + 16) << 10);
+        } else slow_find_nn(S, N, f0, fn);
+        xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb;
+      } else if (f0 == 0u || f == 0u) {                    // unfixed first bond: the general distance test on coordinates
+        const P3 M = dec_bond(N, f0);
+        int Ex = abs(M.x - S.x); Ex = min(Ex, D.LX - Ex);
+        int Ey = abs(M.y - S.y); Ey = min(Ey, D.LY - Ey);
+        const int ez = M.z - S.z;
+        if (Ex * Ex + Ey * Ey + ez * ez == 72) { unsigned fn[2]; slow_find_nn(S, N, f0, fn); xmode = 1; xf0 = fn[0]; xf1 = fn[1]; xfb = fb; }
       }
-    } else if ((FEAT & F_COV) && Occ && !wall && CoorNN <= 3 && rec) { act = A_SET; newCoor = CoorNN; }   // absorption.f:43-72 / desorption.f:54-111
-    if (newCoor >= 0) { wNew = MVBITS(wN, newCoor, LenCoor, PosCoor); qCoor = newCoor; }
+    }
     if (xmode != 1) {                                      // (a second bond is committed after its two extra cells were seen)
       if (wNew != wN) D.state[cN] = wNew;
       if (bN != bN0) D.bonds[cN] = bN;

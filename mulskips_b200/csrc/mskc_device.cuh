@@ -71,6 +71,7 @@ struct DevCtx {
   double rot_c[2], rot_s[2];        // cos/sin(2*irot*Pi_f/3), host libm (FIND_NN.f:51-52)
   int nn_exact;                     // 1: the integer form of FIND_NN.f on the ideal bond shell was verified against the double routine
   const unsigned short *arm_tab;    // [32768] arm-chair offset code per bond code (mskc_coop.cuh), 0 = use find_sn()
+  const uint32_t *pa_tab;           // [192] what an event does to one neighbour of its site (mskc_coop.cuh: pa_rule)
   int *err;                         // [8]: code, x, y, z, aux...
 };
 

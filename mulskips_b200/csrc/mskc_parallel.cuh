@@ -1002,7 +1002,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
   int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
-  if (teamsz != 8 && teamsz != 32) teamsz = 8;
+  if (teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
   const int tpb = CS_THREADS / teamsz;
   const int blocks = (ntc + tpb - 1) / tpb;
   size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
@@ -1011,8 +1011,9 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   // the kernel is instantiated per feature set so that a PVD run does not carry coverage / LA code in its hot loop
   typedef void (*cs_kernel_t)(int, uint2, int);
   static const cs_kernel_t kern8[4] = {colour_step_kernel<8, 0>, colour_step_kernel<8, 1>, colour_step_kernel<8, 2>, colour_step_kernel<8, 3>};
+  static const cs_kernel_t kern16[4] = {colour_step_kernel<16, 0>, colour_step_kernel<16, 1>, colour_step_kernel<16, 2>, colour_step_kernel<16, 3>};
   static const cs_kernel_t kern32[4] = {colour_step_kernel<32, 0>, colour_step_kernel<32, 1>, colour_step_kernel<32, 2>, colour_step_kernel<32, 3>};
-  const cs_kernel_t kern = teamsz == 8 ? kern8[feat] : kern32[feat];
+  const cs_kernel_t kern = teamsz == 8 ? kern8[feat] : (teamsz == 16 ? kern16[feat] : kern32[feat]);
   PCK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 64));
   const double ept = a->events_per_tile > 0 ? a->events_per_tile : 4.0;
   // events one tile may execute in one colour step before the rest of its quantum is carried over (flags & 0xFFFF,

@@ -81,9 +81,9 @@ def test_regression_case(built, tmp_path, case):
 @pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe", "ST", "ST-fixedT", "SiGeBdoped", "LA-fork"])
 def test_file_driven_case(built, tmp_path, kind):
     """InitSt SG (SetSiGex.f), InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
-    temperature file, LA rate law, liquid nucleus) through the host program.  The regression inputs (LattGeo / TempStat
-    480x240x240, 100 MB each) live in the reference tree only, so the files here are synthetic ones in the same format at
-    a small box; the oracle's own builders are pinned on the real files by tests/test_oracle_golden.py."""
+    temperature file, LA rate law, liquid nucleus) through the host program, on synthetic files in the reference's formats at
+    a small box, every output file against the oracle's.  (The reference's real 480x240x240 inputs run at full length
+    against the reference goldens in test_reference_inputs_full_length below.)"""
     g, o = tmp_path / "gpu", tmp_path / "oracle"
     g.mkdir(); o.mkdir()
     box = (96, 96, 120) if kind == "CAD" else (96, 96, 96)
@@ -112,6 +112,37 @@ def test_file_driven_case(built, tmp_path, kind):
     assert len(open(g / "I00000000.xyz").readlines()) > 50
     if kind in ("LA", "LA-fork"):                                 # the Coor (phase) file the FEM side of the LA coupling reads, main.f:407-430
         assert (g / "LattStat.dat").read_bytes() == (o / "LattStat.dat").read_bytes()
+
+
+@pytest.mark.parametrize("case", ["CAD", "LA"])
+def test_reference_inputs_full_length(built, tmp_path, case):
+    """BASELINE configs C3 (CVD on a voxelised nanostructure, InitSt IN) and C4 (laser annealing, InitSt LA) with the
+    reference's REAL inputs -- LattGeo / TempStat 480x240x240 unpacked from the reference's own tarballs
+    (tests/golden/CAD-input.tar.gz, LA-input.tar.gz) -- and its unmodified start files, at full length (3e6 / 1e6 events),
+    against the reference goldens: sha256 of I00000000.xyz / I00000001.xyz and the numeric log tokens of log-CAD.txt:17,24-25 /
+    log-LA.txt:26,33-34.  MSKC_CAD_NOSKIP=1 selects the plane offset of the build that produced these goldens."""
+    import tarfile
+    inputs = tmp_path / "inputs"
+    inputs.mkdir()
+    with tarfile.open(os.path.join(GOLDEN, f"{case}-input.tar.gz")) as tf:
+        tf.extractall(inputs)
+    g = tmp_path / "gpu"
+    g.mkdir()
+    paths = [str(inputs / "LattGeo.480x240x240.withzeros.dat")] if case == "CAD" else [str(inputs / "LattGeo.480x240x240.dat"), str(inputs / "TempStat.480x240x240.dat")]
+    make_start(case, str(g / "start.dat"), paths=paths)
+    env = dict(os.environ, MSKC_CAD_NOSKIP="1")
+    with open(g / "log.txt", "w") as out, open(g / "err.txt", "w") as err:
+        rc = subprocess.run([EXE, "--box", "480", "240", "240"], cwd=g, stdout=out, stderr=err, env=env).returncode
+    assert rc == 0, open(g / "log.txt").read()[-1500:] + open(g / "err.txt").read()[-1500:]
+    m = MAN[case]
+    for k in (0, 1):
+        b = open(g / f"I0000000{k}.xyz", "rb").read()
+        assert b.count(b"\n") == m[f"frame{k}_lines"]
+        assert hashlib.sha256(b).hexdigest() == m[f"frame{k}_sha256"], f"{case} frame {k} differs from the reference golden"
+    assert [int(v) for v in _tokens(g / "log.txt", "Atoms,Voids,AdAtoms")[1:4]] == m["init_lists"]
+    t = _tokens(g / "log.txt", "Iter, Time, Site")
+    assert int(t[3]) == m["final_iter"] and [int(v) for v in t[5:8]] == m["final_site"] and float(t[4]) == float(m["final_time"])
+    assert [int(v) for v in _tokens(g / "log.txt", "NatNvoidNad")[1:4]] == m["final_lists"]
 
 
 def test_checkpoint_restart(built, tmp_path):

@@ -15,9 +15,9 @@ from cases import GOLDEN, make_start, start_path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
 MAN = json.load(open(os.path.join(GOLDEN, "manifest.json")))
-RTIN = "/root/reference/regression-tests/input-and-references-files"
+RTIN = GOLDEN                                 # CAD-input.tar.gz / LA-input.tar.gz: the reference's own tarballs, kept as fixtures
 BOX480 = ["Si-SL", "surface", "cube", "cube-zigzag", "sphere", "inverted-pyramid", "finfet", "CVD-Si-SiH2"]
-FILECASES = ["CAD", "LA"]                     # need the 60-140 MB LattGeo/TempStat inputs of the reference tree
+FILECASES = ["CAD", "LA"]                     # LattGeo / TempStat 480x240x240 (60-140 MB unpacked) from the two tarballs
 
 
 @pytest.fixture(scope="session")

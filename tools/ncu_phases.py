@@ -6,20 +6,25 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 rep, lib, kname = sys.argv[1:4]
 # (file, first line, last line, label) -- line numbers of the build that was profiled
 REGIONS = [
-    ("mskc_parallel.cuh", 60, 95, "Philox4x32-10"),
-    ("mskc_parallel.cuh", 96, 160, "tile lists: put / erase / slot"),
-    ("mskc_parallel.cuh", 161, 215, "tile budget / load"),
-    ("mskc_parallel.cuh", 216, 305, "selection: rate sum, prefix scan, target search, species draw"),
-    ("mskc_parallel.cuh", 306, 370, "tile finish / kernel prologue"),
-    ("mskc_coop.cuh", 1, 62, "cell / bond helpers (coop)"),
-    ("mskc_coop.cuh", 63, 125, "rate of a site (Get_Prob census)"),
-    ("mskc_coop.cuh", 126, 185, "coop_compact / second_bond"),
-    ("mskc_coop.cuh", 186, 232, "event: S word, counters"),
-    ("mskc_coop.cuh", 233, 272, "event: bond fixing + IF_Arm_Choice"),
-    ("mskc_coop.cuh", 273, 334, "event phase A: the four neighbours"),
-    ("mskc_coop.cuh", 335, 370, "event phases B/C glue: S request, commit"),
-    ("mskc_device.cuh", 1, 160, "bond decode / wrap / cell index (device.cuh helpers)"),
-    ("mskc_device.cuh", 161, 300, "geometry + rate tables (device.cuh)"),
+    ("mskc_parallel.cuh", 78, 95, "Philox4x32-10"),
+    ("mskc_parallel.cuh", 96, 116, "list_of / pack_ce"),
+    ("mskc_parallel.cuh", 117, 165, "tile lists: put / erase"),
+    ("mskc_parallel.cuh", 166, 232, "tile budget / load"),
+    ("mskc_parallel.cuh", 233, 300, "selection: chunk sums, scan, walk, decode"),
+    ("mskc_parallel.cuh", 301, 340, "tile finish"),
+    ("mskc_parallel.cuh", 341, 375, "kernel prologue / loop"),
+    ("mskc_coop.cuh", 39, 110, "coop helpers: fld / nbr / flags"),
+    ("mskc_coop.cuh", 111, 196, "coop_rate (full census)"),
+    ("mskc_coop.cuh", 197, 222, "flag_rate"),
+    ("mskc_coop.cuh", 223, 290, "event: species draw, S record"),
+    ("mskc_coop.cuh", 291, 336, "event: bond fixing + IF_Arm_Choice"),
+    ("mskc_coop.cuh", 337, 436, "event phase A: the four neighbours"),
+    ("mskc_coop.cuh", 437, 462, "event: extra cells (second bond / old first neighbour)"),
+    ("mskc_coop.cuh", 463, 490, "event: ballots + S request"),
+    ("mskc_coop.cuh", 491, 503, "event: rate call"),
+    ("mskc_coop.cuh", 504, 525, "event: commit"),
+    ("mskc_device.cuh", 1, 170, "device.cuh: word fields / cell index"),
+    ("mskc_device.cuh", 171, 320, "device.cuh: geometry + rate tables"),
 ]
 sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(sass)))
