@@ -202,7 +202,7 @@ def run_ours(args):
     n_active = r.n_active
 
     # ---- roofline of the dominant kernel: every colour-step launch timed with CUDA events ---------
-    rr = ctx.run_parallel(min(args.sweeps, 16), events_per_tile=args.ept, seed=seed + 999)
+    rr = ctx.run_parallel(min(args.sweeps, 16), events_per_tile=args.ept, seed=seed + 999, time_kernels=True)
     n_launch = rr.sampler_launches
     alg_bytes = B_PER_SITE_UPDATE * rr.site_updates + B_PER_EVENT * rr.events_done
     peak, peak_src = peaks()

@@ -154,8 +154,10 @@ typedef struct {
   int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
   int32_t  flags;            /* bits 0-15: events one tile may execute per colour step before the rest of its
                               * quantum is carried to its next step (0 = default 3*events_per_tile,
-                              * 0xFFFF = no cap); other bits reserved, 0                               */
+                              * 0xFFFF = no cap); bit 16: MSKC_PAR_TIME_KERNELS; other bits reserved, 0   */
 } mskc_parallel_args;
+/* time every colour-step launch with CUDA events on the library's stream (n_sweeps <= 64): sweep_kernel_ms of the result */
+#define MSKC_PAR_TIME_KERNELS 0x10000
 
 typedef struct {
   int64_t events_done;       /* events executed by this call                                        */

@@ -260,8 +260,9 @@ class Mskc:
         self._ck(self.lib.mskc_run_parity(self.h, C.byref(a), C.byref(r)))
         return r
 
-    def run_parallel(self, n_sweeps, events_per_tile=4.0, tau_fixed=0.0, seed=1, flags=0) -> ParallelResult:
-        a = _ParallelArgs(int(n_sweeps), float(events_per_tile), float(tau_fixed), int(seed), 0, int(flags))
+    def run_parallel(self, n_sweeps, events_per_tile=4.0, tau_fixed=0.0, seed=1, flags=0, time_kernels=False) -> ParallelResult:
+        """time_kernels: every colour-step launch is timed with CUDA events (n_sweeps <= 64) -> sweep_kernel_ms"""
+        a = _ParallelArgs(int(n_sweeps), float(events_per_tile), float(tau_fixed), int(seed), 0, int(flags) | (0x10000 if time_kernels else 0))
         r = ParallelResult()
         self._ck(self.lib.mskc_run_parallel(self.h, C.byref(a), C.byref(r)))
         return r

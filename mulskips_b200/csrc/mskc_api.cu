@@ -238,6 +238,11 @@ extern "C" int mskc_destroy(mskc_ctx *h) {
   cudaFree(h->d_stage); cudaFree(h->d_arm_tab); cudaFree(h->d_pa_tab); cudaFree(h->d_frame_cell); cudaFree(h->d_frame_word); cudaFree(h->d_frame_n);
   cudaFree(h->d_la_slot); cudaFree(h->d_la_E); cudaFree(h->d_la_D); cudaFree(h->d_la_A); cudaFree(h->d_la_S); cudaFree(h->d_la3_F); cudaFree(h->d_err);
   cudaFree(h->d_Tree); cudaFree(h->d_lattind); cudaFree(h->d_mc_cell); cudaFree(h->d_void_cell); cudaFree(h->d_mc_ev); cudaFree(h->d_ps);
+#ifndef MSKC_EMU
+  if (h->PC.p2p_left) cudaIpcCloseMemHandle(h->PC.p2p_left);
+  if (h->PC.p2p_right && h->PC.p2p_right != h->PC.p2p_left) cudaIpcCloseMemHandle(h->PC.p2p_right);
+#endif
+  cudaFree(h->PC.p2p_recv); h->PC.p2p_recv = nullptr; h->PC.p2p_left = h->PC.p2p_right = nullptr;
   if (h->PC.comm) { std::string e; if (NcclApi *nccl = nccl_api(&e)) nccl->CommDestroy((ncclComm_t)h->PC.comm); h->PC.comm = nullptr; }
   parallel_free(h->PC);
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
@@ -1051,6 +1056,8 @@ extern "C" int mskc_comm_connect(mskc_ctx *h, const void *id128) {
   ncclResult_t r = nccl->CommInitRank(&comm, h->PC.nranks, id, h->PC.rank);
   if (r != ncclSuccess) return set_err(h, "ncclCommInitRank: %s", nccl->GetErrorString(r));
   h->PC.comm = (void *)comm;
+  // halo buffers of the neighbours mapped into this process (CUDA IPC over NVLink); ncclSend/ncclRecv is the fallback
+  if (p2p_connect(h->PC, h->stream, &h->err)) { g_last_error = h->err; return -1; }
   return 0;
 }
 

@@ -40,13 +40,18 @@ struct TileStat {            // written only by the tile's own lane
 
 struct SweepState {          // one per context, device resident
   double time, tau, total_rate, tree_root;
-  long long n_active, sweeps, step;     // step = global colour-step counter (Philox counter word)
+  long long n_active, sweeps, step;     // step = colour steps done before the current sweep (Philox counter word)
   long long max_cnt;
+  // parameters of the current mskc_run_parallel call (written once per call, so that the kernels of a sweep take no
+  // per-call arguments and a captured CUDA graph of one sweep can be replayed)
+  uint2 key; int event_cap, pad;
+  double events_per_tile, tau_fixed, ntiles_global;
 };
 
 // Per-tile active lists, tile-major: entry k of list l lives at [l*cap + k]; the warp that owns tile l
 // streams its list into shared memory with coalesced loads at the start of its colour step.  Lists of one
 // colour are contiguous (l = colour*ntc + index).
+struct HaloRec;
 struct ParallelCtx {
   int tile = 24, ntx = 0, nty = 0, ntiles = 0, cap = 0;
   double *rate = nullptr; unsigned long long *ce = nullptr; int *cnt = nullptr, *live = nullptr; uint32_t *aux = nullptr; double *tile_rate = nullptr; double *lag = nullptr;
@@ -58,6 +63,9 @@ struct ParallelCtx {
   unsigned char *sendbuf[2] = {nullptr, nullptr}, *recvbuf[2] = {nullptr, nullptr};
   void *comm = nullptr;                 // ncclComm_t
   unsigned int *pack_done = nullptr;
+  // peer-to-peer halo exchange: my receive buffers [2 sides][2 parities] (one allocation, IPC-exported) and the two
+  // neighbours' receive buffers mapped into this process
+  HaloRec *p2p_recv = nullptr; void *p2p_left = nullptr, *p2p_right = nullptr; bool p2p = false; unsigned int halo_seq = 0;
   long long ncell = 0;
   long long base_atoms = 0, base_voids = 0;
   int baseCrystal[3] = {0, 0, 0}, baseCov[3] = {0, 0, 0};
@@ -65,6 +73,10 @@ struct ParallelCtx {
   TileStat extra{};                     // events applied outside the colour steps (trace replay), added to the counters
   double time = 0.0;
   bool ran = false, replayed = false, lists_stale = false, listed_flag_in_state = false;
+#ifndef MSKC_EMU
+  cudaGraphExec_t gexec = nullptr;        // one captured sweep (single GPU)
+#endif
+  void *g_kern = nullptr; int g_blocks = 0, g_launches = 0; size_t g_smem = 0;
 };
 
 struct TileView {            // what the kernels need (constant memory)
@@ -325,7 +337,7 @@ __device__ __forceinline__ void tile_finish(TileRun &t, const TileLists &L, cons
 // executes every iteration (full-mask votes and shuffles are the convergence points), a team without an event
 // only takes part in the synchronisation.
 template <int TEAM, int FEAT>
-__global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int colour, uint2 key, int event_cap) {
+__global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int colour, int pos /* position of this colour step inside its sweep, 0..3 */) {
   constexpr int TPB = CS_THREADS / TEAM;
   constexpr unsigned FULL = 0xFFFFFFFFu;
   MSKC_DYN_SHARED(smem);
@@ -344,7 +356,8 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int co
   // a team beyond the last tile, or on a halo tile (it belongs to the neighbouring rank), idles through the step
   const bool exists = wid < V.ntc && !(V.halo && (t.x0 == 0 || t.x0 == D.LX - TILE));
   const SweepState ss = *V.ss;
-  t.step = (unsigned long long)ss.step; t.budget = t.tau = ss.tau; t.debt = 0.0; t.max_ev = event_cap;
+  const uint2 key = ss.key; const int event_cap = ss.event_cap;
+  t.step = (unsigned long long)ss.step + (unsigned long long)pos; t.budget = t.tau = ss.tau; t.debt = 0.0; t.max_ev = event_cap;
   L.own = exists ? t.l : -2;
   if (exists) { tile_budget(t, ss.tau, event_cap); tile_load<TEAM>(t.l, tl, tshift, tm, L.s_rate, L.s_ce, L.s_n); }
   __syncwarp();
@@ -360,7 +373,25 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int co
 // changed in its two 48-unit strips (its border tile column + its halo column) and applies what it receives.
 struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad /* census flags */; };     // 32 B
 // one launch packs both strips (blockIdx.y = side); the last block to finish clears the dirty counters
-__global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of the owned block */, HaloRec *out0, HaloRec *out1, unsigned int *done) {
+// One launch packs both strips (blockIdx.y = side).  out0 / out1 may live in the NEIGHBOUR's memory (peer-mapped over
+// NVLink, see p2p_connect): the records are stored straight into its receive buffer, and the last block to finish
+// publishes both headers {record count, seq} with one 64-bit store each after a system-wide fence -- the header is the
+// flag the neighbour's halo_apply_kernel waits on.  It also clears the dirty counters.
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+#ifndef MSKC_EMU
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+  *p = v;
+#endif
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+#ifndef MSKC_EMU
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+#else
+  return *p;
+#endif
+}
+__global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of the owned block */, HaloRec *out0, HaloRec *out1, unsigned int *done, unsigned int seq) {
   const int side = blockIdx.y;
   HaloRec *out = side ? out1 : out0;
   const int shift = side ? -owned : owned;
@@ -377,17 +408,30 @@ __global__ void __launch_bounds__(256) halo_pack_kernel(int owned /* width of th
     if (sl) { const long long a = lidx(list_of(s), sl - 1); r.rate = V.rate[a]; r.ev = (uint32_t)ce_event(V.ce[a]); }
     out[1 + k] = r;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { HaloRec h; h.cell = (uint32_t)n; h.state = 0; h.bonds = 0; h.rate = 0; h.ev = 0; h.pad = 0; out[0] = h; }
+  __threadfence_system();                                  // this thread's records are visible to the peer before the header is
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1) { V.dirty_n[0] = 0; V.dirty_n[1] = 0; *done = 0u; }
+    if (atomicAdd(done, 1u) == gridDim.x * gridDim.y - 1) {
+      __threadfence_system();
+      const unsigned long long n0 = (unsigned long long)min(V.dirty_n[0], V.dirty_cap), n1 = (unsigned long long)min(V.dirty_n[1], V.dirty_cap);
+      st_release_sys(reinterpret_cast<unsigned long long *>(out0), n0 | ((unsigned long long)seq << 32));
+      st_release_sys(reinterpret_cast<unsigned long long *>(out1), n1 | ((unsigned long long)seq << 32));
+      V.dirty_n[0] = 0; V.dirty_n[1] = 0; *done = 0u;
+    }
   }
 }
-// one launch applies both received buffers (blockIdx.y selects the buffer)
-__global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in0, const HaloRec *in1) {
+// one launch applies both received buffers (blockIdx.y selects the buffer); every block first waits for the header of
+// its buffer to carry this exchange's sequence number (the neighbour's pack kernel has finished writing it)
+__global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in0, const HaloRec *in1, unsigned int seq) {
   const HaloRec *in = blockIdx.y ? in1 : in0;
-  const int n = (int)in[0].cell;
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    unsigned long long h;
+    do { h = ld_acquire_sys(reinterpret_cast<const unsigned long long *>(in)); } while ((unsigned int)(h >> 32) != seq);
+    s_n = (int)(unsigned int)h;
+  }
+  __syncthreads();
+  const int n = s_n;
   TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const HaloRec r = in[1 + k];
@@ -537,14 +581,17 @@ __global__ void __launch_bounds__(1024) sweep_sum_kernel(int ntiles) {
   }
 }
 // stage 2 (after the all-reduce of V.red over the ranks, if any): clock, next tau, global-coupling terms
-__global__ void sweep_finish_kernel(double ntiles_global, double events_per_tile, double tau_fixed, int advance) {
+__global__ void sweep_finish_kernel(int advance) {
   SweepState &s = *V.ss;
   const double R = V.red[0];
-  if (advance) { s.time += s.tau; s.sweeps++; }
+  if (advance) { s.time += s.tau; s.sweeps++; s.step += 4; }
   s.total_rate = R; s.tree_root = R; s.n_active = (long long)V.red[1];
-  s.tau = tau_fixed > 0 ? tau_fixed : (R > 0 ? events_per_tile * ntiles_global / R : 0.0);
+  s.tau = s.tau_fixed > 0 ? s.tau_fixed : (R > 0 ? s.events_per_tile * s.ntiles_global / R : 0.0);
 }
-__global__ void bump_step_kernel(SweepState *ss) { ss->step++; }
+__global__ void set_params_kernel(uint2 key, int event_cap, double events_per_tile, double tau_fixed, double ntiles_global) {
+  SweepState &s = *V.ss;
+  s.key = key; s.event_cap = event_cap; s.events_per_tile = events_per_tile; s.tau_fixed = tau_fixed; s.ntiles_global = ntiles_global;
+}
 __global__ void reset_maxev_kernel(TileStat *ts, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) ts[i].maxev = 0; }
 
 __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
@@ -797,6 +844,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -810,7 +858,7 @@ static inline NcclApi *nccl_api(std::string *err) {
   for (const char *n : names) { if (n && *n) { api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; } }
   if (!api.lib) { if (err) *err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return nullptr; }
 #define MSKC_SYM(f) *(void **)(&api.f) = dlsym(api.lib, "nccl" #f); if (!api.f) { if (err) *err = "libnccl: missing symbol nccl" #f; api.lib = nullptr; return nullptr; }
-  MSKC_SYM(GetUniqueId) MSKC_SYM(CommInitRank) MSKC_SYM(CommDestroy) MSKC_SYM(Send) MSKC_SYM(Recv) MSKC_SYM(AllReduce) MSKC_SYM(GroupStart) MSKC_SYM(GroupEnd) MSKC_SYM(GetErrorString)
+  MSKC_SYM(GetUniqueId) MSKC_SYM(CommInitRank) MSKC_SYM(CommDestroy) MSKC_SYM(Send) MSKC_SYM(Recv) MSKC_SYM(AllReduce) MSKC_SYM(AllGather) MSKC_SYM(GroupStart) MSKC_SYM(GroupEnd) MSKC_SYM(GetErrorString)
 #undef MSKC_SYM
   return &api;
 }
@@ -820,11 +868,16 @@ enum { HALO_CAP = 16384 };         // records per side per colour step (512 KiB 
 
 static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
+  HaloRec *p2p_recv = P.p2p_recv; void *p2p_left = P.p2p_left, *p2p_right = P.p2p_right; const bool p2p = P.p2p; const unsigned int halo_seq = P.halo_seq;
+#ifndef MSKC_EMU
+  if (P.gexec) { cudaGraphExecDestroy(P.gexec); P.gexec = nullptr; }
+#endif
   cudaFree(P.dirty_bits); cudaFree(P.dirty_cell); cudaFree(P.dirty_n); cudaFree(P.pack_done); cudaFree(P.red);
   for (int i = 0; i < 2; i++) { cudaFree(P.sendbuf[i]); cudaFree(P.recvbuf[i]); }
   cudaFree(P.rate); cudaFree(P.ce); cudaFree(P.cnt); cudaFree(P.live); cudaFree(P.aux); cudaFree(P.tile_rate); cudaFree(P.lag); cudaFree(P.tstat); cudaFree(P.ss); cudaFree(P.tot);
   P = ParallelCtx();
   P.halo = halo; P.rank = rank; P.nranks = nranks; P.comm = comm;
+  P.p2p_recv = p2p_recv; P.p2p_left = p2p_left; P.p2p_right = p2p_right; P.p2p = p2p; P.halo_seq = halo_seq;
 }
 static inline TileView tile_view(const ParallelCtx &P) {
   TileView V; V.tile = P.tile; V.ntx = P.ntx; V.nty = P.nty; V.cap = P.cap; V.NT = P.ntiles; V.hx = P.ntx / 2; V.ntc = (P.ntx / 2) * (P.nty / 2);
@@ -906,38 +959,93 @@ static inline int parallel_census_flags(ParallelCtx &P, const DevCtx &H, cudaStr
 static const int TILE_CAP = MSKC_TILE_CAP;
 
 // per-sweep totals: local sums, all-reduce over the ranks of a slab run, then clock / tau / global-coupling terms
-static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, double ept, double tau_fixed, int advance, int *launches, std::string *err) {
+static inline int sweep_totals(ParallelCtx &P, cudaStream_t st, int advance, int *launches, std::string *err) {
   MSKC_LAUNCH(sweep_sum_kernel, 1, 1024, 0, st, P.ntiles);
   if (P.nranks > 1) {
     NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
     if (!P.comm) { if (err) *err = "slab run with several ranks: call mskc_comm_connect first"; return -1; }
     NCK(nccl->AllReduce(P.red, P.red, 4, ncclDouble, ncclSum, (ncclComm_t)P.comm, st));
   }
-  const double owned = (double)(P.ntx - 2 * P.halo) * P.nty * P.nranks;
-  MSKC_LAUNCH(sweep_finish_kernel, 1, 1, 0, st, owned, ept, tau_fixed, advance);
+  MSKC_LAUNCH(sweep_finish_kernel, 1, 1, 0, st, advance);
   *launches += 2;
   return 0;
 }
 // after a colour step: send the changed records of the two shared strips to the neighbours, apply theirs
+// Receive buffers of the halo exchange: [side][parity][1 + HALO_CAP] records in ONE allocation, so that one IPC handle per
+// rank is enough.  side 0 receives from the right neighbour (its left strip), side 1 from the left neighbour.
+static inline HaloRec *p2p_slot(void *base, int side, int parity) { return reinterpret_cast<HaloRec *>(base) + (size_t)(side * 2 + parity) * (HALO_CAP + 1); }
+static inline int p2p_alloc(ParallelCtx &P, cudaStream_t st, std::string *err) {
+  if (P.p2p_recv) return 0;
+  const size_t bytes = (size_t)4 * (HALO_CAP + 1) * sizeof(HaloRec);
+  PCK(cudaMalloc(&P.p2p_recv, bytes));
+  PCK(cudaMemsetAsync(P.p2p_recv, 0, bytes, st));
+  PCK(cudaStreamSynchronize(st));
+  return 0;
+}
+// Several ranks (one process per GPU): every rank exports its receive buffers through CUDA IPC, the handles travel in one
+// ncclAllGather, and each rank maps the buffers of its two neighbours: halo_pack_kernel then stores its records straight
+// into the neighbour's memory over NVLink and the neighbour's halo_apply_kernel waits on the header -- no collective call,
+// no fixed-size message and no host involvement per colour step.  Falls back to ncclSend/ncclRecv when the mapping fails.
+static inline int p2p_connect(ParallelCtx &P, cudaStream_t st, std::string *err) {
+  if (p2p_alloc(P, st, err)) return -1;
+  P.p2p = false;
+#ifndef MSKC_EMU
+  if (P.nranks == 1 || getenv("MSKC_HALO_NCCL")) return 0;
+  NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, P.p2p_recv) != cudaSuccess) { cudaGetLastError(); return 0; }
+  unsigned char *d_in = nullptr, *d_all = nullptr;
+  const size_t hs = sizeof(cudaIpcMemHandle_t);
+  PCK(cudaMalloc(&d_in, hs)); PCK(cudaMalloc(&d_all, hs * P.nranks));
+  PCK(cudaMemcpyAsync(d_in, &mine, hs, cudaMemcpyHostToDevice, st));
+  NCK(nccl->AllGather(d_in, d_all, hs, ncclUint8, (ncclComm_t)P.comm, st));
+  std::vector<cudaIpcMemHandle_t> all(P.nranks);
+  PCK(cudaMemcpyAsync(all.data(), d_all, hs * P.nranks, cudaMemcpyDeviceToHost, st));
+  PCK(cudaStreamSynchronize(st));
+  cudaFree(d_in); cudaFree(d_all);
+  const int left = (P.rank + P.nranks - 1) % P.nranks, right = (P.rank + 1) % P.nranks;
+  bool ok = cudaIpcOpenMemHandle(&P.p2p_left, all[left], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+  if (ok) { if (right == left) P.p2p_right = P.p2p_left; else ok = cudaIpcOpenMemHandle(&P.p2p_right, all[right], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
+  // every rank must take the same path: agree by all-reduce (sum of successes == nranks)
+  double *d_ok = nullptr, h_ok = ok ? 1.0 : 0.0;
+  PCK(cudaMalloc(&d_ok, sizeof(double)));
+  PCK(cudaMemcpyAsync(d_ok, &h_ok, sizeof(double), cudaMemcpyHostToDevice, st));
+  NCK(nccl->AllReduce(d_ok, d_ok, 1, ncclDouble, ncclSum, (ncclComm_t)P.comm, st));
+  PCK(cudaMemcpyAsync(&h_ok, d_ok, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PCK(cudaStreamSynchronize(st));
+  cudaFree(d_ok);
+  if (!ok) cudaGetLastError();
+  P.p2p = h_ok > P.nranks - 0.5;
+  if (!P.p2p) fprintf(stderr, "mskc: peer-mapped halo buffers unavailable on rank %d, using ncclSend/ncclRecv\n", P.rank);
+#endif
+  return 0;
+}
+// after a colour step: the changed records of the two shared strips go to the neighbours, theirs are applied
 static inline int halo_exchange(ParallelCtx &P, const DevCtx &H, cudaStream_t st, int *launches, std::string *err) {
   const int owned = H.LX - 2 * P.tile;                         // width of the owned block = shift between the two copies of a strip
+  if (p2p_alloc(P, st, err)) return -1;
+  const unsigned int seq = ++P.halo_seq;                       // same on every rank (all run the same sequence of colour steps)
+  const int par = (int)(seq & 1u);                             // double-buffered: a rank one step ahead never overwrites what its neighbour still reads
+  HaloRec *in0 = p2p_slot(P.p2p_recv, 0, par), *in1 = p2p_slot(P.p2p_recv, 1, par);
   // my left strip = the left neighbour's right strip (cells shift by +owned), my right strip = the right neighbour's left strip
-  MSKC_LAUNCH(halo_pack_kernel, dim3(16, 2), 256, 0, st, owned, (HaloRec *)P.sendbuf[0], (HaloRec *)P.sendbuf[1], P.pack_done);
-  const size_t bytes = (size_t)(HALO_CAP + 1) * sizeof(HaloRec);
-  const unsigned char *in0 = P.sendbuf[0], *in1 = P.sendbuf[1];
-  if (P.nranks > 1) {
+  if (P.nranks == 1) {                                         // one rank: it is its own neighbour on both sides (periodic box)
+    MSKC_LAUNCH(halo_pack_kernel, dim3(16, 2), 256, 0, st, owned, in0, in1, P.pack_done, seq);
+  } else if (P.p2p) {
+    MSKC_LAUNCH(halo_pack_kernel, dim3(16, 2), 256, 0, st, owned, p2p_slot(P.p2p_left, 0, par), p2p_slot(P.p2p_right, 1, par), P.pack_done, seq);
+  } else {
     NcclApi *nccl = nccl_api(err); if (!nccl) return -1;
     if (!P.comm) { if (err) *err = "slab run with several ranks: call mskc_comm_connect first"; return -1; }
+    MSKC_LAUNCH(halo_pack_kernel, dim3(16, 2), 256, 0, st, owned, (HaloRec *)P.sendbuf[0], (HaloRec *)P.sendbuf[1], P.pack_done, seq);
+    const size_t bytes = (size_t)(HALO_CAP + 1) * sizeof(HaloRec);
     const int left = (P.rank + P.nranks - 1) % P.nranks, right = (P.rank + 1) % P.nranks;
     NCK(nccl->GroupStart());
     NCK(nccl->Send(P.sendbuf[0], bytes, ncclUint8, left, (ncclComm_t)P.comm, st));
     NCK(nccl->Send(P.sendbuf[1], bytes, ncclUint8, right, (ncclComm_t)P.comm, st));
-    NCK(nccl->Recv(P.recvbuf[0], bytes, ncclUint8, right, (ncclComm_t)P.comm, st));
-    NCK(nccl->Recv(P.recvbuf[1], bytes, ncclUint8, left, (ncclComm_t)P.comm, st));
+    NCK(nccl->Recv(in0, bytes, ncclUint8, right, (ncclComm_t)P.comm, st));
+    NCK(nccl->Recv(in1, bytes, ncclUint8, left, (ncclComm_t)P.comm, st));
     NCK(nccl->GroupEnd());
-    in0 = P.recvbuf[0]; in1 = P.recvbuf[1];
-  }                                                            // one rank: it is its own neighbour on both sides (periodic box)
-  MSKC_LAUNCH(halo_apply_kernel, dim3(16, 2), 256, 0, st, (const HaloRec *)in0, (const HaloRec *)in1);
+  }
+  MSKC_LAUNCH(halo_apply_kernel, dim3(16, 2), 256, 0, st, (const HaloRec *)in0, (const HaloRec *)in1, seq);
   *launches += 2;
   return 0;
 }
@@ -998,18 +1106,26 @@ static inline int parallel_init_flat(ParallelCtx &P, DevCtx &H, cudaStream_t st,
   return 0;
 }
 
+// which team size runs a colour step: every tile of the colour should be resident at once (one wave of 16 warps per SM
+// at 128 registers) with as many lanes per tile as that allows -- the step is bound by the serial chain of the busiest
+// tile, and a wider team shortens that chain (no other tile's branches in its instruction stream)
+static inline int pick_team(int ntc) {
+  if (const char *e = getenv("MSKC_TEAM")) { const int t = atoi(e); if (t == 8 || t == 16 || t == 32) return t; }
+  const int resident_warps = 148 * 16;
+  return ntc <= resident_warps ? 32 : (ntc <= 2 * resident_warps ? 16 : 8);
+}
+
 static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1, const mskc_parallel_args *a, mskc_parallel_result *r, std::string *err) {
   memset(r, 0, sizeof *r);
   const int ntc = (P.ntx / 2) * (P.nty / 2);
-  int teamsz = 8; if (const char *e = getenv("MSKC_TEAM")) teamsz = atoi(e);
-  if (teamsz != 8 && teamsz != 16 && teamsz != 32) teamsz = 8;
+  const int teamsz = pick_team(ntc);
   const int tpb = CS_THREADS / teamsz;
   const int blocks = (ntc + tpb - 1) / tpb;
   size_t smem = (size_t)tpb * P.cap * 16 + tpb * sizeof(int);
   if (const char *e = getenv("MSKC_SMEM_PAD")) smem += (size_t)atoi(e);      // diagnostic: fewer resident blocks per SM
   const int feat = (H.NCov > 0 ? F_COV : 0) | (H.la ? F_LA : 0);
   // the kernel is instantiated per feature set so that a PVD run does not carry coverage / LA code in its hot loop
-  typedef void (*cs_kernel_t)(int, uint2, int);
+  typedef void (*cs_kernel_t)(int, int);
   static const cs_kernel_t kern8[4] = {colour_step_kernel<8, 0>, colour_step_kernel<8, 1>, colour_step_kernel<8, 2>, colour_step_kernel<8, 3>};
   static const cs_kernel_t kern16[4] = {colour_step_kernel<16, 0>, colour_step_kernel<16, 1>, colour_step_kernel<16, 2>, colour_step_kernel<16, 3>};
   static const cs_kernel_t kern32[4] = {colour_step_kernel<32, 0>, colour_step_kernel<32, 1>, colour_step_kernel<32, 2>, colour_step_kernel<32, 3>};
@@ -1022,39 +1138,63 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   if (const char *e = getenv("MSKC_EVCAP")) evcap = atoi(e);
   if (evcap == 0) evcap = std::max(4, (int)(3.0 * ept));
   if (evcap == 0xFFFF) evcap = 1 << 14;
-  uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
+  const uint2 key = make_uint2((uint32_t)a->seed, (uint32_t)(a->seed >> 32));
+  const double owned = (double)(P.ntx - 2 * P.halo) * P.nty * P.nranks;
   TileStat before = P.h_tot;
   int launches = 0;
   MSKC_LAUNCH(reset_maxev_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.tstat, P.ntiles);
+  MSKC_LAUNCH(set_params_kernel, 1, 1, 0, st, key, evcap, ept, a->tau_fixed, owned);
   PCK(cudaEventRecord(e0, st));
   if (!P.ran) {                    // first call: establish total rate and tau
     MSKC_LAUNCH(tile_rate_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.ntiles);
-    if (sweep_totals(P, st, ept, a->tau_fixed, 0, &launches, err)) return -1;
+    if (sweep_totals(P, st, 0, &launches, err)) return -1;
     launches += 1;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
-  // short calls time every sampler kernel on its own (CUDA events on the launching stream): this is
-  // the per-launch duration the roofline in bench.py is computed from
-  const bool timed = a->n_sweeps > 0 && a->n_sweeps <= 64;
+  // on request every sampler kernel is timed on its own (CUDA events on the launching stream): this is the per-launch
+  // duration the roofline in bench.py is computed from
+  const bool timed = (a->flags & MSKC_PAR_TIME_KERNELS) && a->n_sweeps > 0 && a->n_sweeps <= 64;
   std::vector<cudaEvent_t> evs;
   if (timed) { evs.resize((size_t)a->n_sweeps * 8); for (auto &e : evs) PCK(cudaEventCreate(&e)); }
   size_t ke = 0;
   int n_sampler_launches = 0;
-  for (long long s = 0; s < a->n_sweeps; s++) {
-    // fixed colour order every sweep (an alternating ABCD/DCBA order was measured WORSE: a colour then runs twice
-    // in a row, doubling its effective quantum -- DESIGN.md section 5.3)
+  // one sweep = four colour steps (fixed colour order: an alternating ABCD/DCBA order was measured WORSE, a colour then
+  // runs twice in a row, doubling its effective quantum -- DESIGN.md section 5.3) + the per-sweep totals
+  auto one_sweep = [&]() -> int {
     for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, key, evcap);
+      MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, c);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
-      MSKC_LAUNCH(bump_step_kernel, 1, 1, 0, st, P.ss);
-      launches += 2; n_sampler_launches++;
+      launches += 1; n_sampler_launches++;
       if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
     }
     if (P.halo) { MSKC_LAUNCH(compact_halo_kernel, (2 * P.nty * 32 + 127) / 128, 128, 0, st); launches++; }
-    if (sweep_totals(P, st, ept, a->tau_fixed, 1, &launches, err)) return -1;
+    return sweep_totals(P, st, 1, &launches, err);
+  };
+  bool graphed = false;
+#ifndef MSKC_EMU
+  // single GPU: the six launches of a sweep are captured once into a CUDA graph and replayed (launch-bound tail of short
+  // colour steps on small boxes; nothing in a sweep depends on host-side arguments any more)
+  if (!timed && !P.halo && a->n_sweeps >= 4 && !getenv("MSKC_NO_GRAPH")) {
+    if (P.gexec && (P.g_kern != (void *)kern || P.g_blocks != blocks || P.g_smem != smem)) { cudaGraphExecDestroy(P.gexec); P.gexec = nullptr; }
+    if (!P.gexec) {
+      cudaGraph_t g = nullptr; int l0 = launches, n0 = n_sampler_launches;
+      PCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int rc = one_sweep();
+      PCK(cudaStreamEndCapture(st, &g));
+      if (rc) return -1;
+      PCK(cudaGraphInstantiate(&P.gexec, g, 0));
+      cudaGraphDestroy(g);
+      P.g_kern = (void *)kern; P.g_blocks = blocks; P.g_smem = smem; P.g_launches = launches - l0;
+      launches = l0; n_sampler_launches = n0;
+    }
+    for (long long s = 0; s < a->n_sweeps; s++) PCK(cudaGraphLaunch(P.gexec, st));
+    launches += (int)(a->n_sweeps * P.g_launches); n_sampler_launches += (int)(4 * a->n_sweeps);
+    graphed = true;
   }
+#endif
+  if (!graphed) for (long long s = 0; s < a->n_sweeps; s++) if (one_sweep()) return -1;
   MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
   launches++;
   PCK(cudaEventRecord(e1, st));
@@ -1087,7 +1227,7 @@ static inline int parallel_rerate(ParallelCtx &P, DevCtx &H, cudaStream_t st, cu
   PCK(cudaEventRecord(e0, st));
   MSKC_LAUNCH(rerate_kernel, 148 * 8, 256, 0, st, P.ntiles, d_n);
   MSKC_LAUNCH(tile_rate_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.ntiles);
-  { int l_ = 0; if (sweep_totals(P, st, 4.0, 0.0, 0, &l_, err)) return -1; }
+  { int l_ = 0; if (sweep_totals(P, st, 0, &l_, err)) return -1; }
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
   PCK(cudaMemcpyAsync(&h_n, d_n, 8, cudaMemcpyDeviceToHost, st));

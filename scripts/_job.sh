@@ -1,6 +1,5 @@
 set -x
 mkdir -p gpurun_out
-python scripts/probe_bench.py --ept 4 --sweeps 16 --warm 24 2>&1 | tail -1
-python scripts/probe_bench.py --ept 4 --sweeps 16 --warm 24 2>&1 | tail -1
-( python -m pytest tests/test_replay_gpu.py tests/test_sampler_stats_gpu.py -m gpu -x -q ) 2>&1 | tail -2
-ncu --set full --clock-control none --import-source on -k regex:colour_step -s 80 -c 2 -o gpurun_out/colour_step3 -f python scripts/probe_bench.py --ept 4 --sweeps 8 --warm 24 > gpurun_out/ncu_full.log 2>&1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/slab_check.py --bx 4608 --by 4608 --rounds 3 2>&1 | grep -E "round|SEAMS|rank|mskc|Error|error" | head -20
+MSKC_HALO_NCCL=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/slab_check.py --bx 4608 --by 4608 --rounds 3 2>&1 | grep -E "round|SEAMS|rank|mskc|Error|error" | head -20
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 scripts/slab_check.py --bx 2304 --by 4608 --bz 48 --rounds 3 2>&1 | grep -E "round|SEAMS|rank|mskc|Error|error" | head -20

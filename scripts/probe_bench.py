@@ -21,7 +21,7 @@ ctx.set_rates(w["PtransE"], w["PtransD"], w["PtransAbs"], w["PtransDes"], w["Ptr
 ctx.init_flat(a.len1, walls=w["walls"], two_species=w["two_species"])
 for ept in a.ept:
     ctx.run_parallel(a.warm, events_per_tile=ept, seed=1)
-    r = ctx.run_parallel(a.sweeps, events_per_tile=ept, seed=2)
+    r = ctx.run_parallel(a.sweeps, events_per_tile=ept, seed=2, time_kernels=True)
     print(f"TEAM={os.environ.get('MSKC_TEAM','def')} ept={ept}: {r.events_done} ev, {r.kernel_ms:.2f} ms, {r.events_done / r.kernel_ms * 1e3:.4g} ev/s, su/ev={r.site_updates / max(r.events_done,1):.2f} "
           f"active={r.n_active} maxev={r.max_tile_events} us/colourstep={r.sweep_kernel_ms * 1e3 / (4 * a.sweeps):.1f} ev/tile/step={r.events_done / (a.sweeps * 4 * (a.box[0] // 48) * (a.box[1] // 48)):.2f}", flush=True)
 if a.tiles:

@@ -20,7 +20,7 @@ t0 = time.time(); ctx.init_flat(a.len1, walls=w["walls"], two_species=w["two_spe
 c, ms = ctx.census(); print("census ms", ms, "under", c.undercoordinated, "bulk", c.bulk, "GB/s", 4 * np.prod(a.box) / ms / 1e6)
 for ept in a.ept:
     r = ctx.run_parallel(3, events_per_tile=ept, seed=1)
-    r = ctx.run_parallel(a.sweeps, events_per_tile=ept, seed=2)
+    r = ctx.run_parallel(a.sweeps, events_per_tile=ept, seed=2, time_kernels=True)
     print(f"ept={ept}: {r.events_done} events, {r.kernel_ms:.2f} ms, {r.events_done / r.kernel_ms * 1e3:.4g} ev/s, {r.site_updates / r.kernel_ms * 1e3:.4g} su/s, "
           f"active={r.n_active} R={r.total_rate:.4g} t={r.time:.4g} launches={r.launches} maxev={r.max_tile_events} us/sweep={r.kernel_ms * 1e3 / a.sweeps:.1f}")
 c, ms = ctx.census(); print("census", c.undercoordinated, c.bulk, c.noepi_bulk, c.mean_height)

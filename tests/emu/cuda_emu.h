@@ -202,6 +202,7 @@ static inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { emu::exchange(mask,
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
 
 // ---- scalar intrinsics ------------------------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
