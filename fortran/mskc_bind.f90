@@ -192,6 +192,18 @@ module mskc_bind
       import :: c_int, c_ptr
       type(c_ptr), value :: h, c, kernel_ms
     end function
+    integer(c_int) function mskc_set_temperature_u16(h, T) bind(C, name="mskc_set_temperature_u16")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, T
+    end function
+    integer(c_int) function mskc_download_phases(h, phases) bind(C, name="mskc_download_phases")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, phases
+    end function
+    integer(c_int) function mskc_last_dense_ms(h, ms) bind(C, name="mskc_last_dense_ms")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: h, ms
+    end function
     integer(c_int) function mskc_replay_teams(h, n, site_xyz, event, arm, tree_root, n_iterations, n_shared) bind(C, name="mskc_replay_teams")
       import :: c_int, c_ptr, c_int64_t, c_double
       type(c_ptr), value :: h, site_xyz, event, arm, n_iterations, n_shared

@@ -186,6 +186,14 @@ int mskc_rerate_all(mskc_ctx *h, int64_t *n_sites, double *total_rate, float *ke
 /* Replaces: initial/SetT.f:25-50 -- integer kelvin per cell, [lenz][leny*lenx], value 10 = wall
  * (left untouched).  Writes bits 9..21 of every lattice word on the device. */
 int mskc_set_temperature(mskc_ctx *h, const int32_t *T);
+/* the same field as 16-bit kelvin (the lattice word holds 13 bits): half the bytes over PCIe per coupling cycle */
+int mskc_set_temperature_u16(mskc_ctx *h, const uint16_t *T);
+/* Replaces: la/main.f:797-817 (the `c` array the socket's GETPHASES returns): per cell [lenz][leny*lenx] the coordination
+ * of an occupied cell, 10 for a wall, 0 otherwise -- computed on the device, one byte per cell comes down instead of
+ * the whole lattice */
+int mskc_download_phases(mskc_ctx *h, uint8_t *phases);
+/* device time (ms, CUDA events) of the dense kernel the last of the three calls above launched */
+int mskc_last_dense_ms(mskc_ctx *h, float *ms);
 
 /* Replaces: the module globals read by inpout/WriteMolMolXYZFile.f, the checkpoint writer
  * (main.f:385-403) and the Coor dump (main.f:407-430). */

@@ -69,7 +69,7 @@ SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
            "mskc_replay_events", "mskc_download_active", "mskc_download_bonds",
-           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame", "mskc_check_flags", "mskc_replay_teams"]
+           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame", "mskc_check_flags", "mskc_replay_teams", "mskc_set_temperature_u16", "mskc_download_phases", "mskc_last_dense_ms"]
 
 
 def load_library():
@@ -115,6 +115,9 @@ def load_library():
     lib.mskc_comm_unique_id.argtypes = [C.c_void_p]
     lib.mskc_comm_connect.argtypes = [vp, C.c_void_p]
     lib.mskc_extract_frame.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
+    lib.mskc_set_temperature_u16.argtypes = [vp, C.POINTER(C.c_uint16)]
+    lib.mskc_download_phases.argtypes = [vp, C.POINTER(C.c_uint8)]
+    lib.mskc_last_dense_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.mskc_replay_teams.argtypes = [vp, C.c_int64, i32p, i32p, i32p, C.c_double, i64p, i64p]
     lib.mskc_check_flags.argtypes = [vp, i64p, i64p, i64p, C.POINTER(C.c_float)]
     for s in SYMBOLS:
@@ -252,6 +255,22 @@ class Mskc:
         t = _i32(T).reshape(-1)
         assert t.size == self.LenZ * self.LenY * self.LenX
         self._ck(self.lib.mskc_set_temperature(self.h, _p(t, C.c_int32)))
+
+    def set_temperature_u16(self, T):
+        t = np.ascontiguousarray(T, dtype=np.uint16).reshape(-1)
+        assert t.size == self.LenZ * self.LenY * self.LenX
+        self._ck(self.lib.mskc_set_temperature_u16(self.h, t.ctypes.data_as(C.POINTER(C.c_uint16))))
+
+    def download_phases(self):
+        """la/main.f:806-814: coordination of occupied cells, 10 = wall, 0 elsewhere; [LenZ][LenY][LenX] uint8"""
+        p = np.empty((self.LenZ, self.LenY, self.LenX), np.uint8)
+        self._ck(self.lib.mskc_download_phases(self.h, p.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return p
+
+    def last_dense_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.mskc_last_dense_ms(self.h, C.byref(ms)))
+        return ms.value
 
     # -- the loop ----------------------------------------------------------------------------------
     def run_parity(self, max_iter=2100000000, max_time=1e8, exit_on_time=False, out_every=0, out_time=0.0, framecounter=0, event_budget=0) -> ParityResult:

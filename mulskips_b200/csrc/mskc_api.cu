@@ -48,6 +48,7 @@ struct mskc_ctx {
   int tree_variant = 0;
   double *d_la3_F = nullptr;
   int fork_occ = 0, fork_occ0 = 0;
+  float last_dense_ms = 0.0f;
 };
 
 // lattice words and event codes of the LaserAnnealing fork <-> the internal (mulskips-source) ones
@@ -799,8 +800,48 @@ extern "C" int mskc_set_temperature(mskc_ctx *h, const int32_t *T) {
   if (!h->d_stage) CK(cudaMalloc(&h->d_stage, n * 4));        // staging plane stack, kept for the next upload
   if (upload_consts(h)) return -1;
   CK(cudaMemcpyAsync(h->d_stage, T, n * 4, cudaMemcpyHostToDevice, h->stream));
-  MSKC_LAUNCH(set_temperature_kernel, 1184, 256, 0, h->stream, h->d_stage, (long long)n);
+  CK(cudaEventRecord(h->ev2, h->stream));
+  MSKC_LAUNCH(set_temperature_kernel<int32_t>, 148 * 8, 256, 0, h->stream, (const int32_t *)h->d_stage, (long long)n);
+  CK(cudaEventRecord(h->ev3, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_dense_ms, h->ev2, h->ev3));
+  return 0;
+}
+extern "C" int mskc_set_temperature_u16(mskc_ctx *h, const uint16_t *T) {
+  if (!h || !T) return set_err(h, "mskc_set_temperature_u16: NULL argument");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  size_t n = (size_t)D.LX * D.LY * D.LZ;
+  if (!h->d_stage) CK(cudaMalloc(&h->d_stage, n * 4));
+  if (upload_consts(h)) return -1;
+  CK(cudaMemcpyAsync(h->d_stage, T, n * 2, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->ev2, h->stream));
+  MSKC_LAUNCH(set_temperature_kernel<uint16_t>, 148 * 8, 256, 0, h->stream, (const uint16_t *)h->d_stage, (long long)n);
+  CK(cudaEventRecord(h->ev3, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_dense_ms, h->ev2, h->ev3));
+  return 0;
+}
+extern "C" int mskc_download_phases(mskc_ctx *h, uint8_t *phases) {
+  if (!h || !phases) return set_err(h, "mskc_download_phases: NULL argument");
+  if (!h->have_state) return set_err(h, "mskc_download_phases: no state");
+  CK(cudaSetDevice(h->device));
+  DevCtx &D = h->D;
+  size_t n = (size_t)D.LX * D.LY * D.LZ;
+  if (!h->d_stage) CK(cudaMalloc(&h->d_stage, n * 4));
+  if (upload_consts(h)) return -1;
+  CK(cudaEventRecord(h->ev2, h->stream));
+  MSKC_LAUNCH(phases_kernel, 148 * 8, 256, 0, h->stream, (unsigned char *)h->d_stage, (long long)n);
+  CK(cudaEventRecord(h->ev3, h->stream));
+  CK(cudaMemcpyAsync(phases, h->d_stage, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_dense_ms, h->ev2, h->ev3));
+  return 0;
+}
+// device time of the last dense helper kernel (mskc_set_temperature*, mskc_download_phases), for the roofline in bench.py
+extern "C" int mskc_last_dense_ms(mskc_ctx *h, float *ms) {
+  if (!h || !ms) return set_err(h, "mskc_last_dense_ms: NULL argument");
+  *ms = h->last_dense_ms;
   return 0;
 }
 

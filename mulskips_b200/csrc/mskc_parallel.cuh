@@ -654,9 +654,8 @@ __global__ void __launch_bounds__(256) rerate_kernel(int ntiles, unsigned long l
 // coordination in their lattice word) -- Get_Prob.f:216-291 as one streaming pass over bonds[] (8 B/cell)
 __global__ void __launch_bounds__(256) census_flags_kernel(int check, unsigned long long *out /* [3]: sites, flag mismatches, coordination mismatches */) {
   unsigned long long nsite = 0, nbad = 0, ncoor = 0;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < D.ncell; c += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long b = D.bonds[c];
-    if (b == 0ull) continue;
+  auto one = [&](unsigned long long b, long long c) {
+    if (b == 0ull) return;
     const uint32_t w = D.state[c];
     const P3 q = cell_xyz(c);
     const unsigned fl = census_flags(q, w, b);
@@ -669,7 +668,17 @@ __global__ void __launch_bounds__(256) census_flags_kernel(int check, unsigned l
     for (int i = 0; i < 4; i++) { const unsigned f = fld(b, i); if (f && (unsigned)(q.z + cdz(f)) > (unsigned)D.LZ) inside = false; }
     const unsigned nz = (fl | (fl >> 1)) & 0x55u;
     if (inside && w_cov(w) != 113 && __popc(nz) != w_coor(w)) ncoor++;
+  };
+  const long long n2 = D.ncell >> 1, stride = (long long)gridDim.x * blockDim.x;
+  const ulonglong2 *B2 = reinterpret_cast<const ulonglong2 *>(D.bonds);
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n2; q0 += 4 * stride) {      // four 128-bit loads in flight
+    ulonglong2 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const long long q = q0 + u * stride; v[u] = q < n2 ? B2[q] : make_ulonglong2(0ull, 0ull); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const long long c = 2 * (q0 + u * stride); one(v[u].x, c); one(v[u].y, c + 1); }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (D.ncell & 1)) one(D.bonds[D.ncell - 1], D.ncell - 1);
   for (int o = 16; o > 0; o >>= 1) { nsite += __shfl_down_sync(0xFFFFFFFFu, nsite, o); nbad += __shfl_down_sync(0xFFFFFFFFu, nbad, o); ncoor += __shfl_down_sync(0xFFFFFFFFu, ncoor, o); }
   if ((threadIdx.x & 31) == 0) { if (nsite) atomicAdd(&out[0], nsite); if (nbad) atomicAdd(&out[1], nbad); if (ncoor) atomicAdd(&out[2], ncoor); }
 }
@@ -689,12 +698,34 @@ __global__ void collect_bulk(uint32_t *out, long long cap, unsigned long long *c
     if (w_occ(w) && w_coor(w) == 4 && w_cov(w) != 113) { unsigned long long k = atomicAdd(cnt, 1ull); if ((long long)k < cap) out[k] = (uint32_t)c; }
   }
 }
-// initial/SetT.f:36-46
-__global__ void set_temperature_kernel(const int32_t *T, long long n) {
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x) {
-    int t = T[c];
-    if (t != 10) D.state[c] = MVBITS(D.state[c], t, LenT, PosT);
+// initial/SetT.f:36-46: bits 9-21 of every word := T (10 = wall, left alone).  Four cells per thread and iteration
+// (128-bit loads of the field and the words); TT = int32 (the reference's array) or uint16 (half the upload)
+__device__ __forceinline__ uint32_t with_T(uint32_t w, int t) { return t != 10 ? MVBITS(w, t, LenT, PosT) : w; }
+template <class TT>
+__global__ void __launch_bounds__(256) set_temperature_kernel(const TT *T, long long n) {
+  const long long n4 = n >> 2;
+  uint4 *S4 = reinterpret_cast<uint4 *>(D.state);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    int t0, t1, t2, t3;
+    if (sizeof(TT) == 4) { const uint4 tv = reinterpret_cast<const uint4 *>(T)[q]; t0 = (int)tv.x; t1 = (int)tv.y; t2 = (int)tv.z; t3 = (int)tv.w; }
+    else { const uint2 tv = reinterpret_cast<const uint2 *>(T)[q]; t0 = (int)(tv.x & 0xFFFFu); t1 = (int)(tv.x >> 16); t2 = (int)(tv.y & 0xFFFFu); t3 = (int)(tv.y >> 16); }
+    uint4 v = S4[q];
+    v.x = with_T(v.x, t0); v.y = with_T(v.y, t1); v.z = with_T(v.z, t2); v.w = with_T(v.w, t3);
+    S4[q] = v;
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (long long c = n4 << 2; c < n; c++) D.state[c] = with_T(D.state[c], (int)T[c]);
+}
+// the phase array of the laser-annealing coupling (la/main.f:806-814): coordination of every occupied cell, 10 for a
+// wall, 0 elsewhere -- one byte per cell instead of the whole lattice word
+__global__ void __launch_bounds__(256) phases_kernel(unsigned char *out, long long n) {
+  const long long n4 = n >> 2;
+  const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
+  auto ph = [](uint32_t w) -> uint32_t { return w_occ(w) ? (w_cov(w) == 113 ? 10u : (uint32_t)w_coor(w)) : 0u; };
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = S4[q];
+    reinterpret_cast<uint32_t *>(out)[q] = ph(v.x) | (ph(v.y) << 8) | (ph(v.z) << 16) | (ph(v.w) << 24);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (long long c = n4 << 2; c < n; c++) out[c] = (unsigned char)ph(D.state[c]);
 }
 __device__ __forceinline__ bool is_cubic_site(int x, int y, int z, int &kind) {
   if (x % 3 || y % 3 || z % 3) return false;
@@ -712,30 +743,37 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
   const long long n4 = D.ncell >> 2;
   const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
   const long long plane = (long long)D.LX * D.LY;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
-    uint4 v = S4[q];
-    uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto one = [&](uint32_t w, long long c) {
+    if (w == 0) return;
+    if (V.halo) { const int x = (int)(c % D.LX); if (x < TILE || x >= D.LX - TILE) return; }      // halo columns belong to the neighbours
+    const int cov = w_cov(w);
+    if (cov == 113) { nWall++; return; }
+    // plane ranges as the reference scans them: census 1 (atoms with coordination <= 3, coverage sites) over planes
+    // 1..LenZ-1 (WriteMolMolXYZFile.f:77-92), census 2 (non-epitaxial bulk) over planes 0..LenZ-1 (:95-119)
+    const int z = (int)(c / plane);
+    if (w_occ(w)) {
+      nOcc++;
+      if (w_coor(w) <= 3) { if (z >= 1 && z <= D.LZ - 1) { nUnder++; hz += z; hz2 += (double)z * z; } }
+      else if (w_coor(w) == 4) {
+        nBulk++;
+        int r = (int)(c - (long long)z * plane), y = r / D.LX, x = r - y * D.LX, kind;
+        if (z <= D.LZ - 1 && !is_cubic_site(x, y, z, kind)) nNoEpi++;
+      }
+    } else if (cov != 0 && z >= 1 && z <= D.LZ - 1) nCov++;
+  };
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += 4 * stride) {      // four 128-bit loads in flight
+    uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      uint32_t w = ww[k];
-      if (w == 0) continue;
-      if (V.halo) { const int x = (int)((4 * q + k) % D.LX); if (x < TILE || x >= D.LX - TILE) continue; }      // halo columns belong to the neighbours
-      int cov = w_cov(w);
-      if (cov == 113) { nWall++; continue; }
-      // plane ranges as the reference scans them: census 1 (atoms with coordination <= 3, coverage sites) over planes
-      // 1..LenZ-1 (WriteMolMolXYZFile.f:77-92), census 2 (non-epitaxial bulk) over planes 0..LenZ-1 (:95-119)
-      const long long c = 4 * q + k; const int z = (int)(c / plane);
-      if (w_occ(w)) {
-        nOcc++;
-        if (w_coor(w) <= 3) { if (z >= 1 && z <= D.LZ - 1) { nUnder++; hz += z; hz2 += (double)z * z; } }
-        else if (w_coor(w) == 4) {
-          nBulk++;
-          int r = (int)(c - (long long)z * plane), y = r / D.LX, x = r - y * D.LX, kind;
-          if (z <= D.LZ - 1 && !is_cubic_site(x, y, z, kind)) nNoEpi++;
-        }
-      } else if (cov != 0 && z >= 1 && z <= D.LZ - 1) nCov++;
+    for (int u = 0; u < 4; u++) { const long long q = q0 + u * stride; v[u] = q < n4 ? S4[q] : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
+      const long long c = 4 * (q0 + u * stride);
+      one(v[u].x, c); one(v[u].y, c + 1); one(v[u].z, c + 2); one(v[u].w, c + 3);
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (long long c = n4 << 2; c < D.ncell; c++) one(D.state[c], c);
   unsigned long long vals[6] = {nUnder, nCov, nNoEpi, nBulk, nOcc, nWall};
   for (int k = 0; k < 6; k++) {
     unsigned long long v = vals[k];
@@ -746,39 +784,59 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
   if ((threadIdx.x & 31) == 0 && (hz != 0 || hz2 != 0)) { atomicAdd(&hsum[0], hz); atomicAdd(&hsum[1], hz2); }
 }
 
-// Frame extraction (the output scans of inpout/WriteMolMolXYZFile.f:130-215 fused into one streaming pass, 128-bit
-// loads, 4 B/cell of HBM traffic): every cell the reference's frame writers print -- under-coordinated atoms
-// (.xyz), coverage sites (.xyz), non-epitaxial 4-coordinated atoms (_d.xyz) -- is appended as (cell, word) to a
-// compact list with warp-aggregated atomics; the host sorts by cell to get the reference's z,y,x order.
+// Frame extraction (the output scans of inpout/WriteMolMolXYZFile.f:130-215 fused into one streaming pass, 4 B/cell of
+// HBM traffic): every cell the reference's frame writers print -- under-coordinated atoms (.xyz), coverage sites (.xyz),
+// non-epitaxial 4-coordinated atoms (_d.xyz) -- is appended as (cell, word) to a compact list; the host sorts by cell to
+// get the reference's z,y,x order.  Four 128-bit loads are in flight per thread; a thread keeps a 16-bit hit mask of its
+// sixteen words and the warp-aggregated compaction runs only where some lane of the warp has a hit (the printed cells are
+// ~1e-3 of the lattice).
+__device__ __forceinline__ bool frame_hit(uint32_t w, uint32_t c, unsigned plane) {
+  if (w == 0u || w_cov(w) == 113) return false;
+  if (!w_occ(w)) return w_cov(w) != 0;
+  if (w_coor(w) <= 3) return true;
+  if (w_coor(w) != 4) return false;
+  const unsigned z = c / plane, r = c - z * plane, y = r / (unsigned)D.LX, x = r - y * (unsigned)D.LX; int kind;
+  return !is_cubic_site((int)x, (int)y, (int)z, kind);
+}
 __global__ void __launch_bounds__(256) frame_extract_kernel(uint32_t *cells, uint32_t *words, unsigned long long cap, unsigned long long *count) {
   const long long n4 = D.ncell >> 2;
   const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
   const unsigned plane = (unsigned)D.LX * (unsigned)D.LY;
   const int lane = threadIdx.x & 31;
-  for (long long q0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x - lane); q0 < n4; q0 += (long long)gridDim.x * blockDim.x) {
-    const long long q = q0 + lane;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q < n4) v = S4[q];
-    const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; q0 < n4; q0 += 4 * stride) {
+    uint4 v[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t w = ww[k];
-      bool hit = false;
-      if (w != 0 && w_cov(w) != 113) {
-        const uint32_t c = (uint32_t)(4 * q + k);
-        if (w_occ(w)) {
-          if (w_coor(w) <= 3) hit = true;
-          else if (w_coor(w) == 4) { const unsigned z = c / plane, r = c - z * plane, y = r / (unsigned)D.LX, x = r - y * (unsigned)D.LX; int kind; hit = !is_cubic_site((int)x, (int)y, (int)z, kind); }
-        } else hit = w_cov(w) != 0;
-        if (hit && V.halo) { const unsigned x = c % (unsigned)D.LX; if (x < (unsigned)TILE || x >= (unsigned)(D.LX - TILE)) hit = false; }
+    for (int u = 0; u < 4; u++) { const long long q = q0 + lane + u * stride; v[u] = q < n4 ? S4[q] : make_uint4(0, 0, 0, 0); }
+    unsigned hits = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t c0 = (uint32_t)(4 * (q0 + lane + u * stride));
+      if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
+      hits |= (frame_hit(v[u].x, c0, plane) ? 1u : 0u) << (4 * u) | (frame_hit(v[u].y, c0 + 1, plane) ? 2u : 0u) << (4 * u) |
+              (frame_hit(v[u].z, c0 + 2, plane) ? 4u : 0u) << (4 * u) | (frame_hit(v[u].w, c0 + 3, plane) ? 8u : 0u) << (4 * u);
+    }
+    if (V.halo && hits) {                                 // halo columns belong to the neighbours
+#pragma unroll
+      for (int k = 0; k < 16; k++) if ((hits >> k) & 1u) {
+        const unsigned x = (unsigned)((4 * (q0 + lane + (k >> 2) * stride) + (k & 3)) % (unsigned)D.LX);
+        if (x < (unsigned)TILE || x >= (unsigned)(D.LX - TILE)) hits &= ~(1u << k);
       }
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-      if (m) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (hit) { const unsigned long long i = base + __popc(m & ((1u << lane) - 1u)); if (i < cap) { cells[i] = (uint32_t)(4 * q + k); words[i] = w; } }
-      }
+    }
+    if (!__any_sync(0xFFFFFFFFu, hits != 0u)) continue;
+    const int mine = __popc(hits);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0) + (unsigned long long)(incl - mine);
+    for (int k = 0; k < 16; k++) if ((hits >> k) & 1u) {
+      const uint4 vv = v[k >> 2]; const int j = k & 3;
+      const uint32_t w = j == 0 ? vv.x : (j == 1 ? vv.y : (j == 2 ? vv.z : vv.w));
+      if (base < cap) { cells[base] = (uint32_t)(4 * (q0 + lane + (k >> 2) * stride) + j); words[base] = w; }
+      base++;
     }
   }
 }

@@ -18,15 +18,20 @@ class OrcTrace(C.Structure):
                 ("tree1", C.c_double), ("time", C.c_double)]
 
 
-def build_oracle():
+def build_oracle(native=False):
+    """native=True: additionally build oracle/libmskc_oracle_native.so (-march=native) ON THIS machine and make it the library
+    load_oracle() picks (bench.py's CPU arm; the default library is built for a portable target because it travels)"""
     subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    if native:
+        subprocess.run(["make", "-s", "-C", ORACLE_DIR, "native"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        os.environ["MSKC_ORACLE_LIB"] = os.path.join(ORACLE_DIR, "libmskc_oracle_native.so")
 
 
 def load_oracle():
     global _LIB
     if _LIB is not None:
         return _LIB
-    p = os.path.join(ORACLE_DIR, "libmskc_oracle.so")
+    p = os.environ.get("MSKC_ORACLE_LIB") or os.path.join(ORACLE_DIR, "libmskc_oracle.so")
     if not os.path.exists(p):
         build_oracle()
     lib = C.CDLL(p)

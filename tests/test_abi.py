@@ -57,8 +57,8 @@ def test_struct_sizes(tmp_path):
 
 def test_no_cpu_fallback(lib):
     import torch
-    if torch.cuda.is_available():
-        pytest.skip("GPU present")
+    if torch.cuda.is_available() or os.environ.get("MSKC_EMU") == "1":
+        pytest.skip("GPU present (or the SIMT-emulated library was selected explicitly)")
     from mulskips_b200 import Mskc, MskcError
     with pytest.raises(MskcError) as e:
         Mskc(96, 96, 96, [14])

@@ -183,3 +183,33 @@ def test_census_matches_frame_writer(tmp_path, case, box, lens, nev):
     assert cs.occupied == int(np.count_nonzero((occ == 1) & (cov != 113)))
     assert cs.bulk == int(np.count_nonzero((occ == 1) & (cov != 113) & (coor == 4)))
     ctx.close(); orc.close()
+
+
+def test_temperature_u16_and_phases(tmp_path):
+    """mskc_set_temperature_u16 writes the same lattice words as the int32 form (initial/SetT.f:36-46: bits 9-21, value 10 = wall,
+    untouched), and mskc_download_phases is the socket loop's phase array (la/main.f:806-814) computed on the device"""
+    from mulskips_b200 import Mskc
+    box = (96, 96, 96)
+    start = make_la_case(str(tmp_path), box=box, lennuc=18.0)
+    orc = Oracle(*box, start)
+    orc.setup()
+    orc.run(3000)
+    lc, lv = orc.species()
+    a, b = Mskc(*box, lc, lv), Mskc(*box, lc, lv)
+    upload_oracle_state(orc, a, trange=(1500, 1800))
+    upload_oracle_state(orc, b, trange=(1500, 1800))
+    rng = np.random.default_rng(5)
+    T = (1600 + rng.integers(0, 150, size=(box[2], box[1] * box[0]))).astype(np.int32)
+    T[rng.random(T.shape) < 0.05] = 10                               # "wall": the cell keeps its temperature bits
+    a.set_temperature(T)
+    b.set_temperature_u16(T.astype(np.uint16))
+    La, Lb = a.download_lattice(), b.download_lattice()
+    assert np.array_equal(La, Lb)
+    want = np.where(T.reshape(box[2], box[1], box[0]) == 10, (orc.lattcoo()[:-1] >> 9) & 8191, T.reshape(box[2], box[1], box[0]))
+    assert np.array_equal((La[:-1] >> 9) & 8191, want)
+    L = La[:-1]
+    occ, coor, cov = (L >> 23) & 1, (L >> 24) & 7, L & 255
+    ph = np.where(occ == 1, np.where(cov == 113, 10, coor), 0).astype(np.uint8)
+    assert np.array_equal(a.download_phases(), ph)
+    assert a.last_dense_ms() >= 0.0
+    a.close(); b.close(); orc.close()
