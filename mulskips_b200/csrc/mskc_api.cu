@@ -4,6 +4,7 @@
 #include "mskc_device.cuh"
 #include "mskc_parity.cuh"
 #include "mskc_parallel.cuh"
+#include "mskc_parity_coop.cuh"
 #include <cmath>
 #include <cstdarg>
 #include <cstddef>
@@ -624,7 +625,10 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   ParityArgs A{};
   A.max_iter = a->max_iter; A.out_every = a->out_every; A.framecounter = a->framecounter; A.max_time = a->max_time; A.out_time = a->out_time;
   A.exit_on_time = a->exit_on_time;
+  // the warp-cooperative loop (mskc_parity_coop.cuh) is the default; MSKC_PARITY_SERIAL=1 selects the one-thread kernel
+  const bool serial = getenv("MSKC_PARITY_SERIAL") != nullptr;
   CK(cudaFuncSetAttribute(parity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ParShared)));
+  CK(cudaFuncSetAttribute(parity_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PcShared)));
   // The kernel is launched in slices so that a single launch stays well below any watchdog.
   const long long slice = 2000000;
   long long remaining = a->event_budget > 0 ? a->event_budget : -1;
@@ -633,7 +637,8 @@ extern "C" int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_pari
   while (true) {
     A.event_budget = (remaining < 0 || remaining > slice) ? slice : remaining;
     CK(cudaEventRecord(h->ev0, h->stream));
-    MSKC_LAUNCH(parity_kernel, 1, 32, sizeof(ParShared), h->stream, A);
+    if (serial) MSKC_LAUNCH(parity_kernel, 1, 32, sizeof(ParShared), h->stream, A);
+    else MSKC_LAUNCH(parity_coop_kernel, 1, 32, sizeof(PcShared), h->stream, A);
     CK(cudaEventRecord(h->ev1, h->stream));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&h->h_ps, h->d_ps, sizeof(ParityState), cudaMemcpyDeviceToHost, h->stream));

@@ -131,7 +131,17 @@ __device__ __forceinline__ unsigned census_flags(const P3 Q, const uint32_t wQ, 
 // differ from the stored ones, Evaporation.f:123).  Deposition/adsorption sites get EV_DRAW: the species
 // is drawn when the event fires (Get_Prob.f:160-179 draws it here; same distribution).
 // FEAT: bit 0 = coverage species exist (NCov > 0), bit 1 = per-kelvin rate tables (LA rate law or 'ST' field); compiled out otherwise (hot-loop code size)
-enum { F_COV = 1, F_LA = 2 };
+enum { F_COV = 1, F_LA = 2, F_PAR = 4 };
+// F_PAR: the event is applied for the serial-parity loop (mskc_parity_coop.cuh): no census flags / list slots are touched
+// (aux[] may not exist), rates come from the full census with the reference's wrong-list quirk (below), and instead of the
+// tile-list commit every lane hands its request back to the caller, which commits them in the reference's order.
+struct CoopReq {
+  int act, ev, Coor, self, needs_root, arm_used; double p; uint32_t c, w;
+  int Occ, Sp, Cov; P3 N; unsigned long long rb;       // what the site was rated with (the caller may have to rate it again, see mskc_parity_coop.cuh)
+};
+// Get_Prob.f:266-269 looks a coverage neighbour on a 4-coordinated empty site up in ListAdAtom at the vacancy's index
+// (defined by the parity kernel, which owns the lists)
+__device__ bool par_cov_void_recipr(P3 n, uint32_t cn, P3 me);
 // full-census form (coverage runs, the dense re-rate pass): reads the four neighbours' words and bond lists
 template <int FEAT>
 __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, P3 Q, uint32_t cQ, unsigned long long rb, double root, int &ev, double &p, unsigned *flags_out = nullptr) {
@@ -173,9 +183,9 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
     if (w_occ(w)) {
       if (CovN == 113) { N_wall++; fl |= 1u << (2 * i); }
       else if (rec) { const int s = w_sp(w); N_Si += (s == 1); N_C += (s == 2); N_B += (s == 3); fl |= (unsigned)(s & 3) << (2 * i); }
-    } else if ((FEAT & F_COV) && CovN != 0 && rec && w_coor(w) < 4) {
-      // (coverage on a 4-coordinated empty site: the reference looks it up in the wrong list, see
-      // ParityPol::cov_void_recipr, and in effect never counts it)
+    } else if ((FEAT & F_COV) && CovN != 0 && (((FEAT & F_PAR) && w_coor(w) >= 4) ? par_cov_void_recipr(dec_bond(Q, f), ccell(dec_bond(Q, f)), Q) : (rec && w_coor(w) < 4))) {
+      // (coverage on a 4-coordinated empty site: the reference looks it up in the wrong list -- the serial-parity loop
+      // reproduces that lookup, the sampler in effect never counts such a neighbour)
       const int iCov = cov_index(CovN);
       if (iCov == 0 || iCov > D.NCov) { fail_cell(E_COVLIST, cQ); return; }
       cv0 += (iCov == 1); cv1 += (iCov == 2); cv2 += (iCov == 3);
@@ -186,7 +196,7 @@ __device__ __forceinline__ void coop_rate(int Occ, int NSiC, int Cov, int Coor, 
   if (ncry != Coor) { fail(E_CENSUS, Q.x, Q.y, Q.z, Coor * 16 + ncry); return; }
   if (ncry > 3) return;
   ev = 4;
-  if (ncry == 0) { p = (double)100000.f * root; return; }
+  if (ncry == 0) { p = (FEAT & F_PAR) ? -1.0 : (double)100000.f * root; return; }     // (F_PAR: the caller multiplies Tree(1) as of that moment)
   const int idx = IDXE(NSiC, N_Si + N_wall, N_C, N_B, cv0 & 3, cv1 & 3, cv2 & 3);
   p = (FEAT & F_LA) ? rate_E(idx, T) : __ldg(&D.PE[idx]);
 }
@@ -214,6 +224,22 @@ __device__ __forceinline__ void flag_rate(int Occ, int NSiC, int Coor, uint32_t 
   if (ncry == 0) { p = (double)100000.f * root; return; }
   const int idx = IDXE(NSiC, n1, n2, n3, 0, 0, 0);
   p = (FEAT & F_LA) ? rate_E(idx, T) : __ldg(&D.PE[idx]);
+}
+
+// Evaporation.f:95-122 on bond codes, from the lattice itself (serial-parity path, which keeps no census flags): keep the
+// occupied, under-coordinated, reciprocal neighbour (the last one that qualifies), forget the others.
+__device__ __noinline__ unsigned long long coop_compact(P3 me, unsigned long long old) {
+  unsigned keep = 0u; bool found = false;
+  uint32_t w[4]; unsigned long long b[4]; P3 n[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { const uint32_t c = nbr(me, fld(old, j), n[j]); w[j] = D.state[c]; b[j] = D.bonds[c]; }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const unsigned f = fld(old, j);
+    if (w_occ(w[j]) && w_coor(w[j]) <= 3 && w_cov(w[j]) != 113 && recip_f(n[j], b[j], me, f)) { keep = f; found = true; }
+  }
+  if (!found) fail(E_STALE_NBUFF, me.x, me.y, me.z);
+  return (unsigned long long)keep;
 }
 
 // double-precision fallback of the bond fixing (cold): serial find_sn on absolute coordinates
@@ -310,14 +336,14 @@ __device__ __forceinline__ int draw_dep_abs(int Coor, uint32_t wS, uint32_t cS, 
 
 template <int TEAM, int FEAT, class Lists>
 __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const P3 S, const uint32_t cS, int Itrans, const double root,
-                                          const double arm_u, const int forced_arm, CoopCounters &K, const double species_u = 0.5) {
+                                          const double arm_u, const int forced_arm, CoopCounters &K, const double species_u = 0.5, CoopReq *rq = nullptr) {
   enum { DEP = 0, EVAP = 1, DES = 2, ABS = 3 };
   constexpr unsigned FULL = 0xFFFFFFFFu;
   constexpr unsigned tm = TEAM == 32 ? 0xFFFFFFFFu : ((1u << (TEAM & 31)) - 1u);
   const int tshift = (int)(threadIdx.x & 31u) - tl;         // first lane of the team inside the warp
   // ---- S's record (team-uniform: the lanes of a team load the same three words) ------------------------------
   uint32_t wS = 0u, aS = 0u; unsigned long long bS = 0ull;
-  if (go) { wS = D.state[cS]; bS = D.bonds[cS]; aS = D.aux[cS]; }
+  if (go) { wS = D.state[cS]; bS = D.bonds[cS]; if (!(FEAT & F_PAR)) aS = D.aux[cS]; }
   const int c0 = w_coor(wS);
   if (Itrans == EV_DRAW) Itrans = go ? draw_dep_abs<FEAT>(c0, wS, cS, species_u) : 4;
   const int kind = Itrans <= 3 ? DEP : (Itrans == 4 ? EVAP : (Itrans == 5 ? DES : ABS));
@@ -376,6 +402,7 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
     const int CoorZig = __shfl_sync(FULL, cc, 3, TEAM) + __shfl_sync(FULL, cc, 4, TEAM) + __shfl_sync(FULL, cc, 5, TEAM);
     if (fix) {
       bool IF_Arm = CoorZig < CoorArm || (CoorZig == CoorArm && !(arm_u <= D.PZig));
+      if ((FEAT & F_PAR) && rq) rq->arm_used = CoorZig == CoorArm;          // IF_Arm_Choice.f:46-50 drew a uniform
       if (forced_arm >= 0) IF_Arm = forced_arm != 0;
       bS = (unsigned long long)e;
 #pragma unroll
@@ -398,7 +425,7 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
   if (go && tl < 4 && !(kind == DES && c0 == 1 && tl > 0)) {    // desorption.f:54-81: a 1-coordinated site looks at bond 1 only
     const unsigned f = fld(bS, tl);
     P3 N; const uint32_t cN = nbr(S, f, N);
-    const uint32_t wN = D.state[cN], aN = D.aux[cN];
+    const uint32_t wN = D.state[cN], aN = (FEAT & F_PAR) ? 0u : D.aux[cN];
     unsigned long long bN = D.bonds[cN];
     const int Occ = w_occ(wN), CovN = w_cov(wN), CoorNN = w_coor(wN), spN = w_sp(wN) & 3;
     const bool rec = recip_f(N, bN, S, f);
@@ -435,6 +462,8 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
     } else if (spc == PA_ORPHAN) {                         // Evaporation.f:62-79: an orphaned empty site leaves the lattice
       wNew = D.keepT ? (wN & (((1u << LenT) - 1u) << PosT)) : 0u;
       bN = 0ull; qCov = 0;
+    } else if ((FEAT & F_PAR) && spc == PA_COMPACT) {      // (no census flags on the serial-parity path: look at the four neighbours)
+      bN = coop_compact(N, bN);
     } else if (spc == PA_COMPACT) {                        // Evaporation.f:80-128: back to one bond: keep the occupied reciprocal neighbour that is left
       const unsigned others = flN & ~jmask;
       int k = -1;
@@ -534,7 +563,7 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
     if (FEAT & F_COV) {
       unsigned cf = qfl;
       coop_rate<FEAT>(qOcc, qSp, qCov, qCoor, qN, qc, qrb, root, ev, p, &cf);
-      if (qOcc && cf != qfl && !(qCov > 0 && qCov < 113)) fail(E_FLAGS, qN.x, qN.y, qN.z, (int)(cf | (qfl << 8)));
+      if (!(FEAT & F_PAR) && qOcc && cf != qfl && !(qCov > 0 && qCov < 113)) fail(E_FLAGS, qN.x, qN.y, qN.z, (int)(cf | (qfl << 8)));
     } else flag_rate<FEAT>(qOcc, qSp, qCoor, qw, qc, qfl, nb1, root, ev, p);
     K.nsu++;
   }
@@ -543,6 +572,12 @@ __device__ __forceinline__ int coop_event(Lists &L, const int tl, bool go, const
   if (go && tl == 4) {
     if (!(FEAT & F_COV) || wS2 != wS) D.state[cS] = wS2;
     if (act == A_ERASE) D.bonds[cS] = 0ull;
+  }
+  if ((FEAT & F_PAR) && rq) {                              // the caller commits (reference order: neighbours 1..4, then the site itself)
+    rq->act = act; rq->ev = ev; rq->p = p; rq->c = qc; rq->w = qw; rq->Coor = qCoor; rq->self = go && tl == 4; rq->needs_root = p < 0.0;
+    rq->Occ = qOcc; rq->Sp = qSp; rq->Cov = qCov; rq->N = qN; rq->rb = qrb;
+    __syncwarp();
+    return Itrans;
   }
   // ---- phase C: census flags, list bookkeeping (mskc_device.cuh: rq_commit) -------------------------------------------
   if (act >= 0) {
