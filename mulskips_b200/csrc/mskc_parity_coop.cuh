@@ -32,11 +32,11 @@ enum { PC_MAXLEV = 24, PC_UBUF = 64, PC_MIRROR = 24800 /* doubles of tree mirror
 struct PcShared {
   int ma[56]; int inext, inextp, iff, idum;      // ran3 state (random.f SAVEd variables)
   double ubuf[PC_UBUF];                          // uniforms produced ahead, ring buffer
-  int W[PC_MAXLEV], base[PC_MAXLEV];             // per tree level: nodes mirrored (a prefix), offset of the level in tree[]
+  int wl, nlev;                                  // mirrored leaf prefix, level of the leaves
   int NumAdAtom;                                 // for par_cov_void_recipr
   int pend[32];                                  // leaves written in this event (their root paths await the re-sum)
   int quirk[32];                                 // lane consulted the lists while rating (par_cov_void_recipr): its rate is re-evaluated at commit time
-  double tree[PC_MIRROR];
+  double __align__(16) tree[PC_MIRROR];
 };
 #ifndef MSKC_EMU
 extern __shared__ __align__(16) unsigned char pc_smem[];
@@ -45,9 +45,26 @@ __device__ __forceinline__ PcShared &PCS() { return *reinterpret_cast<PcShared *
 __device__ __forceinline__ PcShared &PCS() { return *reinterpret_cast<PcShared *>(emu::dyn_smem()); }
 #endif
 
-// node o of level L (level L has 2^L nodes; heap index 2^L + o)
-__device__ __forceinline__ double pc_ld(int L, int o) { const PcShared &s = PCS(); return o < s.W[L] ? s.tree[s.base[L] + o] : PV.Tree[(1 << L) + o]; }
-__device__ __forceinline__ void pc_st(int L, int o, double v) { PcShared &s = PCS(); if (o < s.W[L]) s.tree[s.base[L] + o] = v; else PV.Tree[(1 << L) + o] = v; }
+// Node o of level L (level L has 2^L nodes; heap index 2^L + o).  Mirrored: the first pc_W(L) nodes of every level -- the
+// ancestors of the first `wl` leaves -- at offset pc_base(L); both are arithmetic in (wl, nlev), no table look-up sits in
+// front of the shared-memory access (wl and nlev live in PcShared, uniform).  pc_base(L) = even(wl >> (nlev-L)) + 4L leaves
+// room for all lower levels (their widths halve), and keeps every (2o, 2o+1) child pair 16-byte aligned.
+__device__ __forceinline__ int pc_W(int L, int wl, int nlev) { return min(1 << L, ((wl >> (nlev - L)) + 3) & ~1); }
+__device__ __forceinline__ int pc_base(int L, int wl, int nlev) { return (((wl >> (nlev - L)) + 1) & ~1) + 4 * L; }
+__device__ __forceinline__ double pc_ld(int L, int o) {
+  const PcShared &s = PCS(); const int wl = s.wl, nlev = s.nlev;
+  return o < pc_W(L, wl, nlev) ? s.tree[pc_base(L, wl, nlev) + o] : PV.Tree[(1 << L) + o];
+}
+__device__ __forceinline__ void pc_st(int L, int o, double v) {
+  PcShared &s = PCS(); const int wl = s.wl, nlev = s.nlev;
+  if (o < pc_W(L, wl, nlev)) s.tree[pc_base(L, wl, nlev) + o] = v; else PV.Tree[(1 << L) + o] = v;
+}
+// both children (2o, 2o+1) of node o of level L-1, one 16-byte access
+__device__ __forceinline__ double2 pc_ld2(int L, int o2, int wl, int nlev) {
+  const PcShared &s = PCS();
+  if (o2 < pc_W(L, wl, nlev)) return *reinterpret_cast<const double2 *>(&s.tree[pc_base(L, wl, nlev) + o2]);
+  return *reinterpret_cast<const double2 *>(&PV.Tree[(1 << L) + o2]);
+}
 
 // Get_Prob.f:266-269 (see ParityPol::cov_void_recipr): the MC record that happens to have the vacancy's index
 __device__ __noinline__ bool par_cov_void_recipr(P3 n, uint32_t cn, P3 me) {
@@ -113,7 +130,7 @@ __device__ __forceinline__ void pc_flush(int lane, int nlev, int &npend) {
 #pragma unroll 1
   for (int L = nlev - 1; L >= 0; L--) {            // parents at level L of nodes at level L+1
     o >>= 1;
-    if (lane < n) pc_st(L, o, pc_ld(L + 1, 2 * o) + pc_ld(L + 1, 2 * o + 1));
+    if (lane < n) { const double2 ch = pc_ld2(L + 1, 2 * o, s.wl, nlev); pc_st(L, o, ch.x + ch.y); }
     __syncwarp();
   }
 }
@@ -126,20 +143,20 @@ __global__ void __launch_bounds__(32, 1) parity_coop_kernel(ParityArgs A) {
   PcShared &sh = PCS();
   ParityState &S = *PV.ps;
   const int nlev = PV.Levels - 1;                  // leaves live on level nlev
+  int mwl = 0;                                     // mirrored leaf prefix (uniform)
   // ---- mirror: the first W[L] nodes of every level (ancestors of the first PC_LEAVES leaves), W even so that siblings stay together
   {
     const int leaves = 1 << nlev;
     int wl = min(leaves, 12000);                   // largest leaf prefix whose ancestors fit the mirror
-    while (wl > 64) { int tot = 0; for (int L = 0; L <= nlev; L++) { int w = (wl >> (nlev - L)) + 2; w += w & 1; tot += min(w, 1 << L); } if (tot <= (int)PC_MIRROR) break; wl -= 500; }
+    while (wl > 64 && pc_base(nlev, wl, nlev) + pc_W(nlev, wl, nlev) > (int)PC_MIRROR) wl -= 500;
     if (lane == 0) {
-      int off = 0;
-      for (int L = 0; L <= nlev; L++) { int w = (wl >> (nlev - L)) + 2; w += w & 1; w = min(w, 1 << L); sh.W[L] = w; sh.base[L] = off; off += w; }
-      for (int L = nlev + 1; L < PC_MAXLEV; L++) { sh.W[L] = 0; sh.base[L] = off; }
+      sh.wl = wl; sh.nlev = nlev;
       for (int i = 0; i < 56; i++) sh.ma[i] = S.r_ma[i];
       sh.inext = S.r_inext; sh.inextp = S.r_inextp; sh.iff = S.r_iff; sh.idum = S.idum;
     }
     __syncwarp();
-    for (int L = 0; L <= nlev; L++) for (int o = lane; o < sh.W[L]; o += 32) sh.tree[sh.base[L] + o] = PV.Tree[(1 << L) + o];
+    mwl = sh.wl;
+    for (int L = 0; L <= nlev; L++) for (int o = lane; o < pc_W(L, sh.wl, nlev); o += 32) sh.tree[pc_base(L, sh.wl, nlev) + o] = PV.Tree[(1 << L) + o];
     __syncwarp();
   }
   // ---- loop state, uniform over the warp
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(32, 1) parity_coop_kernel(ParityArgs A) {
         if (runtype == 'T') { counter++; r = (double)NUMBERSLIST[nli]; nli = nli == 999 ? 0 : nli + 1; }
         else r = next_uniform();
         const double Patom = r * node;
-        const double left = pc_ld(lev + 1, 2 * o), right = pc_ld(lev + 1, 2 * o + 1);
+        const double2 ch = pc_ld2(lev + 1, 2 * o, mwl, nlev); const double left = ch.x, right = ch.y;
         if (left < Patom) { o = 2 * o + 1; node = right; } else { o = 2 * o; node = left; }
       }
       Ind = o + 1;
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(32, 1) parity_coop_kernel(ParityArgs A) {
   __syncwarp();
   pc_flush(lane, nlev, npend);
   // ---- write the mirror and the loop state back
-  for (int L = 0; L <= nlev; L++) for (int o = lane; o < sh.W[L]; o += 32) PV.Tree[(1 << L) + o] = sh.tree[sh.base[L] + o];
+  for (int L = 0; L <= nlev; L++) for (int o = lane; o < pc_W(L, sh.wl, nlev); o += 32) PV.Tree[(1 << L) + o] = sh.tree[pc_base(L, sh.wl, nlev) + o];
   if (lane == 0) {
     pc_ungenerate(uavail);
     S.Iter = Iter; S.Time = Time; S.framecounter = framecounter; S.counter = counter;

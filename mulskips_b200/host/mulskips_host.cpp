@@ -1180,6 +1180,19 @@ bool box_from_defsystem(const char *exe, int box[3]) {      // the line pymulski
   fclose(f); return ok;
 }
 
+// the line pymulskips rewrites in main.f when it is given a socket port ("      port = 31415", setuprun.py:524-545)
+int port_from_mainf(const char *exe) {
+  std::string p(exe); size_t k = p.find_last_of('/'); p = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/main.f";
+  FILE *f = fopen(p.c_str(), "r"); if (!f) return -1;
+  char line[1024]; int port = -1;
+  while (fgets(line, sizeof line, f)) {
+    if (line[0] == '!' || line[0] == 'c' || line[0] == 'C') continue;
+    const char *a = strstr(line, "port =");
+    if (a) { port = atoi(a + 6); break; }
+  }
+  fclose(f); return port > 0 ? port : -1;
+}
+
 }  // namespace
 
 // la/sockets/sockets.c + fsockets.f: 12-byte headers and INTEGER(4) arrays over a TCP connection to the python server
@@ -1203,12 +1216,14 @@ struct Wire {
 int main(int argc, char **argv) {
   Host H; Run R;
   int box[3] = {480, 480, 480}; bool parallel = false; double ept = 4.0; int device = 0; const char *start = "start.dat";
+  int mode = -1;                                                // -1: by RunType (below), 0: serial parity, 1: sublattice sampler
   bool have_box = false;
   const char *dump_state = nullptr;                             // --dump-state file: what is about to be uploaded, as text (tests compare it with the oracle's state)
   const char *sock_host = "localhost"; int sock_port = -1;     // la/main.f:102-131: -h hostname -p port => socket-driven run
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--box") && i + 3 < argc) { box[0] = atoi(argv[i + 1]); box[1] = atoi(argv[i + 2]); box[2] = atoi(argv[i + 3]); i += 3; have_box = true; }
-    else if (!strcmp(argv[i], "--parallel")) parallel = true;
+    else if (!strcmp(argv[i], "--parallel")) mode = 1;
+    else if (!strcmp(argv[i], "--parity") || !strcmp(argv[i], "--serial")) mode = 0;
     else if (!strcmp(argv[i], "--la-tree")) { H.la_tree = true; PosSi = 28; PosC = 29; PosSiC = 28; LenSiC = 2; EvEvap = 3; }
     else if (!strcmp(argv[i], "--events-per-tile") && i + 1 < argc) ept = atof(argv[++i]);
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
@@ -1216,10 +1231,11 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--dump-state") && i + 1 < argc) dump_state = argv[++i];
     else if (!strcmp(argv[i], "-h") && i + 1 < argc) sock_host = argv[++i];
     else if (!strcmp(argv[i], "-p") && i + 1 < argc) sock_port = atoi(argv[++i]);
-    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file]\n", argv[0]); return 2; }
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parity | --parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file]\n", argv[0]); return 2; }
   }
   if (!have_box) { if (const char *e = getenv("MSKC_BOX")) have_box = sscanf(e, "%d %d %d", &box[0], &box[1], &box[2]) == 3; }
   if (!have_box) box_from_defsystem(argv[0], box);
+  if (sock_port < 0 && H.la_tree) sock_port = port_from_mainf(argv[0]);
   H.LX = box[0]; H.LY = box[1]; H.LZ = box[2];
   bool by_time = false;
   float dev_ms = 0; long long events = 0;
@@ -1321,6 +1337,14 @@ int main(int argc, char **argv) {
   };
   // ---- the KMC loop between two calls of the host (main.f:304-371) ----
   auto kmc_loop = [&]() {
+  // Which loop runs when the command line does not say (pymulskips launches `mulskips.e` without arguments): RunType 'T'
+  // ("not so random: use this for regression tests", py/setuprun.py:344) and 'C' ask for the reference's own event sequence
+  // -> serial parity mode, bit-exact; RunType 'R' ("truly random", the production default of pymulskips) asks for a
+  // statistically faithful trajectory -> the synchronous-sublattice sampler, the mode that uses the GPU.  --parity /
+  // --parallel (or MSKC_MODE=parity|parallel) override; socket-driven runs and boxes that are not multiples of 48 stay serial.
+  if (mode < 0) { if (const char *e = getenv("MSKC_MODE")) mode = !strcmp(e, "parallel") ? 1 : (!strcmp(e, "parity") ? 0 : -1); }
+  if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
+  parallel = mode == 1;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;

@@ -35,6 +35,11 @@ def _tokens(log, key):
 
 
 def _run(exe, d, args=()):
+    # (the serial loop is asked for explicitly wherever files are compared byte for byte with the oracle's: without an
+    # option the host program picks the loop by RunType, see test_default_mode_follows_runtype)
+    if exe == EXE and "--parallel" not in args and "--auto" not in args:
+        args = ["--parity", *args]
+    args = [a for a in args if a != "--auto"]
     with open(d / "log.txt", "w") as out, open(d / "err.txt", "w") as err:
         rc = subprocess.run([exe, *args], cwd=d, stdout=out, stderr=err).returncode
     assert rc == 0, open(d / "log.txt").read()[-1500:] + open(d / "err.txt").read()[-1500:]
@@ -143,6 +148,16 @@ def test_reference_inputs_full_length(built, tmp_path, case):
     t = _tokens(g / "log.txt", "Iter, Time, Site")
     assert int(t[3]) == m["final_iter"] and [int(v) for v in t[5:8]] == m["final_site"] and float(t[4]) == float(m["final_time"])
     assert [int(v) for v in _tokens(g / "log.txt", "NatNvoidNad")[1:4]] == m["final_lists"]
+
+
+@pytest.mark.parametrize("runtype,mode", [("T", "serial-parity"), ("R", "sublattice-sampler")])
+def test_default_mode_follows_runtype(built, tmp_path, runtype, mode):
+    """pymulskips launches `mulskips.e` with no arguments (setuprun.py:414).  RunType T (regression: the reference's own
+    event sequence) -> serial parity loop; RunType R (production: "truly random") -> the sublattice sampler."""
+    make_start("surface", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=30000, outmolmol=30000, runtype=runtype)
+    _run(EXE, tmp_path, ["--auto", "--box", "96", "96", "240"])
+    assert f"({mode} mode)" in (tmp_path / "err.txt").read_text()
+    assert (tmp_path / "I00000001.xyz").exists()
 
 
 def test_checkpoint_restart(built, tmp_path):

@@ -108,3 +108,39 @@ def test_reference_socket_server_drives_the_host(tmp_path):
     assert "@ message to server: NEEDINIT" in log and "@ message to server: READY" in log
     assert "Setting input geometry from sockets" in log and "Setting temperatures in LattCoo from array received via sockets" in log
     assert (run / "I00000000.xyz").exists() and len((run / "I00000000.xyz").read_text().splitlines()) > 100
+
+
+def test_execpath_layout_with_reference_setup(tmp_path, monkeypatch):
+    """pymulskips needs `execpath` to hold modules/defsystem.f (whose LenX line it rewrites), main.f (whose port line it
+    rewrites), a makefile whose `make clean; make | tee make.log` says "Compilation terminated", and mulskips.e beside them
+    (pymulskips/setuprun.py:414-420,458-553).  mulskips_b200/execpath is that directory: the reference's OWN
+    setup_mulskips_src() is run on a copy of it, then the executable is launched the way run_mulskips() launches it
+    (`<execpath>/mulskips.e | tee log.txt` in the run directory) and frame 0 must come out at the rewritten box."""
+    import shutil
+    p = os.path.join(REF, "pymulskips", "setuprun.py")
+    if not os.path.exists(p):
+        pytest.skip("reference tree not mounted")
+    spec = importlib.util.spec_from_file_location("pymulskips_setuprun", p)
+    sr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sr)
+    execpath = tmp_path / "execpath"
+    shutil.copytree(os.path.join(ROOT, "mulskips_b200", "execpath"), execpath, ignore=shutil.ignore_patterns("mulskips.e", "make.log"))
+    monkeypatch.setenv("MSKC_ROOT", os.path.join(ROOT, "mulskips_b200"))      # the copy lives outside the package (see the makefile)
+    monkeypatch.setenv("PWD", str(tmp_path))                                  # compile_mulskips() returns to $PWD
+    monkeypatch.chdir(tmp_path)
+    sr.setup_mulskips_src(str(execpath), 96, 96, 240, socketport=31415)
+    assert "LenX=96, LenY=96, LenZ=240" in (execpath / "modules" / "defsystem.f").read_text()
+    assert "port = 31415" in (execpath / "main.f").read_text()
+    assert "Compilation terminated" in (execpath / "make.log").read_text()
+    assert (execpath / "mulskips.e").exists()
+    run = tmp_path / "run"
+    run.mkdir()
+    from cases import make_start
+    make_start("surface", str(run / "start.dat"), lens=(48, 0, 0), maxiter=1000, outmolmol=1000)
+    subprocess.run(f"{execpath}/mulskips.e | tee log.txt;", shell=True, cwd=run, capture_output=True)
+    f0 = run / "I00000000.xyz"
+    assert f0.exists()
+    an = _analyze()
+    sf = 0.38583333333333333
+    assert an.get_box_sides(str(f0)) == pytest.approx([96 * sf, 96 * sf, 240 * sf], rel=1e-6)
+    assert int(open(f0).readline().split()[0]) == 2 * (96 // 12) * (96 // 12)           # one filled surface layer of the 96 x 96 box
