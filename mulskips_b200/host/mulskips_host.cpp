@@ -52,6 +52,7 @@ struct Host {
   int NCrystal = 0, NCov = 0, ListCrystal[3] = {0, 0, 0}, ListCov[3] = {0, 0, 0};
   std::string InitSt, RunType, ExitStrategy, SaveFinalState, SaveCoo, restartfile, coofile;
   int Len1 = 0, Len2 = 0, Len3 = 0, Len4 = 0, Idum = 0;
+  int Idum0 = 0;                                   // the seed as start.dat gives it (ran3 sets IDUM to 1 at its first call, random.f:58)
   double PtransZig = 1.0, sf = 1.0, MaxTime = 0, OutTime = 0, alloy = 0;
   // InitSt IN / LA (main.f:112-141): geometry and temperature files, LA rate law, nucleus geometry
   std::string cadfile, tempfile, Homogeneous;
@@ -412,6 +413,7 @@ void read_start(Host &H, const char *path) {                 // main.f:83-219
   H.RunType = first_token(in.next()).substr(0, 2);
   if (H.RunType == "T") printf(" ATTENTION! You are running mulskips in test modality,  that is random numbers are not so random!!\n");
   H.Idum = (int)strtol(in.next(), nullptr, 10);
+  H.Idum0 = H.Idum;
   printf(" IDUM %d\n", H.Idum);
   H.SaveFinalState = first_token(in.next()).substr(0, 2);
   if (H.SaveFinalState == "T") { H.restartfile = whole_line(in.next()); printf(" ATTENTION! Storing checkpoint file %s\n This will occupy a lot of disk space...\n", H.restartfile.c_str()); }
@@ -1376,7 +1378,7 @@ int main(int argc, char **argv) {
     }
   } else {                                                    // production mode: synchronous-sublattice sampler, frames at the same cadence
     mskc_parallel_args a{}; mskc_parallel_result r{};
-    a.events_per_tile = ept; a.seed = (uint64_t)(H.Idum < 0 ? -H.Idum : H.Idum); a.n_sweeps = 8;
+    a.events_per_tile = ept; a.seed = (uint64_t)(H.Idum0 < 0 ? -(long long)H.Idum0 : H.Idum0); a.n_sweeps = 8;      // Philox key = the seed of start.dat
     long long next_out = H.OutMolMol; double next_t = H.OutTime;
     // a leg of a socket-driven run starts its own clock and iteration count (la/main.f:621-624); the sampler's clock runs on
     long long leg_events = 0;

@@ -1,0 +1,115 @@
+"""Statistical tier on the north star's own metrics: `mulskips.e --parallel` (synchronous-sublattice sampler on the GPU)
+against `oracle/mulskips_oracle.e` (the serial reference loop, ran3), same start.dat, seeds 1..N each side, frames written at
+the same KMC times by both programs and read back with the reference's own analysis (tests/analyze_port.py = pymulskips/
+analyze.py:124-207 surface height, :209-330 growth rate, :418-481 coverage, :584-603 vacancies; `_d.xyz` line count =
+non-epitaxial, i.e. hexagonal / stacking-fault, bulk atoms).
+
+Workloads: C2 (3C-SiC CVD with H coverage, PtransZig 0.8, 240x240x288 -- BASELINE configs[1]); a Si(001) PVD slab
+(start-Si-SL.dat table, 480x480); a laser-annealing nucleus regrowing in the synthetic temperature map (InitSt LA).
+Tolerances (north star): growth RATE within 2 % (+ 3 standard errors of the difference, which is what N seeds can
+resolve); every other metric within 3 standard errors of the difference of the two means.  The bias table is printed."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import analyze_port as ap
+from cases import make_la_case, make_sic_cvd_case, make_start
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "mulskips_b200", "bin", "mulskips.e")
+ORACLE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
+QUICK = os.environ.get("MSKC_STATS_QUICK") == "1"          # mechanics check (SIMT emulation): tiny runs, no assertions on the physics
+
+
+def _time_strategy(path, tot, out, seed):
+    lines = open(path).read().split("\n")
+    i = next(k for k, l in enumerate(lines) if l.split() and l.split()[0] in ("Iter", "Time"))
+    lines[i] = "Time"; lines[i + 1] = f"{tot!r} ! TotTime"; lines[i + 2] = f"{out!r} ! OutTime"
+    lines[i + 3] = "R ! RunType"; lines[i + 4] = f"{seed} ! IDUM"
+    open(path, "w").write("\n".join(lines))
+
+
+def _run(exe, d, args):
+    with open(os.path.join(d, "log.txt"), "w") as out, open(os.path.join(d, "err.txt"), "w") as err:
+        rc = subprocess.run([exe, *args], cwd=d, stdout=out, stderr=err).returncode
+    assert rc == 0, open(os.path.join(d, "err.txt")).read()[-1500:]
+
+
+def _metrics(d, cvd):
+    files = ap.frames(d)
+    last = files[-1]
+    m = {}
+    m["growth_rate"], h, t = ap.growth_rate(d, Nexclude=1)
+    m["height"] = h[-1]
+    nat, box, sp, z, _ = ap.read_xyz(last)
+    under = np.array([s not in ("H", "Cl", "O") for s in sp])
+    m["surf_atoms"] = float(under.sum())
+    m["roughness"] = float(z[under].std())
+    m["defects_d"] = float(ap.count_lines(last.replace(".xyz", "_d.xyz")))
+    m["vacancies_v"] = float(ap.count_lines(last.replace(".xyz", "_v.xyz")))
+    if cvd:
+        m["coverage_H"] = ap.get_coverage(last)["H"]
+    return m
+
+
+def _ensemble(tmp_path, tag, exe, args, make, seeds, tot, out, cvd):
+    rows = []
+    for s in seeds:
+        d = tmp_path / f"{tag}{s}"
+        d.mkdir()
+        start = make(str(d))
+        _time_strategy(start, tot, out, s)
+        _run(exe, str(d), args)
+        rows.append(_metrics(str(d), cvd))
+    return {k: np.array([r[k] for r in rows]) for k in rows[0]}
+
+
+def _compare(name, ref, par):
+    print(f"\n{name}: metric | serial reference mean +- se | sampler mean +- se | bias | bias / se(diff)")
+    out = {}
+    for k in ref:
+        a, b = ref[k], par[k]
+        se = np.hypot(a.std(ddof=1) / np.sqrt(len(a)), b.std(ddof=1) / np.sqrt(len(b)))
+        bias = b.mean() - a.mean()
+        out[k] = (a.mean(), bias, se)
+        print(f"  {k:12s} {a.mean():14.6g} +- {a.std(ddof=1) / np.sqrt(len(a)):10.3g} | {b.mean():14.6g} +- {b.std(ddof=1) / np.sqrt(len(b)):10.3g} | {bias:+11.4g} ({100 * bias / a.mean() if a.mean() else 0:+6.2f} %) | {bias / se if se > 0 else 0:+6.2f}")
+    return out
+
+
+def _assert(out):
+    mean, bias, se = out["growth_rate"]
+    assert abs(bias) <= 0.02 * abs(mean) + 3 * se, ("growth_rate", mean, bias, se)
+    for k, (mean, bias, se) in out.items():
+        if k == "growth_rate":
+            continue
+        # three standard errors of the difference of the means (+ half a count for integer metrics that are ~0 on both sides)
+        assert abs(bias) <= 3 * se + 0.5, (k, mean, bias, se)
+
+
+def test_c2_sic_cvd(tmp_path):
+    """BASELINE configs[1]: 3C-SiC CVD + H coverage + hexagonal-phase nucleation, 240x240x288"""
+    box = ["--box", "240", "240", "288"] if not QUICK else ["--box", "96", "96", "240"]
+    seeds = range(1, 13) if not QUICK else range(1, 3)
+    tot, out = (6.0e5, 7.5e4) if not QUICK else (6.0e4, 1.0e4)
+    make = lambda d: make_sic_cvd_case(d, lens=(96, 0, 0), ptranszig=0.8)
+    ref = _ensemble(tmp_path, "o", ORACLE, box, make, seeds, tot, out, True)
+    par = _ensemble(tmp_path, "g", EXE, ["--parallel", *box], make, seeds, tot, out, True)
+    res = _compare("C2 3C-SiC CVD + H, PtransZig 0.8", ref, par)
+    if not QUICK:
+        _assert(res)
+
+
+def test_si_slab_pvd(tmp_path):
+    """Si(001) PVD slab, the table of regression-tests start-Si-SL.dat, 480x480 surface"""
+    box = ["--box", "480", "480", "240"] if not QUICK else ["--box", "96", "96", "240"]
+    seeds = range(1, 9) if not QUICK else range(1, 3)
+    tot, out = (8.0e4, 1.0e4) if not QUICK else (2.0e4, 2.5e3)
+    make = lambda d: make_start("Si-SL", os.path.join(d, "start.dat"), lens=(120, 0, 0))
+    ref = _ensemble(tmp_path, "o", ORACLE, box, make, seeds, tot, out, False)
+    par = _ensemble(tmp_path, "g", EXE, ["--parallel", *box], make, seeds, tot, out, False)
+    res = _compare("Si(001) PVD slab", ref, par)
+    if not QUICK:
+        _assert(res)
