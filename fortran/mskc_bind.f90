@@ -53,6 +53,7 @@ module mskc_bind
     real(c_float)      :: sweep_kernel_ms
     integer(c_int32_t) :: stop_reason
     integer(c_int32_t) :: sampler_launches, max_tile_events
+    real(c_double) :: tau
   end type
 
   type, bind(C) :: mskc_counters

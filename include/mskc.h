@@ -149,7 +149,7 @@ int mskc_run_parity(mskc_ctx *h, const mskc_parity_args *a, mskc_parity_result *
 typedef struct {
   int64_t n_sweeps;          /* sweeps (4 colour steps each) to run in this call                    */
   double  events_per_tile;   /* target mean events per active tile per colour step (sets tau)       */
-  double  tau_fixed;         /* >0: use this time quantum instead of the adaptive one               */
+  double  tau_fixed;         /* >0: use this time quantum instead of the adaptive one (from the first sweep of this call on) */
   uint64_t seed;             /* Philox key                                                          */
   int32_t  tile;             /* tile edge in super-lattice units (24), 0 = default                  */
   int32_t  flags;            /* bits 0-15: events one tile may execute per colour step before the rest of its
@@ -173,6 +173,7 @@ typedef struct {
   int32_t stop_reason;       /* MSKC_STOP_BUDGET (the sweeps asked for were run) or MSKC_STOP_FEWMC (main.f:307-310) */
   int32_t sampler_launches;  /* how many sampler kernels those were (short calls time each one)     */
   int32_t max_tile_events;   /* diagnostic: most events one tile executed in one colour step        */
+  double  tau;               /* the adaptive quantum (events_per_tile / mean rate of a tile that carries rate) as of the last sweep */
 } mskc_parallel_result;
 
 /* Synchronous-sublattice sampler: x-y tiles coloured 2x2, every tile of one colour runs its own

@@ -45,7 +45,7 @@ class ParallelResult(C.Structure):
     _fields_ = [("events_done", C.c_int64), ("site_updates", C.c_int64), ("sweeps_done", C.c_int64), ("time", C.c_double),
                 ("total_rate", C.c_double), ("n_active", C.c_int64), ("count_dep", C.c_int64 * 3), ("count_evap", C.c_int64),
                 ("count_abs", C.c_int64), ("count_des", C.c_int64), ("kernel_ms", C.c_float), ("launches", C.c_int32),
-                ("sweep_kernel_ms", C.c_float), ("stop_reason", C.c_int32), ("sampler_launches", C.c_int32), ("max_tile_events", C.c_int32)]
+                ("sweep_kernel_ms", C.c_float), ("stop_reason", C.c_int32), ("sampler_launches", C.c_int32), ("max_tile_events", C.c_int32), ("tau", C.c_double)]
 
 
 class Counters(C.Structure):

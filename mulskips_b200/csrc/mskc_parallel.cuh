@@ -46,6 +46,7 @@ struct SweepState {          // one per context, device resident
   // per-call arguments and a captured CUDA graph of one sweep can be replayed)
   uint2 key; int event_cap, pad;
   double events_per_tile, tau_fixed, ntiles_global;
+  double tau_adaptive;                  // the quantum the rates ask for (tau itself may be the caller's tau_fixed)
 };
 
 // Per-tile active lists, tile-major: entry k of list l lives at [l*cap + k]; the warp that owns tile l
@@ -567,16 +568,16 @@ __device__ __forceinline__ bool halo_list(int l) {        // is tile-list l one 
 }
 // Per-sweep bookkeeping ("per-class rate sums"), stage 1: this rank's total rate and active-site count -> V.red.
 __global__ void __launch_bounds__(1024) sweep_sum_kernel(int ntiles) {
-  __shared__ double sR[32]; __shared__ long long sN[32]; __shared__ int sM[32];
-  double r = 0.0; long long n = 0; int mx = 0;
-  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { if (halo_list(t)) continue; r += V.tile_rate[t]; n += V.live[t]; mx = max(mx, V.cnt[t]); }
-  for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); }
-  if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; }
+  __shared__ double sR[32]; __shared__ long long sN[32]; __shared__ int sM[32], sT[32];
+  double r = 0.0; long long n = 0; int mx = 0, nt = 0;        // nt: tiles that carry rate (the tiles the quantum is sized for)
+  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) { if (halo_list(t)) continue; const double q = V.tile_rate[t]; r += q; nt += q > 0.0; n += V.live[t]; mx = max(mx, V.cnt[t]); }
+  for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); nt += __shfl_down_sync(0xFFFFFFFFu, nt, o); }
+  if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; sT[threadIdx.x >> 5] = nt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double R = 0; long long N = 0; int M = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { R += sR[i]; N += sN[i]; M = max(M, sM[i]); }
-    V.red[0] = R; V.red[1] = (double)N; V.red[2] = 0.0; V.red[3] = 0.0;
+    double R = 0; long long N = 0; int M = 0, T = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { R += sR[i]; N += sN[i]; M = max(M, sM[i]); T += sT[i]; }
+    V.red[0] = R; V.red[1] = (double)N; V.red[2] = (double)T; V.red[3] = 0.0;
     V.ss->max_cnt = M;
   }
 }
@@ -586,7 +587,11 @@ __global__ void sweep_finish_kernel(int advance) {
   const double R = V.red[0];
   if (advance) { s.time += s.tau; s.sweeps++; s.step += 4; }
   s.total_rate = R; s.tree_root = R; s.n_active = (long long)V.red[1];
-  s.tau = s.tau_fixed > 0 ? s.tau_fixed : (R > 0 ? s.events_per_tile * s.ntiles_global / R : 0.0);
+  // the quantum: events_per_tile events expected per colour step in a tile that carries rate (a nucleus or a ridge
+  // occupies few tiles of its box: sizing tau on all tiles would multiply the events per busy tile, i.e. the bias)
+  const double nt = V.red[2] > 0.0 ? V.red[2] : s.ntiles_global;
+  s.tau_adaptive = R > 0 ? s.events_per_tile * nt / R : 0.0;
+  s.tau = s.tau_fixed > 0 ? s.tau_fixed : s.tau_adaptive;
 }
 __global__ void set_params_kernel(uint2 key, int event_cap, double events_per_tile, double tau_fixed, double ntiles_global) {
   SweepState &s = *V.ss;
@@ -1207,6 +1212,9 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
     MSKC_LAUNCH(tile_rate_kernel, (P.ntiles + 255) / 256, 256, 0, st, P.ntiles);
     if (sweep_totals(P, st, 0, &launches, err)) return -1;
     launches += 1;
+  } else {                         // later calls: tau of the first sweep from THIS call's parameters (the sums of the last sweep stand)
+    MSKC_LAUNCH(sweep_finish_kernel, 1, 1, 0, st, 0);
+    launches += 1;
   }
   static const int order[4][2] = {{0, 0}, {1, 1}, {1, 0}, {0, 1}};
   // on request every sampler kernel is timed on its own (CUDA events on the launching stream): this is the per-launch
@@ -1275,6 +1283,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   r->launches = launches; r->max_tile_events = P.h_tot.maxev;
   r->stop_reason = r->n_active <= 20 ? MSKC_STOP_FEWMC : MSKC_STOP_BUDGET;      // main.f:307-310 on the live active-site count
   r->sampler_launches = n_sampler_launches;
+  r->tau = P.h_ss.tau_adaptive;
   P.time = P.h_ss.time;
   return 0;
 }

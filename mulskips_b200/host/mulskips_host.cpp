@@ -1384,8 +1384,18 @@ int main(int argc, char **argv) {
     long long leg_events = 0;
     double t_leg0 = 0.0;
     { mskc_counters c0; MS(mskc_get_counters(R.h, &c0)); t_leg0 = c0.time; }
+    double tau = 0.0;                                         // the sampler's adaptive quantum as of the last call
     while (true) {
+      // frames by time: land on the frame time instead of overshooting it by up to a call's worth of quanta -- whole sweeps
+      // while they fit, then one sweep with the remaining time as its quantum (a shorter quantum only lowers the O(tau) bias)
+      a.n_sweeps = (by_time && H.OutTime > 0 && tau == 0.0) ? 1 : 8; a.tau_fixed = 0.0;      // (first call: learn the quantum)
+      if (by_time && H.OutTime > 0 && tau > 0.0) {
+        const double rem = next_t - R.Time;
+        if (rem <= tau) { a.n_sweeps = 1; a.tau_fixed = rem > 1e-12 * next_t ? rem : tau; }
+        else a.n_sweeps = std::min<long long>(8, (long long)(rem / tau));
+      }
       if (mskc_run_parallel(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
+      tau = r.tau;
       events += r.events_done; leg_events += r.events_done; dev_ms += r.kernel_ms; R.Time = r.time - t_leg0; R.Iter = leg_events + 1; R.IterOut = leg_events;
       mskc_counters c; MS(mskc_get_counters(R.h, &c)); R.NumAtoms = c.num_atoms; R.NumVoids = c.num_voids; R.NumAdAtom = c.num_adatom;
       if (r.n_active <= 20) { printf(" few MC particles: stop MC %lld %d\n", R.Iter, (int)r.n_active); break; }
@@ -1393,7 +1403,7 @@ int main(int argc, char **argv) {
         printf(" \n Current number of occupied sites:  %d\n    > initial number of occupied sites:  %d\n ... STOPPING MulSKIPS ...\n \n", c.num_atoms + c.num_adatom_occ, H.NumOcc0);
         break;
       }
-      bool frame = by_time ? (H.OutTime > 0 && R.Time >= next_t) : (H.OutMolMol > 0 && leg_events >= next_out);
+      bool frame = by_time ? (H.OutTime > 0 && R.Time >= next_t * (1.0 - 1e-12)) : (H.OutMolMol > 0 && leg_events >= next_out);
       if (frame) {
         R.framecounter++;
         write_frame(H, R, R.Time, R.IterOut, R.framecounter, true);
