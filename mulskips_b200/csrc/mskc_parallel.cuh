@@ -73,7 +73,7 @@ struct ParallelCtx {
   TileStat h_tot{}; SweepState h_ss{};
   TileStat extra{};                     // events applied outside the colour steps (trace replay), added to the counters
   double time = 0.0;
-  bool ran = false, replayed = false, lists_stale = false, listed_flag_in_state = false;
+  bool ran = false, replayed = false, lists_stale = false, listed_flag_in_state = false, halo_pending = false;
 #ifndef MSKC_EMU
   cudaGraphExec_t gexec = nullptr;        // one captured sweep (single GPU)
 #endif
@@ -747,25 +747,30 @@ __global__ void __launch_bounds__(256) census_kernel(unsigned long long *out, do
   unsigned long long nUnder = 0, nCov = 0, nNoEpi = 0, nBulk = 0, nOcc = 0, nWall = 0; double hz = 0, hz2 = 0;
   const long long n4 = D.ncell >> 2;
   const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
-  const long long plane = (long long)D.LX * D.LY;
+  const unsigned plane = (unsigned)D.LX * (unsigned)D.LY, LXu = (unsigned)D.LX, LZm1 = (unsigned)(D.LZ - 1);
   const long long stride = (long long)gridDim.x * blockDim.x;
-  auto one = [&](uint32_t w, long long c) {
+  // (cell indices fit 32 bits, DESIGN.md section 2: the coordinates of a non-empty cell cost two 32-bit divisions, and only
+  // the classes that need them pay)
+  auto one = [&](uint32_t w, long long cl) {
     if (w == 0) return;
-    if (V.halo) { const int x = (int)(c % D.LX); if (x < TILE || x >= D.LX - TILE) return; }      // halo columns belong to the neighbours
+    const unsigned c = (unsigned)cl;
+    if (V.halo) { const unsigned x = c % LXu; if (x < (unsigned)TILE || x >= LXu - (unsigned)TILE) return; }      // halo columns belong to the neighbours
     const int cov = w_cov(w);
     if (cov == 113) { nWall++; return; }
     // plane ranges as the reference scans them: census 1 (atoms with coordination <= 3, coverage sites) over planes
     // 1..LenZ-1 (WriteMolMolXYZFile.f:77-92), census 2 (non-epitaxial bulk) over planes 0..LenZ-1 (:95-119)
-    const int z = (int)(c / plane);
     if (w_occ(w)) {
       nOcc++;
-      if (w_coor(w) <= 3) { if (z >= 1 && z <= D.LZ - 1) { nUnder++; hz += z; hz2 += (double)z * z; } }
-      else if (w_coor(w) == 4) {
+      const int co = w_coor(w);
+      if (co > 4) return;
+      const unsigned z = c / plane;
+      if (co <= 3) { if (z - 1u < LZm1) { nUnder++; hz += (double)z; hz2 += (double)z * (double)z; } }
+      else {
         nBulk++;
-        int r = (int)(c - (long long)z * plane), y = r / D.LX, x = r - y * D.LX, kind;
-        if (z <= D.LZ - 1 && !is_cubic_site(x, y, z, kind)) nNoEpi++;
+        const unsigned r = c - z * plane, y = r / LXu, x = r - y * LXu; int kind;
+        if (z <= LZm1 && !is_cubic_site((int)x, (int)y, (int)z, kind)) nNoEpi++;
       }
-    } else if (cov != 0 && z >= 1 && z <= D.LZ - 1) nCov++;
+    } else if (cov != 0) { const unsigned z = c / plane; if (z - 1u < LZm1) nCov++; }
   };
   for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += 4 * stride) {      // four 128-bit loads in flight
     uint4 v[4];
@@ -927,7 +932,7 @@ static inline NcclApi *nccl_api(std::string *err) {
 }
 #define NCK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { if (err) *err = std::string("NCCL error ") + nccl->GetErrorString(r_) + " in " #call; return -1; } } while (0)
 
-enum { HALO_CAP = 16384 };         // records per side per colour step (512 KiB messages)
+enum { HALO_CAP = 32768 };         // records per side per exchange (two colour steps' worth of changed cells)
 
 static inline void parallel_free(ParallelCtx &P) {
   const int halo = P.halo, rank = P.rank, nranks = P.nranks; void *comm = P.comm;
@@ -1233,7 +1238,14 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
       MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, c);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       launches += 1; n_sampler_launches++;
-      if (P.halo && halo_exchange(P, H, st, &launches, err)) return -1;
+      // The shared strips cross the seam only when the NEXT colour step runs the other tile-column parity: tiles of the same
+      // parity on the two sides of a rank boundary neither write nor read each other's cells (writes <= 8, reads <= 16 units
+      // from a tile's edge, 24 between them -- the argument that lets one colour run concurrently), so steps 2 -> 3 of a sweep
+      // and 4 -> 1 of the next need no exchange; the changed cells keep accumulating in the dirty list.
+      if (P.halo) {
+        if (order[c][0] != order[(c + 1) & 3][0]) { if (halo_exchange(P, H, st, &launches, err)) return -1; P.halo_pending = false; }
+        else P.halo_pending = true;
+      }
     }
     if (P.halo) { MSKC_LAUNCH(compact_halo_kernel, (2 * P.nty * 32 + 127) / 128, 128, 0, st); launches++; }
     return sweep_totals(P, st, 1, &launches, err);
@@ -1261,6 +1273,7 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   }
 #endif
   if (!graphed) for (long long s = 0; s < a->n_sweeps; s++) if (one_sweep()) return -1;
+  if (P.halo && P.halo_pending) { if (halo_exchange(P, H, st, &launches, err)) return -1; P.halo_pending = false; }     // seams consistent when the call returns
   MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
   launches++;
   PCK(cudaEventRecord(e1, st));

@@ -1171,6 +1171,68 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   fflush(stdout);
 }
 
+// ---- complete checkpoint ("persist bond lists") ------------------------------------------------------
+// The reference's checkpoint (main.f:385-403) holds LattCoo only; its restart (SetCAD.f:54-79,307-322) rebuilds the particle
+// lists by scanning the lattice and re-deriving every bond list from ideal positions, so list order, the bonds of
+// hexagonal / stacking-fault atoms, the rates in the tree, the generator and the clock are lost: a restarted run is a
+// different trajectory.  Beside that file the host writes `<name>.mskc`: lattice words, the three lists in list order with
+// their bond lists, event codes and rates as raw doubles, the ran3 state / numberslist cursor and the clock, so that
+// `--exact-restart <name>.mskc` continues the SAME trajectory bit for bit (tests/test_host_gpu.py).  Serial-parity mode only:
+// the sampler keeps no reference-ordered lists.
+struct CkptHeader {
+  char magic[8]; int32_t LX, LY, LZ, nmc, nbulk, nvoid; int64_t iter, framecounter, counter; double time;
+  int32_t CC[3], CV[3], CCold[3], rng[58], idum, runtype;
+};
+void write_exact_checkpoint(Host &H, Run &R, const std::string &path) {
+  mskc_counters c; MS(mskc_get_counters(R.h, &c));
+  CkptHeader h{}; memcpy(h.magic, "MSKCKPT1", 8);
+  h.LX = H.LX; h.LY = H.LY; h.LZ = H.LZ; h.nmc = c.num_adatom; h.nvoid = c.num_voids; h.iter = c.iter; h.time = c.time; h.framecounter = R.framecounter;
+  for (int i = 0; i < 3; i++) { h.CC[i] = c.CountCrystal[i]; h.CV[i] = c.CountCov[i]; h.CCold[i] = H.CountCrystalOld[i]; }
+  MS(mskc_get_rng(R.h, h.rng, &h.counter, &h.idum)); h.runtype = H.RunType[0];
+  const size_t nb_cap = (size_t)std::max(c.num_atoms, 0) + 16;
+  std::vector<int32_t> mx(3 * (size_t)h.nmc + 3), mn(12 * (size_t)h.nmc + 12), me((size_t)h.nmc + 1), vx(3 * (size_t)h.nvoid + 3), vn(12 * (size_t)h.nvoid + 12), bx(3 * nb_cap), bn(12 * nb_cap);
+  std::vector<double> mr((size_t)h.nmc + 1);
+  int64_t nb = 0;
+  MS(mskc_download_lists(R.h, mx.data(), mn.data(), me.data(), mr.data(), vx.data(), vn.data(), bx.data(), bn.data(), (int64_t)nb_cap, &nb));
+  if (nb > (int64_t)nb_cap) die(" exact checkpoint: %lld bulk atoms found, %zu expected", (long long)nb, nb_cap);
+  h.nbulk = (int32_t)nb;
+  MS(mskc_download_lattice(R.h, H.L.data()));
+  FILE *f = fopen(path.c_str(), "wb"); if (!f) die(" cannot write %s", path.c_str());
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(H.L.data(), 4, H.L.size(), f) == H.L.size();
+  ok = ok && fwrite(mx.data(), 4, 3 * (size_t)h.nmc, f) == 3 * (size_t)h.nmc && fwrite(mn.data(), 4, 12 * (size_t)h.nmc, f) == 12 * (size_t)h.nmc;
+  ok = ok && fwrite(me.data(), 4, (size_t)h.nmc, f) == (size_t)h.nmc && fwrite(mr.data(), 8, (size_t)h.nmc, f) == (size_t)h.nmc;
+  ok = ok && fwrite(vx.data(), 4, 3 * (size_t)h.nvoid, f) == 3 * (size_t)h.nvoid && fwrite(vn.data(), 4, 12 * (size_t)h.nvoid, f) == 12 * (size_t)h.nvoid;
+  ok = ok && fwrite(bx.data(), 4, 3 * (size_t)h.nbulk, f) == 3 * (size_t)h.nbulk && fwrite(bn.data(), 4, 12 * (size_t)h.nbulk, f) == 12 * (size_t)h.nbulk;
+  if (fclose(f) != 0 || !ok) die(" error writing %s", path.c_str());
+}
+// fills H.L / H.mc / H.bulk / H.voids / the generator / the counters from the file; returns the clock
+void read_exact_checkpoint(Host &H, Run &R, const char *path, CkptHeader &h) {
+  FILE *f = fopen(path, "rb"); if (!f) die(" cannot open %s", path);
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "MSKCKPT1", 8)) die(" %s is not a complete checkpoint of this program", path);
+  if (h.LX != H.LX || h.LY != H.LY || h.LZ != H.LZ) die(" %s was written for a %d x %d x %d box, this run is %d x %d x %d", path, h.LX, h.LY, h.LZ, H.LX, H.LY, H.LZ);
+  auto rd = [&](void *p, size_t sz, size_t n) { if (n && fread(p, sz, n, f) != n) die(" %s is truncated", path); };
+  rd(H.L.data(), 4, H.L.size());
+  std::vector<int32_t> x, n, e; std::vector<double> r;
+  auto sites = [&](size_t cnt, auto &out) {
+    x.resize(3 * cnt); n.resize(12 * cnt); rd(x.data(), 4, 3 * cnt); rd(n.data(), 4, 12 * cnt);
+    out.resize(cnt);
+    for (size_t i = 0; i < cnt; i++) { memcpy(out[i].xyz, &x[3 * i], 12); memcpy(out[i].nn, &n[12 * i], 48); }
+  };
+  {
+    const size_t cnt = (size_t)h.nmc;
+    x.resize(3 * cnt); n.resize(12 * cnt); e.resize(cnt); r.resize(cnt);
+    rd(x.data(), 4, 3 * cnt); rd(n.data(), 4, 12 * cnt); rd(e.data(), 4, cnt); rd(r.data(), 8, cnt);
+    H.mc.resize(cnt);
+    for (size_t i = 0; i < cnt; i++) { memcpy(H.mc[i].xyz, &x[3 * i], 12); memcpy(H.mc[i].nn, &n[12 * i], 48); H.mc[i].ev = e[i]; H.mc[i].p = r[i]; }
+  }
+  sites((size_t)h.nvoid, H.voids); sites((size_t)h.nbulk, H.bulk);
+  fclose(f);
+  H.r_iff = h.rng[0]; H.r_inext = h.rng[1]; H.r_inextp = h.rng[2]; for (int i = 1; i <= 55; i++) H.r_ma[i] = h.rng[2 + i];
+  H.Idum = h.idum;
+  for (int i = 0; i < 3; i++) { H.CountCrystal[i] = h.CC[i]; H.CountCov[i] = h.CV[i]; H.CountCrystalOld[i] = h.CCold[i]; }
+  R.Iter = h.iter; R.IterOut = h.iter - 1; R.Time = h.time; R.framecounter = h.framecounter;
+}
+
 bool box_from_defsystem(const char *exe, int box[3]) {      // the line pymulskips rewrites: "INTEGER, PARAMETER :: LenX=480, LenY=480, LenZ=480"
   std::string p(exe); size_t k = p.find_last_of('/'); p = (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/modules/defsystem.f";
   FILE *f = fopen(p.c_str(), "r"); if (!f) return false;
@@ -1220,6 +1282,7 @@ int main(int argc, char **argv) {
   int box[3] = {480, 480, 480}; bool parallel = false; double ept = 4.0; int device = 0; const char *start = "start.dat";
   int mode = -1;                                                // -1: by RunType (below), 0: serial parity, 1: sublattice sampler
   bool have_box = false;
+  const char *exact_restart = nullptr;                          // --exact-restart file.mskc: continue from the complete state (lists, bonds, rates, generator), see write_exact_checkpoint
   const char *dump_state = nullptr;                             // --dump-state file: what is about to be uploaded, as text (tests compare it with the oracle's state)
   const char *sock_host = "localhost"; int sock_port = -1;     // la/main.f:102-131: -h hostname -p port => socket-driven run
   for (int i = 1; i < argc; i++) {
@@ -1231,9 +1294,10 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--start") && i + 1 < argc) start = argv[++i];
     else if (!strcmp(argv[i], "--dump-state") && i + 1 < argc) dump_state = argv[++i];
+    else if (!strcmp(argv[i], "--exact-restart") && i + 1 < argc) exact_restart = argv[++i];
     else if (!strcmp(argv[i], "-h") && i + 1 < argc) sock_host = argv[++i];
     else if (!strcmp(argv[i], "-p") && i + 1 < argc) sock_port = atoi(argv[++i]);
-    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parity | --parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file]\n", argv[0]); return 2; }
+    else { fprintf(stderr, "usage: %s [--box X Y Z] [--parity | --parallel [--events-per-tile e]] [--la-tree [-h host] -p port] [--device d] [--start file] [--exact-restart file.mskc]\n", argv[0]); return 2; }
   }
   if (!have_box) { if (const char *e = getenv("MSKC_BOX")) have_box = sscanf(e, "%d %d %d", &box[0], &box[1], &box[2]) == 3; }
   if (!have_box) box_from_defsystem(argv[0], box);
@@ -1248,7 +1312,13 @@ int main(int argc, char **argv) {
   H.Tree.assign((size_t)1 << H.Levels, 0.0);
   // main.f:225-295
   if (H.la_tree && H.InitSt != "LA" && H.InitSt != "IN") die(" mulskips.e (B200 host): --la-tree (the LaserAnnealing fork) is built for InitSt LA and IN");
-  if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
+  CkptHeader ck{};
+  if (exact_restart) {                                        // the complete state of an earlier run instead of a builder
+    if (H.la_tree || sock_port >= 0) die(" mulskips.e (B200 host): --exact-restart is built for the mulskips-source tree without the socket loop");
+    read_exact_checkpoint(H, R, exact_restart, ck);
+    printf(" Continuing from the complete checkpoint %s: Iter %lld Time %.17g\n", exact_restart, (long long)ck.iter, ck.time);
+  }
+  else if (H.InitSt == "F") { H.Len1 -= H.Len1 % 24; set_flat(H, H.Len1, false, true); }
   else if (H.InitSt == "Fw") {                               // SetSiC3Cww.f: SetSiC3C.f between wall planes, plus a wall block from Len2 up
     H.Len1 -= H.Len1 % 24; H.Len2 -= H.Len2 % 24;
     set_flat(H, H.Len1, true, true); wall_planes(H, H.Len2, H.LZ - 7);
@@ -1298,8 +1368,10 @@ int main(int argc, char **argv) {
     printf(" Atoms,Voids,AdAtoms,AdAtomsOcc %d %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom, H.NumAdAtomOcc);
   } else
   printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+  if (!exact_restart) {
   for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
   write_frame(H, R, 0.0, 0, 0, false);                       // main.f:297-300
+  }
   if (dump_state) {
     // the module globals the builder left, in list order: rates as raw bits, the ran3 stream position, a 64-bit FNV-1a of LattCoo
     FILE *f = fopen(dump_state, "w"); if (!f) die(" cannot write %s", dump_state);
@@ -1330,9 +1402,10 @@ int main(int argc, char **argv) {
     for (size_t i = 0; i < H.mc.size(); i++) { memcpy(&mx[3 * i], H.mc[i].xyz, 12); memcpy(&mn[12 * i], H.mc[i].nn, 48); me[i] = H.mc[i].ev; mr[i] = H.mc[i].p; }
     for (size_t i = 0; i < H.bulk.size(); i++) { memcpy(&bx[3 * i], H.bulk[i].xyz, 12); memcpy(&bn[12 * i], H.bulk[i].nn, 48); }
     int32_t st[58]; st[0] = H.r_iff; st[1] = H.r_inext; st[2] = H.r_inextp; for (int i = 1; i <= 55; i++) st[2 + i] = H.r_ma[i];
-    MS(mskc_seed(R.h, H.Idum, H.RunType[0], 0, st));
+    MS(mskc_seed(R.h, H.Idum, H.RunType[0], exact_restart ? ck.counter : 0, st));
     MS(mskc_upload_state(R.h, H.L.data(), (int)H.mc.size(), mx.data(), mn.data(), me.data(), mr.data(), (int)H.bulk.size(), bx.data(), bn.data(), (int)H.voids.size(), vx.data(), vn.data()));
-    MS(mskc_set_clock(R.h, 1, 0.0, H.CountCrystal, H.CountCov));
+    if (exact_restart) MS(mskc_set_clock(R.h, ck.iter, ck.time, H.CountCrystal, H.CountCov));
+    else MS(mskc_set_clock(R.h, 1, 0.0, H.CountCrystal, H.CountCov));
   }
   std::vector<Active>().swap(H.mc); std::vector<Site>().swap(H.bulk); std::vector<Site>().swap(H.voids);
   by_time = H.ExitStrategy == "Time";
@@ -1345,6 +1418,7 @@ int main(int argc, char **argv) {
   // statistically faithful trajectory -> the synchronous-sublattice sampler, the mode that uses the GPU.  --parity /
   // --parallel (or MSKC_MODE=parity|parallel) override; socket-driven runs and boxes that are not multiples of 48 stay serial.
   if (mode < 0) { if (const char *e = getenv("MSKC_MODE")) mode = !strcmp(e, "parallel") ? 1 : (!strcmp(e, "parity") ? 0 : -1); }
+  if (exact_restart) mode = 0;                                // (the same trajectory: the serial loop)
   if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
   parallel = mode == 1;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
@@ -1425,6 +1499,7 @@ int main(int argc, char **argv) {
       fclose(f);
     }
     printf(" Done writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
+    if (!parallel && !H.la_tree) write_exact_checkpoint(H, R, H.restartfile + ".mskc");      // (stdout stays the reference's)
   }
   if (H.SaveCoo == "T" && H.la_tree && H.coofile == "None") {          // la/main.f:795-817: phases and species go back through the socket
     printf(" Sending phases and Ge fraction back to LA code \n");

@@ -336,3 +336,43 @@ def test_shape_builder(built, tmp_path):
         assert (g / name).read_bytes() == (o / name).read_bytes(), f"SH: {name} differs from the oracle's"
     for key in ("Atoms,Voids,AdAtoms", "Iter, Time, Site", "NatNvoidNad"):
         assert _tokens(g / "log.txt", key) == _tokens(o / "log.txt", key), key
+
+
+@pytest.mark.parametrize("case", ["surface-zig0.8", "CVD-Si-SiH2"])
+def test_exact_checkpoint_restart(built, tmp_path, case):
+    """SURVEY 8 f2, second half: the reference's checkpoint keeps LattCoo only and its restart re-derives the lists (lossy:
+    list order, hexagonal bonds, rates, generator, clock).  Beside it the host program writes `<name>.mskc` -- the complete
+    state -- and `--exact-restart` continues the SAME trajectory: a run of N events + checkpoint + restart to 2N must leave
+    the files and the log lines of an uninterrupted run of 2N events, bit for bit (hexagonal-phase SiC with the
+    numberslist stream; Si CVD with coverage, ran3, exit on KMC time)."""
+    box = ["--box", "96", "96", "240"]
+    if case == "surface-zig0.8":
+        kw1, kw2 = dict(maxiter=30000, outmolmol=15000), dict(maxiter=60000, outmolmol=15000)
+        mk = lambda dst, kw: make_start("surface", dst, lens=(48, 0, 0), ptranszig=0.8, **kw)
+        late = ["I00000003", "I00000004"]
+    else:
+        kw1, kw2 = dict(maxtime=0.02, outtime=0.01), dict(maxtime=0.04, outtime=0.01)
+        mk = lambda dst, kw: make_start("CVD-Si-SiH2", dst, lens=(120, 0, 0), runtype="R", idum=-4711, **kw)
+        late = ["I00000003", "I00000004"]
+    a, b1, b2 = tmp_path / "a", tmp_path / "b1", tmp_path / "b2"
+    for d in (a, b1, b2):
+        d.mkdir()
+    mk(str(a / "start.dat"), kw2)
+    _run(EXE, a, box)
+    mk(str(b1 / "start.dat"), kw1)
+    lines = (b1 / "start.dat").read_text().split("\n")
+    i = next(k for k, l in enumerate(lines) if "Save final state" in l or "SaveFinalState" in l)
+    lines[i] = "T ! Save final state"
+    lines.insert(i + 1, "LattChk.dat")
+    (b1 / "start.dat").write_text("\n".join(lines))
+    _run(EXE, b1, box)
+    assert (b1 / "LattChk.dat.mskc").exists()
+    mk(str(b2 / "start.dat"), kw2)
+    _run(EXE, b2, [*box, "--exact-restart", str(b1 / "LattChk.dat.mskc")])
+    la = [l for l in open(a / "log.txt") if l.startswith((" Iter, Time, Site", " NatNvoidNad"))]
+    lb = [l for l in open(b2 / "log.txt") if l.startswith((" Iter, Time, Site", " NatNvoidNad"))]
+    assert len(lb) >= 2 and la[-len(lb):] == lb, "the continued run's log lines differ from the uninterrupted run's"
+    names = sorted(p.name for p in b2.glob("I0*.xyz"))
+    assert any(n.startswith(late[0]) for n in names) and any(n.startswith(late[1]) for n in names), names
+    for n in names:
+        assert (b2 / n).read_bytes() == (a / n).read_bytes(), f"{n} differs from the uninterrupted run's"
