@@ -77,7 +77,7 @@ struct ParallelCtx {
 #ifndef MSKC_EMU
   cudaGraphExec_t gexec = nullptr;        // one captured sweep (single GPU)
 #endif
-  void *g_kern = nullptr; int g_blocks = 0, g_launches = 0; size_t g_smem = 0;
+  void *g_kern = nullptr; int g_blocks = 0, g_launches = 0, g_sweeps = 0; size_t g_smem = 0;
 };
 
 struct TileView {            // what the kernels need (constant memory)
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(1024) sweep_sum_kernel(int ntiles) {
 __global__ void sweep_finish_kernel(int advance) {
   SweepState &s = *V.ss;
   const double R = V.red[0];
-  if (advance) { s.time += s.tau; s.sweeps++; s.step += 4; }
+  if (advance) { s.time += (double)advance * s.tau; s.sweeps += advance; s.step += 4 * advance; }      // `advance` sweeps ran on this tau
   s.total_rate = R; s.tree_root = R; s.n_active = (long long)V.red[1];
   // the quantum: events_per_tile events expected per colour step in a tile that carries rate (a nucleus or a ridge
   // occupies few tiles of its box: sizing tau on all tiles would multiply the events per busy tile, i.e. the bias)
@@ -1230,12 +1230,18 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
   size_t ke = 0;
   int n_sampler_launches = 0;
   // one sweep = four colour steps (fixed colour order: an alternating ABCD/DCBA order was measured WORSE, a colour then
-  // runs twice in a row, doubling its effective quantum -- DESIGN.md section 5.3) + the per-sweep totals
-  auto one_sweep = [&]() -> int {
-    for (int c = 0; c < 4; c++) {
+  // runs twice in a row, doubling its effective quantum -- DESIGN.md section 5.3).  The totals (sum of rates -> next tau,
+  // clock, active-site count; one all-reduce over the ranks of a slab run) follow every sweep.  MSKC_TOTALS_EVERY=k takes
+  // them once per batch of k sweeps instead (the clock advances by the tau that was used, so this is exact in time): +3 %
+  // events/s at k = 4, but tau then lags the total rate by up to k sweeps, which over-sizes the quantum while a surface is
+  // still roughening (measured: 1.5x the events per step in the first sweeps after a flat start) -- not the default.
+  int totals_every = 1;
+  if (const char *e = getenv("MSKC_TOTALS_EVERY")) totals_every = std::max(1, atoi(e));
+  auto batch = [&](int k) -> int {
+    for (int sw = 0; sw < k; sw++) for (int c = 0; c < 4; c++) {
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       const int col = order[c][1] * 2 + order[c][0];
-      MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, c);
+      MSKC_LAUNCH(kern, blocks, CS_THREADS, smem, st, col, 4 * sw + c);
       if (timed) PCK(cudaEventRecord(evs[ke++], st));
       launches += 1; n_sampler_launches++;
       // The shared strips cross the seam only when the NEXT colour step runs the other tile-column parity: tiles of the same
@@ -1248,31 +1254,29 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
       }
     }
     if (P.halo) { MSKC_LAUNCH(compact_halo_kernel, (2 * P.nty * 32 + 127) / 128, 128, 0, st); launches++; }
-    return sweep_totals(P, st, 1, &launches, err);
+    return sweep_totals(P, st, k, &launches, err);
   };
-  bool graphed = false;
+  long long left = a->n_sweeps;
 #ifndef MSKC_EMU
-  // single GPU: the six launches of a sweep are captured once into a CUDA graph and replayed (launch-bound tail of short
+  // single GPU: the launches of a batch are captured once into a CUDA graph and replayed (launch-bound tail of short
   // colour steps on small boxes; nothing in a sweep depends on host-side arguments any more)
-  if (!timed && !P.halo && a->n_sweeps >= 4 && !getenv("MSKC_NO_GRAPH")) {
-    if (P.gexec && (P.g_kern != (void *)kern || P.g_blocks != blocks || P.g_smem != smem)) { cudaGraphExecDestroy(P.gexec); P.gexec = nullptr; }
+  if (!timed && !P.halo && left >= totals_every && !getenv("MSKC_NO_GRAPH")) {
+    if (P.gexec && (P.g_kern != (void *)kern || P.g_blocks != blocks || P.g_smem != smem || P.g_sweeps != totals_every)) { cudaGraphExecDestroy(P.gexec); P.gexec = nullptr; }
     if (!P.gexec) {
       cudaGraph_t g = nullptr; int l0 = launches, n0 = n_sampler_launches;
       PCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int rc = one_sweep();
+      const int rc = batch(totals_every);
       PCK(cudaStreamEndCapture(st, &g));
       if (rc) return -1;
       PCK(cudaGraphInstantiate(&P.gexec, g, 0));
       cudaGraphDestroy(g);
-      P.g_kern = (void *)kern; P.g_blocks = blocks; P.g_smem = smem; P.g_launches = launches - l0;
+      P.g_kern = (void *)kern; P.g_blocks = blocks; P.g_smem = smem; P.g_launches = launches - l0; P.g_sweeps = totals_every;
       launches = l0; n_sampler_launches = n0;
     }
-    for (long long s = 0; s < a->n_sweeps; s++) PCK(cudaGraphLaunch(P.gexec, st));
-    launches += (int)(a->n_sweeps * P.g_launches); n_sampler_launches += (int)(4 * a->n_sweeps);
-    graphed = true;
+    for (; left >= totals_every; left -= totals_every) { PCK(cudaGraphLaunch(P.gexec, st)); launches += P.g_launches; n_sampler_launches += 4 * totals_every; }
   }
 #endif
-  if (!graphed) for (long long s = 0; s < a->n_sweeps; s++) if (one_sweep()) return -1;
+  for (; left > 0; left -= std::min<long long>(left, totals_every)) if (batch((int)std::min<long long>(left, totals_every))) return -1;
   if (P.halo && P.halo_pending) { if (halo_exchange(P, H, st, &launches, err)) return -1; P.halo_pending = false; }     // seams consistent when the call returns
   MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
   launches++;

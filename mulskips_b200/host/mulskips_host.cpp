@@ -1462,11 +1462,14 @@ int main(int argc, char **argv) {
     while (true) {
       // frames by time: land on the frame time instead of overshooting it by up to a call's worth of quanta -- whole sweeps
       // while they fit, then one sweep with the remaining time as its quantum (a shorter quantum only lowers the O(tau) bias)
-      a.n_sweeps = (by_time && H.OutTime > 0 && tau == 0.0) ? 1 : 8; a.tau_fixed = 0.0;      // (first call: learn the quantum)
-      if (by_time && H.OutTime > 0 && tau > 0.0) {
-        const double rem = next_t - R.Time;
-        if (rem <= tau) { a.n_sweeps = 1; a.tau_fixed = rem > 1e-12 * next_t ? rem : tau; }
-        else a.n_sweeps = std::min<long long>(8, (long long)(rem / tau));
+      a.n_sweeps = (by_time && tau == 0.0) ? 1 : 8; a.tau_fixed = 0.0;      // (first call: learn the quantum)
+      if (by_time && tau > 0.0) {                             // the next time the loop has to stop at: a frame, or the end of the run
+        const double stop_t = H.OutTime > 0 ? std::min(next_t, H.MaxTime) : H.MaxTime;
+        const double rem = stop_t - R.Time;
+        const double nq = rem / tau;                          // quanta left at the present rate
+        if (nq > 12.0) a.n_sweeps = 8;                        // far away: adaptive quanta
+        else if (rem > 1e-12 * stop_t) { a.n_sweeps = std::max<long long>(1, (long long)std::ceil(nq)); a.tau_fixed = rem / (double)a.n_sweeps; }   // land on it: equal quanta <= tau
+        else { a.n_sweeps = 1; a.tau_fixed = tau; }
       }
       if (mskc_run_parallel(R.h, &a, &r) != 0) die(" %s", mskc_last_error(R.h));
       tau = r.tau;
@@ -1485,7 +1488,7 @@ int main(int argc, char **argv) {
         printf(" NatNvoidNad %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
         next_out += H.OutMolMol; next_t += H.OutTime;
       }
-      if (by_time ? R.Time > H.MaxTime : leg_events >= H.MaxIter) break;
+      if (by_time ? R.Time >= H.MaxTime * (1.0 - 1e-12) : leg_events >= H.MaxIter) break;     // (the serial loop stops one event past MaxTime)
     }
   }
   };
