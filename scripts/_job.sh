@@ -1,6 +1,10 @@
 set -x
 mkdir -p gpurun_out
-( time timeout 2400 python -m pytest tests -m gpu -x -q ) > gpurun_out/r02d_pytest_gpu.log 2>&1
-tail -12 gpurun_out/r02d_pytest_gpu.log
-( timeout 1200 python -m pytest tests/test_stats_north_star_gpu.py tests/test_sampler_stats_gpu.py -m gpu -q -s ) > gpurun_out/r02d_stats.log 2>&1
-grep -vE "^\+" gpurun_out/r02d_stats.log | grep -E "^[A-Z]|  [a-z_A-Z]+ |passed|failed" | tail -40
+exec > gpurun_out/ab_loads.txt 2>&1
+( timeout 600 python -m pytest tests/test_slab_gpu.py tests/test_host_gpu.py -m gpu -q -x -k "slab or parallel" ) 2>&1 | tail -2
+for lib in "" scripts/_build/libmskc_prefetch.so scripts/_build/libmskc_early.so scripts/_build/libmskc_early_pf.so; do
+  echo "== lib=${lib:-default}"
+  MSKC_LIB=${lib:+$PWD/$lib} python scripts/probe_slab.py --slab 0 --sweeps 64
+done
+echo "== default again"
+python scripts/probe_slab.py --slab 0 --sweeps 64

@@ -68,3 +68,23 @@ def test_slab_statistics_match_periodic_box():
     assert gb.mean() > 1000
     assert abs(ga.mean() - gb.mean()) <= 0.02 * gb.mean() + 3 * se
     assert abs(a[:, 1].mean() - b[:, 1].mean()) <= 3 * np.hypot(a[:, 1].std(ddof=1), b[:, 1].std(ddof=1))
+
+
+def test_slab_long_growth():
+    """Twenty atomic layers in slab mode (round-1 advisory: the mirrored halo lists only ever received entries -- their
+    tombstones are now dropped once per sweep -- so a long growth run must neither fill a halo list nor let the two copies
+    of a shared column drift apart)."""
+    ctx = make(True)
+    base = 2 * (GX // 12) * (GY // 12) * (LEN1 // 3 + 1)
+    layer = 2 * (GX // 12) * (GY // 12)
+    grown, calls = 0, 0
+    while grown < 20 * layer:
+        ctx.run_parallel(200, events_per_tile=4.0, seed=500 + calls)
+        calls += 1
+        c, _ = ctx.census()
+        grown = c.occupied - base
+        assert calls < 400, f"only {grown} atoms after {calls} calls"
+    L = ctx.download_lattice()
+    assert np.array_equal(L[:, :, 0:24], L[:, :, GX:GX + 24]) and np.array_equal(L[:, :, GX + 24:GX + 48], L[:, :, 24:48])
+    print(f"\n{grown} atoms ({grown / layer:.1f} layers) in {calls} calls of 200 sweeps")
+    ctx.close()
