@@ -571,7 +571,7 @@ __device__ __forceinline__ bool halo_list(int l) {        // is tile-list l one 
 // block to finish adds the partial sums in block order (a fixed order: the totals do not depend on which block came last) and,
 // on a single rank, goes straight on to stage 2.  (One block of 1024 threads over the 3.7e4 tiles of the bench box took 24 us
 // per sweep -- 4 % of a sweep; this takes ~4.)
-enum { SUM_BLOCKS = 64, RED_DOUBLES = 8 + 4 * SUM_BLOCKS };
+enum { SUM_BLOCKS = 64 /* = 2 x 32: the last block's warp 0 takes two partial sums per lane */, RED_DOUBLES = 8 + 4 * SUM_BLOCKS };
 // stage 2 (after the all-reduce of V.red over the ranks, if any): clock, next tau, global-coupling terms
 __device__ __forceinline__ void sweep_finish(int advance) {
   SweepState &s = *V.ss;
@@ -599,15 +599,23 @@ __global__ void __launch_bounds__(256) sweep_sum_kernel(int ntiles, int finish_a
     __threadfence();
     unsigned int *done = reinterpret_cast<unsigned int *>(V.red + 4);
     s_last = atomicAdd(done, 1u) == gridDim.x - 1;
-    if (s_last) {
-      __threadfence();
-      double tR = 0, tN = 0, tT = 0, tM = 0;
-      for (int b = 0; b < (int)gridDim.x; b++) { const volatile double *q = V.red + 8 + 4 * b; tR += q[0]; tN += q[1]; tT += q[2]; tM = fmax(tM, q[3]); }
-      V.red[0] = tR; V.red[1] = tN; V.red[2] = tT; V.red[3] = 0.0;
-      V.ss->max_cnt = (long long)tM;
-      *done = 0u;
-      if (finish_advance >= 0) sweep_finish(finish_advance);
-    }
+    if (s_last) *done = 0u;
+  }
+  __syncthreads();
+  if (!s_last || threadIdx.x >= 32) return;
+  // the last block: warp 0 adds the SUM_BLOCKS partial sums -- lane l takes blocks l and l + 32, then a shuffle tree: a fixed
+  // order whichever block came last (64 dependent L2 reads by one thread took 15 us)
+  __threadfence();
+  const volatile double *q0 = V.red + 8 + 4 * threadIdx.x, *q1 = V.red + 8 + 4 * (threadIdx.x + 32);
+  double tR = q0[0] + q1[0], tN = q0[1] + q1[1], tT = q0[2] + q1[2], tM = fmax(q0[3], q1[3]);
+  for (int o = 16; o > 0; o >>= 1) {
+    tR += __shfl_down_sync(0xFFFFFFFFu, tR, o); tN += __shfl_down_sync(0xFFFFFFFFu, tN, o); tT += __shfl_down_sync(0xFFFFFFFFu, tT, o);
+    tM = fmax(tM, __shfl_down_sync(0xFFFFFFFFu, tM, o));
+  }
+  if (threadIdx.x == 0) {
+    V.red[0] = tR; V.red[1] = tN; V.red[2] = tT; V.red[3] = 0.0;
+    V.ss->max_cnt = (long long)tM;
+    if (finish_advance >= 0) sweep_finish(finish_advance);
   }
 }
 __global__ void sweep_finish_kernel(int advance) { sweep_finish(advance); }
@@ -625,26 +633,32 @@ __global__ void __launch_bounds__(256) tile_rate_kernel(int ntiles) {
   V.tile_rate[l] = r; V.live[l] = live;
 }
 
+// per-call counter reduction: 19 integer columns of every tile's statistics, summed into *out (zeroed by the caller; integer
+// atomics, so the totals do not depend on the order).  Many blocks: one block over the 3.7e4 tiles of the bench box took
+// 150 us per call, 4 % of an 8-sweep call of the host program.
 __global__ void __launch_bounds__(256) reduce_tstat_kernel(const TileStat *ts, int ntiles, TileStat *out) {
-  // one block; 19 integer columns
-  __shared__ long long acc[19];
-  if (threadIdx.x < 19) acc[threadIdx.x] = 0;
+  __shared__ long long acc[17];
+  if (threadIdx.x < 17) acc[threadIdx.x] = 0;
   __syncthreads();
-  long long loc[19];
-  for (int k = 0; k < 19; k++) loc[k] = 0;
-  for (int t = threadIdx.x; t < ntiles; t += blockDim.x) {
+  long long loc[17];
+  for (int k = 0; k < 17; k++) loc[k] = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) {
     const TileStat &s = ts[t];
     loc[0] += s.events; loc[1] += s.site_updates; loc[2] += s.dep[0]; loc[3] += s.dep[1]; loc[4] += s.dep[2]; loc[5] += s.evap; loc[6] += s.abs_; loc[7] += s.des;
     loc[8] += s.dAtoms; loc[9] += s.dVoids; if (s.maxev > loc[16]) loc[16] = s.maxev; loc[10] += s.dCrystal[0]; loc[11] += s.dCrystal[1]; loc[12] += s.dCrystal[2]; loc[13] += s.dCov[0]; loc[14] += s.dCov[1]; loc[15] += s.dCov[2];
   }
-  for (int k = 0; k < 16; k++) atomicAdd((unsigned long long *)&acc[k], (unsigned long long)loc[k]);
-  atomicMax((long long *)&acc[16], loc[16]);
+  for (int k = 0; k < 17; k++) {
+    long long v = loc[k];
+    for (int o = 16; o > 0; o >>= 1) { const long long u = __shfl_down_sync(0xFFFFFFFFu, v, o); v = k == 16 ? (u > v ? u : v) : v + u; }
+    if ((threadIdx.x & 31) == 0) { if (k == 16) atomicMax((long long *)&acc[16], v); else atomicAdd((unsigned long long *)&acc[k], (unsigned long long)v); }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    out->events = acc[0]; out->site_updates = acc[1]; out->dep[0] = (int)acc[2]; out->dep[1] = (int)acc[3]; out->dep[2] = (int)acc[4];
-    out->evap = (int)acc[5]; out->abs_ = (int)acc[6]; out->des = (int)acc[7]; out->dAtoms = (int)acc[8]; out->dVoids = (int)acc[9];
-    for (int i = 0; i < 3; i++) { out->dCrystal[i] = (int)acc[10 + i]; out->dCov[i] = (int)acc[13 + i]; }
-    out->maxev = (int)acc[16];
+    atomicAdd((unsigned long long *)&out->events, (unsigned long long)acc[0]); atomicAdd((unsigned long long *)&out->site_updates, (unsigned long long)acc[1]);
+    atomicAdd(&out->dep[0], (int)acc[2]); atomicAdd(&out->dep[1], (int)acc[3]); atomicAdd(&out->dep[2], (int)acc[4]);
+    atomicAdd(&out->evap, (int)acc[5]); atomicAdd(&out->abs_, (int)acc[6]); atomicAdd(&out->des, (int)acc[7]); atomicAdd(&out->dAtoms, (int)acc[8]); atomicAdd(&out->dVoids, (int)acc[9]);
+    for (int i = 0; i < 3; i++) { atomicAdd(&out->dCrystal[i], (int)acc[10 + i]); atomicAdd(&out->dCov[i], (int)acc[13 + i]); }
+    atomicMax(&out->maxev, (int)acc[16]);
   }
 }
 
@@ -1298,7 +1312,8 @@ static inline int parallel_run(ParallelCtx &P, DevCtx &H, cudaStream_t st, cudaE
 #endif
   for (; left > 0; left -= std::min<long long>(left, totals_every)) if (batch((int)std::min<long long>(left, totals_every))) return -1;
   if (P.halo && P.halo_pending) { if (halo_exchange(P, H, st, &launches, err)) return -1; P.halo_pending = false; }     // seams consistent when the call returns
-  MSKC_LAUNCH(reduce_tstat_kernel, 1, 256, 0, st, P.tstat, P.ntiles, P.tot);
+  PCK(cudaMemsetAsync(P.tot, 0, sizeof(TileStat), st));
+  MSKC_LAUNCH(reduce_tstat_kernel, 32, 256, 0, st, P.tstat, P.ntiles, P.tot);
   launches++;
   PCK(cudaEventRecord(e1, st));
   PCK(cudaGetLastError());
