@@ -567,11 +567,11 @@ __device__ __forceinline__ bool halo_list(int l) {        // is tile-list l one 
   return tx == 0 || tx == V.ntx - 1;
 }
 // Per-sweep bookkeeping ("per-class rate sums").  Stage 1: this rank's total rate, active-site count and number of tiles that
-// carry rate -> V.red[0..2].  SUM_BLOCKS blocks each reduce a strided share of the tiles into V.red[8 + 4b ..]; the last
+// carry rate -> V.red[0..2], the clipped rate the quantum is sized on -> V.red[3].  SUM_BLOCKS blocks each reduce a strided share of the tiles into V.red[8 + 5b ..]; the last
 // block to finish adds the partial sums in block order (a fixed order: the totals do not depend on which block came last) and,
 // on a single rank, goes straight on to stage 2.  (One block of 1024 threads over the 3.7e4 tiles of the bench box took 24 us
 // per sweep -- 4 % of a sweep; this takes ~4.)
-enum { SUM_BLOCKS = 64 /* = 2 x 32: the last block's warp 0 takes two partial sums per lane */, RED_DOUBLES = 8 + 4 * SUM_BLOCKS };
+enum { SUM_BLOCKS = 64 /* = 2 x 32: the last block's warp 0 takes two partial sums per lane */, RED_DOUBLES = 8 + 5 * SUM_BLOCKS };
 // stage 2 (after the all-reduce of V.red over the ranks, if any): clock, next tau, global-coupling terms
 __device__ __forceinline__ void sweep_finish(int advance) {
   SweepState &s = *V.ss;
@@ -581,21 +581,30 @@ __device__ __forceinline__ void sweep_finish(int advance) {
   // the quantum: events_per_tile events expected per colour step in a tile that carries rate (a nucleus or a ridge
   // occupies few tiles of its box: sizing tau on all tiles would multiply the events per busy tile, i.e. the bias)
   const double nt = V.red[2] > 0.0 ? V.red[2] : s.ntiles_global;
-  s.tau_adaptive = R > 0 ? s.events_per_tile * nt / R : 0.0;
+  // ... on the sum of rates with every tile's share clipped at the kernel's own definition of a transient state (see
+  // sweep_sum_kernel): one unstable atom about to re-evaporate carries more rate than the whole rest of a 10^9-site lattice,
+  // lives for a millionth of a quantum, and would otherwise halve tau for the sweep after every step that happened to end on one
+  const double Rq = V.red[3] > 0.0 ? V.red[3] : R;
+  s.tau_adaptive = Rq > 0 ? s.events_per_tile * nt / Rq : 0.0;
   s.tau = s.tau_fixed > 0 ? s.tau_fixed : s.tau_adaptive;
 }
 __global__ void __launch_bounds__(256) sweep_sum_kernel(int ntiles, int finish_advance /* >= 0: single rank, run stage 2 with this `advance`; < 0: leave it to sweep_finish_kernel */) {
-  __shared__ double sR[8]; __shared__ long long sN[8]; __shared__ int sM[8], sT[8]; __shared__ bool s_last;
-  double r = 0.0; long long n = 0; int mx = 0, nt = 0;        // nt: tiles that carry rate (the tiles the quantum is sized for)
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) { if (halo_list(t)) continue; const double q = V.tile_rate[t]; r += q; nt += q > 0.0; n += V.live[t]; mx = max(mx, V.cnt[t]); }
-  for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); nt += __shfl_down_sync(0xFFFFFFFFu, nt, o); }
-  if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; sT[threadIdx.x >> 5] = nt; }
+  __shared__ double sR[8], sQ[8]; __shared__ long long sN[8]; __shared__ int sM[8], sT[8]; __shared__ bool s_last;
+  double r = 0.0, rq = 0.0; long long n = 0; int mx = 0, nt = 0;        // nt: tiles that carry rate (the tiles the quantum is sized for)
+  // rq: the rate the next quantum is sized on -- a tile expected to fire more than CS_BURST * event_cap events in the quantum
+  // just used is in a transient state (the colour step lifts its event cap for exactly that case) and counts with that bound
+  const SweepState &ss = *V.ss;
+  const double tq = fmax(ss.tau, ss.tau_adaptive);            // (tau itself may be a caller's short landing quantum)
+  const double qcap = tq > 0.0 ? CS_BURST * (double)ss.event_cap / tq : 1.0e300;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += gridDim.x * blockDim.x) { if (halo_list(t)) continue; const double q = V.tile_rate[t]; r += q; rq += fmin(q, qcap); nt += q > 0.0; n += V.live[t]; mx = max(mx, V.cnt[t]); }
+  for (int o = 16; o > 0; o >>= 1) { r += __shfl_down_sync(0xFFFFFFFFu, r, o); rq += __shfl_down_sync(0xFFFFFFFFu, rq, o); n += __shfl_down_sync(0xFFFFFFFFu, n, o); mx = max(mx, __shfl_down_sync(0xFFFFFFFFu, mx, o)); nt += __shfl_down_sync(0xFFFFFFFFu, nt, o); }
+  if ((threadIdx.x & 31) == 0) { sR[threadIdx.x >> 5] = r; sQ[threadIdx.x >> 5] = rq; sN[threadIdx.x >> 5] = n; sM[threadIdx.x >> 5] = mx; sT[threadIdx.x >> 5] = nt; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double R = 0; long long N = 0; int M = 0, T = 0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { R += sR[i]; N += sN[i]; M = max(M, sM[i]); T += sT[i]; }
-    double *part = V.red + 8 + 4 * blockIdx.x;
-    part[0] = R; part[1] = (double)N; part[2] = (double)T; part[3] = (double)M;
+    double R = 0, Q = 0; long long N = 0; int M = 0, T = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { R += sR[i]; Q += sQ[i]; N += sN[i]; M = max(M, sM[i]); T += sT[i]; }
+    double *part = V.red + 8 + 5 * blockIdx.x;
+    part[0] = R; part[1] = (double)N; part[2] = (double)T; part[3] = (double)M; part[4] = Q;
     __threadfence();
     unsigned int *done = reinterpret_cast<unsigned int *>(V.red + 4);
     s_last = atomicAdd(done, 1u) == gridDim.x - 1;
@@ -606,14 +615,14 @@ __global__ void __launch_bounds__(256) sweep_sum_kernel(int ntiles, int finish_a
   // the last block: warp 0 adds the SUM_BLOCKS partial sums -- lane l takes blocks l and l + 32, then a shuffle tree: a fixed
   // order whichever block came last (64 dependent L2 reads by one thread took 15 us)
   __threadfence();
-  const volatile double *q0 = V.red + 8 + 4 * threadIdx.x, *q1 = V.red + 8 + 4 * (threadIdx.x + 32);
-  double tR = q0[0] + q1[0], tN = q0[1] + q1[1], tT = q0[2] + q1[2], tM = fmax(q0[3], q1[3]);
+  const volatile double *q0 = V.red + 8 + 5 * threadIdx.x, *q1 = V.red + 8 + 5 * (threadIdx.x + 32);
+  double tR = q0[0] + q1[0], tN = q0[1] + q1[1], tT = q0[2] + q1[2], tM = fmax(q0[3], q1[3]), tQ = q0[4] + q1[4];
   for (int o = 16; o > 0; o >>= 1) {
     tR += __shfl_down_sync(0xFFFFFFFFu, tR, o); tN += __shfl_down_sync(0xFFFFFFFFu, tN, o); tT += __shfl_down_sync(0xFFFFFFFFu, tT, o);
-    tM = fmax(tM, __shfl_down_sync(0xFFFFFFFFu, tM, o));
+    tM = fmax(tM, __shfl_down_sync(0xFFFFFFFFu, tM, o)); tQ += __shfl_down_sync(0xFFFFFFFFu, tQ, o);
   }
   if (threadIdx.x == 0) {
-    V.red[0] = tR; V.red[1] = tN; V.red[2] = tT; V.red[3] = 0.0;
+    V.red[0] = tR; V.red[1] = tN; V.red[2] = tT; V.red[3] = tQ;
     V.ss->max_cnt = (long long)tM;
     if (finish_advance >= 0) sweep_finish(finish_advance);
   }
