@@ -397,18 +397,34 @@ def run_ours(args):
         gx, gy, gz = args.strong_box
         sc = make_ctx(gx, gy, gz)
         fresh(sc)
-        # (the slab grows ~2.5 planes per step from plane 27 and this box has 48 of them: a bounded number of steps)
-        swarm, ssteps = min(args.warmup, 1), min(args.steps, 3)
-        for i in range(swarm):
-            sc.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 300 + i)
+        # This box is 48 planes high and the slab fills 27 of them; the SiC surface roughens fast (after 128 sweeps the highest
+        # active site of a 10^9-site box stands 12+ planes above the mean, and an event there reaches 8 planes further: the
+        # library then stops with "lattice access outside 0..LenZ", as the reference would read foreign memory).  So the
+        # strong-scaling point runs 8-sweep steps, 1 untimed + 3 timed: 32 sweeps, far from the top.
+        ssweeps = max(1, args.sweeps // 4)
+        swarm, ssteps = min(args.warmup, 1), max(1, min(args.steps, 3))
+        sev, s0, s1, serr = 0, 0.0, 0.0, None
+        # (every rank passes both barriers whatever happens: a rank that stops with an error makes its neighbours' halo wait
+        # time out, and the collectives below must still line up)
+        try:
+            for i in range(swarm):
+                sc.run_parallel(ssweeps, events_per_tile=args.ept, seed=seed + 300 + i)
+        except Exception as e:
+            serr = str(e)
         barrier(); s0 = time.perf_counter()
-        sev = 0
-        for i in range(ssteps):
-            sev += sc.run_parallel(args.sweeps, events_per_tile=args.ept, seed=seed + 400 + i).events_done
+        try:
+            for i in range(ssteps if serr is None else 0):
+                sev += sc.run_parallel(ssweeps, events_per_tile=args.ept, seed=seed + 400 + i).events_done
+        except Exception as e:
+            serr = str(e)
         barrier(); s1 = time.perf_counter()
+        okf = torch.tensor([0.0 if serr else 1.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        strong_ok = okf.item() > 0.5
         # seam consistency (N > 1): my right halo column must equal the right neighbour's first owned column and vice versa
         seam = None
-        if world > 1:
+        if world > 1 and strong_ok:
             L = torch.from_numpy(sc.download_lattice()).cuda()
             own = gx // world
             mine = torch.stack([L[:, :, 24:48], L[:, :, own:own + 24]]).contiguous()              # [first owned, last owned]
@@ -429,8 +445,8 @@ def run_ours(args):
         else:
             sdt, sevs = s1 - s0, float(sev)
         sntc = (gx // world // 48) * (gy // 48)
-        strong = {"value": sevs / sdt, "unit": UNIT, "scaling": "strong", "global_box": [gx, gy, gz], "sites": gx * gy * gz, "n_gpus": world,
-                  "ms_per_step": 1e3 * sdt / ssteps, "steps": ssteps, "warmup": swarm, "tiles_per_colour_per_gpu": sntc, "team": 32 if sntc <= 148 * 16 else (16 if sntc <= 2 * 148 * 16 else 8),
+        strong = {"value": sevs / sdt if strong_ok and sdt > 0 else None, "unit": UNIT, "scaling": "strong", "global_box": [gx, gy, gz], "sites": gx * gy * gz, "n_gpus": world,
+                  "ms_per_step": 1e3 * sdt / ssteps if strong_ok else None, "steps": ssteps, "warmup": swarm, "sweeps_per_step": ssweeps, "error": serr, "tiles_per_colour_per_gpu": sntc, "team": 32 if sntc <= 148 * 16 else (16 if sntc <= 2 * 148 * 16 else 8),
                   "seam_check": seam,
                   "note": "a colour step is bound by the serial event chain of its busiest tile; the number of concurrently running tiles (box/48)^2 is fixed by the box, so more GPUs "
                           "shorten the chain only through wider teams per tile (DESIGN.md section 8)"}
@@ -479,6 +495,10 @@ def main():
     ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
+    # the bench box leaves 69 planes above the slab and the surface climbs ~3 planes per 100 sweeps while its highest towers run
+    # ahead of the mean (an event that reaches past the top plane stops the library, as the reference would read foreign memory):
+    # a leg (warm-up + timed steps + the coupling cycles after them) stays under ~640 sweeps, so a long run gets shorter steps
+    args.sweeps = min(args.sweeps, max(8, 640 // (args.steps + args.warmup + 3)))
     # stdout carries exactly ONE line, the JSON: whatever libraries print there (NCCL's version banner, ...) goes to stderr
     sys.stdout.flush()
     keep = os.dup(1)

@@ -106,6 +106,7 @@ static const char *dev_err_text(int code) {
     case E_TRANGE: return "site temperature outside the table range given to mskc_set_la";
     case E_BADEV: return "invalid event code";
     case E_FLAGS: return "incremental census flags disagree with the full neighbour census";
+    case E_HALO_TIMEOUT: return "slab mode: the neighbouring rank did not deliver its halo records (it stopped, or its process is gone)";
   }
   return "unknown device error";
 }

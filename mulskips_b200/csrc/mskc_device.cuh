@@ -35,7 +35,8 @@ enum {
   E_PICK = 5 /* PickTreeEvent.f:58 */, E_ADD_ZERO = 6 /* Add.f:38 */, E_MC_FULL = 7 /* Add.f:42 */, E_VOID_FULL = 8 /* Add.f:94 */,
   E_ERASE = 9 /* Erase.f:47 */, E_COVOCC = 10 /* Get_Prob.f:94 */, E_COVLIST = 11 /* Get_Prob.f:108 */, E_CENSUS = 12 /* Get_Prob.f:293 */,
   E_TEMP0 = 13 /* Get_Prob.f:133 */, E_NNCOV = 14 /* deposition.f:194 */, E_TILE_FULL = 15, E_STALE_NBUFF = 16, E_TRANGE = 17, E_BADEV = 18,
-  E_FLAGS = 19 /* incremental census flags disagree with the full census (mskc_coop.cuh) */
+  E_FLAGS = 19 /* incremental census flags disagree with the full census (mskc_coop.cuh) */,
+  E_HALO_TIMEOUT = 20 /* slab mode: a neighbour rank never published its halo records */
 };
 
 struct P3 { int x, y, z; };

