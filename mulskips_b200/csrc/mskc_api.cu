@@ -979,12 +979,17 @@ extern "C" int mskc_replay_teams(mskc_ctx *h, int64_t n, const int32_t *site_xyz
     dx = std::min(dx, D.LX - dx); dy = std::min(dy, D.LY - dy);
     return dx > 48 || dy > 48;
   };
+  // lanes per team: 8 (four teams, the throughput configuration) or, MSKC_REPLAY_TEAM=16, two 16-lane teams (the instantiation
+  // mskc_run_parallel picks when a colour has few tiles)
+  int team = 8;
+  if (const char *e = getenv("MSKC_REPLAY_TEAM")) { if (atoi(e) == 16) team = 16; }
+  const int nteams = 32 / team;
   std::vector<int32_t> batch; int64_t nb = 0, shared = 0;
   for (int64_t i = 0; i < n;) {
     int64_t j = i + 1;
-    while (j < n && j - i < 4) { bool ok = true; for (int64_t k = i; k < j; k++) ok = ok && far(k, j); if (!ok) break; j++; }
+    while (j < n && j - i < nteams) { bool ok = true; for (int64_t k = i; k < j; k++) ok = ok && far(k, j); if (!ok) break; j++; }
     int32_t row[4] = {-1, -1, -1, -1};
-    for (int64_t k = i; k < j; k++) row[(nb + (k - i)) & 3] = (int32_t)k;
+    for (int64_t k = i; k < j; k++) row[(nb + (k - i)) % nteams] = (int32_t)k;
     batch.insert(batch.end(), row, row + 4);
     if (j - i > 1) shared++;
     nb++; i = j;
@@ -998,8 +1003,9 @@ extern "C" int mskc_replay_teams(mskc_ctx *h, int64_t n, const int32_t *site_xyz
   CK(cudaMemsetAsync(d_out, 0, sizeof(TileStat), h->stream));
   const int feat = (D.NCov > 0 ? F_COV : 0) | (D.la ? F_LA : 0);
   typedef void (*rp_kernel_t)(const int32_t *, const int32_t *, const int32_t *, const int32_t *, long long, double, TileStat *);
-  static const rp_kernel_t kern[4] = {replay_teams_kernel<0>, replay_teams_kernel<1>, replay_teams_kernel<2>, replay_teams_kernel<3>};
-  const rp_kernel_t k = kern[feat];
+  static const rp_kernel_t kern[4] = {replay_teams_kernel<8, 0>, replay_teams_kernel<8, 1>, replay_teams_kernel<8, 2>, replay_teams_kernel<8, 3>};
+  static const rp_kernel_t kern16[4] = {replay_teams_kernel<16, 0>, replay_teams_kernel<16, 1>, replay_teams_kernel<16, 2>, replay_teams_kernel<16, 3>};
+  const rp_kernel_t k = team == 16 ? kern16[feat] : kern[feat];
   const int64_t chunk = 1000;                    // iterations per launch; tombstones are dropped between launches
   for (int64_t b0 = 0; b0 < nb; b0 += chunk) {
     const int64_t m = nb - b0 < chunk ? nb - b0 : chunk;

@@ -536,13 +536,14 @@ __global__ void __launch_bounds__(32) replay_kernel(const int32_t *ev_site, cons
   }
 }
 
-// Trace replay through the instantiation the sampler itself runs: four 8-lane teams in lock step, FEAT as
+// Trace replay through the instantiations the sampler itself runs: 32 / TEAM teams of TEAM lanes in lock step (TEAM = 8: the
+// throughput configuration; 16: what mskc_run_parallel picks when a colour has few tiles, e.g. the strong-scaling slabs), FEAT as
 // mskc_run_parallel picks it.  batch[4*b + t] = index of the event team t applies in lock-step iteration b, or -1 (the
 // team idles through the iteration, as a tile without an event does).  Events of one iteration commute (the host puts
 // only events more than two tile edges apart into one iteration), so the outcome equals the serial trace.
-template <int FEAT>
+template <int TEAM, int FEAT>
 __global__ void __launch_bounds__(32) replay_teams_kernel(const int32_t *ev_site, const int32_t *ev_code, const int32_t *ev_arm, const int32_t *batch, long long nbatch, double root, TileStat *out) {
-  const int lane = threadIdx.x, team = lane >> 3, tl = lane & 7;
+  const int lane = threadIdx.x, team = lane / TEAM, tl = lane % TEAM;
   TileLists L; L.own = -1; L.mark = 0; L.s_rate = nullptr; L.s_ce = nullptr; L.s_n = nullptr;
   CoopCounters K; K.nsu = 0; K.dAtoms = 0; K.dVoids = 0;
   for (int i = 0; i < 3; i++) { K.dCrystal[i] = 0; K.dCov[i] = 0; }
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(32) replay_teams_kernel(const int32_t *ev_site
     const bool go = i >= 0;
     P3 S; S.x = S.y = S.z = 0; int code = 4, arm = 0;
     if (go) { S.x = ev_site[3 * i]; S.y = ev_site[3 * i + 1]; S.z = ev_site[3 * i + 2]; code = ev_code[i]; arm = ev_arm[i]; }
-    coop_event<8, FEAT>(L, tl, go, S, go ? (uint32_t)cidx(S) : 0u, code, root, 0.5, arm == 0 ? -1 : arm - 1, K);
+    coop_event<TEAM, FEAT>(L, tl, go, S, go ? (uint32_t)cidx(S) : 0u, code, root, 0.5, arm == 0 ? -1 : arm - 1, K);
     if (go && tl == 0) done++;
     if (__any_sync(0xFFFFFFFFu, D.err[0] != 0)) break;
   }

@@ -131,6 +131,14 @@ def test_replay_teams(tmp_path, case, box, lens, nev, kw):
     ctx.close(); orc.close()
 
 
+@pytest.mark.parametrize("case,box,lens,nev,kw", [TEAM_CASES[2], TEAM_CASES[4]], ids=[TEAM_CASES[2][0], TEAM_CASES[4][0]])
+def test_replay_teams_16_lanes(tmp_path, monkeypatch, case, box, lens, nev, kw):
+    """the same through two 16-lane teams: the instantiation mskc_run_parallel picks when a colour has 2369..4736 tiles (the
+    strong-scaling slabs at two GPUs) -- hexagonal-phase SiC and Si CVD with coverage"""
+    monkeypatch.setenv("MSKC_REPLAY_TEAM", "16")
+    test_replay_teams(tmp_path, case, box, lens, nev, kw)
+
+
 def test_replay_laser_annealing(tmp_path):
     """the cooperative transition code with the LA rate law (temperature-indexed tables, T kept in erased words)"""
     from cases import make_la_case
