@@ -1023,7 +1023,7 @@ void e15_8(double v, char out[32]) {                         // Fortran E15.8: 0
 }
 void atom_line(FILE *f, const char *el, double sf, int x, int y, int z, const char *tail) { fprintf(f, "%s%10.5f %10.5f %10.5f%s\n", el, sf * x, sf * y, sf * z, tail); }
 
-struct Run { mskc_ctx *h = nullptr; long long Iter = 1, IterOut = 0, framecounter = 0; double Time = 0; int NumAtoms = 0, NumVoids = 0, NumAdAtom = 0; };
+struct Run { mskc_ctx *h = nullptr; long long Iter = 1, IterOut = 0, framecounter = 0; double Time = 0; int NumAtoms = 0, NumVoids = 0, NumAdAtom = 0; bool sampler = false; };
 
 #define MS(call) do { if ((call) != 0) die(" %s", mskc_last_error(R.h)); } while (0)
 
@@ -1036,11 +1036,28 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     mskc_counters c; MS(mskc_get_counters(R.h, &c));
     for (int i = 0; i < 3; i++) { H.CountCrystal[i] = c.CountCrystal[i]; H.CountCov[i] = c.CountCov[i]; H.CountLiquid[i] = H.InitCountCrystal[i] - c.CountCrystal[i]; }
     H.NumAdAtomOcc = c.num_adatom_occ;
+    if (R.sampler) {
+      // the sampler keeps no reference-ordered vacancy list (mskc_download_lists reads the serial loop's): the vacancies are
+      // the empty 4-coordinated sites of the lattice (Add.f:82-100 is called exactly when an empty site reaches four
+      // neighbours), here in z,y,x scan order, with their bond lists from the device
+      std::vector<int32_t> vx;
+      for (int z = 0; z <= LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+        const int32_t w = H.L[H.ci(x, y, z)];
+        if (w != 0 && ibits(w, PosOcc, 1) == 0 && ibits(w, PosCoor, LenCoor) == 4 && ibits(w, PosIndex, LenIndex) != 113) { vx.push_back(x); vx.push_back(y); vx.push_back(z); }
+      }
+      voids.resize(vx.size() / 3);
+      if (!voids.empty()) {
+        std::vector<int32_t> vn(12 * voids.size());
+        MS(mskc_download_bonds(R.h, (int64_t)voids.size(), vx.data(), vn.data()));
+        for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
+      }
+    } else {
     voids.resize((size_t)std::max(c.num_voids, 0));
     if (!voids.empty()) {
       std::vector<int32_t> vx(3 * voids.size()), vn(12 * voids.size());
       MS(mskc_download_lists(R.h, nullptr, nullptr, nullptr, nullptr, vx.data(), vn.data(), nullptr, nullptr, 0, nullptr));
       for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
+    }
     }
   } else voids = H.voids;
   if (H.la_tree) {                                          // la/inpout/WriteMolMolSource.f:42-67
@@ -1420,7 +1437,7 @@ int main(int argc, char **argv) {
   if (mode < 0) { if (const char *e = getenv("MSKC_MODE")) mode = !strcmp(e, "parallel") ? 1 : (!strcmp(e, "parity") ? 0 : -1); }
   if (exact_restart) mode = 0;                                // (the same trajectory: the serial loop)
   if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
-  parallel = mode == 1;
+  parallel = mode == 1; R.sampler = parallel;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;

@@ -315,6 +315,12 @@ def test_host_parallel_mode(built, tmp_path, kind):
     assert t is not None and int(t[3]) > 20000 and float(t[4]) > 0
     err = open(tmp_path / "err.txt").read()
     assert "sublattice-sampler" in err
+    # every frame is well-formed: the header count is the number of atom lines, and no vacancy sits at the absolute origin
+    # (the sampler's vacancy list comes from the lattice, not from the serial loop's list)
+    for f in frames:
+        lines = [l for l in open(tmp_path / f).read().split("\n")[2:] if l.strip()]
+        assert int(open(tmp_path / f).readline().split()[0]) == len(lines), f
+        assert not any(l.split()[0] == "O" and all(float(v) == 0.0 for v in l.split()[1:4]) for l in lines), f
 
 
 def test_shape_builder(built, tmp_path):
