@@ -397,27 +397,55 @@ def run_ours(args):
         gx, gy, gz = args.strong_box
         sc = make_ctx(gx, gy, gz)
         fresh(sc)
-        # This box is 48 planes high and the slab fills 27 of them; the SiC surface roughens fast (after 128 sweeps the highest
-        # active site of a 10^9-site box stands 12+ planes above the mean, and an event there reaches 8 planes further: the
-        # library then stops with "lattice access outside 0..LenZ", as the reference would read foreign memory).  So the
-        # strong-scaling point runs 8-sweep steps, 1 untimed + 3 timed: 32 sweeps, far from the top.
-        ssweeps = max(1, args.sweeps // 4)
-        swarm, ssteps = min(args.warmup, 1), max(1, min(args.steps, 3))
-        sev, s0, s1, serr = 0, 0.0, 0.0, None
-        # (every rank passes both barriers whatever happens: a rank that stops with an error makes its neighbours' halo wait
-        # time out, and the collectives below must still line up)
-        try:
-            for i in range(swarm):
-                sc.run_parallel(ssweeps, events_per_tile=args.ept, seed=seed + 300 + i)
-        except Exception as e:
-            serr = str(e)
-        barrier(); s0 = time.perf_counter()
-        try:
-            for i in range(ssteps if serr is None else 0):
-                sev += sc.run_parallel(ssweeps, events_per_tile=args.ept, seed=seed + 400 + i).events_done
-        except Exception as e:
-            serr = str(e)
-        barrier(); s1 = time.perf_counter()
+        # This box is 48 planes high and the flat slab reaches plane 30; the SiC surface roughens fast and the tallest tower of a
+        # 10^9-site surface runs far ahead of the mean (measured: a top atom at plane 44 within 128 sweeps; an event on its
+        # free site then reads plane 50 and the library stops with "lattice access outside 0..LenZ", as the reference would
+        # read foreign memory).  So this point runs SHORT steps (4 sweeps) and looks at the highest printed atom of the whole
+        # box (frame extraction, max over ranks) before every step: it goes on only while that atom leaves 12 planes of head
+        # room, i.e. it times as many steps as the box allows (up to 6) and says how many.  Every rank takes the same decision.
+        ssweeps = max(1, min(4, args.sweeps))
+        swarm, smax = 1, 6
+        head = 12
+
+        def top_plane():
+            z, e_ = 0.0, None
+            try:
+                cells, _, _ = sc.extract_frame()
+                z = float(int(cells.max()) // (sc.LenX * sc.LenY)) if len(cells) else 0.0
+            except Exception as e:
+                z, e_ = 1e6, str(e)
+            t = torch.tensor([z], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return int(t.item()), e_
+
+        def all_ok(flag):
+            t = torch.tensor([1.0 if flag else 0.0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return t.item() > 0.5
+
+        sev, sdt_local, ssteps, serr, tops = 0, 0.0, 0, None, []
+        # (every rank passes the same collectives whatever happens: a rank that stops with an error makes its neighbours' halo
+        # wait time out, the error is agreed on after every step and all ranks leave the loop together)
+        for i in range(swarm + smax):
+            top, e_ = top_plane()
+            tops.append(top); serr = serr or e_
+            if not all_ok(serr is None) or tops[-1] > gz - head:
+                break
+            barrier(); s0 = time.perf_counter()
+            try:
+                n_ev = sc.run_parallel(ssweeps, events_per_tile=args.ept, seed=seed + 300 + i).events_done
+            except Exception as e:
+                serr = str(e); n_ev = 0
+            barrier(); s1 = time.perf_counter()
+            if not all_ok(serr is None):
+                break
+            if i >= swarm:
+                sev += n_ev; sdt_local += s1 - s0; ssteps += 1
+        if serr is None and ssteps == 0:
+            serr = f"box outgrown before a timed step: highest atom at plane {tops[-1]} of {gz}"
+        s0, s1 = 0.0, sdt_local
         okf = torch.tensor([0.0 if serr else 1.0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(okf, op=dist.ReduceOp.MIN)
@@ -446,7 +474,8 @@ def run_ours(args):
             sdt, sevs = s1 - s0, float(sev)
         sntc = (gx // world // 48) * (gy // 48)
         strong = {"value": sevs / sdt if strong_ok and sdt > 0 else None, "unit": UNIT, "scaling": "strong", "global_box": [gx, gy, gz], "sites": gx * gy * gz, "n_gpus": world,
-                  "ms_per_step": 1e3 * sdt / ssteps if strong_ok else None, "steps": ssteps, "warmup": swarm, "sweeps_per_step": ssweeps, "error": serr, "tiles_per_colour_per_gpu": sntc, "team": 32 if sntc <= 148 * 16 else (16 if sntc <= 2 * 148 * 16 else 8),
+                  "ms_per_step": 1e3 * sdt / ssteps if strong_ok and ssteps else None, "steps": ssteps, "warmup": swarm, "sweeps_per_step": ssweeps, "error": serr,
+                  "highest_atom_plane_before_each_step": tops, "head_room_planes": head, "tiles_per_colour_per_gpu": sntc, "team": 32 if sntc <= 148 * 16 else (16 if sntc <= 2 * 148 * 16 else 8),
                   "seam_check": seam,
                   "note": "a colour step is bound by the serial event chain of its busiest tile; the number of concurrently running tiles (box/48)^2 is fixed by the box, so more GPUs "
                           "shorten the chain only through wider teams per tile (DESIGN.md section 8)"}
