@@ -7,7 +7,8 @@ colour steps each).  Workload (config.workload): flat 3C-SiC(001) slab, the refe
 start-cube-zigzag.dat), 4608x4608x96 super-lattice cells (2.0e9 sites; the 4608x4608 surface of the 10^9-site C5 slab
 with head-room for roughness) PER GPU, built on the device with the geometry of initial/SetSiC3C.f.  N>1: one slab per
 rank (weak scaling), plus the north star's strong-scaling point (`strong_1e9`: ONE 4608x4608x48 box = 1.04e9 sites cut
-into N x-slabs) and a seam-consistency check of the halo exchange.
+into N x-slabs, short steps behind a head-room guard: the 48-plane box is outgrown within a few dozen sweeps) and a
+seam-consistency check of the halo exchange.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 

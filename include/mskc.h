@@ -260,6 +260,20 @@ int mskc_download_bonds(mskc_ctx *h, int64_t n, const int32_t *xyz, int32_t *nn)
  * surface only instead of the whole lattice.  Unordered; sort by cell for the reference's z,y,x order.
  * cap = capacity of the two arrays (host memory), *n = cells found (may exceed cap: call again with more). */
 int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms);
+/* The complete frame without the lattice, for the host program's frame writer (inpout/WriteMolMolXYZFile.f:77-260): the
+ * cells above plus every cell one of the writer's tests touches -- coverage ids 1 / 17 whatever else the word holds
+ * (:169-176), atoms of species 1..3 with coordination <= 3 (:177-215), the cells of the two counting scans (:77-92) and
+ * the empty 4-coordinated sites, i.e. the vacancies of _v.xyz (Add.f:82-100 lists a site exactly when it reaches four
+ * neighbours while empty).  Same calling convention as mskc_extract_frame; the plane ranges of the individual scans are
+ * the caller's (it has the coordinates). */
+int mskc_extract_frame_all(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms);
+/* The antisite scan of the SiC frame writer (inpout/WriteMolMolXYZFile.f:267-398) on the device: (cell, word) of every
+ * 4-coordinated atom of planes 1..LenZ-1 whose number of bonded neighbours of the other species equals target, 0 (the
+ * atoms the reference flips, :330-349) or 3 (the atoms it prints into _w.xyz, :352-372).  Unordered, as above. */
+int mskc_extract_antisites(mskc_ctx *h, int target, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms);
+/* lattice words of n given cells (cell = x + LenX*(y + LenY*z)): what a writer needs of the neighbours of a vacancy
+ * (WriteMolMolXYZFile.f:233-256) without downloading the lattice */
+int mskc_gather_lattice(mskc_ctx *h, int64_t n, const int64_t *cell, int32_t *word);
 
 /* diagnostics: the sampler keeps the neighbour census of every site incrementally (two flag bits per bond: species of
  * the occupied, reciprocal neighbour -- what Get_Prob.f:216-291 recounts at every call).  This recomputes the census of

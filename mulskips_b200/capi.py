@@ -69,7 +69,7 @@ SYMBOLS = ["mskc_create", "mskc_destroy", "mskc_last_error", "mskc_set_rates", "
            "mskc_rerate_all", "mskc_set_temperature", "mskc_download_lattice", "mskc_patch_lattice", "mskc_get_counters",
            "mskc_download_lists", "mskc_state_hash", "mskc_census_lattice", "mskc_debug_tile_stats",
            "mskc_replay_events", "mskc_download_active", "mskc_download_bonds",
-           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame", "mskc_check_flags", "mskc_replay_teams", "mskc_set_temperature_u16", "mskc_download_phases", "mskc_last_dense_ms"]
+           "mskc_create_slab", "mskc_comm_unique_id", "mskc_comm_connect", "mskc_extract_frame", "mskc_extract_frame_all", "mskc_extract_antisites", "mskc_gather_lattice", "mskc_check_flags", "mskc_replay_teams", "mskc_set_temperature_u16", "mskc_download_phases", "mskc_last_dense_ms"]
 
 
 def load_library():
@@ -115,6 +115,9 @@ def load_library():
     lib.mskc_comm_unique_id.argtypes = [C.c_void_p]
     lib.mskc_comm_connect.argtypes = [vp, C.c_void_p]
     lib.mskc_extract_frame.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
+    lib.mskc_extract_frame_all.argtypes = [vp, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
+    lib.mskc_extract_antisites.argtypes = [vp, C.c_int, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), i64p, C.POINTER(C.c_float)]
+    lib.mskc_gather_lattice.argtypes = [vp, C.c_int64, i64p, C.POINTER(C.c_int32)]
     lib.mskc_set_temperature_u16.argtypes = [vp, C.POINTER(C.c_uint16)]
     lib.mskc_download_phases.argtypes = [vp, C.POINTER(C.c_uint8)]
     lib.mskc_last_dense_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -380,6 +383,32 @@ class Mskc:
         k = min(n.value, cap)
         o = np.argsort(cells[:k], kind="stable")
         return cells[:k][o], words[:k][o], ms.value
+
+    def _extract(self, fn, *pre):
+        u32p = C.POINTER(C.c_uint32)
+        n = C.c_int64(); ms = C.c_float()
+        self._ck(fn(self.h, *pre, 0, None, None, C.byref(n), C.byref(ms)))
+        cap = max(n.value, 1)
+        cells, words = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        self._ck(fn(self.h, *pre, cap, cells.ctypes.data_as(u32p), words.ctypes.data_as(u32p), C.byref(n), C.byref(ms)))
+        k = min(n.value, cap)
+        o = np.argsort(cells[:k], kind="stable")
+        return cells[:k][o], words[:k][o], ms.value
+
+    def extract_frame_all(self):
+        """(cells, words, kernel_ms) of every cell any frame writer prints or counts, vacancies included, sorted by cell"""
+        return self._extract(self.lib.mskc_extract_frame_all)
+
+    def extract_antisites(self, target):
+        """(cells, words, kernel_ms): 4-coordinated atoms of planes 1..LenZ-1 with `target` (0 or 3) neighbours of the other species"""
+        return self._extract(self.lib.mskc_extract_antisites, int(target))
+
+    def gather_lattice(self, cells):
+        c = np.ascontiguousarray(cells, np.int64)
+        w = np.zeros(max(len(c), 1), np.int32)
+        if len(c):
+            self._ck(self.lib.mskc_gather_lattice(self.h, len(c), c.ctypes.data_as(C.POINTER(C.c_int64)), w.ctypes.data_as(C.POINTER(C.c_int32))))
+        return w[:len(c)]
 
     def check_flags(self):
         """(sites, stored census flags that differ from a fresh census, sites whose coordination differs from the census, ms)"""

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <array>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 using namespace mskc;
@@ -674,13 +675,34 @@ extern "C" int mskc_download_lattice(mskc_ctx *h, int32_t *LattCoo) {
 }
 extern "C" int mskc_patch_lattice(mskc_ctx *h, int n, const int64_t *cell, const int32_t *word) {
   if (!h) return set_err(h, "mskc_patch_lattice: NULL handle");
+  if (n <= 0) return 0;
+  if (!cell || !word) return set_err(h, "mskc_patch_lattice: NULL argument");
   CK(cudaSetDevice(h->device));
+  // one upload + one scatter kernel (the frame writer's antisite pass patches a list of cells twice per frame); a cell that
+  // occurs twice keeps its LAST word, as a loop of single stores would
+  std::vector<uint32_t> c((size_t)n), w((size_t)n);
   for (int i = 0; i < n; i++) {
     if (cell[i] < 0 || cell[i] >= h->D.ncell) return set_err(h, "mskc_patch_lattice: cell out of range");
-    if (h->tree_variant == MSKC_TREE_LA) { const uint32_t w = word_to_dev((uint32_t)word[i]); CK(cudaMemcpy(h->D.state + cell[i], &w, 4, cudaMemcpyHostToDevice)); }
-    else CK(cudaMemcpyAsync(h->D.state + cell[i], word + i, 4, cudaMemcpyHostToDevice, h->stream));
+    c[(size_t)i] = (uint32_t)cell[i];
+    w[(size_t)i] = h->tree_variant == MSKC_TREE_LA ? word_to_dev((uint32_t)word[i]) : (uint32_t)word[i];
   }
+  {                                                           // duplicates: keep the last occurrence only
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int p, int q) { return c[(size_t)p] < c[(size_t)q]; });
+    std::vector<uint32_t> c2, w2;
+    for (int k = 0; k < n; k++) if (k + 1 == n || c[(size_t)order[(size_t)k]] != c[(size_t)order[(size_t)k + 1]]) { c2.push_back(c[(size_t)order[(size_t)k]]); w2.push_back(w[(size_t)order[(size_t)k]]); }
+    c.swap(c2); w.swap(w2);
+  }
+  const size_t m = c.size();
+  uint32_t *d_c = nullptr, *d_w = nullptr;
+  CK(cudaMalloc(&d_c, m * 4)); CK(cudaMalloc(&d_w, m * 4));
+  CK(cudaMemcpyAsync(d_c, c.data(), m * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_w, w.data(), m * 4, cudaMemcpyHostToDevice, h->stream));
+  MSKC_LAUNCH(scatter_state, (unsigned)((m + 255) / 256), 256, 0, h->stream, h->D.state, (const uint32_t *)d_c, (const uint32_t *)d_w, (long long)m);
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_c); cudaFree(d_w);
   return 0;
 }
 extern "C" int mskc_get_counters(mskc_ctx *h, mskc_counters *c) {
@@ -1114,9 +1136,10 @@ extern "C" int mskc_comm_connect(mskc_ctx *h, const void *id128) {
   return 0;
 }
 
-extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
-  if (!h || !n) return set_err(h, "mskc_extract_frame: NULL argument");
-  if (!h->have_state) return set_err(h, "mskc_extract_frame: no state");
+// which = 0: the cells of mskc_extract_frame; 1: mskc_extract_frame_all; 2 / 3: mskc_extract_antisites with target 0 / 3
+static int extract_cells(mskc_ctx *h, const char *who, int which, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
+  if (!h || !n) return set_err(h, "%s: NULL argument", who);
+  if (!h->have_state) return set_err(h, "%s: no state", who);
   CK(cudaSetDevice(h->device));
   if (cap < 0) cap = 0;
   if (cap > h->frame_cap || !h->d_frame_n) {
@@ -1128,7 +1151,9 @@ extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint
   if (upload_consts(h)) return -1;
   CK(cudaMemsetAsync(h->d_frame_n, 0, 8, h->stream));
   CK(cudaEventRecord(h->ev0, h->stream));
-  MSKC_LAUNCH(frame_extract_kernel, 148 * 8, 256, 0, h->stream, h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
+  if (which == 0) MSKC_LAUNCH(frame_extract_kernel<0>, 148 * 8, 256, 0, h->stream, h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
+  else if (which == 1) MSKC_LAUNCH(frame_extract_kernel<1>, 148 * 8, 256, 0, h->stream, h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
+  else MSKC_LAUNCH(antisite_kernel, 148 * 8, 256, 0, h->stream, which == 2 ? 0 : 3, h->d_frame_cell, h->d_frame_word, (unsigned long long)cap, h->d_frame_n);
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaGetLastError());
   unsigned long long cnt = 0;
@@ -1141,5 +1166,35 @@ extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint
   if (h->tree_variant == MSKC_TREE_LA && word) for (int64_t i = 0; i < m; i++) word[i] = word_from_dev(word[i]);
   if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, h->ev0, h->ev1));
   *n = (int64_t)cnt;
+  return 0;
+}
+extern "C" int mskc_extract_frame(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
+  return extract_cells(h, "mskc_extract_frame", 0, cap, cell, word, n, kernel_ms);
+}
+extern "C" int mskc_extract_frame_all(mskc_ctx *h, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
+  return extract_cells(h, "mskc_extract_frame_all", 1, cap, cell, word, n, kernel_ms);
+}
+extern "C" int mskc_extract_antisites(mskc_ctx *h, int target, int64_t cap, uint32_t *cell, uint32_t *word, int64_t *n, float *kernel_ms) {
+  if (target != 0 && target != 3) return set_err(h, "mskc_extract_antisites: target must be 0 or 3 (WriteMolMolXYZFile.f:330,352)");
+  return extract_cells(h, "mskc_extract_antisites", target == 0 ? 2 : 3, cap, cell, word, n, kernel_ms);
+}
+extern "C" int mskc_gather_lattice(mskc_ctx *h, int64_t n, const int64_t *cell, int32_t *word) {
+  if (!h || (n > 0 && (!cell || !word))) return set_err(h, "mskc_gather_lattice: NULL argument");
+  if (!h->have_state) return set_err(h, "mskc_gather_lattice: no state");
+  if (n <= 0) return 0;
+  CK(cudaSetDevice(h->device));
+  std::vector<uint32_t> c((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    if (cell[i] < 0 || cell[i] >= h->D.ncell) return set_err(h, "mskc_gather_lattice: cell out of range");
+    c[(size_t)i] = (uint32_t)cell[i];
+  }
+  uint32_t *d_c = nullptr, *d_w = nullptr;
+  CK(cudaMalloc(&d_c, (size_t)n * 4)); CK(cudaMalloc(&d_w, (size_t)n * 4));
+  CK(cudaMemcpyAsync(d_c, c.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  MSKC_LAUNCH(gather_state, (unsigned)((n + 255) / 256), 256, 0, h->stream, (const uint32_t *)h->D.state, (const uint32_t *)d_c, d_w, (long long)n);
+  CK(cudaMemcpyAsync(word, d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_c); cudaFree(d_w);
+  if (h->tree_variant == MSKC_TREE_LA) for (int64_t i = 0; i < n; i++) word[i] = (int32_t)word_from_dev((uint32_t)word[i]);
   return 0;
 }

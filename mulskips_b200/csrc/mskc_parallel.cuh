@@ -856,7 +856,26 @@ __device__ __forceinline__ bool frame_hit(uint32_t w, uint32_t c, unsigned plane
   const unsigned z = c / plane, r = c - z * plane, y = r / (unsigned)D.LX, x = r - y * (unsigned)D.LX; int kind;
   return !is_cubic_site((int)x, (int)y, (int)z, kind);
 }
+// MODE 1 ("all"): the union of every test the frame writers apply, vacancies included -- what the host program needs to
+// write I*.xyz, _d.xyz and _v.xyz without the lattice (WriteMolMolXYZFile.f:77-260): coverage ids 1 / 17 whatever else the
+// word holds (:169-176), atoms of species 1..3 with coordination <= 3 (:177-215), the two counting scans (:77-92: occupied
+// with coordination <= 3, empty with a coverage id, walls excluded), non-epitaxial 4-coordinated atoms (:95-159), and the
+// empty 4-coordinated sites (the vacancy list, Add.f:82-100).  The plane ranges of the individual scans are applied by the
+// caller (it has the coordinates).
+__device__ __forceinline__ bool frame_hit_all(uint32_t w, uint32_t c, unsigned plane) {
+  if (w == 0u) return false;
+  const int cov = w_cov(w), co = w_coor(w), a = w_sp(w);
+  const bool occ = w_occ(w) != 0;
+  if (cov == 1 || cov == 17) return true;
+  if (a >= 1 && a <= 3 && co <= 3) return true;
+  if (cov != 113 && (occ ? co <= 3 : (cov != 0 || co == 4))) return true;
+  if (!occ || co != 4) return false;
+  const unsigned z = c / plane, r = c - z * plane, y = r / (unsigned)D.LX, x = r - y * (unsigned)D.LX; int kind;
+  return !is_cubic_site((int)x, (int)y, (int)z, kind);
+}
+template <int MODE>
 __global__ void __launch_bounds__(256) frame_extract_kernel(uint32_t *cells, uint32_t *words, unsigned long long cap, unsigned long long *count) {
+  auto hit = [](uint32_t w, uint32_t c, unsigned plane) -> bool { return MODE ? frame_hit_all(w, c, plane) : frame_hit(w, c, plane); };
   const long long n4 = D.ncell >> 2;
   const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
   const unsigned plane = (unsigned)D.LX * (unsigned)D.LY;
@@ -871,8 +890,8 @@ __global__ void __launch_bounds__(256) frame_extract_kernel(uint32_t *cells, uin
     for (int u = 0; u < 4; u++) {
       const uint32_t c0 = (uint32_t)(4 * (q0 + lane + u * stride));
       if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
-      hits |= (frame_hit(v[u].x, c0, plane) ? 1u : 0u) << (4 * u) | (frame_hit(v[u].y, c0 + 1, plane) ? 2u : 0u) << (4 * u) |
-              (frame_hit(v[u].z, c0 + 2, plane) ? 4u : 0u) << (4 * u) | (frame_hit(v[u].w, c0 + 3, plane) ? 8u : 0u) << (4 * u);
+      hits |= (hit(v[u].x, c0, plane) ? 1u : 0u) << (4 * u) | (hit(v[u].y, c0 + 1, plane) ? 2u : 0u) << (4 * u) |
+              (hit(v[u].z, c0 + 2, plane) ? 4u : 0u) << (4 * u) | (hit(v[u].w, c0 + 3, plane) ? 8u : 0u) << (4 * u);
     }
     if (V.halo && hits) {                                 // halo columns belong to the neighbours
 #pragma unroll
@@ -897,6 +916,60 @@ __global__ void __launch_bounds__(256) frame_extract_kernel(uint32_t *cells, uin
       base++;
     }
   }
+}
+
+// The antisite scan of the SiC frame writer (WriteMolMolXYZFile.f:267-398): every 4-coordinated atom of planes 1..LenZ-1
+// (walls excluded) whose number of bonded neighbours of the OTHER species equals `target` is appended as (cell, word).  The
+// host calls it with target 0 (atoms the reference flips), patches the flipped words in, calls it with target 3 (the atoms
+// it prints into _w.xyz) and patches the words back -- the scan itself stays on the device: 4 B/cell streamed + 8 B bond
+// word and four gathered neighbour words per bulk atom (1/216 of the filled cells).
+__global__ void __launch_bounds__(256) antisite_kernel(int target, uint32_t *cells, uint32_t *words, unsigned long long cap, unsigned long long *count) {
+  const long long n4 = D.ncell >> 2;
+  const uint4 *S4 = reinterpret_cast<const uint4 *>(D.state);
+  const unsigned plane = (unsigned)D.LX * (unsigned)D.LY, LXu = (unsigned)D.LX, LZm1 = (unsigned)(D.LZ - 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  auto one = [&](uint32_t w, long long cl) {
+    if (w == 0u || !w_occ(w) || w_coor(w) != 4 || w_cov(w) == 113) return;
+    const unsigned c = (unsigned)cl, z = c / plane;
+    if (z - 1u >= LZm1) return;                                  // planes 1..LenZ-1
+    const unsigned r = c - z * plane, y = r / LXu, x = r - y * LXu;
+    if (V.halo && (x < (unsigned)TILE || x >= LXu - (unsigned)TILE)) return;
+    const int a = w_sp(w);
+    int n = 0;
+    if (a == 1 || a == 2) {
+      const int bit = a == 1 ? PosSiC + 1 : PosSiC;              // a Si atom counts its C neighbours, a C atom its Si neighbours
+      const unsigned long long b = D.bonds[c];
+      P3 s; s.x = (int)x; s.y = (int)y; s.z = (int)z;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const P3 q = dec_bond(s, (unsigned)((b >> (16 * j)) & 0xFFFFu));
+        if (in_box(q)) n += (int)((D.state[cidx_nofail(q)] >> bit) & 1u);
+      }
+    }
+    if (n != target) return;
+    const unsigned long long k = atomicAdd(count, 1ull);
+    if (k < cap) { cells[k] = c; words[k] = w; }
+  };
+  for (long long q0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; q0 < n4; q0 += 4 * stride) {      // four 128-bit loads in flight
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const long long q = q0 + u * stride; v[u] = q < n4 ? S4[q] : make_uint4(0, 0, 0, 0); }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0u) continue;
+      const long long c = 4 * (q0 + u * stride);
+      one(v[u].x, c); one(v[u].y, c + 1); one(v[u].z, c + 2); one(v[u].w, c + 3);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (long long c = n4 << 2; c < D.ncell; c++) one(D.state[c], c);
+}
+__global__ void scatter_state(uint32_t *state, const uint32_t *cell, const uint32_t *word, long long n) {      // cells are distinct
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) state[cell[i]] = word[i];
+}
+__global__ void gather_state(const uint32_t *state, const uint32_t *cell, uint32_t *out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = state[cell[i]];
 }
 
 // Device-side flat (001) builder: geometry of initial/SetSi.f:25-221 (walls, one species) and

@@ -1023,16 +1023,70 @@ void e15_8(double v, char out[32]) {                         // Fortran E15.8: 0
 }
 void atom_line(FILE *f, const char *el, double sf, int x, int y, int z, const char *tail) { fprintf(f, "%s%10.5f %10.5f %10.5f%s\n", el, sf * x, sf * y, sf * z, tail); }
 
-struct Run { mskc_ctx *h = nullptr; long long Iter = 1, IterOut = 0, framecounter = 0; double Time = 0; int NumAtoms = 0, NumVoids = 0, NumAdAtom = 0; bool sampler = false; };
+struct Run {
+  mskc_ctx *h = nullptr; long long Iter = 1, IterOut = 0, framecounter = 0; double Time = 0; int NumAtoms = 0, NumVoids = 0, NumAdAtom = 0; bool sampler = false;
+  // frames from the device (mskc_extract_frame_all / mskc_extract_antisites / mskc_gather_lattice): the writers below then
+  // never see the lattice -- a frame costs streaming passes on the GPU and a download of the printed cells only
+  bool device_frames = false, lattice_stale = false;
+  std::vector<uint32_t> fcell, fword;                        // receive buffers, grown on demand
+};
+struct Rec { uint32_t cell; int32_t w; };
+// every cell one of the frame writers prints or counts, vacancies included: the union of the tests of
+// WriteMolMolXYZFile.f:77-260 (the device pass frame_extract_kernel<1> applies the same union to the device's words)
+inline bool frame_cell(int32_t w, int x, int y, int z) {
+  if (w == 0) return false;
+  const int cov = ibits(w, PosIndex, LenIndex), co = ibits(w, PosCoor, LenCoor), a = ibits(w, PosSiC, LenSiC), occ = ibits(w, PosOcc, 1);
+  if (cov == 1 || cov == 17) return true;
+  if (a >= 1 && a <= 3 && co <= 3) return true;
+  if (cov != 113 && (occ ? co <= 3 : (cov != 0 || co == 4))) return true;
+  int kind;
+  return occ && co == 4 && !cubic_site(x, y, z, kind);
+}
 
 #define MS(call) do { if ((call) != 0) die(" %s", mskc_last_error(R.h)); } while (0)
+
+// (cell, word) lists from one of the device's extraction passes, in the reference's z,y,x scan order
+template <class F>
+void fetch_cells(Run &R, F call, std::vector<Rec> &out) {
+  if (R.fcell.size() < (1u << 16)) { R.fcell.resize(1u << 16); R.fword.resize(1u << 16); }
+  int64_t n = 0;
+  MS(call((int64_t)R.fcell.size(), R.fcell.data(), R.fword.data(), &n));
+  if ((size_t)n > R.fcell.size()) {                          // more cells than the buffers hold: once more with room
+    R.fcell.resize((size_t)n + (size_t)n / 8); R.fword.resize(R.fcell.size());
+    MS(call((int64_t)R.fcell.size(), R.fcell.data(), R.fword.data(), &n));
+  }
+  out.resize((size_t)n);
+  for (size_t i = 0; i < (size_t)n; i++) { out[i].cell = R.fcell[i]; out[i].w = (int32_t)R.fword[i]; }
+  std::sort(out.begin(), out.end(), [](const Rec &p, const Rec &q) { return p.cell < q.cell; });
+}
 
 void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, bool on_device) {
   const int LX = H.LX, LY = H.LY, LZ = H.LZ; const double sf = H.sf;
   const bool sic = H.NCrystal == 2 && (H.ListCrystal[0] == 6 || H.ListCrystal[1] == 6);
+  const bool dev = on_device && R.device_frames;
+  const size_t plane = (size_t)LX * LY;
   std::vector<Site> voids;
+  std::vector<Rec> recs;                                     // the cells the writers look at, z,y,x order
+  if (dev) {
+    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_frame_all(R.h, cap, c, w, n, nullptr); }, recs);
+    R.lattice_stale = true;
+  } else {
+    if (on_device) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }
+    for (int z = 0; z <= LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
+      const int32_t w = H.L[H.ci(x, y, z)];
+      if (frame_cell(w, x, y, z)) recs.push_back(Rec{(uint32_t)H.ci(x, y, z), w});
+    }
+  }
+  auto rz = [&](const Rec &r) { return (int)(r.cell / plane); };
+  auto ry = [&](const Rec &r) { return (int)((r.cell % plane) / (size_t)LX); };
+  auto rx = [&](const Rec &r) { return (int)(r.cell % (size_t)LX); };
+  // lattice words of given cells: from the device when the lattice stayed there
+  auto words_at = [&](const std::vector<int64_t> &cells, std::vector<int32_t> &out) {
+    out.resize(cells.size());
+    if (dev) { if (!cells.empty()) MS(mskc_gather_lattice(R.h, (int64_t)cells.size(), cells.data(), out.data())); }
+    else for (size_t i = 0; i < cells.size(); i++) out[i] = H.L[(size_t)cells[i]];
+  };
   if (on_device) {                                           // the module globals the writers read, from the device
-    MS(mskc_download_lattice(R.h, H.L.data()));
     mskc_counters c; MS(mskc_get_counters(R.h, &c));
     for (int i = 0; i < 3; i++) { H.CountCrystal[i] = c.CountCrystal[i]; H.CountCov[i] = c.CountCov[i]; H.CountLiquid[i] = H.InitCountCrystal[i] - c.CountCrystal[i]; }
     H.NumAdAtomOcc = c.num_adatom_occ;
@@ -1041,10 +1095,8 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
       // the empty 4-coordinated sites of the lattice (Add.f:82-100 is called exactly when an empty site reaches four
       // neighbours), here in z,y,x scan order, with their bond lists from the device
       std::vector<int32_t> vx;
-      for (int z = 0; z <= LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
-        const int32_t w = H.L[H.ci(x, y, z)];
-        if (w != 0 && ibits(w, PosOcc, 1) == 0 && ibits(w, PosCoor, LenCoor) == 4 && ibits(w, PosIndex, LenIndex) != 113) { vx.push_back(x); vx.push_back(y); vx.push_back(z); }
-      }
+      for (const Rec &r : recs)
+        if (ibits(r.w, PosOcc, 1) == 0 && ibits(r.w, PosCoor, LenCoor) == 4 && ibits(r.w, PosIndex, LenIndex) != 113) { vx.push_back(rx(r)); vx.push_back(ry(r)); vx.push_back(rz(r)); }
       voids.resize(vx.size() / 3);
       if (!voids.empty()) {
         std::vector<int32_t> vn(12 * voids.size());
@@ -1052,12 +1104,12 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
         for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
       }
     } else {
-    voids.resize((size_t)std::max(c.num_voids, 0));
-    if (!voids.empty()) {
-      std::vector<int32_t> vx(3 * voids.size()), vn(12 * voids.size());
-      MS(mskc_download_lists(R.h, nullptr, nullptr, nullptr, nullptr, vx.data(), vn.data(), nullptr, nullptr, 0, nullptr));
-      for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
-    }
+      voids.resize((size_t)std::max(c.num_voids, 0));
+      if (!voids.empty()) {
+        std::vector<int32_t> vx(3 * voids.size()), vn(12 * voids.size());
+        MS(mskc_download_lists(R.h, nullptr, nullptr, nullptr, nullptr, vx.data(), vn.data(), nullptr, nullptr, 0, nullptr));
+        for (size_t i = 0; i < voids.size(); i++) { memcpy(voids[i].xyz, &vx[3 * i], 12); memcpy(voids[i].nn, &vn[12 * i], 48); }
+      }
     }
   } else voids = H.voids;
   if (H.la_tree) {                                          // la/inpout/WriteMolMolSource.f:42-67
@@ -1088,13 +1140,14 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   char base[64]; snprintf(base, sizeof base, "I%08lld", Iout);
   printf(" %s\n", base);
   int NumAtTotal = 0, NumCovTotal = 0, NoEpiBulk = 0, kind;
-  for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {          // WriteMolMolXYZFile.f:77-92
-    int32_t w = H.L[H.ci(x, y, z)]; if (w == 0) continue;
+  for (const Rec &r : recs) {                                 // WriteMolMolXYZFile.f:77-92 (planes 1..LenZ-1)
+    const int z = rz(r); if (z < 1 || z > LZ - 1) continue;
+    const int32_t w = r.w;
     int cov = ibits(w, PosIndex, LenIndex);
     if (cov != 113) { int occ = ibits(w, PosOcc, 1), coo = ibits(w, PosCoor, LenCoor); if (occ == 1 && coo <= 3) NumAtTotal++; else if (occ == 0 && cov != 0) NumCovTotal++; }
   }
   auto is_noepi = [&](int32_t w, int x, int y, int z) { return ibits(w, PosOcc, 1) == 1 && ibits(w, PosCoor, LenCoor) == 4 && !cubic_site(x, y, z, kind); };
-  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) { int32_t w = H.L[H.ci(x, y, z)]; if (w && is_noepi(w, x, y, z)) NoEpiBulk++; }   // :95-119
+  for (const Rec &r : recs) { if (rz(r) <= LZ - 1 && is_noepi(r.w, rx(r), ry(r), rz(r))) NoEpiBulk++; }   // :95-119 (planes 0..LenZ-1)
   printf(" %d\n", NoEpiBulk);
   char e1[32], e2[32], e3[32], et[32], path[128];
   e15_8(sf * (double)LX, e1); e15_8(sf * (double)LY, e2); e15_8(sf * (double)LZ, e3); e15_8(Time, et);
@@ -1103,13 +1156,15 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   snprintf(path, sizeof path, "%s_v.xyz", base); FILE *fv = fopen(path, "w");
   if (!fd || !fx || !fv) die(" cannot open output files in the working directory");
   fprintf(fd, " %8d angstroem KMC-time: %s Iter: %12lld\n periodic %s %s %s\n", NoEpiBulk, et, Iter, e1, e2, e3);         // :125-159
-  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
-    int32_t w = H.L[H.ci(x, y, z)];
-    if (w && is_noepi(w, x, y, z)) { int a = ibits(w, PosSiC, LenSiC); if (a == 1) atom_line(fd, "Ge ", sf, x, y, z, "  "); if (a == 2) atom_line(fd, "B ", sf, x, y, z, "  "); if (a == 3) atom_line(fd, "Cl ", sf, x, y, z, "  "); }
+  for (const Rec &r : recs) {
+    const int x = rx(r), y = ry(r), z = rz(r); if (z > LZ - 1) continue;
+    const int32_t w = r.w;
+    if (is_noepi(w, x, y, z)) { int a = ibits(w, PosSiC, LenSiC); if (a == 1) atom_line(fd, "Ge ", sf, x, y, z, "  "); if (a == 2) atom_line(fd, "B ", sf, x, y, z, "  "); if (a == 3) atom_line(fd, "Cl ", sf, x, y, z, "  "); }
   }
   fprintf(fx, " %8d angstroem KMC-time: %s Iter: %12lld\n periodic %s %s %s\n", NumAtTotal + (int)voids.size() + NumCovTotal, et, Iter, e1, e2, e3);   // :163-221
-  for (int z = 0; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
-    int32_t w = H.L[H.ci(x, y, z)]; if (w == 0) continue;
+  for (const Rec &r : recs) {
+    const int x = rx(r), y = ry(r), z = rz(r); if (z > LZ - 1) continue;
+    const int32_t w = r.w;
     int a = ibits(w, PosSiC, LenSiC), coo = ibits(w, PosCoor, LenCoor), cov = ibits(w, PosIndex, LenIndex);
     if (cov == 1) atom_line(fx, "H ", sf, x, y, z, "  ");
     if (cov == 17) atom_line(fx, "Cl ", sf, x, y, z, "  ");
@@ -1123,9 +1178,17 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   }
   for (auto &v : voids) atom_line(fx, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
   fprintf(fv, " %8d angstroem\n periodic %s %s %s\n", (int)voids.size(), e1, e2, e3);                                     // :228-260
-  for (auto &v : voids) {
-    if (H.NCov == 0 && H.NCrystal == 2 && H.ListCrystal[1] == 6) {
-      int a = 0; for (int j = 0; j < 4; j++) a += ibits(H.at(v.nn[j]), PosSiC, LenSiC);
+  const bool vac_kinds = H.NCov == 0 && H.NCrystal == 2 && H.ListCrystal[1] == 6;
+  std::vector<int32_t> vw;                                    // the words of the vacancies' bonded neighbours
+  if (vac_kinds && !voids.empty()) {
+    std::vector<int64_t> vc(4 * voids.size());
+    for (size_t i = 0; i < voids.size(); i++) for (int j = 0; j < 4; j++) vc[4 * i + j] = (int64_t)H.ci(voids[i].nn[j][0], voids[i].nn[j][1], voids[i].nn[j][2]);
+    words_at(vc, vw);
+  }
+  for (size_t i = 0; i < voids.size(); i++) {
+    const Site &v = voids[i];
+    if (vac_kinds) {
+      int a = 0; for (int j = 0; j < 4; j++) a += ibits(vw[4 * i + j], PosSiC, LenSiC);
       const char *el = a == 4 ? "Mg " : a == 8 ? "He " : a == 7 ? "Ne " : a == 5 ? "Be " : a == 6 ? "Ar " : nullptr;
       const char *tail = a == 4 ? (H.la_tree ? " # SV (Si vacancy)" : " # CV (C vacancy)") : a == 8 ? (H.la_tree ? " # CV (C vacancy)" : " # SV (Si vacancy)")      // la/inpout/WriteMolMolXYZFile.f:66-70
                          : a == 7 ? " # SAV (Si antisite vac)" : a == 5 ? " # CAV (C antisite vac)" : (H.la_tree ? " # surrounded by 2C-2Si" : " # XV (near 2C and 2Si)");
@@ -1134,7 +1197,73 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     } else atom_line(fv, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
   }
   fclose(fd); fclose(fx); fclose(fv);
-  if (sic) {                                                 // :267-398 antisite pass; it flips species bits in LattCoo and restores them with the LAST entry's type (:386)
+  bool dev_w = sic && dev;                                   // the antisite pass runs on the device too (unless the check below says no)
+  std::vector<Rec> w0, w3;
+  std::vector<int64_t> pc; std::vector<int32_t> pw; std::vector<int> wtype; std::vector<size_t> pidx;
+  if (dev_w) {
+    // :267-398 antisite pass with the lattice on the device.  The reference walks the 4-coordinated atoms in scan order and
+    // flips the species of every atom that has, AT THAT MOMENT, no neighbour of the other species (:330-349) -- a flip is seen
+    // by the atoms after it -- then prints the atoms with three (:352-372) and restores the flipped ones with the LAST
+    // entry's type (:386).  Only atoms without such a neighbour BEFORE the pass can flip (a flip turns a like neighbour into
+    // an unlike one, so counts only grow), and an atom of that set flips exactly when none of its bonded neighbours flipped
+    // before it: the device finds the set (target 0), the host replays the order on that set alone with the set's bond
+    // lists, the flips travel as patches, and the second scan (target 3) runs on the device again.
+    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, w0);
+    if (!w0.empty()) {
+      std::vector<int32_t> wx(3 * w0.size()), wn(12 * w0.size());
+      for (size_t i = 0; i < w0.size(); i++) { wx[3 * i] = rx(w0[i]); wx[3 * i + 1] = ry(w0[i]); wx[3 * i + 2] = rz(w0[i]); }
+      MS(mskc_download_bonds(R.h, (int64_t)w0.size(), wx.data(), wn.data()));
+      auto find = [&](size_t cell) -> long long {              // position of a cell in the (sorted) set, -1 = not in it
+        auto it = std::lower_bound(w0.begin(), w0.end(), cell, [](const Rec &r, size_t c) { return (size_t)r.cell < c; });
+        return (it != w0.end() && (size_t)it->cell == cell) ? (long long)(it - w0.begin()) : -1;
+      };
+      for (size_t i = 0; i < w0.size(); i++) {
+        int32_t w = w0[i].w; const int a = ibits(w, PosSiC, LenSiC);
+        int n = 0;
+        if (a == 1 || a == 2) for (int j = 0; j < 4; j++) {   // cells outside the set held no unlike neighbour before the pass and never change
+          const int32_t *q = &wn[12 * i + 3 * j];
+          if (q[2] < 0 || q[2] > LZ) continue;
+          const long long k = find(H.ci(q[0], q[1], q[2]));
+          if (k >= 0) n += ibits(w0[(size_t)k].w, a == 1 ? PosC : PosSi, 1);
+        }
+        if (n != 0) continue;
+        if (a == 1) { w &= ~(1 << PosSi); w |= 1 << PosC; wtype.push_back(1); } else { w &= ~(1 << PosC); w |= 1 << PosSi; wtype.push_back(2); }
+        w0[i].w = w; pc.push_back((int64_t)w0[i].cell); pw.push_back(w); pidx.push_back(i);
+      }
+    }
+    if (!pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));
+    // The argument above needs the bond lists of 4-coordinated atoms to be reciprocal (they are wherever the event code fixed
+    // them).  Its visible consequence is checked: after the flips no atom is left without an unlike neighbour.  If one is,
+    // the flips are undone and this frame's pass runs on the host over the whole lattice, as the serial loop's writer does.
+    if (!pc.empty()) {
+      std::vector<Rec> left;
+      fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, left);
+      if (!left.empty() || getenv("MSKC_TEST_W_FALLBACK")) {     // (the variable: a test hook that takes this branch)
+        for (size_t i = 0; i < pidx.size(); i++) { int32_t w = pw[i]; if (wtype[i] == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; } pw[i] = w; }
+        MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));
+        MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false;
+        dev_w = false;
+      }
+    }
+  }
+  if (dev_w) {
+    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 3, cap, c, w, n, nullptr); }, w3);
+    const int NumAtWrong = (int)w3.size();
+    printf(" NumAtWrong:  %d\n", NumAtWrong);
+    snprintf(path, sizeof path, "%s_w.xyz", base); FILE *fw = fopen(path, "w");
+    if (fw) {
+      fprintf(fw, " %8d angstroem\n periodic %s %s %s\n", NumAtWrong, e1, e2, e3);
+      for (const Rec &r : w3) { int a = ibits(r.w, PosSiC, LenSiC); if (a == 1) atom_line(fw, "Si ", sf, rx(r), ry(r), rz(r), "  "); if (a == 2) atom_line(fw, "C ", sf, rx(r), ry(r), rz(r), "  "); }
+      fclose(fw);
+    }
+    for (size_t i = 0; i < pidx.size(); i++) {
+      int32_t w = w0[pidx[i]].w; const int ty = wtype.back();
+      if (ty == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; }
+      pw[i] = w;
+    }
+    if (!pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));      // the device lattice sees what the reference's LattCoo would hold
+  }
+  if (sic && !dev_w) {                                       // :267-398 antisite pass; it flips species bits in LattCoo and restores them with the LAST entry's type (:386)
     std::vector<int32_t> bx; std::vector<size_t> bcell;
     for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       int32_t w = H.L[H.ci(x, y, z)];
@@ -1438,6 +1567,11 @@ int main(int argc, char **argv) {
   if (exact_restart) mode = 0;                                // (the same trajectory: the serial loop)
   if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
   parallel = mode == 1; R.sampler = parallel;
+  // frames: the sampler's come from the device's extraction passes (a production box is 10^9 cells: no lattice download, no
+  // host scans); the serial loop keeps the whole-lattice writer its byte-for-byte tests were pinned with.  MSKC_DEVICE_FRAMES=1 / 0
+  // forces one or the other (the two writers produce identical files: tests/test_host_gpu.py)
+  R.device_frames = parallel;
+  if (const char *e = getenv("MSKC_DEVICE_FRAMES")) R.device_frames = atoi(e) != 0;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;
@@ -1512,6 +1646,7 @@ int main(int argc, char **argv) {
   // main.f:374-430: final frame, checkpoint, Coor
   auto finish_run = [&]() {
   write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter : (H.OutMolMol > 0 ? R.IterOut / H.OutMolMol : 0), true);
+  if (R.lattice_stale && (H.SaveFinalState == "T" || H.SaveCoo == "T")) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }   // the files below hold every cell
   if (H.SaveFinalState == "T") {
     printf(" Writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
     if (FILE *f = fopen(H.restartfile.c_str(), "w")) {

@@ -93,6 +93,9 @@ def test_null_handle_is_an_error_not_a_crash(lib):
         "mskc_get_counters": (null, None),
         "mskc_set_temperature": (null, None),
         "mskc_extract_frame": (null, 0, None, None, None, None),
+        "mskc_extract_frame_all": (null, 0, None, None, None, None),
+        "mskc_extract_antisites": (null, 0, 0, None, None, None, None),
+        "mskc_gather_lattice": (null, 0, None, None),
         "mskc_replay_events": (null, 0, None, None, None, C.c_double(1.0)),
     }
     for name, args in calls.items():

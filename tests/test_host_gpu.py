@@ -83,6 +83,27 @@ def test_regression_case(built, tmp_path, case):
     assert (g / "movie.mos").exists() and (g / "fort.30").exists() and (g / "I00000001.src").exists()
 
 
+@pytest.mark.parametrize("case", ["finfet"])
+def test_reference_golden_full_length(built, tmp_path, case):
+    """One of the reference's C1 regression cases with its UNMODIFIED start file at full length (finfet: 5e6 events at 480^3,
+    about a minute in serial-parity mode) against the reference's own golden: sha256 of both frames and the final log tokens
+    of log-finfet.txt -- in the default suite, so that every GPU run of it holds a full-length golden.  MSKC_FULL_GOLDEN=1
+    runs all eight at full length through test_regression_case (1e7 events each, 4.3e7 for CVD-Si-SiH2)."""
+    if os.environ.get("MSKC_EMU") == "1":
+        pytest.skip("5e6 events: too long for the SIMT emulator")
+    g = tmp_path / "gpu"
+    g.mkdir()
+    (g / "start.dat").write_text(open(start_path(case)).read())
+    _run(EXE, g)
+    m = MAN[case]
+    for k in (0, 1):
+        b = open(g / f"I0000000{k}.xyz", "rb").read()
+        assert hashlib.sha256(b).hexdigest() == m[f"frame{k}_sha256"], f"{case} frame {k} differs from the reference golden"
+    t = _tokens(g / "log.txt", "Iter, Time, Site")
+    assert int(t[3]) == m["final_iter"] and [int(v) for v in t[5:8]] == m["final_site"] and float(t[4]) == float(m["final_time"])
+    assert [int(v) for v in _tokens(g / "log.txt", "NatNvoidNad")[1:4]] == m["final_lists"]
+
+
 @pytest.mark.parametrize("kind", ["CAD", "LA", "SiGe", "ST", "ST-fixedT", "SiGeBdoped", "LA-fork"])
 def test_file_driven_case(built, tmp_path, kind):
     """InitSt SG (SetSiGex.f), InitSt IN (SetCAD.f: geometry file with crystal / wall / empty voxels, H coverage) and InitSt LA (SetT.f + SetCAD.f:
@@ -321,6 +342,64 @@ def test_host_parallel_mode(built, tmp_path, kind):
         lines = [l for l in open(tmp_path / f).read().split("\n")[2:] if l.strip()]
         assert int(open(tmp_path / f).readline().split()[0]) == len(lines), f
         assert not any(l.split()[0] == "O" and all(float(v) == 0.0 for v in l.split()[1:4]) for l in lines), f
+
+
+def _run_env(exe, d, args, env):
+    with open(d / "log.txt", "w") as out, open(d / "err.txt", "w") as err:
+        rc = subprocess.run([exe, *args], cwd=d, stdout=out, stderr=err, env=dict(os.environ, **env)).returncode
+    assert rc == 0, open(d / "log.txt").read()[-1500:] + open(d / "err.txt").read()[-1500:]
+
+
+def _same_files(a, b, what):
+    names = sorted(p.name for p in a.glob("I*.xyz"))
+    assert len(names) >= 6 and names == sorted(p.name for p in b.glob("I*.xyz"))
+    for name in names:
+        assert (a / name).read_bytes() == (b / name).read_bytes(), f"{what}: {name}"
+    assert (a / "log.txt").read_text() == (b / "log.txt").read_text(), what
+
+
+@pytest.mark.parametrize("kind", ["SiC", "SiC-cube", "CVD"])
+def test_device_frames_equal_lattice_frames_sampler(built, tmp_path, kind):
+    """Sampler mode writes its frames from the device's extraction passes (mskc_extract_frame_all, mskc_extract_antisites,
+    mskc_gather_lattice: no lattice download, no host scans -- inpout/WriteMolMolXYZFile.f:77-398 on compact lists).  The
+    same run with MSKC_DEVICE_FRAMES=0 downloads the lattice and scans it on the host like the serial loop's writer: every
+    file (.xyz, _d, _v, _w) and the log must be identical, also when the antisite pass takes its host fall-back."""
+    box = {"SiC": (96, 96, 240), "SiC-cube": (144, 144, 144), "CVD": (96, 96, 96)}[kind]
+    dirs = {}
+    for tag, env in (("dev", {}), ("lat", {"MSKC_DEVICE_FRAMES": "0"}), ("fb", {"MSKC_TEST_W_FALLBACK": "1"})):
+        d = tmp_path / tag
+        d.mkdir()
+        if kind == "SiC":
+            make_start("cube-zigzag", str(d / "start.dat"), lens=(48, 0, 0), maxiter=60000, outmolmol=20000, runtype="R", initst="F")
+        elif kind == "SiC-cube":          # InitSt C: a faceted crystal, stacking faults enabled (the order-dependent flips of the antisite pass are the
+            make_start("cube-zigzag", str(d / "start.dat"), lens=(48, 48, 48), maxiter=60000, outmolmol=20000, runtype="R")      # subject of the serial test below, builder D)
+        else:
+            make_start("CVD-Si-SiH2", str(d / "start.dat"), lens=(48, 0, 0), runtype="R", maxtime=0.15, outtime=0.05)      # (exits on KMC time)
+        _run_env(EXE, d, ["--parallel", "--box", *[str(v) for v in box]], env)
+        assert "sublattice-sampler" in (d / "err.txt").read_text()
+        dirs[tag] = d
+    _same_files(dirs["dev"], dirs["lat"], f"{kind}: device frames vs lattice frames")
+    _same_files(dirs["dev"], dirs["fb"], f"{kind}: antisite pass fall-back")
+    if kind != "CVD":
+        assert any(p.name.endswith("_w.xyz") for p in dirs["dev"].glob("I*.xyz"))
+
+
+@pytest.mark.parametrize("case,initst,lens,box,nrun", [("surface", "F", (48, 0, 0), (96, 96, 240), 60000), ("inverted-pyramid", "D", (30, 93, 0), (96, 96, 144), 1000),
+                                                      ("CVD-Si-SiH2", "FS", (48, 0, 0), (96, 96, 96), 60000)], ids=["surface", "D", "CVD"])
+def test_device_frames_equal_oracle_serial(built, tmp_path, case, initst, lens, box, nrun):
+    """the serial loop with MSKC_DEVICE_FRAMES=1: the device-side frame passes against the ORACLE's files byte for byte (the
+    vacancy list keeps the reference's list order here, so _v.xyz and the O lines of .xyz are compared as they are)"""
+    g, o = tmp_path / "gpu", tmp_path / "oracle"
+    g.mkdir(); o.mkdir()
+    make_start(case, str(g / "start.dat"), lens=lens, maxiter=nrun, outmolmol=nrun // 2, initst=initst, maxtime=0.15, outtime=0.05)      # (CVD exits on KMC time)
+    (o / "start.dat").write_text((g / "start.dat").read_text())
+    args = ["--box", *[str(v) for v in box]]
+    _run(ORACLE, o, args)
+    _run_env(EXE, g, ["--parity", *args], {"MSKC_DEVICE_FRAMES": "1"})
+    names = sorted(p.name for p in o.glob("I*.xyz"))
+    assert len(names) >= 6
+    for name in names:
+        assert (g / name).read_bytes() == (o / name).read_bytes(), name
 
 
 def test_shape_builder(built, tmp_path):
