@@ -480,6 +480,23 @@ def run_ours(args):
                   "seam_check": seam,
                   "note": "a colour step is bound by the serial event chain of its busiest tile; the number of concurrently running tiles (box/48)^2 is fixed by the box, so more GPUs "
                           "shorten the chain only through wider teams per tile (DESIGN.md section 8)"}
+        # the complete-frame passes of the host program's sampler-mode writer, on this box (last GPU work of the run: they were
+        # built after the round's GPU budget was spent, so nothing else depends on them)
+        if world == 1 and not args.no_dense and strong_ok:
+            try:
+                ncs = (gz + 1) * gy * sc.LenX
+                sc.extract_frame_all()
+                fc, _, ms = sc.extract_frame_all()
+                d = dense("frame_extract_kernel<1>", "every cell a test of WriteMolMolXYZFile.f:77-260 touches, vacancies included: 4 B/cell read", 4 * ncs, ms)
+                d["box"] = [gx, gy, gz]; d["cells_out"] = int(len(fc)); dense_passes.append(d)
+                cs_, _ = sc.census()
+                sc.extract_antisites(3)
+                ac, _, ms = sc.extract_antisites(3)
+                d = dense("antisite_kernel", "the scans of the SiC antisite pass (WriteMolMolXYZFile.f:330-372): 4 B/cell read + 8 B bond word and four 4 B neighbour words "
+                          "per 4-coordinated atom", 4 * ncs + 24 * int(cs_.bulk), ms)
+                d["box"] = [gx, gy, gz]; d["cells_out"] = int(len(ac)); dense_passes.append(d)
+            except Exception as e:
+                dense_passes.append({"kernel": "frame_extract_kernel<1> / antisite_kernel", "error": str(e)})
         sc.close()
 
     # ---- aggregate over ranks -----------------------------------------------------------------------

@@ -40,7 +40,8 @@ def test_bench_line_and_strong_point(emu_lib):
     assert d["metric"] == "kmc_events_per_s" and d["value"] > 0 and d["gpu_launches"] > 0
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
-    assert len(d["dense_passes"]) == 6
+    assert len(d["dense_passes"]) == 8 and not any("error" in p for p in d["dense_passes"])
+    assert {p["kernel"] for p in d["dense_passes"]} >= {"frame_extract_kernel<1>", "antisite_kernel", "frame_extract_kernel", "census_kernel"}
     s = d["strong_1e9"]
     assert s["error"] is None and s["value"] > 0 and 1 <= s["steps"] <= 6
     tops = s["highest_atom_plane_before_each_step"]
