@@ -1028,6 +1028,7 @@ struct Run {
   // frames from the device (mskc_extract_frame_all / mskc_extract_antisites / mskc_gather_lattice): the writers below then
   // never see the lattice -- a frame costs streaming passes on the GPU and a download of the printed cells only
   bool device_frames = false, lattice_stale = false;
+  bool crosscheck = false; long long crosschecked = 0;      // MSKC_FRAME_CROSSCHECK (test hook): every device-side frame pass against a whole-lattice scan of the same state
   std::vector<uint32_t> fcell, fword;                        // receive buffers, grown on demand
 };
 struct Rec { uint32_t cell; int32_t w; };
@@ -1070,6 +1071,17 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
   if (dev) {
     fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_frame_all(R.h, cap, c, w, n, nullptr); }, recs);
     R.lattice_stale = true;
+    if (R.crosscheck) {                                       // the same list from a host scan of the downloaded lattice
+      MS(mskc_download_lattice(R.h, H.L.data()));
+      size_t k = 0; bool same = true;
+      for (int z = 0; z <= LZ && same; z++) for (int y = 0; y < LY && same; y++) for (int x = 0; x < LX; x++) {
+        const int32_t w = H.L[H.ci(x, y, z)];
+        if (!frame_cell(w, x, y, z)) continue;
+        if (k >= recs.size() || recs[k].cell != (uint32_t)H.ci(x, y, z) || recs[k].w != w) { same = false; break; }
+        k++;
+      }
+      if (!same || k != recs.size()) die(" frame cross-check: mskc_extract_frame_all differs from the scan of the lattice (frame %lld, entry %zu of %zu)", Iout, k, recs.size());
+    }
   } else {
     if (on_device) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }
     for (int z = 0; z <= LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
@@ -1184,6 +1196,7 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     std::vector<int64_t> vc(4 * voids.size());
     for (size_t i = 0; i < voids.size(); i++) for (int j = 0; j < 4; j++) vc[4 * i + j] = (int64_t)H.ci(voids[i].nn[j][0], voids[i].nn[j][1], voids[i].nn[j][2]);
     words_at(vc, vw);
+    if (dev && R.crosscheck) for (size_t i = 0; i < vc.size(); i++) if (vw[i] != H.L[(size_t)vc[i]]) die(" frame cross-check: mskc_gather_lattice differs from the lattice (frame %lld)", Iout);
   }
   for (size_t i = 0; i < voids.size(); i++) {
     const Site &v = voids[i];
@@ -1197,73 +1210,19 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     } else atom_line(fv, "O ", sf, v.xyz[0], v.xyz[1], v.xyz[2], "  ");
   }
   fclose(fd); fclose(fx); fclose(fv);
-  bool dev_w = sic && dev;                                   // the antisite pass runs on the device too (unless the check below says no)
-  std::vector<Rec> w0, w3;
-  std::vector<int64_t> pc; std::vector<int32_t> pw; std::vector<int> wtype; std::vector<size_t> pidx;
-  if (dev_w) {
-    // :267-398 antisite pass with the lattice on the device.  The reference walks the 4-coordinated atoms in scan order and
-    // flips the species of every atom that has, AT THAT MOMENT, no neighbour of the other species (:330-349) -- a flip is seen
-    // by the atoms after it -- then prints the atoms with three (:352-372) and restores the flipped ones with the LAST
-    // entry's type (:386).  Only atoms without such a neighbour BEFORE the pass can flip (a flip turns a like neighbour into
-    // an unlike one, so counts only grow), and an atom of that set flips exactly when none of its bonded neighbours flipped
-    // before it: the device finds the set (target 0), the host replays the order on that set alone with the set's bond
-    // lists, the flips travel as patches, and the second scan (target 3) runs on the device again.
-    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, w0);
-    if (!w0.empty()) {
-      std::vector<int32_t> wx(3 * w0.size()), wn(12 * w0.size());
-      for (size_t i = 0; i < w0.size(); i++) { wx[3 * i] = rx(w0[i]); wx[3 * i + 1] = ry(w0[i]); wx[3 * i + 2] = rz(w0[i]); }
-      MS(mskc_download_bonds(R.h, (int64_t)w0.size(), wx.data(), wn.data()));
-      auto find = [&](size_t cell) -> long long {              // position of a cell in the (sorted) set, -1 = not in it
-        auto it = std::lower_bound(w0.begin(), w0.end(), cell, [](const Rec &r, size_t c) { return (size_t)r.cell < c; });
-        return (it != w0.end() && (size_t)it->cell == cell) ? (long long)(it - w0.begin()) : -1;
-      };
-      for (size_t i = 0; i < w0.size(); i++) {
-        int32_t w = w0[i].w; const int a = ibits(w, PosSiC, LenSiC);
-        int n = 0;
-        if (a == 1 || a == 2) for (int j = 0; j < 4; j++) {   // cells outside the set held no unlike neighbour before the pass and never change
-          const int32_t *q = &wn[12 * i + 3 * j];
-          if (q[2] < 0 || q[2] > LZ) continue;
-          const long long k = find(H.ci(q[0], q[1], q[2]));
-          if (k >= 0) n += ibits(w0[(size_t)k].w, a == 1 ? PosC : PosSi, 1);
-        }
-        if (n != 0) continue;
-        if (a == 1) { w &= ~(1 << PosSi); w |= 1 << PosC; wtype.push_back(1); } else { w &= ~(1 << PosC); w |= 1 << PosSi; wtype.push_back(2); }
-        w0[i].w = w; pc.push_back((int64_t)w0[i].cell); pw.push_back(w); pidx.push_back(i);
-      }
-    }
-    if (!pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));
-    // The argument above needs the bond lists of 4-coordinated atoms to be reciprocal (they are wherever the event code fixed
-    // them).  Its visible consequence is checked: after the flips no atom is left without an unlike neighbour.  If one is,
-    // the flips are undone and this frame's pass runs on the host over the whole lattice, as the serial loop's writer does.
-    if (!pc.empty()) {
-      std::vector<Rec> left;
-      fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, left);
-      if (!left.empty() || getenv("MSKC_TEST_W_FALLBACK")) {     // (the variable: a test hook that takes this branch)
-        for (size_t i = 0; i < pidx.size(); i++) { int32_t w = pw[i]; if (wtype[i] == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; } pw[i] = w; }
-        MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));
-        MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false;
-        dev_w = false;
-      }
-    }
-  }
-  if (dev_w) {
-    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 3, cap, c, w, n, nullptr); }, w3);
-    const int NumAtWrong = (int)w3.size();
-    printf(" NumAtWrong:  %d\n", NumAtWrong);
-    snprintf(path, sizeof path, "%s_w.xyz", base); FILE *fw = fopen(path, "w");
-    if (fw) {
-      fprintf(fw, " %8d angstroem\n periodic %s %s %s\n", NumAtWrong, e1, e2, e3);
-      for (const Rec &r : w3) { int a = ibits(r.w, PosSiC, LenSiC); if (a == 1) atom_line(fw, "Si ", sf, rx(r), ry(r), rz(r), "  "); if (a == 2) atom_line(fw, "C ", sf, rx(r), ry(r), rz(r), "  "); }
-      fclose(fw);
-    }
-    for (size_t i = 0; i < pidx.size(); i++) {
-      int32_t w = w0[pidx[i]].w; const int ty = wtype.back();
-      if (ty == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; }
-      pw[i] = w;
-    }
-    if (!pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));      // the device lattice sees what the reference's LattCoo would hold
-  }
-  if (sic && !dev_w) {                                       // :267-398 antisite pass; it flips species bits in LattCoo and restores them with the LAST entry's type (:386)
+  // ---- :267-398 antisite pass (SiC).  The reference walks the 4-coordinated atoms of planes 1..LenZ-1 in scan order and flips
+  // the species of every atom that has, AT THAT MOMENT, no neighbour of the other species (:330-349) -- a flip is seen by the
+  // atoms after it -- then prints the atoms with three (:352-372) and restores the flipped ones with the LAST entry's type
+  // (:386).  Both forms below return the printed atoms (scan order, words as they are while the flips stand) and the patch
+  // that leaves the lattice as the reference's LattCoo would be.
+  struct WPass { std::vector<Rec> w3; std::vector<int64_t> pc; std::vector<int32_t> pw; };
+  auto restore_word = [&](int32_t w, int ty) { if (ty == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; } return w; };
+  auto flip_word = [&](int32_t w, std::vector<int> &wtype) {
+    if (ibits(w, PosSiC, LenSiC) == 1) { w &= ~(1 << PosSi); w |= 1 << PosC; wtype.push_back(1); } else { w &= ~(1 << PosC); w |= 1 << PosSi; wtype.push_back(2); }
+    return w;
+  };
+  // the whole-lattice form, on H.L (which it leaves in the reference's final state)
+  auto antisite_host = [&](WPass &out) {
     std::vector<int32_t> bx; std::vector<size_t> bcell;
     for (int z = 1; z <= LZ - 1; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       int32_t w = H.L[H.ci(x, y, z)];
@@ -1286,28 +1245,87 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     };
     std::vector<size_t> wrong; std::vector<int> wtype;
     for (size_t i = 0; i < bcell.size(); i++)
-      if (ncorr(i) == 0) {
-        int32_t &w = H.L[bcell[i]]; int a = ibits(w, PosSiC, LenSiC);
-        if (a == 1) { w &= ~(1 << PosSi); w |= 1 << PosC; wtype.push_back(1); } else { w &= ~(1 << PosC); w |= 1 << PosSi; wtype.push_back(2); }
-        wrong.push_back(bcell[i]);
+      if (ncorr(i) == 0) { H.L[bcell[i]] = flip_word(H.L[bcell[i]], wtype); wrong.push_back(bcell[i]); }
+    for (size_t i = 0; i < bcell.size(); i++) if (ncorr(i) == 3) out.w3.push_back(Rec{(uint32_t)bcell[i], H.L[bcell[i]]});
+    for (size_t i = 0; i < wrong.size(); i++) {
+      int32_t &w = H.L[wrong[i]]; w = restore_word(w, wtype.back());
+      out.pc.push_back((int64_t)wrong[i]); out.pw.push_back(w);
+    }
+  };
+  // The device form.  Only atoms without an unlike neighbour BEFORE the pass can flip (a flip turns a like neighbour into an
+  // unlike one, so counts only grow), and an atom of that set flips exactly when none of its bonded neighbours flipped before
+  // it: the device finds the set (target 0), the host replays the order on that set alone with the set's bond lists, the
+  // flips travel as a patch, and the second scan (target 3) runs on the device again.  Returns false -- with the device
+  // lattice as it was -- when the check described inside fails.
+  auto antisite_device = [&](WPass &out) -> bool {
+    std::vector<Rec> w0;
+    std::vector<int> wtype; std::vector<size_t> pidx;
+    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, w0);
+    if (!w0.empty()) {
+      std::vector<int32_t> wx(3 * w0.size()), wn(12 * w0.size());
+      for (size_t i = 0; i < w0.size(); i++) { wx[3 * i] = rx(w0[i]); wx[3 * i + 1] = ry(w0[i]); wx[3 * i + 2] = rz(w0[i]); }
+      MS(mskc_download_bonds(R.h, (int64_t)w0.size(), wx.data(), wn.data()));
+      auto find = [&](size_t cell) -> long long {              // position of a cell in the (sorted) set, -1 = not in it
+        auto it = std::lower_bound(w0.begin(), w0.end(), cell, [](const Rec &r, size_t c) { return (size_t)r.cell < c; });
+        return (it != w0.end() && (size_t)it->cell == cell) ? (long long)(it - w0.begin()) : -1;
+      };
+      for (size_t i = 0; i < w0.size(); i++) {
+        const int32_t w = w0[i].w; const int a = ibits(w, PosSiC, LenSiC);
+        int n = 0;
+        if (a == 1 || a == 2) for (int j = 0; j < 4; j++) {   // cells outside the set held no unlike neighbour before the pass and never change
+          const int32_t *q = &wn[12 * i + 3 * j];
+          if (q[2] < 0 || q[2] > LZ) continue;
+          const long long k = find(H.ci(q[0], q[1], q[2]));
+          if (k >= 0) n += ibits(w0[(size_t)k].w, a == 1 ? PosC : PosSi, 1);
+        }
+        if (n != 0) continue;
+        w0[i].w = flip_word(w, wtype); out.pc.push_back((int64_t)w0[i].cell); out.pw.push_back(w0[i].w); pidx.push_back(i);
       }
-    int NumAtWrong = 0;
-    for (size_t i = 0; i < bcell.size(); i++) if (ncorr(i) == 3) NumAtWrong++;
+    }
+    if (!out.pc.empty()) {
+      MS(mskc_patch_lattice(R.h, (int)out.pc.size(), out.pc.data(), out.pw.data()));
+      // The argument needs the bond lists of 4-coordinated atoms to be reciprocal (they are wherever the event code fixed them).
+      // Its visible consequence is checked: after the flips no atom is left without an unlike neighbour.  If one is, the
+      // flips are undone and this frame's pass runs over the whole lattice on the host, as the serial loop's writer does.
+      std::vector<Rec> left;
+      fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 0, cap, c, w, n, nullptr); }, left);
+      if (!left.empty() || getenv("MSKC_TEST_W_FALLBACK")) {     // (the variable: a test hook that takes this branch)
+        for (size_t i = 0; i < pidx.size(); i++) out.pw[i] = restore_word(out.pw[i], wtype[i]);
+        MS(mskc_patch_lattice(R.h, (int)out.pc.size(), out.pc.data(), out.pw.data()));
+        out.pc.clear(); out.pw.clear();
+        return false;
+      }
+    }
+    fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_antisites(R.h, 3, cap, c, w, n, nullptr); }, out.w3);
+    for (size_t i = 0; i < pidx.size(); i++) out.pw[i] = restore_word(w0[pidx[i]].w, wtype.back());
+    return true;
+  };
+  if (sic) {
+    WPass wp, wh;
+    const bool check = dev && R.crosscheck;                   // test hook: the whole-lattice pass on the snapshot taken above, beside the device's
+    if (check) antisite_host(wh);
+    bool done = false;
+    if (dev) {
+      done = antisite_device(wp);
+      if (!done) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }
+    }
+    if (!done) { wp = WPass(); antisite_host(wp); }
+    if (check) {
+      bool same = wp.w3.size() == wh.w3.size() && wp.pc == wh.pc && wp.pw == wh.pw;
+      for (size_t i = 0; same && i < wp.w3.size(); i++) same = wp.w3[i].cell == wh.w3[i].cell && wp.w3[i].w == wh.w3[i].w;
+      if (!same) die(" frame cross-check: the antisite pass on the device differs from the whole-lattice pass (frame %lld)", Iout);
+    }
+    const int NumAtWrong = (int)wp.w3.size();
     printf(" NumAtWrong:  %d\n", NumAtWrong);
     snprintf(path, sizeof path, "%s_w.xyz", base); FILE *fw = fopen(path, "w");
     if (fw) {
       fprintf(fw, " %8d angstroem\n periodic %s %s %s\n", NumAtWrong, e1, e2, e3);
-      for (size_t i = 0; i < bcell.size(); i++) if (ncorr(i) == 3) { int a = ibits(H.L[bcell[i]], PosSiC, LenSiC); if (a == 1) atom_line(fw, "Si ", sf, bx[3 * i], bx[3 * i + 1], bx[3 * i + 2], "  "); if (a == 2) atom_line(fw, "C ", sf, bx[3 * i], bx[3 * i + 1], bx[3 * i + 2], "  "); }
+      for (const Rec &r : wp.w3) { int a = ibits(r.w, PosSiC, LenSiC); if (a == 1) atom_line(fw, "Si ", sf, rx(r), ry(r), rz(r), "  "); if (a == 2) atom_line(fw, "C ", sf, rx(r), ry(r), rz(r), "  "); }
       fclose(fw);
     }
-    std::vector<int64_t> pc; std::vector<int32_t> pw;
-    for (size_t i = 0; i < wrong.size(); i++) {
-      int32_t &w = H.L[wrong[i]]; int ty = wtype.back();
-      if (ty == 1) { w &= ~(1 << PosC); w |= 1 << PosSi; } else { w &= ~(1 << PosSi); w |= 1 << PosC; }
-      pc.push_back((int64_t)wrong[i]); pw.push_back(w);
-    }
-    if (on_device && !pc.empty()) MS(mskc_patch_lattice(R.h, (int)pc.size(), pc.data(), pw.data()));      // the device lattice sees what the reference's LattCoo would hold
+    if (on_device && !wp.pc.empty()) MS(mskc_patch_lattice(R.h, (int)wp.pc.size(), wp.pc.data(), wp.pw.data()));      // the device lattice sees what the reference's LattCoo would hold
   }
+  if (dev && R.crosscheck) R.crosschecked++;
   FILE *f;                                                   // WriteMolMolSource.f:77-112 side files
   if ((f = fopen("fort.30", "a"))) { fprintf(f, " %.17g\n", Time); fclose(f); }
   snprintf(path, sizeof path, "%s.src", base);
@@ -1572,6 +1590,7 @@ int main(int argc, char **argv) {
   // forces one or the other (the two writers produce identical files: tests/test_host_gpu.py)
   R.device_frames = parallel;
   if (const char *e = getenv("MSKC_DEVICE_FRAMES")) R.device_frames = atoi(e) != 0;
+  R.crosscheck = getenv("MSKC_FRAME_CROSSCHECK") != nullptr;
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;
@@ -1743,6 +1762,7 @@ int main(int argc, char **argv) {
       fieldisinit = false; phasesready = true; xgeready = true; LAcounter++;
     }
   }
+  if (R.crosscheck) fprintf(stderr, "frame cross-check: %lld frames, device passes == whole-lattice scans\n", R.crosschecked);
   fprintf(stderr, "mulskips.e (B200): %lld events, %.1f ms on the device = %.4g events/s (%s mode)\n", events, dev_ms, dev_ms > 0 ? events / (dev_ms * 1e-3) : 0.0, parallel ? "sublattice-sampler" : "serial-parity");
   mskc_destroy(R.h);
   return 0;
