@@ -280,6 +280,55 @@ def test_socket_driven_laser_annealing(built, tmp_path):
     orc.close()
 
 
+def test_socket_driven_laser_annealing_sampler(built, tmp_path):
+    """The same socket loop with the event loop in sampler mode (`--parallel --la-tree -p port`): two legs, a colder temperature
+    map in the second; the phase and species arrays that go back are well-formed (coordination 0..4 of occupied cells, 10 = wall,
+    species 1..2), the walls stay where they are, the solid does not shrink on the colder map, every frame is well-formed."""
+    import numpy as np
+    from la_socket_server import Server
+    box = (96, 96, 96)
+    g, o = tmp_path / "gpu", tmp_path / "inputs"
+    g.mkdir(); o.mkdir()
+    make_la_tree_case(str(o), box=box, maxiter=30000)
+    make_la_tree_case(str(g), box=box, maxiter=30000, sockets=True)
+    geo = np.loadtxt(o / "LattGeo.dat", dtype=np.int32)
+    t1 = np.loadtxt(o / "TempStat.dat", dtype=np.int32)
+    srv = Server((box[2], box[0] * box[1]), timeout=240.0)
+    out, err = open(g / "log.txt", "w"), open(g / "err.txt", "w")
+    p = subprocess.Popen([EXE, "--parallel", "--la-tree", "-p", str(srv.port), "--box", *[str(v) for v in box]], cwd=g, stdout=out, stderr=err)
+    try:
+        srv.accept()
+        assert srv.status() == "NEEDINIT"
+        srv.init()
+        srv.send("geo", geo)
+        srv.send("field", t1)
+        srv.wait_status("HAVEDATA")
+        c1, d1 = srv.get("phases"), srv.get("xge")
+        assert srv.status() == "READY"
+        srv.send("field", t1 - 25)
+        srv.wait_status("HAVEDATA")
+        c2, d2 = srv.get("phases"), srv.get("xge")
+        srv.exit()
+        assert p.wait(timeout=60) == 0
+    finally:
+        if p.poll() is None:
+            p.kill()
+        srv.close()
+        out.close(); err.close()
+    for c, d in ((c1, d1), (c2, d2)):
+        assert set(np.unique(c)) <= {0, 1, 2, 3, 4, 10} and set(np.unique(d)) <= {0, 1, 2, 10}
+        assert np.array_equal(c == 10, d == 10) and np.array_equal((c > 0) & (c < 10), (d > 0) & (d < 10))
+    assert np.array_equal(c1 == 10, c2 == 10) and np.count_nonzero(c1 == 10) > 0
+    n1, n2 = np.count_nonzero((c1 > 0) & (c1 < 10)), np.count_nonzero((c2 > 0) & (c2 < 10))
+    assert n1 > 500 and n2 >= n1, (n1, n2)                  # the melt resolidifies (leg 2 is 25 K colder; it ends at the latest when the nucleus is whole again)
+    assert "sublattice-sampler" in (g / "err.txt").read_text()
+    frames = sorted(q.name for q in g.glob("I*[0-9].xyz"))
+    assert len(frames) >= 2
+    for f in frames:
+        lines = [l for l in open(g / f).read().split("\n")[2:] if l.strip()]
+        assert int(open(g / f).readline().split()[0]) == len(lines), f
+
+
 MORE_BUILDERS = [("SS", "Si-SL", (60, 0, 0), (144, 144, 144), 30000), ("D", "inverted-pyramid", (30, 93, 0), (96, 96, 144), 1000),
                  ("Z", "Si-SL", (30, 93, 0), (96, 96, 144), 5000), ("T", "cube", (20, 45, 90), (96, 48, 144), 30000),
                  ("Fw", "surface", (48, 96, 0), (96, 96, 144), 30000), ("Fa", "surface", (48, 72, 48), (96, 96, 144), 30000),
