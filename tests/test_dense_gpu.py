@@ -213,61 +213,3 @@ def test_temperature_u16_and_phases(tmp_path):
     assert np.array_equal(a.download_phases(), ph)
     assert a.last_dense_ms() >= 0.0
     a.close(); b.close(); orc.close()
-
-
-def _cubic(x, y, z):
-    """the site test of every builder (SetSi.f:52-57): diamond sites of the ideal lattice"""
-    ok = (x % 3 == 0) & (y % 3 == 0) & (z % 3 == 0)
-    x1, y1, z1 = x // 3, y // 3, z // 3
-    ok &= ((x1 & 1) == (y1 & 1)) & ((x1 & 1) == (z1 & 1))
-    m = (x1 + y1 + z1) & 3
-    return ok & ((m == 0) | (m == 3))
-
-
-@pytest.mark.parametrize("case,box,lens,nev", [("cube-zigzag", (144, 144, 144), (48, 48, 48), 100000), ("CVD-Si-SiH2", (96, 96, 96), (48, 0, 0), 100000),
-                                               ("Si-SL", (96, 96, 240), (216, 0, 0), 40000)], ids=["cube-zigzag", "CVD", "Si-SL"])
-def test_extract_frame_all_and_antisites(tmp_path, case, box, lens, nev):
-    """the complete-frame passes the host program's sampler-mode writer uses instead of the lattice: mskc_extract_frame_all
-    == the union of the tests of WriteMolMolXYZFile.f:77-260 (vacancies included) applied to the oracle's lattice with numpy;
-    mskc_extract_antisites(0 / 3) == the neighbour counts of :267-372 computed from the oracle's lattice and the device's bond
-    lists; mskc_gather_lattice == plain indexing"""
-    from mulskips_b200 import Mskc
-    start = make_start(case, str(tmp_path / "start.dat"), lens=lens, maxiter=10**9, outmolmol=10**9, maxtime=1e30, outtime=1e30)
-    orc = Oracle(*box, start)
-    orc.setup()
-    assert orc.run(nev) == nev
-    lc, lv = orc.species()
-    ctx = Mskc(*box, lc, lv)
-    upload_oracle_state(orc, ctx)
-    L = orc.lattcoo().astype(np.int64).ravel()                   # cell = x + LenX*(y + LenY*z)
-    LX, LY = box[0], box[1]
-    c = np.arange(L.size, dtype=np.int64)
-    x, y, z = c % LX, (c // LX) % LY, c // (LX * LY)
-    occ, coor, cov, a = (L >> 23) & 1, (L >> 24) & 7, L & 255, (L >> 27) & 7
-    hit = (cov == 1) | (cov == 17) | ((a >= 1) & (a <= 3) & (coor <= 3))
-    hit |= (cov != 113) & np.where(occ == 1, coor <= 3, (cov != 0) | (coor == 4))
-    hit |= (occ == 1) & (coor == 4) & ~_cubic(x, y, z)
-    hit &= L != 0
-    cells, words, _ = ctx.extract_frame_all()
-    assert np.array_equal(cells.astype(np.int64), c[hit])
-    assert np.array_equal(words.astype(np.int64), L[hit] & 0xFFFFFFFF)
-    # the narrower list of mskc_extract_frame is a subset
-    c0, _, _ = ctx.extract_frame()
-    assert np.isin(c0, cells).all()
-    # gather
-    pick = c[hit][:: max(1, int(hit.sum()) // 500)]
-    assert np.array_equal(ctx.gather_lattice(pick).astype(np.int64) & 0xFFFFFFFF, L[pick] & 0xFFFFFFFF)
-    # antisite scan: 4-coordinated atoms of planes 1..LenZ-1, walls excluded; neighbours from the device's bond lists
-    bulk = (L != 0) & (occ == 1) & (coor == 4) & (cov != 113) & (z >= 1) & (z <= box[2] - 1)
-    bc = c[bulk]
-    if len(lc) == 2 and bc.size:
-        nn = ctx.download_bonds(np.stack([x[bulk], y[bulk], z[bulk]], axis=1).astype(np.int32))     # [n][4][3]
-        ncell = nn[:, :, 0].astype(np.int64) + LX * (nn[:, :, 1].astype(np.int64) + LY * nn[:, :, 2].astype(np.int64))
-        nw = L[ncell]
-        ab = a[bulk]
-        n = np.where(ab == 1, ((nw >> 28) & 1).sum(axis=1), np.where(ab == 2, ((nw >> 27) & 1).sum(axis=1), 0))
-        for target in (0, 3):
-            got, gw, _ = ctx.extract_antisites(target)
-            assert np.array_equal(got.astype(np.int64), bc[n == target]), target
-            assert np.array_equal(gw.astype(np.int64), L[bc[n == target]] & 0xFFFFFFFF)
-    ctx.close(); orc.close()
