@@ -1032,6 +1032,8 @@ struct Run {
   std::vector<uint32_t> fcell, fword;                        // receive buffers, grown on demand
 };
 struct Rec { uint32_t cell; int32_t w; };
+// the host copy of the lattice, allocated when something first needs it (a device-built sampler run may never)
+inline int32_t *host_lattice(Host &H) { const size_t n = (size_t)H.LX * H.LY * (H.LZ + 1); if (H.L.size() != n) H.L.assign(n, 0); return H.L.data(); }
 // every cell one of the frame writers prints or counts, vacancies included: the union of the tests of
 // WriteMolMolXYZFile.f:77-260 (the device pass frame_extract_kernel<1> applies the same union to the device's words)
 inline bool frame_cell(int32_t w, int x, int y, int z) {
@@ -1072,7 +1074,7 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     fetch_cells(R, [&](int64_t cap, uint32_t *c, uint32_t *w, int64_t *n) { return mskc_extract_frame_all(R.h, cap, c, w, n, nullptr); }, recs);
     R.lattice_stale = true;
     if (R.crosscheck) {                                       // the same list from a host scan of the downloaded lattice
-      MS(mskc_download_lattice(R.h, H.L.data()));
+      MS(mskc_download_lattice(R.h, host_lattice(H)));
       size_t k = 0; bool same = true;
       for (int z = 0; z <= LZ && same; z++) for (int y = 0; y < LY && same; y++) for (int x = 0; x < LX; x++) {
         const int32_t w = H.L[H.ci(x, y, z)];
@@ -1083,7 +1085,7 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
       if (!same || k != recs.size()) die(" frame cross-check: mskc_extract_frame_all differs from the scan of the lattice (frame %lld, entry %zu of %zu)", Iout, k, recs.size());
     }
   } else {
-    if (on_device) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }
+    if (on_device) { MS(mskc_download_lattice(R.h, host_lattice(H))); R.lattice_stale = false; }
     for (int z = 0; z <= LZ; z++) for (int y = 0; y < LY; y++) for (int x = 0; x < LX; x++) {
       const int32_t w = H.L[H.ci(x, y, z)];
       if (frame_cell(w, x, y, z)) recs.push_back(Rec{(uint32_t)H.ci(x, y, z), w});
@@ -1307,7 +1309,7 @@ void write_frame(Host &H, Run &R, double Time, long long Iter, long long Iout, b
     bool done = false;
     if (dev) {
       done = antisite_device(wp);
-      if (!done) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }
+      if (!done) { MS(mskc_download_lattice(R.h, host_lattice(H))); R.lattice_stale = false; }
     }
     if (!done) { wp = WPass(); antisite_host(wp); }
     if (check) {
@@ -1360,7 +1362,7 @@ void write_exact_checkpoint(Host &H, Run &R, const std::string &path) {
   MS(mskc_download_lists(R.h, mx.data(), mn.data(), me.data(), mr.data(), vx.data(), vn.data(), bx.data(), bn.data(), (int64_t)nb_cap, &nb));
   if (nb > (int64_t)nb_cap) die(" exact checkpoint: %lld bulk atoms found, %zu expected", (long long)nb, nb_cap);
   h.nbulk = (int32_t)nb;
-  MS(mskc_download_lattice(R.h, H.L.data()));
+  MS(mskc_download_lattice(R.h, host_lattice(H)));
   FILE *f = fopen(path.c_str(), "wb"); if (!f) die(" cannot write %s", path.c_str());
   bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(H.L.data(), 4, H.L.size(), f) == H.L.size();
   ok = ok && fwrite(mx.data(), 4, 3 * (size_t)h.nmc, f) == 3 * (size_t)h.nmc && fwrite(mn.data(), 4, 12 * (size_t)h.nmc, f) == 12 * (size_t)h.nmc;
@@ -1470,10 +1472,46 @@ int main(int argc, char **argv) {
   bool by_time = false;
   float dev_ms = 0; long long events = 0;
   // ---- first cycle: input, initial structure, upload (main.f:83-300; la/main.f:348-631 with LAcounter = 0) ----
+  // Which loop runs when the command line does not say (pymulskips launches `mulskips.e` without arguments): RunType 'T'
+  // ("not so random: use this for regression tests", py/setuprun.py:344) and 'C' ask for the reference's own event sequence
+  // -> serial parity mode, bit-exact; RunType 'R' ("truly random", the production default of pymulskips) asks for a
+  // statistically faithful trajectory -> the synchronous-sublattice sampler, the mode that uses the GPU.  --parity /
+  // --parallel (or MSKC_MODE=parity|parallel) override; socket-driven runs and boxes that are not multiples of 48 stay serial.
+  auto pick_mode = [&]() {
+    if (mode < 0) { if (const char *e = getenv("MSKC_MODE")) mode = !strcmp(e, "parallel") ? 1 : (!strcmp(e, "parity") ? 0 : -1); }
+    if (exact_restart) mode = 0;                              // (the same trajectory: the serial loop)
+    if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
+    parallel = mode == 1; R.sampler = parallel;
+    // frames: the sampler's come from the device's extraction passes (a production box is 10^9 cells: no lattice download, no
+    // host scans); the serial loop keeps the whole-lattice writer its byte-for-byte tests were pinned with.  MSKC_DEVICE_FRAMES=1 / 0
+    // forces one or the other (the two writers produce identical files: tests/test_zzz_frames_gpu.py)
+    R.device_frames = parallel;
+    if (const char *e = getenv("MSKC_DEVICE_FRAMES")) R.device_frames = atoi(e) != 0;
+    R.crosscheck = getenv("MSKC_FRAME_CROSSCHECK") != nullptr;
+  };
   auto init_run = [&]() {
   read_start(H, start);
-  H.L.assign((size_t)H.LX * H.LY * (H.LZ + 1), 0);
+  pick_mode();
   H.Tree.assign((size_t)1 << H.Levels, 0.0);
+  // Sampler mode on a flat slab (InitSt F / FS, the production PVD / CVD start): the structure is built ON the device
+  // (mskc_init_flat: the geometry of initial/SetSiC3C.f / SetSi.f, checked word for word against the oracle's builders,
+  // tests/test_dense_gpu.py) and frame 0 comes from the device's frame passes -- no 4 B/cell lattice, no particle lists and no
+  // scan on the host, which at a 10^9-cell box is minutes of set-up and 8+ GB.  MSKC_HOST_BUILD=1 keeps the host builder.
+  if (parallel && !exact_restart && !dump_state && ((H.InitSt == "F" && H.NCrystal >= 2) || H.InitSt == "FS") && H.LX % 48 == 0 && H.LY % 48 == 0 && !getenv("MSKC_HOST_BUILD")) {
+    H.Len1 -= H.Len1 % 24;                                    // main.f:226,240
+    if (mskc_create(H.LX, H.LY, H.LZ, H.NCrystal, H.NCov, H.ListCrystal, H.ListCov, device, 0, &R.h) != 0) die(" %s", mskc_last_error(nullptr));
+    MS(mskc_set_rates(R.h, H.PE.data(), H.PD.data(), H.PA.data(), H.PS.data(), H.PtransZig));
+    MS(mskc_init_flat(R.h, H.Len1, H.InitSt == "FS" ? 1 : 0, H.InitSt == "F" ? 1 : 0));
+    mskc_counters c; MS(mskc_get_counters(R.h, &c));
+    int64_t nact = 0; MS(mskc_download_active(R.h, 0, nullptr, nullptr, nullptr, &nact));
+    R.NumAtoms = c.num_atoms; R.NumVoids = c.num_voids; R.NumAdAtom = (int)nact;
+    printf(" Atoms,Voids,AdAtoms %d %d %d\n", R.NumAtoms, R.NumVoids, R.NumAdAtom);
+    for (int i = 0; i < 3; i++) H.CountCrystalOld[i] = H.CountCrystal[i];
+    write_frame(H, R, 0.0, 0, 0, true);                       // main.f:297-300
+    by_time = H.ExitStrategy == "Time";
+    return;
+  }
+  H.L.assign((size_t)H.LX * H.LY * (H.LZ + 1), 0);
   // main.f:225-295
   if (H.la_tree && H.InitSt != "LA" && H.InitSt != "IN") die(" mulskips.e (B200 host): --la-tree (the LaserAnnealing fork) is built for InitSt LA and IN");
   CkptHeader ck{};
@@ -1576,21 +1614,7 @@ int main(int argc, char **argv) {
   };
   // ---- the KMC loop between two calls of the host (main.f:304-371) ----
   auto kmc_loop = [&]() {
-  // Which loop runs when the command line does not say (pymulskips launches `mulskips.e` without arguments): RunType 'T'
-  // ("not so random: use this for regression tests", py/setuprun.py:344) and 'C' ask for the reference's own event sequence
-  // -> serial parity mode, bit-exact; RunType 'R' ("truly random", the production default of pymulskips) asks for a
-  // statistically faithful trajectory -> the synchronous-sublattice sampler, the mode that uses the GPU.  --parity /
-  // --parallel (or MSKC_MODE=parity|parallel) override; socket-driven runs and boxes that are not multiples of 48 stay serial.
-  if (mode < 0) { if (const char *e = getenv("MSKC_MODE")) mode = !strcmp(e, "parallel") ? 1 : (!strcmp(e, "parity") ? 0 : -1); }
-  if (exact_restart) mode = 0;                                // (the same trajectory: the serial loop)
-  if (mode < 0) mode = (H.RunType == "R" && sock_port < 0 && !H.la_tree && H.LX % 48 == 0 && H.LY % 48 == 0) ? 1 : 0;
-  parallel = mode == 1; R.sampler = parallel;
-  // frames: the sampler's come from the device's extraction passes (a production box is 10^9 cells: no lattice download, no
-  // host scans); the serial loop keeps the whole-lattice writer its byte-for-byte tests were pinned with.  MSKC_DEVICE_FRAMES=1 / 0
-  // forces one or the other (the two writers produce identical files: tests/test_host_gpu.py)
-  R.device_frames = parallel;
-  if (const char *e = getenv("MSKC_DEVICE_FRAMES")) R.device_frames = atoi(e) != 0;
-  R.crosscheck = getenv("MSKC_FRAME_CROSSCHECK") != nullptr;
+  pick_mode();
   if (!parallel) {                                            // main.f:304-371, bit-exact replay on the device
     mskc_parity_args a{}; mskc_parity_result r{};
     a.max_iter = H.MaxIter; a.max_time = H.MaxTime; a.exit_on_time = by_time; a.out_every = H.OutMolMol; a.out_time = H.OutTime; a.event_budget = 0;
@@ -1665,7 +1689,7 @@ int main(int argc, char **argv) {
   // main.f:374-430: final frame, checkpoint, Coor
   auto finish_run = [&]() {
   write_frame(H, R, R.Time, R.IterOut, by_time ? R.framecounter : (H.OutMolMol > 0 ? R.IterOut / H.OutMolMol : 0), true);
-  if (R.lattice_stale && (H.SaveFinalState == "T" || H.SaveCoo == "T")) { MS(mskc_download_lattice(R.h, H.L.data())); R.lattice_stale = false; }   // the files below hold every cell
+  if (R.lattice_stale && (H.SaveFinalState == "T" || H.SaveCoo == "T")) { MS(mskc_download_lattice(R.h, host_lattice(H))); R.lattice_stale = false; }   // the files below hold every cell
   if (H.SaveFinalState == "T") {
     printf(" Writing checkpoint file for a restart run %s\n", H.restartfile.c_str());
     if (FILE *f = fopen(H.restartfile.c_str(), "w")) {

@@ -312,3 +312,24 @@ def test_bench_box_full_size_properties():
     assert int(np.count_nonzero((occ == 1) & (coor == 4) & (z <= big[2] - 1))) == c1.noepi_bulk
     assert np.all(np.diff(cells.astype(np.int64)) > 0)
     ctx.close()
+
+
+@pytest.mark.parametrize("case", ["surface", "Si-SL"])
+def test_device_built_start_frame0_is_reference_golden(built, tmp_path, case):
+    """Sampler mode on a flat slab (InitSt F / FS) builds the structure on the device (mskc_init_flat) and writes frame 0 from the
+    device's frame passes -- no lattice, no lists, no scan on the host.  With the reference's regression start files (RunType
+    switched to R) at 480^3 that frame is the reference's golden I00000000.xyz byte for byte and the list sizes are the
+    golden log's; MSKC_HOST_BUILD=1 (the host builder + upload) writes the same frame-0 files."""
+    m = MAN[case]
+    dirs = {}
+    for tag, env in (("dev", {}), ("host", {"MSKC_HOST_BUILD": "1"})):
+        d = tmp_path / tag
+        d.mkdir()
+        make_start(case, str(d / "start.dat"), maxiter=2000, outmolmol=2000, runtype="R")
+        _run_env(EXE, d, [], env)
+        assert "sublattice-sampler" in (d / "err.txt").read_text()
+        assert hashlib.sha256((d / "I00000000.xyz").read_bytes()).hexdigest() == m["frame0_sha256"], f"{case} ({tag}): frame 0 differs from the reference golden"
+        assert [int(v) for v in _tokens(d / "log.txt", "Atoms,Voids,AdAtoms")[1:4]] == m["init_lists"]
+        dirs[tag] = d
+    for name in sorted(p.name for p in dirs["host"].glob("I00000000*.xyz")):
+        assert (dirs["dev"] / name).read_bytes() == (dirs["host"] / name).read_bytes(), name
