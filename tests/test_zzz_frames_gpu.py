@@ -333,3 +333,36 @@ def test_device_built_start_frame0_is_reference_golden(built, tmp_path, case):
         dirs[tag] = d
     for name in sorted(p.name for p in dirs["host"].glob("I00000000*.xyz")):
         assert (dirs["dev"] / name).read_bytes() == (dirs["host"] / name).read_bytes(), name
+
+
+@pytest.mark.parametrize("kind", ["CVD-FS", "C2-F"])
+def test_init_flat_matches_oracle_with_coverage(tmp_path, kind):
+    """mskc_init_flat on tables WITH coverage species (the device-built start of the host program's sampler mode takes them too):
+    Si + H on the FS builder (start-CVD-Si-SiH2.dat) and BASELINE config 2, SiC + H on the F builder -- every lattice word and
+    the active set with (event class, rate bits) against the oracle's builders, as tests/test_dense_gpu.py does without coverage"""
+    from cases import make_sic_cvd_case
+    from mulskips_b200 import Mskc
+    from test_dense_gpu import active_dict
+    from test_replay_gpu import expected_active
+    box = (96, 96, 144)
+    if kind == "CVD-FS":
+        start = make_start("CVD-Si-SiH2", str(tmp_path / "start.dat"), lens=(48, 0, 0), maxiter=10**9, outmolmol=10**9, initst="FS")
+        walls, two, zig = True, False, 1.0
+    else:
+        start = make_sic_cvd_case(str(tmp_path), lens=(48, 0, 0))
+        walls, two, zig = False, True, 0.8
+    orc = Oracle(*box, start)
+    orc.setup()
+    lc, lv = orc.species()
+    assert len(lv) == 1
+    ctx = Mskc(*box, lc, lv)
+    t = orc.tables()
+    ctx.set_rates(t["PtransE"], t["PtransD"], t["PtransAbs"], t["PtransDes"], zig)
+    ctx.init_flat(48, walls=walls, two_species=two)
+    assert np.array_equal(ctx.download_lattice(), orc.lattcoo())
+    exp, _ = expected_active(orc)
+    got = active_dict(ctx)
+    assert set(got) == set(exp) and got == exp
+    c, s = ctx.counters(), orc.sizes()
+    assert (c.num_atoms, c.num_voids) == (s["NumAtoms"], s["NumVoids"])
+    ctx.close(); orc.close()
