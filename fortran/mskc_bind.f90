@@ -262,10 +262,10 @@ module mskc_bind
       type(c_ptr), value :: h, cell, word, n, kernel_ms
       integer(c_int64_t), value :: cap
     end function
-    integer(c_int) function mskc_extract_antisites(h, target, cap, cell, word, n, kernel_ms) bind(C, name="mskc_extract_antisites")
+    integer(c_int) function mskc_extract_antisites(h, nunlike, cap, cell, word, n, kernel_ms) bind(C, name="mskc_extract_antisites")
       import :: c_int, c_ptr, c_int64_t
       type(c_ptr), value :: h, cell, word, n, kernel_ms
-      integer(c_int), value :: target
+      integer(c_int), value :: nunlike     ! 0 or 3 (the C prototype calls it target)
       integer(c_int64_t), value :: cap
     end function
     integer(c_int) function mskc_gather_lattice(h, n, cell, word) bind(C, name="mskc_gather_lattice")
